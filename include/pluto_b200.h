@@ -1,0 +1,174 @@
+/* pluto_b200.h -- C ABI of libplutob200.so: the B200 (sm_100a) implementation of PLUTO's
+ * unsplit finite-volume HD update as built in the sirocco-coupled fork.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, no C++/torch types.  The reference has
+ * no FFI layer; its seam for this path is the link-time symbol set.  Each
+ * entry point below names the reference interface it stands in for.  INTEGRATION.md shows
+ * the shim (pluto_sirocco_b200/csrc/pluto_shim.c) that maps the reference's
+ * `int AdvanceStep(Data*, timeStep*, Grid*)` (Src/prototypes.h:5) onto these calls.
+ *
+ * All arrays are FP64.  Host-side state arrays use the reference layout of d->Vc:
+ * Vc[nvar][NX3_TOT][NX2_TOT][NX1_TOT], i fastest, ghost zones included
+ * (Src/arrays.c:251-330, Src/initialize.c:442).  Inactive dimensions have 1 zone, no ghosts.
+ *
+ * Error convention: functions return 0 on success, a negative PB200_E* code on failure
+ * (pb200_last_error() gives text).  Recoverable cons->prim failures are floored on the
+ * device exactly like Src/HD/mappers.c:139-218 and COUNTED (pb200_step_info.c2p_failures);
+ * a NaN in the state makes the step return PB200_ENAN (reference: CheckNaN -> QUIT_PLUTO,
+ * Src/Time_Stepping/update_stage.c:227).  There is no CPU fallback: without a CUDA device
+ * pb200_create() fails with PB200_ENODEV.
+ */
+#ifndef PLUTO_B200_H
+#define PLUTO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_VERSION 100
+
+/* GEOMETRY: same values as Src/pluto.h:34-37.  The other option codes below are this
+ * library's own; the shim translates the reference macros (pluto.h:66-70,254-287). */
+#define PB200_CARTESIAN 1   /* pluto.h: CARTESIAN   */
+#define PB200_SPHERICAL 4   /* pluto.h: SPHERICAL   */
+
+#define PB200_FLAT      1   /* RECONSTRUCTION FLAT      */
+#define PB200_LINEAR    2   /* RECONSTRUCTION LINEAR    (Src/States/plm_states.c)  */
+#define PB200_PARABOLIC 3   /* RECONSTRUCTION PARABOLIC (Src/States/ppm_states.c, PPM_ORDER 4) */
+
+#define PB200_EULER 1       /* TIME_STEPPING EULER */
+#define PB200_RK2   2       /* TIME_STEPPING RK2  (Src/Time_Stepping/rk_step.c) */
+#define PB200_RK3   3       /* TIME_STEPPING RK3 */
+
+#define PB200_TVDLF 1       /* Solver tvdlf  -> LF_Solver   (Src/HD/tvdlf.c:38) */
+#define PB200_HLL   2       /* Solver hll    -> HLL_Solver  (Src/HD/hll.c:30)   */
+#define PB200_HLLC  3       /* Solver hllc   -> HLLC_Solver (Src/HD/hllc.c:28)  */
+
+#define PB200_LIM_DEFAULT   0  /* LIMITER DEFAULT: MC rho, VL v, MM p (plm_states.c:202-244) */
+#define PB200_LIM_FLAT      1
+#define PB200_LIM_MINMOD    2
+#define PB200_LIM_VANLEER   3
+#define PB200_LIM_MC        4
+#define PB200_LIM_VANALBADA 5
+#define PB200_LIM_OSPRE     6
+#define PB200_LIM_UMIST     7
+
+/* boundary types: same values as Src/pluto.h:163-170 (OUTFLOW..USERDEF); PB200_BC_NEIGHBOUR = face owned by another
+ * rank of the slab decomposition (ghosts arrive by halo exchange, not by a fill) */
+#define PB200_BC_OUTFLOW      1
+#define PB200_BC_REFLECTIVE   2
+#define PB200_BC_AXISYMMETRIC 3
+#define PB200_BC_EQTSYMMETRIC 4
+#define PB200_BC_PERIODIC     5
+#define PB200_BC_USERDEF      8
+#define PB200_BC_NEIGHBOUR    100
+
+#define PB200_OK        0
+#define PB200_EINVAL   -1
+#define PB200_ENODEV   -2
+#define PB200_ECUDA    -3
+#define PB200_ENOMEM   -4
+#define PB200_ENAN     -5
+#define PB200_ENOTSUP  -6
+
+typedef struct pb200_ctx pb200_ctx;
+
+/* Compile-time (definitions.h) and run-time (pluto.ini) options of one block of the grid. */
+typedef struct pb200_config {
+  int dimensions;        /* DIMENSIONS 1|2|3 */
+  int geometry;          /* GEOMETRY */
+  int nx[3];             /* interior zones of THIS block: NX1, NX2, NX3 */
+  int nghost;            /* GetNghost(): 2 LINEAR, 3 PARABOLIC (Src/get_nghost.c:19) */
+  int ntracer;           /* NTRACER */
+  int reconstruction;    /* RECONSTRUCTION */
+  int limiter;           /* LIMITER */
+  int time_stepping;     /* TIME_STEPPING */
+  int solver;            /* [Solver] Solver, Src/HD/set_solver.c:4-58 */
+  int bc[6];             /* [Boundary] X1-beg, X1-end, X2-beg, ... */
+  double gamma;          /* g_gamma */
+  double small_density;  /* g_smallDensity  (Src/globals.h) */
+  double small_pressure; /* g_smallPressure */
+  double xbeg[3];        /* g_domBeg of this block */
+  double xend[3];        /* g_domEnd of this block */
+  int device;            /* CUDA device ordinal */
+  int reserved[7];
+} pb200_config;
+
+/* What one AdvanceStep leaves in timeStep / globals (Src/structs.h:372, globals.h). */
+typedef struct pb200_step_info {
+  double invDt_hyp;            /* Dts->invDt_hyp contribution of this step */
+  double maxMach;              /* g_maxMach contribution */
+  unsigned long long c2p_failures; /* zones floored by ConsToPrim */
+  float  gpu_ms;               /* device time of the step (CUDA events) */
+  int    launches;             /* kernels launched by the step */
+} pb200_step_info;
+
+const char *pb200_last_error(void);
+int  pb200_version(void);
+
+/* defaults matching Src/pluto.h / globals.h (g_gamma 5/3, small 1e-12, LIMITER DEFAULT) */
+void pb200_config_default(pb200_config *cfg);
+
+/* lifecycle: after Initialize() (Src/main.c:110) / before exit (Src/main.c:372) */
+int  pb200_create(const pb200_config *cfg, pb200_ctx **out);
+void pb200_destroy(pb200_ctx *ctx);
+
+/* total zones per direction incl. ghosts (NX1_TOT, NX2_TOT, NX3_TOT) and NVAR */
+int  pb200_shape(const pb200_ctx *ctx, int tot[3], int *nvar);
+
+/* grid->xl / grid->xr / grid->dx of direction dir (np_tot entries each; dx may be NULL ->
+ * xr-xl); default = uniform from xbeg/xend (Src/set_grid.c:405-412).  Needed before the
+ * first step only for non-uniform grids. */
+int  pb200_set_grid(pb200_ctx *ctx, int dir, const double *xl, const double *xr, const double *dx);
+
+/* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
+int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);
+int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);
+/* device pointer of the current d->Vc mirror (for torch / NCCL interop, zero copy) */
+double *pb200_device_vc(pb200_ctx *ctx);
+
+/* Boundary(d, 0, grid) on the device mirror (Src/boundary.c:56) */
+int  pb200_boundary(pb200_ctx *ctx);
+
+/* AdvanceStep(d, Dts, grid) with g_dt = dt  (Src/Time_Stepping/rk_step.c:29) on the
+ * device-resident state.  info may be NULL. */
+int  pb200_advance_step(pb200_ctx *ctx, double dt, pb200_step_info *info);
+
+/* Same call on HOST buffers (the strict drop-in: d->Vc is authoritative on the host):
+ * H2D of vc_host, AdvanceStep, D2H back into vc_host. */
+int  pb200_advance_step_host(pb200_ctx *ctx, double *vc_host, double dt, pb200_step_info *info);
+
+/* NextTimeStep() (Src/main.c:521-697) for COOLING NO, no parabolic terms.
+ * Returns the new g_dt, or a negative value if dt < first_dt*1e-9 ("dt is too small"). */
+double pb200_next_time_step(double invDt_hyp, double cfl, double cfl_max_var, double g_dt,
+                            double first_dt);
+
+/* main() loop body (Src/main.c:215-337) run nsteps times entirely from the device-resident
+ * state: clip g_dt to tstop, AdvanceStep, g_time += g_dt, g_dt = NextTimeStep.
+ * t and dt are in/out.  Returns the number of steps done (>=0) or a negative error. */
+int  pb200_integrate(pb200_ctx *ctx, int nsteps, double tstop, double cfl, double cfl_max_var,
+                     double first_dt, double *t, double *dt, pb200_step_info *last);
+
+/* slab decomposition (replaces Src/Parallel/al_exchange_dim.c): device pointers/sizes of
+ * the ghost and edge slabs of direction dir so the caller (NCCL send/recv) can move them.
+ * lo_ghost/lo_edge/hi_edge/hi_ghost are offsets (in doubles) into variable 0 of the device
+ * Vc of the array that the NEXT stage will sweep; count = doubles per variable slab;
+ * var_stride = doubles between variables. */
+int  pb200_halo_layout(const pb200_ctx *ctx, int dir, long *lo_ghost, long *lo_edge,
+                       long *hi_edge, long *hi_ghost, long *count, long *var_stride);
+
+/* Stage-level entry points for a caller that must act between stages (halo exchange,
+ * UserDefBoundary): begin -> [stage(s): exchange halos of pb200_stage_array(), then
+ * pb200_stage(s)] -> end.  pb200_advance_step == begin; for s in 1..nstages: stage(s); end. */
+int  pb200_step_begin(pb200_ctx *ctx, double dt);
+double *pb200_stage_array(pb200_ctx *ctx, int stage);  /* device Vc swept by stage s */
+int  pb200_stage(pb200_ctx *ctx, int stage);
+int  pb200_step_end(pb200_ctx *ctx, pb200_step_info *info);
+int  pb200_nstages(const pb200_ctx *ctx);
+/* CUDA stream (cudaStream_t as void*) all kernels of ctx are launched on */
+void *pb200_stream(pb200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

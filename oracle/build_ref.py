@@ -1,0 +1,159 @@
+#!/usr/bin/env python3
+"""Build the UNMODIFIED reference (PLUTO 4.4-patch3 + sirocco fork) for the hot-path
+configurations, straight from the sources where they lie under /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported, linked or executed by the
+product path (pluto_sirocco_b200/); only tests/, __graft_entry__.smoke() and bench.py's
+CPU legs may use it, and only as the checker / the CPU baseline.
+
+This is our own recipe (plain gcc on an explicit source list) - the reference's
+setup.py / curses menu / generated makefile are not run.  The source list mirrors what
+Tools/Python/define_problem.py:533-711 + Src/Templates/makefile + Src/HD/makefile +
+Src/EOS/Ideal/makefile would select for PHYSICS=HD on a static grid.  The only files
+written are under oracle/_ref/<config>/ (git-ignored; they DO travel to the GPU box):
+  definitions.h   problem header = the reference's own definitions_NN.h with the
+                  overrides listed in CONFIGS (e.g. RECONSTRUCTION PARABOLIC)
+  obj/*.o, pluto  the reference executable for that definitions.h
+No reference source is copied into the repository.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import os
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF = Path(os.environ.get("PLUTO_DIR", "/root/reference"))
+OUT = HERE / "_ref"
+
+# Flags of Config/Linux.gcc.defs:8-9 (the serial gcc configuration of the reference).
+CFLAGS = ["-c", "-O3", "-std=c17"]
+LDFLAGS = ["-lm"]
+
+# Src/Templates/makefile OBJ lists (static grid, serial).
+CORE = """adv_flux arrays array_reconstruct boundary check_states cmd_line_opt debug_tools
+entropy_switch failsafe flag_shock flatten fluid_interface_boundary get_nghost
+int_bound_reset input_data mappers3D mean_mol_weight parse_file plm_coeffs rbox
+reconstruct rotate set_indexes set_geometry set_output tools var_names
+bin_io colortable initialize jet_domain main output_log restart ring_average
+runtime_setup set_image show_config set_grid startup split_source
+write_data write_tab write_img write_vtk write_vtk_proc""".split()
+MATH = """math_interp math_lu_decomp math_qr_decomp math_misc math_ode math_quadrature
+math_random math_root_finders math_table2D""".split()
+HD = """advection_solver ausm eigenv fluxes mappers mappers_loc hll_speed hll hllc
+set_solver tvdlf two_shock roe prim_eqn rhs rhs_source""".split()
+EOS_IDEAL = ["eos"]
+RK = ["rk_step", "update_stage"]
+
+# search path for sources, in make-VPATH order (problem directory first)
+def vpath(problem_dir: Path, extra: list[str]) -> list[Path]:
+    s = REF / "Src"
+    return [problem_dir, s, s / "Math_Tools", s / "HD", s / "MHD", s / "EOS" / "Ideal",
+            s / "States", s / "Time_Stepping"] + [s / e for e in extra]
+
+
+CONFIGS = {
+    # C1: Sod tube, PLM + RK2 (solver chosen in pluto.ini)  Test_Problems/HD/Sod conf 01
+    "sod": dict(problem="HD/Sod", defs="definitions_01.h", overrides={}, states="plm"),
+    # same problem with PPM + RK3
+    "sod_ppm": dict(problem="HD/Sod", defs="definitions_01.h",
+                    overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"},
+                    states="ppm"),
+    # C2: Sedov 3-D Cartesian PLM + RK2   Test_Problems/HD/Sedov conf 05
+    "sedov3d": dict(problem="HD/Sedov", defs="definitions_05.h", overrides={}, states="plm"),
+    # C5: Sedov 3-D PPM + RK3
+    "sedov3d_ppm": dict(problem="HD/Sedov", defs="definitions_05.h",
+                        overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"},
+                        states="ppm"),
+    # Sedov 2-D Cartesian PLM + RK2   (conf 05 with DIMENSIONS 2)
+    "sedov2d": dict(problem="HD/Sedov", defs="definitions_05.h", overrides={"DIMENSIONS": "2"},
+                    states="plm"),
+    # C3: Rayleigh-Taylor, PHYSICS HD, BODY_FORCE POTENTIAL, 2-D and 3-D
+    "rt2d": dict(problem="MHD/Rayleigh_Taylor", defs="definitions_04.h", overrides={},
+                 states="plm"),
+    "rt3d": dict(problem="MHD/Rayleigh_Taylor", defs="definitions_04.h",
+                 overrides={"DIMENSIONS": "3"}, states="plm"),
+}
+
+
+def patch_definitions(text: str, overrides: dict[str, str]) -> str:
+    for key, val in overrides.items():
+        pat = re.compile(r"^(#define\s+%s\s+)\S+" % re.escape(key), re.M)
+        if pat.search(text):
+            text = pat.sub(lambda m: m.group(1) + val, text)
+        else:
+            text = "#define  %s  %s\n" % (key, val) + text
+    return text
+
+
+def find_source(name: str, paths: list[Path]) -> Path:
+    for p in paths:
+        f = p / (name + ".c")
+        if f.exists():
+            return f
+    raise FileNotFoundError(name)
+
+
+def build(cfg_name: str, force: bool = False, verbose: bool = False) -> Path:
+    cfg = CONFIGS[cfg_name]
+    problem_dir = REF / "Test_Problems" / cfg["problem"]
+    wd = OUT / cfg_name
+    exe = wd / "pluto"
+    if exe.exists() and not force:
+        return exe
+    if not REF.exists():
+        raise RuntimeError("reference tree %s not present; cannot build oracle/_ref" % REF)
+    (wd / "obj").mkdir(parents=True, exist_ok=True)
+    defs = patch_definitions((problem_dir / cfg["defs"]).read_text(), cfg["overrides"])
+    (wd / "definitions.h").write_text(defs)
+
+    extra = cfg.get("extra_vpath", [])
+    paths = vpath(problem_dir, extra)
+    names = CORE + MATH + HD + EOS_IDEAL + RK + ["init"]
+    names += ["plm_states"] if cfg["states"] == "plm" else ["ppm_states", "ppm_coeffs"]
+    names += cfg.get("extra_objs", [])
+    if not (problem_dir / "userdef_output.c").exists():
+        names.append("userdef_output")   # Src/userdef_output.c template
+    else:
+        names.append("userdef_output")
+    s = REF / "Src"
+    incs = ["-I%s" % wd, "-I%s" % s, "-I%s" % (s / "HD"), "-I%s" % (s / "EOS" / "Ideal"),
+            "-I%s" % (s / "States"), "-I%s" % (s / "Math_Tools")]
+    incs += ["-I%s" % (s / e) for e in extra]
+
+    def cc(name: str):
+        src = find_source(name, paths)
+        obj = wd / "obj" / (name + ".o")
+        cmd = ["gcc"] + CFLAGS + incs + [str(src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("gcc failed for %s:\n%s" % (src, r.stderr[-4000:]))
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(cc, names))
+    r = subprocess.run(["gcc"] + [str(o) for o in objs] + LDFLAGS + ["-o", str(exe)],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    if verbose:
+        print("built", exe)
+    return exe
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=list(CONFIGS))
+    ap.add_argument("--force", action="store_true")
+    a = ap.parse_args()
+    for c in a.configs:
+        build(c, force=a.force, verbose=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI in include/pluto_b200.h.  No fallback: if the CUDA library
+is missing or cannot be loaded this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libplutob200.so"
+
+# option codes (include/pluto_b200.h)
+CARTESIAN, SPHERICAL = 1, 4
+FLAT, LINEAR, PARABOLIC = 1, 2, 3
+EULER, RK2, RK3 = 1, 2, 3
+TVDLF, HLL, HLLC = 1, 2, 3
+LIMITERS = dict(DEFAULT=0, FLAT_LIM=1, MINMOD_LIM=2, VANLEER_LIM=3, MC_LIM=4, VANALBADA_LIM=5,
+                OSPRE_LIM=6, UMIST_LIM=7)
+BC = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8,
+          neighbour=100)
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, ENAN, ENOTSUP = 0, -1, -2, -3, -4, -5, -6
+
+
+class Config(C.Structure):
+    _fields_ = [("dimensions", C.c_int), ("geometry", C.c_int), ("nx", C.c_int * 3),
+                ("nghost", C.c_int), ("ntracer", C.c_int), ("reconstruction", C.c_int),
+                ("limiter", C.c_int), ("time_stepping", C.c_int), ("solver", C.c_int),
+                ("bc", C.c_int * 6), ("gamma", C.c_double), ("small_density", C.c_double),
+                ("small_pressure", C.c_double), ("xbeg", C.c_double * 3),
+                ("xend", C.c_double * 3), ("device", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("invDt_hyp", C.c_double), ("maxMach", C.c_double),
+                ("c2p_failures", C.c_ulonglong), ("gpu_ms", C.c_float), ("launches", C.c_int)]
+
+
+# every symbol include/pluto_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_D = C.c_double
+_PD = C.POINTER(C.c_double)
+_PL = C.POINTER(C.c_long)
+SYMBOLS = {
+    "pb200_last_error": (C.c_char_p, []),
+    "pb200_version": (C.c_int, []),
+    "pb200_config_default": (None, [C.POINTER(Config)]),
+    "pb200_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "pb200_destroy": (None, [_P]),
+    "pb200_shape": (C.c_int, [_P, C.POINTER(C.c_int * 3), C.POINTER(C.c_int)]),
+    "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pb200_upload_vc": (C.c_int, [_P, _P]),
+    "pb200_download_vc": (C.c_int, [_P, _P]),
+    "pb200_device_vc": (_P, [_P]),
+    "pb200_boundary": (C.c_int, [_P]),
+    "pb200_advance_step": (C.c_int, [_P, _D, C.POINTER(StepInfo)]),
+    "pb200_advance_step_host": (C.c_int, [_P, _P, _D, C.POINTER(StepInfo)]),
+    "pb200_next_time_step": (_D, [_D, _D, _D, _D, _D]),
+    "pb200_integrate": (C.c_int, [_P, C.c_int, _D, _D, _D, _D, _PD, _PD, C.POINTER(StepInfo)]),
+    "pb200_halo_layout": (C.c_int, [_P, C.c_int, _PL, _PL, _PL, _PL, _PL, _PL]),
+    "pb200_step_begin": (C.c_int, [_P, _D]),
+    "pb200_stage_array": (_P, [_P, C.c_int]),
+    "pb200_stage": (C.c_int, [_P, C.c_int]),
+    "pb200_step_end": (C.c_int, [_P, C.POINTER(StepInfo)]),
+    "pb200_nstages": (C.c_int, [_P]),
+    "pb200_stream": (_P, [_P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libplutob200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            "%s not built: run `python -m pluto_sirocco_b200.build` (there is no CPU fallback)"
+            % LIB_PATH)
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)     # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class PB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def check(rc: int):
+    if rc < 0:
+        raise PB200Error(rc, load().pb200_last_error().decode())
+    return rc

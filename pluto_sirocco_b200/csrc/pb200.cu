@@ -1,0 +1,479 @@
+// pb200.cu -- C ABI (include/pluto_b200.h) and stage sequencing of AdvanceStep().
+//
+// Host-side restatement of the control flow of Src/Time_Stepping/rk_step.c:29-322:
+//   stage s:  Boundary(V_s)  ->  directional sweeps (x1 [, x2 [, x3]])  ->  V_{s+1}
+// with the RK weights of rk_step.c:18-24 / :304.  All state stays in HBM between calls.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pluto_b200.h"
+#include "pb200_kernels.cuh"
+
+using namespace pb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(PB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+struct pb200_ctx {
+  pb200_config cfg;
+  Dev dev;
+  int nvar;
+  long nzone;        // zones incl. ghosts
+  size_t vbytes;     // bytes of one [nvar] state array
+  double *V[3];      // primitive state copies (A = current d->Vc, B, C)
+  double *acc;       // conservative accumulator (DIMENSIONS > 1)
+  double *cdt;       // C_dt
+  double *d_dt;      // device g_dt
+  unsigned long long *d_red;   // reduction cell: invDt bits, maxMach bits, #fail, NaN flag
+  unsigned long long *h_red;   // pinned
+  double *h_dt;                // pinned
+  double *d_invdx[3];
+  std::vector<double> xl[3], xr[3], dx[3];
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  int launches;
+  int cur;           // index of the array holding d->Vc
+  int nstages;
+  int stage_in[4], stage_out[4];  // array indices per stage (1-based)
+  bool in_step;
+};
+
+extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
+extern "C" int pb200_version(void) { return PB200_VERSION; }
+
+extern "C" void pb200_config_default(pb200_config *c) {
+  memset(c, 0, sizeof(*c));
+  c->dimensions = 1;
+  c->geometry = PB200_CARTESIAN;
+  c->nx[0] = c->nx[1] = c->nx[2] = 1;
+  c->nghost = 2;
+  c->reconstruction = PB200_LINEAR;
+  c->limiter = PB200_LIM_DEFAULT;
+  c->time_stepping = PB200_RK2;
+  c->solver = PB200_HLLC;
+  for (int s = 0; s < 6; s++) c->bc[s] = PB200_BC_OUTFLOW;
+  c->gamma = 5.0 / 3.0;
+  c->small_density = 1.e-12;
+  c->small_pressure = 1.e-12;
+  for (int d = 0; d < 3; d++) { c->xbeg[d] = 0.0; c->xend[d] = 1.0; }
+}
+
+static int upload_grid(pb200_ctx *c, int dir) {
+  int n = c->dev.tot[dir];
+  std::vector<double> inv(n);
+  for (int i = 0; i < n; i++) inv[i] = 1.0 / c->dx[dir][i];  // grid->inv_dx
+  CK(cudaMemcpy(c->d_invdx[dir], inv.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  return PB200_OK;
+}
+
+extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
+  if (!cfg || !out) return fail(PB200_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->dimensions < 1 || cfg->dimensions > 3) return fail(PB200_EINVAL, "dimensions must be 1..3");
+  if (cfg->geometry != PB200_CARTESIAN) return fail(PB200_ENOTSUP, "geometry: only CARTESIAN is built");
+  if (cfg->ntracer != 0) return fail(PB200_ENOTSUP, "ntracer > 0 not built yet");
+  if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
+    return fail(PB200_EINVAL, "bad reconstruction");
+  if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_HLLC) return fail(PB200_EINVAL, "bad solver");
+  if (cfg->time_stepping < PB200_EULER || cfg->time_stepping > PB200_RK3)
+    return fail(PB200_EINVAL, "bad time_stepping");
+  int need = cfg->reconstruction == PB200_PARABOLIC ? 3 : 2;
+  if (cfg->nghost < need) return fail(PB200_EINVAL, "nghost too small for the reconstruction stencil");
+  for (int d = 0; d < cfg->dimensions; d++)
+    if (cfg->nx[d] < cfg->nghost) return fail(PB200_EINVAL, "nx < nghost in an active dimension");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PB200_ENODEV, "no CUDA device: libplutob200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PB200_EINVAL, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+
+  pb200_ctx *c = new pb200_ctx();
+  c->cfg = *cfg;
+  c->nvar = 5 + cfg->ntracer;
+  Dev &D = c->dev;
+  D.ndim = cfg->dimensions;
+  for (int d = 0; d < 3; d++) {
+    bool act = d < cfg->dimensions;
+    int ng = act ? cfg->nghost : 0;
+    int nx = act ? cfg->nx[d] : 1;
+    D.tot[d] = nx + 2 * ng;
+    D.beg[d] = ng;
+    D.end[d] = ng + nx - 1;
+  }
+  D.sj = D.tot[0];
+  D.sk = (long)D.tot[0] * D.tot[1];
+  D.sv = D.sk * D.tot[2];
+  c->nzone = D.sv;
+  c->vbytes = (size_t)c->nvar * c->nzone * sizeof(double);
+  D.gas.gamma = cfg->gamma;
+  D.gas.gmm1 = cfg->gamma - 1.0;
+  D.gas.inv_gmm1 = 1.0 / (cfg->gamma - 1.0);
+  D.gas.small_dn = cfg->small_density;
+  D.gas.small_pr = cfg->small_pressure;
+
+  c->nstages = cfg->time_stepping == PB200_EULER ? 1 : (cfg->time_stepping == PB200_RK2 ? 2 : 3);
+  int ncopies = c->nstages == 3 ? 3 : 2;
+  for (int k = 0; k < 3; k++) c->V[k] = nullptr;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < ncopies && e == cudaSuccess; k++) {
+    e = cudaMalloc(&c->V[k], c->vbytes);
+    if (e == cudaSuccess) e = cudaMemset(c->V[k], 0, c->vbytes);
+  }
+  c->acc = nullptr;
+  c->cdt = nullptr;
+  if (e == cudaSuccess && D.ndim > 1) {
+    e = cudaMalloc(&c->acc, c->vbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->cdt, c->nzone * sizeof(double));
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_dt, sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_red, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&c->h_red, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&c->h_dt, sizeof(double));
+  for (int d = 0; d < 3 && e == cudaSuccess; d++) e = cudaMalloc(&c->d_invdx[d], D.tot[d] * sizeof(double));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+  if (e != cudaSuccess) {
+    std::string m = std::string("allocation failed: ") + cudaGetErrorString(e);
+    pb200_destroy(c);
+    return fail(e == cudaErrorMemoryAllocation ? PB200_ENOMEM : PB200_ECUDA, m);
+  }
+  // uniform grid from xbeg/xend, ghost zones continue the spacing (Src/set_grid.c)
+  for (int d = 0; d < 3; d++) {
+    int n = D.tot[d];
+    c->xl[d].resize(n);
+    c->xr[d].resize(n);
+    c->dx[d].resize(n);
+    int nx = D.end[d] - D.beg[d] + 1;
+    double dx = (cfg->xend[d] - cfg->xbeg[d]) / nx;
+    for (int i = 0; i < n; i++) {
+      c->xl[d][i] = cfg->xbeg[d] + (i - D.beg[d]) * dx;
+      c->xr[d][i] = cfg->xbeg[d] + (i - D.beg[d] + 1) * dx;
+      c->dx[d][i] = dx;  // Src/set_grid.c:410
+    }
+    int rc = upload_grid(c, d);
+    if (rc) { pb200_destroy(c); return rc; }
+    D.inv_dx[d] = c->d_invdx[d];
+  }
+  c->cur = 0;
+  c->in_step = false;
+  c->launches = 0;
+  *out = c;
+  return PB200_OK;
+}
+
+extern "C" void pb200_destroy(pb200_ctx *c) {
+  if (!c) return;
+  for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
+  if (c->acc) cudaFree(c->acc);
+  if (c->cdt) cudaFree(c->cdt);
+  if (c->d_dt) cudaFree(c->d_dt);
+  if (c->d_red) cudaFree(c->d_red);
+  if (c->h_red) cudaFreeHost(c->h_red);
+  if (c->h_dt) cudaFreeHost(c->h_dt);
+  for (int d = 0; d < 3; d++) if (c->d_invdx[d]) cudaFree(c->d_invdx[d]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+extern "C" int pb200_shape(const pb200_ctx *c, int tot[3], int *nvar) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  if (tot) for (int d = 0; d < 3; d++) tot[d] = c->dev.tot[d];
+  if (nvar) *nvar = c->nvar;
+  return PB200_OK;
+}
+
+extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const double *xr, const double *dx) {
+  if (!c || dir < 0 || dir > 2 || !xl || !xr) return fail(PB200_EINVAL, "bad argument");
+  int n = c->dev.tot[dir];
+  for (int i = 0; i < n; i++) {
+    if (!(xr[i] > xl[i])) return fail(PB200_EINVAL, "grid: xr <= xl");
+    c->xl[dir][i] = xl[i];
+    c->xr[dir][i] = xr[i];
+    c->dx[dir][i] = dx ? dx[i] : xr[i] - xl[i];
+  }
+  CK(cudaSetDevice(c->cfg.device));
+  return upload_grid(c, dir);
+}
+
+extern "C" int pb200_upload_vc(pb200_ctx *c, const double *h) {
+  if (!c || !h) return fail(PB200_EINVAL, "null argument");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpyAsync(c->V[c->cur], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+extern "C" int pb200_download_vc(pb200_ctx *c, double *h) {
+  if (!c || !h) return fail(PB200_EINVAL, "null argument");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpyAsync(h, c->V[c->cur], c->vbytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+extern "C" double *pb200_device_vc(pb200_ctx *c) { return c ? c->V[c->cur] : nullptr; }
+extern "C" void *pb200_stream(pb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int pb200_nstages(const pb200_ctx *c) { return c ? c->nstages : 0; }
+
+// ---- Boundary() ------------------------------------------------------------------------
+static int boundary_on(pb200_ctx *c, double *V) {
+  const Dev &D = c->dev;
+  for (int side = 0; side < 2 * D.ndim; side++) {
+    int type = c->cfg.bc[side];
+    if (type == PB200_BC_NEIGHBOUR || type == PB200_BC_USERDEF || type == 0) continue;
+    BcArgs b;
+    b.V = V;
+    b.side = side;
+    b.type = type;
+    b.nvar = c->nvar;
+    b.nghost = c->cfg.nghost;
+    for (int nv = 0; nv < 16; nv++) b.sign[nv] = 1.0;
+    b.sign[1 + side / 2] = -1.0;  // FlipSign(): normal velocity (Src/boundary.c:503)
+    int ext[3] = {D.tot[0], D.tot[1], D.tot[2]};
+    ext[side / 2] = b.nghost;
+    long n = (long)ext[0] * ext[1] * ext[2];
+    int nb = (int)((n + 255) / 256);
+    bc_fill<<<nb, 256, 0, c->stream>>>(D, b);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return PB200_OK;
+}
+
+extern "C" int pb200_boundary(pb200_ctx *c) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->cfg.device));
+  int rc = boundary_on(c, c->V[c->cur]);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+
+// ---- sweeps ------------------------------------------------------------------------------
+template <int NV, int RECON, int SOLVER>
+static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
+  const Dev &D = c->dev;
+  int nx = D.end[0] - D.beg[0] + 1;
+  if (dir == 0) {
+    constexpr int LO = (RECON == RECON_PARABOLIC) ? 2 : 1;
+    constexpr int USE = BX - 1 - LO;
+    dim3 grid((nx + USE - 1) / USE, D.end[1] - D.beg[1] + 1, D.end[2] - D.beg[2] + 1);
+    sweep_x1<NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a);
+  } else {
+    int npen = D.end[dir] - D.beg[dir] + 1;
+    int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
+    int nbx = (nx + BX - 1) / BX;
+    // chunk the pencil so that the grid holds at least ~8 waves of 148 SMs x 8 blocks
+    long want = 148L * 8 * 8;
+    int nchunk = 1;
+    while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
+    int chunk = (npen + nchunk - 1) / nchunk;
+    nchunk = (npen + chunk - 1) / chunk;
+    dim3 grid(nbx, ntr, nchunk);
+    if (dir == 1) sweep_march<1, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
+    else sweep_march<2, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
+  }
+  c->launches++;
+}
+
+template <int NV, int RECON>
+static void launch_solver(pb200_ctx *c, int dir, const SweepArgs &a) {
+  switch (c->cfg.solver) {
+    case PB200_TVDLF: launch_dir<NV, RECON, SOLVER_TVDLF>(c, dir, a); break;
+    case PB200_HLL: launch_dir<NV, RECON, SOLVER_HLL>(c, dir, a); break;
+    default: launch_dir<NV, RECON, SOLVER_HLLC>(c, dir, a); break;
+  }
+}
+
+static void launch_sweep(pb200_ctx *c, int dir, const SweepArgs &a) {
+  switch (c->cfg.reconstruction) {
+    case PB200_FLAT: launch_solver<5, RECON_FLAT>(c, dir, a); break;
+    case PB200_PARABOLIC: launch_solver<5, RECON_PARABOLIC>(c, dir, a); break;
+    default: launch_solver<5, RECON_LINEAR>(c, dir, a); break;
+  }
+}
+
+// NaN screen of the array about to be swept is folded into the reduction cell by a tiny
+// kernel over the dt-reduction result instead of a full pass: a NaN anywhere propagates to
+// cmax of its faces, and fmax() drops NaNs, so test invDt/maxMach via the c2p counter.
+__global__ void reset_red(unsigned long long *red, double *dt, double dtval) {
+  red[0] = 0ull;
+  red[1] = 0ull;
+  red[2] = 0ull;
+  red[3] = 0ull;
+  *dt = dtval;
+}
+
+extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  if (!(dt > 0.0)) return fail(PB200_EINVAL, "dt must be > 0");
+  CK(cudaSetDevice(c->cfg.device));
+  c->launches = 0;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  reset_red<<<1, 1, 0, c->stream>>>(c->d_red, c->d_dt, dt);
+  c->launches++;
+  // array rotation: stage s sweeps stage_in[s] and writes stage_out[s]
+  int A = c->cur, B = (c->cur + 1) % (c->nstages == 3 ? 3 : 2), C = (c->cur + 2) % 3;
+  if (c->nstages == 1) { c->stage_in[1] = A; c->stage_out[1] = B; }
+  else if (c->nstages == 2) { c->stage_in[1] = A; c->stage_out[1] = B; c->stage_in[2] = B; c->stage_out[2] = A; }
+  else { c->stage_in[1] = A; c->stage_out[1] = B; c->stage_in[2] = B; c->stage_out[2] = C;
+         c->stage_in[3] = C; c->stage_out[3] = A; }
+  c->in_step = true;
+  return PB200_OK;
+}
+
+extern "C" double *pb200_stage_array(pb200_ctx *c, int stage) {
+  if (!c || stage < 1 || stage > c->nstages) return nullptr;
+  return c->V[c->stage_in[stage]];
+}
+
+extern "C" int pb200_stage(pb200_ctx *c, int stage) {
+  if (!c || !c->in_step) return fail(PB200_EINVAL, "pb200_stage outside begin/end");
+  if (stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad stage");
+  const Dev &D = c->dev;
+  double *Vin = c->V[c->stage_in[stage]];
+  int rc = boundary_on(c, Vin);  // Boundary(d, 0, grid), rk_step.c:121,213,285
+  if (rc) return rc;
+  SweepArgs a;
+  a.V = Vin;
+  a.V0 = c->V[c->cur];
+  a.acc = c->acc;
+  a.Vout = c->V[c->stage_out[stage]];
+  a.cdt = c->cdt;
+  a.dt = c->d_dt;
+  a.red = c->d_red;
+  a.stage = stage;
+  a.limiter = c->cfg.limiter;
+  a.comb = 0; a.w0 = 0.0; a.wc = 1.0;
+  if (stage == 2) {  // rk_step.c:18-24
+    a.comb = 1;
+    if (c->nstages == 2) { a.w0 = 0.5; a.wc = 0.5; } else { a.w0 = 0.75; a.wc = 0.25; }
+  } else if (stage == 3) {
+    a.comb = 2;
+  }
+  for (int dir = 0; dir < D.ndim; dir++) {
+    a.first = (dir == 0);
+    a.last = (dir == D.ndim - 1);
+    launch_sweep(c, dir, a);
+  }
+  CK(cudaGetLastError());
+  return PB200_OK;
+}
+
+extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {
+  if (!c || !c->in_step) return fail(PB200_EINVAL, "pb200_step_end outside a step");
+  c->in_step = false;
+  if (c->nstages == 1) c->cur = c->stage_out[1];  // EULER: result lives in the other array
+  CK(cudaMemcpyAsync(c->h_red, c->d_red, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  double invdt, mach;
+  memcpy(&invdt, &c->h_red[0], 8);
+  memcpy(&mach, &c->h_red[1], 8);
+  if (c->dev.ndim > 1) invdt /= (double)c->dev.ndim;  // update_stage.c:392
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (info) {
+    info->invDt_hyp = invdt;
+    info->maxMach = mach;
+    info->c2p_failures = c->h_red[2];
+    info->gpu_ms = ms;
+    info->launches = c->launches;
+  }
+  if (!(invdt > 0.0) || !isfinite(invdt))
+    return fail(PB200_ENAN, "non-finite or zero signal speed: NaN in the state (CheckNaN)");
+  return PB200_OK;
+}
+
+extern "C" int pb200_advance_step(pb200_ctx *c, double dt, pb200_step_info *info) {
+  int rc = pb200_step_begin(c, dt);
+  if (rc) return rc;
+  for (int s = 1; s <= c->nstages; s++) {
+    rc = pb200_stage(c, s);
+    if (rc) { c->in_step = false; return rc; }
+  }
+  return pb200_step_end(c, info);
+}
+
+extern "C" int pb200_advance_step_host(pb200_ctx *c, double *vc_host, double dt, pb200_step_info *info) {
+  if (!c || !vc_host) return fail(PB200_EINVAL, "null argument");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaMemcpyAsync(c->V[c->cur], vc_host, c->vbytes, cudaMemcpyHostToDevice, c->stream));
+  int rc = pb200_advance_step(c, dt, info);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(vc_host, c->V[c->cur], c->vbytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+
+extern "C" double pb200_next_time_step(double invDt_hyp, double cfl, double cfl_max_var, double g_dt,
+                                       double first_dt) {
+  // Src/main.c:601-697 with COOLING NO, PARABOLIC_FLUX NO, no particles
+  double dt_hyp = 1.0 / invDt_hyp;
+  dt_hyp *= cfl;
+  double dtnext = dt_hyp;
+  double lim = cfl_max_var * g_dt;
+  dtnext = dtnext <= lim ? dtnext : lim;
+  if (dtnext < first_dt * 1.e-9) return -1.0;
+  if (cfl_max_var == 1.0) return g_dt;
+  return dtnext;
+}
+
+extern "C" int pb200_integrate(pb200_ctx *c, int nsteps, double tstop, double cfl, double cfl_max_var,
+                               double first_dt, double *t, double *dt, pb200_step_info *last) {
+  if (!c || !t || !dt) return fail(PB200_EINVAL, "null argument");
+  int done = 0;
+  pb200_step_info info;
+  memset(&info, 0, sizeof(info));
+  for (int n = 0; n < nsteps; n++) {
+    bool last_step = false;
+    if ((*t + *dt) >= tstop * (1.0 - 1.e-8)) {  // Src/main.c:227-230
+      *dt = tstop - *t;
+      last_step = true;
+    }
+    int rc = pb200_advance_step(c, *dt, &info);
+    if (rc) return rc;
+    *t += *dt;
+    double nd = pb200_next_time_step(info.invDt_hyp, cfl, cfl_max_var, *dt, first_dt);
+    if (nd < 0.0) return fail(PB200_EINVAL, "NextTimeStep(): dt is too small");
+    *dt = nd;
+    done++;
+    if (last_step) break;
+  }
+  if (last) *last = info;
+  return done;
+}
+
+extern "C" int pb200_halo_layout(const pb200_ctx *c, int dir, long *lo_ghost, long *lo_edge,
+                                 long *hi_edge, long *hi_ghost, long *count, long *var_stride) {
+  if (!c || dir < 0 || dir >= c->dev.ndim) return fail(PB200_EINVAL, "bad argument");
+  if (dir != c->dev.ndim - 1)
+    return fail(PB200_ENOTSUP, "slab split is along the outermost active direction only (contiguous planes)");
+  const Dev &D = c->dev;
+  long plane = (dir == 2) ? D.sk : (dir == 1 ? D.sj : 1);
+  int ng = c->cfg.nghost;
+  if (lo_ghost) *lo_ghost = 0;
+  if (lo_edge) *lo_edge = (long)D.beg[dir] * plane;
+  if (hi_edge) *hi_edge = (long)(D.end[dir] - ng + 1) * plane;
+  if (hi_ghost) *hi_ghost = (long)(D.end[dir] + 1) * plane;
+  if (count) *count = (long)ng * plane;
+  if (var_stride) *var_stride = D.sv;
+  return PB200_OK;
+}

@@ -1,0 +1,364 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+Names follow the reference: `Runtime` (Src/structs.h:434, filled from pluto.ini by
+Src/runtime_setup.c:67-507), `Definitions` (the problem's definitions.h), `Grid`
+(Src/structs.h:133), `Data.Vc` (Src/structs.h:525), `AdvanceStep` (rk_step.c:29),
+`NextTimeStep` / `Integrate` / the main loop (Src/main.c:215-337,383,521).
+
+Everything numerical happens in libplutob200.so (CUDA, sm_100a) through the C ABI of
+include/pluto_b200.h; this module only parses the reference's input files, owns the host
+copy of Vc and sequences calls.  It has no CPU implementation of the update.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib as L
+
+NVAR_HD = 5
+RHO, VX1, VX2, VX3, PRS = 0, 1, 2, 3, 4
+
+_SOLVERS = {"tvdlf": L.TVDLF, "hll": L.HLL, "hllc": L.HLLC}
+_RECON = {"FLAT": L.FLAT, "LINEAR": L.LINEAR, "PARABOLIC": L.PARABOLIC}
+_TSTEP = {"EULER": L.EULER, "RK2": L.RK2, "RK3": L.RK3}
+
+
+# --------------------------------------------------------------------------------------
+#  definitions.h / pluto.ini  (the unchanged user surface)
+# --------------------------------------------------------------------------------------
+@dataclass
+class Definitions:
+    """Compile-time options of a problem (definitions.h)."""
+    PHYSICS: str = "HD"
+    DIMENSIONS: int = 1
+    GEOMETRY: str = "CARTESIAN"
+    BODY_FORCE: str = "NO"
+    COOLING: str = "NO"
+    RECONSTRUCTION: str = "LINEAR"
+    TIME_STEPPING: str = "RK2"
+    NTRACER: int = 0
+    EOS: str = "IDEAL"
+    ENTROPY_SWITCH: str = "NO"
+    LIMITER: str = "DEFAULT"
+    user_params: list = field(default_factory=list)   # labels, in index order
+    extra: dict = field(default_factory=dict)
+
+    @classmethod
+    def parse(cls, path_or_text) -> "Definitions":
+        text = Path(path_or_text).read_text() if "\n" not in str(path_or_text) else str(path_or_text)
+        d = cls()
+        in_user = False
+        for line in text.splitlines():
+            if "user-defined parameters (labels)" in line:
+                in_user = True
+                continue
+            if "[Beg] user-defined constants" in line:
+                in_user = False
+            m = re.match(r"\s*#define\s+(\w+)\s+(\S+)", line)
+            if not m:
+                continue
+            k, v = m.group(1), m.group(2)
+            if in_user:
+                d.user_params.append(k)
+            elif k in ("DIMENSIONS", "NTRACER"):
+                setattr(d, k, int(v))
+            elif hasattr(d, k) and k not in ("user_params", "extra"):
+                setattr(d, k, v)
+            else:
+                d.extra[k] = v
+        return d
+
+    def nghost(self) -> int:
+        """GetNghost(), Src/get_nghost.c:19-42."""
+        return 3 if self.RECONSTRUCTION == "PARABOLIC" else 2
+
+    def check_supported(self):
+        if self.PHYSICS != "HD":
+            raise NotImplementedError("PHYSICS %s: only HD is on the hot path" % self.PHYSICS)
+        if self.EOS != "IDEAL":
+            raise NotImplementedError("EOS %s" % self.EOS)
+        if self.RECONSTRUCTION not in _RECON:
+            raise NotImplementedError("RECONSTRUCTION %s" % self.RECONSTRUCTION)
+        if self.TIME_STEPPING not in _TSTEP:
+            raise NotImplementedError("TIME_STEPPING %s" % self.TIME_STEPPING)
+
+
+@dataclass
+class Runtime:
+    """Run-time options (pluto.ini), Src/structs.h:434 / Src/runtime_setup.c."""
+    npoint: list = field(default_factory=lambda: [1, 1, 1])
+    xbeg: list = field(default_factory=lambda: [0.0, 0.0, 0.0])
+    xend: list = field(default_factory=lambda: [1.0, 1.0, 1.0])
+    cfl: float = 0.4
+    cfl_max_var: float = 1.1
+    tstop: float = 1.0
+    first_dt: float = 1.e-4
+    solver: str = "hllc"
+    left_bound: list = field(default_factory=lambda: ["outflow"] * 3)
+    right_bound: list = field(default_factory=lambda: ["outflow"] * 3)
+    params: dict = field(default_factory=dict)
+
+    @classmethod
+    def parse(cls, path) -> "Runtime":
+        rt = cls()
+        section = None
+        for raw in Path(path).read_text().splitlines():
+            line = raw.split("#")[0].strip()
+            if not line:
+                continue
+            m = re.match(r"\[(.+)\]", line)
+            if m:
+                section = m.group(1).strip()
+                continue
+            tok = line.split()
+            key = tok[0]
+            if section == "Grid" and re.match(r"X[123]-grid", key):
+                d = int(key[1]) - 1
+                npatch = int(tok[1])
+                if npatch != 1 or tok[4] != "u":
+                    raise NotImplementedError("only single uniform patches ('u') are parsed here")
+                rt.xbeg[d] = float(tok[2])
+                rt.npoint[d] = int(tok[3])
+                rt.xend[d] = float(tok[5])
+            elif section == "Time":
+                if key == "CFL": rt.cfl = float(tok[1])
+                elif key == "CFL_max_var": rt.cfl_max_var = float(tok[1])
+                elif key == "tstop": rt.tstop = float(tok[1])
+                elif key == "first_dt": rt.first_dt = float(tok[1])
+            elif section == "Solver" and key == "Solver":
+                rt.solver = tok[1]
+            elif section == "Boundary":
+                m = re.match(r"X([123])-(beg|end)", key)
+                if m:
+                    d = int(m.group(1)) - 1
+                    (rt.left_bound if m.group(2) == "beg" else rt.right_bound)[d] = tok[1]
+            elif section == "Parameters":
+                rt.params[key] = float(tok[1])
+        return rt
+
+
+# --------------------------------------------------------------------------------------
+#  Hydro: one block of the grid resident on one B200
+# --------------------------------------------------------------------------------------
+class Hydro:
+    """Device-resident d->Vc plus the AdvanceStep family of calls."""
+
+    def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
+                 reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
+                 bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
+                 small_density=1e-12, small_pressure=1e-12):
+        lib = L.load()
+        cfg = L.Config()
+        lib.pb200_config_default(C.byref(cfg))
+        cfg.dimensions = dimensions
+        for d in range(3):
+            cfg.nx[d] = int(nx[d]) if d < dimensions else 1
+            cfg.xbeg[d] = float(xbeg[d])
+            cfg.xend[d] = float(xend[d])
+        cfg.reconstruction = _RECON[reconstruction]
+        cfg.nghost = nghost if nghost is not None else (3 if reconstruction == "PARABOLIC" else 2)
+        cfg.ntracer = ntracer
+        cfg.limiter = L.LIMITERS[limiter]
+        cfg.time_stepping = _TSTEP[time_stepping]
+        if solver not in _SOLVERS:
+            # SetSolver(): "is not available" -> QUIT_PLUTO (Src/HD/set_solver.c:52-56)
+            raise ValueError("! SetSolver: '%s' is not available on the B200 path" % solver)
+        cfg.solver = _SOLVERS[solver]
+        for s in range(6):
+            b = bcs[s]
+            cfg.bc[s] = L.BC[b] if isinstance(b, str) else int(b)
+        cfg.gamma = gamma
+        cfg.small_density = small_density
+        cfg.small_pressure = small_pressure
+        cfg.device = device
+        self.cfg = cfg
+        self._lib = lib
+        h = C.c_void_p()
+        L.check(lib.pb200_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        tot = (C.c_int * 3)()
+        nv = C.c_int()
+        L.check(lib.pb200_shape(h, C.byref(tot), C.byref(nv)))
+        self.tot = tuple(tot)                      # NX1_TOT, NX2_TOT, NX3_TOT
+        self.nvar = nv.value
+        self.nghost = cfg.nghost
+        self.dimensions = dimensions
+        self.shape = (self.nvar, tot[2], tot[1], tot[0])   # Vc[nv][k][j][i]
+        self.beg = tuple(cfg.nghost if d < dimensions else 0 for d in range(3))
+        self.nx = tuple(cfg.nx[d] for d in range(3))
+        self.last = L.StepInfo()
+
+    @classmethod
+    def from_files(cls, definitions: Definitions, runtime: Runtime, gamma=5. / 3., device=0):
+        definitions.check_supported()
+        nd = definitions.DIMENSIONS
+        bcs = []
+        for d in range(3):
+            bcs += [runtime.left_bound[d], runtime.right_bound[d]]
+        return cls(dimensions=nd, nx=runtime.npoint, xbeg=runtime.xbeg, xend=runtime.xend,
+                   gamma=gamma, reconstruction=definitions.RECONSTRUCTION,
+                   time_stepping=definitions.TIME_STEPPING, solver=runtime.solver,
+                   limiter=definitions.LIMITER, bcs=bcs, ntracer=definitions.NTRACER,
+                   device=device)
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- geometry helpers (host) -----------------------------------------------------------
+    def interior(self):
+        """slices selecting the interior (DOM) zones of Vc[nv][k][j][i]."""
+        sl = [slice(None)]
+        for d in (2, 1, 0):
+            b = self.beg[d]
+            sl.append(slice(b, b + self.nx[d]))
+        return tuple(sl)
+
+    def cell_centers(self, d):
+        n = self.tot[d]
+        dx = (self.cfg.xend[d] - self.cfg.xbeg[d]) / self.nx[d]
+        return self.cfg.xbeg[d] + (np.arange(n) - self.beg[d] + 0.5) * dx
+
+    def new_vc(self):
+        return np.zeros(self.shape, dtype=np.float64)
+
+    # -- data movement -----------------------------------------------------------------------
+    def upload(self, vc: np.ndarray):
+        vc = np.ascontiguousarray(vc, dtype=np.float64)
+        assert vc.shape == self.shape, (vc.shape, self.shape)
+        L.check(self._lib.pb200_upload_vc(self._h, vc.ctypes.data_as(C.c_void_p)))
+
+    def download(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        assert out.flags["C_CONTIGUOUS"] and out.shape == self.shape
+        L.check(self._lib.pb200_download_vc(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_interior(self, v_int: np.ndarray):
+        """Load interior zones [nv][nz][ny][nx] (e.g. a data.NNNN.dbl dump); ghosts are
+        filled by the first Boundary() of the step."""
+        vc = self.new_vc()
+        vc[:, :, :, :] = 1.0   # harmless positive filler for corner ghosts never touched by BCs
+        vc[1:4] = 0.0
+        vc[self.interior()] = v_int
+        self.upload(vc)
+
+    def get_interior(self) -> np.ndarray:
+        return self.download()[self.interior()].copy()
+
+    # -- the reference calls -------------------------------------------------------------------
+    def boundary(self):
+        """Boundary(d, 0, grid)."""
+        L.check(self._lib.pb200_boundary(self._h))
+
+    def advance_step(self, dt: float) -> L.StepInfo:
+        """AdvanceStep(d, Dts, grid) with g_dt = dt on the device-resident state."""
+        L.check(self._lib.pb200_advance_step(self._h, float(dt), C.byref(self.last)))
+        return self.last
+
+    def advance_step_host(self, vc: np.ndarray, dt: float) -> L.StepInfo:
+        """AdvanceStep on a HOST d->Vc (H2D + step + D2H inside the call)."""
+        assert vc.flags["C_CONTIGUOUS"] and vc.shape == self.shape and vc.dtype == np.float64
+        L.check(self._lib.pb200_advance_step_host(self._h, vc.ctypes.data_as(C.c_void_p),
+                                                  float(dt), C.byref(self.last)))
+        return self.last
+
+    def next_time_step(self, invDt_hyp, cfl, cfl_max_var, g_dt, first_dt) -> float:
+        """NextTimeStep(), Src/main.c:521."""
+        r = self._lib.pb200_next_time_step(invDt_hyp, cfl, cfl_max_var, g_dt, first_dt)
+        if r < 0:
+            raise RuntimeError("! NextTimeStep(): dt is too small. Cannot continue.")
+        return r
+
+    def integrate(self, nsteps, *, t, dt, tstop, cfl, cfl_max_var, first_dt):
+        """nsteps iterations of the main loop (Src/main.c:215-337) without leaving C."""
+        tt, dd = C.c_double(t), C.c_double(dt)
+        n = L.check(self._lib.pb200_integrate(self._h, int(nsteps), float(tstop), float(cfl),
+                                              float(cfl_max_var), float(first_dt), C.byref(tt),
+                                              C.byref(dd), C.byref(self.last)))
+        return n, tt.value, dd.value
+
+    # -- stage-level access (halo exchange between stages) ---------------------------------
+    def step_begin(self, dt):
+        L.check(self._lib.pb200_step_begin(self._h, float(dt)))
+
+    def stage(self, s):
+        L.check(self._lib.pb200_stage(self._h, int(s)))
+
+    def step_end(self) -> L.StepInfo:
+        L.check(self._lib.pb200_step_end(self._h, C.byref(self.last)))
+        return self.last
+
+    def nstages(self) -> int:
+        return self._lib.pb200_nstages(self._h)
+
+    def stage_array_ptr(self, s) -> int:
+        return self._lib.pb200_stage_array(self._h, int(s))
+
+    def device_vc_ptr(self) -> int:
+        return self._lib.pb200_device_vc(self._h)
+
+    def stream_ptr(self) -> int:
+        return self._lib.pb200_stream(self._h)
+
+    def halo_layout(self, d):
+        v = [C.c_long() for _ in range(6)]
+        L.check(self._lib.pb200_halo_layout(self._h, d, *[C.byref(x) for x in v]))
+        keys = ("lo_ghost", "lo_edge", "hi_edge", "hi_ghost", "count", "var_stride")
+        return {k: x.value for k, x in zip(keys, v)}
+
+
+# --------------------------------------------------------------------------------------
+#  Simulation: the reference's main() time loop around Hydro
+# --------------------------------------------------------------------------------------
+class Simulation:
+    """main() loop of Src/main.c:215-337 for COOLING NO: clip dt at tstop, AdvanceStep,
+    g_time += g_dt, g_dt = NextTimeStep, g_stepNumber++."""
+
+    def __init__(self, hydro: Hydro, runtime: Runtime):
+        self.h = hydro
+        self.rt = runtime
+        self.g_time = 0.0
+        self.g_dt = runtime.first_dt
+        self.g_stepNumber = 0
+        self.g_maxMach = 0.0
+        self.history = []     # (nstep, t, dt) before each step, like restart.out records
+
+    def step(self) -> bool:
+        """One pass of the loop body; returns True if this was the last step."""
+        rt = self.rt
+        last = False
+        if (self.g_time + self.g_dt) >= rt.tstop * (1.0 - 1.e-8):
+            self.g_dt = rt.tstop - self.g_time
+            last = True
+        self.history.append((self.g_stepNumber, self.g_time, self.g_dt))
+        info = self.h.advance_step(self.g_dt)
+        self.g_maxMach = info.maxMach
+        self.g_time += self.g_dt
+        self.g_dt = self.h.next_time_step(info.invDt_hyp, rt.cfl, rt.cfl_max_var, self.g_dt,
+                                          rt.first_dt)
+        self.g_stepNumber += 1
+        return last
+
+    def run(self, maxsteps=None):
+        n = 0
+        while True:
+            last = self.step()
+            n += 1
+            if last or (maxsteps is not None and n >= maxsteps):
+                break
+        return n
