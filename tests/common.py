@@ -1,0 +1,78 @@
+"""Shared helpers of the test-suite (golden loader, error norms, seeded states)."""
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+
+# north_star tolerances
+TOL_STEP = 1e-12     # relative, per step
+TOL_RUN = 1e-9       # relative L1 after a full run
+
+
+def load_golden(name):
+    z = np.load(GOLDEN / (name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    for k in ("recon", "rk", "solver", "ref_config"):
+        g[k] = str(g[k])
+    g["dims"] = int(g["dims"])
+    g["bcs"] = tuple(str(b) for b in g["bcs"])
+    for k in ("gamma", "cfl", "cfl_max_var", "first_dt", "tstop"):
+        g[k] = float(g[k])
+    g["nx"] = tuple(int(x) for x in g["nx"])
+    return g
+
+
+def kwargs_from_golden(g):
+    return dict(dimensions=g["dims"], nx=g["nx"], gamma=g["gamma"], reconstruction=g["recon"],
+                time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"])
+
+
+def rel_err(a, b):
+    """max over variables of max|a-b| / max|b| (velocities share one scale)."""
+    a = np.asarray(a); b = np.asarray(b)
+    worst = 0.0
+    vscale = max(np.abs(b[1:4]).max(), 1e-300)
+    for nv in range(b.shape[0]):
+        scale = vscale if 1 <= nv <= 3 else max(np.abs(b[nv]).max(), 1e-300)
+        worst = max(worst, np.abs(a[nv] - b[nv]).max() / scale)
+    return worst
+
+
+def rel_l1(a, b):
+    worst = 0.0
+    vscale = max(np.abs(b[1:4]).sum(), 1e-300)
+    for nv in range(b.shape[0]):
+        scale = vscale if 1 <= nv <= 3 else max(np.abs(b[nv]).sum(), 1e-300)
+        worst = max(worst, np.abs(a[nv] - b[nv]).sum() / scale)
+    return worst
+
+
+def random_state(shape_int, seed, smooth=True):
+    """Seeded primitive state [5][nz][ny][nx]: smooth waves plus a few jumps (shocks/contacts)."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = shape_int
+    z, y, x = np.meshgrid(np.linspace(0, 1, nz, endpoint=False), np.linspace(0, 1, ny, endpoint=False),
+                          np.linspace(0, 1, nx, endpoint=False), indexing="ij")
+    v = np.empty((5, nz, ny, nx))
+    ph = rng.uniform(0, 2 * np.pi, size=(5, 3))
+    k = rng.integers(1, 4, size=(5, 3))
+    def wave(n):
+        return (np.sin(2 * np.pi * k[n, 0] * x + ph[n, 0]) * np.cos(2 * np.pi * k[n, 1] * y * (ny > 1) + ph[n, 1])
+                * np.cos(2 * np.pi * k[n, 2] * z * (nz > 1) + ph[n, 2]))
+    v[0] = 1.0 + 0.4 * wave(0)
+    v[1] = 0.8 * wave(1)
+    v[2] = 0.8 * wave(2)
+    v[3] = 0.8 * wave(3)
+    v[4] = 1.0 + 0.5 * wave(4)
+    if not smooth:
+        # jumps: a dense over-pressured box and a rarefied slab
+        sx = slice(nx // 4, max(nx // 4 + 1, nx // 2)); sy = slice(ny // 4, max(ny // 4 + 1, ny // 2))
+        sz = slice(nz // 4, max(nz // 4 + 1, nz // 2))
+        v[0][sz, sy, sx] *= 4.0
+        v[4][sz, sy, sx] *= 20.0
+        v[0][..., (3 * nx) // 4:] *= 0.125
+        v[4][..., (3 * nx) // 4:] *= 0.1
+        v[1:4] += rng.normal(0, 0.05, size=(3, nz, ny, nx))
+    return v

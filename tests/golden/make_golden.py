@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference executables in oracle/_ref
+(built by oracle/build_ref.py from /root/reference).  Run in the build container only;
+the fixtures are committed so that the GPU box (no /root/reference) can check against them.
+
+Each fixture holds, for one configuration: the run parameters, the list of (nstep, t, dt)
+records of restart.out, and selected per-step dumps of d->Vc (interior zones)."""
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT / "oracle"))
+import build_ref  # noqa: E402
+import refrun     # noqa: E402
+
+SOD_BCS = ("outflow", "outflow", "periodic", "periodic", "outflow", "outflow")
+SEDOV_BCS = ("reflective", "outflow") * 3
+SEDOV_PAR = dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4)
+
+CASES = {
+    # name: (ref config, dims, N, recon, rk, solver, bcs, maxsteps, params, gamma, cfl, first_dt, tstop, keep)
+    "sod_plm_hllc": ("sod", 1, 400, "LINEAR", "RK2", "hllc", SOD_BCS, 60, {"SCRH": 0}, 1.4, 0.8, 1e-4, 0.2),
+    "sod_plm_hll": ("sod", 1, 400, "LINEAR", "RK2", "hll", SOD_BCS, 30, {"SCRH": 0}, 1.4, 0.8, 1e-4, 0.2),
+    "sod_plm_tvdlf": ("sod", 1, 400, "LINEAR", "RK2", "tvdlf", SOD_BCS, 30, {"SCRH": 0}, 1.4, 0.8, 1e-4, 0.2),
+    "sod_ppm_hllc": ("sod_ppm", 1, 400, "PARABOLIC", "RK3", "hllc", SOD_BCS, 30, {"SCRH": 0}, 1.4, 0.8, 1e-4, 0.2),
+    "sedov2d_plm_hllc": ("sedov2d", 2, 32, "LINEAR", "RK2", "hllc", SEDOV_BCS, 16, SEDOV_PAR, 1.4, 0.3, 1e-9, 0.5),
+    "sedov3d_plm_hllc": ("sedov3d", 3, 16, "LINEAR", "RK2", "hllc", SEDOV_BCS, 12, SEDOV_PAR, 1.4, 0.3, 1e-9, 0.5),
+    "sedov3d_plm_hll": ("sedov3d", 3, 16, "LINEAR", "RK2", "hll", SEDOV_BCS, 8, SEDOV_PAR, 1.4, 0.3, 1e-9, 0.5),
+    "sedov3d_ppm_hllc": ("sedov3d_ppm", 3, 16, "PARABOLIC", "RK3", "hllc", SEDOV_BCS, 10, SEDOV_PAR, 1.4, 0.3, 1e-9, 0.5),
+    "sedov3d_ppm_tvdlf": ("sedov3d_ppm", 3, 16, "PARABOLIC", "RK3", "tvdlf", SEDOV_BCS, 6, SEDOV_PAR, 1.4, 0.3, 1e-9, 0.5),
+}
+
+
+def main():
+    out = Path(__file__).resolve().parent
+    for name, (cfg, nd, N, recon, rk, solver, bcs, maxsteps, params, gamma, cfl, first_dt, tstop) in CASES.items():
+        build_ref.build(cfg)
+        nx = [N if d < nd else 1 for d in range(3)]
+        with tempfile.TemporaryDirectory() as wd:
+            r = refrun.run(cfg, wd, shape=(nx[2], nx[1], nx[0]), maxsteps=maxsteps,
+                           grid=[(0, nx[0], 1), (0, nx[1], 1), (0, nx[2], 1)], cfl=cfl, tstop=tstop,
+                           first_dt=first_dt, solver=solver, bcs=bcs, dbl=(-1.0, 1), params=params)
+        nd_ = len(r["data"]) - 1          # last file = state after the final (non-dumped) steps
+        steps = np.array(r["steps"][:nd_], dtype=np.float64)   # (nstep, t, dt-of-next-step)
+        data = np.stack(r["data"][:nd_])
+        np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx),
+                            dims=nd, recon=recon, rk=rk, solver=solver, bcs=np.array(bcs),
+                            gamma=gamma, cfl=cfl, cfl_max_var=1.1, first_dt=first_dt, tstop=tstop,
+                            ref_config=cfg)
+        print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
+
+
+if __name__ == "__main__":
+    main()
