@@ -1,0 +1,405 @@
+#!/usr/bin/env python3
+"""bench.py -- zone-updates/s of the unsplit HD update (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU build
+
+A "step" is one full time step (all RK stages, all directions, boundaries, cons<->prim, dt
+reduction) of the workload `sedov3d-512^3 PLM+HLLC+RK2` per GPU (BASELINE.json configs[1]);
+with N > 1 the blocks are stacked along x3 (weak scaling, slab decomposition, NCCL halo
+exchange per stage + one max-allreduce per step).  State arrays (5.5 GB each) are far larger
+than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+
+value : device-resident state (inputs in HBM when the timed region starts)
+e2e   : the same steps through the host-buffer entry point pb200_advance_step_host(): H2D of
+        d->Vc from pinned host memory, AdvanceStep, D2H of d->Vc, every step.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "zone-updates/s"
+UNIT = "Mzones/s"
+ALG_BYTES_RK2 = 360.0     # FP64, NVAR=5: 160 B (stage 1) + 200 B (stage 2)
+ALG_BYTES_RK3 = 560.0
+SEDOV_BCS = ("reflective", "outflow") * 3
+
+
+def workload_name(n, recon, rk, solver):
+    return "sedov3d-%d^3-per-gpu %s+%s+%s" % (n, {"LINEAR": "PLM", "PARABOLIC": "PPM"}[recon], solver.upper(), rk)
+
+
+def sedov_block(nx, zoff, nglob, gamma=1.4):
+    """Sedov IC of Test_Problems/HD/Sedov/init.c:49-91 (INITIAL_SMOOTHING NO) for the block
+    whose x3 index starts at zoff; unit cube spacing 1/nglob in every direction."""
+    import numpy as np
+    n1, n2, n3 = nx
+    x = (np.arange(n1) + 0.5) / nglob
+    y = (np.arange(n2) + 0.5) / nglob
+    z = (np.arange(n3) + zoff + 0.5) / nglob
+    dr = 3.5 / nglob
+    vol = 4.0 / 3.0 * np.pi * dr ** 3
+    v = np.zeros((5, n3, n2, n1))
+    v[0] = 1.0
+    v[4] = 1.0e-5
+    # the deposition sphere touches only the first few zones
+    m = 8
+    r = np.sqrt(x[None, None, :m] ** 2 + y[None, :m, None] ** 2 + z[:m, None, None] ** 2)
+    v[4, :m, :m, :m] = np.where(r <= dr, (gamma - 1.0) * 1.0 / vol, 1.0e-5)
+    return v
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------
+#  reference arm: the unmodified reference C build on the host cores
+# --------------------------------------------------------------------------------------
+def reference_rate(cfg, n, nproc, warm, steps, solver="hllc"):
+    """Mzones/s of `nproc` concurrent serial reference processes (no MPI on this image, so this
+    is the communication-free upper bound of an MPI run) on n^3 zones each.  Timed by
+    differencing a (warm) and a (warm+steps) run so initialisation is excluded."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import refrun
+    exe = refrun.REFDIR / cfg / "pluto"
+    if not exe.exists():
+        return None
+
+    def launch(maxsteps):
+        procs, dirs = [], []
+        for p in range(nproc):
+            d = tempfile.mkdtemp(prefix="plref_")
+            dirs.append(d)
+            refrun.write_ini(Path(d) / "pluto.ini", grid=[(0, n, 1)] * 3, cfl=0.3, tstop=0.5, first_dt=1e-9,
+                             solver=solver, bcs=SEDOV_BCS, params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4))
+            procs.append(subprocess.Popen([str(exe), "-no-write", "-maxsteps", str(maxsteps)], cwd=d,
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        t0 = time.perf_counter()
+        for pr in procs:
+            pr.wait()
+        t = time.perf_counter() - t0
+        import shutil
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+        return t
+
+    ta = launch(warm)
+    tb = launch(warm + steps)
+    dt = max(tb - ta, 1e-9)
+    return nproc * n ** 3 * steps / dt / 1e6, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    cfg = "sedov3d" if args.recon == "LINEAR" else "sedov3d_ppm"
+    n = args.ref_size
+    # keep the run bounded: about steps*n^3/1e6 seconds per process
+    res = reference_rate(cfg, n, cores, args.warmup, args.steps, args.solver)
+    wl = workload_name(args.size, args.recon, args.rk, args.solver)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/%s/pluto not built on this box" % cfg}))
+        return 0
+    rate, dt = res
+    sample = ("%d concurrent serial processes (no MPI on this image: communication-free upper bound), "
+              "%d^3 zones each, same problem/solver, %d timed steps (init excluded by differencing two runs); "
+              "gcc -O3 -std=c17 (Config/Linux.gcc.defs)" % (cores, n, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+#  this repo's arm
+# --------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pluto_sirocco_b200 import Hydro
+    from pluto_sirocco_b200.slab import Slab, SlabHydro
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.size
+    gnx = (n, n, n * world)
+    bcs = SEDOV_BCS
+    slab = Slab(rank, world, 3, gnx, (0., 0., 0.), (1., 1., float(world)), bcs)
+    xb, xe = slab.local_extent()
+    h = Hydro(dimensions=3, nx=slab.local_nx(), xbeg=xb, xend=xe, gamma=1.4, reconstruction=args.recon,
+              time_stepping=args.rk, solver=args.solver, bcs=slab.local_bcs(), device=local_rank,
+              dx=slab.global_dx())
+    sh = SlabHydro(h, slab)
+    zones_local = n * n * n
+    zones_total = zones_local * world
+
+    # host state in pinned memory (needed by the e2e leg; also the upload source)
+    pin = torch.empty(h.shape, dtype=torch.float64, pin_memory=True)
+    vc = pin.numpy()
+    vc[:] = 1.0
+    vc[1:4] = 0.0
+    if args.state == "sedov":
+        vc[h.interior()] = sedov_block(slab.local_nx(), slab.offset, n)
+    else:   # "busy": seeded waves + jumps everywhere: every limiter/solver branch is exercised
+        sys.path.insert(0, str(ROOT / "tests"))
+        from common import random_state
+        vc[h.interior()] = random_state((n, n, n), seed=rank, smooth=False)
+    h.upload(vc)
+
+    cfl, cmv, first_dt = 0.3, 1.1, 1e-9
+    g = {"dt": first_dt if args.state == "sedov" else 1e-5}
+
+    def one_step():
+        inv, mach, info = sh.advance_step(g["dt"])
+        g["dt"] = h.next_time_step(inv, cfl, cmv, g["dt"], first_dt)
+        return info
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stream = sh.stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        info = one_step()
+        launches += info.launches
+    ev1.record(stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = zones_total * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel times (CUDA events inside the library, on the launching stream) ----
+    h.set_profiling(True)
+    acc = {}
+    nprof = 3
+    for _ in range(nprof):
+        one_step()
+        for (kms, kdir, kstage) in h.kernel_times():
+            acc.setdefault((kdir, kstage), []).append(kms)
+    h.set_profiling(False)
+    kern = {k: sum(v) / len(v) for k, v in acc.items()}
+    sweep_ms = sum(kern.values())
+    (ddir, dstage), dms = max(kern.items(), key=lambda kv: kv[1])
+
+    # ---- e2e: host buffers, H2D + step + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h.download(vc)
+        dt_e = g["dt"]
+
+        def e2e_step():
+            nonlocal dt_e
+            if world == 1:
+                info = h.advance_step_host(vc, dt_e)
+                inv = info.invDt_hyp
+            else:
+                h.upload(vc)
+                inv, mach, info = sh.advance_step(dt_e)
+                h.download(vc)
+            dt_e = h.next_time_step(inv, cfl, cmv, dt_e, first_dt)
+
+        e2e_step()
+        sync_all()
+        ne = max(2, min(args.steps, args.e2e_steps))
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(ne):
+            e2e_step()
+        ev1.record(stream)
+        sync_all()
+        wall = time.perf_counter() - t0
+        ems = max(ev0.elapsed_time(ev1), wall * 1e3)   # copies are synchronous: wall clock covers them
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = t.item()
+        nbytes = int(np.prod(h.shape)) * 8
+        e2e = {"value": zones_total * ne / (ems * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": ne,
+               "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    alg = ALG_BYTES_RK2 if args.rk == "RK2" else ALG_BYTES_RK3
+    nlaunch_sweeps = len(kern)
+    step_ms = ms / args.steps
+    achieved_step = alg * zones_local / (step_ms * 1e-3) / 1e9          # GB/s per GPU, whole step
+    achieved_kernel = (alg / nlaunch_sweeps) * zones_local / (dms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("x%d_stage%d" % (ddir + 1, dstage))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved_kernel, "peak": peak, "unit": "GB/s",
+                "frac": achieved_kernel / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "x%d sweep, stage %d" % (ddir + 1, dstage), "kernel_ms": dms,
+                "algorithmic_bytes_per_launch": (alg / nlaunch_sweeps) * zones_local,
+                "step": {"achieved": achieved_step, "frac": achieved_step / peak, "ms": step_ms,
+                         "sweep_kernels_ms": sweep_ms, "algorithmic_bytes_per_zone_update": alg},
+                "kernels_ms": {"x%d_stage%d" % (k[0] + 1, k[1]): v for k, v in sorted(kern.items())}}
+
+    cpu_baseline = None
+    if not args.no_cpu:
+        cfg = "sedov3d" if args.recon == "LINEAR" else "sedov3d_ppm"
+        r = reference_rate(cfg, args.cpu_size, 1, 1, args.cpu_steps, args.solver)
+        if r is not None:
+            cpu_baseline = {"value": r[0], "unit": UNIT, "cores": 1, "kind": "reference",
+                            "sample": "unmodified reference executable (oracle/_ref/%s), %d^3 zones, %d steps, 1 core, "
+                                      "init excluded by differencing two runs" % (cfg, args.cpu_size, args.cpu_steps)}
+        else:
+            sys.path.insert(0, str(ROOT / "oracle"))
+            from oracle import Oracle
+            m = 64
+            o = Oracle(dimensions=3, nx=(m, m, m), gamma=1.4, reconstruction=args.recon, time_stepping=args.rk,
+                       solver=args.solver, bcs=bcs)
+            w = o.embed(sedov_block((m, m, m), 0, m))
+            t0 = time.perf_counter()
+            ns = 8
+            o.integrate(w, ns, t=0.0, dt=1e-9, tstop=0.5, cfl=0.3, cfl_max_var=1.1, first_dt=1e-9)
+            dtw = time.perf_counter() - t0
+            cpu_baseline = {"value": m ** 3 * ns / dtw / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": "oracle/hd_oracle.c, %d^3 zones, %d steps, 1 core" % (m, ns)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n, args.recon, args.rk, args.solver), "state": args.state,
+                       "zones_per_gpu": zones_local, "decomposition": "x3 slabs" if world > 1 else "none",
+                       "l2": "inputs (5.5 GB per state array) larger than L2, no flush needed",
+                       "boundaries": "reflective-beg/outflow-end", "cfl": cfl},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="zones per direction per GPU")
+    ap.add_argument("--recon", default="LINEAR", choices=["LINEAR", "PARABOLIC"])
+    ap.add_argument("--rk", default="RK2", choices=["RK2", "RK3"])
+    ap.add_argument("--solver", default="hllc", choices=["hllc", "hll", "tvdlf"])
+    ap.add_argument("--state", default="sedov", choices=["sedov", "busy"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--ref-size", type=int, default=96)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

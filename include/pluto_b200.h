@@ -165,6 +165,12 @@ double *pb200_stage_array(pb200_ctx *ctx, int stage);  /* device Vc swept by sta
 int  pb200_stage(pb200_ctx *ctx, int stage);
 int  pb200_step_end(pb200_ctx *ctx, pb200_step_info *info);
 int  pb200_nstages(const pb200_ctx *ctx);
+/* Measurement aid (the reference's FUNCTION_CLOCK_PROFILE, Src/pluto.h:414-419, rk_step.c:
+ * 51-55): record CUDA events around every sweep kernel of the following steps;
+ * pb200_kernel_times() returns, for the last finished step, the device time [ms], sweep
+ * direction and RK stage of each sweep launch (return value = number of launches, <= max). */
+int  pb200_set_profiling(pb200_ctx *ctx, int on);
+int  pb200_kernel_times(const pb200_ctx *ctx, int max, float *ms, int *dir, int *stage);
 /* CUDA stream (cudaStream_t as void*) all kernels of ctx are launched on */
 void *pb200_stream(pb200_ctx *ctx);
 

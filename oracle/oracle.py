@@ -23,7 +23,7 @@ class Cfg(C.Structure):
     _fields_ = [("ndim", C.c_int), ("nx", C.c_int * 3), ("ng", C.c_int), ("nvar", C.c_int),
                 ("recon", C.c_int), ("limiter", C.c_int), ("rk", C.c_int), ("solver", C.c_int),
                 ("bc", C.c_int * 6), ("gamma", C.c_double), ("small_dn", C.c_double),
-                ("small_pr", C.c_double), ("xbeg", C.c_double * 3), ("xend", C.c_double * 3)]
+                ("small_pr", C.c_double), ("xbeg", C.c_double * 3), ("xend", C.c_double * 3), ("dx", C.c_double * 3)]
 
 
 def build(force=False):
@@ -46,6 +46,13 @@ def lib():
         _lib.orc_advance_step.restype = C.c_int
         _lib.orc_advance_step.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_double,
                                           C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _lib.orc_step_begin.restype = C.c_void_p
+        _lib.orc_step_begin.argtypes = [C.POINTER(Cfg), C.c_void_p]
+        _lib.orc_stage.restype = None
+        _lib.orc_stage.argtypes = [C.POINTER(Cfg), C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _lib.orc_step_end.restype = C.c_int
+        _lib.orc_step_end.argtypes = [C.c_void_p]
         _lib.orc_boundary.restype = None
         _lib.orc_boundary.argtypes = [C.POINTER(Cfg), C.c_void_p]
         _lib.orc_next_time_step.restype = C.c_double
@@ -63,7 +70,7 @@ class Oracle:
     def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, small_density=1e-12,
-                 small_pressure=1e-12, **_):
+                 small_pressure=1e-12, dx=None, **_):
         c = Cfg()
         c.ndim = dimensions
         for d in range(3):
@@ -79,6 +86,8 @@ class Oracle:
         for s in range(6):
             c.bc[s] = BCS[bcs[s]] if isinstance(bcs[s], str) else int(bcs[s])
         c.gamma = gamma
+        for d in range(3):
+            c.dx[d] = dx[d] if dx is not None else 0.0
         c.small_dn = small_density
         c.small_pr = small_pressure
         self.c = c

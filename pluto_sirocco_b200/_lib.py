@@ -62,6 +62,9 @@ SYMBOLS = {
     "pb200_step_end": (C.c_int, [_P, C.POINTER(StepInfo)]),
     "pb200_nstages": (C.c_int, [_P]),
     "pb200_stream": (_P, [_P]),
+    "pb200_set_profiling": (C.c_int, [_P, C.c_int]),
+    "pb200_kernel_times": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int)]),
 }
 
 _lib = None

@@ -51,6 +51,12 @@ struct pb200_ctx {
   int nstages;
   int stage_in[4], stage_out[4];  // array indices per stage (1-based)
   bool in_step;
+  // optional per-kernel timing (pb200_set_profiling)
+  bool profiling;
+  int nprof;
+  cudaEvent_t pev0[16], pev1[16];
+  int pdir[16], pstage[16];
+  float pms[16];
 };
 
 extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
@@ -191,6 +197,10 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 16; k++) {
+    if (c->pev0[k]) cudaEventDestroy(c->pev0[k]);
+    if (c->pev1[k]) cudaEventDestroy(c->pev1[k]);
+  }
   delete c;
 }
 
@@ -270,6 +280,13 @@ extern "C" int pb200_boundary(pb200_ctx *c) {
 template <int NV, int RECON, int SOLVER>
 static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   const Dev &D = c->dev;
+  const int slot = (c->profiling && c->nprof < 16) ? c->nprof++ : -1;
+  if (slot >= 0) {
+    if (!c->pev0[slot]) { cudaEventCreate(&c->pev0[slot]); cudaEventCreate(&c->pev1[slot]); }
+    c->pdir[slot] = dir;
+    c->pstage[slot] = a.stage;
+    cudaEventRecord(c->pev0[slot], c->stream);
+  }
   int nx = D.end[0] - D.beg[0] + 1;
   if (dir == 0) {
     constexpr int LO = (RECON == RECON_PARABOLIC) ? 2 : 1;
@@ -290,6 +307,7 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     if (dir == 1) sweep_march<1, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
     else sweep_march<2, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
   }
+  if (slot >= 0) cudaEventRecord(c->pev1[slot], c->stream);
   c->launches++;
 }
 
@@ -326,6 +344,7 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   if (!(dt > 0.0)) return fail(PB200_EINVAL, "dt must be > 0");
   CK(cudaSetDevice(c->cfg.device));
   c->launches = 0;
+  c->nprof = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
   reset_red<<<1, 1, 0, c->stream>>>(c->d_red, c->d_dt, dt);
   c->launches++;
@@ -390,6 +409,7 @@ extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {
   if (c->dev.ndim > 1) invdt /= (double)c->dev.ndim;  // update_stage.c:392
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  for (int k = 0; k < c->nprof; k++) cudaEventElapsedTime(&c->pms[k], c->pev0[k], c->pev1[k]);
   if (info) {
     info->invDt_hyp = invdt;
     info->maxMach = mach;
@@ -400,6 +420,23 @@ extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {
   if (!(invdt > 0.0) || !isfinite(invdt))
     return fail(PB200_ENAN, "non-finite or zero signal speed: NaN in the state (CheckNaN)");
   return PB200_OK;
+}
+
+extern "C" int pb200_set_profiling(pb200_ctx *c, int on) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  c->profiling = on != 0;
+  return PB200_OK;
+}
+
+extern "C" int pb200_kernel_times(const pb200_ctx *c, int max, float *ms, int *dir, int *stage) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  int n = c->nprof < max ? c->nprof : max;
+  for (int k = 0; k < n; k++) {
+    if (ms) ms[k] = c->pms[k];
+    if (dir) dir[k] = c->pdir[k];
+    if (stage) stage[k] = c->pstage[k];
+  }
+  return n;
 }
 
 extern "C" int pb200_advance_step(pb200_ctx *c, double dt, pb200_step_info *info) {

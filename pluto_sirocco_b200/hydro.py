@@ -151,7 +151,7 @@ class Hydro:
     def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
-                 small_density=1e-12, small_pressure=1e-12):
+                 small_density=1e-12, small_pressure=1e-12, dx=None):
         lib = L.load()
         cfg = L.Config()
         lib.pb200_config_default(C.byref(cfg))
@@ -192,6 +192,14 @@ class Hydro:
         self.beg = tuple(cfg.nghost if d < dimensions else 0 for d in range(3))
         self.nx = tuple(cfg.nx[d] for d in range(3))
         self.last = L.StepInfo()
+        if dx is not None:      # block of a larger uniform grid: impose the global grid->dx
+            for d in range(dimensions):
+                n = self.tot[d]
+                xl = cfg.xbeg[d] + (np.arange(n) - self.beg[d]) * dx[d]
+                xr = xl + dx[d]
+                dxa = np.full(n, dx[d])
+                L.check(lib.pb200_set_grid(h, d, xl.ctypes.data_as(C.c_void_p),
+                                           xr.ctypes.data_as(C.c_void_p), dxa.ctypes.data_as(C.c_void_p)))
 
     @classmethod
     def from_files(cls, definitions: Definitions, runtime: Runtime, gamma=5. / 3., device=0):
@@ -314,6 +322,15 @@ class Hydro:
 
     def stream_ptr(self) -> int:
         return self._lib.pb200_stream(self._h)
+
+    def set_profiling(self, on: bool):
+        L.check(self._lib.pb200_set_profiling(self._h, int(on)))
+
+    def kernel_times(self):
+        """[(ms, dir, stage)] of the sweep launches of the last step (profiling on)."""
+        ms = (C.c_float * 16)(); di = (C.c_int * 16)(); st = (C.c_int * 16)()
+        n = L.check(self._lib.pb200_kernel_times(self._h, 16, ms, di, st))
+        return [(ms[k], di[k], st[k]) for k in range(n)]
 
     def halo_layout(self, d):
         v = [C.c_long() for _ in range(6)]
