@@ -288,24 +288,41 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     cudaEventRecord(c->pev0[slot], c->stream);
   }
   int nx = D.end[0] - D.beg[0] + 1;
-  if (dir == 0) {
+  if (dir == 0) {  // DIMENSIONS == 1 only: plain x1 sweep
     constexpr int LO = (RECON == RECON_PARABOLIC) ? 2 : 1;
     constexpr int USE = BX - 1 - LO;
     dim3 grid((nx + USE - 1) / USE, D.end[1] - D.beg[1] + 1, D.end[2] - D.beg[2] + 1);
     sweep_x1<NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a);
   } else {
+    // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
+    const bool fusex = (dir == 1);
+    constexpr int XH = (RECON == RECON_PARABOLIC) ? 3 : (RECON == RECON_LINEAR ? 2 : 1);
+    const int use = fusex ? BX - 2 * XH : BX;
     int npen = D.end[dir] - D.beg[dir] + 1;
     int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
-    int nbx = (nx + BX - 1) / BX;
-    // chunk the pencil so that the grid holds at least ~8 waves of 148 SMs x 8 blocks
-    long want = 148L * 8 * 8;
+    int nbx = (nx + use - 1) / use;
+    // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks
+    long want = 148L * 3 * 6;
     int nchunk = 1;
     while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
     int chunk = (npen + nchunk - 1) / nchunk;
     nchunk = (npen + chunk - 1) / chunk;
     dim3 grid(nbx, ntr, nchunk);
-    if (dir == 1) sweep_march<1, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
-    else sweep_march<2, NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a, chunk);
+    const bool first = fusex ? true : (a.first != 0);
+    const bool cdt_in = D.ndim > 1 && a.stage == 1 && !first;
+    const int nq = ring_nq(NV, first, a.last != 0, a.comb, cdt_in);
+    size_t shm = ((size_t)RING * nq * BX + (fusex ? (size_t)(3 * NV + 2) * BX : 0)) * sizeof(double);
+    if (fusex) {
+      auto k = sweep_fused<1, true, NV, RECON, SOLVER>;
+      static size_t cur = 0;
+      if (shm > cur) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); cur = shm; }
+      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
+    } else {
+      auto k = sweep_fused<2, false, NV, RECON, SOLVER>;
+      static size_t cur = 0;
+      if (shm > cur) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); cur = shm; }
+      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
+    }
   }
   if (slot >= 0) cudaEventRecord(c->pev1[slot], c->stream);
   c->launches++;
@@ -387,10 +404,16 @@ extern "C" int pb200_stage(pb200_ctx *c, int stage) {
   } else if (stage == 3) {
     a.comb = 2;
   }
-  for (int dir = 0; dir < D.ndim; dir++) {
-    a.first = (dir == 0);
-    a.last = (dir == D.ndim - 1);
-    launch_sweep(c, dir, a);
+  if (D.ndim == 1) {
+    a.first = 1; a.last = 1;
+    launch_sweep(c, 0, a);
+  } else {
+    a.first = 1; a.last = (D.ndim == 2);
+    launch_sweep(c, 1, a);          // x1 + x2 in one kernel
+    if (D.ndim == 3) {
+      a.first = 0; a.last = 1;
+      launch_sweep(c, 2, a);        // x3
+    }
   }
   CK(cudaGetLastError());
   return PB200_OK;

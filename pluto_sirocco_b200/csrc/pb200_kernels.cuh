@@ -265,85 +265,272 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
 }
 
 // ------------------------------------------------------------------------------------
-//  x2 / x3 sweep: thread per i, marching along the sweep direction in registers
+//  marching sweeps (x2 / x3) with an asynchronous prefetch ring, optionally fused with x1
 // ------------------------------------------------------------------------------------
-template <int DIR, int NV, int RECON, int SOLVER>
-__global__ void __launch_bounds__(BX) sweep_march(Dev d, SweepArgs a, int chunk) {
+// thread <-> i (coalesced); each thread marches along direction DIR keeping the stencil, the
+// previous left state and the previous flux in registers.  Every global read of the loop goes
+// through a per-thread ring in shared memory filled by cp.async (LDGSTS) DEPTH iterations
+// ahead, so HBM latency is covered by a handful of warps per SM without spending registers.
+// With FUSEX the kernel also performs the x1 sweep of every finished row: the three
+// neighbour exchanges (centre states, right states, fluxes) go through shared memory, so
+// the x1 and x2 updates of a stage share ONE read of V and ONE write of the accumulator.
+constexpr int RING = 4;    // ring slots
+constexpr int DEPTH = 3;   // cp.async groups in flight
+
+__device__ __forceinline__ void cp_async8(double *sdst, const double *gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// number of ring quantities a sweep needs (host and device must agree)
+__host__ __device__ inline int ring_nq(int nv, bool first, bool last, int comb, bool cdt_in) {
+  return nv + (first ? 0 : nv) + ((last && comb) ? nv : 0) + (cdt_in ? 1 : 0);
+}
+
+template <int DIR, bool FUSEX, int NV, int RECON, int SOLVER>
+__global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
-  const int i = d.beg[0] + blockIdx.x * BX + threadIdx.x;
-  const bool active = i <= d.end[0];
+  constexpr int LEAD = (RECON == RECON_PARABOLIC) ? 2 : 1;
+  constexpr int XH = (RECON == RECON_PARABOLIC) ? 3 : (RECON == RECON_LINEAR ? 2 : 1);
+  constexpr int LO = FUSEX ? XH : 0, HI = FUSEX ? XH : 0;
+  constexpr int USE = BX - LO - HI;
+  extern __shared__ double smem[];
+
+  const int t = threadIdx.x;
+  const int i = d.beg[0] + blockIdx.x * USE + t - LO;
+  const bool own = (t >= LO) && (t < BX - HI) && (i <= d.end[0]);
+  const int ic = min(max(i, 0), d.tot[0] - 1);
   const int tr = blockIdx.y;  // transverse index (k for x2 sweeps, j for x3 sweeps)
   const long st = (DIR == 1) ? d.sj : d.sk;
-  const long base = (DIR == 1) ? ((long)(d.beg[2] + tr) * d.sk + i) : ((long)(d.beg[1] + tr) * d.sj + i);
+  const long base = (DIR == 1) ? ((long)(d.beg[2] + tr) * d.sk + ic) : ((long)(d.beg[1] + tr) * d.sj + ic);
   const int cb = d.beg[DIR] + blockIdx.z * chunk;
   const int ce = min(cb + chunk - 1, d.end[DIR]);
   const double dt = *a.dt;
   const double *__restrict__ inv_dx = d.inv_dx[DIR];
 
-  double mach = 0.0, cdt_max = 0.0;
-  if (active) {
-    double vm1[NV], v0[NV], vp1[NV], vp2[NV];
-    double vpL[NV], vp[NV], vm[NV];
-    double qm[NV];  // PPM: interface value at n-1/2
-    Face<NV> Fm, Fp;
-    int n0 = cb - 1;  // first zone to reconstruct
-    if (RECON == RECON_PARABOLIC) {
-      // interface value at (cb-2)+1/2 needs zones cb-3 .. cb
-      double a0[NV], a1[NV];
-      load_zone<DIR, NV>(a.V, base + (long)(cb - 3) * st, d.sv, a0);
-      load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
-      load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
-      load_zone<DIR, NV>(a.V, base + (long)(cb)*st, d.sv, vp1);
+  const bool first = FUSEX ? true : (a.first != 0);
+  const bool last = a.last != 0;
+  const bool use_v0 = last && a.comb != 0;
+  const bool cdt_on = d.ndim > 1 && a.stage == 1;
+  const bool cdt_in = cdt_on && !first;
+  const int qA = NV, q0 = qA + (first ? 0 : NV), qC = q0 + (use_v0 ? NV : 0);
+  const int nq = qC + (cdt_in ? 1 : 0);
+  double *ring = smem;                                  // [RING][nq][BX]
+  double *exv = smem + RING * nq * BX;                  // FUSEX: [NV][BX] centre states
+  double *exm = exv + NV * BX;                          //        [NV][BX] right states (vm)
+  double *exf = exm + NV * BX;                          //        [NV+2][BX] fluxes, prs, cmax
+
+  const int n0 = cb - 1;  // first zone to reconstruct
+  auto issue = [&](int m) {  // prefetch the global data iteration m will consume
+    if (m <= ce + 1) {
+      double *slot = ring + ((m - n0) % RING) * nq * BX + t;
+      const long oV = base + (long)(m + LEAD) * st;
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) qm[nv] = ppm4_iface(a0[nv], vm1[nv], v0[nv], vp1[nv]);
-      (void)a1;
-    } else {
-      load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
-      load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
-    }
-    for (int n = n0; n <= ce + 1; n++) {
-      // ---- reconstruct zone n ----
-      if (RECON == RECON_PARABOLIC) {
-        if (n > n0) {  // vp1 already holds zone n+1 for n == n0
+      for (int c = 0; c < NV; c++) cp_async8(slot + c * BX, a.V + gvar<DIR>(c) * d.sv + oV);
+      const int z = m - 1;
+      if (z >= cb && own) {
+        const long oz = base + (long)z * st;
+        if (!first) {
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) vp1[nv] = vp2[nv];
+          for (int c = 0; c < NV; c++) cp_async8(slot + (qA + c) * BX, a.acc + gvar<DIR>(c) * d.sv + oz);
         }
-        load_zone<DIR, NV>(a.V, base + (long)(n + 2) * st, d.sv, vp2);
+        if (use_v0) {
 #pragma unroll
-        for (int nv = 0; nv < NV; nv++) {
-          double q = ppm4_iface(vm1[nv], v0[nv], vp1[nv], vp2[nv]);
-          vp[nv] = q;
-          vm[nv] = qm[nv];
-          qm[nv] = q;
-          ppm_parabola(v0[nv], vp[nv], vm[nv], 2.0, 2.0);
+          for (int c = 0; c < NV; c++) cp_async8(slot + (q0 + c) * BX, a.V0 + gvar<DIR>(c) * d.sv + oz);
         }
-      } else if (RECON == RECON_LINEAR) {
-        load_zone<DIR, NV>(a.V, base + (long)(n + 1) * st, d.sv, vp1);
-        plm_rt<NV>(a.limiter, vm1, v0, vp1, vp, vm);
-      } else {
-        load_zone<DIR, NV>(a.V, base + (long)(n + 1) * st, d.sv, vp1);
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) vp[nv] = vm[nv] = v0[nv];
+        if (cdt_in) cp_async8(slot + qC * BX, a.cdt + oz);
       }
-      // ---- face n-1/2: left = vp of zone n-1, right = vm of zone n ----
-      if (n >= cb) {
-        riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach);
-        if (n >= cb + 1) {  // zone z = n-1 has both faces
-          const int z = n - 1;
-          const double inv_dl = inv_dx[z];
-          finish_zone<DIR, NV>(d, a, base + (long)z * st, vm1, Fm, Fp, dt * inv_dl, inv_dl, cdt_max);
-        }
-        Fm = Fp;
+    }
+    cp_async_commit();
+  };
+
+  double mach = 0.0, cdt_max = 0.0;
+  double vm1[NV], v0[NV], vp1[NV], vp2[NV];
+  double vpL[NV], vp[NV], vm[NV];
+  double qm[NV];  // PPM: interface value at n-1/2
+  Face<NV> Fm, Fp;
+
+#pragma unroll
+  for (int g = 0; g < DEPTH; g++) issue(n0 + g);
+  if (RECON == RECON_PARABOLIC) {
+    double a0[NV];
+    load_zone<DIR, NV>(a.V, base + (long)(cb - 3) * st, d.sv, a0);
+    load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
+    load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
+    load_zone<DIR, NV>(a.V, base + (long)(cb)*st, d.sv, vp1);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) qm[nv] = ppm4_iface(a0[nv], vm1[nv], v0[nv], vp1[nv]);
+  } else {
+    load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
+    load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
+  }
+
+  for (int n = n0; n <= ce + 1; n++) {
+    // ---- data of this iteration has landed in the ring; refill the slot DEPTH ahead ----
+    cp_async_wait<DEPTH - 1>();
+    const double *slot = ring + ((n - n0) % RING) * nq * BX + t;
+    double vin[NV];
+#pragma unroll
+    for (int c = 0; c < NV; c++) vin[c] = slot[c * BX];
+    const int z = n - 1;  // zone finished by this iteration
+    const bool fin = z >= cb;  // block-uniform
+    double U[NV], v0z[NV], cin = 0.0;
+    if (fin && own) {
+      if (!first) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) U[c] = slot[(qA + c) * BX];
+      }
+      if (use_v0) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) v0z[c] = slot[(q0 + c) * BX];
+      }
+      if (cdt_in) cin = slot[qC * BX];
+    }
+    issue(n + DEPTH);
+
+    // ---- reconstruct zone n along DIR ----
+    if (RECON == RECON_PARABOLIC) {
+      if (n > n0) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) vp1[nv] = vp2[nv];
       }
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) {
-        vpL[nv] = vp[nv];
-        vm1[nv] = v0[nv];
-        v0[nv] = vp1[nv];
+        vp2[nv] = vin[nv];
+        double q = ppm4_iface(vm1[nv], v0[nv], vp1[nv], vp2[nv]);
+        vp[nv] = q;
+        vm[nv] = qm[nv];
+        qm[nv] = q;
+        ppm_parabola(v0[nv], vp[nv], vm[nv], 2.0, 2.0);
+      }
+    } else if (RECON == RECON_LINEAR) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vp1[nv] = vin[nv];
+      plm_rt<NV>(a.limiter, vm1, v0, vp1, vp, vm);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) { vp1[nv] = vin[nv]; vp[nv] = vm[nv] = v0[nv]; }
+    }
+
+    // ---- face n-1/2 along DIR ----
+    if (n >= cb && own) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach);
+
+    if (fin) {
+      double cx = 0.0;
+      if (FUSEX) {
+        // ---- x1 sweep of row z: thread <-> zone, neighbours through shared memory ----
+        double vx[NV];  // this zone in x1 (= global) component order
+#pragma unroll
+        for (int c = 0; c < NV; c++) vx[gvar<DIR>(c)] = vm1[c];
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) exv[nv * BX + t] = vx[nv];
+        __syncthreads();
+        const int tm = t > 0 ? t - 1 : 0, tp = t < BX - 1 ? t + 1 : BX - 1;
+        double xp[NV], xm[NV];
+        if (RECON == RECON_PARABOLIC) {
+          const int tp2 = t < BX - 2 ? t + 2 : BX - 1;
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) {
+            xp[nv] = ppm4_iface(exv[nv * BX + tm], vx[nv], exv[nv * BX + tp], exv[nv * BX + tp2]);
+            exm[nv * BX + t] = xp[nv];   // interface value at t+1/2
+          }
+          __syncthreads();
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) {
+            xm[nv] = exm[nv * BX + tm];
+            ppm_parabola(vx[nv], xp[nv], xm[nv], 2.0, 2.0);
+          }
+          __syncthreads();
+        } else if (RECON == RECON_LINEAR) {
+          double m1[NV], p1[NV];
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) { m1[nv] = exv[nv * BX + tm]; p1[nv] = exv[nv * BX + tp]; }
+          plm_rt<NV>(a.limiter, m1, vx, p1, xp, xm);
+        } else {
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) xp[nv] = xm[nv] = vx[nv];
+        }
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) exm[nv * BX + t] = xm[nv];
+        __syncthreads();
+        double xr[NV];
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) xr[nv] = exm[nv * BX + tp];
+        Face<NV> Gp;
+        double machx = 0.0;
+        riemann<NV, SOLVER>(xp, xr, d.gas, Gp, machx);
+        if (t >= LO - 1 && t < BX - HI && i >= d.beg[0] - 1 && i <= d.end[0]) mach = fmax(mach, machx);
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) exf[nv * BX + t] = Gp.f[nv];
+        exf[NV * BX + t] = Gp.prs;
+        exf[(NV + 1) * BX + t] = Gp.cmax;
+        __syncthreads();
+        if (own) {
+          const double idx1 = d.inv_dx[0][i];
+          const double dtdx1 = dt * idx1;
+          double ux[NV];
+          prim2cons<NV>(vx, ux, d.gas);
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) ux[nv] += -dtdx1 * (Gp.f[nv] - exf[nv * BX + tm]);
+          ux[iVN] -= dtdx1 * (Gp.prs - exf[NV * BX + tm]);
+          cx = 0.5 * (exf[(NV + 1) * BX + tm] + Gp.cmax) * idx1;
+#pragma unroll
+          for (int c = 0; c < NV; c++) U[c] = ux[gvar<DIR>(c)];   // back to DIR-local order
+        }
+      } else if (first && own) {
+        prim2cons<NV>(vm1, U, d.gas);
+      }
+
+      if (own && n >= cb + 1) {
+        // ---- finish zone z: add this direction, combine, cons->prim ----
+        const double inv_dl = inv_dx[z];
+        const double dtdx = dt * inv_dl;
+        const long oz = base + (long)z * st;
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) U[nv] += -dtdx * (Fp.f[nv] - Fm.f[nv]);
+        U[iVN] -= dtdx * (Fp.prs - Fm.prs);
+        if (last) {
+          if (use_v0) {
+            double U0[NV];
+            prim2cons<NV>(v0z, U0, d.gas);
+            if (a.comb == 1) {
+#pragma unroll
+              for (int nv = 0; nv < NV; nv++) U[nv] = a.w0 * U0[nv] + a.wc * U[nv];
+            } else {
+              const double one_third = 1.0 / 3.0;
+#pragma unroll
+              for (int nv = 0; nv < NV; nv++) U[nv] = one_third * (U0[nv] + 2.0 * U[nv]);
+            }
+          }
+          double vn[NV];
+          int fl = cons2prim<NV>(U, vn, d.gas);
+          if (fl) atomicAdd(a.red + 2, 1ull);
+          store_zone<DIR, NV>(a.Vout, oz, d.sv, vn);
+        } else {
+          store_zone<DIR, NV>(a.acc, oz, d.sv, U);
+        }
+        if (cdt_on) {
+          double c = 0.5 * (Fm.cmax + Fp.cmax) * inv_dl;
+          if (FUSEX) c = cx + c;
+          else if (!first) c = cin + c;
+          if (last) cdt_max = fmax(cdt_max, c);
+          else a.cdt[oz] = c;
+        }
       }
     }
+    if (n >= cb) Fm = Fp;
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      vpL[nv] = vp[nv];
+      vm1[nv] = v0[nv];
+      v0[nv] = vp1[nv];
+    }
   }
-  block_reduce_max2(cdt_max, mach, a.stage == 1 && a.last, a.red);
+  cp_async_wait<0>();
+  block_reduce_max2(cdt_max, mach, a.stage == 1 && last, a.red);
 }
 
 // ------------------------------------------------------------------------------------
