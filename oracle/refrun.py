@@ -75,12 +75,12 @@ def read_dbl(path, nvar, shape):
 
 
 def run(cfg, workdir, *, shape, nvar=5, maxsteps=None, no_write=False, extra_args=(),
-        timeout=3600, **ini):
+        timeout=3600, exe=None, env=None, **ini):
     """Run oracle/_ref/<cfg>/pluto in `workdir` with a generated pluto.ini.
 
     shape = (nz, ny, nx) interior zones.  Returns dict(steps=[(nstep,t,dt)], data=[arrays],
     wall=seconds, log=stdout)."""
-    exe = REFDIR / cfg / "pluto"
+    exe = Path(exe) if exe is not None else REFDIR / cfg / "pluto"
     if not exe.exists():
         raise FileNotFoundError("%s missing: run `python oracle/build_ref.py %s`" % (exe, cfg))
     wd = Path(workdir)
@@ -97,7 +97,7 @@ def run(cfg, workdir, *, shape, nvar=5, maxsteps=None, no_write=False, extra_arg
     if no_write:
         cmd += ["-no-write"]
     cmd += list(extra_args)
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", **(env or {}))
     t0 = time.perf_counter()
     r = subprocess.run(cmd, cwd=wd, capture_output=True, text=True, timeout=timeout, env=env)
     wall = time.perf_counter() - t0

@@ -1,0 +1,157 @@
+/* pluto_shim.c -- the reference-side binding of libplutob200.so.
+ *
+ * Compiled TOGETHER WITH THE REFERENCE (it includes the reference's own pluto.h and the
+ * problem's definitions.h) and linked INSTEAD OF Src/Time_Stepping/rk_step.o, so that every
+ * other reference object - main(), the pluto.ini parser, set_grid, init.c, output - stays
+ * unmodified.  It replaces exactly one symbol:
+ *
+ *     int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)      Src/prototypes.h:5
+ *                                                               Src/Time_Stepping/rk_step.c:29
+ *
+ * Modes (environment):
+ *   default            strict drop-in: d->Vc on the host is authoritative; every call does
+ *                      H2D(d->Vc) -> AdvanceStep on the GPU -> D2H(d->Vc).
+ *   PB200_RESIDENT=1   the state stays in HBM between steps; d->Vc is refreshed only before
+ *                      WriteData()/Analysis() (link with -Wl,--wrap=WriteData,--wrap=Analysis).
+ */
+#include "pluto.h"
+#include "pluto_b200.h"
+
+static pb200_ctx *s_ctx = NULL;
+static int s_resident = 0, s_dirty = 0;
+
+static int translate_limiter(void) {
+#ifdef LIMITER
+#if LIMITER == DEFAULT
+  return PB200_LIM_DEFAULT;
+#elif LIMITER == FLAT_LIM
+  return PB200_LIM_FLAT;
+#elif LIMITER == MINMOD_LIM
+  return PB200_LIM_MINMOD;
+#elif LIMITER == VANLEER_LIM
+  return PB200_LIM_VANLEER;
+#elif LIMITER == MC_LIM
+  return PB200_LIM_MC;
+#elif LIMITER == VANALBADA_LIM
+  return PB200_LIM_VANALBADA;
+#elif LIMITER == OSPRE_LIM
+  return PB200_LIM_OSPRE;
+#elif LIMITER == UMIST_LIM
+  return PB200_LIM_UMIST;
+#else
+  return -1;
+#endif
+#else
+  return PB200_LIM_DEFAULT;
+#endif
+}
+
+static void shim_init(Data *d, Grid *grid) {
+  pb200_config cfg;
+  int dir;
+  pb200_config_default(&cfg);
+#if PHYSICS != HD || EOS != IDEAL
+#error "libplutob200: only PHYSICS HD with EOS IDEAL is on the B200 path"
+#endif
+  cfg.dimensions = DIMENSIONS;
+  cfg.geometry   = GEOMETRY;          /* same codes, Src/pluto.h:34-37 */
+  cfg.nghost     = GetNghost();
+  cfg.ntracer    = NTRACER;
+#if RECONSTRUCTION == FLAT
+  cfg.reconstruction = PB200_FLAT;
+#elif RECONSTRUCTION == LINEAR
+  cfg.reconstruction = PB200_LINEAR;
+#elif RECONSTRUCTION == PARABOLIC
+  cfg.reconstruction = PB200_PARABOLIC;
+#else
+#error "libplutob200: RECONSTRUCTION must be FLAT, LINEAR or PARABOLIC"
+#endif
+#if TIME_STEPPING == EULER
+  cfg.time_stepping = PB200_EULER;
+#elif TIME_STEPPING == RK2
+  cfg.time_stepping = PB200_RK2;
+#elif TIME_STEPPING == RK3
+  cfg.time_stepping = PB200_RK3;
+#else
+#error "libplutob200: TIME_STEPPING must be EULER, RK2 or RK3"
+#endif
+  cfg.limiter = translate_limiter();
+  /* SetSolver() stored a function pointer (Src/HD/set_solver.c:4-58) */
+  if      (d->fluidRiemannSolver == &HLLC_Solver) cfg.solver = PB200_HLLC;
+  else if (d->fluidRiemannSolver == &HLL_Solver)  cfg.solver = PB200_HLL;
+  else if (d->fluidRiemannSolver == &LF_Solver)   cfg.solver = PB200_TVDLF;
+  else {
+    print ("! AdvanceStep(): this Riemann solver is not available in libplutob200\n");
+    QUIT_PLUTO(1);
+  }
+  for (dir = 0; dir < 3; dir++) {
+    cfg.nx[dir]   = grid->np_int[dir];
+    cfg.xbeg[dir] = grid->xbeg[dir];
+    cfg.xend[dir] = grid->xend[dir];
+    cfg.bc[2*dir]     = grid->lbound[dir];   /* same codes, Src/pluto.h:163-170 */
+    cfg.bc[2*dir + 1] = grid->rbound[dir];
+  }
+  cfg.gamma          = g_gamma;
+  cfg.small_density  = g_smallDensity;
+  cfg.small_pressure = g_smallPressure;
+  if (getenv("PB200_DEVICE")) cfg.device = atoi(getenv("PB200_DEVICE"));
+  s_resident = getenv("PB200_RESIDENT") && atoi(getenv("PB200_RESIDENT"));
+  if (pb200_create(&cfg, &s_ctx) != PB200_OK) {
+    print ("! AdvanceStep(): pb200_create: %s\n", pb200_last_error());
+    QUIT_PLUTO(1);
+  }
+  for (dir = 0; dir < DIMENSIONS; dir++) {   /* the reference's own grid arrays */
+    if (pb200_set_grid(s_ctx, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir]) != PB200_OK) {
+      print ("! AdvanceStep(): pb200_set_grid: %s\n", pb200_last_error());
+      QUIT_PLUTO(1);
+    }
+  }
+  print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode)\n", pb200_version(),
+         s_resident ? "resident" : "strict host-buffer");
+}
+
+int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
+{
+  pb200_step_info info;
+  int rc;
+  double *vc = d->Vc[0][0][0];   /* contiguous [NVAR][NX3_TOT][NX2_TOT][NX1_TOT], Src/arrays.c:251 */
+
+  if (s_ctx == NULL) {
+    shim_init(d, grid);
+    if (s_resident) pb200_upload_vc(s_ctx, vc);
+  }
+  if (s_resident) {
+    rc = pb200_advance_step(s_ctx, g_dt, &info);
+    s_dirty = 1;
+  } else {
+    rc = pb200_advance_step_host(s_ctx, vc, g_dt, &info);
+  }
+  if (rc != PB200_OK) {
+    print ("! AdvanceStep(): %s\n", pb200_last_error());
+    QUIT_PLUTO(1);
+  }
+  Dts->invDt_hyp = MAX(Dts->invDt_hyp, info.invDt_hyp);   /* update_stage.c:320,391 */
+  g_maxMach      = MAX(g_maxMach, info.maxMach);          /* hll_speed.c:89 */
+  return 0;
+}
+
+/* resident mode: refresh d->Vc just before the reference reads it */
+void pb200_shim_sync_to_host(const Data *d)
+{
+  if (s_ctx != NULL && s_resident && s_dirty) {
+    pb200_download_vc(s_ctx, d->Vc[0][0][0]);
+    s_dirty = 0;
+  }
+}
+void __real_WriteData (const Data *, Output *, Grid *);
+void __wrap_WriteData (const Data *d, Output *output, Grid *grid)
+{
+  pb200_shim_sync_to_host(d);
+  __real_WriteData(d, output, grid);
+}
+void __real_Analysis (const Data *, Grid *);
+void __wrap_Analysis (const Data *d, Grid *grid)
+{
+  pb200_shim_sync_to_host(d);
+  __real_Analysis(d, grid);
+}

@@ -1,0 +1,48 @@
+"""GPU: the real drop-in.  The reference's own executable (main loop, pluto.ini parser, grid,
+init.c, output - all unmodified objects) linked with pluto_shim.c + libplutob200.so in place of
+rk_step.o (integration/build_dropin.py) must write the same data.NNNN.dbl / restart.out as the
+stock reference executable on the same pluto.ini."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import refrun
+from common import TOL_RUN, TOL_STEP, rel_err, rel_l1
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+SOD_BCS = ("outflow", "outflow", "periodic", "periodic", "outflow", "outflow")
+SEDOV = dict(bcs=("reflective", "outflow") * 3, params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4), cfl=0.3,
+             tstop=0.5, first_dt=1e-9)
+CASES = {
+    "sod": dict(shape=(1, 1, 400), grid=[(0, 400, 1), (0, 1, 1), (0, 1, 1)], cfl=0.8, tstop=0.2, first_dt=1e-4,
+                bcs=SOD_BCS, params={"SCRH": 0}, maxsteps=80),
+    "sedov3d": dict(shape=(24, 24, 24), grid=[(0, 24, 1)] * 3, maxsteps=15, **SEDOV),
+    "sedov3d_ppm": dict(shape=(24, 24, 24), grid=[(0, 24, 1)] * 3, maxsteps=10, **SEDOV),
+}
+
+
+@pytest.mark.parametrize("cfg", list(CASES))
+@pytest.mark.parametrize("solver", ["hllc", "hll"])
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_dropin_executable_matches_reference_executable(cuda_lib, tmp_path, cfg, solver, resident):
+    exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
+    if not exe.exists() or not refrun.have_ref(cfg):
+        pytest.skip("drop-in / reference executables were not built in the container (needs /root/reference)")
+    kw = dict(CASES[cfg])
+    ref = refrun.run(cfg, tmp_path / "ref", solver=solver, dbl=(-1.0, 1), **kw)
+    got = refrun.run(cfg, tmp_path / "b200", solver=solver, dbl=(-1.0, 1), exe=exe,
+                     env={"PB200_RESIDENT": resident}, **kw)
+    assert "runs on the GPU" in got["log"]
+    assert len(got["data"]) == len(ref["data"]) and len(ref["data"]) >= 8
+    # identical step numbering, time and dt sequence (NextTimeStep stays the reference's code)
+    for (n1, t1, d1), (n2, t2, d2) in zip(ref["steps"], got["steps"]):
+        assert n1 == n2
+        assert abs(t1 - t2) <= 1e-11 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-10 * d1
+    # the very first step starts from bit-identical data: per-step tolerance
+    assert np.array_equal(ref["data"][0], got["data"][0])
+    assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
+    # end of the run: 1e-9 relative L1
+    assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
