@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/pluto_b200.h"
@@ -277,7 +278,15 @@ extern "C" int pb200_boundary(pb200_ctx *c) {
 }
 
 // ---- sweeps ------------------------------------------------------------------------------
-template <int NV, int RECON, int SOLVER>
+template <typename K>
+static void set_smem(K k, size_t shm) {
+  // high-water mark of the opt-in dynamic shared memory per kernel
+  static std::unordered_map<const void *, size_t> cur;
+  size_t &c = cur[(const void *)k];
+  if (shm > c) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); c = shm; }
+}
+
+template <int NV, int RECON, int SOLVER, int LIM>
 static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   const Dev &D = c->dev;
   const int slot = (c->profiling && c->nprof < 16) ? c->nprof++ : -1;
@@ -296,8 +305,8 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   } else {
     // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
     const bool fusex = (dir == 1);
-    constexpr int XH = (RECON == RECON_PARABOLIC) ? 3 : (RECON == RECON_LINEAR ? 2 : 1);
-    const int use = fusex ? BX - 2 * XH : BX;
+    const bool last = (dir == D.ndim - 1);
+    const int use = fusex ? BX - 2 * recon_xhalo<RECON>() : BX;
     int npen = D.end[dir] - D.beg[dir] + 1;
     int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
     int nbx = (nx + use - 1) / use;
@@ -308,19 +317,22 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     int chunk = (npen + nchunk - 1) / nchunk;
     nchunk = (npen + chunk - 1) / chunk;
     dim3 grid(nbx, ntr, nchunk);
-    const bool first = fusex ? true : (a.first != 0);
-    const bool cdt_in = D.ndim > 1 && a.stage == 1 && !first;
-    const int nq = ring_nq(NV, first, a.last != 0, a.comb, cdt_in);
-    size_t shm = ((size_t)RING * nq * BX + (fusex ? (size_t)(3 * NV + 2) * BX : 0)) * sizeof(double);
-    if (fusex) {
-      auto k = sweep_fused<1, true, NV, RECON, SOLVER>;
-      static size_t cur = 0;
-      if (shm > cur) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); cur = shm; }
+    const bool cdt_in = D.ndim > 1 && a.stage == 1 && !fusex;
+    const int nq = ring_nq(NV, fusex, a.comb, cdt_in);
+    if (fusex && !last) {
+      auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM>;
+      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
+      set_smem(k, shm);
+      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
+    } else if (fusex) {
+      auto k = sweep_fused<1, true, true, NV, RECON, SOLVER, LIM>;
+      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
+      set_smem(k, shm);
       k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
     } else {
-      auto k = sweep_fused<2, false, NV, RECON, SOLVER>;
-      static size_t cur = 0;
-      if (shm > cur) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); cur = shm; }
+      auto k = sweep_fused<2, false, true, NV, RECON, SOLVER, LIM>;
+      size_t shm = sweep_smem_bytes<false, NV, RECON>(nq);
+      set_smem(k, shm);
       k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
     }
   }
@@ -328,12 +340,19 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   c->launches++;
 }
 
+template <int NV, int RECON, int SOLVER>
+static void launch_lim(pb200_ctx *c, int dir, const SweepArgs &a) {
+  // LIMITER DEFAULT is compiled in; any other choice takes the run-time limiter switch
+  if (RECON != RECON_LINEAR || c->cfg.limiter == PB200_LIM_DEFAULT) launch_dir<NV, RECON, SOLVER, LIM_DEFAULT>(c, dir, a);
+  else launch_dir<NV, RECON, SOLVER, LIM_RT>(c, dir, a);
+}
+
 template <int NV, int RECON>
 static void launch_solver(pb200_ctx *c, int dir, const SweepArgs &a) {
   switch (c->cfg.solver) {
-    case PB200_TVDLF: launch_dir<NV, RECON, SOLVER_TVDLF>(c, dir, a); break;
-    case PB200_HLL: launch_dir<NV, RECON, SOLVER_HLL>(c, dir, a); break;
-    default: launch_dir<NV, RECON, SOLVER_HLLC>(c, dir, a); break;
+    case PB200_TVDLF: launch_lim<NV, RECON, SOLVER_TVDLF>(c, dir, a); break;
+    case PB200_HLL: launch_lim<NV, RECON, SOLVER_HLL>(c, dir, a); break;
+    default: launch_lim<NV, RECON, SOLVER_HLLC>(c, dir, a); break;
   }
 }
 
@@ -405,15 +424,10 @@ extern "C" int pb200_stage(pb200_ctx *c, int stage) {
     a.comb = 2;
   }
   if (D.ndim == 1) {
-    a.first = 1; a.last = 1;
     launch_sweep(c, 0, a);
   } else {
-    a.first = 1; a.last = (D.ndim == 2);
-    launch_sweep(c, 1, a);          // x1 + x2 in one kernel
-    if (D.ndim == 3) {
-      a.first = 0; a.last = 1;
-      launch_sweep(c, 2, a);        // x3
-    }
+    launch_sweep(c, 1, a);                    // x1 + x2 in one kernel
+    if (D.ndim == 3) launch_sweep(c, 2, a);   // x3
   }
   CK(cudaGetLastError());
   return PB200_OK;
@@ -440,7 +454,7 @@ extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {
     info->gpu_ms = ms;
     info->launches = c->launches;
   }
-  if (!(invdt > 0.0) || !isfinite(invdt))
+  if (c->h_red[3] != 0ull || !(invdt > 0.0) || !isfinite(invdt))
     return fail(PB200_ENAN, "non-finite or zero signal speed: NaN in the state (CheckNaN)");
   return PB200_OK;
 }

@@ -6,17 +6,20 @@
 //
 // Data layout in HBM (all FP64, i fastest, same as the reference's d->Vc):
 //   V*   [NVAR][NX3_TOT][NX2_TOT][NX1_TOT]  primitive state incl. ghost zones (2 or 3 copies)
-//   acc  [NVAR][...same...]                 conservative accumulator  U + dt*(Rx [+Ry])
+//   acc  [NVAR][...same...]                 conservative accumulator  U + dt*(Rx + Ry)
 //   cdt  [NX3_TOT][NX2_TOT][NX1_TOT]        C_dt partial sums (update_stage.c:314)
 // U0 and Uc of the reference are NOT stored: cons(V) is recomputed in registers from the V
-// that the sweep loads anyway, so a stage moves (stage 1) 40 B in + 40 B out through HBM in
-// 1-D, and V once per direction + one accumulator round trip in 2-D/3-D.
+// that the sweep loads anyway.
 //
-// One kernel per direction; every interface flux and every limited slope is computed ONCE:
-//   x1 sweep  : thread <-> zone along i; L/R states and fluxes are exchanged between
-//               neighbouring threads through shared memory (2 halo threads of 128).
-//   x2/x3 sweep: thread <-> i (coalesced), each thread MARCHES along j (or k) keeping the
-//               stencil, the previous left state and the previous flux in registers.
+// Kernels per RK stage:
+//   1-D : sweep_x1     thread <-> zone along i, neighbours through shared memory
+//   2-D : sweep_fused<1,FUSEX,LAST>   marches along x2, x1 sweep of every finished row fused in
+//   3-D : sweep_fused<1,FUSEX,!LAST>  (x1+x2 -> acc, cdt)  then  sweep_fused<2,!FUSEX,LAST>
+//         (x3 march: acc + Rz, RK combination with cons(V^n), cons->prim, store, C_dt max)
+// Marching sweeps: thread <-> i (coalesced), each thread marches along the sweep direction
+// keeping the zone value, the backward difference, the previous left state and the previous
+// face flux in registers, so every limited slope and every interface flux is computed ONCE.
+// All code inside the marching loop is branch free apart from block-uniform conditions.
 // Accumulation order is the reference's: ((U + Rx) + Ry) + Rz, then w0*U0 + wc*U.
 #pragma once
 #include <cuda_runtime.h>
@@ -45,142 +48,94 @@ struct SweepArgs {
   double *Vout;       // primitive output of the stage (written by the LAST sweep)
   double *cdt;        // C_dt accumulator (stage 1, DIMENSIONS > 1)
   const double *dt;   // device pointer to g_dt
-  unsigned long long *red;  // [0] invDt_hyp bits  [1] maxMach bits  [2] #cons2prim failures
+  unsigned long long *red;  // [0] invDt_hyp bits [1] maxMach bits [2] #cons2prim failures [3] NaN flag
   double w0, wc;
   int comb;    // 0: U ; 1: w0*U0 + wc*U (rk_step.c:236) ; 2: (U0 + 2U)/3 (rk_step.c:304)
-  int first;   // this sweep starts the accumulation: U = cons(V)
-  int last;    // this sweep finishes the stage: combination + cons->prim + store Vout
   int stage;   // g_intStage
   int limiter;
 };
 
 // local (sweep) component c=1,2,3 -> global velocity variable, Src/set_indexes.c:18-110
 template <int DIR>
-__device__ __forceinline__ constexpr int gvar(int c) {
+__host__ __device__ __forceinline__ constexpr int gvar(int c) {
   return c == 0 ? 0 : (c >= 4 ? c : ((c - 1 + DIR) % 3) + 1);
+}
+// inverse: global variable -> sweep-local component
+template <int DIR>
+__host__ __device__ __forceinline__ constexpr int lvar(int v) {
+  return v == 0 ? 0 : (v >= 4 ? v : ((v - 1 - DIR + 3) % 3) + 1);
 }
 
 template <int DIR, int NV>
-__device__ __forceinline__ void load_zone(const double *__restrict__ V, long off, long sv,
-                                          double (&q)[NV]) {
+PB_D void load_zone(const double *__restrict__ V, long off, long sv, double (&q)[NV]) {
 #pragma unroll
   for (int c = 0; c < NV; c++) q[c] = __ldg(V + gvar<DIR>(c) * sv + off);
 }
-template <int DIR, int NV>
-__device__ __forceinline__ void store_zone(double *__restrict__ V, long off, long sv,
-                                           const double (&q)[NV]) {
-#pragma unroll
-  for (int c = 0; c < NV; c++) V[gvar<DIR>(c) * sv + off] = q[c];
-}
 
-__device__ __forceinline__ void atomic_max_pos(unsigned long long *p, double x) {
+PB_D void atomic_max_pos(unsigned long long *p, double x) {
   // valid for x >= 0: IEEE ordering == unsigned integer ordering
   atomicMax(p, (unsigned long long)__double_as_longlong(x));
 }
 
-__device__ __forceinline__ double warp_max(double x) {
+PB_D double warp_max(double x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
   return x;
 }
 
-// block-wide max of two values -> global atomics (one per block)
-__device__ __forceinline__ void block_reduce_max2(double a, double b, bool do_a,
-                                                  unsigned long long *red) {
+// end-of-kernel reduction: block-wide max of (C_dt, Mach), sum of cons2prim failures and the
+// NaN flag -> one atomic each per block
+PB_D void block_reduce(double cdt, double mach, int nfail, int nan, bool do_cdt,
+                       unsigned long long *red) {
   __shared__ double sa[BX / 32], sb[BX / 32];
-  a = warp_max(a);
-  b = warp_max(b);
+  __shared__ int sf[BX / 32], sn[BX / 32];
+  cdt = warp_max(cdt);
+  mach = warp_max(mach);
+  nfail = __reduce_add_sync(0xffffffffu, nfail);
+  nan = __reduce_or_sync(0xffffffffu, nan);
   int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sa[w] = a; sb[w] = b; }
+  if (l == 0) { sa[w] = cdt; sb[w] = mach; sf[w] = nfail; sn[w] = nan; }
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 1; k < BX / 32; k++) { a = fmax(a, sa[k]); b = fmax(b, sb[k]); }
-    if (do_a && a > 0.0) atomic_max_pos(red + 0, a);
-    if (b > 0.0) atomic_max_pos(red + 1, b);
+    for (int k = 1; k < BX / 32; k++) {
+      cdt = fmax(cdt, sa[k]); mach = fmax(mach, sb[k]); nfail += sf[k]; nan |= sn[k];
+    }
+    if (do_cdt && cdt > 0.0) atomic_max_pos(red + 0, cdt);
+    if (mach > 0.0) atomic_max_pos(red + 1, mach);
+    if (nfail) atomicAdd(red + 2, (unsigned long long)nfail);
+    if (nan) atomicOr(red + 3, 1ull);
   }
 }
 
-template <int LIM_RT_DUMMY = 0>
-__device__ __forceinline__ double slope_rt(int lim, int nv, double dp, double dm) {
-  switch (lim) {
-    case LIM_FLAT: return 0.0;
-    case LIM_MINMOD: return lim_mm(dp, dm);
-    case LIM_VANLEER: return lim_vl(dp, dm);
-    case LIM_MC: return lim_mc(dp, dm);
-    case LIM_VANALBADA: return lim_va(dp, dm);
-    case LIM_OSPRE: return lim_os(dp, dm);
-    case LIM_UMIST: return lim_um(dp, dm);
-    default: return plm_slope<LIM_DEFAULT>(nv, dp, dm);
-  }
-}
-
+// RK combination (rk_step.c:236,304) with U0 = cons(V^n); U in any component order
 template <int NV>
-__device__ __forceinline__ void plm_rt(int lim, const double (&vm1)[NV], const double (&v0)[NV],
-                                       const double (&vp1)[NV], double (&vp)[NV],
-                                       double (&vm)[NV]) {
-  if (lim == LIM_DEFAULT) {
-    plm_zone<NV, LIM_DEFAULT>(vm1, v0, vp1, vp, vm);
-  } else {
+PB_D void rk_combine(double (&U)[NV], const double (&v0z)[NV], const Gas &gas, int comb,
+                     double w0, double wc) {
+  double U0[NV];
+  prim2cons<NV>(v0z, U0, gas);
+  if (comb == 1) {
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) {
-      double dvp = vp1[nv] - v0[nv], dvm = v0[nv] - vm1[nv];
-      double dv = slope_rt<>(lim, nv, dvp, dvm);
-      vp[nv] = v0[nv] + dv * 0.5;
-      vm[nv] = v0[nv] - dv * 0.5;
-    }
+    for (int nv = 0; nv < NV; nv++) U[nv] = w0 * U0[nv] + wc * U[nv];
+  } else {
+    const double one_third = 1.0 / 3.0;
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) U[nv] = one_third * (U0[nv] + 2.0 * U[nv]);
   }
 }
 
-// Finish one zone: rhs from the two faces, accumulate, optionally combine + cons->prim.
-// vz = primitive state of the zone (sweep-local order), off = linear zone offset.
-template <int DIR, int NV>
-__device__ __forceinline__ void finish_zone(const Dev &d, const SweepArgs &a, long off,
-                                            const double (&vz)[NV], const Face<NV> &Fm,
-                                            const Face<NV> &Fp, double dtdx, double inv_dl,
-                                            double &cdt_max) {
-  double U[NV];
-  if (a.first) {
-    prim2cons<NV>(vz, U, d.gas);
-  } else {
-    load_zone<DIR, NV>(a.acc, off, d.sv, U);
-  }
-#pragma unroll
-  for (int nv = 0; nv < NV; nv++) U[nv] += -dtdx * (Fp.f[nv] - Fm.f[nv]);
-  U[iVN] -= dtdx * (Fp.prs - Fm.prs);
-
-  if (a.last) {
-    if (a.comb) {
-      double v0[NV], U0[NV];
-      load_zone<DIR, NV>(a.V0, off, d.sv, v0);
-      prim2cons<NV>(v0, U0, d.gas);
-      if (a.comb == 1) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) U[nv] = a.w0 * U0[nv] + a.wc * U[nv];
-      } else {
-        const double one_third = 1.0 / 3.0;
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) U[nv] = one_third * (U0[nv] + 2.0 * U[nv]);
-      }
-    }
-    double vn[NV];
-    int fail = cons2prim<NV>(U, vn, d.gas);
-    if (fail) atomicAdd(a.red + 2, 1ull);
-    store_zone<DIR, NV>(a.Vout, off, d.sv, vn);
-  } else {
-    store_zone<DIR, NV>(a.acc, off, d.sv, U);
-  }
-  // inverse time step, update_stage.c:303-316 (DIMENSIONS > 1, predictor only)
-  if (d.ndim > 1 && a.stage == 1) {
-    double c = 0.5 * (Fm.cmax + Fp.cmax) * inv_dl;
-    if (!a.first) c = a.cdt[off] + c;
-    if (a.last) cdt_max = fmax(cdt_max, c);
-    else a.cdt[off] = c;
-  }
+// RK combination + cons->prim of one zone
+template <int NV>
+PB_D void combine_c2p(double (&U)[NV], const double (&v0z)[NV], const Gas &gas, int comb,
+                      double w0, double wc, double (&vn)[NV], int &nfail, int &nan, bool own) {
+  if (comb) rk_combine<NV>(U, v0z, gas, comb, w0, wc);
+  int fl = cons2prim<NV>(U, vn, gas);
+  nfail += (own && fl != 0) ? 1 : 0;
+  nan |= (own && !(vn[iPRS] == vn[iPRS])) ? 1 : 0;   // any NaN in U ends up in the pressure
 }
 
 // ------------------------------------------------------------------------------------
-//  x1 sweep: thread per zone, neighbour exchange through shared memory
+//  x1 sweep (DIMENSIONS == 1): thread per zone, neighbour exchange through shared memory
 // ------------------------------------------------------------------------------------
 template <int NV, int RECON, int SOLVER>
 __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
@@ -217,10 +172,12 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
     }
     __syncthreads();
   } else if (RECON == RECON_LINEAR) {
-    double m1[NV], p1[NV];
+    double m1[NV], p1[NV], dvp[NV], dvm[NV];
     load_zone<0, NV>(a.V, row + cl(i - 1), d.sv, m1);
     load_zone<0, NV>(a.V, row + cl(i + 1), d.sv, p1);
-    plm_rt<NV>(a.limiter, m1, v0, p1, vp, vm);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { dvp[nv] = p1[nv] - v0[nv]; dvm[nv] = v0[nv] - m1[nv]; }
+    plm_zone<NV, LIM_RT>(v0, dvp, dvm, vp, vm, a.limiter);
   } else {
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) vp[nv] = vm[nv] = v0[nv];
@@ -236,10 +193,10 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
   __syncthreads();
 
   Face<NV> Fp, Fm;
-  double mach = 0.0;
-  riemann<NV, SOLVER>(vp, vR, d.gas, Fp, mach);
+  Ratio mach;
+  mach.init();
   const bool face_ok = (t >= LO - 1) && (t <= BX - 2) && (i >= d.beg[0] - 1) && (i <= d.end[0]);
-  if (!face_ok) mach = 0.0;
+  riemann<NV, SOLVER>(vp, vR, d.gas, Fp, mach, face_ok);
 
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) sm[nv][t] = Fp.f[nv];
@@ -253,50 +210,78 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
   Fm.cmax = sm[NV + 1][tm];
 
   double cdt_max = 0.0;
+  int nfail = 0, nan = 0;
   const double inv_dl = d.inv_dx[0][cl(i)];
-  if (t >= LO && t <= BX - 2 && i >= d.beg[0] && i <= d.end[0]) {
-    finish_zone<0, NV>(d, a, row + i, v0, Fm, Fp, dt * inv_dl, inv_dl, cdt_max);
+  const bool own = t >= LO && t <= BX - 2 && i >= d.beg[0] && i <= d.end[0];
+  {
+    const double dtdx = dt * inv_dl;
+    const long off = row + cl(i);
+    double U[NV], vn[NV], v0z[NV];
+    prim2cons<NV>(v0, U, d.gas);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) U[nv] += -dtdx * (Fp.f[nv] - Fm.f[nv]);
+    U[iVN] -= dtdx * (Fp.prs - Fm.prs);
+    if (a.comb) load_zone<0, NV>(a.V0, off, d.sv, v0z);
+    combine_c2p<NV>(U, v0z, d.gas, a.comb, a.w0, a.wc, vn, nfail, nan, own);
+    if (own) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) a.Vout[nv * d.sv + off] = vn[nv];
+    }
   }
-  if (d.ndim == 1) {  // update_stage.c:317-322: every stage, faces IBEG-1..IEND
-    if (face_ok) cdt_max = Fp.cmax * inv_dl;
-  }
-  const bool want_dt = (d.ndim == 1) || (a.stage == 1 && a.last);
-  block_reduce_max2(cdt_max, mach, want_dt, a.red);
+  // update_stage.c:317-322: every stage, faces IBEG-1..IEND
+  if (face_ok) cdt_max = Fp.cmax * inv_dl;
+  block_reduce(cdt_max, mach.value(), nfail, nan, true, a.red);
 }
 
 // ------------------------------------------------------------------------------------
 //  marching sweeps (x2 / x3) with an asynchronous prefetch ring, optionally fused with x1
 // ------------------------------------------------------------------------------------
-// thread <-> i (coalesced); each thread marches along direction DIR keeping the stencil, the
-// previous left state and the previous flux in registers.  Every global read of the loop goes
-// through a per-thread ring in shared memory filled by cp.async (LDGSTS) DEPTH iterations
-// ahead, so HBM latency is covered by a handful of warps per SM without spending registers.
-// With FUSEX the kernel also performs the x1 sweep of every finished row: the three
-// neighbour exchanges (centre states, right states, fluxes) go through shared memory, so
-// the x1 and x2 updates of a stage share ONE read of V and ONE write of the accumulator.
-constexpr int RING = 4;    // ring slots
+// Every global read of the loop goes through a ring in shared memory filled by cp.async
+// (LDGSTS) DEPTH iterations ahead, so HBM latency is covered by a handful of warps per SM
+// without spending registers.  With FUSEX the kernel also performs the x1 sweep of every
+// finished row: neighbours' zone values are read straight from the ring (the rows stay
+// resident two iterations longer), right states and fluxes are exchanged through two small
+// shared arrays (2 barriers per row), so the x1 and x2 updates of a stage share ONE read of V
+// and ONE write of the accumulator.
 constexpr int DEPTH = 3;   // cp.async groups in flight
 
-__device__ __forceinline__ void cp_async8(double *sdst, const double *gsrc) {
+PB_D void cp_async8(double *sdst, const double *gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+PB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+PB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int RECON>
+__host__ __device__ constexpr int recon_lead() { return RECON == RECON_PARABOLIC ? 2 : 1; }
+template <int RECON>
+__host__ __device__ constexpr int recon_xhalo() {
+  return RECON == RECON_PARABOLIC ? 3 : (RECON == RECON_LINEAR ? 2 : 1);
+}
+template <bool FUSEX, int RECON>
+__host__ __device__ constexpr int ring_slots() {
+  return FUSEX ? DEPTH + recon_lead<RECON>() + 2 : DEPTH + 1;
+}
 // number of ring quantities a sweep needs (host and device must agree)
-__host__ __device__ inline int ring_nq(int nv, bool first, bool last, int comb, bool cdt_in) {
-  return nv + (first ? 0 : nv) + ((last && comb) ? nv : 0) + (cdt_in ? 1 : 0);
+__host__ __device__ inline int ring_nq(int nv, bool first, int comb, bool cdt_in) {
+  return nv + (first ? 0 : nv) + ((first && comb) ? nv : 0) + (cdt_in ? 1 : 0);
+}
+template <bool FUSEX, int NV, int RECON>
+__host__ __device__ inline size_t sweep_smem_bytes(int nq) {
+  return ((size_t)ring_slots<FUSEX, RECON>() * nq * BX + (FUSEX ? (size_t)(2 * NV + 2) * BX : 0)) *
+         sizeof(double);
 }
 
-template <int DIR, bool FUSEX, int NV, int RECON, int SOLVER>
+template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM>
 __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
-  constexpr int LEAD = (RECON == RECON_PARABOLIC) ? 2 : 1;
-  constexpr int XH = (RECON == RECON_PARABOLIC) ? 3 : (RECON == RECON_LINEAR ? 2 : 1);
+  constexpr int LEAD = recon_lead<RECON>();
+  constexpr int XH = recon_xhalo<RECON>();
   constexpr int LO = FUSEX ? XH : 0, HI = FUSEX ? XH : 0;
   constexpr int USE = BX - LO - HI;
+  constexpr int RING = ring_slots<FUSEX, RECON>();
+  constexpr bool FIRST = FUSEX;   // the x1(+x2) kernel starts the accumulation: U = cons(V)
   extern __shared__ double smem[];
 
   const int t = threadIdx.x;
@@ -310,227 +295,240 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
   const int ce = min(cb + chunk - 1, d.end[DIR]);
   const double dt = *a.dt;
   const double *__restrict__ inv_dx = d.inv_dx[DIR];
+  const int lim = a.limiter;
 
-  const bool first = FUSEX ? true : (a.first != 0);
-  const bool last = a.last != 0;
-  const bool use_v0 = last && a.comb != 0;
+  // The RK combination with U0 = cons(V^n) is applied by the kernel that STARTS the
+  // accumulation (it is compute bound and has HBM bandwidth to spare for the extra read of
+  // V^n):  acc = w0 U0 + wc (U + Rx + Ry);  the x3 kernel then adds wc Rz.
+  const int comb = a.comb;
+  const bool use_v0 = FIRST && comb != 0;
+  const double wscale = (FIRST || comb == 0) ? 1.0 : (comb == 1 ? a.wc : 2.0 / 3.0);
   const bool cdt_on = d.ndim > 1 && a.stage == 1;
-  const bool cdt_in = cdt_on && !first;
-  const int qA = NV, q0 = qA + (first ? 0 : NV), qC = q0 + (use_v0 ? NV : 0);
+  const bool cdt_in = cdt_on && !FIRST;
+  const int qA = NV, q0 = qA + (FIRST ? 0 : NV), qC = q0 + (use_v0 ? NV : 0);
   const int nq = qC + (cdt_in ? 1 : 0);
-  double *ring = smem;                                  // [RING][nq][BX]
-  double *exv = smem + RING * nq * BX;                  // FUSEX: [NV][BX] centre states
-  double *exm = exv + NV * BX;                          //        [NV][BX] right states (vm)
+  const int slot_sz = nq * BX;
+  double *ring = smem + t;                              // [RING][nq][BX]
+  double *exm = smem + RING * slot_sz;                  // FUSEX: [NV][BX] right states (vm)
   double *exf = exm + NV * BX;                          //        [NV+2][BX] fluxes, prs, cmax
 
-  const int n0 = cb - 1;  // first zone to reconstruct
-  auto issue = [&](int m) {  // prefetch the global data iteration m will consume
+  const int n0 = cb - LEAD;  // first iteration: consumes V row cb, so the ring holds rows >= cb
+  // iteration m consumes V row m+LEAD and the stored quantities of zone m-1
+  auto issue = [&](int m, int s) {
     if (m <= ce + 1) {
-      double *slot = ring + ((m - n0) % RING) * nq * BX + t;
+      double *slot = ring + s * slot_sz;
       const long oV = base + (long)(m + LEAD) * st;
 #pragma unroll
       for (int c = 0; c < NV; c++) cp_async8(slot + c * BX, a.V + gvar<DIR>(c) * d.sv + oV);
       const int z = m - 1;
       if (z >= cb && own) {
         const long oz = base + (long)z * st;
-        if (!first) {
+        if (!FIRST) {
 #pragma unroll
-          for (int c = 0; c < NV; c++) cp_async8(slot + (qA + c) * BX, a.acc + gvar<DIR>(c) * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(slot + (qA + v) * BX, a.acc + v * d.sv + oz);
         }
         if (use_v0) {
 #pragma unroll
-          for (int c = 0; c < NV; c++) cp_async8(slot + (q0 + c) * BX, a.V0 + gvar<DIR>(c) * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(slot + (q0 + v) * BX, a.V0 + v * d.sv + oz);
         }
         if (cdt_in) cp_async8(slot + qC * BX, a.cdt + oz);
       }
     }
     cp_async_commit();
   };
+  auto wrap = [](int s) { return s >= RING ? s - RING : s; };
 
-  double mach = 0.0, cdt_max = 0.0;
-  double vm1[NV], v0[NV], vp1[NV], vp2[NV];
-  double vpL[NV], vp[NV], vm[NV];
-  double qm[NV];  // PPM: interface value at n-1/2
-  Face<NV> Fm, Fp;
+  Ratio mach;
+  mach.init();
+  double cdt_max = 0.0;
+  int nfail = 0, nan = 0;
+  double v0[NV], dvm[NV];          // PLM/FLAT carry: zone n and its backward difference
+  double vm1[NV], vp1[NV], qm[NV]; // PPM carry: zones n-1, n+1, interface value at n-1/2
+  double vpL[NV];                  // left state of face n-1/2 (= vp of zone n-1)
+  Face<NV> Fm;                     // face n-3/2
 
 #pragma unroll
-  for (int g = 0; g < DEPTH; g++) issue(n0 + g);
-  if (RECON == RECON_PARABOLIC) {
-    double a0[NV];
-    load_zone<DIR, NV>(a.V, base + (long)(cb - 3) * st, d.sv, a0);
-    load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
-    load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
-    load_zone<DIR, NV>(a.V, base + (long)(cb)*st, d.sv, vp1);
+  for (int g = 0; g < DEPTH; g++) issue(n0 + g, g);
+  {
+    double b0[NV];
+    load_zone<DIR, NV>(a.V, base + (long)(n0 - 1) * st, d.sv, b0);
+    load_zone<DIR, NV>(a.V, base + (long)n0 * st, d.sv, v0);
+    if (RECON == RECON_PARABOLIC) {
+      // iteration n0 = cb-2 only builds the interface value at cb-3/2; its own states
+      // (which would need row cb-4) are never used, so qm may hold anything finite
+      load_zone<DIR, NV>(a.V, base + (long)(n0 + 1) * st, d.sv, vp1);
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) qm[nv] = ppm4_iface(a0[nv], vm1[nv], v0[nv], vp1[nv]);
-  } else {
-    load_zone<DIR, NV>(a.V, base + (long)(cb - 2) * st, d.sv, vm1);
-    load_zone<DIR, NV>(a.V, base + (long)(cb - 1) * st, d.sv, v0);
+      for (int nv = 0; nv < NV; nv++) { vm1[nv] = b0[nv]; qm[nv] = v0[nv]; }
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) dvm[nv] = v0[nv] - b0[nv];
+    }
   }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) { vpL[nv] = v0[nv]; Fm.f[nv] = 0.0; }
+  Fm.prs = 0.0;
+  Fm.cmax = 0.0;
 
+  int sc = 0;  // ring slot consumed by this iteration
+#pragma unroll 2
   for (int n = n0; n <= ce + 1; n++) {
     // ---- data of this iteration has landed in the ring; refill the slot DEPTH ahead ----
     cp_async_wait<DEPTH - 1>();
-    const double *slot = ring + ((n - n0) % RING) * nq * BX + t;
+    const double *slot = ring + sc * slot_sz;
     double vin[NV];
 #pragma unroll
     for (int c = 0; c < NV; c++) vin[c] = slot[c * BX];
-    const int z = n - 1;  // zone finished by this iteration
-    const bool fin = z >= cb;  // block-uniform
-    double U[NV], v0z[NV], cin = 0.0;
-    if (fin && own) {
-      if (!first) {
+    const int z = n - 1;          // zone finished by this iteration
+    const bool fin = n >= cb + 1;  // block-uniform
+    double U[NV], v0z[NV], cin = 0.0;   // U, v0z: GLOBAL variable order
+    if (fin) {
+      if (!FIRST) {
 #pragma unroll
-        for (int c = 0; c < NV; c++) U[c] = slot[(qA + c) * BX];
+        for (int v = 0; v < NV; v++) U[v] = slot[(qA + v) * BX];
       }
       if (use_v0) {
 #pragma unroll
-        for (int c = 0; c < NV; c++) v0z[c] = slot[(q0 + c) * BX];
+        for (int v = 0; v < NV; v++) v0z[v] = slot[(q0 + v) * BX];
       }
       if (cdt_in) cin = slot[qC * BX];
     }
-    issue(n + DEPTH);
+    const double inv_dl = __ldg(inv_dx + max(z, 0));
+    issue(n + DEPTH, wrap(sc + DEPTH));
 
     // ---- reconstruct zone n along DIR ----
+    double vp[NV], vm[NV];
     if (RECON == RECON_PARABOLIC) {
-      if (n > n0) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) vp1[nv] = vp2[nv];
-      }
+      // rows: vm1 = n-1, v0 = n, vp1 = n+1, vin = n+2
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) {
-        vp2[nv] = vin[nv];
-        double q = ppm4_iface(vm1[nv], v0[nv], vp1[nv], vp2[nv]);
+        double q = ppm4_iface(vm1[nv], v0[nv], vp1[nv], vin[nv]);
         vp[nv] = q;
         vm[nv] = qm[nv];
         qm[nv] = q;
         ppm_parabola(v0[nv], vp[nv], vm[nv], 2.0, 2.0);
       }
     } else if (RECON == RECON_LINEAR) {
+      double dvp[NV];
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) vp1[nv] = vin[nv];
-      plm_rt<NV>(a.limiter, vm1, v0, vp1, vp, vm);
+      for (int nv = 0; nv < NV; nv++) dvp[nv] = vin[nv] - v0[nv];
+      plm_zone<NV, LIM>(v0, dvp, dvm, vp, vm, lim);
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) dvm[nv] = dvp[nv];
     } else {
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) { vp1[nv] = vin[nv]; vp[nv] = vm[nv] = v0[nv]; }
+      for (int nv = 0; nv < NV; nv++) vp[nv] = vm[nv] = v0[nv];
     }
 
-    // ---- face n-1/2 along DIR ----
-    if (n >= cb && own) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach);
+    // ---- face n-1/2 along DIR (result unused before n = cb) ----
+    // With FUSEX the call is placed between the two barriers of the x1 sweep, next to the x1
+    // Riemann problem: two independent dependency chains for the scheduler to interleave.
+    Face<NV> Fp;
+    if (!FUSEX || !fin) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own && n >= cb);
 
     if (fin) {
       double cx = 0.0;
       if (FUSEX) {
-        // ---- x1 sweep of row z: thread <-> zone, neighbours through shared memory ----
-        double vx[NV];  // this zone in x1 (= global) component order
-#pragma unroll
-        for (int c = 0; c < NV; c++) vx[gvar<DIR>(c)] = vm1[c];
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) exv[nv * BX + t] = vx[nv];
-        __syncthreads();
+        // ---- x1 sweep of row z: thread <-> zone; neighbours' values straight from the ring
+        int sz = sc - (1 + LEAD);
+        sz = sz < 0 ? sz + RING : sz;
+        const double *rz = smem + sz * slot_sz;   // row z, all threads
         const int tm = t > 0 ? t - 1 : 0, tp = t < BX - 1 ? t + 1 : BX - 1;
-        double xp[NV], xm[NV];
+        double vx[NV], xp[NV], xm[NV];            // x1-local = global component order
+#pragma unroll
+        for (int v = 0; v < NV; v++) vx[v] = rz[lvar<DIR>(v) * BX + t];
         if (RECON == RECON_PARABOLIC) {
           const int tp2 = t < BX - 2 ? t + 2 : BX - 1;
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) {
-            xp[nv] = ppm4_iface(exv[nv * BX + tm], vx[nv], exv[nv * BX + tp], exv[nv * BX + tp2]);
-            exm[nv * BX + t] = xp[nv];   // interface value at t+1/2
+          for (int v = 0; v < NV; v++) {
+            const double *r = rz + lvar<DIR>(v) * BX;
+            xp[v] = ppm4_iface(r[tm], vx[v], r[tp], r[tp2]);
+            exm[v * BX + t] = xp[v];   // interface value at t+1/2
           }
           __syncthreads();
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) {
-            xm[nv] = exm[nv * BX + tm];
-            ppm_parabola(vx[nv], xp[nv], xm[nv], 2.0, 2.0);
+          for (int v = 0; v < NV; v++) {
+            xm[v] = exm[v * BX + tm];
+            ppm_parabola(vx[v], xp[v], xm[v], 2.0, 2.0);
           }
           __syncthreads();
         } else if (RECON == RECON_LINEAR) {
-          double m1[NV], p1[NV];
+          double dp[NV], dm[NV];
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) { m1[nv] = exv[nv * BX + tm]; p1[nv] = exv[nv * BX + tp]; }
-          plm_rt<NV>(a.limiter, m1, vx, p1, xp, xm);
+          for (int v = 0; v < NV; v++) {
+            const double *r = rz + lvar<DIR>(v) * BX;
+            dp[v] = r[tp] - vx[v];
+            dm[v] = vx[v] - r[tm];
+          }
+          plm_zone<NV, LIM>(vx, dp, dm, xp, xm, lim);
         } else {
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) xp[nv] = xm[nv] = vx[nv];
+          for (int v = 0; v < NV; v++) xp[v] = xm[v] = vx[v];
         }
 #pragma unroll
-        for (int nv = 0; nv < NV; nv++) exm[nv * BX + t] = xm[nv];
+        for (int v = 0; v < NV; v++) exm[v * BX + t] = xm[v];
         __syncthreads();
         double xr[NV];
 #pragma unroll
-        for (int nv = 0; nv < NV; nv++) xr[nv] = exm[nv * BX + tp];
+        for (int v = 0; v < NV; v++) xr[v] = exm[v * BX + tp];
         Face<NV> Gp;
-        double machx = 0.0;
-        riemann<NV, SOLVER>(xp, xr, d.gas, Gp, machx);
-        if (t >= LO - 1 && t < BX - HI && i >= d.beg[0] - 1 && i <= d.end[0]) mach = fmax(mach, machx);
+        const bool xface = t >= LO - 1 && t < BX - HI && i >= d.beg[0] - 1 && i <= d.end[0];
+        riemann<NV, SOLVER>(xp, xr, d.gas, Gp, mach, xface);
+        riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own);
 #pragma unroll
-        for (int nv = 0; nv < NV; nv++) exf[nv * BX + t] = Gp.f[nv];
+        for (int v = 0; v < NV; v++) exf[v * BX + t] = Gp.f[v];
         exf[NV * BX + t] = Gp.prs;
         exf[(NV + 1) * BX + t] = Gp.cmax;
         __syncthreads();
-        if (own) {
-          const double idx1 = d.inv_dx[0][i];
-          const double dtdx1 = dt * idx1;
-          double ux[NV];
-          prim2cons<NV>(vx, ux, d.gas);
+        const double idx1 = __ldg(d.inv_dx[0] + ic);
+        const double dtdx1 = dt * idx1;
+        prim2cons<NV>(vx, U, d.gas);
 #pragma unroll
-          for (int nv = 0; nv < NV; nv++) ux[nv] += -dtdx1 * (Gp.f[nv] - exf[nv * BX + tm]);
-          ux[iVN] -= dtdx1 * (Gp.prs - exf[NV * BX + tm]);
-          cx = 0.5 * (exf[(NV + 1) * BX + tm] + Gp.cmax) * idx1;
-#pragma unroll
-          for (int c = 0; c < NV; c++) U[c] = ux[gvar<DIR>(c)];   // back to DIR-local order
-        }
-      } else if (first && own) {
-        prim2cons<NV>(vm1, U, d.gas);
+        for (int v = 0; v < NV; v++) U[v] += -dtdx1 * (Gp.f[v] - exf[v * BX + tm]);
+        U[iVN] -= dtdx1 * (Gp.prs - exf[NV * BX + tm]);
+        cx = 0.5 * (exf[(NV + 1) * BX + tm] + Gp.cmax) * idx1;
       }
 
-      if (own && n >= cb + 1) {
-        // ---- finish zone z: add this direction, combine, cons->prim ----
-        const double inv_dl = inv_dx[z];
-        const double dtdx = dt * inv_dl;
-        const long oz = base + (long)z * st;
+      // ---- finish zone z: add this direction, combine, cons->prim ----
+      const double dtdx = dt * inv_dl * wscale;
+      const long oz = base + (long)z * st;
 #pragma unroll
-        for (int nv = 0; nv < NV; nv++) U[nv] += -dtdx * (Fp.f[nv] - Fm.f[nv]);
-        U[iVN] -= dtdx * (Fp.prs - Fm.prs);
-        if (last) {
-          if (use_v0) {
-            double U0[NV];
-            prim2cons<NV>(v0z, U0, d.gas);
-            if (a.comb == 1) {
+      for (int c = 0; c < NV; c++) U[gvar<DIR>(c)] += -dtdx * (Fp.f[c] - Fm.f[c]);
+      U[gvar<DIR>(iVN)] -= dtdx * (Fp.prs - Fm.prs);
+      if (LAST) {
+        double vn[NV];
+        combine_c2p<NV>(U, v0z, d.gas, FIRST ? comb : 0, a.w0, a.wc, vn, nfail, nan, own);
+        if (own) {
 #pragma unroll
-              for (int nv = 0; nv < NV; nv++) U[nv] = a.w0 * U0[nv] + a.wc * U[nv];
-            } else {
-              const double one_third = 1.0 / 3.0;
-#pragma unroll
-              for (int nv = 0; nv < NV; nv++) U[nv] = one_third * (U0[nv] + 2.0 * U[nv]);
-            }
-          }
-          double vn[NV];
-          int fl = cons2prim<NV>(U, vn, d.gas);
-          if (fl) atomicAdd(a.red + 2, 1ull);
-          store_zone<DIR, NV>(a.Vout, oz, d.sv, vn);
-        } else {
-          store_zone<DIR, NV>(a.acc, oz, d.sv, U);
+          for (int v = 0; v < NV; v++) a.Vout[v * d.sv + oz] = vn[v];
         }
-        if (cdt_on) {
-          double c = 0.5 * (Fm.cmax + Fp.cmax) * inv_dl;
-          if (FUSEX) c = cx + c;
-          else if (!first) c = cin + c;
-          if (last) cdt_max = fmax(cdt_max, c);
-          else a.cdt[oz] = c;
+      } else {
+        if (use_v0) rk_combine<NV>(U, v0z, d.gas, comb, a.w0, a.wc);
+        if (own) {
+#pragma unroll
+          for (int v = 0; v < NV; v++) a.acc[v * d.sv + oz] = U[v];
         }
       }
+      if (cdt_on) {
+        double c = 0.5 * (Fm.cmax + Fp.cmax) * inv_dl;
+        if (FUSEX) c = cx + c;
+        else if (!FIRST) c = cin + c;
+        if (LAST) cdt_max = fmax(cdt_max, own ? c : 0.0);
+        else if (own) a.cdt[oz] = c;
+      }
+    } else if (FUSEX) {
+      __syncthreads();   // rows landed so far become visible to the neighbours
     }
-    if (n >= cb) Fm = Fp;
+    Fm = Fp;
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) {
       vpL[nv] = vp[nv];
-      vm1[nv] = v0[nv];
-      v0[nv] = vp1[nv];
+      if (RECON == RECON_PARABOLIC) { vm1[nv] = v0[nv]; v0[nv] = vp1[nv]; vp1[nv] = vin[nv]; }
+      else v0[nv] = vin[nv];
     }
+    sc = wrap(sc + 1);
   }
   cp_async_wait<0>();
-  block_reduce_max2(cdt_max, mach, a.stage == 1 && last, a.red);
+  block_reduce(cdt_max, mach.value(), nfail, nan, a.stage == 1 && LAST, a.red);
 }
 
 // ------------------------------------------------------------------------------------
