@@ -63,6 +63,11 @@ extern "C" {
 #define PB200_BC_USERDEF      8
 #define PB200_BC_NEIGHBOUR    100
 
+/* BODY_FORCE bits: same values as Src/pluto.h (VECTOR 4, POTENTIAL 8) are NOT assumed; the
+ * shim translates. */
+#define PB200_BF_VECTOR    1
+#define PB200_BF_POTENTIAL 2
+
 #define PB200_OK        0
 #define PB200_EINVAL   -1
 #define PB200_ENODEV   -2
@@ -91,7 +96,8 @@ typedef struct pb200_config {
   double xbeg[3];        /* g_domBeg of this block */
   double xend[3];        /* g_domEnd of this block */
   int device;            /* CUDA device ordinal */
-  int reserved[7];
+  int body_force;        /* BODY_FORCE: 0 NO, PB200_BF_VECTOR, PB200_BF_POTENTIAL or both (pluto.h:76-77) */
+  int reserved[6];
 } pb200_config;
 
 /* What one AdvanceStep leaves in timeStep / globals (Src/structs.h:372, globals.h). */
@@ -120,6 +126,22 @@ int  pb200_shape(const pb200_ctx *ctx, int tot[3], int *nvar);
  * xr-xl); default = uniform from xbeg/xend (Src/set_grid.c:405-412).  Needed before the
  * first step only for non-uniform grids. */
 int  pb200_set_grid(pb200_ctx *ctx, int dir, const double *xl, const double *xr, const double *dx);
+
+/* BODY_FORCE tables.  The reference calls the user's BodyForceVector(v, g, x1, x2, x3) per zone
+ * and sweep (Src/MHD/rhs_source.c:256,367) and BodyForcePotential(x1, x2, x3) at zone centres
+ * and faces (Src/MHD/rhs.c:168-182, rhs_source.c:279,382).  Both are functions of position only
+ * in every configuration on the path, so the caller evaluates them ONCE with the reference's
+ * grid arrays and hands over strided tables:  value(i,j,k) = tab[i*si + j*sj + k*sk], indices
+ * including ghost zones, a stride of 0 meaning "does not depend on that coordinate" (a constant
+ * g is a 1-element table with si=sj=sk=0).  n = number of doubles in tab (copied to the device).
+ *   vector:    comp 0..2 = g[IDIR], g[JDIR], g[KDIR] at (x1[i], x2[j], x3[k])
+ *   potential: where 0 = Phi(x1[i],x2[j],x3[k]);  1,2,3 = Phi at the upper x1 / x2 / x3 face,
+ *              i.e. Phi(x1p[i],x2[j],x3[k]), Phi(x1[i],x2p[j],x3[k]), Phi(x1[i],x2[j],x3p[k]).
+ * Every table that cfg.body_force asks for must be set before the first step. */
+int  pb200_set_body_force_vector(pb200_ctx *ctx, int comp, const double *tab, long n,
+                                 long si, long sj, long sk);
+int  pb200_set_body_force_potential(pb200_ctx *ctx, int where, const double *tab, long n,
+                                    long si, long sj, long sk);
 
 /* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
 int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);

@@ -73,11 +73,16 @@ CONFIGS = {
     # Sedov 2-D Cartesian PLM + RK2   (conf 05 with DIMENSIONS 2)
     "sedov2d": dict(problem="HD/Sedov", defs="definitions_05.h", overrides={"DIMENSIONS": "2"},
                     states="plm"),
-    # C3: Rayleigh-Taylor, PHYSICS HD, BODY_FORCE POTENTIAL, 2-D and 3-D
-    "rt2d": dict(problem="MHD/Rayleigh_Taylor", defs="definitions_04.h", overrides={},
-                 states="plm"),
-    "rt3d": dict(problem="MHD/Rayleigh_Taylor", defs="definitions_04.h",
-                 overrides={"DIMENSIONS": "3"}, states="plm"),
+    # C3: Rayleigh-Taylor with a tracer; user files of THIS repository (oracle/problems/rt:
+    # the reference's Rayleigh_Taylor conf 04 is CHAR_LIMITING + AMR oriented and has no tracer)
+    "rt3d_vec": dict(local="rt", overrides={}, states="plm"),
+    "rt3d_pot": dict(local="rt", overrides={"BODY_FORCE": "POTENTIAL"}, states="plm"),
+    "rt2d_vec": dict(local="rt", overrides={"DIMENSIONS": "2"}, states="plm"),
+    "rt2d_pot": dict(local="rt", overrides={"DIMENSIONS": "2", "BODY_FORCE": "POTENTIAL",
+                                            "LIMITER": "MC_LIM"}, states="plm"),
+    "rt1d_vec": dict(local="rt", overrides={"DIMENSIONS": "1"}, states="plm"),
+    # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
+    "kh3d": dict(local="kh", overrides={}, states="plm"),
 }
 
 
@@ -101,7 +106,11 @@ def find_source(name: str, paths: list[Path]) -> Path:
 
 def build(cfg_name: str, force: bool = False, verbose: bool = False) -> Path:
     cfg = CONFIGS[cfg_name]
-    problem_dir = REF / "Test_Problems" / cfg["problem"]
+    if "local" in cfg:   # user files written for this repository (init.c, definitions.h)
+        problem_dir = HERE / "problems" / cfg["local"]
+        cfg = dict(cfg, defs="definitions.h")
+    else:
+        problem_dir = REF / "Test_Problems" / cfg["problem"]
     wd = OUT / cfg_name
     exe = wd / "pluto"
     if exe.exists() and not force:

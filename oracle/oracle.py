@@ -23,7 +23,8 @@ class Cfg(C.Structure):
     _fields_ = [("ndim", C.c_int), ("nx", C.c_int * 3), ("ng", C.c_int), ("nvar", C.c_int),
                 ("recon", C.c_int), ("limiter", C.c_int), ("rk", C.c_int), ("solver", C.c_int),
                 ("bc", C.c_int * 6), ("gamma", C.c_double), ("small_dn", C.c_double),
-                ("small_pr", C.c_double), ("xbeg", C.c_double * 3), ("xend", C.c_double * 3), ("dx", C.c_double * 3)]
+                ("small_pr", C.c_double), ("xbeg", C.c_double * 3), ("xend", C.c_double * 3), ("dx", C.c_double * 3),
+                ("body_force", C.c_int), ("bf_g", C.c_void_p * 3), ("bf_phi", C.c_void_p * 4)]
 
 
 def build(force=False):
@@ -70,7 +71,7 @@ class Oracle:
     def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, small_density=1e-12,
-                 small_pressure=1e-12, dx=None, **_):
+                 small_pressure=1e-12, dx=None, body_force=0, **_):
         c = Cfg()
         c.ndim = dimensions
         for d in range(3):
@@ -97,7 +98,22 @@ class Oracle:
         self.beg = tuple(c.ng if d < dimensions else 0 for d in range(3))
         self.tot = tuple(self.nx[d] + 2 * self.beg[d] for d in range(3))
         self.nvar = c.nvar
+        self.xbeg = tuple(xbeg)
+        self.xend = tuple(xend)
         self.shape = (self.nvar, self.tot[2], self.tot[1], self.tot[0])
+        c.body_force = body_force
+        self._bf = {}
+
+    # BODY_FORCE tables: full [k][j][i] arrays incl. ghosts (broadcast from whatever shape)
+    def set_body_force_vector(self, comp, tab):
+        a = np.ascontiguousarray(np.broadcast_to(tab, self.shape[1:]), dtype=np.float64)
+        self._bf[("g", comp)] = a
+        self.c.bf_g[comp] = a.ctypes.data
+
+    def set_body_force_potential(self, where, tab):
+        a = np.ascontiguousarray(np.broadcast_to(tab, self.shape[1:]), dtype=np.float64)
+        self._bf[("phi", where)] = a
+        self.c.bf_phi[where] = a.ctypes.data
 
     def interior(self):
         sl = [slice(None)]

@@ -26,7 +26,8 @@ class Config(C.Structure):
                 ("limiter", C.c_int), ("time_stepping", C.c_int), ("solver", C.c_int),
                 ("bc", C.c_int * 6), ("gamma", C.c_double), ("small_density", C.c_double),
                 ("small_pressure", C.c_double), ("xbeg", C.c_double * 3),
-                ("xend", C.c_double * 3), ("device", C.c_int), ("reserved", C.c_int * 7)]
+                ("xend", C.c_double * 3), ("device", C.c_int), ("body_force", C.c_int),
+                ("reserved", C.c_int * 6)]
 
 
 class StepInfo(C.Structure):
@@ -47,6 +48,8 @@ SYMBOLS = {
     "pb200_destroy": (None, [_P]),
     "pb200_shape": (C.c_int, [_P, C.POINTER(C.c_int * 3), C.POINTER(C.c_int)]),
     "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pb200_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
+    "pb200_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),

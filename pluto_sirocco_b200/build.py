@@ -15,10 +15,15 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libplutob200.so"
-SOURCES = ["pb200.cu"]
-HEADERS = ["hd_physics.cuh", "pb200_kernels.cuh", "../../include/pluto_b200.h"]
+SOURCES = ["pb200.cu", "pb200_sweeps.cu"]
+HEADERS = ["hd_physics.cuh", "pb200_kernels.cuh", "pb200_internal.h", "../../include/pluto_b200.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+# translation units: (object name, source, extra defines).  pb200_sweeps.cu is compiled once per
+# (NVAR, BODY_FORCE) pair so that the kernel instantiations build in parallel.
+UNITS = [("pb200", "pb200.cu", [])] + [
+    ("sweeps_nv%d_bf%d" % (nv, bf), "pb200_sweeps.cu", ["-DPB_NV=%d" % nv, "-DPB_BF=%d" % bf])
+    for nv in (5, 6, 7) for bf in (0, 1)]
 
 
 def _digest() -> str:
@@ -36,15 +41,30 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+
+    def cc(unit):
+        name, src, defs = unit
+        obj = objdir / (name + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed (%s):\n%s%s" % (name, r.stdout, r.stderr))
+        if verbose:
+            print(" ".join(cmd))
+            print(r.stderr)
+        return obj
+
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(cc, UNITS))
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)]
+                       + [str(o) for o in objs], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     stamp.write_text(dig)
     return LIB
 

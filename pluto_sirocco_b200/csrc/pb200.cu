@@ -13,8 +13,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/pluto_b200.h"
-#include "pb200_kernels.cuh"
+#include "pb200_internal.h"
 
 using namespace pb;
 
@@ -29,36 +28,6 @@ static int fail(int code, const std::string &msg) {
     if (e_ != cudaSuccess)                                                              \
       return fail(PB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
   } while (0)
-
-struct pb200_ctx {
-  pb200_config cfg;
-  Dev dev;
-  int nvar;
-  long nzone;        // zones incl. ghosts
-  size_t vbytes;     // bytes of one [nvar] state array
-  double *V[3];      // primitive state copies (A = current d->Vc, B, C)
-  double *acc;       // conservative accumulator (DIMENSIONS > 1)
-  double *cdt;       // C_dt
-  double *d_dt;      // device g_dt
-  unsigned long long *d_red;   // reduction cell: invDt bits, maxMach bits, #fail, NaN flag
-  unsigned long long *h_red;   // pinned
-  double *h_dt;                // pinned
-  double *d_invdx[3];
-  std::vector<double> xl[3], xr[3], dx[3];
-  cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
-  int launches;
-  int cur;           // index of the array holding d->Vc
-  int nstages;
-  int stage_in[4], stage_out[4];  // array indices per stage (1-based)
-  bool in_step;
-  // optional per-kernel timing (pb200_set_profiling)
-  bool profiling;
-  int nprof;
-  cudaEvent_t pev0[16], pev1[16];
-  int pdir[16], pstage[16];
-  float pms[16];
-};
 
 extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
 extern "C" int pb200_version(void) { return PB200_VERSION; }
@@ -93,7 +62,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   *out = nullptr;
   if (cfg->dimensions < 1 || cfg->dimensions > 3) return fail(PB200_EINVAL, "dimensions must be 1..3");
   if (cfg->geometry != PB200_CARTESIAN) return fail(PB200_ENOTSUP, "geometry: only CARTESIAN is built");
-  if (cfg->ntracer != 0) return fail(PB200_ENOTSUP, "ntracer > 0 not built yet");
+  if (cfg->ntracer < 0 || cfg->ntracer > 2) return fail(PB200_ENOTSUP, "ntracer must be 0..2");
+  if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
     return fail(PB200_EINVAL, "bad reconstruction");
   if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_HLLC) return fail(PB200_EINVAL, "bad solver");
@@ -178,6 +148,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
     if (rc) { pb200_destroy(c); return rc; }
     D.inv_dx[d] = c->d_invdx[d];
   }
+  D.bf_kind = cfg->body_force;
+  for (int q = 0; q < 7; q++) { D.bf_tab[q] = nullptr; c->d_bf[q] = nullptr; }
   c->cur = 0;
   c->in_step = false;
   c->launches = 0;
@@ -195,6 +167,7 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->h_dt) cudaFreeHost(c->h_dt);
   for (int d = 0; d < 3; d++) if (c->d_invdx[d]) cudaFree(c->d_invdx[d]);
+  for (int q = 0; q < 7; q++) if (c->d_bf[q]) cudaFree(c->d_bf[q]);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -223,6 +196,32 @@ extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const dou
   }
   CK(cudaSetDevice(c->cfg.device));
   return upload_grid(c, dir);
+}
+
+static int set_bf_table(pb200_ctx *c, int q, const double *tab, long n, long si, long sj, long sk) {
+  if (!c || !tab || n < 1) return fail(PB200_EINVAL, "bad argument");
+  const Dev &D = c->dev;
+  long last = (long)(D.tot[0] - 1) * si + (long)(D.tot[1] - 1) * sj + (long)(D.tot[2] - 1) * sk;
+  if (si < 0 || sj < 0 || sk < 0 || last >= n) return fail(PB200_EINVAL, "body-force table too small for its strides");
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->d_bf[q]) { cudaFree(c->d_bf[q]); c->d_bf[q] = nullptr; }
+  CK(cudaMalloc(&c->d_bf[q], n * sizeof(double)));
+  CK(cudaMemcpy(c->d_bf[q], tab, n * sizeof(double), cudaMemcpyHostToDevice));
+  c->dev.bf_tab[q] = c->d_bf[q];
+  c->dev.bf_st[q][0] = si; c->dev.bf_st[q][1] = sj; c->dev.bf_st[q][2] = sk;
+  return PB200_OK;
+}
+extern "C" int pb200_set_body_force_vector(pb200_ctx *c, int comp, const double *tab, long n, long si,
+                                           long sj, long sk) {
+  if (!c || comp < 0 || comp > 2) return fail(PB200_EINVAL, "bad component");
+  if (!(c->cfg.body_force & PB200_BF_VECTOR)) return fail(PB200_EINVAL, "cfg.body_force has no VECTOR part");
+  return set_bf_table(c, comp, tab, n, si, sj, sk);
+}
+extern "C" int pb200_set_body_force_potential(pb200_ctx *c, int where, const double *tab, long n, long si,
+                                              long sj, long sk) {
+  if (!c || where < 0 || where > 3) return fail(PB200_EINVAL, "bad table selector");
+  if (!(c->cfg.body_force & PB200_BF_POTENTIAL)) return fail(PB200_EINVAL, "cfg.body_force has no POTENTIAL part");
+  return set_bf_table(c, 3 + where, tab, n, si, sj, sk);
 }
 
 extern "C" int pb200_upload_vc(pb200_ctx *c, const double *h) {
@@ -277,91 +276,13 @@ extern "C" int pb200_boundary(pb200_ctx *c) {
   return PB200_OK;
 }
 
-// ---- sweeps ------------------------------------------------------------------------------
-template <typename K>
-static void set_smem(K k, size_t shm) {
-  // high-water mark of the opt-in dynamic shared memory per kernel
-  static std::unordered_map<const void *, size_t> cur;
-  size_t &c = cur[(const void *)k];
-  if (shm > c) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); c = shm; }
-}
-
-template <int NV, int RECON, int SOLVER, int LIM>
-static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
-  const Dev &D = c->dev;
-  const int slot = (c->profiling && c->nprof < 16) ? c->nprof++ : -1;
-  if (slot >= 0) {
-    if (!c->pev0[slot]) { cudaEventCreate(&c->pev0[slot]); cudaEventCreate(&c->pev1[slot]); }
-    c->pdir[slot] = dir;
-    c->pstage[slot] = a.stage;
-    cudaEventRecord(c->pev0[slot], c->stream);
-  }
-  int nx = D.end[0] - D.beg[0] + 1;
-  if (dir == 0) {  // DIMENSIONS == 1 only: plain x1 sweep
-    constexpr int LO = (RECON == RECON_PARABOLIC) ? 2 : 1;
-    constexpr int USE = BX - 1 - LO;
-    dim3 grid((nx + USE - 1) / USE, D.end[1] - D.beg[1] + 1, D.end[2] - D.beg[2] + 1);
-    sweep_x1<NV, RECON, SOLVER><<<grid, BX, 0, c->stream>>>(D, a);
-  } else {
-    // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
-    const bool fusex = (dir == 1);
-    const bool last = (dir == D.ndim - 1);
-    const int use = fusex ? BX - 2 * recon_xhalo<RECON>() : BX;
-    int npen = D.end[dir] - D.beg[dir] + 1;
-    int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
-    int nbx = (nx + use - 1) / use;
-    // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks
-    long want = 148L * 3 * 6;
-    int nchunk = 1;
-    while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
-    int chunk = (npen + nchunk - 1) / nchunk;
-    nchunk = (npen + chunk - 1) / chunk;
-    dim3 grid(nbx, ntr, nchunk);
-    const bool cdt_in = D.ndim > 1 && a.stage == 1 && !fusex;
-    const int nq = ring_nq(NV, fusex, a.comb, cdt_in);
-    if (fusex && !last) {
-      auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
-      set_smem(k, shm);
-      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
-    } else if (fusex) {
-      auto k = sweep_fused<1, true, true, NV, RECON, SOLVER, LIM>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
-      set_smem(k, shm);
-      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
-    } else {
-      auto k = sweep_fused<2, false, true, NV, RECON, SOLVER, LIM>;
-      size_t shm = sweep_smem_bytes<false, NV, RECON>(nq);
-      set_smem(k, shm);
-      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
-    }
-  }
-  if (slot >= 0) cudaEventRecord(c->pev1[slot], c->stream);
-  c->launches++;
-}
-
-template <int NV, int RECON, int SOLVER>
-static void launch_lim(pb200_ctx *c, int dir, const SweepArgs &a) {
-  // LIMITER DEFAULT is compiled in; any other choice takes the run-time limiter switch
-  if (RECON != RECON_LINEAR || c->cfg.limiter == PB200_LIM_DEFAULT) launch_dir<NV, RECON, SOLVER, LIM_DEFAULT>(c, dir, a);
-  else launch_dir<NV, RECON, SOLVER, LIM_RT>(c, dir, a);
-}
-
-template <int NV, int RECON>
-static void launch_solver(pb200_ctx *c, int dir, const SweepArgs &a) {
-  switch (c->cfg.solver) {
-    case PB200_TVDLF: launch_lim<NV, RECON, SOLVER_TVDLF>(c, dir, a); break;
-    case PB200_HLL: launch_lim<NV, RECON, SOLVER_HLL>(c, dir, a); break;
-    default: launch_lim<NV, RECON, SOLVER_HLLC>(c, dir, a); break;
-  }
-}
-
+// ---- sweeps: one launcher per (NVAR, body force), see pb200_sweeps.cu -----------------------
 static void launch_sweep(pb200_ctx *c, int dir, const SweepArgs &a) {
-  switch (c->cfg.reconstruction) {
-    case PB200_FLAT: launch_solver<5, RECON_FLAT>(c, dir, a); break;
-    case PB200_PARABOLIC: launch_solver<5, RECON_PARABOLIC>(c, dir, a); break;
-    default: launch_solver<5, RECON_LINEAR>(c, dir, a); break;
-  }
+  static const pb200_sweep_fn tab[3][2] = {
+      {pb200_launch_sweep_nv5_bf0, pb200_launch_sweep_nv5_bf1},
+      {pb200_launch_sweep_nv6_bf0, pb200_launch_sweep_nv6_bf1},
+      {pb200_launch_sweep_nv7_bf0, pb200_launch_sweep_nv7_bf1}};
+  tab[c->nvar - 5][c->dev.bf_kind ? 1 : 0](c, dir, a);
 }
 
 // NaN screen of the array about to be swept is folded into the reduction cell by a tiny
@@ -378,6 +299,11 @@ __global__ void reset_red(unsigned long long *red, double *dt, double dtval) {
 extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   if (!c) return fail(PB200_EINVAL, "null ctx");
   if (!(dt > 0.0)) return fail(PB200_EINVAL, "dt must be > 0");
+  for (int q = 0; q < 7; q++) {   // every table BODY_FORCE needs has been handed over
+    bool need = (q < 3) ? (c->cfg.body_force & PB200_BF_VECTOR) != 0
+                        : ((c->cfg.body_force & PB200_BF_POTENTIAL) != 0 && (q == 3 || q - 4 < c->dev.ndim));
+    if (need && !c->dev.bf_tab[q]) return fail(PB200_EINVAL, "BODY_FORCE table not set (pb200_set_body_force_*)");
+  }
   CK(cudaSetDevice(c->cfg.device));
   c->launches = 0;
   c->nprof = 0;

@@ -1,0 +1,50 @@
+// pb200_internal.h -- state shared by the translation units of libplutob200.so (not part of
+// the ABI; the public interface is include/pluto_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/pluto_b200.h"
+#include "pb200_kernels.cuh"
+
+struct pb200_ctx {
+  pb::Dev dev;
+  pb200_config cfg;
+  int nvar;
+  long nzone;        // zones incl. ghosts
+  size_t vbytes;     // bytes of one [nvar] state array
+  double *V[3];      // primitive state copies (A = current d->Vc, B, C)
+  double *acc;       // conservative accumulator (DIMENSIONS > 1)
+  double *cdt;       // C_dt
+  double *d_dt;      // device g_dt
+  unsigned long long *d_red;   // reduction cell: invDt bits, maxMach bits, #fail, NaN flag
+  unsigned long long *h_red;   // pinned
+  double *h_dt;                // pinned
+  double *d_invdx[3];
+  double *d_bf[7];   // body-force tables (Dev::bf_tab)
+  std::vector<double> xl[3], xr[3], dx[3];
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  int launches;
+  int cur;           // index of the array holding d->Vc
+  int nstages;
+  int stage_in[4], stage_out[4];  // array indices per stage (1-based)
+  bool in_step;
+  // optional per-kernel timing (pb200_set_profiling)
+  bool profiling;
+  int nprof;
+  cudaEvent_t pev0[16], pev1[16];
+  int pdir[16], pstage[16];
+  float pms[16];
+};
+
+
+// One launcher per (NVAR, body force) pair, each compiled in its own translation unit
+// (pb200_sweeps.cu with -DPB_NV=.. -DPB_BF=..) so that the template instantiations build in
+// parallel.  dir 0: x1 sweep of a 1-D grid; 1: fused x1+x2 march; 2: x3 march.
+typedef void (*pb200_sweep_fn)(pb200_ctx *, int dir, const pb::SweepArgs &);
+#define PB200_SWEEP_DECL(NV, BF) void pb200_launch_sweep_nv##NV##_bf##BF(pb200_ctx *, int, const pb::SweepArgs &);
+PB200_SWEEP_DECL(5, 0) PB200_SWEEP_DECL(5, 1)
+PB200_SWEEP_DECL(6, 0) PB200_SWEEP_DECL(6, 1)
+PB200_SWEEP_DECL(7, 0) PB200_SWEEP_DECL(7, 1)

@@ -39,7 +39,19 @@ struct Dev {
   long sj, sk, sv;  // strides (zones): j, k, variable
   Gas gas;
   const double *inv_dx[3];  // 1/dx per zone index, per direction
+  // BODY_FORCE (Src/MHD/rhs_source.c:253-281): strided tables evaluated once from the user's
+  // BodyForceVector / BodyForcePotential.  value(i,j,k) = tab[q][i*st[q][0]+j*st[q][1]+k*st[q][2]]
+  // (indices incl. ghosts; stride 0 = independent of that coordinate).
+  //   bf_kind & 1 (VECTOR):    tab[0..2] = g[IDIR], g[JDIR], g[KDIR] at zone centres
+  //   bf_kind & 2 (POTENTIAL): tab[3] = Phi at zone centres, tab[4+d] = Phi at the x_d upper face
+  int bf_kind;
+  const double *bf_tab[7];
+  long bf_st[7][3];
 };
+
+PB_D double bf_at(const Dev &d, int q, int i, int j, int k) {
+  return __ldg(d.bf_tab[q] + i * d.bf_st[q][0] + j * d.bf_st[q][1] + k * d.bf_st[q][2]);
+}
 
 struct SweepArgs {
   const double *V;    // primitive array being swept (ghosts filled)
@@ -137,7 +149,7 @@ PB_D void combine_c2p(double (&U)[NV], const double (&v0z)[NV], const Gas &gas, 
 // ------------------------------------------------------------------------------------
 //  x1 sweep (DIMENSIONS == 1): thread per zone, neighbour exchange through shared memory
 // ------------------------------------------------------------------------------------
-template <int NV, int RECON, int SOLVER>
+template <int NV, int RECON, int SOLVER, int BF>
 __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
   constexpr int LO = (RECON == RECON_PARABOLIC) ? 2 : 1;
   constexpr int USE = BX - 1 - LO;
@@ -197,6 +209,11 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
   mach.init();
   const bool face_ok = (t >= LO - 1) && (t <= BX - 2) && (i >= d.beg[0] - 1) && (i <= d.end[0]);
   riemann<NV, SOLVER>(vp, vR, d.gas, Fp, mach, face_ok);
+  double phi_p = 0.0;
+  if (BF && (d.bf_kind & 2)) {   // TotalFlux(): F_E += F_rho Phi at the face (rhs.c:524-526)
+    phi_p = bf_at(d, 4, cl(i), j, k);
+    Fp.f[iPRS] += Fp.f[iRHO] * phi_p;
+  }
 
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) sm[nv][t] = Fp.f[nv];
@@ -221,6 +238,24 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) U[nv] += -dtdx * (Fp.f[nv] - Fm.f[nv]);
     U[iVN] -= dtdx * (Fp.prs - Fm.prs);
+    if (BF) {   // RightHandSideSource(), x1 sweep of a 1-D grid: all three components
+      const int ii = cl(i);
+      if (d.bf_kind & 1) {   // rhs_source.c:253-272
+        const double g1 = bf_at(d, 0, ii, j, k), g2 = bf_at(d, 1, ii, j, k), g3 = bf_at(d, 2, ii, j, k);
+        const double dr = dt * v0[iRHO];
+        U[iVN] += dr * g1;
+        U[iPRS] += dt * 0.5 * (Fp.f[iRHO] + Fm.f[iRHO]) * g1;
+        U[iVT] += dr * g2;
+        U[iPRS] += dr * v0[iVT] * g2;
+        U[iVB] += dr * g3;
+        U[iPRS] += dr * v0[iVB] * g3;
+      }
+      if (d.bf_kind & 2) {   // rhs_source.c:276-281
+        const double phi_m = bf_at(d, 4, cl(i - 1), j, k);
+        U[iVN] -= dtdx * v0[iRHO] * (phi_p - phi_m);
+        U[iPRS] -= bf_at(d, 3, ii, j, k) * (-dtdx * (Fp.f[iRHO] - Fm.f[iRHO]));
+      }
+    }
     if (a.comb) load_zone<0, NV>(a.V0, off, d.sv, v0z);
     combine_c2p<NV>(U, v0z, d.gas, a.comb, a.w0, a.wc, vn, nfail, nan, own);
     if (own) {
@@ -273,7 +308,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
          sizeof(double);
 }
 
-template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM>
+template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM, int BF>
 __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
   constexpr int LEAD = recon_lead<RECON>();
@@ -368,6 +403,10 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
   for (int nv = 0; nv < NV; nv++) { vpL[nv] = v0[nv]; Fm.f[nv] = 0.0; }
   Fm.prs = 0.0;
   Fm.cmax = 0.0;
+  // BODY_FORCE carries: centre density of zone n (x3 march; the fused kernel has the whole row
+  // in the ring) and the potential at the face behind
+  double rho_c = v0[iRHO], phi_m = 0.0;
+  const int jt = (DIR == 1) ? 0 : d.beg[1] + tr, kt = (DIR == 1) ? d.beg[2] + tr : 0;
 
   int sc = 0;  // ring slot consumed by this iteration
 #pragma unroll 2
@@ -424,16 +463,21 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
     // Riemann problem: two independent dependency chains for the scheduler to interleave.
     Face<NV> Fp;
     if (!FUSEX || !fin) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own && n >= cb);
+    // zone z = n-1 sits at (ic, z, kt) for the x2 march and (ic, jt, z) for the x3 march
+    const int zj = (DIR == 1) ? max(z, 0) : jt, zk = (DIR == 1) ? kt : max(z, 0);
+    double phi_p = 0.0;
+    if (BF && (d.bf_kind & 2)) phi_p = bf_at(d, 4 + DIR, ic, zj, zk);
 
     if (fin) {
       double cx = 0.0;
+      double vx[NV];   // FUSEX: centre state of zone z, global component order
       if (FUSEX) {
         // ---- x1 sweep of row z: thread <-> zone; neighbours' values straight from the ring
         int sz = sc - (1 + LEAD);
         sz = sz < 0 ? sz + RING : sz;
         const double *rz = smem + sz * slot_sz;   // row z, all threads
         const int tm = t > 0 ? t - 1 : 0, tp = t < BX - 1 ? t + 1 : BX - 1;
-        double vx[NV], xp[NV], xm[NV];            // x1-local = global component order
+        double xp[NV], xm[NV];                    // x1-local = global component order
 #pragma unroll
         for (int v = 0; v < NV; v++) vx[v] = rz[lvar<DIR>(v) * BX + t];
         if (RECON == RECON_PARABOLIC) {
@@ -474,6 +518,11 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
         const bool xface = t >= LO - 1 && t < BX - HI && i >= d.beg[0] - 1 && i <= d.end[0];
         riemann<NV, SOLVER>(xp, xr, d.gas, Gp, mach, xface);
         riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own);
+        double phx = 0.0;
+        if (BF && (d.bf_kind & 2)) {   // TotalFlux(): F_E += F_rho Phi(x1p) (rhs.c:524-526)
+          phx = bf_at(d, 4, ic, zj, zk);
+          Gp.f[iPRS] += Gp.f[iRHO] * phx;
+        }
 #pragma unroll
         for (int v = 0; v < NV; v++) exf[v * BX + t] = Gp.f[v];
         exf[NV * BX + t] = Gp.prs;
@@ -486,7 +535,20 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
         for (int v = 0; v < NV; v++) U[v] += -dtdx1 * (Gp.f[v] - exf[v * BX + tm]);
         U[iVN] -= dtdx1 * (Gp.prs - exf[NV * BX + tm]);
         cx = 0.5 * (exf[(NV + 1) * BX + tm] + Gp.cmax) * idx1;
+        if (BF) {   // RightHandSideSource(), x1 sweep (rhs_source.c:253-281)
+          if (d.bf_kind & 1) {
+            const double g1 = bf_at(d, 0, ic, zj, zk);
+            U[iVN] += dt * vx[iRHO] * g1;
+            U[iPRS] += dt * 0.5 * (Gp.f[iRHO] + exf[iRHO * BX + tm]) * g1;
+          }
+          if (d.bf_kind & 2) {
+            const double phm = bf_at(d, 4, max(ic - 1, 0), zj, zk);
+            U[iVN] -= dtdx1 * vx[iRHO] * (phx - phm);
+            U[iPRS] -= bf_at(d, 3, ic, zj, zk) * (-dtdx1 * (Gp.f[iRHO] - exf[iRHO * BX + tm]));
+          }
+        }
       }
+      if (BF && (d.bf_kind & 2)) Fp.f[iPRS] += Fp.f[iRHO] * phi_p;
 
       // ---- finish zone z: add this direction, combine, cons->prim ----
       const double dtdx = dt * inv_dl * wscale;
@@ -494,6 +556,25 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
 #pragma unroll
       for (int c = 0; c < NV; c++) U[gvar<DIR>(c)] += -dtdx * (Fp.f[c] - Fm.f[c]);
       U[gvar<DIR>(iVN)] -= dtdx * (Fp.prs - Fm.prs);
+      if (BF) {   // RightHandSideSource(), x2 / x3 sweep (rhs_source.c:360-384 and the x3 twin)
+        const double dts = dt * wscale;
+        double rz, vbz;   // centre density and the velocity along the next (inactive) direction
+        if (FUSEX) { rz = vx[iRHO]; vbz = vx[3]; } else { rz = rho_c; vbz = 0.0; }
+        if (d.bf_kind & 1) {
+          const double gn = bf_at(d, DIR, ic, zj, zk);
+          U[gvar<DIR>(iVN)] += dts * rz * gn;
+          U[iPRS] += dts * 0.5 * (Fp.f[iRHO] + Fm.f[iRHO]) * gn;
+          if (DIR == 1 && d.ndim == 2) {   // !INCLUDE_KDIR: g[KDIR] is added by the x2 sweep
+            const double g3 = bf_at(d, 2, ic, zj, zk);
+            U[3] += dts * rz * g3;
+            U[iPRS] += dts * rz * vbz * g3;
+          }
+        }
+        if (d.bf_kind & 2) {
+          U[gvar<DIR>(iVN)] -= dtdx * rz * (phi_p - phi_m);
+          U[iPRS] -= bf_at(d, 3, ic, zj, zk) * (-dtdx * (Fp.f[iRHO] - Fm.f[iRHO]));
+        }
+      }
       if (LAST) {
         double vn[NV];
         combine_c2p<NV>(U, v0z, d.gas, FIRST ? comb : 0, a.w0, a.wc, vn, nfail, nan, own);
@@ -515,10 +596,12 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
         if (LAST) cdt_max = fmax(cdt_max, own ? c : 0.0);
         else if (own) a.cdt[oz] = c;
       }
-    } else if (FUSEX) {
-      __syncthreads();   // rows landed so far become visible to the neighbours
+    } else {
+      if (BF && (d.bf_kind & 2)) Fp.f[iPRS] += Fp.f[iRHO] * phi_p;
+      if (FUSEX) __syncthreads();   // rows landed so far become visible to the neighbours
     }
     Fm = Fp;
+    if (BF) { phi_m = phi_p; rho_c = v0[iRHO]; }
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) {
       vpL[nv] = vp[nv];
@@ -546,7 +629,7 @@ struct BcArgs {
   double sign[16];
 };
 
-__global__ void bc_fill(Dev d, BcArgs b) {
+static __global__ void bc_fill(Dev d, BcArgs b) {
   const int dir = b.side >> 1;
   const bool hi = b.side & 1;
   // extents of the ghost box: nghost layers along dir, full transverse range

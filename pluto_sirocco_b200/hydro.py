@@ -151,7 +151,7 @@ class Hydro:
     def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
-                 small_density=1e-12, small_pressure=1e-12, dx=None):
+                 small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0):
         lib = L.load()
         cfg = L.Config()
         lib.pb200_config_default(C.byref(cfg))
@@ -176,6 +176,7 @@ class Hydro:
         cfg.small_density = small_density
         cfg.small_pressure = small_pressure
         cfg.device = device
+        cfg.body_force = int(body_force)
         self.cfg = cfg
         self._lib = lib
         h = C.c_void_p()
@@ -191,6 +192,8 @@ class Hydro:
         self.shape = (self.nvar, tot[2], tot[1], tot[0])   # Vc[nv][k][j][i]
         self.beg = tuple(cfg.nghost if d < dimensions else 0 for d in range(3))
         self.nx = tuple(cfg.nx[d] for d in range(3))
+        self.xbeg = tuple(cfg.xbeg)
+        self.xend = tuple(cfg.xend)
         self.last = L.StepInfo()
         if dx is not None:      # block of a larger uniform grid: impose the global grid->dx
             for d in range(dimensions):
@@ -242,6 +245,32 @@ class Hydro:
 
     def new_vc(self):
         return np.zeros(self.shape, dtype=np.float64)
+
+    # -- BODY_FORCE tables ---------------------------------------------------------------------
+    def _bf_table(self, tab):
+        """tab: array broadcastable to [NX3_TOT][NX2_TOT][NX1_TOT]; axes of length 1 get stride 0."""
+        a = np.asarray(tab, dtype=np.float64)
+        while a.ndim < 3:
+            a = a[None]
+        full = (self.tot[2], self.tot[1], self.tot[0])
+        for ax in range(3):
+            if a.shape[ax] not in (1, full[ax]):
+                raise ValueError("body-force table axis %d has length %d, expected 1 or %d" % (ax, a.shape[ax], full[ax]))
+        a = np.ascontiguousarray(a)
+        st = [a.strides[ax] // 8 if a.shape[ax] > 1 else 0 for ax in range(3)]   # k, j, i
+        return a, st[2], st[1], st[0]
+
+    def set_body_force_vector(self, comp, tab):
+        """g[comp] of BodyForceVector at zone centres (rhs_source.c:256)."""
+        a, si, sj, sk = self._bf_table(tab)
+        L.check(self._lib.pb200_set_body_force_vector(self._h, int(comp), a.ctypes.data_as(C.c_void_p),
+                                                      a.size, si, sj, sk))
+
+    def set_body_force_potential(self, where, tab):
+        """BodyForcePotential at zone centres (where=0) or at the upper x1/x2/x3 faces (1,2,3)."""
+        a, si, sj, sk = self._bf_table(tab)
+        L.check(self._lib.pb200_set_body_force_potential(self._h, int(where), a.ctypes.data_as(C.c_void_p),
+                                                         a.size, si, sj, sk))
 
     # -- data movement -----------------------------------------------------------------------
     def upload(self, vc: np.ndarray):

@@ -21,12 +21,59 @@ def load_golden(name):
     for k in ("gamma", "cfl", "cfl_max_var", "first_dt", "tstop"):
         g[k] = float(g[k])
     g["nx"] = tuple(int(x) for x in g["nx"])
+    # optional keys of the later fixtures (tracers, body force, non-unit domains)
+    g["xbeg"] = tuple(float(x) for x in g["xbeg"]) if "xbeg" in g else (0.0, 0.0, 0.0)
+    g["xend"] = tuple(float(x) for x in g["xend"]) if "xend" in g else (1.0, 1.0, 1.0)
+    g["ntracer"] = int(g["ntracer"]) if "ntracer" in g else 0
+    g["body_force"] = str(g["body_force"]) if "body_force" in g else "none"
+    g["grav"] = float(g["grav"]) if "grav" in g else 0.0
+    g["limiter"] = str(g["limiter"]) if "limiter" in g else "DEFAULT"
     return g
+
+
+BODY_FORCE = dict(none=0, vector=1, potential=2)
 
 
 def kwargs_from_golden(g):
     return dict(dimensions=g["dims"], nx=g["nx"], gamma=g["gamma"], reconstruction=g["recon"],
-                time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"])
+                time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"], xbeg=g["xbeg"], xend=g["xend"],
+                ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]])
+
+
+def set_gravity_x2(obj, kind, grav):
+    """Hand a constant gravity GRAV along x2 to a Hydro or an Oracle, the way the shim does it for
+    oracle/problems/rt/init.c: BodyForceVector = (0, GRAV, 0), BodyForcePotential = -GRAV*x2,
+    evaluated on the object's own grid (cell centres x2[j], upper faces x2p[j])."""
+    if kind == "none":
+        return
+    ny = obj.tot[1]
+    if kind == "vector":
+        for comp, val in enumerate((0.0, grav, 0.0)):
+            obj.set_body_force_vector(comp, np.full((1, 1, 1), val))
+        return
+    dx2 = (obj_xend(obj, 1) - obj_xbeg(obj, 1)) / obj.nx[1] if obj.dimensions > 1 else 1.0
+    j = np.arange(ny) - obj.beg[1]
+    if obj.dimensions > 1:
+        # Src/set_grid.c: xl = xbeg + j dx, xr = xl + dx, x = 0.5 (xl + xr)
+        xl = obj_xbeg(obj, 1) + j * dx2
+        xr = xl + dx2
+    else:   # inactive direction: one zone spanning the ini range
+        xl = np.array([obj_xbeg(obj, 1)]); xr = np.array([obj_xend(obj, 1)])
+    x2 = 0.5 * (xl + xr)
+    phic = (-grav * x2).reshape(1, -1, 1)
+    phif = (-grav * xr).reshape(1, -1, 1)
+    obj.set_body_force_potential(0, phic)
+    obj.set_body_force_potential(1, phic)   # Phi(x1p, x2, x3) = Phi(x2)
+    obj.set_body_force_potential(2, phif)
+    obj.set_body_force_potential(3, phic)
+
+
+def obj_xbeg(obj, d):
+    return obj.xbeg[d]
+
+
+def obj_xend(obj, d):
+    return obj.xend[d]
 
 
 def rel_err(a, b):

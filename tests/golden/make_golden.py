@@ -34,9 +34,63 @@ CASES = {
 }
 
 
+# cases with tracers / body forces / non-unit domains (dict form)
+RT_BCS = ("periodic", "periodic", "reflective", "reflective", "periodic", "periodic")
+RT_PAR = dict(ETA=2.0, GRAV=-0.1)
+KH_BCS = ("periodic", "periodic", "outflow", "outflow", "periodic", "periodic")
+CASES2 = {
+    "rt3d_vec_hllc": dict(cfg="rt3d_vec", dims=3, nx=(12, 24, 10), xbeg=(-0.5, -1.0, -0.5), xend=(0.5, 1.0, 0.5),
+                          solver="hllc", bcs=RT_BCS, maxsteps=8, params=RT_PAR, gamma=5. / 3., cfl=0.4,
+                          first_dt=1e-3, tstop=5.0, ntracer=1, body_force="vector", limiter="DEFAULT"),
+    "rt3d_pot_hll": dict(cfg="rt3d_pot", dims=3, nx=(12, 24, 10), xbeg=(-0.5, -1.0, -0.5), xend=(0.5, 1.0, 0.5),
+                         solver="hll", bcs=RT_BCS, maxsteps=8, params=RT_PAR, gamma=5. / 3., cfl=0.4,
+                         first_dt=1e-3, tstop=5.0, ntracer=1, body_force="potential", limiter="DEFAULT"),
+    "rt2d_vec_hllc": dict(cfg="rt2d_vec", dims=2, nx=(16, 48, 1), xbeg=(-0.5, -1.5, -0.5), xend=(0.5, 1.5, 0.5),
+                          solver="hllc", bcs=RT_BCS, maxsteps=12, params=RT_PAR, gamma=5. / 3., cfl=0.4,
+                          first_dt=1e-3, tstop=5.0, ntracer=1, body_force="vector", limiter="DEFAULT"),
+    "rt2d_pot_mc_hllc": dict(cfg="rt2d_pot", dims=2, nx=(16, 48, 1), xbeg=(-0.5, -1.5, -0.5), xend=(0.5, 1.5, 0.5),
+                             solver="hllc", bcs=RT_BCS, maxsteps=12, params=RT_PAR, gamma=5. / 3., cfl=0.4,
+                             first_dt=1e-3, tstop=5.0, ntracer=1, body_force="potential", limiter="MC_LIM"),
+    "rt1d_vec_tvdlf": dict(cfg="rt1d_vec", dims=1, nx=(64, 1, 1), xbeg=(-0.5, -1.0, -0.5), xend=(0.5, 1.0, 0.5),
+                           solver="tvdlf", bcs=RT_BCS, maxsteps=10, params=RT_PAR, gamma=5. / 3., cfl=0.4,
+                           first_dt=1e-3, tstop=5.0, ntracer=1, body_force="vector", limiter="DEFAULT"),
+    "kh3d_hllc": dict(cfg="kh3d", dims=3, nx=(16, 20, 8), xbeg=(0.0, -0.5, 0.0), xend=(1.0, 0.5, 0.5),
+                      solver="hllc", bcs=KH_BCS, maxsteps=8, params=dict(A_KH=0.05, DRHO=1.0, MACH=0.8),
+                      gamma=1.4, cfl=0.4, first_dt=1e-4, tstop=5.0, ntracer=1, body_force="none",
+                      limiter="DEFAULT"),
+}
+
+
+def make_case2(out, name, c):
+    build_ref.build(c["cfg"])
+    nd, nx = c["dims"], c["nx"]
+    nvar = 5 + c["ntracer"]
+    with tempfile.TemporaryDirectory() as wd:
+        r = refrun.run(c["cfg"], wd, shape=(nx[2], nx[1], nx[0]), nvar=nvar, maxsteps=c["maxsteps"],
+                       grid=[(c["xbeg"][d], nx[d], c["xend"][d]) for d in range(3)], cfl=c["cfl"],
+                       tstop=c["tstop"], first_dt=c["first_dt"], solver=c["solver"], bcs=c["bcs"],
+                       dbl=(-1.0, 1), params=c["params"])
+    nd_ = len(r["data"]) - 1
+    steps = np.array(r["steps"][:nd_], dtype=np.float64)
+    data = np.stack(r["data"][:nd_])
+    np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx), dims=nd,
+                        recon="LINEAR", rk="RK2", solver=c["solver"], bcs=np.array(c["bcs"]),
+                        gamma=c["gamma"], cfl=c["cfl"], cfl_max_var=1.1, first_dt=c["first_dt"],
+                        tstop=c["tstop"], ref_config=c["cfg"], xbeg=np.array(c["xbeg"]),
+                        xend=np.array(c["xend"]), ntracer=c["ntracer"], body_force=c["body_force"],
+                        grav=c["params"].get("GRAV", 0.0), limiter=c["limiter"])
+    print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
+
+
 def main():
     out = Path(__file__).resolve().parent
+    only = set(sys.argv[1:])
+    for name, c in CASES2.items():
+        if not only or name in only:
+            make_case2(out, name, c)
     for name, (cfg, nd, N, recon, rk, solver, bcs, maxsteps, params, gamma, cfl, first_dt, tstop) in CASES.items():
+        if only and name not in only:
+            continue
         build_ref.build(cfg)
         nx = [N if d < nd else 1 for d in range(3)]
         with tempfile.TemporaryDirectory() as wd:

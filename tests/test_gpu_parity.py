@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from common import (GOLDEN_CASES, TOL_RUN, TOL_STEP, kwargs_from_golden, load_golden, random_state,
-                    rel_err, rel_l1)
+                    rel_err, rel_l1, set_gravity_x2)
 from oracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -25,6 +25,7 @@ def Hydro(cuda_lib):
 def test_per_step_vs_reference_dumps(Hydro, name):
     g = load_golden(name)
     h = Hydro(**kwargs_from_golden(g))
+    set_gravity_x2(h, g["body_force"], g["grav"])
     data, steps = g["data"], g["steps"]
     worst = 0.0
     for n in range(len(data) - 1):
@@ -45,6 +46,7 @@ def test_full_run_vs_reference_dumps(Hydro, name):
     from pluto_sirocco_b200 import Runtime, Simulation
     g = load_golden(name)
     h = Hydro(**kwargs_from_golden(g))
+    set_gravity_x2(h, g["body_force"], g["grav"])
     h.set_interior(g["data"][0])
     rt = Runtime(cfl=g["cfl"], cfl_max_var=g["cfl_max_var"], tstop=g["tstop"], first_dt=g["first_dt"])
     sim = Simulation(h, rt)
@@ -54,6 +56,7 @@ def test_full_run_vs_reference_dumps(Hydro, name):
     assert rel_l1(h.get_interior(), g["data"][-1]) <= TOL_RUN
     # the C-side loop gives the same answer as the Python-side loop
     h2 = Hydro(**kwargs_from_golden(g))
+    set_gravity_x2(h2, g["body_force"], g["grav"])
     h2.set_interior(g["data"][0])
     n, t, dt = h2.integrate(nsteps, t=0.0, dt=g["first_dt"], tstop=g["tstop"], cfl=g["cfl"],
                             cfl_max_var=g["cfl_max_var"], first_dt=g["first_dt"])
@@ -95,6 +98,60 @@ def test_steps_vs_oracle_seeded(Hydro, recon, solver, dims, nx, bcname):
         # per-step test: restart the device from the oracle state so errors do not accumulate
         h.set_interior(vc[o.interior()])
         dt = min(o.next_time_step(inv, 0.3, 1.1, dt, 1e-6), 1.1 * dt)
+    h.close()
+
+
+def _state_with_tracers(shape_int, ntr, seed):
+    v5 = random_state(shape_int, seed=seed, smooth=False)
+    rng = np.random.default_rng(seed + 1)
+    tr = [np.clip(0.5 + 0.5 * np.sin(7.0 * v5[0] + k) + rng.normal(0, 0.05, size=v5[0].shape), 0, 1)
+          for k in range(ntr)]
+    return np.concatenate([v5, np.stack(tr)]) if ntr else v5
+
+
+@pytest.mark.parametrize("recon,rk", [("LINEAR", "RK2"), ("PARABOLIC", "RK3")])
+@pytest.mark.parametrize("dims,nx", [(1, (131, 1, 1)), (2, (53, 37, 1)), (3, (29, 17, 21))])
+@pytest.mark.parametrize("ntr,bf", [(1, 0), (2, 1), (0, 2), (1, 3)])
+def test_tracers_and_body_force_vs_oracle(Hydro, recon, rk, dims, nx, ntr, bf):
+    """NTRACER 1-2 (AdvectFlux, adv_flux.c:61-72) and BODY_FORCE VECTOR / POTENTIAL / both
+    (rhs_source.c:253-281, rhs.c:524-526) with tables that vary in all three directions."""
+    kw = dict(dimensions=dims, nx=nx, gamma=1.4, reconstruction=recon, time_stepping=rk, solver="hllc",
+              bcs=("periodic", "periodic", "reflective", "outflow", "periodic", "periodic"), ntracer=ntr,
+              body_force=bf)
+    h, o = Hydro(**kw), Oracle(**kw)
+    rng = np.random.default_rng(17 * dims + bf)
+    full = (o.tot[2], o.tot[1], o.tot[0])
+    shapes = [full, (1, full[1], 1), (1, 1, 1), (full[0], 1, full[2])]   # 3-D, x2 only, constant, x1-x3
+    if bf & 1:
+        for comp in range(3):
+            tab = rng.uniform(-2.0, 2.0, size=shapes[comp])
+            h.set_body_force_vector(comp, tab); o.set_body_force_vector(comp, tab)
+    if bf & 2:
+        for where in range(4):
+            tab = rng.uniform(-0.5, 0.5, size=shapes[(where + 1) % 4])
+            h.set_body_force_potential(where, tab); o.set_body_force_potential(where, tab)
+    v = _state_with_tracers((nx[2], nx[1], nx[0]), ntr, seed=dims + 10 * ntr)
+    vc = o.embed(v)
+    h.set_interior(v)
+    dt = 2e-4
+    for n in range(3):
+        inv, mach, nf = o.advance_step(vc, dt)
+        info = h.advance_step(dt)
+        e = rel_err(h.get_interior(), vc[o.interior()])
+        assert e <= TOL_STEP, (n, e)
+        assert abs(info.invDt_hyp - inv) <= TOL_STEP * inv
+        h.set_interior(vc[o.interior()])
+    h.close()
+
+
+def test_body_force_tables_are_required(Hydro):
+    from pluto_sirocco_b200._lib import PB200Error
+    h = Hydro(dimensions=2, nx=(16, 16, 1), body_force=1)
+    h.set_interior(np.concatenate([np.ones((1, 1, 16, 16)), np.zeros((3, 1, 16, 16)), np.ones((1, 1, 16, 16))]))
+    with pytest.raises(PB200Error):
+        h.advance_step(1e-3)          # tables not handed over yet
+    with pytest.raises(PB200Error):
+        h.set_body_force_potential(0, np.zeros((1, 1, 1)))   # cfg.body_force has no POTENTIAL part
     h.close()
 
 

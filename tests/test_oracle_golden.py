@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from common import GOLDEN_CASES, kwargs_from_golden, load_golden, rel_err
+from common import GOLDEN_CASES, kwargs_from_golden, load_golden, rel_err, set_gravity_x2
 from oracle import Oracle
 
 
@@ -10,6 +10,7 @@ from oracle import Oracle
 def test_oracle_per_step_matches_reference_dumps(name):
     g = load_golden(name)
     o = Oracle(**kwargs_from_golden(g))
+    set_gravity_x2(o, g["body_force"], g["grav"])
     data, steps = g["data"], g["steps"]
     for n in range(len(data) - 1):
         vc = o.embed(data[n])
