@@ -185,6 +185,17 @@ int  pb200_halo_layout(const pb200_ctx *ctx, int dir, long *lo_ghost, long *lo_e
 int  pb200_step_begin(pb200_ctx *ctx, double dt);
 double *pb200_stage_array(pb200_ctx *ctx, int stage);  /* device Vc swept by stage s */
 int  pb200_stage(pb200_ctx *ctx, int stage);
+/* pb200_stage in three parts, for overlapping the halo exchange with compute (replaces the
+ * blocking exchange inside Boundary(), Src/boundary.c:139-158):
+ *   _boundary  fills the physical boundaries of the array stage s sweeps;
+ *   _begin     runs the sweeps that do not read the ghost planes of the outermost active
+ *              direction (3-D: the fused x1+x2 kernel; 1-D/2-D: nothing);
+ *   _finish    runs the sweeps that do.
+ * A slab-decomposed caller posts the exchange between _boundary and _begin and waits for it
+ * before _finish.  pb200_stage(s) == _boundary; _begin; _finish. */
+int  pb200_stage_boundary(pb200_ctx *ctx, int stage);
+int  pb200_stage_begin(pb200_ctx *ctx, int stage);
+int  pb200_stage_finish(pb200_ctx *ctx, int stage);
 int  pb200_step_end(pb200_ctx *ctx, pb200_step_info *info);
 int  pb200_nstages(const pb200_ctx *ctx);
 /* Measurement aid (the reference's FUNCTION_CLOCK_PROFILE, Src/pluto.h:414-419, rk_step.c:

@@ -62,6 +62,9 @@ SYMBOLS = {
     "pb200_step_begin": (C.c_int, [_P, _D]),
     "pb200_stage_array": (_P, [_P, C.c_int]),
     "pb200_stage": (C.c_int, [_P, C.c_int]),
+    "pb200_stage_boundary": (C.c_int, [_P, C.c_int]),
+    "pb200_stage_begin": (C.c_int, [_P, C.c_int]),
+    "pb200_stage_finish": (C.c_int, [_P, C.c_int]),
     "pb200_step_end": (C.c_int, [_P, C.POINTER(StepInfo)]),
     "pb200_nstages": (C.c_int, [_P]),
     "pb200_stream": (_P, [_P]),

@@ -325,15 +325,15 @@ extern "C" double *pb200_stage_array(pb200_ctx *c, int stage) {
   return c->V[c->stage_in[stage]];
 }
 
-extern "C" int pb200_stage(pb200_ctx *c, int stage) {
+// A stage in three parts so that a slab-decomposed caller can overlap the halo exchange of the
+// outermost direction with the sweeps that do not read those ghost planes:
+//   pb200_stage_boundary: Boundary() fills of the physical sides;
+//   pb200_stage_begin : (3-D only) the fused x1+x2 kernel, which touches interior planes only;
+//   pb200_stage_finish: the sweeps that read the ghosts of the outermost active direction.
+static int stage_args(pb200_ctx *c, int stage, SweepArgs &a) {
   if (!c || !c->in_step) return fail(PB200_EINVAL, "pb200_stage outside begin/end");
   if (stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad stage");
-  const Dev &D = c->dev;
-  double *Vin = c->V[c->stage_in[stage]];
-  int rc = boundary_on(c, Vin);  // Boundary(d, 0, grid), rk_step.c:121,213,285
-  if (rc) return rc;
-  SweepArgs a;
-  a.V = Vin;
+  a.V = c->V[c->stage_in[stage]];
   a.V0 = c->V[c->cur];
   a.acc = c->acc;
   a.Vout = c->V[c->stage_out[stage]];
@@ -349,14 +349,43 @@ extern "C" int pb200_stage(pb200_ctx *c, int stage) {
   } else if (stage == 3) {
     a.comb = 2;
   }
-  if (D.ndim == 1) {
-    launch_sweep(c, 0, a);
-  } else {
-    launch_sweep(c, 1, a);                    // x1 + x2 in one kernel
-    if (D.ndim == 3) launch_sweep(c, 2, a);   // x3
-  }
+  return PB200_OK;
+}
+
+extern "C" int pb200_stage_boundary(pb200_ctx *c, int stage) {
+  SweepArgs a;
+  int rc = stage_args(c, stage, a);
+  if (rc) return rc;
+  return boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
+}
+
+extern "C" int pb200_stage_begin(pb200_ctx *c, int stage) {
+  SweepArgs a;
+  int rc = stage_args(c, stage, a);
+  if (rc) return rc;
+  if (c->dev.ndim == 3) launch_sweep(c, 1, a);    // x1 + x2 in one kernel: interior planes only
   CK(cudaGetLastError());
   return PB200_OK;
+}
+
+extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
+  SweepArgs a;
+  int rc = stage_args(c, stage, a);
+  if (rc) return rc;
+  const Dev &D = c->dev;
+  if (D.ndim == 1) launch_sweep(c, 0, a);
+  else if (D.ndim == 2) launch_sweep(c, 1, a);    // x1 + x2 (reads the x2 ghosts)
+  else launch_sweep(c, 2, a);                     // x3
+  CK(cudaGetLastError());
+  return PB200_OK;
+}
+
+extern "C" int pb200_stage(pb200_ctx *c, int stage) {
+  int rc = pb200_stage_boundary(c, stage);
+  if (rc) return rc;
+  rc = pb200_stage_begin(c, stage);
+  if (rc) return rc;
+  return pb200_stage_finish(c, stage);
 }
 
 extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {

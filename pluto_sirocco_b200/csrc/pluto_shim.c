@@ -46,6 +46,66 @@ static int translate_limiter(void) {
 #endif
 }
 
+#if BODY_FORCE != NO
+/* Evaluate a user body-force callback once on the reference's own grid arrays and hand the
+ * result over as the smallest strided table: axes the values do not depend on get stride 0
+ * (a constant g is one double, a Phi(x2) potential NX2_TOT doubles).                        */
+typedef int (*bf_setter)(pb200_ctx *, int, const double *, long, long, long, long);
+static void shim_set_table(bf_setter set, int sel, const double *full)
+{
+  long n[3] = {NX1_TOT, NX2_TOT, NX3_TOT}, st_full[3] = {1, NX1_TOT, (long)NX1_TOT*NX2_TOT};
+  long dep[3] = {0, 0, 0}, st[3], m[3], i, j, k, cnt = 1;
+  double *tab;
+  for (k = 0; k < n[2]; k++) for (j = 0; j < n[1]; j++) for (i = 0; i < n[0]; i++) {
+    double q = full[k*st_full[2] + j*st_full[1] + i];
+    if (q != full[k*st_full[2] + j*st_full[1]])  dep[0] = 1;
+    if (q != full[k*st_full[2] + i])             dep[1] = 1;
+    if (q != full[j*st_full[1] + i])             dep[2] = 1;
+  }
+  for (i = 0; i < 3; i++) { m[i] = dep[i] ? n[i] : 1; st[i] = dep[i] ? cnt : 0; cnt *= m[i]; }
+  tab = (double *) malloc(cnt*sizeof(double));
+  for (k = 0; k < m[2]; k++) for (j = 0; j < m[1]; j++) for (i = 0; i < m[0]; i++)
+    tab[i*st[0] + j*st[1] + k*st[2]] = full[k*st_full[2] + j*st_full[1] + i];
+  if (set(s_ctx, sel, tab, cnt, st[0], st[1], st[2]) != PB200_OK) {
+    print ("! AdvanceStep(): body-force table: %s\n", pb200_last_error());
+    QUIT_PLUTO(1);
+  }
+  free(tab);
+}
+
+static void shim_body_force(Data *d, Grid *grid)
+{
+  long ntot = (long)NX1_TOT*NX2_TOT*NX3_TOT, o;
+  int i, j, k, nv, c;
+  double *x1 = grid->x[IDIR], *x2 = grid->x[JDIR], *x3 = grid->x[KDIR];
+  double *full = (double *) malloc(3*ntot*sizeof(double));
+#if (BODY_FORCE & VECTOR)
+  double v[NVAR], g[3];
+  TOT_LOOP(k,j,i) {                      /* rhs_source.c:256,367,429 */
+    NVAR_LOOP(nv) v[nv] = d->Vc[nv][k][j][i];
+    g[0] = g[1] = g[2] = 0.0;
+    BodyForceVector(v, g, x1[i], x2[j], x3[k]);
+    o = ((long)k*NX2_TOT + j)*NX1_TOT + i;
+    for (c = 0; c < 3; c++) full[c*ntot + o] = g[c];
+  }
+  for (c = 0; c < 3; c++) shim_set_table(pb200_set_body_force_vector, c, full + c*ntot);
+#endif
+#if (BODY_FORCE & POTENTIAL)
+  for (c = 0; c < 4; c++) {              /* rhs.c:168-182, rhs_source.c:279,382,441 */
+    if (c > DIMENSIONS) break;
+    TOT_LOOP(k,j,i) {
+      o = ((long)k*NX2_TOT + j)*NX1_TOT + i;
+      full[o] = BodyForcePotential(c == 1 ? grid->xr[IDIR][i] : x1[i],
+                                   c == 2 ? grid->xr[JDIR][j] : x2[j],
+                                   c == 3 ? grid->xr[KDIR][k] : x3[k]);
+    }
+    shim_set_table(pb200_set_body_force_potential, c, full);
+  }
+#endif
+  free(full);
+}
+#endif
+
 static void shim_init(Data *d, Grid *grid) {
   pb200_config cfg;
   int dir;
@@ -76,6 +136,12 @@ static void shim_init(Data *d, Grid *grid) {
 #error "libplutob200: TIME_STEPPING must be EULER, RK2 or RK3"
 #endif
   cfg.limiter = translate_limiter();
+#if (BODY_FORCE & VECTOR)
+  cfg.body_force |= PB200_BF_VECTOR;
+#endif
+#if (BODY_FORCE & POTENTIAL)
+  cfg.body_force |= PB200_BF_POTENTIAL;
+#endif
   /* SetSolver() stored a function pointer (Src/HD/set_solver.c:4-58) */
   if      (d->fluidRiemannSolver == &HLLC_Solver) cfg.solver = PB200_HLLC;
   else if (d->fluidRiemannSolver == &HLL_Solver)  cfg.solver = PB200_HLL;
@@ -106,6 +172,9 @@ static void shim_init(Data *d, Grid *grid) {
       QUIT_PLUTO(1);
     }
   }
+#if BODY_FORCE != NO
+  shim_body_force(d, grid);
+#endif
   print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode)\n", pb200_version(),
          s_resident ? "resident" : "strict host-buffer");
 }

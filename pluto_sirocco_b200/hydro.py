@@ -336,6 +336,15 @@ class Hydro:
     def stage(self, s):
         L.check(self._lib.pb200_stage(self._h, int(s)))
 
+    def stage_boundary(self, s):
+        L.check(self._lib.pb200_stage_boundary(self._h, int(s)))
+
+    def stage_begin(self, s):
+        L.check(self._lib.pb200_stage_begin(self._h, int(s)))
+
+    def stage_finish(self, s):
+        L.check(self._lib.pb200_stage_finish(self._h, int(s)))
+
     def step_end(self) -> L.StepInfo:
         L.check(self._lib.pb200_step_end(self._h, C.byref(self.last)))
         return self.last

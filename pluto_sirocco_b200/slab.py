@@ -89,13 +89,16 @@ class Slab:
         return tuple(sl)
 
 
-def exchange_halos(vc: torch.Tensor, slab: Slab, nghost: int):
-    """Fill the ghost planes of direction slab.sdir of vc[nv][k][j][i] (ghosts included) from
-    the neighbouring ranks' edge planes.  Works for CUDA tensors (nccl) and CPU tensors (gloo).
+def post_halo_exchange(vc: torch.Tensor, slab: Slab, nghost: int):
+    """Post the exchange of the ghost planes of direction slab.sdir of vc[nv][k][j][i] (ghosts
+    included) with the neighbouring ranks' edge planes; returns the outstanding requests (wait on
+    them before reading the ghost planes).  With NCCL the transfers run on NCCL's own stream,
+    ordered after the work already enqueued on the current stream, so kernels launched between
+    post and wait overlap with them.  Works for CUDA tensors (nccl) and CPU tensors (gloo).
     Every plane set is contiguous per variable, so tensors are sent in place (no packing)."""
     lo, hi = slab.neighbours()
     if lo is None and hi is None:
-        return
+        return []
     axis = 3 - slab.sdir                 # position of the split direction in [nv][k][j][i]
     n = vc.shape[axis]
     ng = nghost
@@ -125,7 +128,12 @@ def exchange_halos(vc: torch.Tensor, slab: Slab, nghost: int):
     if hi is not None:
         for nv in range(nvar):
             ops.append(dist.P2POp(dist.irecv, hi_ghost[nv], hi, tag=100 + nv))
-    for r in dist.batch_isend_irecv(ops):
+    return dist.batch_isend_irecv(ops)
+
+
+def exchange_halos(vc: torch.Tensor, slab: Slab, nghost: int):
+    """Blocking form: post + wait."""
+    for r in post_halo_exchange(vc, slab, nghost):
         r.wait()
 
 
@@ -169,8 +177,14 @@ class SlabHydro:
         with torch.cuda.stream(self.stream):
             h.step_begin(dt)
             for s in range(1, h.nstages() + 1):
-                exchange_halos(self._view(h.stage_array_ptr(s)), self.slab, h.nghost)
-                h.stage(s)
+                # the x3 ghost planes are only read by the x3 sweep: fill the physical boundaries,
+                # post the exchange, run the fused x1+x2 kernel while the planes travel, then wait
+                h.stage_boundary(s)
+                reqs = post_halo_exchange(self._view(h.stage_array_ptr(s)), self.slab, h.nghost)
+                h.stage_begin(s)
+                for r in reqs:
+                    r.wait()
+                h.stage_finish(s)
             info = h.step_end()
             if self.slab.world > 1:
                 inv, mach = allreduce_max([info.invDt_hyp, info.maxMach], self.device)

@@ -16,11 +16,18 @@ ROOT = Path(__file__).resolve().parents[1]
 SOD_BCS = ("outflow", "outflow", "periodic", "periodic", "outflow", "outflow")
 SEDOV = dict(bcs=("reflective", "outflow") * 3, params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4), cfl=0.3,
              tstop=0.5, first_dt=1e-9)
+RT = dict(bcs=("periodic", "periodic", "reflective", "reflective", "periodic", "periodic"),
+          params=dict(ETA=2.0, GRAV=-0.1), cfl=0.4, tstop=5.0, first_dt=1e-3)
 CASES = {
     "sod": dict(shape=(1, 1, 400), grid=[(0, 400, 1), (0, 1, 1), (0, 1, 1)], cfl=0.8, tstop=0.2, first_dt=1e-4,
                 bcs=SOD_BCS, params={"SCRH": 0}, maxsteps=80),
     "sedov3d": dict(shape=(24, 24, 24), grid=[(0, 24, 1)] * 3, maxsteps=15, **SEDOV),
     "sedov3d_ppm": dict(shape=(24, 24, 24), grid=[(0, 24, 1)] * 3, maxsteps=10, **SEDOV),
+    # tracer + BODY_FORCE: the shim evaluates the user's BodyForceVector / BodyForcePotential
+    "rt3d_vec": dict(shape=(10, 24, 12), nvar=6, grid=[(-0.5, 12, 0.5), (-1.0, 24, 1.0), (-0.5, 10, 0.5)],
+                     maxsteps=10, **RT),
+    "rt2d_pot": dict(shape=(1, 48, 16), nvar=6, grid=[(-0.5, 16, 0.5), (-1.5, 48, 1.5), (-0.5, 1, 0.5)],
+                     maxsteps=12, **RT),
 }
 
 
