@@ -81,6 +81,16 @@ CONFIGS = {
     "rt2d_pot": dict(local="rt", overrides={"DIMENSIONS": "2", "BODY_FORCE": "POTENTIAL",
                                             "LIMITER": "MC_LIM"}, states="plm"),
     "rt1d_vec": dict(local="rt", overrides={"DIMENSIONS": "1"}, states="plm"),
+    # C4 building blocks: spherical geometry on stretched grids (oracle/problems/sph)
+    "sph2d": dict(local="sph", overrides={}, states="plm"),
+    "sph2d_char": dict(local="sph", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM"}, states="plm"),
+    "sph2d_flat": dict(local="sph", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
+                                               "SHOCK_FLATTENING": "MULTID"}, states="plm"),
+    "sph2d_entr": dict(local="sph", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
+                                               "SHOCK_FLATTENING": "MULTID", "ENTROPY_SWITCH": "ALWAYS"},
+                       states="plm"),
+    "sph1d": dict(local="sph", overrides={"DIMENSIONS": "1"}, states="plm"),
+    "sph3d": dict(local="sph", overrides={"DIMENSIONS": "3"}, states="plm"),
     # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
     "kh3d": dict(local="kh", overrides={}, states="plm"),
 }

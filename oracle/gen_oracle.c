@@ -1,0 +1,846 @@
+/* gen_oracle.c -- CPU restatement of the reference's unsplit HD update on GENERAL grids
+ * (the checker for the curvilinear / line-driven-wind rows of SURVEY.md 8a: a4, a8-a14).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may
+ * build, link or call this file.  The product (pluto_sirocco_b200/, libplutob200.so) never does.
+ *
+ * Parity status: PINNED against the compiled, unmodified reference (oracle/_ref/<cfg>/pluto built
+ * by oracle/build_ref.py with the user files of oracle/problems/) through the golden dumps of
+ * tests/golden/ (tests/test_gen_oracle_golden.py).
+ *
+ * Scope: PHYSICS HD, EOS IDEAL, GEOMETRY CARTESIAN or SPHERICAL, DIMENSIONS 1-3, uniform or
+ * non-uniform grids (grid->xl/xr are inputs: the reference's own set_grid.c output),
+ * RECONSTRUCTION LINEAR with every LIMITER, CHAR_LIMITING NO/YES, SHOCK_FLATTENING NO/MULTID,
+ * ENTROPY_SWITCH NO/ALWAYS, NTRACER >= 0, BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3,
+ * Solver tvdlf/hll/hllc, outflow/reflective/axisymmetric/eqtsymmetric/periodic boundaries plus
+ * the user-defined boundaries of the line-driven-wind problem, LINE_DRIVEN_WIND (VGradCalc +
+ * LineForce) and COOLING BLONDIN.
+ *
+ * Plain C17, scalar, pencil by pencil like the reference so that the operation order is the
+ * reference's; build with -ffp-contract=off.  Each function cites the reference file:line.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define RHO 0
+#define VX1 1
+#define VX2 2
+#define VX3 3
+#define PRS 4
+#define NFLX 5
+#define NVMAX 10
+
+#define FLAG_MINMOD 1      /* pluto.h:212-221 */
+#define FLAG_FLAT 2
+#define FLAG_HLL 4
+#define FLAG_ENTROPY 8
+#define FLAG_CONS2PRIM_FAIL 64
+
+#define CARTESIAN 1
+#define SPHERICAL 4
+
+#define MAXV(a, b) ((a) >= (b) ? (a) : (b))
+#define MINV(a, b) ((a) <= (b) ? (a) : (b))
+#define ABS_MIN(a, b) (fabs(a) < fabs(b) ? (a) : (b))
+#define MINMOD_LIMITER(a, b) ((a) * (b) > 0.0 ? (fabs(a) < fabs(b) ? (a) : (b)) : 0.0)
+
+typedef struct gen_cfg {
+  int ndim, nx[3], ng;
+  int ntracer, entropy;     /* NTRACER; ENTROPY_SWITCH: 0 NO, 1 ALWAYS */
+  int geometry;             /* CARTESIAN 1, SPHERICAL 4 (pluto.h:34-37) */
+  int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
+  int char_limiting;        /* CHAR_LIMITING */
+  int flattening;           /* SHOCK_FLATTENING MULTID */
+  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc */
+  int bc[6];                /* pluto.h:163-170; 8 userdef -> ldw_bc != 0 selects the built-in LDW fills */
+  double gamma, small_dn, small_pr;
+  const double *xl[3], *xr[3];   /* grid->xl, grid->xr incl. ghosts (np_tot each) */
+  int body_force;           /* bit 0: VECTOR */
+  const double *bf_g[3];    /* BodyForceVector at zone centres, [k][j][i] incl. ghosts */
+  /* --- line-driven wind (Src/LineDriven/line_connect.c), COOLING BLONDIN: see ldw section --- */
+  int ldw;                  /* LINE_DRIVEN_WIND != NO */
+  int ldw_bc;               /* user-defined boundaries / floors of Test_Problems/LineDrivenWind/cv_idl/init.c */
+  int nangles;              /* NFLUX_ANGLES */
+  const double *flux_r, *flux_t, *flux_p;   /* [nangles][k][j][i] */
+  double unit_length, unit_velocity, unit_density;
+  double mu, krad, alpharad, t_iso;
+  double dfloor, rho0, rho_alpha, cent_mass, disk_mdot;   /* g_inputParam[] of the LDW problem */
+  int cooling;              /* COOLING BLONDIN */
+  const double *cool_tab[8]; /* comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, xi, T_r? (see ldw section) */
+  double lx, tx;            /* L_star*f_x, T_x */
+} gen_cfg;
+
+typedef struct {
+  int tot[3], beg[3], end[3], nvar;
+  long sj, sk, sv;
+  double *x[3], *xl[3], *xr[3], *dx[3], *xgc[3], *inv_dx[3];
+  double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];   /* PLM_CoefficientsSet */
+  double *rt, *s, *sp, *dmu;
+  double *dV;          /* [k][j][i] */
+  double *A[3];        /* A[d] with one extra layer at index -1 along d */
+  long Aoff[3], Asj[3], Ask[3];
+  double *dx_dl[3];    /* [j][i] */
+} geom_t;
+
+/* ---------------------------------------------------------------------------------------
+ *  Grid-derived arrays: set_grid.c:135-138 (cell centres), set_geometry.c:20-290,
+ *  States/plm_coeffs.c:66-88
+ * --------------------------------------------------------------------------------------- */
+static double A_at(const geom_t *g, int d, int k, int j, int i) {
+  return g->A[d][g->Aoff[d] + (long)k * g->Ask[d] + (long)j * g->Asj[d] + i];
+}
+
+static geom_t *geom_new(const gen_cfg *c) {
+  geom_t *g = calloc(1, sizeof(geom_t));
+  g->nvar = NFLX + c->ntracer + (c->entropy ? 1 : 0);
+  for (int d = 0; d < 3; d++) {
+    int act = d < c->ndim;
+    int ng = act ? c->ng : 0, nx = act ? c->nx[d] : 1;
+    g->tot[d] = nx + 2 * ng;
+    g->beg[d] = ng;
+    g->end[d] = ng + nx - 1;
+  }
+  g->sj = g->tot[0];
+  g->sk = (long)g->tot[0] * g->tot[1];
+  g->sv = g->sk * g->tot[2];
+  for (int d = 0; d < 3; d++) {
+    int n = g->tot[d];
+    g->x[d] = calloc(n, 8); g->xl[d] = calloc(n, 8); g->xr[d] = calloc(n, 8); g->dx[d] = calloc(n, 8);
+    g->xgc[d] = calloc(n, 8); g->inv_dx[d] = calloc(n, 8);
+    g->cp[d] = calloc(n, 8); g->cm[d] = calloc(n, 8); g->wp[d] = calloc(n, 8); g->wm[d] = calloc(n, 8);
+    g->dp[d] = calloc(n, 8); g->dm[d] = calloc(n, 8);
+    for (int i = 0; i < n; i++) {
+      g->xl[d][i] = c->xl[d][i];
+      g->xr[d][i] = c->xr[d][i];
+      g->dx[d][i] = c->xr[d][i] - c->xl[d][i];
+      g->x[d][i] = 0.5 * (c->xl[d][i] + c->xr[d][i]);     /* set_grid.c:137 */
+    }
+  }
+  return g;
+}
+
+/* grid->dx is an INPUT of the reference's geometry (set_grid.c fills it together with xl/xr and
+ * xr - xl is not always bit-identical to it), so the caller may override it. */
+static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]) {
+  int n1 = g->tot[0], n2 = g->tot[1], n3 = g->tot[2];
+  for (int d = 0; d < 3; d++)
+    if (dxin && dxin[d]) for (int i = 0; i < g->tot[d]; i++) g->dx[d][i] = dxin[d][i];
+  double *x1 = g->x[0], *x2 = g->x[1], *dx1 = g->dx[0], *dx2 = g->dx[1], *dx3 = g->dx[2];
+  double *x1p = g->xr[0], *x1m = g->xl[0], *x2p = g->xr[1], *x2m = g->xl[1];
+  g->rt = calloc(n1, 8); g->s = calloc(n2, 8); g->sp = calloc(n2, 8); g->dmu = calloc(n2, 8);
+  for (int i = 0; i < n1; i++) {   /* set_geometry.c:83-97 */
+    double xL = x1m[i], xR = x1p[i];
+    if (c->geometry == CARTESIAN) { g->xgc[0][i] = x1[i]; g->rt[i] = x1[i]; }
+    else {
+      g->xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
+      g->rt[i] = (xR * xR * xR - xL * xL * xL) / (xR * xR - xL * xL) / 1.5;
+    }
+  }
+  for (int j = 0; j < n2; j++) {   /* set_geometry.c:103-116 */
+    double xL = x2m[j], xR = x2p[j];
+    if (c->geometry != SPHERICAL) g->xgc[1][j] = x2[j];
+    else {
+      g->xgc[1][j] = sin(xR) - sin(xL) + xL * cos(xL) - xR * cos(xR);
+      g->xgc[1][j] /= cos(xL) - cos(xR);
+      g->sp[j] = fabs(sin(xR));
+      g->s[j] = fabs(sin(x2[j]));
+      g->dmu[j] = fabs(cos(xL) - cos(xR));
+    }
+  }
+  for (int k = 0; k < n3; k++) g->xgc[2][k] = g->x[2][k];
+  /* volumes and areas: DIM_EXPAND keeps only the factors of the active dimensions */
+  int nd = c->ndim;
+  g->dV = calloc(g->sv, 8);
+  for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double v;
+    if (c->geometry == CARTESIAN) {
+      v = dx1[i]; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * dx3[k];
+    } else {
+      double dVr = fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
+      double dmu = fabs(cos(x2m[j]) - cos(x2p[j]));
+      v = dVr; if (nd > 1) v = v * dmu; if (nd > 2) v = v * dx3[k];
+    }
+    g->dV[k * g->sk + j * g->sj + i] = v;
+  }
+  for (int d = 0; d < 3; d++) {
+    int e1 = n1 + (d == 0), e2 = n2 + (d == 1), e3 = n3 + (d == 2);
+    g->Asj[d] = e1; g->Ask[d] = (long)e1 * e2;
+    g->Aoff[d] = (d == 0) ? 1 : (d == 1 ? g->Asj[d] : g->Ask[d]);
+    g->A[d] = calloc((long)e1 * e2 * e3, 8);
+  }
+  for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = -1; i < n1; i++) {
+    double a;
+    if (c->geometry == CARTESIAN) { a = 1.0; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * dx3[k]; }
+    else {
+      double dmu = fabs(cos(x2m[j]) - cos(x2p[j]));
+      a = (i == -1) ? x1m[0] * x1m[0] : x1p[i] * x1p[i];
+      if (nd > 1) a = a * dmu; if (nd > 2) a = a * dx3[k];
+    }
+    g->A[0][g->Aoff[0] + k * g->Ask[0] + j * g->Asj[0] + i] = a;
+  }
+  for (int k = 0; k < n3; k++) for (int j = -1; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double a;
+    if (c->geometry == CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    else {
+      a = fabs(x1[i]) * dx1[i];
+      if (nd > 1) a = a * ((j == -1) ? fabs(sin(x2m[0])) : fabs(sin(x2p[j])));
+      if (nd > 2) a = a * dx3[k];
+    }
+    g->A[1][g->Aoff[1] + k * g->Ask[1] + j * g->Asj[1] + i] = a;
+  }
+  for (int k = -1; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double a;
+    if (c->geometry == CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * 1.0; }
+    else { a = fabs(x1[i]) * dx1[i]; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * 1.0; }
+    g->A[2][g->Aoff[2] + k * g->Ask[2] + j * g->Asj[2] + i] = a;
+  }
+  for (int d = 0; d < 3; d++) g->dx_dl[d] = calloc((long)n1 * n2, 8);
+  for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {   /* set_geometry.c:236-254 */
+    long o = (long)j * n1 + i;
+    g->dx_dl[0][o] = 1.0;
+    if (c->geometry == CARTESIAN) { g->dx_dl[1][o] = 1.0; g->dx_dl[2][o] = 1.0; }
+    else { g->dx_dl[1][o] = 1.0 / g->rt[i]; g->dx_dl[2][o] = dx2[j] / (g->rt[i] * g->dmu[j]); }
+  }
+  for (int d = 0; d < 3; d++) {
+    for (int i = 0; i < g->tot[d]; i++) g->inv_dx[d][i] = 1.0 / g->dx[d][i];
+    /* plm_coeffs.c:66-88 (first and last zone excluded) */
+    double *dx = g->dx[d], *xgc = g->xgc[d], *xr = g->xr[d];
+    for (int i = 1; i <= g->tot[d] - 2; i++) {
+      g->wp[d][i] = dx[i] / (xgc[i + 1] - xgc[i]);
+      g->wm[d][i] = dx[i] / (xgc[i] - xgc[i - 1]);
+      g->cp[d][i] = (xgc[i + 1] - xgc[i]) / (xr[i] - xgc[i]);
+      g->cm[d][i] = (xgc[i] - xgc[i - 1]) / (xgc[i] - xr[i - 1]);
+      g->dp[d][i] = (xr[i] - xgc[i]) / dx[i];
+      g->dm[d][i] = (xgc[i] - xr[i - 1]) / dx[i];
+    }
+  }
+}
+
+static void geom_free(geom_t *g) {
+  for (int d = 0; d < 3; d++) {
+    free(g->x[d]); free(g->xl[d]); free(g->xr[d]); free(g->dx[d]); free(g->xgc[d]); free(g->inv_dx[d]);
+    free(g->cp[d]); free(g->cm[d]); free(g->wp[d]); free(g->wm[d]); free(g->dp[d]); free(g->dm[d]);
+    free(g->A[d]); free(g->dx_dl[d]);
+  }
+  free(g->rt); free(g->s); free(g->sp); free(g->dmu); free(g->dV);
+  free(g);
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Limiters: States/plm_coeffs.h:72-152.  uniform = UNIFORM_CARTESIAN_GRID (GEOMETRY CARTESIAN)
+ * --------------------------------------------------------------------------------------- */
+static double lim_apply(int kind, int uniform, double dvp, double dvm, double cp, double cm) {
+  double dv = 0.0;
+  switch (kind) {
+    case 1: dv = 0.0; break;
+    case 2: dv = (dvp * dvm > 0.0 ? ABS_MIN(dvp, dvm) : 0.0); break;
+    case 3:
+      if (uniform) dv = (dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0);
+      else dv = (dvp * dvm > 0.0 ? (dvp) * (dvm) * (cp * (dvm) + cm * (dvp)) /
+                 ((dvp) * (dvp) + (dvm) * (dvm) + (cp + cm - 2.0) * (dvp) * (dvm)) : 0.0);
+      break;
+    case 4:
+      if (dvp * dvm > 0.0) {
+        double qc = 0.5 * (dvm + dvp);
+        double scrh = uniform ? 2.0 * ABS_MIN(dvp, dvm) : ABS_MIN((dvp) * cp, (dvm) * cm);
+        dv = ABS_MIN(qc, scrh);
+      }
+      break;
+    case 5:
+      if (dvp * dvm > 0.0) {
+        double dpp = dvp * dvp, dmm = dvm * dvm;
+        dv = (dvp * (dmm + 1.e-18) + dvm * (dpp + 1.e-18)) / (dpp + dmm + 1.e-18);
+      }
+      break;
+    case 6:
+      if (uniform) dv = (dvp * dvm > 0.0 ? 1.5 * dvp * dvm * (dvm + dvp) / (dvp * dvp + dvm * dvm + dvp * dvm) : 0.0);
+      else if (dvp * dvm > 0.0) {
+        double den = 2.0 * (dvp) * (dvp) + 2.0 * (dvm) * (dvm) + (cp + cm - 2.0) * (dvp) * (dvm);
+        dv = dvp * dvm * ((1.0 + cp) * (dvm) + (1.0 + cm) * (dvp)) / den;
+      }
+      break;
+    case 7:
+      if (dvp * dvm > 0.0) {
+        double ddp = 0.25 * (dvp + 3.0 * dvm), ddm = 0.25 * (dvm + 3.0 * dvp);
+        double d2 = 2.0 * ABS_MIN(dvp, dvm);
+        d2 = ABS_MIN(d2, ddp);
+        dv = ABS_MIN(d2, ddm);
+      }
+      break;
+    case 8:   /* SET_GM_LIMITER, plm_coeffs.h:96-100 */
+      if (dvp * dvm > 0.0) {
+        double qc = 0.5 * (dvm + dvp), scrh = ABS_MIN((dvp) * (cp), (dvm) * (cm));
+        dv = ABS_MIN(qc, scrh);
+      }
+      break;
+  }
+  return dv;
+}
+
+/* HD/mappers.c:26-56 (+ scalars incl. ENTR: u = rho*v) */
+static void prim_to_cons(const gen_cfg *c, int nvar, const double *v, double *u) {
+  double gmm1 = c->gamma - 1.0, rho = v[RHO];
+  u[RHO] = rho;
+  u[VX1] = rho * v[VX1];
+  u[VX2] = rho * v[VX2];
+  u[VX3] = rho * v[VX3];
+  u[PRS] = v[VX1] * v[VX1] + v[VX2] * v[VX2] + v[VX3] * v[VX3];
+  u[PRS] = 0.5 * rho * u[PRS] + v[PRS] / gmm1;
+  for (int nv = NFLX; nv < nvar; nv++) u[nv] = rho * v[nv];
+}
+
+/* HD/mappers.c:98-290 with ENTROPY_SWITCH */
+static int cons_to_prim(const gen_cfg *c, int nvar, double *u, double *v, uint16_t *flag) {
+  int fail = 0;
+  double gmm1 = c->gamma - 1.0;
+  int ENTR = nvar - 1;
+  double m2 = u[VX1] * u[VX1] + u[VX2] * u[VX2] + u[VX3] * u[VX3];
+  if (u[RHO] < 0.0) { u[RHO] = c->small_dn; *flag |= FLAG_CONS2PRIM_FAIL; fail = 1; }
+  double rho = v[RHO] = u[RHO];
+  double tau = 1.0 / u[RHO];
+  v[VX1] = u[VX1] * tau;
+  v[VX2] = u[VX2] * tau;
+  v[VX3] = u[VX3] * tau;
+  double kin = 0.5 * m2 / u[RHO];
+  if (u[PRS] < 0.0) { u[PRS] = c->small_pr / gmm1 + kin; *flag |= FLAG_CONS2PRIM_FAIL; fail = 1; }
+  int use_entropy = c->entropy && (*flag & FLAG_ENTROPY);
+  if (use_entropy) {
+    double rhog1 = pow(rho, gmm1);
+    v[PRS] = u[ENTR] * rhog1;
+    if (v[PRS] < 0.0) { v[PRS] = c->small_pr; *flag |= FLAG_CONS2PRIM_FAIL; fail = 1; }
+    u[PRS] = v[PRS] / gmm1 + kin;
+  } else {
+    v[PRS] = gmm1 * (u[PRS] - kin);
+    if (v[PRS] < 0.0) {
+      v[PRS] = c->small_pr;
+      u[PRS] = v[PRS] / gmm1 + kin;
+      *flag |= FLAG_CONS2PRIM_FAIL;
+      fail = 1;
+    }
+    if (c->entropy) u[ENTR] = v[PRS] / pow(rho, gmm1);
+  }
+  for (int nv = NFLX; nv < nvar; nv++) v[nv] = u[nv] * tau;
+  return fail;
+}
+
+/* 1-D work arrays of one pencil (Sweep, tools.c:261-335) */
+typedef struct {
+  double (*v)[NVMAX], (*vp)[NVMAX], (*vm)[NVMAX], (*flux)[NVMAX], (*rhs)[NVMAX], (*fA)[NVMAX];
+  double *press, *cmax;
+  uint16_t *flag;
+} sweep_t;
+
+static void sweep_alloc(sweep_t *s, int n) {
+  s->v = calloc(n + 4, sizeof(*s->v)); s->vp = calloc(n + 4, sizeof(*s->vp)); s->vm = calloc(n + 4, sizeof(*s->vm));
+  s->flux = calloc(n + 4, sizeof(*s->flux)); s->rhs = calloc(n + 4, sizeof(*s->rhs)); s->fA = calloc(n + 4, sizeof(*s->fA));
+  s->press = calloc(n + 4, 8); s->cmax = calloc(n + 4, 8); s->flag = calloc(n + 4, sizeof(uint16_t));
+  s->fA += 1;     /* fA[-1] is used by the curvilinear rhs */
+  s->flux += 1; s->press += 1; s->cmax += 1;
+}
+static void sweep_free(sweep_t *s) {
+  free(s->v); free(s->vp); free(s->vm); free(s->flux - 1); free(s->rhs); free(s->fA - 1);
+  free(s->press - 1); free(s->cmax - 1); free(s->flag);
+}
+
+/* States/plm_states.c:83-337 (CHAR_LIMITING NO) and :481-690 (CHAR_LIMITING YES) */
+static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end) {
+  int nvar = g->nvar;
+  int uniform = (c->geometry == CARTESIAN);   /* plm_coeffs.h:23-29 */
+  int VXn = 1 + dir, VXt = 1 + (dir + 1) % 3, VXb = 1 + (dir + 2) % 3;
+  double dvp[NVMAX], dvm[NVMAX], dv_lim[NVMAX];
+  for (int i = beg; i <= end; i++) {
+    double cp, cm, wp, wm, dp, dm;
+    const double *v = s->v[i];
+    if (uniform) {
+      cp = cm = 2.0; dp = dm = 0.5; wp = wm = 1.0;
+      for (int nv = 0; nv < nvar; nv++) { dvp[nv] = s->v[i + 1][nv] - v[nv]; dvm[nv] = v[nv] - s->v[i - 1][nv]; }
+    } else {
+      cp = g->cp[dir][i]; cm = g->cm[dir][i]; wp = g->wp[dir][i]; wm = g->wm[dir][i];
+      dp = g->dp[dir][i]; dm = g->dm[dir][i];
+      for (int nv = 0; nv < nvar; nv++) {
+        dvp[nv] = (s->v[i + 1][nv] - v[nv]) * wp;
+        dvm[nv] = (v[nv] - s->v[i - 1][nv]) * wm;
+      }
+    }
+    if (!c->char_limiting) {
+      if (c->flattening) {   /* plm_states.c:177-195 */
+        if (s->flag[i] & FLAG_FLAT) {
+          for (int nv = 0; nv < nvar; nv++) s->vp[i][nv] = s->vm[i][nv] = v[nv];
+          continue;
+        } else if (s->flag[i] & FLAG_MINMOD) {
+          for (int nv = 0; nv < nvar; nv++) {
+            dv_lim[nv] = lim_apply(2, uniform, dvp[nv], dvm[nv], cp, cm);
+            s->vp[i][nv] = v[nv] + dv_lim[nv] * dp;
+            s->vm[i][nv] = v[nv] - dv_lim[nv] * dm;
+          }
+          continue;
+        }
+      }
+      for (int nv = 0; nv < nvar; nv++) {
+        int kind;
+        if (c->limiter == 0) {
+          if (nv == RHO) kind = 4; else if (nv == PRS) kind = 2; else if (nv >= NFLX) kind = 4; else kind = 3;
+        } else kind = c->limiter;
+        dv_lim[nv] = lim_apply(kind, uniform, dvp[nv], dvm[nv], cp, cm);
+      }
+      for (int nv = 0; nv < nvar; nv++) {
+        s->vp[i][nv] = v[nv] + dv_lim[nv] * dp;
+        s->vm[i][nv] = v[nv] - dv_lim[nv] * dm;
+      }
+    } else {
+      /* SoundSpeed2 (eos.c:33), PrimEigenvectors (eigenv.c:92-200), PrimToChar (eigenv.c:575-616) */
+      double a2 = c->gamma * v[PRS] / v[RHO];
+      double cs = sqrt(a2), rhocs = v[RHO] * cs, rho_cs = v[RHO] / cs;
+      double R[NFLX][NFLX], kstp[NFLX], cpk[NFLX], cmk[NFLX], dwp[NFLX], dwm[NFLX], dw_lim[NFLX];
+      memset(R, 0, sizeof(R));
+      R[RHO][0] = 0.5 * rho_cs; R[VXn][0] = -0.5; R[PRS][0] = 0.5 * rhocs;
+      R[RHO][1] = 0.5 * rho_cs; R[VXn][1] = 0.5;  R[PRS][1] = 0.5 * rhocs;
+      R[RHO][2] = 1.0; R[VXt][3] = 1.0; R[VXb][4] = 1.0;
+      double L0n = -1.0, L0p = 1.0 / rhocs, L1n = 1.0, L1p = 1.0 / rhocs, L2p = -1.0 / a2;
+      for (int k = 0; k < NFLX; k++) kstp[k] = 2.0;
+      kstp[0] = kstp[1] = 1.0;
+      for (int k = 0; k < NFLX; k++) {
+        if (uniform) cpk[k] = cmk[k] = kstp[k];
+        else { cpk[k] = (2.0 - cp) + (cp - 1.0) * kstp[k]; cmk[k] = (2.0 - cm) + (cm - 1.0) * kstp[k]; }
+      }
+      dwm[0] = L0n * dvm[VXn] + L0p * dvm[PRS]; dwm[1] = L1n * dvm[VXn] + L1p * dvm[PRS];
+      dwm[2] = dvm[RHO] + L2p * dvm[PRS]; dwm[3] = dvm[VXt]; dwm[4] = dvm[VXb];
+      dwp[0] = L0n * dvp[VXn] + L0p * dvp[PRS]; dwp[1] = L1n * dvp[VXn] + L1p * dvp[PRS];
+      dwp[2] = dvp[RHO] + L2p * dvp[PRS]; dwp[3] = dvp[VXt]; dwp[4] = dvp[VXb];
+      if (c->flattening && (s->flag[i] & FLAG_FLAT)) {
+        for (int k = NFLX; k--;) dw_lim[k] = 0.0;
+      } else if (c->flattening && (s->flag[i] & FLAG_MINMOD)) {
+        for (int k = NFLX; k--;) dw_lim[k] = lim_apply(2, uniform, dwp[k], dwm[k], cp, cm);
+      } else {
+        for (int k = NFLX; k--;) {
+          if (c->limiter == 0) dw_lim[k] = lim_apply(8, uniform, dwp[k], dwm[k], cpk[k], cmk[k]);
+          else dw_lim[k] = lim_apply(c->limiter, uniform, dwp[k], dwm[k], cp, cm);
+        }
+      }
+      for (int nv = NFLX; nv--;) {
+        double dc = 0.0;
+        for (int k = 0; k < NFLX; k++) dc += dw_lim[k] * R[nv][k];
+        if (dvp[nv] * dvm[nv] > 0.0) {
+          double d2v = ABS_MIN(cp * dvp[nv], cm * dvm[nv]);
+          dv_lim[nv] = MINMOD_LIMITER(d2v, dc);
+        } else dv_lim[nv] = 0.0;
+      }
+      for (int nv = NFLX; nv < nvar; nv++)
+        dv_lim[nv] = lim_apply(c->limiter == 0 ? 4 : c->limiter, uniform, dvp[nv], dvm[nv], cp, cm);
+      for (int nv = nvar; nv--;) {
+        s->vp[i][nv] = v[nv] + dv_lim[nv] * dp;
+        s->vm[i][nv] = v[nv] - dv_lim[nv] * dm;
+      }
+    }
+  }
+}
+
+/* HD/hllc.c:28-178, HD/hll.c:30-96, HD/tvdlf.c:38-130, HD/hll_speed.c:76-90, HD/fluxes.c:36-47,
+ * adv_flux.c:47-134 (scalars + entropy) */
+static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end, double *maxMach) {
+  int nvar = g->nvar;
+  int VXn = 1 + dir, VXt = 1 + (dir + 1) % 3, VXb = 1 + (dir + 2) % 3;
+  for (int i = beg; i <= end; i++) {
+    const double *vL = s->vp[i], *vR = s->vm[i + 1];
+    double uL[NVMAX], uR[NVMAX], fL[NFLX], fR[NFLX];
+    prim_to_cons(c, nvar, vL, uL);
+    prim_to_cons(c, nvar, vR, uR);
+    double a2L = c->gamma * vL[PRS] / vL[RHO];
+    double a2R = c->gamma * vR[PRS] / vR[RHO];
+    fL[RHO] = uL[VXn]; fL[VX1] = uL[VX1] * vL[VXn]; fL[VX2] = uL[VX2] * vL[VXn];
+    fL[VX3] = uL[VX3] * vL[VXn]; fL[PRS] = (uL[PRS] + vL[PRS]) * vL[VXn];
+    fR[RHO] = uR[VXn]; fR[VX1] = uR[VX1] * vR[VXn]; fR[VX2] = uR[VX2] * vR[VXn];
+    fR[VX3] = uR[VX3] * vR[VXn]; fR[PRS] = (uR[PRS] + vR[PRS]) * vR[VXn];
+    double pL = vL[PRS], pR = vR[PRS];
+    double *flux = s->flux[i];
+    if (c->solver == 1) {
+      double vRL[NVMAX];
+      for (int nv = 0; nv < nvar; nv++) vRL[nv] = 0.5 * (vL[nv] + vR[nv]);
+      vRL[VXn] = 0.5 * (fabs(vL[VXn]) + fabs(vR[VXn]));
+      double a2 = c->gamma * vRL[PRS] / vRL[RHO];
+      double a = sqrt(a2);
+      double cmin = vRL[VXn] - a, cmaxv = vRL[VXn] + a;
+      s->cmax[i] = MAXV(fabs(cmaxv), fabs(cmin));
+      *maxMach = MAXV(*maxMach, fabs(vRL[VXn]) / sqrt(a2));
+      for (int nv = NFLX; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
+      s->press[i] = 0.5 * (pL + pR);
+    } else {
+      double aL = sqrt(a2L), aR = sqrt(a2R);
+      double SL = MINV(vL[VXn] - aL, vR[VXn] - aR);
+      double SR = MAXV(vL[VXn] + aL, vR[VXn] + aR);
+      double scrh = fabs(vL[VXn]) + fabs(vR[VXn]);
+      scrh /= aL + aR;
+      *maxMach = MAXV(scrh, *maxMach);
+      s->cmax[i] = MAXV(fabs(SL), fabs(SR));
+      if (SL > 0.0) {
+        for (int nv = NFLX; nv--;) flux[nv] = fL[nv];
+        s->press[i] = pL;
+      } else if (SR < 0.0) {
+        for (int nv = NFLX; nv--;) flux[nv] = fR[nv];
+        s->press[i] = pR;
+      } else if (c->solver == 2 ||
+                 (c->flattening && ((s->flag[i] & FLAG_HLL) || (s->flag[i + 1] & FLAG_HLL)))) {
+        scrh = 1.0 / (SR - SL);
+        for (int nv = NFLX; nv--;) {
+          flux[nv] = SL * SR * (uR[nv] - uL[nv]) + SR * fL[nv] - SL * fR[nv];
+          flux[nv] *= scrh;
+        }
+        s->press[i] = (SR * pL - SL * pR) * scrh;
+      } else {
+        double usL[NFLX], usR[NFLX];
+        double vxr = vR[VXn], vxl = vL[VXn];
+        double qL = vL[PRS] + uL[VXn] * (vL[VXn] - SL);     /* hllc.c:112-116 */
+        double qR = vR[PRS] + uR[VXn] * (vR[VXn] - SR);
+        double wL = vL[RHO] * (vL[VXn] - SL);
+        double wR = vR[RHO] * (vR[VXn] - SR);
+        double vs = (qR - qL) / (wR - wL);
+        usL[RHO] = uL[RHO] * (SL - vxl) / (SL - vs);
+        usR[RHO] = uR[RHO] * (SR - vxr) / (SR - vs);
+        usL[VXn] = usL[RHO] * vs;       usR[VXn] = usR[RHO] * vs;
+        usL[VXt] = usL[RHO] * vL[VXt];  usR[VXt] = usR[RHO] * vR[VXt];
+        usL[VXb] = usL[RHO] * vL[VXb];  usR[VXb] = usR[RHO] * vR[VXb];
+        usL[PRS] = uL[PRS] / vL[RHO] + (vs - vxl) * (vs + vL[PRS] / (vL[RHO] * (SL - vxl)));
+        usR[PRS] = uR[PRS] / vR[RHO] + (vs - vxr) * (vs + vR[PRS] / (vR[RHO] * (SR - vxr)));
+        usL[PRS] *= usL[RHO];
+        usR[PRS] *= usR[RHO];
+        if (vs >= 0.0) {
+          for (int nv = NFLX; nv--;) flux[nv] = fL[nv] + SL * (usL[nv] - uL[nv]);
+          s->press[i] = pL;
+        } else {
+          for (int nv = NFLX; nv--;) flux[nv] = fR[nv] + SR * (usR[nv] - uR[nv]);
+          s->press[i] = pR;
+        }
+      }
+    }
+    const double *ts = flux[RHO] > 0.0 ? vL : vR;
+    for (int nv = NFLX; nv < nvar; nv++) flux[nv] = flux[RHO] * ts[nv];
+    if (c->entropy) {
+      int ENTR = nvar - 1;
+      if (flux[RHO] >= 0.0) flux[ENTR] = vL[ENTR] * flux[RHO];
+      else flux[ENTR] = vR[ENTR] * flux[RHO];
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Boundaries: boundary.c:228-459 (side order, full transverse range), fills :617-767,
+ *  FlipSign :503-610 (reflective: vn; axisymmetric: vn and vphi; eqtsymmetric: vn)
+ * --------------------------------------------------------------------------------------- */
+static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side);
+static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc);
+
+static void boundary(const gen_cfg *c, const geom_t *g, double *Vc) {
+  int nvar = g->nvar;
+  if (c->ldw_bc) ldw_internal_floor(c, g, Vc);        /* boundary.c:126-128, side == 0 */
+  for (int side = 0; side < 2 * c->ndim; side++) {
+    int type = c->bc[side], dir = side / 2, hi = side & 1;
+    if (type == 8) { if (c->ldw_bc) ldw_userdef_side(c, g, Vc, side); continue; }
+    if (type != 1 && type != 2 && type != 3 && type != 4 && type != 5) continue;
+    int nb = g->beg[dir], ne = g->end[dir], nxd = ne - nb + 1;
+    int lo[3] = {0, 0, 0}, up[3] = {g->tot[0] - 1, g->tot[1] - 1, g->tot[2] - 1};
+    if (hi) { lo[dir] = ne + 1; up[dir] = g->tot[dir] - 1; }
+    else { lo[dir] = 0; up[dir] = nb - 1; }
+    for (int nv = 0; nv < nvar; nv++) {
+      double sgn = 1.0;
+      if ((type == 2 || type == 3 || type == 4) && nv == 1 + dir) sgn = -1.0;
+      if (type == 3 && nv == VX3 && c->geometry == SPHERICAL) sgn = -1.0;   /* boundary.c:560-575: iVPHI */
+      int mirror = (type == 2 || type == 3 || type == 4);
+      double *q = Vc + nv * g->sv;
+      for (int k = lo[2]; k <= up[2]; k++)
+        for (int j = lo[1]; j <= up[1]; j++)
+          for (int i = lo[0]; i <= up[0]; i++) {
+            int idx[3] = {i, j, k};
+            int n = idx[dir], src;
+            if (type == 1) src = hi ? ne : nb;
+            else if (type == 5) src = hi ? n - nxd : n + nxd;
+            else src = hi ? 2 * ne + 1 - n : 2 * nb - 1 - n;
+            idx[dir] = src;
+            double val = q[idx[2] * g->sk + idx[1] * g->sj + idx[0]];
+            q[k * g->sk + j * g->sj + i] = mirror ? sgn * val : val;
+          }
+    }
+  }
+  if (c->entropy) {      /* ComputeEntropy, entropy_switch.c:14-39, Entropy eos.c:77-103 */
+    int ENTR = nvar - 1;
+    for (long o = 0; o < g->sv; o++) Vc[ENTR * g->sv + o] = Vc[PRS * g->sv + o] / pow(Vc[RHO * g->sv + o], c->gamma);
+  }
+}
+
+/* flag_shock.c:81-260 */
+static void flag_shock(const gen_cfg *c, const geom_t *g, const double *Vc, uint16_t *flag) {
+  const double *pt = Vc + PRS * g->sv;
+  const double *vx[3] = {Vc + VX1 * g->sv, Vc + VX2 * g->sv, Vc + VX3 * g->sv};
+  long st[3] = {1, g->sj, g->sk};
+  if (c->entropy) for (long o = 0; o < g->sv; o++) flag[o] |= FLAG_ENTROPY;
+  int inc[3] = {c->ndim > 0, c->ndim > 1, c->ndim > 2};
+  for (int k = inc[2]; k < g->tot[2] - inc[2]; k++)
+    for (int j = inc[1]; j < g->tot[1] - inc[1]; j++)
+      for (int i = inc[0]; i < g->tot[0] - inc[0]; i++) {
+        long o = k * g->sk + j * g->sj + i;
+        int idx[3] = {i, j, k};
+        double dvx[3] = {0, 0, 0}, divv;
+        for (int d = 0; d < c->ndim; d++) {
+          if (c->geometry == CARTESIAN) dvx[d] = (vx[d][o + st[d]] - vx[d][o - st[d]]) / g->dx[d][idx[d]];
+          else {
+            int im[3] = {i, j, k};
+            im[d] -= 1;
+            dvx[d] = A_at(g, d, k, j, i) * (vx[d][o + st[d]] + vx[d][o]) -
+                     A_at(g, d, im[2], im[1], im[0]) * (vx[d][o - st[d]] + vx[d][o]);
+          }
+        }
+        divv = dvx[0];
+        if (c->ndim > 1) divv = divv + dvx[1];
+        if (c->ndim > 2) divv = divv + dvx[2];
+        if (c->geometry != CARTESIAN) divv = divv / g->dV[o];
+        if (divv < 0.0) {
+          double pt_min = pt[o], gradp = 0.0;
+          for (int d = 0; d < c->ndim; d++) {
+            double m = MINV(pt[o + st[d]], pt[o - st[d]]);
+            pt_min = MINV(pt_min, m);
+          }
+          for (int d = 0; d < c->ndim; d++) {
+            double dpx = fabs(pt[o + st[d]] - pt[o - st[d]]);
+            gradp = (d == 0) ? dpx : gradp + dpx;
+          }
+          if (c->flattening && gradp > 5.0 * pt_min) {
+            flag[o] |= FLAG_HLL | FLAG_MINMOD;
+            for (int d = 0; d < c->ndim; d++) { flag[o + st[d]] |= FLAG_MINMOD; flag[o - st[d]] |= FLAG_MINMOD; }
+          }
+        }
+      }
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Line-driven wind and BLONDIN cooling hooks (filled in below)
+ * --------------------------------------------------------------------------------------- */
+static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, double *dvds);
+static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad);
+
+/* Time_Stepping/update_stage.c:35-394 + MHD/rhs.c:84-420 + MHD/rhs_source.c:101-470 */
+static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, double *Uc, const uint16_t *flag,
+                         double *C_dt, double *dvds, double dt, int stage, double *invDt_hyp, double *maxMach) {
+  int nvar = g->nvar;
+  int nmax = MAXV(g->tot[0], MAXV(g->tot[1], g->tot[2]));
+  sweep_t s;
+  sweep_alloc(&s, nmax);
+  if (c->ndim > 1 && stage == 1) memset(C_dt, 0, sizeof(double) * g->sv);
+  if (c->ldw) ldw_vgrad_calc(c, g, Vc, dvds);         /* update_stage.c:116-118 */
+  double *inv_dl = calloc(nmax, 8);
+  for (int dir = 0; dir < c->ndim; dir++) {
+    int VXn = 1 + dir;
+    int ntot = g->tot[dir], nbeg = g->beg[dir], nend = g->end[dir];
+    long st = dir == 0 ? 1 : (dir == 1 ? g->sj : g->sk);
+    int t1 = (dir + 1) % 3, t2 = (dir + 2) % 3;
+    int idx[3];
+    /* BOX_TRANSVERSE_LOOP: the direction after dir varies fastest (macros.h / rbox.c) */
+    for (idx[t2] = g->beg[t2]; idx[t2] <= g->end[t2]; idx[t2]++)
+      for (idx[t1] = g->beg[t1]; idx[t1] <= g->end[t1]; idx[t1]++) {
+        idx[dir] = 0;
+        long base = idx[2] * g->sk + idx[1] * g->sj + idx[0];
+        for (int n = 0; n < ntot; n++) {
+          for (int nv = 0; nv < nvar; nv++) s.v[n][nv] = Vc[nv * g->sv + base + n * st];
+          s.flag[n] = flag[base + n * st];
+        }
+        states(c, g, &s, dir, nbeg - 1, nend + 1);
+        riemann(c, g, &s, dir, nbeg - 1, nend, maxMach);
+        /* ---- RightHandSide ---- */
+        int i = idx[0], j = idx[1], k = idx[2];
+        if (c->geometry == CARTESIAN) {
+          for (int n = nbeg; n <= nend; n++) {
+            double scrh = dt / g->dx[dir][n];
+            for (int nv = 0; nv < nvar; nv++) s.rhs[n][nv] = -scrh * (s.flux[n][nv] - s.flux[n - 1][nv]);
+            s.rhs[n][VXn] -= scrh * (s.press[n] - s.press[n - 1]);
+          }
+        } else {
+          /* TotalFlux rhs.c:530-600: fA = F A, fA[iMPHI] *= |x1p| (r) or |sp| (theta) */
+          for (int n = nbeg - 1; n <= nend; n++) {
+            int q[3] = {i, j, k};
+            q[dir] = n;
+            double A = A_at(g, dir, q[2], q[1], q[0]);
+            for (int nv = 0; nv < nvar; nv++) s.fA[n][nv] = s.flux[n][nv] * A;
+            if (dir == 0) s.fA[n][VX3] *= fabs(g->xr[0][n]);
+            else if (dir == 1) s.fA[n][VX3] *= fabs(g->sp[n]);
+          }
+          for (int n = nbeg; n <= nend; n++) {
+            int q[3] = {i, j, k};
+            q[dir] = n;
+            long o = q[2] * g->sk + q[1] * g->sj + q[0];
+            double dtdV = dt / g->dV[o], dtdl;
+            if (dir == 0) dtdl = dt / g->dx[0][n];
+            else dtdl = dt / g->dx[dir][n] * g->dx_dl[dir][(long)q[1] * g->tot[0] + q[0]];
+            for (int nv = 0; nv < nvar; nv++) s.rhs[n][nv] = -dtdV * (s.fA[n][nv] - s.fA[n - 1][nv]);
+            s.rhs[n][VXn] -= dtdl * (s.press[n] - s.press[n - 1]);
+            if (dir == 0) s.rhs[n][VX3] /= fabs(g->x[0][n]);
+            else if (dir == 1) s.rhs[n][VX3] /= fabs(g->s[n]);
+          }
+        }
+        /* ---- RightHandSideSource ---- */
+        for (int n = nbeg; n <= nend; n++) {
+          int q[3] = {i, j, k};
+          q[dir] = n;
+          long o = q[2] * g->sk + q[1] * g->sj + q[0];
+          double vc[NVMAX];
+          const double *vg = s.v[n];
+          if (c->geometry == SPHERICAL && dir == 0) {          /* rhs_source.c:229-241 */
+            double r_1 = 1.0 / g->x[0][n];
+            for (int nv = 0; nv < nvar; nv++) vc[nv] = 0.5 * (s.vp[n][nv] + s.vm[n][nv]);
+            vg = vc;
+            double vphi = vc[VX3];
+            double Sm = vc[RHO] * (vc[VX2] * vc[VX2] + vphi * vphi);
+            s.rhs[n][VX1] += dt * Sm * r_1;
+          } else if (c->geometry == SPHERICAL && dir == 1) {   /* rhs_source.c:311-357 */
+            double r_1 = 1.0 / g->rt[i];
+            double ct = 1.0 / tan(g->x[1][n]);
+            for (int nv = 0; nv < nvar; nv++) vc[nv] = s.v[n][nv];
+            vg = vc;
+            double vphi = vc[VX3];
+            double Sm = vc[RHO] * (-vc[VX2] * vc[VX1] + ct * vphi * vphi);
+            s.rhs[n][VX2] += dt * Sm * r_1;
+          }
+          double gv[3];
+          for (int pass = 0; pass < 2; pass++) {
+            /* pass 0: BodyForceVector (rhs_source.c:253-272,360-376,428-440);
+             * pass 1: LineForce, same pattern (rhs_source.c:284-297,386-396,448-458) */
+            if (pass == 0) {
+              if (!(c->body_force & 1)) continue;
+              gv[0] = c->bf_g[0][o]; gv[1] = c->bf_g[1][o]; gv[2] = c->bf_g[2][o];
+            } else {
+              if (!c->ldw) continue;
+              ldw_line_force(c, g, vg, dvds, o, gv);
+            }
+            s.rhs[n][VXn] += dt * vg[RHO] * gv[dir];
+            s.rhs[n][PRS] += dt * 0.5 * (s.flux[n][RHO] + s.flux[n - 1][RHO]) * gv[dir];
+            if (dir == 0 && c->ndim == 1) {
+              s.rhs[n][VX2] += dt * vg[RHO] * gv[1];
+              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX2] * gv[1];
+              s.rhs[n][VX3] += dt * vg[RHO] * gv[2];
+              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
+            }
+            if (dir == 1 && c->ndim == 2) {
+              s.rhs[n][VX3] += dt * vg[RHO] * gv[2];
+              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
+            }
+          }
+        }
+        for (int n = nbeg; n <= nend; n++) {
+          double *U = Uc + (base + n * st) * nvar;
+          for (int nv = 0; nv < nvar; nv++) U[nv] += s.rhs[n][nv];
+        }
+        /* GetInverse_dl, set_geometry.c:303-375 */
+        for (int n = 0; n < ntot; n++) {
+          inv_dl[n] = g->inv_dx[dir][n];
+          if (c->geometry == SPHERICAL && dir == 1) inv_dl[n] = g->inv_dx[1][n] * (1.0 / g->x[0][i]);
+          if (c->geometry == SPHERICAL && dir == 2) inv_dl[n] = g->inv_dx[2][n] * (1.0 / g->x[0][i]) / sin(g->x[1][j]);
+        }
+        if (c->ndim > 1) {
+          if (stage == 1)
+            for (int n = nbeg; n <= nend; n++)
+              C_dt[base + n * st] += 0.5 * (s.cmax[n - 1] + s.cmax[n]) * inv_dl[n];
+        } else {
+          for (int n = nbeg - 1; n <= nend; n++) *invDt_hyp = MAXV(*invDt_hyp, s.cmax[n] * inv_dl[n]);
+        }
+      }
+  }
+  if (c->ndim > 1 && stage == 1) {
+    for (int k = g->beg[2]; k <= g->end[2]; k++)
+      for (int j = g->beg[1]; j <= g->end[1]; j++)
+        for (int i = g->beg[0]; i <= g->end[0]; i++)
+          *invDt_hyp = MAXV(*invDt_hyp, C_dt[k * g->sk + j * g->sj + i]);
+    *invDt_hyp /= (double)c->ndim;
+  }
+  free(inv_dl);
+  sweep_free(&s);
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  AdvanceStep(): Time_Stepping/rk_step.c:29-322
+ * --------------------------------------------------------------------------------------- */
+typedef struct gen_ctx {
+  gen_cfg c;
+  geom_t *g;
+  double *Uc, *U0, *C_dt, *dvds;
+  uint16_t *flag;
+} gen_ctx;
+
+void *gen_create(const gen_cfg *c, const double *dx1, const double *dx2, const double *dx3) {
+  gen_ctx *x = calloc(1, sizeof(gen_ctx));
+  x->c = *c;
+  x->g = geom_new(c);
+  const double *dxin[3] = {dx1, dx2, dx3};
+  geom_finish(c, x->g, dxin);
+  long n = x->g->sv * x->g->nvar;
+  x->Uc = calloc(n, 8); x->U0 = calloc(n, 8); x->C_dt = calloc(x->g->sv, 8);
+  x->flag = calloc(x->g->sv, sizeof(uint16_t));
+  if (c->ldw) x->dvds = calloc((long)c->nangles * x->g->sv, 8);
+  return x;
+}
+void gen_destroy(void *p) {
+  gen_ctx *x = p;
+  geom_free(x->g);
+  free(x->Uc); free(x->U0); free(x->C_dt); free(x->flag); free(x->dvds);
+  free(x);
+}
+int gen_nvar(void *p) { return ((gen_ctx *)p)->g->nvar; }
+void gen_boundary(void *p, double *Vc) { gen_ctx *x = p; boundary(&x->c, x->g, Vc); }
+/* copies of derived geometry for the tests: which = 0 dV, 1..3 A[d] (without the -1 layer) */
+void gen_get_geometry(void *p, int which, double *out) {
+  gen_ctx *x = p;
+  const geom_t *g = x->g;
+  for (int k = 0; k < g->tot[2]; k++) for (int j = 0; j < g->tot[1]; j++) for (int i = 0; i < g->tot[0]; i++) {
+    long o = k * g->sk + j * g->sj + i;
+    out[o] = which == 0 ? g->dV[o] : A_at(g, which - 1, k, j, i);
+  }
+}
+
+int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *maxMach) {
+  gen_ctx *x = p;
+  const gen_cfg *c = &x->c;
+  const geom_t *g = x->g;
+  int nvar = g->nvar, nfail = 0;
+  long ntot = g->sv * nvar;
+  memset(x->flag, 0, g->sv * sizeof(uint16_t));          /* main.c:258-261 */
+  double v[NVMAX];
+  for (int stage = 1; stage <= c->rk; stage++) {
+    boundary(c, g, Vc);
+    if (stage == 1) {
+      if (c->flattening || c->entropy) flag_shock(c, g, Vc, x->flag);   /* rk_step.c:123-125 */
+      for (int k = g->beg[2]; k <= g->end[2]; k++)
+        for (int j = g->beg[1]; j <= g->end[1]; j++)
+          for (int i = g->beg[0]; i <= g->end[0]; i++) {
+            long o = k * g->sk + j * g->sj + i;
+            for (int nv = 0; nv < nvar; nv++) v[nv] = Vc[nv * g->sv + o];
+            prim_to_cons(c, nvar, v, x->Uc + o * nvar);
+          }
+      memcpy(x->U0, x->Uc, ntot * 8);
+    }
+    double hyp = 0.0;
+    update_stage(c, g, Vc, x->Uc, x->flag, x->C_dt, x->dvds, dt, stage, &hyp, maxMach);
+    *invDt_hyp = MAXV(*invDt_hyp, hyp);
+    double w0 = 0, wc = 1;
+    if (stage == 2) { w0 = c->rk == 2 ? 0.5 : 0.75; wc = c->rk == 2 ? 0.5 : 0.25; }
+    for (int k = g->beg[2]; k <= g->end[2]; k++)
+      for (int j = g->beg[1]; j <= g->end[1]; j++)
+        for (int i = g->beg[0]; i <= g->end[0]; i++) {
+          long o = k * g->sk + j * g->sj + i;
+          double *U = x->Uc + o * nvar, *U0 = x->U0 + o * nvar;
+          if (stage == 2) for (int nv = 0; nv < nvar; nv++) U[nv] = w0 * U0[nv] + wc * U[nv];
+          if (stage == 3) for (int nv = 0; nv < nvar; nv++) U[nv] = (1.0 / 3.0) * (U0[nv] + 2.0 * U[nv]);
+          nfail += cons_to_prim(c, nvar, U, v, &x->flag[o]);
+          for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = v[nv];
+        }
+  }
+  return nfail;
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  Line-driven wind: placeholders until the LDW rows are restated (ldw == 0 never calls them)
+ * --------------------------------------------------------------------------------------- */
+static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side) { (void)c; (void)g; (void)Vc; (void)side; }
+static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) { (void)c; (void)g; (void)Vc; }
+static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, double *dvds) { (void)c; (void)g; (void)Vc; (void)dvds; }
+static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad) {
+  (void)c; (void)g; (void)v; (void)dvds; (void)o; grad[0] = grad[1] = grad[2] = 0.0;
+}

@@ -75,7 +75,7 @@ def read_dbl(path, nvar, shape):
 
 
 def run(cfg, workdir, *, shape, nvar=5, maxsteps=None, no_write=False, extra_args=(),
-        timeout=3600, exe=None, env=None, **ini):
+        timeout=300, exe=None, env=None, **ini):
     """Run oracle/_ref/<cfg>/pluto in `workdir` with a generated pluto.ini.
 
     shape = (nz, ny, nx) interior zones.  Returns dict(steps=[(nstep,t,dt)], data=[arrays],

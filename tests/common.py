@@ -4,7 +4,9 @@ from pathlib import Path
 import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+_GEN_PREFIXES = ("sph", "ldw")     # general-grid fixtures (GenOracle / the gen path of the library)
+GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(_GEN_PREFIXES))
+GEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_GEN_PREFIXES))
 
 # north_star tolerances
 TOL_STEP = 1e-12     # relative, per step
@@ -32,6 +34,29 @@ def load_golden(name):
 
 
 BODY_FORCE = dict(none=0, vector=1, potential=2)
+
+
+def gen_kwargs_from_golden(g):
+    """Constructor keywords shared by GenOracle and Hydro for a general-grid fixture."""
+    grid = []
+    for row in g["gridspec"]:
+        if row[3] == 1.0:
+            grid.append((float(row[0]), int(row[1]), float(row[2]), "r", float(row[4])))
+        else:
+            grid.append((float(row[0]), int(row[1]), float(row[2])))
+    return dict(dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
+                reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
+                ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
+                char_limiting=bool(int(g["char_limiting"])), shock_flattening=bool(int(g["shock_flattening"])),
+                entropy_switch=bool(int(g["entropy_switch"])))
+
+
+def set_point_mass_gravity(obj, gm):
+    """BodyForceVector of oracle/problems/sph/init.c: g = (-GM/x1^2, 0, 0) at the zone centres."""
+    x1 = obj.x(0)
+    obj.set_body_force_vector(0, (-gm / (x1 * x1)).reshape(1, 1, -1))
+    obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
+    obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
 
 
 def kwargs_from_golden(g):

@@ -82,12 +82,69 @@ def make_case2(out, name, c):
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
+# general-grid cases (spherical geometry, stretched grids, characteristic limiting, MULTID
+# flattening, entropy switch): user files oracle/problems/sph
+import pluto_grid  # noqa: E402
+
+SPH_PAR = dict(GM=1.0, RBLOB=2.0, TBLOB=1.0, PBLOB=5.0)
+HALF_PI = 1.5707963267948966
+SPH_GRID2 = [(1.0, 40, 4.0, "r", 1.03), (0.2, 28, HALF_PI, "r", 0.97), (0.0, 1, 1.0)]
+SPH_BCS = ("outflow", "outflow", "axisymmetric", "reflective", "periodic", "periodic")
+CASES3 = {
+    "sph2d_hll": dict(cfg="sph2d", dims=2, grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, maxsteps=10),
+    "sph2d_hllc": dict(cfg="sph2d", dims=2, grid=[(1.0, 40, 4.0), (0.2, 28, HALF_PI), (0.0, 1, 1.0)],
+                       solver="hllc", bcs=("reflective", "outflow", "reflective", "eqtsymmetric", "periodic", "periodic"),
+                       maxsteps=10),
+    "sph2d_char_hll": dict(cfg="sph2d_char", dims=2, grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, maxsteps=10,
+                           char_limiting=True, limiter="VANLEER_LIM"),
+    "sph2d_flat_hllc": dict(cfg="sph2d_flat", dims=2, grid=SPH_GRID2, solver="hllc", bcs=SPH_BCS, maxsteps=10,
+                            char_limiting=True, limiter="VANLEER_LIM", shock_flattening=True),
+    "sph2d_entr_hll": dict(cfg="sph2d_entr", dims=2, grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, maxsteps=10,
+                           char_limiting=True, limiter="VANLEER_LIM", shock_flattening=True, entropy_switch=True),
+    "sph1d_tvdlf": dict(cfg="sph1d", dims=1, grid=[(1.0, 64, 4.0, "r", 1.02), (1.0, 1, 1.2), (0.0, 1, 1.0)],
+                        solver="tvdlf", bcs=("reflective", "outflow") * 3, maxsteps=10),
+    "sph3d_hllc": dict(cfg="sph3d", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
+                       solver="hllc", bcs=("outflow", "outflow", "reflective", "reflective", "periodic", "periodic"),
+                       maxsteps=6),
+}
+
+
+def make_case3(out, name, c):
+    build_ref.build(c["cfg"])
+    nd = c["dims"]
+    grid = c["grid"]
+    nx = [int(grid[d][1]) if d < nd else 1 for d in range(3)]
+    ntr = 1
+    nvar = 5 + ntr      # ENTR is not written: Boundary() recomputes it (ComputeEntropy)
+    with tempfile.TemporaryDirectory() as wd:
+        r = refrun.run(c["cfg"], wd, shape=(nx[2], nx[1], nx[0]), nvar=nvar, maxsteps=c["maxsteps"],
+                       grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=10.0, first_dt=1e-5,
+                       solver=c["solver"], bcs=c["bcs"], dbl=(-1.0, 1), params=SPH_PAR, timeout=120)
+    nd_ = len(r["data"]) - 1
+    steps = np.array(r["steps"][:nd_], dtype=np.float64)
+    data = np.stack(r["data"][:nd_])
+    gridarr = np.array([[g[0], g[1], g[2], 1.0 if (len(g) > 3 and g[3] == "r") else 0.0,
+                         g[4] if len(g) > 4 else 1.0] for g in grid], dtype=np.float64)
+    np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx), dims=nd,
+                        recon="LINEAR", rk="RK2", solver=c["solver"], bcs=np.array(c["bcs"]),
+                        gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-5, tstop=10.0,
+                        ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=ntr,
+                        body_force="vector", gm=SPH_PAR["GM"], limiter=c.get("limiter", "DEFAULT"),
+                        char_limiting=int(c.get("char_limiting", False)),
+                        shock_flattening=int(c.get("shock_flattening", False)),
+                        entropy_switch=int(c.get("entropy_switch", False)))
+    print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
+
+
 def main():
     out = Path(__file__).resolve().parent
     only = set(sys.argv[1:])
     for name, c in CASES2.items():
         if not only or name in only:
             make_case2(out, name, c)
+    for name, c in CASES3.items():
+        if not only or name in only:
+            make_case3(out, name, c)
     for name, (cfg, nd, N, recon, rk, solver, bcs, maxsteps, params, gamma, cfl, first_dt, tstop) in CASES.items():
         if only and name not in only:
             continue
