@@ -97,7 +97,10 @@ typedef struct pb200_config {
   double xend[3];        /* g_domEnd of this block */
   int device;            /* CUDA device ordinal */
   int body_force;        /* BODY_FORCE: 0 NO, PB200_BF_VECTOR, PB200_BF_POTENTIAL or both (pluto.h:76-77) */
-  int reserved[6];
+  int char_limiting;     /* CHAR_LIMITING YES (Src/States/plm_states.c:481) */
+  int shock_flattening;  /* SHOCK_FLATTENING MULTID (Src/flag_shock.c:81) */
+  int entropy_switch;    /* ENTROPY_SWITCH ALWAYS: NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219) */
+  int reserved[3];
 } pb200_config;
 
 /* What one AdvanceStep leaves in timeStep / globals (Src/structs.h:372, globals.h). */

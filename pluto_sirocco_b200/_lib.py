@@ -27,7 +27,8 @@ class Config(C.Structure):
                 ("bc", C.c_int * 6), ("gamma", C.c_double), ("small_density", C.c_double),
                 ("small_pressure", C.c_double), ("xbeg", C.c_double * 3),
                 ("xend", C.c_double * 3), ("device", C.c_int), ("body_force", C.c_int),
-                ("reserved", C.c_int * 6)]
+                ("char_limiting", C.c_int), ("shock_flattening", C.c_int), ("entropy_switch", C.c_int),
+                ("reserved", C.c_int * 3)]
 
 
 class StepInfo(C.Structure):

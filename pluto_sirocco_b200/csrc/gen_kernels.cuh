@@ -1,0 +1,492 @@
+// gen_kernels.cuh -- the GENERAL-GRID path of the HD update: curvilinear geometry, non-uniform
+// grids, characteristic limiting, MULTID shock flattening, the entropy switch, body forces and
+// the line-driven-wind sources.
+//
+// The grids this path serves are small (the line-driven-wind problem is 1024 x 512 zones, 30 MB
+// of state), so every intermediate array stays resident in the 126 MB L2 and the update is split
+// into simple, one-thread-per-zone (or per-face) kernels that mirror the reference's stages:
+//   gen_entropy   ComputeEntropy           Src/entropy_switch.c:14-39 (after Boundary)
+//   gen_shock / gen_flags   FlagShock      Src/flag_shock.c:81-260 (gather form of the scatter)
+//   gen_p2c       PrimToCons3D + U0 copy   Src/Time_Stepping/rk_step.c:129-130
+//   gen_states    States (PLM)             Src/States/plm_states.c:83-337 and :481-690
+//   gen_riemann   Riemann solver + AdvectFlux  Src/HD/{hllc,hll,tvdlf}.c, Src/adv_flux.c:47-134
+//   gen_rhs       RightHandSide + Source + U += rhs + C_dt   Src/MHD/rhs.c:84-420,
+//                 Src/MHD/rhs_source.c:101-470, Src/Time_Stepping/update_stage.c:283,303-322
+//   gen_finish    RK combination + ConsToPrim3D + dt reduction  rk_step.c:235-237,304,
+//                 Src/HD/mappers.c:98-290, update_stage.c:389-392
+// Arrays are SoA [var][k][j][i] like d->Vc, threads map to i fastest: every access is coalesced.
+// The sweep direction is a RUN-TIME argument (only global-memory indices depend on it); the
+// number of variables is a template parameter so that per-zone vectors live in registers.
+#pragma once
+#include "pb200_kernels.cuh"
+
+namespace pb {
+
+enum { GF_MINMOD = 1, GF_FLAT = 2, GF_HLL = 4, GF_ENTROPY = 8, GF_C2P_FAIL = 64 };   // pluto.h:212-221
+enum { GEO_CARTESIAN = 1, GEO_SPHERICAL = 4 };
+
+struct GenDev {
+  Dev d;
+  int nvar, geometry, limiter, char_lim, flatten, entropy, solver;
+  // 1-D grid arrays per direction (np_tot entries): grid->x, xr, dx, inv_dx and PLM_Coeffs
+  const double *x[3], *xr[3], *dx[3], *inv_dx[3];
+  const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
+  const double *rt, *s, *sp;           // grid->rt[i], s[j], sp[j]
+  const double *dV;                    // grid->dV[k][j][i]
+  const double *A[3];                  // grid->A[d], one extra layer at index -1 along d
+  long Aoff[3], Asj[3], Ask[3];
+  const double *dx_dl[3];              // grid->dx_dl[d][j][i]
+  const double *gline;                 // LINE_DRIVEN_WIND: LineForce() per zone, [3][k][j][i], or null
+};
+
+struct GenArgs {
+  double *V;             // d->Vc (updated in place like the reference)
+  double *U, *U0;        // d->Uc, U0 (SoA)
+  double *VP, *VM;       // stateL.v = vp, stateR.v - 1 = vm of the current direction
+  double *F;             // sweep.flux [nvar] + press + cmax  (nvar + 2 arrays)
+  double *cdt;           // C_dt
+  unsigned short *flag;  // d->flag
+  unsigned char *shock;  // zones with div v < 0 and grad p > 5 p_min
+  const double *dt;
+  unsigned long long *red;
+  double w0, wc;
+  int comb, stage, dir;
+};
+
+PB_D double gen_A(const GenDev &g, int dir, int k, int j, int i) {
+  return __ldg(g.A[dir] + g.Aoff[dir] + (long)k * g.Ask[dir] + (long)j * g.Asj[dir] + i);
+}
+
+// ---- limiters on general grids (States/plm_coeffs.h:72-152) ------------------------------
+PB_D double gen_lim(int kind, bool uniform, double dvp, double dvm, double cp, double cm) {
+  if (!(dvp * dvm > 0.0)) return 0.0;
+  switch (kind) {
+    case LIM_MINMOD: return absmin(dvp, dvm);
+    case LIM_VANLEER:
+      if (uniform) return 2.0 * dvp * dvm / (dvp + dvm);
+      return dvp * dvm * (cp * dvm + cm * dvp) / (dvp * dvp + dvm * dvm + (cp + cm - 2.0) * dvp * dvm);
+    case LIM_MC: {
+      double qc = 0.5 * (dvm + dvp);
+      double scrh = uniform ? 2.0 * absmin(dvp, dvm) : absmin(dvp * cp, dvm * cm);
+      return absmin(qc, scrh);
+    }
+    case LIM_VANALBADA: {
+      double pp = dvp * dvp, mm = dvm * dvm;
+      return (dvp * (mm + 1.e-18) + dvm * (pp + 1.e-18)) / (pp + mm + 1.e-18);
+    }
+    case LIM_OSPRE:
+      if (uniform) return 1.5 * dvp * dvm * (dvm + dvp) / (dvp * dvp + dvm * dvm + dvp * dvm);
+      return dvp * dvm * ((1.0 + cp) * dvm + (1.0 + cm) * dvp) /
+             (2.0 * dvp * dvp + 2.0 * dvm * dvm + (cp + cm - 2.0) * dvp * dvm);
+    case LIM_UMIST: {
+      double ddp = 0.25 * (dvp + 3.0 * dvm), ddm = 0.25 * (dvm + 3.0 * dvp);
+      double d2 = 2.0 * absmin(dvp, dvm);
+      d2 = absmin(d2, ddp);
+      return absmin(d2, ddm);
+    }
+    case 8: {  // SET_GM_LIMITER
+      double qc = 0.5 * (dvm + dvp), scrh = absmin(dvp * cp, dvm * cm);
+      return absmin(qc, scrh);
+    }
+    default: return 0.0;   // LIM_FLAT
+  }
+}
+
+// zone (i,j,k) of a launch over the box [lo, hi] (inclusive), i fastest
+PB_D bool gen_zone(const int lo[3], const int hi[3], int &i, int &j, int &k) {
+  long n1 = hi[0] - lo[0] + 1, n2 = hi[1] - lo[1] + 1, n3 = hi[2] - lo[2] + 1;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n1 * n2 * n3) return false;
+  i = lo[0] + (int)(t % n1);
+  j = lo[1] + (int)((t / n1) % n2);
+  k = lo[2] + (int)(t / (n1 * n2));
+  return true;
+}
+struct GenBox { int lo[3], hi[3]; };
+
+// ---- ComputeEntropy over the whole array ------------------------------------------------
+static __global__ void gen_entropy(GenDev g, double *V) {
+  long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= g.d.sv) return;
+  const int ENTR = g.nvar - 1;
+  V[ENTR * g.d.sv + o] = V[iPRS * g.d.sv + o] / pow(V[o], g.d.gas.gamma);   // eos.c:95
+}
+
+// ---- FlagShock, gather form: (a) shock indicator per zone, (b) flags from the neighbours ---
+static __global__ void gen_shock(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  const long st[3] = {1, d.sj, d.sk};
+  const int idx[3] = {i, j, k};
+  const double *pt = a.V + iPRS * d.sv;
+  double divv = 0.0;
+  for (int dir = 0; dir < d.ndim; dir++) {
+    const double *vx = a.V + (1 + dir) * d.sv;
+    double dv;
+    if (g.geometry == GEO_CARTESIAN) dv = (vx[o + st[dir]] - vx[o - st[dir]]) / __ldg(g.dx[dir] + idx[dir]);
+    else {
+      int m[3] = {i, j, k};
+      m[dir] -= 1;
+      dv = gen_A(g, dir, k, j, i) * (vx[o + st[dir]] + vx[o]) - gen_A(g, dir, m[2], m[1], m[0]) * (vx[o - st[dir]] + vx[o]);
+    }
+    divv = (dir == 0) ? dv : divv + dv;
+  }
+  if (g.geometry != GEO_CARTESIAN) divv = divv / __ldg(g.dV + o);
+  unsigned char sh = 0;
+  if (divv < 0.0) {
+    double pt_min = pt[o], gradp = 0.0;
+    for (int dir = 0; dir < d.ndim; dir++) {
+      pt_min = fmin(pt_min, fmin(pt[o + st[dir]], pt[o - st[dir]]));
+      double dp = fabs(pt[o + st[dir]] - pt[o - st[dir]]);
+      gradp = (dir == 0) ? dp : gradp + dp;
+    }
+    sh = (gradp > 5.0 * pt_min) ? 1 : 0;      // EPS_PSHOCK_FLATTEN, flag_shock.c:69-70
+  }
+  a.shock[o] = sh;
+}
+
+static __global__ void gen_flags(GenDev g, GenArgs a) {
+  const Dev &d = g.d;
+  long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= d.sv) return;
+  int i = (int)(o % d.tot[0]), j = (int)((o / d.sj) % d.tot[1]), k = (int)(o / d.sk);
+  const long st[3] = {1, d.sj, d.sk};
+  const int idx[3] = {i, j, k};
+  unsigned short f = g.entropy ? GF_ENTROPY : 0;
+  if (g.flatten) {
+    if (a.shock[o]) f |= GF_HLL | GF_MINMOD;
+    for (int dir = 0; dir < d.ndim; dir++) {
+      if (idx[dir] > 0 && a.shock[o - st[dir]]) f |= GF_MINMOD;
+      if (idx[dir] < d.tot[dir] - 1 && a.shock[o + st[dir]]) f |= GF_MINMOD;
+    }
+  }
+  a.flag[o] = f;
+}
+
+// ---- PrimToCons3D + RBoxCopy(U0) over the interior --------------------------------------
+template <int NV>
+static __global__ void gen_p2c(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  double v[NV], u[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) v[nv] = a.V[nv * d.sv + o];
+  // exact restatement (no reciprocal sharing): these values seed U0
+  const double rho = v[iRHO];
+  u[0] = rho; u[1] = rho * v[1]; u[2] = rho * v[2]; u[3] = rho * v[3];
+  double k2 = v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  u[4] = 0.5 * rho * k2 + v[4] / d.gas.gmm1;
+#pragma unroll
+  for (int nv = NFLX; nv < NV; nv++) u[nv] = rho * v[nv];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) { a.U[nv * d.sv + o] = u[nv]; a.U0[nv * d.sv + o] = u[nv]; }
+}
+
+// ---- States: PLM on general grids, primitive or characteristic limiting -------------------
+template <int NV>
+static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const int dir = a.dir;
+  const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  const int n = dir == 0 ? i : (dir == 1 ? j : k);
+  const bool uniform = g.geometry == GEO_CARTESIAN;     // UNIFORM_CARTESIAN_GRID, plm_coeffs.h:23-29
+  double v[NV], dvp[NV], dvm[NV], dvl[NV];
+  double cp = 2.0, cm = 2.0, dp = 0.5, dm = 0.5, wp = 1.0, wm = 1.0;
+  if (!uniform) {
+    cp = __ldg(g.cp[dir] + n); cm = __ldg(g.cm[dir] + n); wp = __ldg(g.wp[dir] + n); wm = __ldg(g.wm[dir] + n);
+    dp = __ldg(g.dp[dir] + n); dm = __ldg(g.dm[dir] + n);
+  }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    v[nv] = a.V[nv * d.sv + o];
+    double fp = a.V[nv * d.sv + o + st] - v[nv], fm = v[nv] - a.V[nv * d.sv + o - st];
+    dvp[nv] = uniform ? fp : fp * wp;
+    dvm[nv] = uniform ? fm : fm * wm;
+  }
+  const unsigned short fl = g.flatten ? a.flag[o] : 0;
+  if (!g.char_lim) {
+    if (fl & GF_FLAT) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) dvl[nv] = 0.0;
+    } else if (fl & GF_MINMOD) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) dvl[nv] = gen_lim(LIM_MINMOD, uniform, dvp[nv], dvm[nv], cp, cm);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        int kind = g.limiter;
+        if (kind == LIM_DEFAULT) kind = (nv == iRHO || nv >= NFLX) ? LIM_MC : (nv == iPRS ? LIM_MINMOD : LIM_VANLEER);
+        dvl[nv] = gen_lim(kind, uniform, dvp[nv], dvm[nv], cp, cm);
+      }
+    }
+  } else {
+    // SoundSpeed2, PrimEigenvectors (HD/eigenv.c:92-200), PrimToChar (:575-616)
+    const double a2 = d.gas.gamma * v[iPRS] / v[iRHO];
+    const double cs = sqrt(a2), rhocs = v[iRHO] * cs, rho_cs = v[iRHO] / cs;
+    const double L0p = 1.0 / rhocs, L2p = -1.0 / a2;
+    // dvp/dvm of the normal, tangent, bitangent velocity: select without dynamic register indexing
+    const double pn = dir == 0 ? dvp[1] : (dir == 1 ? dvp[2] : dvp[3]);
+    const double pt_ = dir == 0 ? dvp[2] : (dir == 1 ? dvp[3] : dvp[1]);
+    const double pb_ = dir == 0 ? dvp[3] : (dir == 1 ? dvp[1] : dvp[2]);
+    const double mn = dir == 0 ? dvm[1] : (dir == 1 ? dvm[2] : dvm[3]);
+    const double mt_ = dir == 0 ? dvm[2] : (dir == 1 ? dvm[3] : dvm[1]);
+    const double mb_ = dir == 0 ? dvm[3] : (dir == 1 ? dvm[1] : dvm[2]);
+    double dwp[NFLX], dwm[NFLX], dwl[NFLX];
+    dwm[0] = -1.0 * mn + L0p * dvm[iPRS]; dwm[1] = 1.0 * mn + L0p * dvm[iPRS];
+    dwm[2] = dvm[iRHO] + L2p * dvm[iPRS]; dwm[3] = mt_; dwm[4] = mb_;
+    dwp[0] = -1.0 * pn + L0p * dvp[iPRS]; dwp[1] = 1.0 * pn + L0p * dvp[iPRS];
+    dwp[2] = dvp[iRHO] + L2p * dvp[iPRS]; dwp[3] = pt_; dwp[4] = pb_;
+#pragma unroll
+    for (int q = 0; q < NFLX; q++) {
+      if (fl & GF_FLAT) dwl[q] = 0.0;
+      else if (fl & GF_MINMOD) dwl[q] = gen_lim(LIM_MINMOD, uniform, dwp[q], dwm[q], cp, cm);
+      else if (g.limiter == LIM_DEFAULT) {
+        const double kstp = q < 2 ? 1.0 : 2.0;
+        const double cpk = uniform ? kstp : (2.0 - cp) + (cp - 1.0) * kstp;
+        const double cmk = uniform ? kstp : (2.0 - cm) + (cm - 1.0) * kstp;
+        dwl[q] = gen_lim(8, uniform, dwp[q], dwm[q], cpk, cmk);
+      } else dwl[q] = gen_lim(g.limiter, uniform, dwp[q], dwm[q], cp, cm);
+    }
+    // dv = sum_k dw_lim[k] R[nv][k]: the reference adds all five products, zeros included
+    double dc[NFLX];
+    dc[iRHO] = (((dwl[0] * (0.5 * rho_cs) + dwl[1] * (0.5 * rho_cs)) + dwl[2] * 1.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
+    dc[iPRS] = (((dwl[0] * (0.5 * rhocs) + dwl[1] * (0.5 * rhocs)) + dwl[2] * 0.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
+    const double dcn = dwl[0] * -0.5 + dwl[1] * 0.5, dct = dwl[3], dcb = dwl[4];
+    dc[1] = dir == 0 ? dcn : (dir == 1 ? dcb : dct);
+    dc[2] = dir == 0 ? dct : (dir == 1 ? dcn : dcb);
+    dc[3] = dir == 0 ? dcb : (dir == 1 ? dct : dcn);
+#pragma unroll
+    for (int nv = 0; nv < NFLX; nv++) {
+      if (dvp[nv] * dvm[nv] > 0.0) {
+        double d2v = absmin(cp * dvp[nv], cm * dvm[nv]);
+        dvl[nv] = (d2v * dc[nv] > 0.0) ? absmin(d2v, dc[nv]) : 0.0;
+      } else dvl[nv] = 0.0;
+    }
+#pragma unroll
+    for (int nv = NFLX; nv < NV; nv++)
+      dvl[nv] = gen_lim(g.limiter == LIM_DEFAULT ? LIM_MC : g.limiter, uniform, dvp[nv], dvm[nv], cp, cm);
+  }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    a.VP[nv * d.sv + o] = v[nv] + dvl[nv] * dp;
+    a.VM[nv * d.sv + o] = v[nv] - dvl[nv] * dm;
+  }
+}
+
+// ---- Riemann solver + AdvectFlux at the face between zone n and n+1 -------------------------
+template <int NV>
+static __global__ void gen_riemann(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  double machv = 0.0;
+  const Dev &d = g.d;
+  if (gen_zone(b.lo, b.hi, i, j, k)) {
+    const int dir = a.dir;
+    const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+    const long o = (long)k * d.sk + (long)j * d.sj + i;
+    const int gn = 1 + dir, gt = 1 + (dir + 1) % 3, gb = 1 + (dir + 2) % 3;
+    double vL[NV], vR[NV];     // sweep-local order (n, t, b)
+    vL[0] = a.VP[o]; vR[0] = a.VM[o + st];
+    vL[1] = a.VP[gn * d.sv + o]; vR[1] = a.VM[gn * d.sv + o + st];
+    vL[2] = a.VP[gt * d.sv + o]; vR[2] = a.VM[gt * d.sv + o + st];
+    vL[3] = a.VP[gb * d.sv + o]; vR[3] = a.VM[gb * d.sv + o + st];
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) { vL[nv] = a.VP[nv * d.sv + o]; vR[nv] = a.VM[nv * d.sv + o + st]; }
+    const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
+    Face<NV> F;
+    Ratio mach;
+    mach.init();
+    if (g.solver == SOLVER_TVDLF) riemann<NV, SOLVER_TVDLF>(vL, vR, d.gas, F, mach);
+    else if (g.solver == SOLVER_HLL) riemann<NV, SOLVER_HLL>(vL, vR, d.gas, F, mach);
+    else riemann<NV, SOLVER_HLLC>(vL, vR, d.gas, F, mach, true, hll);
+    if (g.entropy) {    // adv_flux.c:131-134: ">=" for the entropy, ">" for the other scalars
+      F.f[NV - 1] = F.f[iRHO] * sel(F.f[iRHO] >= 0.0, vL[NV - 1], vR[NV - 1]);
+    }
+    machv = mach.value();
+    const long nz = d.sv;
+    a.F[o] = F.f[0];
+    a.F[gn * nz + o] = F.f[1];
+    a.F[gt * nz + o] = F.f[2];
+    a.F[gb * nz + o] = F.f[3];
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) a.F[nv * nz + o] = F.f[nv];
+    a.F[NV * nz + o] = F.prs;
+    a.F[(NV + 1) * nz + o] = F.cmax;
+  }
+  machv = warp_max(machv);
+  if ((threadIdx.x & 31) == 0 && machv > 0.0) atomic_max_pos(a.red + 1, machv);
+}
+
+// ---- RightHandSide + RightHandSideSource + U += rhs + C_dt -------------------------------
+template <int NV>
+static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  const Dev &d = g.d;
+  double inv_max = 0.0;
+  if (gen_zone(b.lo, b.hi, i, j, k)) {
+    const int dir = a.dir;
+    const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+    const long o = (long)k * d.sk + (long)j * d.sj + i;
+    const long nz = d.sv;
+    const int n = dir == 0 ? i : (dir == 1 ? j : k);
+    const double dt = *a.dt;
+    const int gn = 1 + dir;
+    double rhs[NV], fp[NV], fm[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { fp[nv] = a.F[nv * nz + o]; fm[nv] = a.F[nv * nz + o - st]; }
+    const double pp = a.F[NV * nz + o], pm = a.F[NV * nz + o - st];
+    const double cp_ = a.F[(NV + 1) * nz + o], cm_ = a.F[(NV + 1) * nz + o - st];
+    const double frp = fp[iRHO], frm = fm[iRHO];      // mass fluxes (not area weighted)
+    double dpn;   // pressure-gradient term of the normal momentum
+    if (g.geometry == GEO_CARTESIAN) {
+      const double scrh = dt / __ldg(g.dx[dir] + n);
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) rhs[nv] = -scrh * (fp[nv] - fm[nv]);
+      dpn = scrh * (pp - pm);
+    } else {
+      // TotalFlux (rhs.c:530-600): fA = F A, fA[iMPHI] *= |x1p| (r sweep) or |sp| (theta sweep)
+      int m[3] = {i, j, k};
+      m[dir] -= 1;
+      const double Ap = gen_A(g, dir, k, j, i), Am = gen_A(g, dir, m[2], m[1], m[0]);
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) { fp[nv] = fp[nv] * Ap; fm[nv] = fm[nv] * Am; }
+      if (dir == 0) { fp[3] *= fabs(__ldg(g.xr[0] + n)); fm[3] *= fabs(__ldg(g.xr[0] + n - 1)); }
+      else if (dir == 1) { fp[3] *= fabs(__ldg(g.sp + n)); fm[3] *= fabs(__ldg(g.sp + n - 1)); }
+      const double dtdV = dt / __ldg(g.dV + o);
+      double dtdl = dt / __ldg(g.dx[dir] + n);
+      if (dir != 0) dtdl = dtdl * __ldg(g.dx_dl[dir] + (long)j * d.tot[0] + i);
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (fp[nv] - fm[nv]);
+      dpn = dtdl * (pp - pm);
+      if (dir == 0) rhs[3] /= fabs(__ldg(g.x[0] + n));
+      else if (dir == 1) rhs[3] /= fabs(__ldg(g.s + n));
+    }
+    // centre state (stateC->v) and, for the spherical r sweep, vc = (vp + vm)/2  (rhs_source.c:229-232)
+    double vg[NV];
+    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (a.VP[nv * nz + o] + a.VM[nv * nz + o]);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = a.V[nv * nz + o];
+    }
+    double sn = 0.0;   // source of the normal momentum
+    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+      const double r_1 = 1.0 / __ldg(g.x[0] + n);
+      const double Sm = vg[iRHO] * (vg[2] * vg[2] + vg[3] * vg[3]);
+      sn = dt * Sm * r_1;
+    } else if (g.geometry == GEO_SPHERICAL && dir == 1) {
+      const double r_1 = 1.0 / __ldg(g.rt + i);
+      const double ct = 1.0 / tan(__ldg(g.x[1] + n));
+      const double Sm = vg[iRHO] * (-vg[2] * vg[1] + ct * vg[3] * vg[3]);
+      sn = dt * Sm * r_1;
+    }
+    // accumulate in the reference's order: flux difference, pressure gradient, geometry, forces
+    double rn = (dir == 0 ? rhs[1] : (dir == 1 ? rhs[2] : rhs[3])) - dpn;
+    if (g.geometry == GEO_SPHERICAL && dir <= 1) rn += sn;
+    for (int pass = 0; pass < 2; pass++) {
+      double gv[3];
+      if (pass == 0) {
+        if (!(d.bf_kind & 1)) continue;
+        gv[0] = bf_at(d, 0, i, j, k); gv[1] = bf_at(d, 1, i, j, k); gv[2] = bf_at(d, 2, i, j, k);
+      } else {
+        if (!g.gline) continue;
+        gv[0] = __ldg(g.gline + o); gv[1] = __ldg(g.gline + nz + o); gv[2] = __ldg(g.gline + 2 * nz + o);
+      }
+      const double gd = dir == 0 ? gv[0] : (dir == 1 ? gv[1] : gv[2]);
+      rn += dt * vg[iRHO] * gd;
+      rhs[iPRS] += dt * 0.5 * (frp + frm) * gd;
+      if (dir == 0 && d.ndim == 1) {
+        rhs[2] += dt * vg[iRHO] * gv[1];
+        rhs[iPRS] += dt * vg[iRHO] * vg[2] * gv[1];
+        rhs[3] += dt * vg[iRHO] * gv[2];
+        rhs[iPRS] += dt * vg[iRHO] * vg[3] * gv[2];
+      }
+      if (dir == 1 && d.ndim == 2) {
+        rhs[3] += dt * vg[iRHO] * gv[2];
+        rhs[iPRS] += dt * vg[iRHO] * vg[3] * gv[2];
+      }
+    }
+    if (dir == 0) rhs[1] = rn; else if (dir == 1) rhs[2] = rn; else rhs[3] = rn;
+    (void)gn;
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] += rhs[nv];
+    // GetInverse_dl (set_geometry.c:303-375) and C_dt (update_stage.c:303-322)
+    double inv_dl = __ldg(g.inv_dx[dir] + n);
+    if (g.geometry == GEO_SPHERICAL && dir == 1) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i));
+    if (g.geometry == GEO_SPHERICAL && dir == 2) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i)) / sin(__ldg(g.x[1] + j));
+    if (d.ndim > 1) {
+      if (a.stage == 1) {
+        const double c = 0.5 * (cm_ + cp_) * inv_dl;
+        a.cdt[o] = (dir == 0) ? c : a.cdt[o] + c;
+      }
+    } else {
+      // 1-D: every stage, faces IBEG-1..IEND with inv_dl of the face's left zone
+      inv_max = cp_ * inv_dl;
+      if (n == d.beg[0]) inv_max = fmax(inv_max, cm_ * __ldg(g.inv_dx[0] + n - 1));
+    }
+  }
+  if (g.d.ndim == 1) {
+    inv_max = warp_max(inv_max);
+    if ((threadIdx.x & 31) == 0 && inv_max > 0.0) atomic_max_pos(a.red + 0, inv_max);
+  }
+}
+
+// ---- RK combination + ConsToPrim3D (entropy aware) + dt reduction ---------------------------
+template <int NV>
+static __global__ void gen_finish(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  const Dev &d = g.d;
+  double cmaxv = 0.0;
+  int nfail = 0, nan = 0;
+  if (gen_zone(b.lo, b.hi, i, j, k)) {
+    const long o = (long)k * d.sk + (long)j * d.sj + i;
+    const long nz = d.sv;
+    double u[NV], v[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) u[nv] = a.U[nv * nz + o];
+    if (a.comb == 1) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) u[nv] = a.w0 * a.U0[nv * nz + o] + a.wc * u[nv];
+    } else if (a.comb == 2) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) u[nv] = (1.0 / 3.0) * (a.U0[nv * nz + o] + 2.0 * u[nv]);
+    }
+    // ConsToPrim, mappers.c:98-290
+    unsigned short fl = a.flag[o];
+    const Gas &gs = d.gas;
+    const double m2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+    bool bad = false;
+    if (u[0] < 0.0) { u[0] = gs.small_dn; bad = true; }
+    const double rho = u[0], tau = 1.0 / u[0];
+    v[0] = rho; v[1] = u[1] * tau; v[2] = u[2] * tau; v[3] = u[3] * tau;
+    const double kin = 0.5 * m2 / u[0];
+    if (u[4] < 0.0) { u[4] = gs.small_pr / gs.gmm1 + kin; bad = true; }
+    if (g.entropy && (fl & GF_ENTROPY)) {
+      const double rhog1 = pow(rho, gs.gmm1);
+      v[4] = u[NV - 1] * rhog1;
+      if (v[4] < 0.0) { v[4] = gs.small_pr; bad = true; }
+      u[4] = v[4] / gs.gmm1 + kin;
+    } else {
+      v[4] = gs.gmm1 * (u[4] - kin);
+      if (v[4] < 0.0) { v[4] = gs.small_pr; u[4] = v[4] / gs.gmm1 + kin; bad = true; }
+      if (g.entropy) u[NV - 1] = v[4] / pow(rho, gs.gmm1);
+    }
+#pragma unroll
+    for (int nv = NFLX; nv < NV; nv++) v[nv] = u[nv] * tau;
+    if (bad) { fl |= GF_C2P_FAIL; nfail = 1; a.flag[o] = fl; }
+    nan = !(v[4] == v[4]) || !(v[0] == v[0]);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { a.U[nv * nz + o] = u[nv]; a.V[nv * nz + o] = v[nv]; }
+    if (a.stage == 1 && d.ndim > 1) cmaxv = a.cdt[o];
+  }
+  block_reduce(cmaxv, 0.0, nfail, nan, a.stage == 1 && g.d.ndim > 1, a.red);
+}
+
+}  // namespace pb

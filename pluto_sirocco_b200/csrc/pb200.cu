@@ -61,7 +61,16 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (!cfg || !out) return fail(PB200_EINVAL, "null argument");
   *out = nullptr;
   if (cfg->dimensions < 1 || cfg->dimensions > 3) return fail(PB200_EINVAL, "dimensions must be 1..3");
-  if (cfg->geometry != PB200_CARTESIAN) return fail(PB200_ENOTSUP, "geometry: only CARTESIAN is built");
+  if (cfg->geometry != PB200_CARTESIAN && cfg->geometry != PB200_SPHERICAL)
+    return fail(PB200_ENOTSUP, "geometry: CARTESIAN and SPHERICAL are built");
+  // curvilinear geometry, characteristic limiting, MULTID flattening and the entropy switch run
+  // on the general-grid path (pb200_gen.cu)
+  const bool gen = cfg->geometry != PB200_CARTESIAN || cfg->char_limiting || cfg->shock_flattening ||
+                   cfg->entropy_switch;
+  if (gen && cfg->reconstruction != PB200_LINEAR)
+    return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR");
+  if (cfg->body_force & PB200_BF_POTENTIAL && gen)
+    return fail(PB200_ENOTSUP, "BODY_FORCE POTENTIAL on the general-grid path");
   if (cfg->ntracer < 0 || cfg->ntracer > 2) return fail(PB200_ENOTSUP, "ntracer must be 0..2");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
@@ -82,7 +91,12 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
 
   pb200_ctx *c = new pb200_ctx();
   c->cfg = *cfg;
-  c->nvar = 5 + cfg->ntracer;
+  c->nvar = 5 + cfg->ntracer + (cfg->entropy_switch ? 1 : 0);
+  c->gen = gen;
+  c->gen_ready = false;
+  c->gdev = nullptr;
+  c->gline = nullptr;
+  c->ldw_hook = nullptr;
   Dev &D = c->dev;
   D.ndim = cfg->dimensions;
   for (int d = 0; d < 3; d++) {
@@ -105,7 +119,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   D.gas.small_pr = cfg->small_pressure;
 
   c->nstages = cfg->time_stepping == PB200_EULER ? 1 : (cfg->time_stepping == PB200_RK2 ? 2 : 3);
-  int ncopies = c->nstages == 3 ? 3 : 2;
+  int ncopies = gen ? 1 : (c->nstages == 3 ? 3 : 2);   // the general path updates d->Vc in place
   for (int k = 0; k < 3; k++) c->V[k] = nullptr;
   cudaError_t e = cudaSuccess;
   for (int k = 0; k < ncopies && e == cudaSuccess; k++) {
@@ -114,7 +128,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   }
   c->acc = nullptr;
   c->cdt = nullptr;
-  if (e == cudaSuccess && D.ndim > 1) {
+  if (e == cudaSuccess && D.ndim > 1 && !gen) {
     e = cudaMalloc(&c->acc, c->vbytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->cdt, c->nzone * sizeof(double));
   }
@@ -159,6 +173,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
 
 extern "C" void pb200_destroy(pb200_ctx *c) {
   if (!c) return;
+  pb200_gen_release(c);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
   if (c->acc) cudaFree(c->acc);
   if (c->cdt) cudaFree(c->cdt);
@@ -195,6 +210,7 @@ extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const dou
     c->dx[dir][i] = dx ? dx[i] : xr[i] - xl[i];
   }
   CK(cudaSetDevice(c->cfg.device));
+  c->gen_ready = false;
   return upload_grid(c, dir);
 }
 
@@ -256,6 +272,7 @@ static int boundary_on(pb200_ctx *c, double *V) {
     b.nghost = c->cfg.nghost;
     for (int nv = 0; nv < 16; nv++) b.sign[nv] = 1.0;
     b.sign[1 + side / 2] = -1.0;  // FlipSign(): normal velocity (Src/boundary.c:503)
+    if (type == PB200_BC_AXISYMMETRIC && c->cfg.geometry != PB200_CARTESIAN) b.sign[3] = -1.0;  // iVPHI (boundary.c:548)
     int ext[3] = {D.tot[0], D.tot[1], D.tot[2]};
     ext[side / 2] = b.nghost;
     long n = (long)ext[0] * ext[1] * ext[2];
@@ -307,6 +324,10 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   CK(cudaSetDevice(c->cfg.device));
   c->launches = 0;
   c->nprof = 0;
+  if (c->gen) {
+    int rc = pb200_gen_setup(c);
+    if (rc) return fail(rc, "general-grid set-up failed (out of device memory?)");
+  }
   CK(cudaEventRecord(c->ev0, c->stream));
   reset_red<<<1, 1, 0, c->stream>>>(c->d_red, c->d_dt, dt);
   c->launches++;
@@ -316,6 +337,7 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   else if (c->nstages == 2) { c->stage_in[1] = A; c->stage_out[1] = B; c->stage_in[2] = B; c->stage_out[2] = A; }
   else { c->stage_in[1] = A; c->stage_out[1] = B; c->stage_in[2] = B; c->stage_out[2] = C;
          c->stage_in[3] = C; c->stage_out[3] = A; }
+  if (c->gen) for (int s = 1; s <= 3; s++) c->stage_in[s] = c->stage_out[s] = c->cur;
   c->in_step = true;
   return PB200_OK;
 }
@@ -363,6 +385,7 @@ extern "C" int pb200_stage_begin(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
+  if (c->gen) return PB200_OK;
   if (c->dev.ndim == 3) launch_sweep(c, 1, a);    // x1 + x2 in one kernel: interior planes only
   CK(cudaGetLastError());
   return PB200_OK;
@@ -372,6 +395,10 @@ extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
+  if (c->gen) {
+    rc = pb200_gen_stage(c, stage);
+    return rc ? fail(rc, "general-grid stage failed") : PB200_OK;
+  }
   const Dev &D = c->dev;
   if (D.ndim == 1) launch_sweep(c, 0, a);
   else if (D.ndim == 2) launch_sweep(c, 1, a);    // x1 + x2 (reads the x2 ghosts)

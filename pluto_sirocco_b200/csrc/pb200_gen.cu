@@ -1,0 +1,266 @@
+// pb200_gen.cu -- host side of the general-grid path (gen_kernels.cuh): geometry set-up and the
+// stage sequencing of AdvanceStep() for curvilinear / characteristic-limited / flattened /
+// entropy-switched / line-driven-wind configurations.
+//
+// Geometry: the reference derives dV, A, dx_dl, xgc, rt, s, sp and the PLM coefficients from
+// grid->xl/xr/dx once at start-up (Src/set_geometry.c:20-290, Src/States/plm_coeffs.c:66-88).
+// gen_setup() restates those formulas on the host with the same libm calls (set-up code, not
+// the hot path) and uploads the arrays; every time step then runs on the device only.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pb200_internal.h"
+#include "gen_kernels.cuh"
+
+using namespace pb;
+
+namespace {
+
+template <typename T>
+T *upload(pb200_ctx *c, const std::vector<T> &h) {
+  T *p = nullptr;
+  if (cudaMalloc(&p, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  c->gen_allocs.push_back(p);
+  return p;
+}
+template <typename T>
+T *dalloc(pb200_ctx *c, size_t n) {
+  T *p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, n * sizeof(T));
+  c->gen_allocs.push_back(p);
+  return p;
+}
+
+}  // namespace
+
+void pb200_gen_release(pb200_ctx *c) {
+  for (void *p : c->gen_allocs) cudaFree(p);
+  c->gen_allocs.clear();
+  c->gen_ready = false;
+  delete c->gdev;
+  c->gdev = nullptr;
+}
+
+int pb200_gen_setup(pb200_ctx *c) {
+  if (c->gen_ready) return PB200_OK;
+  pb200_gen_release(c);
+  c->gdev = new GenDev;
+  GenDev &G = *c->gdev;
+  memset(&G, 0, sizeof(G));
+  G.d = c->dev;
+  const Dev &D = c->dev;
+  const int n1 = D.tot[0], n2 = D.tot[1], n3 = D.tot[2], nd = D.ndim;
+  const int geo = c->cfg.geometry;
+  G.nvar = c->nvar;
+  G.geometry = geo;
+  G.limiter = c->cfg.limiter;
+  G.char_lim = c->cfg.char_limiting;
+  G.flatten = c->cfg.shock_flattening;
+  G.entropy = c->cfg.entropy_switch;
+  G.solver = c->cfg.solver;
+
+  std::vector<double> x[3], xgc[3], inv[3], cp[3], cm[3], wp[3], wm[3], dp[3], dm[3];
+  for (int d = 0; d < 3; d++) {
+    int n = D.tot[d];
+    x[d].resize(n); xgc[d].resize(n); inv[d].resize(n);
+    for (int i = 0; i < n; i++) x[d][i] = 0.5 * (c->xl[d][i] + c->xr[d][i]);   // set_grid.c:137
+  }
+  const std::vector<double> &x1 = x[0], &x2 = x[1], &dx1 = c->dx[0], &dx2 = c->dx[1], &dx3 = c->dx[2];
+  const std::vector<double> &x1p = c->xr[0], &x1m = c->xl[0], &x2p = c->xr[1], &x2m = c->xl[1];
+  std::vector<double> rt(n1), s(n2), sp(n2), dmu(n2);
+  for (int i = 0; i < n1; i++) {                 // set_geometry.c:83-97
+    double xL = x1m[i], xR = x1p[i];
+    if (geo == PB200_CARTESIAN) { xgc[0][i] = x1[i]; rt[i] = x1[i]; }
+    else {
+      xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
+      rt[i] = (xR * xR * xR - xL * xL * xL) / (xR * xR - xL * xL) / 1.5;
+    }
+  }
+  for (int j = 0; j < n2; j++) {                 // set_geometry.c:103-116
+    double xL = x2m[j], xR = x2p[j];
+    if (geo != PB200_SPHERICAL) xgc[1][j] = x2[j];
+    else {
+      xgc[1][j] = sin(xR) - sin(xL) + xL * cos(xL) - xR * cos(xR);
+      xgc[1][j] /= cos(xL) - cos(xR);
+      sp[j] = fabs(sin(xR));
+      s[j] = fabs(sin(x2[j]));
+      dmu[j] = fabs(cos(xL) - cos(xR));
+    }
+  }
+  for (int k = 0; k < n3; k++) xgc[2][k] = x[2][k];
+  // volumes and areas (DIM_EXPAND: factors of the active dimensions only), set_geometry.c:122-230
+  std::vector<double> dV((size_t)D.sv);
+  for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double v;
+    if (geo == PB200_CARTESIAN) { v = dx1[i]; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * dx3[k]; }
+    else {
+      double dVr = fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
+      double dm_ = fabs(cos(x2m[j]) - cos(x2p[j]));
+      v = dVr; if (nd > 1) v = v * dm_; if (nd > 2) v = v * dx3[k];
+    }
+    dV[(size_t)k * D.sk + (size_t)j * D.sj + i] = v;
+  }
+  std::vector<double> A[3];
+  for (int d = 0; d < 3; d++) {
+    int e1 = n1 + (d == 0), e2 = n2 + (d == 1), e3 = n3 + (d == 2);
+    G.Asj[d] = e1;
+    G.Ask[d] = (long)e1 * e2;
+    G.Aoff[d] = d == 0 ? 1 : (d == 1 ? G.Asj[d] : G.Ask[d]);
+    A[d].assign((size_t)e1 * e2 * e3, 0.0);
+  }
+  for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = -1; i < n1; i++) {
+    double a;
+    if (geo == PB200_CARTESIAN) { a = 1.0; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * dx3[k]; }
+    else {
+      double dm_ = fabs(cos(x2m[j]) - cos(x2p[j]));
+      a = (i == -1) ? x1m[0] * x1m[0] : x1p[i] * x1p[i];
+      if (nd > 1) a = a * dm_;
+      if (nd > 2) a = a * dx3[k];
+    }
+    A[0][G.Aoff[0] + (long)k * G.Ask[0] + (long)j * G.Asj[0] + i] = a;
+  }
+  for (int k = 0; k < n3; k++) for (int j = -1; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double a;
+    if (geo == PB200_CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    else {
+      a = fabs(x1[i]) * dx1[i];
+      if (nd > 1) a = a * ((j == -1) ? fabs(sin(x2m[0])) : fabs(sin(x2p[j])));
+      if (nd > 2) a = a * dx3[k];
+    }
+    A[1][G.Aoff[1] + (long)k * G.Ask[1] + (long)j * G.Asj[1] + i] = a;
+  }
+  for (int k = -1; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
+    double a;
+    if (geo == PB200_CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * dx2[j]; }
+    else { a = fabs(x1[i]) * dx1[i]; if (nd > 1) a = a * dx2[j]; }
+    A[2][G.Aoff[2] + (long)k * G.Ask[2] + (long)j * G.Asj[2] + i] = a;
+  }
+  std::vector<double> dxdl[3];
+  for (int d = 0; d < 3; d++) dxdl[d].assign((size_t)n1 * n2, 1.0);
+  if (geo == PB200_SPHERICAL)
+    for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {      // set_geometry.c:250-254
+      dxdl[1][(size_t)j * n1 + i] = 1.0 / rt[i];
+      dxdl[2][(size_t)j * n1 + i] = dx2[j] / (rt[i] * dmu[j]);
+    }
+  for (int d = 0; d < 3; d++) {
+    int n = D.tot[d];
+    cp[d].assign(n, 2.0); cm[d].assign(n, 2.0); wp[d].assign(n, 1.0); wm[d].assign(n, 1.0);
+    dp[d].assign(n, 0.5); dm[d].assign(n, 0.5);
+    const std::vector<double> &dx = c->dx[d], &xr = c->xr[d];
+    for (int i = 0; i < n; i++) inv[d][i] = 1.0 / dx[i];
+    for (int i = 1; i <= n - 2; i++) {           // plm_coeffs.c:66-88
+      wp[d][i] = dx[i] / (xgc[d][i + 1] - xgc[d][i]);
+      wm[d][i] = dx[i] / (xgc[d][i] - xgc[d][i - 1]);
+      cp[d][i] = (xgc[d][i + 1] - xgc[d][i]) / (xr[i] - xgc[d][i]);
+      cm[d][i] = (xgc[d][i] - xgc[d][i - 1]) / (xgc[d][i] - xr[i - 1]);
+      dp[d][i] = (xr[i] - xgc[d][i]) / dx[i];
+      dm[d][i] = (xgc[d][i] - xr[i - 1]) / dx[i];
+    }
+  }
+  bool ok = true;
+  for (int d = 0; d < 3; d++) {
+    ok &= (G.x[d] = upload(c, x[d])) != nullptr;
+    ok &= (G.xr[d] = upload(c, c->xr[d])) != nullptr;
+    ok &= (G.dx[d] = upload(c, c->dx[d])) != nullptr;
+    ok &= (G.inv_dx[d] = upload(c, inv[d])) != nullptr;
+    ok &= (G.cp[d] = upload(c, cp[d])) != nullptr;
+    ok &= (G.cm[d] = upload(c, cm[d])) != nullptr;
+    ok &= (G.wp[d] = upload(c, wp[d])) != nullptr;
+    ok &= (G.wm[d] = upload(c, wm[d])) != nullptr;
+    ok &= (G.dp[d] = upload(c, dp[d])) != nullptr;
+    ok &= (G.dm[d] = upload(c, dm[d])) != nullptr;
+    ok &= (G.A[d] = upload(c, A[d])) != nullptr;
+    ok &= (G.dx_dl[d] = upload(c, dxdl[d])) != nullptr;
+  }
+  ok &= (G.rt = upload(c, rt)) != nullptr;
+  ok &= (G.s = upload(c, s)) != nullptr;
+  ok &= (G.sp = upload(c, sp)) != nullptr;
+  ok &= (G.dV = upload(c, dV)) != nullptr;
+  const size_t nz = (size_t)D.sv, nv = (size_t)c->nvar;
+  ok &= (c->gU = dalloc<double>(c, nz * nv)) != nullptr;
+  ok &= (c->gU0 = dalloc<double>(c, nz * nv)) != nullptr;
+  ok &= (c->gVP = dalloc<double>(c, nz * nv)) != nullptr;
+  ok &= (c->gVM = dalloc<double>(c, nz * nv)) != nullptr;
+  ok &= (c->gF = dalloc<double>(c, nz * (nv + 2))) != nullptr;
+  ok &= (c->gflag = dalloc<unsigned short>(c, nz)) != nullptr;
+  ok &= (c->gshock = dalloc<unsigned char>(c, nz)) != nullptr;
+  ok &= (c->gcdt = dalloc<double>(c, nz)) != nullptr;
+  if (!ok) { pb200_gen_release(c); return PB200_ENOMEM; }
+  c->gen_ready = true;
+  return PB200_OK;
+}
+
+template <int NV>
+static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
+  GenDev G = *c->gdev;
+  G.d = c->dev;     // body-force tables may have been set after gen_setup
+  G.gline = c->gline;
+  const Dev &D = c->dev;
+  cudaStream_t st = c->stream;
+  GenArgs a;
+  a.V = c->V[c->cur];
+  a.U = c->gU; a.U0 = c->gU0; a.VP = c->gVP; a.VM = c->gVM; a.F = c->gF;
+  a.cdt = c->gcdt; a.flag = c->gflag; a.shock = c->gshock;
+  a.dt = c->d_dt; a.red = c->d_red;
+  a.w0 = w0; a.wc = wc; a.comb = comb; a.stage = stage; a.dir = 0;
+  const int T = 128;
+  auto blocks = [&](const GenBox &b) {
+    long n = (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
+    return (unsigned)((n + T - 1) / T);
+  };
+  const unsigned ball = (unsigned)((D.sv + T - 1) / T);
+  GenBox dom;
+  for (int d = 0; d < 3; d++) { dom.lo[d] = D.beg[d]; dom.hi[d] = D.end[d]; }
+  // Boundary() ended with ComputeEntropy (boundary.c:488-493)
+  if (G.entropy) { gen_entropy<<<ball, T, 0, st>>>(G, a.V); c->launches++; }
+  if (stage == 1) {
+    if (G.flatten || G.entropy) {   // FlagShock, rk_step.c:123-125 (flags were zeroed by main.c:258-261)
+      if (G.flatten) {
+        GenBox b;
+        for (int d = 0; d < 3; d++) { int inc = d < D.ndim; b.lo[d] = inc; b.hi[d] = D.tot[d] - 1 - inc; }
+        gen_shock<<<blocks(b), T, 0, st>>>(G, a, b);
+        c->launches++;
+      }
+      gen_flags<<<ball, T, 0, st>>>(G, a);
+      c->launches++;
+    }
+    gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
+    c->launches++;
+  }
+  if (c->ldw_hook) c->ldw_hook(c, stage);       // VGradCalc + LineForce once per stage (update_stage.c:116-118)
+  G.gline = c->gline;
+  for (int dir = 0; dir < D.ndim; dir++) {
+    a.dir = dir;
+    GenBox bs = dom, bf = dom;
+    bs.lo[dir] = D.beg[dir] - 1; bs.hi[dir] = D.end[dir] + 1;     // States(nbeg-1, nend+1)
+    bf.lo[dir] = D.beg[dir] - 1; bf.hi[dir] = D.end[dir];         // Riemann(nbeg-1, nend)
+    gen_states<NV><<<blocks(bs), T, 0, st>>>(G, a, bs);
+    gen_riemann<NV><<<blocks(bf), T, 0, st>>>(G, a, bf);
+    gen_rhs<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
+    c->launches += 3;
+  }
+  gen_finish<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
+  c->launches++;
+}
+
+// one stage of AdvanceStep() on the general path; Boundary() fills were enqueued by the caller
+int pb200_gen_stage(pb200_ctx *c, int stage) {
+  double w0 = 0.0, wc = 1.0;
+  int comb = 0;
+  if (stage == 2) {  // rk_step.c:18-24
+    comb = 1;
+    if (c->nstages == 2) { w0 = 0.5; wc = 0.5; } else { w0 = 0.75; wc = 0.25; }
+  } else if (stage == 3) comb = 2;
+  switch (c->nvar) {
+    case 5: gen_stage_nv<5>(c, stage, w0, wc, comb); break;
+    case 6: gen_stage_nv<6>(c, stage, w0, wc, comb); break;
+    case 7: gen_stage_nv<7>(c, stage, w0, wc, comb); break;
+    case 8: gen_stage_nv<8>(c, stage, w0, wc, comb); break;
+    default: return PB200_ENOTSUP;
+  }
+  return cudaGetLastError() == cudaSuccess ? PB200_OK : PB200_ECUDA;
+}

@@ -8,6 +8,8 @@
 #include "../../include/pluto_b200.h"
 #include "pb200_kernels.cuh"
 
+namespace pb { struct GenDev; }
+
 struct pb200_ctx {
   pb::Dev dev;
   pb200_config cfg;
@@ -37,7 +39,20 @@ struct pb200_ctx {
   cudaEvent_t pev0[16], pev1[16];
   int pdir[16], pstage[16];
   float pms[16];
+  // general-grid path (pb200_gen.cu / gen_kernels.cuh)
+  bool gen, gen_ready;
+  pb::GenDev *gdev;
+  double *gU, *gU0, *gVP, *gVM, *gF, *gcdt;
+  unsigned short *gflag;
+  unsigned char *gshock;
+  std::vector<void *> gen_allocs;
+  double *gline;                          // LineForce() per zone [3][k][j][i] (line-driven wind)
+  void (*ldw_hook)(pb200_ctx *, int stage);
 };
+
+int  pb200_gen_setup(pb200_ctx *c);
+void pb200_gen_release(pb200_ctx *c);
+int  pb200_gen_stage(pb200_ctx *c, int stage);
 
 
 // One launcher per (NVAR, body force) pair, each compiled in its own translation unit

@@ -151,7 +151,9 @@ class Hydro:
     def __init__(self, *, dimensions, nx, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
-                 small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0):
+                 small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0,
+                 geometry="CARTESIAN", grid_arrays=None, char_limiting=False, shock_flattening=False,
+                 entropy_switch=False):
         lib = L.load()
         cfg = L.Config()
         lib.pb200_config_default(C.byref(cfg))
@@ -177,6 +179,10 @@ class Hydro:
         cfg.small_pressure = small_pressure
         cfg.device = device
         cfg.body_force = int(body_force)
+        cfg.geometry = {"CARTESIAN": L.CARTESIAN, "SPHERICAL": L.SPHERICAL}[geometry]
+        cfg.char_limiting = int(bool(char_limiting))
+        cfg.shock_flattening = int(bool(shock_flattening))
+        cfg.entropy_switch = int(bool(entropy_switch))
         self.cfg = cfg
         self._lib = lib
         h = C.c_void_p()
@@ -195,6 +201,15 @@ class Hydro:
         self.xbeg = tuple(cfg.xbeg)
         self.xend = tuple(cfg.xend)
         self.last = L.StepInfo()
+        self._grid = None
+        if grid_arrays is not None:   # grid->xl, xr, dx of every active direction (np_tot entries)
+            self._grid = []
+            for d in range(3):
+                xl, xr, dxa = (np.ascontiguousarray(a, dtype=np.float64) for a in grid_arrays[d])
+                assert xl.size == self.tot[d], (d, xl.size, self.tot[d])
+                self._grid.append((xl, xr, dxa))
+                L.check(lib.pb200_set_grid(h, d, xl.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p),
+                                           dxa.ctypes.data_as(C.c_void_p)))
         if dx is not None:      # block of a larger uniform grid: impose the global grid->dx
             for d in range(dimensions):
                 n = self.tot[d]
@@ -237,6 +252,12 @@ class Hydro:
             b = self.beg[d]
             sl.append(slice(b, b + self.nx[d]))
         return tuple(sl)
+
+    def x(self, d):
+        """grid->x[d] (cell centres incl. ghosts)."""
+        if self._grid is not None:
+            return 0.5 * (self._grid[d][0] + self._grid[d][1])
+        return self.cell_centers(d)
 
     def cell_centers(self, d):
         n = self.tot[d]

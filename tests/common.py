@@ -148,3 +148,21 @@ def random_state(shape_int, seed, smooth=True):
         v[4][..., (3 * nx) // 4:] *= 0.1
         v[1:4] += rng.normal(0, 0.05, size=(3, nz, ny, nx))
     return v
+
+
+def hydro_kwargs_from_gen(kw):
+    """GenOracle keywords -> pluto_sirocco_b200.Hydro keywords (grid arrays from the restated
+    set_grid.c of oracle/pluto_grid.py, exactly what the shim passes from the reference's Grid)."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    from pluto_grid import make_grid
+    kw = dict(kw)
+    grid = kw.pop("grid")
+    nd = kw["dimensions"]
+    ng = kw.get("nghost", 2)
+    arrays = [make_grid(grid[d], ng if d < nd else 0) for d in range(3)]
+    kw["nx"] = tuple(int(grid[d][1]) if d < nd else 1 for d in range(3))
+    kw["xbeg"] = tuple(float(grid[d][0]) for d in range(3))
+    kw["xend"] = tuple(float(grid[d][2]) for d in range(3))
+    kw["grid_arrays"] = arrays
+    return kw
