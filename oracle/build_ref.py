@@ -91,6 +91,13 @@ CONFIGS = {
                        states="plm"),
     "sph1d": dict(local="sph", overrides={"DIMENSIONS": "1"}, states="plm"),
     "sph3d": dict(local="sph", overrides={"DIMENSIONS": "3"}, states="plm"),
+    # C4: the line-driven disc wind of the sirocco coupling, UNMODIFIED user files of the reference
+    # (Test_Problems/LineDrivenWind/cv_idl: init.c, definitions.h, userdef_output.c)
+    "ldw": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={}, states="plm",
+                extra_vpath=["Cooling/BLONDIN", "LineDriven"], extra_objs=["cooling", "line_connect"]),
+    # the same without the BLONDIN source step: isolates the hydro + line-force update
+    "ldw_nocool": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={"COOLING": "NO"},
+                       states="plm", extra_vpath=["LineDriven"], extra_objs=["line_connect"]),
     # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
     "kh3d": dict(local="kh", overrides={}, states="plm"),
 }

@@ -529,6 +529,7 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
  *  Boundaries: boundary.c:228-459 (side order, full transverse range), fills :617-767,
  *  FlipSign :503-610 (reflective: vn; axisymmetric: vn and vphi; eqtsymmetric: vn)
  * --------------------------------------------------------------------------------------- */
+static double *g_Uc_for_floor = NULL;   /* Uc, while Boundary() runs inside stages >= 2 */
 static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side);
 static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc);
 
@@ -804,7 +805,9 @@ int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *
   memset(x->flag, 0, g->sv * sizeof(uint16_t));          /* main.c:258-261 */
   double v[NVMAX];
   for (int stage = 1; stage <= c->rk; stage++) {
+    g_Uc_for_floor = (stage > 1) ? x->Uc : NULL;    /* stage 1 re-derives all of Uc right after */
     boundary(c, g, Vc);
+    g_Uc_for_floor = NULL;
     if (stage == 1) {
       if (c->flattening || c->entropy) flag_shock(c, g, Vc, x->flag);   /* rk_step.c:123-125 */
       for (int k = g->beg[2]; k <= g->end[2]; k++)
@@ -836,11 +839,192 @@ int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *
 }
 
 /* ---------------------------------------------------------------------------------------
- *  Line-driven wind: placeholders until the LDW rows are restated (ldw == 0 never calls them)
+ *  Line-driven wind (LINE_DRIVEN_WIND SIROCCO_MODE), Src/LineDriven/line_connect.c, and the user
+ *  boundaries of Test_Problems/LineDrivenWind/cv_idl/init.c:157-316
  * --------------------------------------------------------------------------------------- */
-static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side) { (void)c; (void)g; (void)Vc; (void)side; }
-static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) { (void)c; (void)g; (void)Vc; }
-static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, double *dvds) { (void)c; (void)g; (void)Vc; (void)dvds; }
+#define CONST_amu 1.66053886e-24    /* pluto.h:299-321 */
+#define CONST_c 2.99792458e10
+#define CONST_G 6.6726e-8
+#define CONST_kB 1.3806505e-16
+#define CONST_mp 1.67262171e-24
+#define CONST_PI 3.14159265358979
+#define CONST_sigma 5.67051e-5
+#define CONST_sigmaT 6.6524e-25
+
+static double kelvin(const gen_cfg *c) { return c->unit_velocity * c->unit_velocity * CONST_amu / CONST_kB; }  /* pluto.h:560 */
+
+/* UserDefBoundary(side == 0): density / pressure floors over TOT_LOOP and the mid-plane reset
+ * (init.c:199-316).  Uc of a floored zone is re-derived like PrimToCons3D(d->Vc, d->Uc, 1-zone box). */
+static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) {
+  int nvar = g->nvar, TRC = NFLX;
+  double KELVIN = kelvin(c), mu = c->mu;
+  double dfloor = c->dfloor / c->unit_density;
+  double rho_0 = c->rho0 / c->unit_density;
+  double tfloor = 5.e2, pfloor = dfloor * tfloor / (KELVIN * mu);
+  double r_WD = g->xl[0][g->beg[0]];                 /* g_domBeg[IDIR] */
+  double gm_cgs = CONST_G * c->cent_mass;
+  double gm_code = gm_cgs / (c->unit_length * c->unit_velocity * c->unit_velocity);
+  const double *x1 = g->xgc[0], *x2 = g->xgc[1];
+  int jlast = g->end[1];     /* j == np_int[JDIR] + 2 with the 3 ghost zones of this configuration */
+  for (int k = 0; k < g->tot[2]; k++) for (int j = 0; j < g->tot[1]; j++) for (int i = 0; i < g->tot[0]; i++) {
+    long o = k * g->sk + j * g->sj + i;
+    double *rho = Vc + RHO * g->sv + o, *prs = Vc + PRS * g->sv + o;
+    double *v1 = Vc + VX1 * g->sv + o, *v2 = Vc + VX2 * g->sv + o, *v3 = Vc + VX3 * g->sv + o;
+    int convert = 0;
+    if (*rho < dfloor) {
+      if (*rho < 0.0) *rho = dfloor;
+      double cs = sqrt(c->gamma * *prs / *rho);
+      double dfact = *rho / dfloor;
+      *rho = dfloor;
+      *v1 = dfact * *v1; *v2 = dfact * *v2; *v3 = dfact * *v3;
+      *prs = pow(cs, 2) * *rho / c->gamma;
+      double temp = *prs / *rho * KELVIN * mu;
+      if (temp < tfloor) { temp = tfloor; *prs = *rho * temp / (KELVIN * mu); }
+      Vc[TRC * g->sv + o] = 0.0;
+      convert = 1;
+    }
+    if (*prs < pfloor) { *prs = pfloor; convert = 1; }
+    if (convert && g_Uc_for_floor) {
+      double v[NVMAX];
+      for (int nv = 0; nv < nvar; nv++) v[nv] = Vc[nv * g->sv + o];
+      prim_to_cons(c, nvar, v, g_Uc_for_floor + o * nvar);
+    }
+    if (j == jlast) {     /* the coordinate test of init.c:283-284 holds on a single-block grid */
+      double r = x1[i], theta = x2[j], rcyl = r * sin(theta);
+      double rho_mid = rho_0 * pow((r / r_WD), -1.0 * c->rho_alpha);
+      *v2 = (*rho * *v2) / rho_mid;
+      *rho = rho_mid;
+      *v1 = 0.0;
+      *v3 = sqrt(gm_code / r) * sin(theta);
+      double teff = pow(3.0 * gm_cgs * c->disk_mdot / (8.0 * CONST_PI * CONST_sigma), 0.25);
+      teff *= pow(r_WD * c->unit_length, -0.75);
+      double temp = teff * pow(r_WD / rcyl, 0.75) * pow(1.0 - sqrt(r_WD / rcyl), 0.25);
+      *prs = rho_mid * temp / (KELVIN * mu);
+      Vc[TRC * g->sv + o] = 1.0;
+    }
+  }
+}
+
+/* UserDefBoundary(X1_BEG / X1_END / X2_BEG), init.c:319-363 */
+static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side) {
+  (void)c;
+  int nvar = g->nvar;
+  int IBEG = g->beg[0], IEND = g->end[0], JBEG = g->beg[1];
+  for (int k = 0; k < g->tot[2]; k++) {
+    if (side == 0) {          /* X1_BEG */
+      for (int j = 0; j < g->tot[1]; j++) for (int i = 0; i < IBEG; i++) {
+        long o = k * g->sk + j * g->sj + i, os = k * g->sk + j * g->sj + IBEG;
+        for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = Vc[nv * g->sv + os];
+        Vc[VX1 * g->sv + o] = MINV(Vc[VX1 * g->sv + o], 0.0);
+      }
+    } else if (side == 1) {   /* X1_END */
+      for (int j = 0; j < g->tot[1]; j++) for (int i = IEND + 1; i < g->tot[0]; i++) {
+        long o = k * g->sk + j * g->sj + i, os = k * g->sk + j * g->sj + IEND;
+        for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = Vc[nv * g->sv + os];
+        Vc[VX1 * g->sv + o] = MAXV(Vc[VX1 * g->sv + o], 0.0);
+      }
+    } else if (side == 2) {   /* X2_BEG: reflective velocities, outflow density and pressure */
+      for (int j = 0; j < JBEG; j++) for (int i = 0; i < g->tot[0]; i++) {
+        long o = k * g->sk + j * g->sj + i, os = k * g->sk + (2 * JBEG - j - 1) * g->sj + i;
+        long ob = k * g->sk + JBEG * g->sj + i;
+        for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = Vc[nv * g->sv + os];
+        Vc[VX2 * g->sv + o] *= -1.0;
+        Vc[RHO * g->sv + o] = Vc[RHO * g->sv + ob];
+        Vc[PRS * g->sv + o] = Vc[PRS * g->sv + ob];
+      }
+    }
+  }
+}
+
+/* bilinear(), line_connect.c:746-767 */
+static void bilinear(const double x11[2], const double x22[2], const double v11[2], const double v12[2],
+                     const double v21[2], const double v22[2], const double test[2], double ans[2]) {
+  double fracx1 = (test[0] - x11[0]) / (x22[0] - x11[0]);
+  double fracx2 = (test[1] - x11[1]) / (x22[1] - x11[1]);
+  double temp1 = (1.0 - fracx1) * v11[0] + fracx1 * v21[0];
+  double temp2 = (1.0 - fracx1) * v12[0] + fracx1 * v22[0];
+  ans[0] = (1.0 - fracx2) * temp1 + fracx2 * temp2;
+  temp1 = (1.0 - fracx1) * v11[1] + fracx1 * v21[1];
+  temp2 = (1.0 - fracx1) * v12[1] + fracx1 * v22[1];
+  ans[1] = (1.0 - fracx2) * temp1 + fracx2 * temp2;
+}
+
+/* VGradCalc(), line_connect.c:504-744: dvds[iangle][k][j][i] over the interior */
+static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, double *dvds) {
+  const double UL = c->unit_length, UV = c->unit_velocity;
+  const double *x1 = g->x[0], *x2 = g->x[1];
+  const double *V1 = Vc + VX1 * g->sv, *V2 = Vc + VX2 * g->sv;
+  long sj = g->sj;
+  for (int ia = 0; ia < c->nangles; ia++)
+    for (int k = g->beg[2]; k <= g->end[2]; k++) for (int j = g->beg[1]; j <= g->end[1]; j++)
+      for (int i = g->beg[0]; i <= g->end[0]; i++) {
+        long o = k * g->sk + j * g->sj + i;
+        double x11[2], x22[2], v11[2], v12[2], v22[2], v21[2], loc[2], ans1[2], ans2[2];
+        x11[0] = (x1[i - 1] + x1[i]) / 2.0 * UL;
+        x11[1] = (x2[j - 1] + x2[j]) / 2.0;
+        x22[0] = (x1[i + 1] + x1[i]) / 2.0 * UL;
+        x22[1] = (x2[j + 1] + x2[j]) / 2.0;
+        double maxds = fabs(x22[0] - x11[0]);
+        if (maxds > (x1[i] * UL * fabs(x22[1] - x11[1]))) maxds = x1[i] * UL * fabs(x22[1] - x11[1]);
+        maxds /= 2.0;
+        double fr = c->flux_r[ia * g->sv + o], ft = c->flux_t[ia * g->sv + o], fp = c->flux_p[ia * g->sv + o];
+        double mod_flux = sqrt(pow(fr, 2) + pow(ft, 2) + pow(fp, 2));
+        double r_off = 0, t_off = 0, ds;
+        double theta_angle = (ia + 0.5) * (2.0 * CONST_PI) / 36.0;
+        if (mod_flux == 0.0) ds = -999;
+        else {
+          double x = x1[i] * sin(x2[j]) * UL, z = x1[i] * cos(x2[j]) * UL;
+          double dx1 = maxds * sin(theta_angle), dx2 = maxds * cos(theta_angle);
+          ds = sqrt(dx1 * dx1 + dx2 * dx2);
+          r_off = sqrt((x + dx1) * (x + dx1) + (z + dx2) * (z + dx2));
+          t_off = atan((x + dx1) / (z + dx2));
+        }
+        v11[0] = (V1[o - sj - 1] + V1[o - sj] + V1[o - 1] + V1[o]) / 4.0;
+        v11[1] = (V2[o - sj - 1] + V2[o - sj] + V2[o - 1] + V2[o]) / 4.0;
+        v12[0] = (V1[o + sj - 1] + V1[o - 1] + V1[o + sj] + V1[o]) / 4.0;
+        v12[1] = (V2[o + sj - 1] + V2[o - 1] + V2[o + sj] + V2[o]) / 4.0;
+        v22[0] = (V1[o + sj] + V1[o + sj + 1] + V1[o + 1] + V1[o]) / 4.0;
+        v22[1] = (V2[o + sj] + V2[o + sj + 1] + V2[o + 1] + V2[o]) / 4.0;
+        v21[0] = (V1[o + 1] + V1[o - sj + 1] + V1[o - sj] + V1[o]) / 4.0;
+        v21[1] = (V2[o + 1] + V2[o - sj + 1] + V2[o - sj] + V2[o]) / 4.0;
+        loc[0] = x1[i] * UL;
+        loc[1] = x2[j];
+        bilinear(x11, x22, v11, v12, v21, v22, loc, ans1);
+        double vx1 = (ans1[0] * UV * sin(x2[j]) + ans1[1] * UV * cos(x2[j]));
+        double vz1 = (ans1[0] * UV * cos(x2[j]) - ans1[1] * UV * sin(x2[j]));
+        double out;
+        if (ds == -999) out = -999;
+        else {
+          loc[0] = r_off; loc[1] = t_off;
+          bilinear(x11, x22, v11, v12, v21, v22, loc, ans2);
+          double vx2 = (ans2[0] * UV * sin(loc[1]) + ans2[1] * UV * cos(loc[1]));
+          double vz2 = (ans2[0] * UV * cos(loc[1]) - ans2[1] * UV * sin(loc[1]));
+          double v1 = sin(theta_angle) * vx1 + cos(theta_angle) * vz1;
+          double v2 = sin(theta_angle) * vx2 + cos(theta_angle) * vz2;
+          out = fabs((v2 - v1) / ds);
+        }
+        dvds[ia * g->sv + o] = out;
+      }
+}
+
+/* LineForce(), line_connect.c:815-903 (KRAD/ALPHARAD power-law multiplier) */
 static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad) {
-  (void)c; (void)g; (void)v; (void)dvds; (void)o; grad[0] = grad[1] = grad[2] = 0.0;
+  double sigma_e = CONST_sigmaT / CONST_amu / 1.18;
+  double rho = v[RHO] * c->unit_density;
+  double T = v[PRS] / v[RHO] * kelvin(c) * c->mu;
+  double v_th = sqrt((2.0 * CONST_kB * T) / CONST_mp);
+  double M_max = 4400.;
+  double UNIT_ACC = c->unit_velocity * c->unit_velocity / c->unit_length;
+  grad[0] = grad[1] = grad[2] = 0.0;
+  for (int ia = 0; ia < c->nangles; ia++) {
+    double flux_r = c->flux_r[ia * g->sv + o], flux_t = c->flux_t[ia * g->sv + o], M_UV;
+    double dv = dvds[ia * g->sv + o];
+    if (dv > 0.0) {
+      double t_UV = sigma_e * rho * v_th / dv;
+      M_UV = c->krad * pow(t_UV, c->alpharad);
+      if (M_UV > M_max) M_UV = M_max;
+    } else M_UV = 0.0;
+    grad[0] += ((1.0 + M_UV) * sigma_e * flux_r / CONST_c) / UNIT_ACC;
+    grad[1] += ((1.0 + M_UV) * sigma_e * flux_t / CONST_c) / UNIT_ACC;
+  }
 }

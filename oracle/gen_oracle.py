@@ -55,7 +55,7 @@ class GenOracle:
     def __init__(self, *, dimensions, grid, geometry="CARTESIAN", gamma=5. / 3., reconstruction="LINEAR",
                  time_stepping="RK2", solver="hllc", limiter="DEFAULT", bcs=("outflow",) * 6, ntracer=0,
                  nghost=2, small_density=1e-12, small_pressure=1e-12, body_force=0, char_limiting=False,
-                 shock_flattening=False, entropy_switch=False, **_):
+                 shock_flattening=False, entropy_switch=False, ldw=None, **_):
         assert reconstruction == "LINEAR"
         c = GenCfg()
         c.ndim = dimensions
@@ -93,6 +93,8 @@ class GenOracle:
         self.shape = (self.nvar, self.tot[2], self.tot[1], self.tot[0])
         self._h = None
         self._bf = {}
+        if ldw is not None:
+            self.set_ldw(**ldw)
 
     def x(self, d):
         return 0.5 * (self.xl[d] + self.xr[d])
@@ -101,6 +103,22 @@ class GenOracle:
         a = np.ascontiguousarray(np.broadcast_to(tab, self.shape[1:]), dtype=np.float64)
         self._bf[comp] = a
         self.c.bf_g[comp] = a.ctypes.data
+
+    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p, userdef_bc=True):
+        """LINE_DRIVEN_WIND SIROCCO_MODE: g_inputParam[] of cv_idl (dict by label), UNIT_* (dict),
+        directional fluxes [nangles][k][j][i] incl. ghosts."""
+        c = self.c
+        c.ldw = 1
+        c.ldw_bc = int(userdef_bc)
+        self._flux = [np.ascontiguousarray(a, dtype=np.float64) for a in (flux_r, flux_t, flux_p)]
+        assert self._flux[0].shape[1:] == self.shape[1:], (self._flux[0].shape, self.shape)
+        c.nangles = self._flux[0].shape[0]
+        c.flux_r, c.flux_t, c.flux_p = (a.ctypes.data for a in self._flux)
+        c.unit_length, c.unit_velocity, c.unit_density = units["length"], units["velocity"], units["density"]
+        c.mu, c.krad, c.alpharad, c.t_iso = params["MU"], params["KRAD"], params["ALPHARAD"], params["T_ISO"]
+        c.dfloor, c.rho0, c.rho_alpha = params["DFLOOR"], params["RHO_0"], params["RHO_ALPHA"]
+        c.cent_mass, c.disk_mdot = params["CENT_MASS"], params["DISK_MDOT"]
+        c.lx, c.tx = params["L_star"] * params["f_x"], params["T_x"]
 
     def _handle(self):
         if self._h is None:

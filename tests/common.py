@@ -44,11 +44,13 @@ def gen_kwargs_from_golden(g):
             grid.append((float(row[0]), int(row[1]), float(row[2]), "r", float(row[4])))
         else:
             grid.append((float(row[0]), int(row[1]), float(row[2])))
+    flat = bool(int(g["shock_flattening"]))
     return dict(dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
-                char_limiting=bool(int(g["char_limiting"])), shock_flattening=bool(int(g["shock_flattening"])),
-                entropy_switch=bool(int(g["entropy_switch"])))
+                char_limiting=bool(int(g["char_limiting"])), shock_flattening=flat,
+                entropy_switch=bool(int(g["entropy_switch"])),
+                nghost=3 if flat else 2)     # GetNghost(), Src/get_nghost.c:42-51
 
 
 def set_point_mass_gravity(obj, gm):
@@ -166,3 +168,61 @@ def hydro_kwargs_from_gen(kw):
     kw["xend"] = tuple(float(grid[d][2]) for d in range(3))
     kw["grid_arrays"] = arrays
     return kw
+
+
+# ---------------------------------------------------------------------------------------------
+#  Line-driven wind (Test_Problems/LineDrivenWind/cv_idl): parameters and synthetic sirocco tables
+# ---------------------------------------------------------------------------------------------
+MSUN = 1.98840987e33
+LDW_PARAMS = dict(MU=0.6, RHO_0=1e-9, R_0=8.31e8, RHO_ALPHA=0.0, CENT_MASS=0.6 * MSUN,
+                  DISK_MDOT=3.14e-8 * MSUN / (365.25 * 24 * 3600), T_ISO=40000.0, L_star=9.05e34, f_x=0.1,
+                  f_uv=0.9, T_x=160000.0, KRAD=0.59, ALPHARAD=-0.6, DFLOOR=1e-24, GAMMA=5.0 / 3.0)
+LDW_UNITS = dict(density=1e-14, length=1e9, velocity=1e9)
+LDW_BCS = ("userdef", "outflow", "userdef", "reflective", "outflow", "outflow")
+LDW_NANGLES = 36
+
+
+def ldw_flux_tables(x1, x2, nangles=LDW_NANGLES):
+    """Synthetic directional UV fluxes in the layout of flux_{r,t,p}_UV[iangle][k][j][i]
+    (line_connect.c:97-110), for ALL zones of the 1-D coordinate arrays given (the reference only
+    fills the interior; ghost entries are never read).  Bin a points along (sin th_a, cos th_a) in
+    the (x, z) plane with th_a = (a + 1/2) 2 pi / nangles (line_connect.c:563,654); the flux a disc
+    + central source would send through it is modelled as F0(r) w_a(theta), zero in the bins
+    pointing back at the source (so that the "no flux" branch, dvds = -999, is exercised)."""
+    r = np.asarray(x1)[None, None, :] * LDW_UNITS["length"]
+    th = np.asarray(x2)[None, :, None]
+    a = (np.arange(nangles) + 0.5) * (2.0 * np.pi) / nangles
+    da = a[:, None, None] - th
+    w = np.clip(np.cos(da), 0.0, None) ** 3 * (1.0 + 0.3 * np.sin(3.0 * a[:, None, None]))
+    f0 = LDW_PARAMS["f_uv"] * LDW_PARAMS["L_star"] / (4.0 * np.pi * r * r) / 6.0
+    fr = f0 * w * np.cos(da)
+    ft = f0 * w * np.sin(da)
+    shape = (nangles, 1, th.shape[1], r.shape[2])
+    # round-trip through the text format of the flux files so both sides hold the same doubles
+    rt = np.vectorize(lambda q: float("%.17e" % q))
+    return rt(fr).reshape(shape), rt(ft).reshape(shape), np.zeros(shape)
+
+
+def write_ldw_flux_files(wd, x1, x2, ng, fr, ft, fp):
+    """directional_flux_{r,theta,phi}.dat in the format read by read_sirocco_fluxes()
+    (line_connect.c:84-165): two header lines (the 2nd ends with the number of angular bins), then
+    `i j inwind r[cm] theta[rad] f0 ... f{n-1}` per interior zone."""
+    nang = fr.shape[0]
+    for name, tab in (("r", fr), ("theta", ft), ("phi", fp)):
+        with open(Path(wd) / ("directional_flux_%s.dat" % name), "w") as f:
+            f.write("# synthetic directional fluxes\n# NANGLES %d\n" % nang)
+            for j in range(ng, len(x2) - ng):
+                for i in range(ng, len(x1) - ng):
+                    vals = " ".join("%.17e" % tab[a, 0, j, i] for a in range(nang))
+                    f.write("%d %d 0 %.17e %.17e %s\n" % (i - ng, j - ng, x1[i] * LDW_UNITS["length"], x2[j], vals))
+
+
+def ldw_setup(obj, x1, x2):
+    """Hand the cv_idl problem to a GenOracle or a Hydro: gravity of the central mass
+    (BodyForceVector, init.c:372-386), units, parameters and the synthetic flux tables."""
+    gm_code = 6.6726e-8 * LDW_PARAMS["CENT_MASS"] / (LDW_UNITS["length"] * LDW_UNITS["velocity"] ** 2)
+    obj.set_body_force_vector(0, (-1.0 * gm_code / (x1 * x1)).reshape(1, 1, -1))
+    obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
+    obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
+    fr, ft, fp = ldw_flux_tables(x1, x2)
+    obj.set_ldw(params=LDW_PARAMS, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)

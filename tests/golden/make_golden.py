@@ -136,6 +136,46 @@ def make_case3(out, name, c):
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
+# the line-driven disc wind (UNMODIFIED user files of the reference, cv_idl) with synthetic
+# sirocco flux tables (tests/common.py: ldw_flux_tables)
+sys.path.insert(0, str(ROOT / "tests"))
+import common  # noqa: E402
+
+LDW_GRID = [(0.87, 48, 8.7, "r", 1.05), (0.0, 36, HALF_PI, "r", 0.95), (0.0, 1, 1.0)]
+CASES4 = {
+    "ldw_nocool_hll": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hll", maxsteps=10, cooling=False),
+    "ldw_nocool_hllc": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hllc", maxsteps=8, cooling=False),
+}
+
+
+def make_case4(out, name, c):
+    build_ref.build(c["cfg"])
+    grid = c["grid"]
+    ng = 3
+    nx = [int(grid[0][1]), int(grid[1][1]), 1]
+    xl1, xr1, _ = pluto_grid.make_grid(grid[0], ng)
+    xl2, xr2, _ = pluto_grid.make_grid(grid[1], ng)
+    x1, x2 = 0.5 * (xl1 + xr1), 0.5 * (xl2 + xr2)
+    fr, ft, fp = common.ldw_flux_tables(x1, x2)
+    with tempfile.TemporaryDirectory() as wd:
+        common.write_ldw_flux_files(wd, x1, x2, ng, fr, ft, fp)
+        r = refrun.run(c["cfg"], wd, shape=(1, nx[1], nx[0]), nvar=6, maxsteps=c["maxsteps"],
+                       grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
+                       solver=c["solver"], bcs=common.LDW_BCS, dbl=(-1.0, 1), params=common.LDW_PARAMS, timeout=250)
+    nd_ = len(r["data"]) - 1
+    steps = np.array(r["steps"][:nd_], dtype=np.float64)
+    data = np.stack(r["data"][:nd_])
+    gridarr = np.array([[g[0], g[1], g[2], 1.0 if (len(g) > 3 and g[3] == "r") else 0.0,
+                         g[4] if len(g) > 4 else 1.0] for g in grid], dtype=np.float64)
+    np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx), dims=2,
+                        recon="LINEAR", rk="RK2", solver=c["solver"], bcs=np.array(common.LDW_BCS),
+                        gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-4, tstop=1.0,
+                        ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=1,
+                        body_force="vector", limiter="VANLEER_LIM", char_limiting=1, shock_flattening=1,
+                        entropy_switch=1, cooling=int(c["cooling"]))
+    print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
+
+
 def main():
     out = Path(__file__).resolve().parent
     only = set(sys.argv[1:])
@@ -145,6 +185,9 @@ def main():
     for name, c in CASES3.items():
         if not only or name in only:
             make_case3(out, name, c)
+    for name, c in CASES4.items():
+        if not only or name in only:
+            make_case4(out, name, c)
     for name, (cfg, nd, N, recon, rk, solver, bcs, maxsteps, params, gamma, cfl, first_dt, tstop) in CASES.items():
         if only and name not in only:
             continue
