@@ -146,6 +146,27 @@ int  pb200_set_body_force_vector(pb200_ctx *ctx, int comp, const double *tab, lo
 int  pb200_set_body_force_potential(pb200_ctx *ctx, int where, const double *tab, long n,
                                     long si, long sj, long sk);
 
+/* LINE_DRIVEN_WIND SIROCCO_MODE (Src/LineDriven/line_connect.c; definitions.h of
+ * Test_Problems/LineDrivenWind/cv_idl).  The reference keeps the sirocco tables in globals
+ * (flux_r_UV, flux_t_UV, flux_p_UV[NFLUX_ANGLES][k][j][i], Src/globals.h:197-217) filled by
+ * read_sirocco_fluxes(); VGradCalc() runs once per UpdateStage (update_stage.c:139) and
+ * LineForce() per zone and sweep (rhs_source.c:284-297,386-396).  pb200_ldw_enable() switches
+ * both on for a general-path context, pb200_ldw_set_fluxes() uploads the tables (whole arrays
+ * incl. ghost zones; call again whenever the reference re-reads them).  userdef_bc != 0 also
+ * installs the device versions of that problem's UserDefBoundary(): the side == 0 floors and
+ * mid-plane reset (cv_idl/init.c:199-316, INTERNAL_BOUNDARY YES) and the X1_BEG / X1_END / X2_BEG
+ * fills (init.c:319-363) for every side whose type is PB200_BC_USERDEF. */
+typedef struct pb200_ldw_config {
+  int    nangles;                 /* NFLUX_ANGLES (<= 64) */
+  int    userdef_bc;
+  double unit_length, unit_velocity, unit_density;      /* UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY */
+  double mu, krad, alpharad;      /* g_inputParam[MU], [KRAD], [ALPHARAD] (the 999/999 fit-table mode is not built) */
+  double dfloor, rho_0, rho_alpha, cent_mass, disk_mdot;   /* g_inputParam[DFLOOR], [RHO_0], [RHO_ALPHA], [CENT_MASS], [DISK_MDOT] (cgs) */
+  double lx, tx;                  /* g_inputParam[L_star]*[f_x], g_inputParam[T_x] (BLONDIN cooling) */
+} pb200_ldw_config;
+int  pb200_ldw_enable(pb200_ctx *ctx, const pb200_ldw_config *ldw);
+int  pb200_ldw_set_fluxes(pb200_ctx *ctx, const double *flux_r, const double *flux_t, const double *flux_p);
+
 /* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
 int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);
 int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);

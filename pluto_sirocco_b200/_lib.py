@@ -31,6 +31,14 @@ class Config(C.Structure):
                 ("reserved", C.c_int * 3)]
 
 
+class LdwConfig(C.Structure):
+    _fields_ = [("nangles", C.c_int), ("userdef_bc", C.c_int), ("unit_length", C.c_double),
+                ("unit_velocity", C.c_double), ("unit_density", C.c_double), ("mu", C.c_double),
+                ("krad", C.c_double), ("alpharad", C.c_double), ("dfloor", C.c_double), ("rho_0", C.c_double),
+                ("rho_alpha", C.c_double), ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
+                ("lx", C.c_double), ("tx", C.c_double)]
+
+
 class StepInfo(C.Structure):
     _fields_ = [("invDt_hyp", C.c_double), ("maxMach", C.c_double),
                 ("c2p_failures", C.c_ulonglong), ("gpu_ms", C.c_float), ("launches", C.c_int)]
@@ -51,6 +59,8 @@ SYMBOLS = {
     "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pb200_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
+    "pb200_ldw_enable": (C.c_int, [_P, C.POINTER(LdwConfig)]),
+    "pb200_ldw_set_fluxes": (C.c_int, [_P, _P, _P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),

@@ -25,6 +25,22 @@ namespace pb {
 enum { GF_MINMOD = 1, GF_FLAT = 2, GF_HLL = 4, GF_ENTROPY = 8, GF_C2P_FAIL = 64 };   // pluto.h:212-221
 enum { GEO_CARTESIAN = 1, GEO_SPHERICAL = 4 };
 
+// LINE_DRIVEN_WIND SIROCCO_MODE (Src/LineDriven/line_connect.c) + the user boundaries of
+// Test_Problems/LineDrivenWind/cv_idl/init.c
+struct LdwDev {
+  int on, userdef_bc, nangles;
+  const double *flux_r, *flux_t, *flux_p;   // [nangles][k][j][i]
+  double *dvds;                             // dvds_array [nangles][k][j][i]
+  const double *sin_a, *cos_a;              // sin/cos((a + 1/2) 2 pi / 36), libm values from the host
+  const double *sin_t, *cos_t;              // sin/cos(x2[j])
+  const double *xgc1, *xgc2;                // grid->xgc (mid-plane reset uses the centroids)
+  double UL, UV, UD;                        // UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY
+  double kelvin_mu;                         // KELVIN * mu
+  double krad, alpharad;
+  double sigma_e, unit_acc;                 // sigma_T/amu/1.18 ; UNIT_ACCELERATION
+  double dfloor, pfloor, tfloor, rho_0, rho_alpha, r_WD, gm_code, teff_wd;   // init.c:175-197,296-300
+};
+
 struct GenDev {
   Dev d;
   int nvar, geometry, limiter, char_lim, flatten, entropy, solver;
@@ -36,7 +52,8 @@ struct GenDev {
   const double *A[3];                  // grid->A[d], one extra layer at index -1 along d
   long Aoff[3], Asj[3], Ask[3];
   const double *dx_dl[3];              // grid->dx_dl[d][j][i]
-  const double *gline;                 // LINE_DRIVEN_WIND: LineForce() per zone, [3][k][j][i], or null
+  const double *gline;                 // unused (kept for layout stability)
+  LdwDev ldw;
 };
 
 struct GenArgs {
@@ -323,6 +340,179 @@ static __global__ void gen_riemann(GenDev g, GenArgs a, GenBox b) {
   if ((threadIdx.x & 31) == 0 && machv > 0.0) atomic_max_pos(a.red + 1, machv);
 }
 
+// ---- line-driven wind ----------------------------------------------------------------------
+// bilinear(), line_connect.c:746-767
+PB_D void gen_bilinear(const double (&x11)[2], const double (&x22)[2], const double (&v11)[2], const double (&v12)[2],
+                       const double (&v21)[2], const double (&v22)[2], double t0, double t1, double (&ans)[2]) {
+  const double f1 = (t0 - x11[0]) / (x22[0] - x11[0]);
+  const double f2 = (t1 - x11[1]) / (x22[1] - x11[1]);
+  double a = (1.0 - f1) * v11[0] + f1 * v21[0];
+  double b = (1.0 - f1) * v12[0] + f1 * v22[0];
+  ans[0] = (1.0 - f2) * a + f2 * b;
+  a = (1.0 - f1) * v11[1] + f1 * v21[1];
+  b = (1.0 - f1) * v12[1] + f1 * v22[1];
+  ans[1] = (1.0 - f2) * a + f2 * b;
+}
+
+// VGradCalc(), line_connect.c:504-744: one thread per (zone, angular bin); the offsets that the
+// reference tabulates once (dvds_r/t/mod_offset) are recomputed, they only depend on the grid
+static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const LdwDev &w = g.ldw;
+  const int ia = blockIdx.y;
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  const long sj = d.sj;
+  const double *x1 = g.x[0], *x2 = g.x[1];
+  const double *V1 = a.V + 1 * d.sv, *V2 = a.V + 2 * d.sv;
+  double x11[2], x22[2], v11[2], v12[2], v22[2], v21[2], ans1[2], ans2[2];
+  const double x1i = __ldg(x1 + i), x2j = __ldg(x2 + j);
+  x11[0] = (__ldg(x1 + i - 1) + x1i) / 2.0 * w.UL;
+  x11[1] = (__ldg(x2 + j - 1) + x2j) / 2.0;
+  x22[0] = (__ldg(x1 + i + 1) + x1i) / 2.0 * w.UL;
+  x22[1] = (__ldg(x2 + j + 1) + x2j) / 2.0;
+  double maxds = fabs(x22[0] - x11[0]);
+  const double arc = x1i * w.UL * fabs(x22[1] - x11[1]);
+  if (maxds > arc) maxds = arc;
+  maxds /= 2.0;
+  const double fr = __ldg(w.flux_r + ia * d.sv + o), ft = __ldg(w.flux_t + ia * d.sv + o);
+  const double fp = w.flux_p ? __ldg(w.flux_p + ia * d.sv + o) : 0.0;
+  const double mod_flux = sqrt(fr * fr + ft * ft + fp * fp);
+  double out = -999.0;
+  if (mod_flux != 0.0) {
+    const double st = __ldg(w.sin_t + j), ct = __ldg(w.cos_t + j);
+    const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
+    v11[0] = (V1[o - sj - 1] + V1[o - sj] + V1[o - 1] + V1[o]) / 4.0;
+    v11[1] = (V2[o - sj - 1] + V2[o - sj] + V2[o - 1] + V2[o]) / 4.0;
+    v12[0] = (V1[o + sj - 1] + V1[o - 1] + V1[o + sj] + V1[o]) / 4.0;
+    v12[1] = (V2[o + sj - 1] + V2[o - 1] + V2[o + sj] + V2[o]) / 4.0;
+    v22[0] = (V1[o + sj] + V1[o + sj + 1] + V1[o + 1] + V1[o]) / 4.0;
+    v22[1] = (V2[o + sj] + V2[o + sj + 1] + V2[o + 1] + V2[o]) / 4.0;
+    v21[0] = (V1[o + 1] + V1[o - sj + 1] + V1[o - sj] + V1[o]) / 4.0;
+    v21[1] = (V2[o + 1] + V2[o - sj + 1] + V2[o - sj] + V2[o]) / 4.0;
+    gen_bilinear(x11, x22, v11, v12, v21, v22, x1i * w.UL, x2j, ans1);
+    const double vx1 = (ans1[0] * w.UV * st + ans1[1] * w.UV * ct);
+    const double vz1 = (ans1[0] * w.UV * ct - ans1[1] * w.UV * st);
+    const double x = x1i * st * w.UL, z = x1i * ct * w.UL;
+    const double dx1 = maxds * sa, dx2 = maxds * ca;
+    const double ds = sqrt(dx1 * dx1 + dx2 * dx2);
+    const double r_off = sqrt((x + dx1) * (x + dx1) + (z + dx2) * (z + dx2));
+    const double t_off = atan((x + dx1) / (z + dx2));
+    gen_bilinear(x11, x22, v11, v12, v21, v22, r_off, t_off, ans2);
+    double so, co;
+    sincos(t_off, &so, &co);
+    const double vx2 = (ans2[0] * w.UV * so + ans2[1] * w.UV * co);
+    const double vz2 = (ans2[0] * w.UV * co - ans2[1] * w.UV * so);
+    const double v1 = sa * vx1 + ca * vz1;
+    const double v2 = sa * vx2 + ca * vz2;
+    out = fabs((v2 - v1) / ds);
+  }
+  w.dvds[ia * d.sv + o] = out;
+}
+
+// LineForce(), line_connect.c:815-903 (KRAD / ALPHARAD power law, capped at M_max = 4400)
+PB_D void gen_line_force(const GenDev &g, double rho_code, double prs_code, long o, double (&grad)[3]) {
+  const LdwDev &w = g.ldw;
+  const double rho = rho_code * w.UD;
+  const double T = prs_code / rho_code * w.kelvin_mu;
+  const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
+  grad[0] = grad[1] = grad[2] = 0.0;
+  for (int ia = 0; ia < w.nangles; ia++) {
+    const double dv = w.dvds[ia * g.d.sv + o];
+    double M = 0.0;
+    if (dv > 0.0) {
+      const double t = w.sigma_e * rho * v_th / dv;
+      M = fmin(w.krad * pow(t, w.alpharad), 4400.0);
+    }
+    grad[0] += ((1.0 + M) * w.sigma_e * __ldg(w.flux_r + ia * g.d.sv + o) / 2.99792458e10) / w.unit_acc;
+    grad[1] += ((1.0 + M) * w.sigma_e * __ldg(w.flux_t + ia * g.d.sv + o) / 2.99792458e10) / w.unit_acc;
+  }
+}
+
+// UserDefBoundary(side == 0) of cv_idl (init.c:199-316): floors over the WHOLE array and the
+// mid-plane reset of the last active theta row; Uc of a floored zone is re-derived when the
+// call sits inside stage >= 2 (PrimToCons3D on a 1-zone box, init.c:272-275)
+template <int NV>
+static __global__ void gen_ldw_floor(GenDev g, GenArgs a, int update_U) {
+  const Dev &d = g.d;
+  const LdwDev &w = g.ldw;
+  long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= d.sv) return;
+  const int i = (int)(o % d.tot[0]), j = (int)((o / d.sj) % d.tot[1]);
+  double v[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) v[nv] = a.V[nv * d.sv + o];
+  bool convert = false;
+  if (v[iRHO] < w.dfloor) {
+    if (v[iRHO] < 0.0) v[iRHO] = w.dfloor;
+    const double cs = sqrt(d.gas.gamma * v[iPRS] / v[iRHO]);
+    const double dfact = v[iRHO] / w.dfloor;
+    v[iRHO] = w.dfloor;
+    v[1] = dfact * v[1]; v[2] = dfact * v[2]; v[3] = dfact * v[3];
+    v[iPRS] = (cs * cs) * v[iRHO] / d.gas.gamma;
+    double temp = v[iPRS] / v[iRHO] * w.kelvin_mu;
+    if (temp < w.tfloor) { temp = w.tfloor; v[iPRS] = v[iRHO] * temp / w.kelvin_mu; }
+    v[NFLX] = 0.0;
+    convert = true;
+  }
+  if (v[iPRS] < w.pfloor) { v[iPRS] = w.pfloor; convert = true; }
+  if (convert && update_U) {
+    const double rho = v[iRHO];
+    a.U[o] = rho;
+    a.U[1 * d.sv + o] = rho * v[1];
+    a.U[2 * d.sv + o] = rho * v[2];
+    a.U[3 * d.sv + o] = rho * v[3];
+    a.U[4 * d.sv + o] = 0.5 * rho * (v[1] * v[1] + v[2] * v[2] + v[3] * v[3]) + v[iPRS] / d.gas.gmm1;
+#pragma unroll
+    for (int nv = NFLX; nv < NV; nv++) a.U[nv * d.sv + o] = rho * v[nv];
+  }
+  if (j == d.end[1]) {
+    const double r = __ldg(w.xgc1 + i), theta = __ldg(w.xgc2 + j);
+    const double sth = sin(theta), rcyl = r * sth;
+    const double rho_mid = w.rho_0 * pow(r / w.r_WD, -1.0 * w.rho_alpha);
+    v[2] = (v[iRHO] * v[2]) / rho_mid;
+    v[iRHO] = rho_mid;
+    v[1] = 0.0;
+    v[3] = sqrt(w.gm_code / r) * sth;
+    const double temp = w.teff_wd * pow(w.r_WD / rcyl, 0.75) * pow(1.0 - sqrt(w.r_WD / rcyl), 0.25);
+    v[iPRS] = rho_mid * temp / w.kelvin_mu;
+    v[NFLX] = 1.0;
+    convert = true;
+  }
+  if (convert) {
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) a.V[nv * d.sv + o] = v[nv];
+  }
+}
+
+// UserDefBoundary(X1_BEG / X1_END / X2_BEG) of cv_idl (init.c:319-363)
+static __global__ void gen_ldw_side(GenDev g, double *V, int side) {
+  const Dev &d = g.d;
+  const int ng = d.beg[side / 2];
+  int ext[3] = {d.tot[0], d.tot[1], d.tot[2]};
+  ext[side / 2] = ng;
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)ext[0] * ext[1] * ext[2]) return;
+  int c0 = (int)(t % ext[0]), c1 = (int)((t / ext[0]) % ext[1]), c2 = (int)(t / ((long)ext[0] * ext[1]));
+  long o, os, ob = 0;
+  if (side == 0) { o = (long)c2 * d.sk + (long)c1 * d.sj + c0; os = (long)c2 * d.sk + (long)c1 * d.sj + d.beg[0]; }
+  else if (side == 1) { o = (long)c2 * d.sk + (long)c1 * d.sj + d.end[0] + 1 + c0; os = (long)c2 * d.sk + (long)c1 * d.sj + d.end[0]; }
+  else {
+    o = (long)c2 * d.sk + (long)c1 * d.sj + c0;
+    os = (long)c2 * d.sk + (long)(2 * d.beg[1] - c1 - 1) * d.sj + c0;
+    ob = (long)c2 * d.sk + (long)d.beg[1] * d.sj + c0;
+  }
+  for (int nv = 0; nv < g.nvar; nv++) V[nv * d.sv + o] = V[nv * d.sv + os];
+  if (side == 0) V[1 * d.sv + o] = fmin(V[1 * d.sv + o], 0.0);
+  else if (side == 1) V[1 * d.sv + o] = fmax(V[1 * d.sv + o], 0.0);
+  else {
+    V[2 * d.sv + o] *= -1.0;
+    V[o] = V[ob];
+    V[iPRS * d.sv + o] = V[iPRS * d.sv + ob];
+  }
+}
+
 // ---- RightHandSide + RightHandSideSource + U += rhs + C_dt -------------------------------
 template <int NV>
 static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
@@ -396,8 +586,8 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
         if (!(d.bf_kind & 1)) continue;
         gv[0] = bf_at(d, 0, i, j, k); gv[1] = bf_at(d, 1, i, j, k); gv[2] = bf_at(d, 2, i, j, k);
       } else {
-        if (!g.gline) continue;
-        gv[0] = __ldg(g.gline + o); gv[1] = __ldg(g.gline + nz + o); gv[2] = __ldg(g.gline + 2 * nz + o);
+        if (!g.ldw.on) continue;
+        gen_line_force(g, vg[iRHO], vg[iPRS], o, gv);
       }
       const double gd = dir == 0 ? gv[0] : (dir == 1 ? gv[1] : gv[2]);
       rn += dt * vg[iRHO] * gd;

@@ -97,6 +97,10 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->gdev = nullptr;
   c->gline = nullptr;
   c->ldw_hook = nullptr;
+  c->ldw_on = false;
+  c->cur_stage = 0;
+  for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
+  c->ldw_dvds = nullptr;
   Dev &D = c->dev;
   D.ndim = cfg->dimensions;
   for (int d = 0; d < 3; d++) {
@@ -174,6 +178,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
 extern "C" void pb200_destroy(pb200_ctx *c) {
   if (!c) return;
   pb200_gen_release(c);
+  for (int q = 0; q < 3; q++) if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
+  if (c->ldw_dvds) cudaFree(c->ldw_dvds);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
   if (c->acc) cudaFree(c->acc);
   if (c->cdt) cudaFree(c->cdt);
@@ -261,9 +267,21 @@ extern "C" int pb200_nstages(const pb200_ctx *c) { return c ? c->nstages : 0; }
 // ---- Boundary() ------------------------------------------------------------------------
 static int boundary_on(pb200_ctx *c, double *V) {
   const Dev &D = c->dev;
+  // INTERNAL_BOUNDARY YES: UserDefBoundary(d, NULL, 0, grid) comes first (boundary.c:126-128)
+  int rc0 = pb200_gen_internal_boundary(c, V);
+  if (rc0) return fail(rc0, "internal boundary (UserDefBoundary side 0) failed");
   for (int side = 0; side < 2 * D.ndim; side++) {
     int type = c->cfg.bc[side];
-    if (type == PB200_BC_NEIGHBOUR || type == PB200_BC_USERDEF || type == 0) continue;
+    if (type == PB200_BC_USERDEF) {
+      // device versions exist for the line-driven-wind problem only; other user code must fill
+      // its ghost zones itself between pb200_stage_boundary() and pb200_stage_begin()
+      if (c->ldw_on && c->ldw.userdef_bc) {
+        int rc = pb200_gen_userdef_side(c, V, side);
+        if (rc) return fail(rc, "no device UserDefBoundary for this side");
+      }
+      continue;
+    }
+    if (type == PB200_BC_NEIGHBOUR || type == 0) continue;
     BcArgs b;
     b.V = V;
     b.side = side;
@@ -280,6 +298,8 @@ static int boundary_on(pb200_ctx *c, double *V) {
     bc_fill<<<nb, 256, 0, c->stream>>>(D, b);
     c->launches++;
   }
+  int rce = pb200_gen_entropy(c, V);
+  if (rce) return fail(rce, "ComputeEntropy failed");
   CK(cudaGetLastError());
   return PB200_OK;
 }
@@ -378,7 +398,10 @@ extern "C" int pb200_stage_boundary(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
-  return boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
+  c->cur_stage = stage;
+  rc = boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
+  c->cur_stage = 0;
+  return rc;
 }
 
 extern "C" int pb200_stage_begin(pb200_ctx *c, int stage) {

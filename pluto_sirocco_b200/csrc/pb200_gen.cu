@@ -37,6 +37,8 @@ T *dalloc(pb200_ctx *c, size_t n) {
 
 }  // namespace
 
+static void fill_ldw(pb200_ctx *c, GenDev &G);
+
 void pb200_gen_release(pb200_ctx *c) {
   for (void *p : c->gen_allocs) cudaFree(p);
   c->gen_allocs.clear();
@@ -189,8 +191,139 @@ int pb200_gen_setup(pb200_ctx *c) {
   ok &= (c->gflag = dalloc<unsigned short>(c, nz)) != nullptr;
   ok &= (c->gshock = dalloc<unsigned char>(c, nz)) != nullptr;
   ok &= (c->gcdt = dalloc<double>(c, nz)) != nullptr;
+  // line-driven wind: libm sin/cos tables of the angular bins and of theta, centroids
+  {
+    std::vector<double> sa(64), ca(64), st(n2), ct(n2);
+    for (int a = 0; a < 64; a++) {
+      double theta_angle = (a + 0.5) * (2.0 * 3.14159265358979) / 36.0;     // line_connect.c:563
+      sa[a] = sin(theta_angle); ca[a] = cos(theta_angle);
+    }
+    for (int j = 0; j < n2; j++) { st[j] = sin(x2[j]); ct[j] = cos(x2[j]); }
+    ok &= (G.ldw.sin_a = upload(c, sa)) != nullptr;
+    ok &= (G.ldw.cos_a = upload(c, ca)) != nullptr;
+    ok &= (G.ldw.sin_t = upload(c, st)) != nullptr;
+    ok &= (G.ldw.cos_t = upload(c, ct)) != nullptr;
+    ok &= (G.ldw.xgc1 = upload(c, xgc[0])) != nullptr;
+    ok &= (G.ldw.xgc2 = upload(c, xgc[1])) != nullptr;
+  }
   if (!ok) { pb200_gen_release(c); return PB200_ENOMEM; }
   c->gen_ready = true;
+  return PB200_OK;
+}
+
+// constants of the line-driven-wind problem (cv_idl/init.c:175-197, line_connect.c:831-846)
+static void fill_ldw(pb200_ctx *c, GenDev &G) {
+  LdwDev &w = G.ldw;
+  w.on = c->ldw_on;
+  if (!c->ldw_on) return;
+  const pb200_ldw_config &L = c->ldw;
+  const double amu = 1.66053886e-24, kB = 1.3806505e-16, Gc = 6.6726e-8, sigma = 5.67051e-5, sigmaT = 6.6524e-25;
+  const double PI = 3.14159265358979;
+  w.userdef_bc = L.userdef_bc;
+  w.nangles = L.nangles;
+  w.flux_r = c->ldw_flux[0]; w.flux_t = c->ldw_flux[1]; w.flux_p = c->ldw_flux[2];
+  w.dvds = c->ldw_dvds;
+  w.UL = L.unit_length; w.UV = L.unit_velocity; w.UD = L.unit_density;
+  const double KELVIN = L.unit_velocity * L.unit_velocity * amu / kB;      // pluto.h:560
+  w.kelvin_mu = KELVIN * L.mu;
+  w.krad = L.krad; w.alpharad = L.alpharad;
+  w.sigma_e = sigmaT / amu / 1.18;
+  w.unit_acc = L.unit_velocity * L.unit_velocity / L.unit_length;
+  w.dfloor = L.dfloor / L.unit_density;
+  w.tfloor = 5.e2;
+  w.pfloor = w.dfloor * w.tfloor / (KELVIN * L.mu);
+  w.rho_0 = L.rho_0 / L.unit_density;
+  w.rho_alpha = L.rho_alpha;
+  w.r_WD = c->xl[0][c->dev.beg[0]];                 // g_domBeg[IDIR]
+  const double gm_cgs = Gc * L.cent_mass;
+  w.gm_code = gm_cgs / (L.unit_length * L.unit_velocity * L.unit_velocity);
+  double teff = pow(3.0 * gm_cgs * L.disk_mdot / (8.0 * PI * sigma), 0.25);
+  teff *= pow(w.r_WD * L.unit_length, -0.75);
+  w.teff_wd = teff;
+}
+
+template <int NV>
+static void gen_floor_nv(pb200_ctx *c, double *V) {
+  GenDev G = *c->gdev;
+  G.d = c->dev;
+  fill_ldw(c, G);
+  GenArgs a;
+  memset(&a, 0, sizeof(a));
+  a.V = V; a.U = c->gU;
+  const int T = 128;
+  gen_ldw_floor<NV><<<(unsigned)((c->dev.sv + T - 1) / T), T, 0, c->stream>>>(G, a, c->cur_stage > 1 ? 1 : 0);
+  c->launches++;
+}
+
+int pb200_gen_internal_boundary(pb200_ctx *c, double *V) {
+  if (!c->gen || !c->ldw_on || !c->ldw.userdef_bc) return PB200_OK;
+  int rc = pb200_gen_setup(c);
+  if (rc) return rc;
+  switch (c->nvar) {
+    case 6: gen_floor_nv<6>(c, V); break;
+    case 7: gen_floor_nv<7>(c, V); break;
+    case 8: gen_floor_nv<8>(c, V); break;
+    default: return PB200_ENOTSUP;    // the problem carries a tracer: NVAR >= 6
+  }
+  return PB200_OK;
+}
+
+// the last act of Boundary(): ComputeEntropy over the whole array (boundary.c:488-493)
+int pb200_gen_entropy(pb200_ctx *c, double *V) {
+  if (!c->gen || !c->cfg.entropy_switch) return PB200_OK;
+  int rc = pb200_gen_setup(c);
+  if (rc) return rc;
+  GenDev G = *c->gdev;
+  G.d = c->dev;
+  gen_entropy<<<(unsigned)((c->dev.sv + 127) / 128), 128, 0, c->stream>>>(G, V);
+  c->launches++;
+  return PB200_OK;
+}
+
+int pb200_gen_userdef_side(pb200_ctx *c, double *V, int side) {
+  if (!c->gen || !c->ldw_on || !c->ldw.userdef_bc) return PB200_ENOTSUP;
+  if (side > 2) return PB200_ENOTSUP;               // cv_idl defines X1_BEG, X1_END, X2_BEG only
+  int rc = pb200_gen_setup(c);
+  if (rc) return rc;
+  GenDev G = *c->gdev;
+  G.d = c->dev;
+  const Dev &D = c->dev;
+  int ext[3] = {D.tot[0], D.tot[1], D.tot[2]};
+  ext[side / 2] = D.beg[side / 2];
+  long n = (long)ext[0] * ext[1] * ext[2];
+  gen_ldw_side<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(G, V, side);
+  c->launches++;
+  return PB200_OK;
+}
+
+extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
+  if (!c || !l) return PB200_EINVAL;
+  if (!c->gen || c->cfg.geometry != PB200_SPHERICAL || c->dev.ndim != 2) return PB200_ENOTSUP;
+  if (l->nangles < 1 || l->nangles > 64) return PB200_EINVAL;
+  if (l->krad == 999 && l->alpharad == 999) return PB200_ENOTSUP;   // M_UV fit tables (line_connect.c:185-256)
+  cudaSetDevice(c->cfg.device);
+  c->ldw = *l;
+  c->ldw_on = true;
+  size_t n = (size_t)l->nangles * c->dev.sv;
+  for (int q = 0; q < 3; q++) {
+    if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
+    if (cudaMalloc(&c->ldw_flux[q], n * sizeof(double)) != cudaSuccess) return PB200_ENOMEM;
+    cudaMemset(c->ldw_flux[q], 0, n * sizeof(double));
+  }
+  if (c->ldw_dvds) cudaFree(c->ldw_dvds);
+  if (cudaMalloc(&c->ldw_dvds, n * sizeof(double)) != cudaSuccess) return PB200_ENOMEM;
+  cudaMemset(c->ldw_dvds, 0, n * sizeof(double));
+  return PB200_OK;
+}
+
+extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double *ft, const double *fp) {
+  if (!c || !c->ldw_on || !fr || !ft) return PB200_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  size_t n = (size_t)c->ldw.nangles * c->dev.sv * sizeof(double);
+  if (cudaMemcpy(c->ldw_flux[0], fr, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
+  if (cudaMemcpy(c->ldw_flux[1], ft, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
+  if (fp) { if (cudaMemcpy(c->ldw_flux[2], fp, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA; }
+  else cudaMemset(c->ldw_flux[2], 0, n);
   return PB200_OK;
 }
 
@@ -198,7 +331,7 @@ template <int NV>
 static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
   GenDev G = *c->gdev;
   G.d = c->dev;     // body-force tables may have been set after gen_setup
-  G.gline = c->gline;
+  fill_ldw(c, G);
   const Dev &D = c->dev;
   cudaStream_t st = c->stream;
   GenArgs a;
@@ -215,8 +348,6 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   const unsigned ball = (unsigned)((D.sv + T - 1) / T);
   GenBox dom;
   for (int d = 0; d < 3; d++) { dom.lo[d] = D.beg[d]; dom.hi[d] = D.end[d]; }
-  // Boundary() ended with ComputeEntropy (boundary.c:488-493)
-  if (G.entropy) { gen_entropy<<<ball, T, 0, st>>>(G, a.V); c->launches++; }
   if (stage == 1) {
     if (G.flatten || G.entropy) {   // FlagShock, rk_step.c:123-125 (flags were zeroed by main.c:258-261)
       if (G.flatten) {
@@ -231,8 +362,11 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
     c->launches++;
   }
-  if (c->ldw_hook) c->ldw_hook(c, stage);       // VGradCalc + LineForce once per stage (update_stage.c:116-118)
-  G.gline = c->gline;
+  if (c->ldw_on) {                              // VGradCalc, update_stage.c:138-140
+    dim3 grid(blocks(dom), c->ldw.nangles);
+    gen_vgrad<<<grid, T, 0, st>>>(G, a, dom);
+    c->launches++;
+  }
   for (int dir = 0; dir < D.ndim; dir++) {
     a.dir = dir;
     GenBox bs = dom, bf = dom;

@@ -46,13 +46,21 @@ struct pb200_ctx {
   unsigned short *gflag;
   unsigned char *gshock;
   std::vector<void *> gen_allocs;
-  double *gline;                          // LineForce() per zone [3][k][j][i] (line-driven wind)
+  double *gline;
   void (*ldw_hook)(pb200_ctx *, int stage);
+  // line-driven wind
+  bool ldw_on;
+  pb200_ldw_config ldw;
+  double *ldw_flux[3], *ldw_dvds;
+  int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
 };
 
 int  pb200_gen_setup(pb200_ctx *c);
 void pb200_gen_release(pb200_ctx *c);
 int  pb200_gen_stage(pb200_ctx *c, int stage);
+int  pb200_gen_internal_boundary(pb200_ctx *c, double *V);   // UserDefBoundary(side == 0)
+int  pb200_gen_userdef_side(pb200_ctx *c, double *V, int side);
+int  pb200_gen_entropy(pb200_ctx *c, double *V);               // ComputeEntropy at the end of Boundary()
 
 
 // One launcher per (NVAR, body force) pair, each compiled in its own translation unit

@@ -293,6 +293,26 @@ class Hydro:
         L.check(self._lib.pb200_set_body_force_potential(self._h, int(where), a.ctypes.data_as(C.c_void_p),
                                                          a.size, si, sj, sk))
 
+    # -- line-driven wind ----------------------------------------------------------------------
+    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p=None, userdef_bc=True):
+        """LINE_DRIVEN_WIND SIROCCO_MODE: g_inputParam[] of the cv_idl problem (dict by label), UNIT_*
+        (dict), directional fluxes [nangles][k][j][i] incl. ghosts (read_sirocco_fluxes())."""
+        lc = L.LdwConfig()
+        fr = np.ascontiguousarray(flux_r, dtype=np.float64)
+        ft = np.ascontiguousarray(flux_t, dtype=np.float64)
+        assert fr.shape[1:] == self.shape[1:] and ft.shape == fr.shape
+        lc.nangles = fr.shape[0]
+        lc.userdef_bc = int(userdef_bc)
+        lc.unit_length, lc.unit_velocity, lc.unit_density = units["length"], units["velocity"], units["density"]
+        lc.mu, lc.krad, lc.alpharad = params["MU"], params["KRAD"], params["ALPHARAD"]
+        lc.dfloor, lc.rho_0, lc.rho_alpha = params["DFLOOR"], params["RHO_0"], params["RHO_ALPHA"]
+        lc.cent_mass, lc.disk_mdot = params["CENT_MASS"], params["DISK_MDOT"]
+        lc.lx, lc.tx = params["L_star"] * params["f_x"], params["T_x"]
+        L.check(self._lib.pb200_ldw_enable(self._h, C.byref(lc)))
+        fp = None if flux_p is None else np.ascontiguousarray(flux_p, dtype=np.float64)
+        L.check(self._lib.pb200_ldw_set_fluxes(self._h, fr.ctypes.data_as(C.c_void_p), ft.ctypes.data_as(C.c_void_p),
+                                               None if fp is None else fp.ctypes.data_as(C.c_void_p)))
+
     # -- data movement -----------------------------------------------------------------------
     def upload(self, vc: np.ndarray):
         vc = np.ascontiguousarray(vc, dtype=np.float64)
