@@ -377,8 +377,130 @@ def run_b200(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------
+#  secondary workload (BASELINE.json configs[3]): line-driven disc wind, spherical r-theta
+# --------------------------------------------------------------------------------------
+ALG_BYTES_LDW = 224.0 + 280.0 + 2 * 576.0   # NVAR 7 stages + 36 x (F_r, F_theta) x 8 B per stage
+
+
+def ldw_state(x1, x2, P, U):
+    """Initial condition of Test_Problems/LineDrivenWind/cv_idl/init.c:27-102 (synthetic input of
+    that shape): hydrostatic PSD98 disc atmosphere, Keplerian rotation, density floor, tracer."""
+    import numpy as np
+    G, Rgas, sigma, amu, kB = 6.6726e-8, 8.3144598e7, 5.67051e-5, 1.66053886e-24, 1.3806505e-16
+    KELVIN = U["velocity"] ** 2 * amu / kB
+    r_WD = x1.min()
+    X1, X2 = np.meshgrid(x1, x2, indexing="xy")          # [j][i]
+    gm = G * P["CENT_MASS"]
+    r = X1 * U["length"]
+    teff = (3.0 * gm * P["DISK_MDOT"] / (8.0 * np.pi * sigma)) ** 0.25 * (r_WD * U["length"]) ** -0.75
+    temp = teff * (r_WD / X1) ** 0.75
+    cs2 = Rgas * temp / 0.6
+    with np.errstate(divide="ignore", over="ignore", under="ignore"):
+        rho_d = P["RHO_0"] * np.exp(-gm / (2.0 * cs2 * r * np.tan(X2) ** 2)) / U["density"]
+    rho_a = P["DFLOOR"] / U["density"]
+    disc = rho_d > rho_a
+    v = np.zeros((7, 1) + X1.shape)
+    v[0, 0] = np.where(disc, rho_d, rho_a)
+    v[3, 0] = np.sqrt(gm / r) * np.sin(X2) / U["velocity"]
+    v[4, 0] = v[0, 0] * temp / (KELVIN * P["MU"])
+    v[5, 0] = disc.astype(float)
+    v[6, 0] = 1.0
+    return v
+
+
+def run_ldw(args):
+    """C4: 1024 x 512 spherical r-theta grid, NVAR 7 (tracer + entropy), char-limited PLM (van Leer),
+    MULTID flattening, entropy switch, BODY_FORCE VECTOR, VGradCalc + LineForce with 36-angle
+    synthetic sirocco tables, cv_idl user boundaries; HLL, RK2 (pluto_sirocco_sub.py:46-118)."""
+    import numpy as np
+    import torch
+    from pluto_sirocco_b200 import Hydro, make_grid
+    sys.path.insert(0, str(ROOT / "tests"))
+    from common import LDW_BCS, LDW_PARAMS, LDW_UNITS, ldw_flux_tables
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    n1, n2 = args.ldw_size
+    grid = [(0.87, n1, 8.7, "r", args.ldw_ratio[0]), (0.0, n2, float(np.radians(90.0)), "r", args.ldw_ratio[1]), (0.0, 1, 1.0)]
+    arrays = [make_grid(grid[0], 3), make_grid(grid[1], 3), make_grid(grid[2], 0)]
+    h = Hydro(dimensions=2, nx=(n1, n2, 1), xbeg=(0.87, 0.0, 0.0), xend=(8.7, float(np.radians(90.0)), 1.0),
+              gamma=5. / 3., solver="hll", limiter="VANLEER_LIM", bcs=LDW_BCS, ntracer=1, body_force=1,
+              geometry="SPHERICAL", grid_arrays=arrays, char_limiting=True, shock_flattening=True,
+              entropy_switch=True, nghost=3)
+    x1, x2 = h.x(0), h.x(1)
+    gm_code = 6.6726e-8 * LDW_PARAMS["CENT_MASS"] / (LDW_UNITS["length"] * LDW_UNITS["velocity"] ** 2)
+    h.set_body_force_vector(0, (-gm_code / (x1 * x1)).reshape(1, 1, -1))
+    h.set_body_force_vector(1, np.zeros((1, 1, 1)))
+    h.set_body_force_vector(2, np.zeros((1, 1, 1)))
+    fr, ft, fp = ldw_flux_tables(x1, x2, roundtrip=False)
+    h.set_ldw(params=LDW_PARAMS, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)
+    v = ldw_state(x1[3:-3], x2[3:-3], LDW_PARAMS, LDW_UNITS)
+    h.set_interior(v)
+    zones = n1 * n2
+    cfl, cmv, first_dt = 0.4, 1.1, 1e-4
+    g = {"dt": first_dt}
+
+    def one_step():
+        info = h.advance_step(g["dt"])
+        g["dt"] = h.next_time_step(info.invDt_hyp, cfl, cmv, g["dt"], first_dt)
+        return info
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(h.stream_ptr())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        launches += one_step().launches
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    value = zones * args.steps / (ms * 1e-3) / 1e6
+    # e2e: host d->Vc in and out every step
+    vc = h.download()
+    pin = torch.empty(h.shape, dtype=torch.float64, pin_memory=True)
+    pin.numpy()[:] = vc
+    t0 = time.perf_counter()
+    ne = max(2, min(args.steps, 20))
+    dt_e = g["dt"]
+    for _ in range(ne):
+        info = h.advance_step_host(pin.numpy(), dt_e)
+        dt_e = h.next_time_step(info.invDt_hyp, cfl, cmv, dt_e, first_dt)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    nbytes = int(np.prod(h.shape)) * 8
+    e2e = {"value": zones * ne / wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+           "steps": ne, "api": "pb200_advance_step_host"}
+    peak, peak_src = measured_peaks()
+    step_ms = ms / args.steps
+    achieved = ALG_BYTES_LDW * zones / (step_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "line-driven-wind spherical r-theta %dx%d PLM(char,VL)+HLL+RK2, 36-angle line force" % (n1, n2),
+                       "grid_ratio": list(args.ldw_ratio), "zones_per_gpu": zones, "nvar": 7,
+                       "l2": "state + work arrays (%.0f MB) and the 36-angle tables (%.0f MB) exceed L2 together" % (
+                           zones * 8 * 7 * 7 / 1e6, zones * 8 * 36 * 4 / 1e6), "cfl": cfl},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole step (multi-kernel general path)",
+                         "algorithmic_bytes_per_zone_update": ALG_BYTES_LDW},
+            "cpu_baseline": None}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sedov", choices=["sedov", "ldw"],
+                    help="sedov: BASELINE configs[1] (the metric's config); ldw: configs[3]")
+    ap.add_argument("--ldw-size", type=int, nargs=2, default=[1024, 512])
+    ap.add_argument("--ldw-ratio", type=float, nargs=2, default=[1.005, 0.995])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -398,6 +520,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "ldw":
+        return run_ldw(args)
     return run_b200(args)
 
 

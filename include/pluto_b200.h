@@ -167,6 +167,18 @@ typedef struct pb200_ldw_config {
 int  pb200_ldw_enable(pb200_ctx *ctx, const pb200_ldw_config *ldw);
 int  pb200_ldw_set_fluxes(pb200_ctx *ctx, const double *flux_r, const double *flux_t, const double *flux_p);
 
+/* COOLING BLONDIN.  pb200_split_source() is SplitSource(d, dt, Dts, grid) (Src/split_source.c:29,
+ * called from Integrate, Src/main.c:479-485) for the BLONDIN module: BlondinCooling(d->Vc, d, dt)
+ * (Src/Cooling/BLONDIN/cooling.c:50-170) on the device-resident d->Vc; g_time selects the analytic
+ * ionisation parameter (g_time <= 3) or the sirocco tables.  pb200_cooling_set_tables() uploads the
+ * per-zone tables of Data (Src/structs.h:621-643), each [NX3_TOT][NX2_TOT][NX1_TOT]:
+ *   tabs[0..4] = comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre   (NULL: 1.0, the
+ *                defaults of read_sirocco_heatcool(), Src/LineDriven/line_connect.c:383-393)
+ *   tabs[5..6] = sirocco_xi, sirocco_t_r   (NULL: analytic xi, T_x)
+ * Needs pb200_ldw_enable() (units and L_x, T_x come from there). */
+int  pb200_cooling_set_tables(pb200_ctx *ctx, const double *const tabs[7]);
+int  pb200_split_source(pb200_ctx *ctx, double dt, double g_time);
+
 /* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
 int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);
 int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);

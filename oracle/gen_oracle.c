@@ -1028,3 +1028,110 @@ static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, c
     grad[1] += ((1.0 + M_UV) * sigma_e * flux_t / CONST_c) / UNIT_ACC;
   }
 }
+
+/* ---------------------------------------------------------------------------------------
+ *  COOLING BLONDIN: BlondinCooling(), heatcool(), ne_rat(), zfunc(), zbrent()
+ *  Src/Cooling/BLONDIN/cooling.c:50-330 (SplitSource, Src/split_source.c:53)
+ * --------------------------------------------------------------------------------------- */
+typedef struct {
+  double comp_c_pre, comp_h_pre, line_c_pre, brem_c_pre, xray_h_pre;
+  double nH, ne, xi, tx, sqxi, sqsqxi, n, E, hc_init, dt_share;
+} cool_t;
+
+static double ne_rat(double T) {
+  if (T < 1.5e4) return 1e-2 + pow(10, (-51.59417133 + 12.27740153 * log10(T)));
+  else if (T >= 1.5e4 && T < 3.3e4) return pow(10, (-3.80749689 + 0.86092628 * log10(T)));
+  return 1.21;
+}
+static double heatcool(cool_t *q, double T) {
+  double sqT = sqrt(T);
+  q->ne = q->nH * ne_rat(T);
+  double comp_heat = q->comp_h_pre * (8.9e-36 * q->xi * q->tx);
+  double comp_cool = q->comp_c_pre * (8.9e-36 * q->xi * (4.0 * T));
+  double xray_heat = q->xray_h_pre * (1.5e-21 * (q->sqsqxi / sqT));
+  double line_cool = q->line_c_pre * ((1e-16 * exp(-1.3e5 / T) / q->sqxi / T) + fmin(fmin(1e-24, 5e-27 * sqT), 1.5e-17 / T));
+  double brem_cool = q->brem_c_pre * (3.3e-27 * sqT);
+  return q->nH * (q->ne * comp_heat + q->nH * xray_heat - q->ne * comp_cool - q->ne * line_cool - q->ne * brem_cool);
+}
+static double zfunc(cool_t *q, double temp) {
+  return (temp * q->n * CONST_kB / (2.0 / 3.0)) - q->E - q->dt_share * (q->hc_init + heatcool(q, temp)) / 2.0;
+}
+static double zbrent(cool_t *z, int which, double x1, double x2, double tol) {
+#define FUNC(x) (which ? zfunc(z, (x)) : heatcool(z, (x)))
+  const double EPS = 3.0e-8;
+  double a = x1, b = x2, c = x2, d = 0.0, e = 0.0;
+  double fa = FUNC(a), fb = FUNC(b), fc = fb, p, q, r, s, tol1, xm;
+  if (fb * fa > 0.0) return b;
+  for (int iter = 1; iter <= 100; iter++) {
+    if (fb * fc > 0.0) { c = a; fc = fa; e = d = b - a; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol;
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      s = fb / fa;
+      if (a == c) { p = 2.0 * xm * s; q = 1.0 - s; }
+      else {
+        q = fa / fc; r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      double min1 = 3.0 * xm * q - fabs(tol1 * q), min2 = fabs(e * q);
+      if (2.0 * p < (min1 < min2 ? min1 : min2)) { e = d; d = p / q; }
+      else { d = xm; e = d; }
+    } else { d = xm; e = d; }
+    a = b; fa = fb;
+    if (fabs(d) > tol1) b += d;
+    else b += (xm > 0.0 ? fabs(tol1) : -fabs(tol1));
+    fb = FUNC(b);
+  }
+  return b;
+#undef FUNC
+}
+
+/* tabs: comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r  [k][j][i] */
+void gen_blondin_cooling(void *p, double *Vc, double dt, double g_time, const double *const tabs[7]) {
+  gen_ctx *x = p;
+  const gen_cfg *c = &x->c;
+  const geom_t *g = x->g;
+  double UNIT_TIME = c->unit_length / c->unit_velocity;
+  double UNIT_PRESSURE = c->unit_density * c->unit_velocity * c->unit_velocity;
+  double KELVIN = kelvin(c), mu = c->mu, lx = c->lx;
+  double minT = 1.e4;
+  cool_t q;
+  q.dt_share = dt * UNIT_TIME;
+  for (int k = g->beg[2]; k <= g->end[2]; k++) for (int j = g->beg[1]; j <= g->end[1]; j++)
+    for (int i = g->beg[0]; i <= g->end[0]; i++) {
+      long o = k * g->sk + j * g->sj + i;
+      q.comp_h_pre = tabs[0][o]; q.comp_c_pre = tabs[1][o]; q.xray_h_pre = tabs[2][o];
+      q.line_c_pre = tabs[3][o]; q.brem_c_pre = tabs[4][o];
+      double r = g->x[0][i] * c->unit_length;
+      double rho = Vc[RHO * g->sv + o] * c->unit_density;
+      double pr = Vc[PRS * g->sv + o];
+      double T = pr / Vc[RHO * g->sv + o] * KELVIN * mu;
+      q.E = (pr * UNIT_PRESSURE) / (c->gamma - 1);
+      q.nH = rho / (1.43 * CONST_mp);
+      if (g_time <= 3.0) { q.xi = lx / q.nH / r / r; q.tx = c->tx; }
+      else { q.xi = tabs[5][o]; q.tx = tabs[6][o]; }
+      q.n = rho / (mu * CONST_mp);
+      T = q.E * (2.0 / 3.0) / (q.n * CONST_kB);
+      if (T < minT) continue;
+      q.sqxi = sqrt(q.xi);
+      q.sqsqxi = pow(q.xi, 0.25);
+      q.hc_init = heatcool(&q, T);
+      double t_l = T * 0.9, t_u = T * 1.1, T_f;
+      double test = zfunc(&q, t_l) * zfunc(&q, t_u);
+      while (test > 0 && test == test) { t_l *= 0.9; t_u *= 1.1; test = zfunc(&q, t_l) * zfunc(&q, t_u); }
+      if (test != test) T_f = T;
+      else {
+        T_f = zbrent(&q, 1, t_l, t_u, 1.0);
+        double hc_final = heatcool(&q, T_f);
+        if (hc_final * q.hc_init < 0.0) T_f = zbrent(&q, 0, fmin(T_f, T), fmax(T_f, T), 1.0);
+      }
+      T_f = MAXV(T_f, minT);
+      double E_f = T_f / (2.0 / 3.0) * (q.n * CONST_kB);
+      Vc[PRS * g->sv + o] = E_f * (c->gamma - 1) / UNIT_PRESSURE;
+    }
+}

@@ -42,6 +42,8 @@ def lib():
         L.gen_nvar.argtypes = [C.c_void_p]
         L.gen_boundary.argtypes = [C.c_void_p, C.c_void_p]
         L.gen_get_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.gen_blondin_cooling.restype = None
+        L.gen_blondin_cooling.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.gen_advance_step.restype = C.c_int
         L.gen_advance_step.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]
@@ -162,5 +164,12 @@ class GenOracle:
         inv, mach = C.c_double(0.0), C.c_double(0.0)
         nf = lib().gen_advance_step(self._handle(), vc.ctypes.data, float(dt), C.byref(inv), C.byref(mach))
         return inv.value, mach.value, nf
+
+    def blondin_cooling(self, vc, dt, g_time, tabs):
+        """SplitSource() -> BlondinCooling(d->Vc, d, dt): tabs = [comp_h_pre, comp_c_pre, xray_h_pre,
+        line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r], each [k][j][i] incl. ghosts."""
+        arrs = [np.ascontiguousarray(np.broadcast_to(t, self.shape[1:]), dtype=np.float64) for t in tabs]
+        ptrs = (C.c_void_p * 7)(*[a.ctypes.data for a in arrs])
+        lib().gen_blondin_cooling(self._handle(), vc.ctypes.data, float(dt), float(g_time), ptrs)
 
     next_time_step = staticmethod(_o.Oracle.next_time_step)

@@ -59,6 +59,8 @@ SYMBOLS = {
     "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pb200_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
+    "pb200_cooling_set_tables": (C.c_int, [_P, C.POINTER(C.c_void_p * 7)]),
+    "pb200_split_source": (C.c_int, [_P, _D, _D]),
     "pb200_ldw_enable": (C.c_int, [_P, C.POINTER(LdwConfig)]),
     "pb200_ldw_set_fluxes": (C.c_int, [_P, _P, _P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),

@@ -30,7 +30,7 @@ enum { GEO_CARTESIAN = 1, GEO_SPHERICAL = 4 };
 struct LdwDev {
   int on, userdef_bc, nangles;
   const double *flux_r, *flux_t, *flux_p;   // [nangles][k][j][i]
-  double *dvds;                             // dvds_array [nangles][k][j][i]
+  double *dvds;                             // dvds_array^(-alpha) [nangles][k][j][i] (0 where dvds <= 0)
   const double *sin_a, *cos_a;              // sin/cos((a + 1/2) 2 pi / 36), libm values from the host
   const double *sin_t, *cos_t;              // sin/cos(x2[j])
   const double *xgc1, *xgc2;                // grid->xgc (mid-plane reset uses the centroids)
@@ -408,7 +408,10 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
     const double v2 = sa * vx2 + ca * vz2;
     out = fabs((v2 - v1) / ds);
   }
-  w.dvds[ia * d.sv + o] = out;
+  // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per angle and SWEEP (the sweeps pass
+  // different centre states); the angle-dependent factor dvds^(-alpha) is taken here, once per
+  // stage, so that the sweeps are left with one pow() per zone instead of 36
+  w.dvds[ia * d.sv + o] = out > 0.0 ? pow(out, -w.alpharad) : 0.0;
 }
 
 // LineForce(), line_connect.c:815-903 (KRAD / ALPHARAD power law, capped at M_max = 4400)
@@ -418,13 +421,10 @@ PB_D void gen_line_force(const GenDev &g, double rho_code, double prs_code, long
   const double T = prs_code / rho_code * w.kelvin_mu;
   const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
   grad[0] = grad[1] = grad[2] = 0.0;
+  const double kS = w.krad * pow(w.sigma_e * rho * v_th, w.alpharad);
   for (int ia = 0; ia < w.nangles; ia++) {
-    const double dv = w.dvds[ia * g.d.sv + o];
-    double M = 0.0;
-    if (dv > 0.0) {
-      const double t = w.sigma_e * rho * v_th / dv;
-      M = fmin(w.krad * pow(t, w.alpharad), 4400.0);
-    }
+    const double D = __ldg(w.dvds + ia * g.d.sv + o);     // dvds^(-alpha), 0 where dvds <= 0
+    const double M = fmin(kS * D, 4400.0);
     grad[0] += ((1.0 + M) * w.sigma_e * __ldg(w.flux_r + ia * g.d.sv + o) / 2.99792458e10) / w.unit_acc;
     grad[1] += ((1.0 + M) * w.sigma_e * __ldg(w.flux_t + ia * g.d.sv + o) / 2.99792458e10) / w.unit_acc;
   }
@@ -511,6 +511,113 @@ static __global__ void gen_ldw_side(GenDev g, double *V, int side) {
     V[o] = V[ob];
     V[iPRS * d.sv + o] = V[iPRS * d.sv + ob];
   }
+}
+
+// ---- COOLING BLONDIN: BlondinCooling(), Src/Cooling/BLONDIN/cooling.c:50-330 ---------------
+struct CoolDev {
+  const double *tab[7];   // comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r (null: 1 / unused)
+  double dt_share;        // dt * UNIT_TIME
+  double unit_pressure, lx, tx, mu;
+  int analytic_xi;        // g_time <= 3.0 (cooling.c:99-106)
+};
+struct CoolZone {
+  double comp_c_pre, comp_h_pre, line_c_pre, brem_c_pre, xray_h_pre;
+  double nH, xi, tx, sqxi, sqsqxi, n, E, hc_init, dt_share;
+};
+PB_D double cool_ne_rat(double T) {
+  if (T < 1.5e4) return 1e-2 + pow(10.0, (-51.59417133 + 12.27740153 * log10(T)));
+  else if (T < 3.3e4) return pow(10.0, (-3.80749689 + 0.86092628 * log10(T)));
+  return 1.21;
+}
+PB_D double cool_heatcool(const CoolZone &q, double T) {
+  const double sqT = sqrt(T);
+  const double ne = q.nH * cool_ne_rat(T);
+  const double comp_heat = q.comp_h_pre * (8.9e-36 * q.xi * q.tx);
+  const double comp_cool = q.comp_c_pre * (8.9e-36 * q.xi * (4.0 * T));
+  const double xray_heat = q.xray_h_pre * (1.5e-21 * (q.sqsqxi / sqT));
+  const double line_cool = q.line_c_pre * ((1e-16 * exp(-1.3e5 / T) / q.sqxi / T) + fmin(fmin(1e-24, 5e-27 * sqT), 1.5e-17 / T));
+  const double brem_cool = q.brem_c_pre * (3.3e-27 * sqT);
+  return q.nH * (ne * comp_heat + q.nH * xray_heat - ne * comp_cool - ne * line_cool - ne * brem_cool);
+}
+PB_D double cool_zfunc(const CoolZone &q, double temp) {
+  return (temp * q.n * 1.3806505e-16 / (2.0 / 3.0)) - q.E - q.dt_share * (q.hc_init + cool_heatcool(q, temp)) / 2.0;
+}
+template <bool ZF>
+__device__ double cool_zbrent(const CoolZone &z, double x1, double x2, double tol) {
+  auto F = [&](double x) { return ZF ? cool_zfunc(z, x) : cool_heatcool(z, x); };
+  const double EPS = 3.0e-8;
+  double a = x1, b = x2, c = x2, d = 0.0, e = 0.0;
+  double fa = F(a), fb = F(b), fc = fb, p, q, r, s, tol1, xm;
+  if (fb * fa > 0.0) return b;
+  for (int iter = 1; iter <= 100; iter++) {
+    if (fb * fc > 0.0) { c = a; fc = fa; e = d = b - a; }
+    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+    tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol;
+    xm = 0.5 * (c - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      s = fb / fa;
+      if (a == c) { p = 2.0 * xm * s; q = 1.0 - s; }
+      else {
+        q = fa / fc; r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      const double min1 = 3.0 * xm * q - fabs(tol1 * q), min2 = fabs(e * q);
+      if (2.0 * p < (min1 < min2 ? min1 : min2)) { e = d; d = p / q; }
+      else { d = xm; e = d; }
+    } else { d = xm; e = d; }
+    a = b; fa = fb;
+    if (fabs(d) > tol1) b += d;
+    else b += (xm > 0.0 ? fabs(tol1) : -fabs(tol1));
+    fb = F(b);
+  }
+  return b;
+}
+
+static __global__ void gen_blondin(GenDev g, double *V, CoolDev cd, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  CoolZone q;
+  q.dt_share = cd.dt_share;
+  q.comp_h_pre = cd.tab[0] ? cd.tab[0][o] : 1.0;     // defaults of read_sirocco_heatcool(), line_connect.c:383-393
+  q.comp_c_pre = cd.tab[1] ? cd.tab[1][o] : 1.0;
+  q.xray_h_pre = cd.tab[2] ? cd.tab[2][o] : 1.0;
+  q.line_c_pre = cd.tab[3] ? cd.tab[3][o] : 1.0;
+  q.brem_c_pre = cd.tab[4] ? cd.tab[4][o] : 1.0;
+  const double r = __ldg(g.x[0] + i) * g.ldw.UL;
+  const double rho_code = V[o], pr = V[iPRS * d.sv + o];
+  const double rho = rho_code * g.ldw.UD;
+  q.E = (pr * cd.unit_pressure) / (d.gas.gamma - 1);
+  q.nH = rho / (1.43 * 1.67262171e-24);
+  if (cd.analytic_xi || !cd.tab[5] || !cd.tab[6]) { q.xi = cd.lx / q.nH / r / r; q.tx = cd.tx; }
+  else { q.xi = cd.tab[5][o]; q.tx = cd.tab[6][o]; }
+  q.n = rho / (cd.mu * 1.67262171e-24);
+  const double T = q.E * (2.0 / 3.0) / (q.n * 1.3806505e-16);
+  if (T < 1.e4) return;                               // g_minCoolingTemp
+  q.sqxi = sqrt(q.xi);
+  q.sqsqxi = pow(q.xi, 0.25);
+  q.hc_init = cool_heatcool(q, T);
+  double t_l = T * 0.9, t_u = T * 1.1, T_f;
+  double test = cool_zfunc(q, t_l) * cool_zfunc(q, t_u);
+  int guard = 0;
+  while (test > 0 && test == test && guard++ < 4000) {
+    t_l *= 0.9; t_u *= 1.1;
+    test = cool_zfunc(q, t_l) * cool_zfunc(q, t_u);
+  }
+  if (test != test) T_f = T;
+  else {
+    T_f = cool_zbrent<true>(q, t_l, t_u, 1.0);
+    const double hc_final = cool_heatcool(q, T_f);
+    if (hc_final * q.hc_init < 0.0) T_f = cool_zbrent<false>(q, fmin(T_f, T), fmax(T_f, T), 1.0);
+  }
+  T_f = fmax(T_f, 1.e4);
+  const double E_f = T_f / (2.0 / 3.0) * (q.n * 1.3806505e-16);
+  V[iPRS * d.sv + o] = E_f * (d.gas.gamma - 1) / cd.unit_pressure;
 }
 
 // ---- RightHandSide + RightHandSideSource + U += rhs + C_dt -------------------------------

@@ -101,6 +101,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->cur_stage = 0;
   for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
   c->ldw_dvds = nullptr;
+  for (int q = 0; q < 7; q++) c->cool_tab[q] = nullptr;
   Dev &D = c->dev;
   D.ndim = cfg->dimensions;
   for (int d = 0; d < 3; d++) {
@@ -180,6 +181,7 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   pb200_gen_release(c);
   for (int q = 0; q < 3; q++) if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
+  for (int q = 0; q < 7; q++) if (c->cool_tab[q]) cudaFree(c->cool_tab[q]);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
   if (c->acc) cudaFree(c->acc);
   if (c->cdt) cudaFree(c->cdt);

@@ -327,6 +327,43 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
   return PB200_OK;
 }
 
+// SplitSource() for COOLING BLONDIN (Src/split_source.c:53): BlondinCooling(d->Vc, d, dt, ...)
+extern "C" int pb200_cooling_set_tables(pb200_ctx *c, const double *const tabs[7]) {
+  if (!c || !c->ldw_on) return PB200_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  size_t n = (size_t)c->dev.sv * sizeof(double);
+  for (int q = 0; q < 7; q++) {
+    if (c->cool_tab[q]) { cudaFree(c->cool_tab[q]); c->cool_tab[q] = nullptr; }
+    if (!tabs || !tabs[q]) continue;
+    if (cudaMalloc(&c->cool_tab[q], n) != cudaSuccess) return PB200_ENOMEM;
+    if (cudaMemcpy(c->cool_tab[q], tabs[q], n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
+  }
+  return PB200_OK;
+}
+
+extern "C" int pb200_split_source(pb200_ctx *c, double dt, double g_time) {
+  if (!c || !c->gen || !c->ldw_on) return PB200_ENOTSUP;
+  cudaSetDevice(c->cfg.device);
+  int rc = pb200_gen_setup(c);
+  if (rc) return rc;
+  GenDev G = *c->gdev;
+  G.d = c->dev;
+  fill_ldw(c, G);
+  const pb200_ldw_config &L = c->ldw;
+  CoolDev cd;
+  for (int q = 0; q < 7; q++) cd.tab[q] = c->cool_tab[q];
+  cd.dt_share = dt * (L.unit_length / L.unit_velocity);                     // dt * UNIT_TIME
+  cd.unit_pressure = L.unit_density * L.unit_velocity * L.unit_velocity;    // UNIT_PRESSURE
+  cd.lx = L.lx; cd.tx = L.tx; cd.mu = L.mu;
+  cd.analytic_xi = g_time <= 3.0;
+  GenBox dom;
+  for (int d = 0; d < 3; d++) { dom.lo[d] = c->dev.beg[d]; dom.hi[d] = c->dev.end[d]; }
+  long n = (long)(dom.hi[0] - dom.lo[0] + 1) * (dom.hi[1] - dom.lo[1] + 1) * (dom.hi[2] - dom.lo[2] + 1);
+  gen_blondin<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(G, c->V[c->cur], cd, dom);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return PB200_ECUDA;
+  return PB200_OK;
+}
+
 template <int NV>
 static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
   GenDev G = *c->gdev;

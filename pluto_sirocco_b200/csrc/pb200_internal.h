@@ -52,6 +52,7 @@ struct pb200_ctx {
   bool ldw_on;
   pb200_ldw_config ldw;
   double *ldw_flux[3], *ldw_dvds;
+  double *cool_tab[7];                    // BLONDIN tables (null: defaults)
   int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
 };
 

@@ -106,6 +106,42 @@ static void shim_body_force(Data *d, Grid *grid)
 }
 #endif
 
+#if LINE_DRIVEN_WIND != NO
+/* LINE_DRIVEN_WIND SIROCCO_MODE: parameters of the cv_idl problem and the flux tables that
+ * read_sirocco_fluxes() left in the globals flux_{r,t,p}_UV[NFLUX_ANGLES][k][j][i]
+ * (Src/globals.h:193-200, Src/main.c:157-200).  ARRAY_4D payloads are contiguous.           */
+static void shim_line_driven_wind(void)
+{
+  pb200_ldw_config l;
+  memset(&l, 0, sizeof(l));
+  l.nangles       = NFLUX_ANGLES;
+  l.userdef_bc    = 1;       /* the UserDefBoundary() of Test_Problems/LineDrivenWind/cv_idl */
+  l.unit_length   = UNIT_LENGTH;
+  l.unit_velocity = UNIT_VELOCITY;
+  l.unit_density  = UNIT_DENSITY;
+  l.mu        = g_inputParam[MU];
+  l.krad      = g_inputParam[KRAD];
+  l.alpharad  = g_inputParam[ALPHARAD];
+  l.dfloor    = g_inputParam[DFLOOR];
+  l.rho_0     = g_inputParam[RHO_0];
+  l.rho_alpha = g_inputParam[RHO_ALPHA];
+  l.cent_mass = g_inputParam[CENT_MASS];
+  l.disk_mdot = g_inputParam[DISK_MDOT];
+  l.lx        = g_inputParam[L_star]*g_inputParam[f_x];
+  l.tx        = g_inputParam[T_x];
+  if (flux_r_UV == NULL || flux_t_UV == NULL) {
+    print ("! AdvanceStep(): no sirocco flux tables (directional_flux_*.dat) were read\n");
+    QUIT_PLUTO(1);
+  }
+  if (pb200_ldw_enable(s_ctx, &l) != PB200_OK ||
+      pb200_ldw_set_fluxes(s_ctx, flux_r_UV[0][0][0], flux_t_UV[0][0][0],
+                           flux_p_UV != NULL ? flux_p_UV[0][0][0] : NULL) != PB200_OK) {
+    print ("! AdvanceStep(): line-driven wind set-up failed: %s\n", pb200_last_error());
+    QUIT_PLUTO(1);
+  }
+}
+#endif
+
 static void shim_init(Data *d, Grid *grid) {
   pb200_config cfg;
   int dir;
@@ -136,6 +172,19 @@ static void shim_init(Data *d, Grid *grid) {
 #error "libplutob200: TIME_STEPPING must be EULER, RK2 or RK3"
 #endif
   cfg.limiter = translate_limiter();
+#if CHAR_LIMITING == YES
+  cfg.char_limiting = 1;
+#endif
+#if SHOCK_FLATTENING == MULTID
+  cfg.shock_flattening = 1;
+#elif SHOCK_FLATTENING != NO
+#error "libplutob200: SHOCK_FLATTENING must be NO or MULTID"
+#endif
+#if ENTROPY_SWITCH == ALWAYS
+  cfg.entropy_switch = 1;
+#elif ENTROPY_SWITCH != NO
+#error "libplutob200: ENTROPY_SWITCH must be NO or ALWAYS"
+#endif
 #if (BODY_FORCE & VECTOR)
   cfg.body_force |= PB200_BF_VECTOR;
 #endif
@@ -174,6 +223,9 @@ static void shim_init(Data *d, Grid *grid) {
   }
 #if BODY_FORCE != NO
   shim_body_force(d, grid);
+#endif
+#if LINE_DRIVEN_WIND != NO
+  shim_line_driven_wind();
 #endif
   print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode)\n", pb200_version(),
          s_resident ? "resident" : "strict host-buffer");

@@ -142,6 +142,39 @@ class Runtime:
         return rt
 
 
+def make_grid(spec, nghost):
+    """One direction of the reference's grid for a single-patch [Grid] line of pluto.ini:
+    spec = (xL, n, xR) or (xL, n, xR, 'u') uniform, (xL, n, xR, 'r', ratio) the fork's ratio grid.
+    Mirrors MakeGrid() (Src/set_grid.c:395-450) and the ghost extension (Src/set_grid.c:100-127) so
+    that a Python caller can hand pb200_set_grid() the same xl / xr / dx the reference's Grid holds."""
+    import math
+    xL, n, xR = float(spec[0]), int(spec[1]), float(spec[2])
+    kind = spec[3] if len(spec) > 3 else "u"
+    b = nghost
+    xl = np.zeros(n + 2 * b); xr = np.zeros(n + 2 * b); dx = np.zeros(n + 2 * b)
+    if kind == "u":
+        for i in range(n):
+            dx[b + i] = (xR - xL) / float(n)
+            xl[b + i] = xL + float(i) * dx[b + i]
+            xr[b + i] = xl[b + i] + dx[b + i]
+    elif kind == "r":
+        ratio = float(spec[4])
+        xl[b] = xL
+        dx[b] = (xR - xL) * (ratio - 1.0) / (math.pow(ratio, n) - 1.0)
+        xr[b] = xl[b] + dx[b]
+        for i in range(1, n):
+            dx[b + i] = dx[b + i - 1] * ratio
+            xl[b + i] = xl[b + i - 1] + dx[b + i - 1]
+            xr[b + i] = xl[b + i] + dx[b + i]
+    else:
+        raise NotImplementedError("grid type %r" % kind)
+    e = b + n - 1
+    for i in range(b):
+        dx[i] = dx[b]; xl[i] = xl[b] - (b - i) * dx[b]; xr[i] = xl[i] + dx[b]
+        dx[e + i + 1] = dx[e]; xl[e + i + 1] = xl[e] + (i + 1) * dx[e]; xr[e + i + 1] = xl[e] + (i + 2) * dx[e]
+    return xl, xr, dx
+
+
 # --------------------------------------------------------------------------------------
 #  Hydro: one block of the grid resident on one B200
 # --------------------------------------------------------------------------------------
@@ -312,6 +345,18 @@ class Hydro:
         fp = None if flux_p is None else np.ascontiguousarray(flux_p, dtype=np.float64)
         L.check(self._lib.pb200_ldw_set_fluxes(self._h, fr.ctypes.data_as(C.c_void_p), ft.ctypes.data_as(C.c_void_p),
                                                None if fp is None else fp.ctypes.data_as(C.c_void_p)))
+
+    def set_cooling_tables(self, tabs):
+        """Data->comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r
+        (None entries keep the reference's defaults)."""
+        keep = [None if t is None else np.ascontiguousarray(np.broadcast_to(t, self.shape[1:]), dtype=np.float64)
+                for t in tabs]
+        ptrs = (C.c_void_p * 7)(*[None if a is None else a.ctypes.data for a in keep])
+        L.check(self._lib.pb200_cooling_set_tables(self._h, C.byref(ptrs)))
+
+    def split_source(self, dt, g_time):
+        """SplitSource(d, dt, Dts, grid) for COOLING BLONDIN (Src/split_source.c:53)."""
+        L.check(self._lib.pb200_split_source(self._h, float(dt), float(g_time)))
 
     # -- data movement -----------------------------------------------------------------------
     def upload(self, vc: np.ndarray):

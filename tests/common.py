@@ -182,7 +182,7 @@ LDW_BCS = ("userdef", "outflow", "userdef", "reflective", "outflow", "outflow")
 LDW_NANGLES = 36
 
 
-def ldw_flux_tables(x1, x2, nangles=LDW_NANGLES):
+def ldw_flux_tables(x1, x2, nangles=LDW_NANGLES, roundtrip=True):
     """Synthetic directional UV fluxes in the layout of flux_{r,t,p}_UV[iangle][k][j][i]
     (line_connect.c:97-110), for ALL zones of the 1-D coordinate arrays given (the reference only
     fills the interior; ghost entries are never read).  Bin a points along (sin th_a, cos th_a) in
@@ -199,6 +199,8 @@ def ldw_flux_tables(x1, x2, nangles=LDW_NANGLES):
     ft = f0 * w * np.sin(da)
     shape = (nangles, 1, th.shape[1], r.shape[2])
     # round-trip through the text format of the flux files so both sides hold the same doubles
+    if not roundtrip:
+        return fr.reshape(shape), ft.reshape(shape), np.zeros(shape)
     rt = np.vectorize(lambda q: float("%.17e" % q))
     return rt(fr).reshape(shape), rt(ft).reshape(shape), np.zeros(shape)
 

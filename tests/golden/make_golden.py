@@ -145,6 +145,9 @@ LDW_GRID = [(0.87, 48, 8.7, "r", 1.05), (0.0, 36, HALF_PI, "r", 0.95), (0.0, 1, 
 CASES4 = {
     "ldw_nocool_hll": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hll", maxsteps=10, cooling=False),
     "ldw_nocool_hllc": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hllc", maxsteps=8, cooling=False),
+    # with the BLONDIN source step (Strang alternation of Src/main.c:479-485); the prefactor tables
+    # of a first (non-restart) run are never assigned by the reference (Src/initialize.c:505-520)
+    "ldw_cool_hll": dict(cfg="ldw", grid=LDW_GRID, solver="hll", maxsteps=9, cooling=True),
 }
 
 
