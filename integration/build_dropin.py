@@ -41,7 +41,7 @@ def build(cfg: str, force: bool = False) -> Path:
     if r.returncode:
         raise RuntimeError("shim compile failed:\n" + r.stderr[-4000:])
     objs = [str(o) for o in sorted((wd / "obj").glob("*.o")) if o.name != "rk_step.o"]
-    cmd = ["gcc"] + objs + [str(obj), "-Wl,--wrap=WriteData,--wrap=Analysis", "-L%s" % lib.parent, "-lplutob200",
+    cmd = ["gcc"] + objs + [str(obj), "-Wl,--wrap=WriteData,--wrap=Analysis,--wrap=SplitSource", "-L%s" % lib.parent, "-lplutob200",
            "-Wl,-rpath,$ORIGIN/../../../pluto_sirocco_b200/lib", "-lm", "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:

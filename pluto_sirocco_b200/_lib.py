@@ -6,7 +6,9 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libplutob200.so"
+import os
+
+LIB_PATH = Path(os.environ["PB200_LIB"]) if os.environ.get("PB200_LIB") else PKG / "lib" / "libplutob200.so"
 
 # option codes (include/pluto_b200.h)
 CARTESIAN, SPHERICAL = 1, 4

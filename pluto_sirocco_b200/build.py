@@ -26,28 +26,35 @@ UNITS = [("pb200", "pb200.cu", []), ("pb200_gen", "pb200_gen.cu", [])] + [
     for nv in (5, 6, 7) for bf in (0, 1)]
 
 
+# experiment hooks: PB200_EXTRA_DEFS="-DPB_MINBLK=4 ..." and PB200_LIB_NAME=libplutob200_v1.so build a
+# variant library next to the default one (select it at run time with PB200_LIB=<path>)
+EXTRA_DEFS = os.environ.get("PB200_EXTRA_DEFS", "").split()
+if os.environ.get("PB200_LIB_NAME"):
+    LIB = LIBDIR / os.environ["PB200_LIB_NAME"]
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
         h.update((CSRC / f).read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_DEFS).encode())
     return h.hexdigest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
-    stamp = LIBDIR / "libplutob200.sha256"
+    stamp = LIBDIR / (LIB.stem + ".sha256")
     dig = _digest()
     if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    objdir = LIBDIR / "obj"
+    objdir = LIBDIR / ("obj_" + LIB.stem)
     objdir.mkdir(exist_ok=True)
 
     def cc(unit):
         name, src, defs = unit
         obj = objdir / (name + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + defs + ["-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc] + NVCC_FLAGS + defs + EXTRA_DEFS + ["-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

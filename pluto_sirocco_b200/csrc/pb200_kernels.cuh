@@ -278,7 +278,17 @@ __global__ void __launch_bounds__(BX) sweep_x1(Dev d, SweepArgs a) {
 // resident two iterations longer), right states and fluxes are exchanged through two small
 // shared arrays (2 barriers per row), so the x1 and x2 updates of a stage share ONE read of V
 // and ONE write of the accumulator.
-constexpr int DEPTH = 3;   // cp.async groups in flight
+#ifndef PB_DEPTH
+#define PB_DEPTH 2   // measured: 2 beats 3 (smaller ring, same latency cover) on B200
+#endif
+#ifndef PB_MINBLK
+#define PB_MINBLK 3
+#endif
+#ifndef PB_UNROLL
+#define PB_UNROLL 2
+#endif
+constexpr int DEPTH = PB_DEPTH;   // cp.async groups in flight
+constexpr int MARCH_UNROLL = PB_UNROLL;
 
 PB_D void cp_async8(double *sdst, const double *gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
@@ -309,7 +319,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
 }
 
 template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM, int BF>
-__global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chunk) {
+__global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
   constexpr int LEAD = recon_lead<RECON>();
   constexpr int XH = recon_xhalo<RECON>();
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(BX, 3) sweep_fused(Dev d, SweepArgs a, int chu
   const int jt = (DIR == 1) ? 0 : d.beg[1] + tr, kt = (DIR == 1) ? d.beg[2] + tr : 0;
 
   int sc = 0;  // ring slot consumed by this iteration
-#pragma unroll 2
+#pragma unroll MARCH_UNROLL
   for (int n = n0; n <= ce + 1; n++) {
     // ---- data of this iteration has landed in the ring; refill the slot DEPTH ahead ----
     cp_async_wait<DEPTH - 1>();

@@ -226,6 +226,16 @@ static void shim_init(Data *d, Grid *grid) {
 #endif
 #if LINE_DRIVEN_WIND != NO
   shim_line_driven_wind();
+#if COOLING == BLONDIN
+  {   /* Data tables of the BLONDIN module (Src/structs.h:621-643, contiguous ARRAY_3D payloads) */
+    const double *tabs[7] = {d->comp_h_pre[0][0], d->comp_c_pre[0][0], d->xray_h_pre[0][0], d->line_c_pre[0][0],
+                             d->brem_c_pre[0][0], d->sirocco_xi[0][0], d->sirocco_t_r[0][0]};
+    if (pb200_cooling_set_tables(s_ctx, tabs) != PB200_OK) {
+      print ("! AdvanceStep(): pb200_cooling_set_tables failed\n");
+      QUIT_PLUTO(1);
+    }
+  }
+#endif
 #endif
   print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode)\n", pb200_version(),
          s_resident ? "resident" : "strict host-buffer");
@@ -264,6 +274,24 @@ void pb200_shim_sync_to_host(const Data *d)
     s_dirty = 0;
   }
 }
+/* resident mode with COOLING BLONDIN: the source step runs on the device copy as well
+ * (link with -Wl,--wrap=SplitSource); host-buffer mode keeps the reference's own SplitSource() */
+void __real_SplitSource (Data *, double, timeStep *, Grid *);
+void __wrap_SplitSource (Data *d, double dt, timeStep *Dts, Grid *grid)
+{
+#if COOLING == BLONDIN && LINE_DRIVEN_WIND != NO
+  if (s_ctx != NULL && s_resident) {
+    if (pb200_split_source(s_ctx, dt, g_time) != PB200_OK) {
+      print ("! SplitSource(): pb200_split_source failed\n");
+      QUIT_PLUTO(1);
+    }
+    s_dirty = 1;
+    return;
+  }
+#endif
+  __real_SplitSource(d, dt, Dts, grid);
+}
+
 void __real_WriteData (const Data *, Output *, Grid *);
 void __wrap_WriteData (const Data *d, Output *output, Grid *grid)
 {

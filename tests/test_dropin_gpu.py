@@ -31,10 +31,13 @@ CASES = {
 }
 
 
-def test_dropin_line_driven_wind_matches_reference_executable(cuda_lib, tmp_path):
-    """C4 end to end: the reference's own driver + cv_idl user files + BLONDIN cooling (SplitSource stays
-    the reference's CPU code in host-buffer mode), with AdvanceStep replaced by libplutob200, on
-    synthetic sirocco flux files read by the reference's own reader."""
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_dropin_line_driven_wind_matches_reference_executable(cuda_lib, tmp_path, resident):
+    """C4 end to end: the reference's own driver + cv_idl user files + BLONDIN cooling, with
+    AdvanceStep replaced by libplutob200, on synthetic sirocco flux files read by the reference's
+    own reader.  Host-buffer mode keeps SplitSource() on the reference's CPU code; resident mode
+    runs BlondinCooling on the device too (--wrap=SplitSource), where a zone sitting on the Brent
+    solver's 1 K stopping threshold may end one iteration apart (see test_gpu_gen.py)."""
     import pluto_grid
     from common import LDW_BCS, LDW_PARAMS, ldw_flux_tables, write_ldw_flux_files
     cfg = "ldw"
@@ -52,6 +55,7 @@ def test_dropin_line_driven_wind_matches_reference_executable(cuda_lib, tmp_path
         wd.mkdir()
         write_ldw_flux_files(wd, x1, x2, 3, fr, ft, fp)
         out[tag] = refrun.run(cfg, wd, shape=(1, 36, 48), nvar=6, maxsteps=12, timeout=250, exe=ex,
+                              env={"PB200_RESIDENT": resident},
                               grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
                               solver="hll", bcs=LDW_BCS, dbl=(-1.0, 1), params=LDW_PARAMS)
     ref, got = out["ref"], out["b200"]
@@ -60,8 +64,12 @@ def test_dropin_line_driven_wind_matches_reference_executable(cuda_lib, tmp_path
     for (n1, t1, d1), (n2, t2, d2) in zip(ref["steps"], got["steps"]):
         assert n1 == n2 and abs(t1 - t2) <= 1e-11 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-10 * d1
     assert np.array_equal(ref["data"][0], got["data"][0])
-    assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
-    assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
+    if resident == "0":
+        assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
+        assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
+    else:
+        assert rel_err(got["data"][1], ref["data"][1]) <= 2e-4      # pressure: Brent tolerance 1 K
+        assert rel_l1(got["data"][-1], ref["data"][-1]) <= 1e-6
 
 
 @pytest.mark.parametrize("cfg", list(CASES))
