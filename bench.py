@@ -38,7 +38,10 @@ ALG_BYTES_RK3 = 560.0
 SEDOV_BCS = ("reflective", "outflow") * 3
 
 
-def workload_name(n, recon, rk, solver):
+def workload_name(n, recon, rk, solver, rt=False):
+    if rt:
+        return "rayleigh-taylor3d-%d^3-global %s+%s+%s, tracer, gravity" % (
+            n, {"LINEAR": "PLM", "PARABOLIC": "PPM"}[recon], solver.upper(), rk)
     return "sedov3d-%d^3-per-gpu %s+%s+%s" % (n, {"LINEAR": "PLM", "PARABOLIC": "PPM"}[recon], solver.upper(), rk)
 
 
@@ -59,6 +62,25 @@ def sedov_block(nx, zoff, nglob, gamma=1.4):
     m = 8
     r = np.sqrt(x[None, None, :m] ** 2 + y[None, :m, None] ** 2 + z[:m, None, None] ** 2)
     v[4, :m, :m, :m] = np.where(r <= dr, (gamma - 1.0) * 1.0 / vol, 1.0e-5)
+    return v
+
+
+def rt_block(nx, zoff, nglob, gamma=5. / 3., eta=2.0, grav=-0.1):
+    """Rayleigh-Taylor IC of oracle/problems/rt/init.c (3-D branch) for the block whose x3 index
+    starts at zoff: heavy fluid (eta) above light fluid in gravity along x2, hydrostatic pressure,
+    single-mode velocity seed, tracer = heavy fluid.  Unit cube centred on the origin."""
+    import numpy as np
+    n1, n2, n3 = nx
+    x = -0.5 + (np.arange(n1) + 0.5) / nglob
+    y = -0.5 + (np.arange(n2) + 0.5) / nglob
+    z = -0.5 + (np.arange(n3) + zoff + 0.5) / nglob
+    v = np.zeros((6, n3, n2, n1))
+    heavy = (y >= 0.0).astype(float)[None, :, None]
+    v[0] = 1.0 + (eta - 1.0) * heavy
+    v[4] = 1.0 / gamma + v[0] * grav * y[None, :, None]
+    seed = (1.0 + np.cos(2.0 * np.pi * x))[None, None, :] * (1.0 + np.cos(2.0 * np.pi * z))[:, None, None] * 0.5
+    v[2] = -1.e-2 * seed * np.exp(-y * y * 50.0)[None, :, None]
+    v[5] = heavy
     return v
 
 
@@ -201,17 +223,37 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.size
-    gnx = (n, n, n * world)
-    bcs = SEDOV_BCS
-    slab = Slab(rank, world, 3, gnx, (0., 0., 0.), (1., 1., float(world)), bcs)
+    rt = args.workload == "rt"
+    if rt:
+        # BASELINE configs[2]: Rayleigh-Taylor, 3-D, n x n x n GLOBAL zones split into world x3 slabs
+        # (1024^3 over 8 GPUs = 1024 x 1024 x 128 per GPU); strong scaling in the driver's terms is not
+        # asked for: run it with --gpus 8 --size 1024.  Periodic x1/x3, reflective x2, gravity along x2,
+        # one tracer (oracle/problems/rt/init.c is the same set-up for the reference).
+        if n % world:
+            raise SystemExit("--size must be a multiple of the number of GPUs for --workload rt")
+        gnx = (n, n, n)
+        bcs = ("periodic", "periodic", "reflective", "reflective", "periodic", "periodic")
+        gxb, gxe = (-0.5, -0.5, -0.5), (0.5, 0.5, 0.5)
+        gamma, ntr, bf = 5. / 3., 1, 1
+        zones_local = n * n * (n // world)
+    else:
+        gnx = (n, n, n * world)
+        bcs = SEDOV_BCS
+        gxb, gxe = (0., 0., 0.), (1., 1., float(world))
+        gamma, ntr, bf = 1.4, 0, 0
+        zones_local = n * n * n
+    slab = Slab(rank, world, 3, gnx, gxb, gxe, bcs)
     xb, xe = slab.local_extent()
-    h = Hydro(dimensions=3, nx=slab.local_nx(), xbeg=xb, xend=xe, gamma=1.4, reconstruction=args.recon,
+    h = Hydro(dimensions=3, nx=slab.local_nx(), xbeg=xb, xend=xe, gamma=gamma, reconstruction=args.recon,
               time_stepping=args.rk, solver=args.solver, bcs=slab.local_bcs(), device=local_rank,
-              dx=slab.global_dx())
+              dx=slab.global_dx(), ntracer=ntr, body_force=bf)
+    if rt:
+        for comp, val in enumerate((0.0, -0.1, 0.0)):      # BodyForceVector = (0, GRAV, 0)
+            h.set_body_force_vector(comp, np.full((1, 1, 1), val))
     sh = SlabHydro(h, slab)
-    zones_local = n * n * n
     zones_total = zones_local * world
 
     # host state in pinned memory (needed by the e2e leg; also the upload source)
@@ -219,7 +261,9 @@ def run_b200(args):
     vc = pin.numpy()
     vc[:] = 1.0
     vc[1:4] = 0.0
-    if args.state == "sedov":
+    if rt:
+        vc[h.interior()] = rt_block(slab.local_nx(), slab.offset, n)
+    elif args.state == "sedov":
         vc[h.interior()] = sedov_block(slab.local_nx(), slab.offset, n)
     else:   # "busy": seeded waves + jumps everywhere: every limiter/solver branch is exercised
         sys.path.insert(0, str(ROOT / "tests"))
@@ -227,8 +271,8 @@ def run_b200(args):
         vc[h.interior()] = random_state((n, n, n), seed=rank, smooth=False)
     h.upload(vc)
 
-    cfl, cmv, first_dt = 0.3, 1.1, 1e-9
-    g = {"dt": first_dt if args.state == "sedov" else 1e-5}
+    cfl, cmv, first_dt = (0.4, 1.1, 1e-3) if rt else (0.3, 1.1, 1e-9)
+    g = {"dt": first_dt if (args.state == "sedov" or rt) else 1e-5}
 
     def one_step():
         inv, mach, info = sh.advance_step(g["dt"])
@@ -320,7 +364,7 @@ def run_b200(args):
         return 0
 
     peak, peak_src = measured_peaks()
-    alg = ALG_BYTES_RK2 if args.rk == "RK2" else ALG_BYTES_RK3
+    alg = (ALG_BYTES_RK2 if args.rk == "RK2" else ALG_BYTES_RK3) * h.nvar / 5.0   # 40 B per 5-vector -> 8 B x NVAR
     nlaunch_sweeps = len(kern)
     step_ms = ms / args.steps
     achieved_step = alg * zones_local / (step_ms * 1e-3) / 1e9          # GB/s per GPU, whole step
@@ -341,7 +385,7 @@ def run_b200(args):
                 "kernels_ms": {"x%d_stage%d" % (k[0] + 1, k[1]): v for k, v in sorted(kern.items())}}
 
     cpu_baseline = None
-    if not args.no_cpu:
+    if not args.no_cpu and not rt:
         cfg = "sedov3d" if args.recon == "LINEAR" else "sedov3d_ppm"
         r = reference_rate(cfg, args.cpu_size, 1, 1, args.cpu_steps, args.solver)
         if r is not None:
@@ -363,12 +407,12 @@ def run_b200(args):
                             "sample": "oracle/hd_oracle.c, %d^3 zones, %d steps, 1 core" % (m, ns)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if rt else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n, args.recon, args.rk, args.solver), "state": args.state,
+            "config": {"workload": workload_name(n, args.recon, args.rk, args.solver, rt), "state": "rt" if rt else args.state,
                        "zones_per_gpu": zones_local, "decomposition": "x3 slabs" if world > 1 else "none",
-                       "l2": "inputs (5.5 GB per state array) larger than L2, no flush needed",
-                       "boundaries": "reflective-beg/outflow-end", "cfl": cfl},
+                       "l2": "inputs (%.1f GB per state array) larger than L2, no flush needed" % (int(np.prod(h.shape)) * 8 / 1e9),
+                       "boundaries": "periodic x1/x3, reflective x2" if rt else "reflective-beg/outflow-end", "cfl": cfl},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
@@ -497,8 +541,9 @@ def run_ldw(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sedov", choices=["sedov", "ldw"],
-                    help="sedov: BASELINE configs[1] (the metric's config); ldw: configs[3]")
+    ap.add_argument("--workload", default="sedov", choices=["sedov", "rt", "ldw"],
+                    help="sedov: BASELINE configs[1] (the metric's config; configs[4] with --recon PARABOLIC --rk RK3 "
+                         "--size 256); rt: configs[2] (--gpus 8 --size 1024); ldw: configs[3]")
     ap.add_argument("--ldw-size", type=int, nargs=2, default=[1024, 512])
     ap.add_argument("--ldw-ratio", type=float, nargs=2, default=[1.005, 0.995])
     ap.add_argument("--gpus", type=int, default=1)
