@@ -18,3 +18,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:swee
   -o $OUT/full -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/full.log 2>&1
 ncu -i $OUT/full.ncu-rep --page raw --csv > $OUT/full_raw.csv 2>/dev/null
 ls -la $OUT
+# general path (LDW workload): full capture of one stage worth of gen_* kernels
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gen_ --launch-skip 96 -c 16 \
+  -o $OUT/full_ldw -f python bench.py --workload ldw --steps 2 --warmup 3 > $OUT/full_ldw.log 2>&1
+ncu -i $OUT/full_ldw.ncu-rep --page raw --csv > $OUT/full_ldw_raw.csv 2>/dev/null
+rm -f $OUT/full_ldw.ncu-rep $OUT/full.ncu-rep
+ls -la $OUT
