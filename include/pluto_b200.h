@@ -233,6 +233,13 @@ int  pb200_stage_boundary(pb200_ctx *ctx, int stage);
 int  pb200_stage_begin(pb200_ctx *ctx, int stage);
 int  pb200_stage_finish(pb200_ctx *ctx, int stage);
 int  pb200_step_end(pb200_ctx *ctx, pb200_step_info *info);
+/* Host round trip of the array stage s sweeps (whole d->Vc layout incl. ghosts), for callers whose
+ * boundary conditions are arbitrary host code: the shim downloads it, runs the reference's own
+ * Boundary(d, 0, grid) -> UserDefBoundary() (Src/boundary.c:56, Src/prototypes.h:217) on the host
+ * copy and uploads it again before pb200_stage(s).  Slow by construction (PCIe per stage); it is
+ * the correctness path for user plug-ins, not a CPU implementation of the update. */
+int  pb200_stage_download(pb200_ctx *ctx, int stage, double *vc_host);
+int  pb200_stage_upload(pb200_ctx *ctx, int stage, const double *vc_host);
 int  pb200_nstages(const pb200_ctx *ctx);
 /* Measurement aid (the reference's FUNCTION_CLOCK_PROFILE, Src/pluto.h:414-419, rk_step.c:
  * 51-55): record CUDA events around every sweep kernel of the following steps;

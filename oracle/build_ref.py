@@ -98,6 +98,9 @@ CONFIGS = {
     # the same without the BLONDIN source step: isolates the hydro + line-force update
     "ldw_nocool": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={"COOLING": "NO"},
                        states="plm", extra_vpath=["LineDriven"], extra_objs=["line_connect"]),
+    # an arbitrary, time-dependent UserDefBoundary() (oracle/problems/jet): the shim's host-boundary mode
+    "jet2d": dict(local="jet", overrides={}, states="plm"),
+    "jet2d_ppm": dict(local="jet", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
     # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
     "kh3d": dict(local="kh", overrides={}, states="plm"),
 }

@@ -80,6 +80,8 @@ SYMBOLS = {
     "pb200_stage_boundary": (C.c_int, [_P, C.c_int]),
     "pb200_stage_begin": (C.c_int, [_P, C.c_int]),
     "pb200_stage_finish": (C.c_int, [_P, C.c_int]),
+    "pb200_stage_download": (C.c_int, [_P, C.c_int, _P]),
+    "pb200_stage_upload": (C.c_int, [_P, C.c_int, _P]),
     "pb200_step_end": (C.c_int, [_P, C.POINTER(StepInfo)]),
     "pb200_nstages": (C.c_int, [_P]),
     "pb200_stream": (_P, [_P]),

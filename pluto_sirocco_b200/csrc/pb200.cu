@@ -369,6 +369,19 @@ extern "C" double *pb200_stage_array(pb200_ctx *c, int stage) {
   return c->V[c->stage_in[stage]];
 }
 
+extern "C" int pb200_stage_download(pb200_ctx *c, int stage, double *h) {
+  if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
+  CK(cudaMemcpyAsync(h, c->V[c->stage_in[stage]], c->vbytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
+  if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
+  CK(cudaMemcpyAsync(c->V[c->stage_in[stage]], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+
 // A stage in three parts so that a slab-decomposed caller can overlap the halo exchange of the
 // outermost direction with the sweeps that do not read those ghost planes:
 //   pb200_stage_boundary: Boundary() fills of the physical sides;

@@ -19,6 +19,7 @@
 
 static pb200_ctx *s_ctx = NULL;
 static int s_resident = 0, s_dirty = 0;
+static int s_host_bc = 0;   /* boundaries are filled by the reference's own Boundary() on the host */
 
 static int translate_limiter(void) {
 #ifdef LIMITER
@@ -199,12 +200,22 @@ static void shim_init(Data *d, Grid *grid) {
     print ("! AdvanceStep(): this Riemann solver is not available in libplutob200\n");
     QUIT_PLUTO(1);
   }
+  /* USERDEF sides (other than the line-driven-wind problem's, which has device versions) and
+     INTERNAL_BOUNDARY are arbitrary host code: fall back to the reference's Boundary() per stage */
+#if LINE_DRIVEN_WIND == NO
+  for (dir = 0; dir < DIMENSIONS; dir++)
+    if (grid->lbound[dir] == USERDEF || grid->rbound[dir] == USERDEF) s_host_bc = 1;
+#if INTERNAL_BOUNDARY == YES
+  s_host_bc = 1;
+#endif
+#endif
+  if (getenv("PB200_HOST_BOUNDARY")) s_host_bc = atoi(getenv("PB200_HOST_BOUNDARY"));
   for (dir = 0; dir < 3; dir++) {
     cfg.nx[dir]   = grid->np_int[dir];
     cfg.xbeg[dir] = grid->xbeg[dir];
     cfg.xend[dir] = grid->xend[dir];
-    cfg.bc[2*dir]     = grid->lbound[dir];   /* same codes, Src/pluto.h:163-170 */
-    cfg.bc[2*dir + 1] = grid->rbound[dir];
+    cfg.bc[2*dir]     = s_host_bc ? PB200_BC_NEIGHBOUR : grid->lbound[dir];   /* same codes, Src/pluto.h:163-170 */
+    cfg.bc[2*dir + 1] = s_host_bc ? PB200_BC_NEIGHBOUR : grid->rbound[dir];
   }
   cfg.gamma          = g_gamma;
   cfg.small_density  = g_smallDensity;
@@ -237,8 +248,9 @@ static void shim_init(Data *d, Grid *grid) {
   }
 #endif
 #endif
-  print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode)\n", pb200_version(),
-         s_resident ? "resident" : "strict host-buffer");
+  print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode%s)\n", pb200_version(),
+         s_resident ? "resident" : "strict host-buffer",
+         s_host_bc ? ", boundaries by the host's Boundary()/UserDefBoundary()" : "");
 }
 
 int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
@@ -251,7 +263,21 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
     shim_init(d, grid);
     if (s_resident) pb200_upload_vc(s_ctx, vc);
   }
-  if (s_resident) {
+  if (s_host_bc) {
+    /* per stage: D2H, the reference's Boundary() (-> UserDefBoundary) on d->Vc, H2D, stage */
+    int s, ns = pb200_nstages(s_ctx);
+    rc = pb200_step_begin(s_ctx, g_dt);
+    for (s = 1; s <= ns && rc == PB200_OK; s++) {
+      g_intStage = s;
+      if (s > 1 || s_resident) rc = pb200_stage_download(s_ctx, s, vc);
+      if (rc != PB200_OK) break;
+      Boundary (d, 0, grid);
+      rc = pb200_stage_upload(s_ctx, s, vc);
+      if (rc == PB200_OK) rc = pb200_stage(s_ctx, s);
+    }
+    if (rc == PB200_OK) rc = pb200_step_end(s_ctx, &info);
+    if (rc == PB200_OK) rc = pb200_download_vc(s_ctx, vc);
+  } else if (s_resident) {
     rc = pb200_advance_step(s_ctx, g_dt, &info);
     s_dirty = 1;
   } else {

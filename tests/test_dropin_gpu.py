@@ -26,6 +26,13 @@ CASES = {
     # tracer + BODY_FORCE: the shim evaluates the user's BodyForceVector / BodyForcePotential
     "rt3d_vec": dict(shape=(10, 24, 12), nvar=6, grid=[(-0.5, 12, 0.5), (-1.0, 24, 1.0), (-0.5, 10, 0.5)],
                      maxsteps=10, **RT),
+    # arbitrary, time-dependent UserDefBoundary(): the shim falls back to the reference's Boundary() per stage
+    "jet2d": dict(shape=(1, 64, 48), nvar=6, grid=[(-3.0, 48, 3.0), (0.0, 64, 8.0), (0.0, 1, 1.0)], maxsteps=30,
+                  bcs=("outflow", "outflow", "userdef", "outflow", "outflow", "outflow"),
+                  params=dict(ETA=10.0, MACH=5.0), cfl=0.4, tstop=5.0, first_dt=1e-4),
+    "jet2d_ppm": dict(shape=(1, 64, 48), nvar=6, grid=[(-3.0, 48, 3.0), (0.0, 64, 8.0), (0.0, 1, 1.0)], maxsteps=20,
+                      bcs=("outflow", "outflow", "userdef", "outflow", "outflow", "outflow"),
+                      params=dict(ETA=10.0, MACH=5.0), cfl=0.4, tstop=5.0, first_dt=1e-4),
     "rt2d_pot": dict(shape=(1, 48, 16), nvar=6, grid=[(-0.5, 16, 0.5), (-1.5, 48, 1.5), (-0.5, 1, 0.5)],
                      maxsteps=12, **RT),
 }
