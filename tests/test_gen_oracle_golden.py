@@ -28,7 +28,7 @@ def test_gen_oracle_per_step_matches_reference_dumps(name):
     o.close()
 
 
-LDW_CASES = [c for c in GEN_CASES if c.startswith("ldw")]
+LDW_CASES = [c for c in GEN_CASES if c.startswith("ldw_nocool")]
 
 
 @pytest.mark.parametrize("name", LDW_CASES)
@@ -49,4 +49,29 @@ def test_gen_oracle_ldw_per_step_matches_reference_dumps(name):
         assert np.array_equal(got, data[n + 1]), (name, n, rel_err(got, data[n + 1]))
         dtn = o.next_time_step(inv, g["cfl"], g["cfl_max_var"], dt, g["first_dt"])
         assert dtn == steps[n + 1, 2], (name, n)
+    o.close()
+
+
+def test_gen_oracle_ldw_with_blondin_cooling_matches_reference_dumps():
+    """COOLING BLONDIN in the Strang order of Src/main.c:479-485 (even steps: AdvanceStep then
+    SplitSource, odd steps the reverse; dt renewed every second step), prefactors at their defaults
+    (1.0, line_connect.c:383-393), analytic ionisation parameter (g_time <= 3): bit-exact."""
+    g = load_golden("ldw_cool_hll")
+    o = GenOracle(**gen_kwargs_from_golden(g))
+    ldw_setup(o, o.x(0), o.x(1))
+    data, steps = g["data"], g["steps"]
+    nfile = data.shape[1]
+    tabs = [np.ones((1, 1, 1))] * 5 + [np.zeros((1, 1, 1))] * 2
+    for n in range(len(data) - 1):
+        vc = o.embed(data[n])
+        dt, t = steps[n, 2], steps[n, 1]
+        if n % 2 == 0:
+            o.advance_step(vc, dt); o.blondin_cooling(vc, dt, t, tabs)
+        else:
+            o.blondin_cooling(vc, dt, t, tabs); o.advance_step(vc, dt)
+        assert np.array_equal(vc[o.interior()][:nfile], data[n + 1]), n
+        if n % 2 == 1:      # NextTimeStep every second step (main.c:326-330)
+            assert steps[n + 1, 2] != steps[n, 2]
+        else:
+            assert steps[n + 1, 2] == steps[n, 2]
     o.close()
