@@ -97,10 +97,11 @@ PB_D double warp_max(double x) {
 
 // end-of-kernel reduction: block-wide max of (C_dt, Mach), sum of cons2prim failures and the
 // NaN flag -> one atomic each per block
-PB_D void block_reduce(double cdt, double mach, int nfail, int nan, bool do_cdt,
-                       unsigned long long *red) {
-  __shared__ double sa[BX / 32], sb[BX / 32];
-  __shared__ int sf[BX / 32], sn[BX / 32];
+template <int BXT>
+PB_D void block_reduce_t(double cdt, double mach, int nfail, int nan, bool do_cdt,
+                         unsigned long long *red) {
+  __shared__ double sa[BXT / 32], sb[BXT / 32];
+  __shared__ int sf[BXT / 32], sn[BXT / 32];
   cdt = warp_max(cdt);
   mach = warp_max(mach);
   nfail = __reduce_add_sync(0xffffffffu, nfail);
@@ -110,7 +111,7 @@ PB_D void block_reduce(double cdt, double mach, int nfail, int nan, bool do_cdt,
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 1; k < BX / 32; k++) {
+    for (int k = 1; k < BXT / 32; k++) {
       cdt = fmax(cdt, sa[k]); mach = fmax(mach, sb[k]); nfail += sf[k]; nan |= sn[k];
     }
     if (do_cdt && cdt > 0.0) atomic_max_pos(red + 0, cdt);
@@ -118,6 +119,10 @@ PB_D void block_reduce(double cdt, double mach, int nfail, int nan, bool do_cdt,
     if (nfail) atomicAdd(red + 2, (unsigned long long)nfail);
     if (nan) atomicOr(red + 3, 1ull);
   }
+}
+
+PB_D void block_reduce(double cdt, double mach, int nfail, int nan, bool do_cdt, unsigned long long *red) {
+  block_reduce_t<BX>(cdt, mach, nfail, nan, do_cdt, red);
 }
 
 // RK combination (rk_step.c:236,304) with U0 = cons(V^n); U in any component order
@@ -312,26 +317,29 @@ __host__ __device__ constexpr int ring_slots() {
 __host__ __device__ inline int ring_nq(int nv, bool first, int comb, bool cdt_in) {
   return nv + (first ? 0 : nv) + ((first && comb) ? nv : 0) + (cdt_in ? 1 : 0);
 }
-template <bool FUSEX, int NV, int RECON>
+template <bool FUSEX, int NV, int RECON, int BXT = BX>
 __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
-  return ((size_t)ring_slots<FUSEX, RECON>() * nq * BX + (FUSEX ? (size_t)(2 * NV + 2) * BX : 0)) *
+  return ((size_t)ring_slots<FUSEX, RECON>() * nq * BXT + (FUSEX ? (size_t)(2 * NV + 2) * BXT : 0)) *
          sizeof(double);
 }
 
-template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM, int BF>
-__global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a, int chunk) {
+// BXT: threads per block.  The fused x1+x2 kernel loses 2*XH threads per block to the x1 halo, so
+// on a 512-wide grid 128-thread blocks need 5 blocks (20 warps) per row where 192-thread blocks
+// need 3 (18 warps): the launcher picks the width that runs the fewest warps.
+template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM, int BF, int BXT = BX>
+__global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
   constexpr int LEAD = recon_lead<RECON>();
   constexpr int XH = recon_xhalo<RECON>();
   constexpr int LO = FUSEX ? XH : 0, HI = FUSEX ? XH : 0;
-  constexpr int USE = BX - LO - HI;
+  constexpr int USE = BXT - LO - HI;
   constexpr int RING = ring_slots<FUSEX, RECON>();
   constexpr bool FIRST = FUSEX;   // the x1(+x2) kernel starts the accumulation: U = cons(V)
   extern __shared__ double smem[];
 
   const int t = threadIdx.x;
   const int i = d.beg[0] + blockIdx.x * USE + t - LO;
-  const bool own = (t >= LO) && (t < BX - HI) && (i <= d.end[0]);
+  const bool own = (t >= LO) && (t < BXT - HI) && (i <= d.end[0]);
   const int ic = min(max(i, 0), d.tot[0] - 1);
   const int tr = blockIdx.y;  // transverse index (k for x2 sweeps, j for x3 sweeps)
   const long st = (DIR == 1) ? d.sj : d.sk;
@@ -352,10 +360,10 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
   const bool cdt_in = cdt_on && !FIRST;
   const int qA = NV, q0 = qA + (FIRST ? 0 : NV), qC = q0 + (use_v0 ? NV : 0);
   const int nq = qC + (cdt_in ? 1 : 0);
-  const int slot_sz = nq * BX;
-  double *ring = smem + t;                              // [RING][nq][BX]
-  double *exm = smem + RING * slot_sz;                  // FUSEX: [NV][BX] right states (vm)
-  double *exf = exm + NV * BX;                          //        [NV+2][BX] fluxes, prs, cmax
+  const int slot_sz = nq * BXT;
+  double *ring = smem + t;                              // [RING][nq][BXT]
+  double *exm = smem + RING * slot_sz;                  // FUSEX: [NV][BXT] right states (vm)
+  double *exf = exm + NV * BXT;                          //        [NV+2][BXT] fluxes, prs, cmax
 
   const int n0 = cb - LEAD;  // first iteration: consumes V row cb, so the ring holds rows >= cb
   // iteration m consumes V row m+LEAD and the stored quantities of zone m-1
@@ -364,19 +372,19 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
       double *slot = ring + s * slot_sz;
       const long oV = base + (long)(m + LEAD) * st;
 #pragma unroll
-      for (int c = 0; c < NV; c++) cp_async8(slot + c * BX, a.V + gvar<DIR>(c) * d.sv + oV);
+      for (int c = 0; c < NV; c++) cp_async8(slot + c * BXT, a.V + gvar<DIR>(c) * d.sv + oV);
       const int z = m - 1;
       if (z >= cb && own) {
         const long oz = base + (long)z * st;
         if (!FIRST) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) cp_async8(slot + (qA + v) * BX, a.acc + v * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(slot + (qA + v) * BXT, a.acc + v * d.sv + oz);
         }
         if (use_v0) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) cp_async8(slot + (q0 + v) * BX, a.V0 + v * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(slot + (q0 + v) * BXT, a.V0 + v * d.sv + oz);
         }
-        if (cdt_in) cp_async8(slot + qC * BX, a.cdt + oz);
+        if (cdt_in) cp_async8(slot + qC * BXT, a.cdt + oz);
       }
     }
     cp_async_commit();
@@ -426,20 +434,20 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
     const double *slot = ring + sc * slot_sz;
     double vin[NV];
 #pragma unroll
-    for (int c = 0; c < NV; c++) vin[c] = slot[c * BX];
+    for (int c = 0; c < NV; c++) vin[c] = slot[c * BXT];
     const int z = n - 1;          // zone finished by this iteration
     const bool fin = n >= cb + 1;  // block-uniform
     double U[NV], v0z[NV], cin = 0.0;   // U, v0z: GLOBAL variable order
     if (fin) {
       if (!FIRST) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) U[v] = slot[(qA + v) * BX];
+        for (int v = 0; v < NV; v++) U[v] = slot[(qA + v) * BXT];
       }
       if (use_v0) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) v0z[v] = slot[(q0 + v) * BX];
+        for (int v = 0; v < NV; v++) v0z[v] = slot[(q0 + v) * BXT];
       }
-      if (cdt_in) cin = slot[qC * BX];
+      if (cdt_in) cin = slot[qC * BXT];
     }
     const double inv_dl = __ldg(inv_dx + max(z, 0));
     issue(n + DEPTH, wrap(sc + DEPTH));
@@ -486,22 +494,22 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
         int sz = sc - (1 + LEAD);
         sz = sz < 0 ? sz + RING : sz;
         const double *rz = smem + sz * slot_sz;   // row z, all threads
-        const int tm = t > 0 ? t - 1 : 0, tp = t < BX - 1 ? t + 1 : BX - 1;
+        const int tm = t > 0 ? t - 1 : 0, tp = t < BXT - 1 ? t + 1 : BXT - 1;
         double xp[NV], xm[NV];                    // x1-local = global component order
 #pragma unroll
-        for (int v = 0; v < NV; v++) vx[v] = rz[lvar<DIR>(v) * BX + t];
+        for (int v = 0; v < NV; v++) vx[v] = rz[lvar<DIR>(v) * BXT + t];
         if (RECON == RECON_PARABOLIC) {
-          const int tp2 = t < BX - 2 ? t + 2 : BX - 1;
+          const int tp2 = t < BXT - 2 ? t + 2 : BXT - 1;
 #pragma unroll
           for (int v = 0; v < NV; v++) {
-            const double *r = rz + lvar<DIR>(v) * BX;
+            const double *r = rz + lvar<DIR>(v) * BXT;
             xp[v] = ppm4_iface(r[tm], vx[v], r[tp], r[tp2]);
-            exm[v * BX + t] = xp[v];   // interface value at t+1/2
+            exm[v * BXT + t] = xp[v];   // interface value at t+1/2
           }
           __syncthreads();
 #pragma unroll
           for (int v = 0; v < NV; v++) {
-            xm[v] = exm[v * BX + tm];
+            xm[v] = exm[v * BXT + tm];
             ppm_parabola(vx[v], xp[v], xm[v], 2.0, 2.0);
           }
           __syncthreads();
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
           double dp[NV], dm[NV];
 #pragma unroll
           for (int v = 0; v < NV; v++) {
-            const double *r = rz + lvar<DIR>(v) * BX;
+            const double *r = rz + lvar<DIR>(v) * BXT;
             dp[v] = r[tp] - vx[v];
             dm[v] = vx[v] - r[tm];
           }
@@ -519,13 +527,13 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
           for (int v = 0; v < NV; v++) xp[v] = xm[v] = vx[v];
         }
 #pragma unroll
-        for (int v = 0; v < NV; v++) exm[v * BX + t] = xm[v];
+        for (int v = 0; v < NV; v++) exm[v * BXT + t] = xm[v];
         __syncthreads();
         double xr[NV];
 #pragma unroll
-        for (int v = 0; v < NV; v++) xr[v] = exm[v * BX + tp];
+        for (int v = 0; v < NV; v++) xr[v] = exm[v * BXT + tp];
         Face<NV> Gp;
-        const bool xface = t >= LO - 1 && t < BX - HI && i >= d.beg[0] - 1 && i <= d.end[0];
+        const bool xface = t >= LO - 1 && t < BXT - HI && i >= d.beg[0] - 1 && i <= d.end[0];
         riemann<NV, SOLVER>(xp, xr, d.gas, Gp, mach, xface);
         riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own);
         double phx = 0.0;
@@ -534,27 +542,27 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
           Gp.f[iPRS] += Gp.f[iRHO] * phx;
         }
 #pragma unroll
-        for (int v = 0; v < NV; v++) exf[v * BX + t] = Gp.f[v];
-        exf[NV * BX + t] = Gp.prs;
-        exf[(NV + 1) * BX + t] = Gp.cmax;
+        for (int v = 0; v < NV; v++) exf[v * BXT + t] = Gp.f[v];
+        exf[NV * BXT + t] = Gp.prs;
+        exf[(NV + 1) * BXT + t] = Gp.cmax;
         __syncthreads();
         const double idx1 = __ldg(d.inv_dx[0] + ic);
         const double dtdx1 = dt * idx1;
         prim2cons<NV>(vx, U, d.gas);
 #pragma unroll
-        for (int v = 0; v < NV; v++) U[v] += -dtdx1 * (Gp.f[v] - exf[v * BX + tm]);
-        U[iVN] -= dtdx1 * (Gp.prs - exf[NV * BX + tm]);
-        cx = 0.5 * (exf[(NV + 1) * BX + tm] + Gp.cmax) * idx1;
+        for (int v = 0; v < NV; v++) U[v] += -dtdx1 * (Gp.f[v] - exf[v * BXT + tm]);
+        U[iVN] -= dtdx1 * (Gp.prs - exf[NV * BXT + tm]);
+        cx = 0.5 * (exf[(NV + 1) * BXT + tm] + Gp.cmax) * idx1;
         if (BF) {   // RightHandSideSource(), x1 sweep (rhs_source.c:253-281)
           if (d.bf_kind & 1) {
             const double g1 = bf_at(d, 0, ic, zj, zk);
             U[iVN] += dt * vx[iRHO] * g1;
-            U[iPRS] += dt * 0.5 * (Gp.f[iRHO] + exf[iRHO * BX + tm]) * g1;
+            U[iPRS] += dt * 0.5 * (Gp.f[iRHO] + exf[iRHO * BXT + tm]) * g1;
           }
           if (d.bf_kind & 2) {
             const double phm = bf_at(d, 4, max(ic - 1, 0), zj, zk);
             U[iVN] -= dtdx1 * vx[iRHO] * (phx - phm);
-            U[iPRS] -= bf_at(d, 3, ic, zj, zk) * (-dtdx1 * (Gp.f[iRHO] - exf[iRHO * BX + tm]));
+            U[iPRS] -= bf_at(d, 3, ic, zj, zk) * (-dtdx1 * (Gp.f[iRHO] - exf[iRHO * BXT + tm]));
           }
         }
       }
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(BX, PB_MINBLK) sweep_fused(Dev d, SweepArgs a,
     sc = wrap(sc + 1);
   }
   cp_async_wait<0>();
-  block_reduce(cdt_max, mach.value(), nfail, nan, a.stage == 1 && LAST, a.red);
+  block_reduce_t<BXT>(cdt_max, mach.value(), nfail, nan, a.stage == 1 && LAST, a.red);
 }
 
 // ------------------------------------------------------------------------------------

@@ -44,12 +44,19 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
     const bool fusex = (dir == 1);
     const bool last = (dir == D.ndim - 1);
-    const int use = fusex ? BX - 2 * recon_xhalo<RECON>() : BX;
+    // block width of the fused kernel: fewest warps per row (ties go to the narrower block)
+    int bx = BX;
+    if (fusex) {
+      const int h2 = 2 * recon_xhalo<RECON>();
+      const int w128 = ((nx + (128 - h2) - 1) / (128 - h2)) * 4, w192 = ((nx + (192 - h2) - 1) / (192 - h2)) * 6;
+      if (w192 < w128) bx = 192;
+    }
+    const int use = fusex ? bx - 2 * recon_xhalo<RECON>() : BX;
     int npen = D.end[dir] - D.beg[dir] + 1;
     int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
     int nbx = (nx + use - 1) / use;
     // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks
-    long want = 148L * 3 * 6;
+    long want = 148L * (bx == 192 ? 2 : 3) * 6;
     int nchunk = 1;
     while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
     int chunk = (npen + nchunk - 1) / nchunk;
@@ -57,7 +64,17 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     dim3 grid(nbx, ntr, nchunk);
     const bool cdt_in = D.ndim > 1 && a.stage == 1 && !fusex;
     const int nq = ring_nq(NV, fusex, a.comb, cdt_in);
-    if (fusex && !last) {
+    if (fusex && !last && bx == 192) {
+      auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM, BF, 192>;
+      size_t shm = sweep_smem_bytes<true, NV, RECON, 192>(nq);
+      set_smem(k, shm);
+      k<<<grid, 192, shm, c->stream>>>(D, a, chunk);
+    } else if (fusex && bx == 192) {
+      auto k = sweep_fused<1, true, true, NV, RECON, SOLVER, LIM, BF, 192>;
+      size_t shm = sweep_smem_bytes<true, NV, RECON, 192>(nq);
+      set_smem(k, shm);
+      k<<<grid, 192, shm, c->stream>>>(D, a, chunk);
+    } else if (fusex && !last) {
       auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM, BF>;
       size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
       set_smem(k, shm);
