@@ -399,6 +399,7 @@ static int stage_args(pb200_ctx *c, int stage, SweepArgs &a) {
   a.red = c->d_red;
   a.stage = stage;
   a.limiter = c->cfg.limiter;
+  a.i0 = 0;
   a.comb = 0; a.w0 = 0.0; a.wc = 1.0;
   if (stage == 2) {  // rk_step.c:18-24
     a.comb = 1;

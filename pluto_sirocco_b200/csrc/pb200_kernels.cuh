@@ -65,6 +65,7 @@ struct SweepArgs {
   int comb;    // 0: U ; 1: w0*U0 + wc*U (rk_step.c:236) ; 2: (U0 + 2U)/3 (rk_step.c:304)
   int stage;   // g_intStage
   int limiter;
+  int i0;      // first interior zone (relative to IBEG) of this launch of the fused kernel
 };
 
 // local (sweep) component c=1,2,3 -> global velocity variable, Src/set_indexes.c:18-110
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   extern __shared__ double smem[];
 
   const int t = threadIdx.x;
-  const int i = d.beg[0] + blockIdx.x * USE + t - LO;
+  const int i = d.beg[0] + a.i0 + blockIdx.x * USE + t - LO;
   const bool own = (t >= LO) && (t < BXT - HI) && (i <= d.end[0]);
   const int ic = min(max(i, 0), d.tot[0] - 1);
   const int tr = blockIdx.y;  // transverse index (k for x2 sweeps, j for x3 sweeps)

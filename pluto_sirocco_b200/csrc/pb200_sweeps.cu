@@ -44,47 +44,62 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
     const bool fusex = (dir == 1);
     const bool last = (dir == D.ndim - 1);
-    // block width of the fused kernel: fewest warps per row (ties go to the narrower block)
-    int bx = BX;
-    if (fusex) {
-      const int h2 = 2 * recon_xhalo<RECON>();
-      const int w128 = ((nx + (128 - h2) - 1) / (128 - h2)) * 4, w192 = ((nx + (192 - h2) - 1) / (192 - h2)) * 6;
-      if (w192 < w128) bx = 192;
-    }
-    const int use = fusex ? bx - 2 * recon_xhalo<RECON>() : BX;
     int npen = D.end[dir] - D.beg[dir] + 1;
     int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
-    int nbx = (nx + use - 1) / use;
-    // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks
-    long want = 148L * (bx == 192 ? 2 : 3) * 6;
-    int nchunk = 1;
-    while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
-    int chunk = (npen + nchunk - 1) / nchunk;
-    nchunk = (npen + chunk - 1) / chunk;
-    dim3 grid(nbx, ntr, nchunk);
     const bool cdt_in = D.ndim > 1 && a.stage == 1 && !fusex;
     const int nq = ring_nq(NV, fusex, a.comb, cdt_in);
-    if (fusex && !last && bx == 192) {
-      auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM, BF, 192>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON, 192>(nq);
-      set_smem(k, shm);
-      k<<<grid, 192, shm, c->stream>>>(D, a, chunk);
-    } else if (fusex && bx == 192) {
-      auto k = sweep_fused<1, true, true, NV, RECON, SOLVER, LIM, BF, 192>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON, 192>(nq);
-      set_smem(k, shm);
-      k<<<grid, 192, shm, c->stream>>>(D, a, chunk);
-    } else if (fusex && !last) {
-      auto k = sweep_fused<1, true, false, NV, RECON, SOLVER, LIM, BF>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
-      set_smem(k, shm);
-      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
-    } else if (fusex) {
-      auto k = sweep_fused<1, true, true, NV, RECON, SOLVER, LIM, BF>;
-      size_t shm = sweep_smem_bytes<true, NV, RECON>(nq);
-      set_smem(k, shm);
-      k<<<grid, BX, shm, c->stream>>>(D, a, chunk);
+    // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks
+    auto chunks = [&](int nbx, int resident, int &chunk) {
+      long want = 148L * resident * 6;
+      int nchunk = 1;
+      while ((long)nbx * ntr * nchunk < want && npen / (nchunk * 2) >= 32) nchunk *= 2;
+      chunk = (npen + nchunk - 1) / nchunk;
+      return (npen + chunk - 1) / chunk;
+    };
+    if (fusex) {
+      // The fused kernel loses 2*XH threads per block to the x1 halo.  Cover the row with blocks of
+      // 128, 160 and 192 threads so that the FEWEST WARPS run (512 zones, PLM: 2x192 + 1x160 = 17
+      // warps instead of 5x128 = 20); one launch per block width, at its x1 offset.
+      const int h2 = 2 * recon_xhalo<RECON>();
+      const int W[3] = {192, 160, 128};
+      int best[3] = {0, 0, (nx + 128 - h2 - 1) / (128 - h2)}, bestw = best[2] * 4;
+      for (int n0 = 0; n0 * (192 - h2) < nx + (192 - h2); n0++)
+        for (int n1 = 0; n0 * (192 - h2) + n1 * (160 - h2) < nx + (160 - h2); n1++) {
+          int rest = nx - n0 * (192 - h2) - n1 * (160 - h2);
+          int n2 = rest > 0 ? (rest + 128 - h2 - 1) / (128 - h2) : 0;
+          int w = n0 * 6 + n1 * 5 + n2 * 4;
+          if (w < bestw || (w == bestw && n0 + n1 + n2 < best[0] + best[1] + best[2])) {
+            bestw = w; best[0] = n0; best[1] = n1; best[2] = n2;
+          }
+        }
+      SweepArgs b = a;
+      b.i0 = 0;
+      for (int g = 0; g < 3; g++) {
+        if (!best[g]) continue;
+        int chunk;
+        const int nchunk = chunks(best[g], W[g] == 128 ? 3 : 2, chunk);
+        dim3 grid(best[g], ntr, nchunk);
+#define PB_LAUNCH_FUSED(LASTF, WIDTH)                                                        \
+  {                                                                                          \
+    auto k = sweep_fused<1, true, LASTF, NV, RECON, SOLVER, LIM, BF, WIDTH>;                 \
+    size_t shm = sweep_smem_bytes<true, NV, RECON, WIDTH>(nq);                               \
+    set_smem(k, shm);                                                                        \
+    k<<<grid, WIDTH, shm, c->stream>>>(D, b, chunk);                                         \
+  }
+        if (last) {
+          if (W[g] == 192) PB_LAUNCH_FUSED(true, 192) else if (W[g] == 160) PB_LAUNCH_FUSED(true, 160) else PB_LAUNCH_FUSED(true, 128)
+        } else {
+          if (W[g] == 192) PB_LAUNCH_FUSED(false, 192) else if (W[g] == 160) PB_LAUNCH_FUSED(false, 160) else PB_LAUNCH_FUSED(false, 128)
+        }
+#undef PB_LAUNCH_FUSED
+        b.i0 += best[g] * (W[g] - h2);
+        c->launches++;
+      }
+      c->launches--;   // the common exit counts one
     } else {
+      int chunk;
+      const int nchunk = chunks((nx + BX - 1) / BX, 3, chunk);
+      dim3 grid((nx + BX - 1) / BX, ntr, nchunk);
       auto k = sweep_fused<2, false, true, NV, RECON, SOLVER, LIM, BF>;
       size_t shm = sweep_smem_bytes<false, NV, RECON>(nq);
       set_smem(k, shm);
