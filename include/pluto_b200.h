@@ -193,8 +193,16 @@ int  pb200_boundary(pb200_ctx *ctx);
 int  pb200_advance_step(pb200_ctx *ctx, double dt, pb200_step_info *info);
 
 /* Same call on HOST buffers (the strict drop-in: d->Vc is authoritative on the host):
- * H2D of vc_host, AdvanceStep, D2H back into vc_host. */
+ * H2D of vc_host, AdvanceStep, D2H back into vc_host.  For 3-D RK2 runs on the Cartesian path with
+ * non-periodic x3 sides the three phases are pipelined over slabs of x3 planes (upload of slab
+ * s+1, both stages on the slabs that are ready, download of finished slabs all overlap), so the
+ * call costs about one PCIe direction; results are identical to pb200_advance_step().  Ghost zones
+ * of vc_host are not written back.  PB200_HOST_PIPELINE=<planes per slab> (0: off). */
 int  pb200_advance_step_host(pb200_ctx *ctx, double *vc_host, double dt, pb200_step_info *info);
+/* cudaHostRegister / cudaHostUnregister of a caller-owned buffer (the reference's d->Vc payload):
+ * page-locked memory makes the copies above asynchronous and full speed. */
+int  pb200_host_register(void *ptr, size_t bytes);
+int  pb200_host_unregister(void *ptr);
 
 /* NextTimeStep() (Src/main.c:521-697) for COOLING NO, no parabolic terms.
  * Returns the new g_dt, or a negative value if dt < first_dt*1e-9 ("dt is too small"). */

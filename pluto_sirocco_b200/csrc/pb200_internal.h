@@ -27,6 +27,9 @@ struct pb200_ctx {
   double *d_bf[7];   // body-force tables (Dev::bf_tab)
   std::vector<double> xl[3], xr[3], dx[3];
   cudaStream_t stream;
+  cudaStream_t h2d, d2h;        // copy streams of the slab-wise host pipeline (pb200_advance_step_host)
+  cudaEvent_t ev_up[64], ev_done[64];
+  int host_pipeline;            // x3 planes per slab of that pipeline, 0: plain copy - step - copy
   cudaEvent_t ev0, ev1;
   int launches;
   int cur;           // index of the array holding d->Vc

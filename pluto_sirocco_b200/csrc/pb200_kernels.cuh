@@ -66,6 +66,7 @@ struct SweepArgs {
   int stage;   // g_intStage
   int limiter;
   int i0;      // first interior zone (relative to IBEG) of this launch of the fused kernel
+  int k0, k1;  // x3 planes [k0, k1) relative to KBEG covered by this launch (slab-wise host pipeline); 3-D
 };
 
 // local (sweep) component c=1,2,3 -> global velocity variable, Src/set_indexes.c:18-110
@@ -342,11 +343,11 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   const int i = d.beg[0] + a.i0 + blockIdx.x * USE + t - LO;
   const bool own = (t >= LO) && (t < BXT - HI) && (i <= d.end[0]);
   const int ic = min(max(i, 0), d.tot[0] - 1);
-  const int tr = blockIdx.y;  // transverse index (k for x2 sweeps, j for x3 sweeps)
+  const int tr = blockIdx.y + ((DIR == 1 && d.ndim == 3) ? a.k0 : 0);  // transverse index (k for x2 sweeps, j for x3 sweeps)
   const long st = (DIR == 1) ? d.sj : d.sk;
   const long base = (DIR == 1) ? ((long)(d.beg[2] + tr) * d.sk + ic) : ((long)(d.beg[1] + tr) * d.sj + ic);
-  const int cb = d.beg[DIR] + blockIdx.z * chunk;
-  const int ce = min(cb + chunk - 1, d.end[DIR]);
+  const int cb = d.beg[DIR] + (DIR == 2 ? a.k0 : 0) + blockIdx.z * chunk;
+  const int ce = min(cb + chunk - 1, DIR == 2 ? d.beg[2] + a.k1 - 1 : d.end[DIR]);
   const double dt = *a.dt;
   const double *__restrict__ inv_dx = d.inv_dx[DIR];
   const int lim = a.limiter;
@@ -646,6 +647,7 @@ struct BcArgs {
   int nvar;
   int nghost;
   double sign[16];
+  int k0, k1;     // restrict the fill of an x1 / x2 side to the x3 planes [k0, k1) (absolute indices)
 };
 
 static __global__ void bc_fill(Dev d, BcArgs b) {
@@ -654,13 +656,15 @@ static __global__ void bc_fill(Dev d, BcArgs b) {
   // extents of the ghost box: nghost layers along dir, full transverse range
   int ext[3] = {d.tot[0], d.tot[1], d.tot[2]};
   ext[dir] = b.nghost;
+  const int koff = dir < 2 ? b.k0 : 0;
+  if (dir < 2) ext[2] = b.k1 - b.k0;
   long ntot = (long)ext[0] * ext[1] * ext[2];
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ntot) return;
   int c[3];
   c[0] = (int)(idx % ext[0]);
   c[1] = (int)((idx / ext[0]) % ext[1]);
-  c[2] = (int)(idx / ((long)ext[0] * ext[1]));
+  c[2] = (int)(idx / ((long)ext[0] * ext[1])) + koff;
   const int g = c[dir];
   const int nb = d.beg[dir], ne = d.end[dir], nx = ne - nb + 1;
   const int n = hi ? ne + 1 + g : nb - 1 - g;

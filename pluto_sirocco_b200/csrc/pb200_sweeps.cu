@@ -27,6 +27,7 @@ static void set_smem(K k, size_t shm) {
 template <int NV, int RECON, int SOLVER, int LIM, int BF>
 static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   const Dev &D = c->dev;
+  cudaStream_t stream = c->stream;
   const int slot = (c->profiling && c->nprof < 16) ? c->nprof++ : -1;
   if (slot >= 0) {
     if (!c->pev0[slot]) { cudaEventCreate(&c->pev0[slot]); cudaEventCreate(&c->pev1[slot]); }
@@ -44,8 +45,10 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
     // dir 1: x1+x2 fused march along x2 ; dir 2: x3 march
     const bool fusex = (dir == 1);
     const bool last = (dir == D.ndim - 1);
-    int npen = D.end[dir] - D.beg[dir] + 1;
-    int ntr = (dir == 1) ? (D.end[2] - D.beg[2] + 1) : (D.end[1] - D.beg[1] + 1);
+    // a launch covers the x3 planes [k0, k1) (all of them except in the slab-wise host pipeline)
+    const int nk = (D.ndim == 3) ? a.k1 - a.k0 : 1;
+    int npen = (dir == 2) ? nk : (D.end[dir] - D.beg[dir] + 1);
+    int ntr = (dir == 1) ? nk : (D.end[1] - D.beg[1] + 1);
     const bool cdt_in = D.ndim > 1 && a.stage == 1 && !fusex;
     const int nq = ring_nq(NV, fusex, a.comb, cdt_in);
     // chunk the pencil so that the grid holds several waves of 148 SMs x resident blocks

@@ -261,6 +261,8 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
 
   if (s_ctx == NULL) {
     shim_init(d, grid);
+    /* page-lock the contiguous payload of d->Vc (ARRAY_4D, Src/arrays.c:251-330) for the copies */
+    pb200_host_register(vc, (size_t)NVAR*NX3_TOT*NX2_TOT*NX1_TOT*sizeof(double));
     if (s_resident) pb200_upload_vc(s_ctx, vc);
   }
   if (s_host_bc) {
