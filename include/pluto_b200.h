@@ -185,7 +185,9 @@ int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);
 /* device pointer of the current d->Vc mirror (for torch / NCCL interop, zero copy) */
 double *pb200_device_vc(pb200_ctx *ctx);
 
-/* Boundary(d, 0, grid) on the device mirror (Src/boundary.c:56) */
+/* Boundary(d, 0, grid) on the device mirror (Src/boundary.c:56).  On the Cartesian 2-D/3-D path the x1
+ * ghost zones of standard sides (outflow, reflective-type, periodic) are never materialised: the sweep
+ * kernels map them at load time, so ghost zones of a downloaded array are scratch. */
 int  pb200_boundary(pb200_ctx *ctx);
 
 /* AdvanceStep(d, Dts, grid) with g_dt = dt  (Src/Time_Stepping/rk_step.c:29) on the

@@ -169,6 +169,20 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   }
   D.bf_kind = cfg->body_force;
   for (int q = 0; q < 7; q++) { D.bf_tab[q] = nullptr; c->d_bf[q] = nullptr; }
+  // PB200_FUSE_BC=0: materialise the x1 ghost zones with bc_fill instead of mapping them at load time.
+  // (Writing the x2/x3 ghost copies from the x3 sweep's store was tried too: it removes four more
+  // launches but slows the HBM-bound x3 kernel by 5 %, a net loss.)
+  bool fuse_env = true;
+  if (const char *p = getenv("PB200_FUSE_BC")) fuse_env = atoi(p) != 0;
+  c->fuse_bc = 0;
+  for (int k = 0; k < 3; k++) c->ghosts_ok[k] = false;
+  D.nghost = cfg->nghost;
+  for (int s = 0; s < 6; s++) {
+    int t = cfg->bc[s];
+    const bool on = s < 2 ? (!gen && D.ndim >= 2 && fuse_env) : (c->fuse_bc != 0);   // x1: virtual ghosts in 2-D and 3-D
+    D.bc_fuse[s] = (on && s < 2 * D.ndim && (t == PB200_BC_OUTFLOW || t == PB200_BC_REFLECTIVE || t == PB200_BC_AXISYMMETRIC ||
+                                   t == PB200_BC_EQTSYMMETRIC || t == PB200_BC_PERIODIC)) ? t : 0;
+  }
   c->h2d = c->d2h = nullptr;
   for (int k = 0; k < 64; k++) c->ev_up[k] = c->ev_done[k] = nullptr;
   c->host_pipeline = 16;   // measured on 512^3: 16 planes per slab gives the best overlap (1.02 vs 0.61 Gzones/s unpipelined)
@@ -260,6 +274,7 @@ extern "C" int pb200_upload_vc(pb200_ctx *c, const double *h) {
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpyAsync(c->V[c->cur], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->ghosts_ok[c->cur] = false;
   return PB200_OK;
 }
 extern "C" int pb200_download_vc(pb200_ctx *c, double *h) {
@@ -293,6 +308,7 @@ static int boundary_on(pb200_ctx *c, double *V, unsigned sides = 0x3f, int k0 = 
       continue;
     }
     if (type == PB200_BC_NEIGHBOUR || type == 0 || !(sides & (1u << side))) continue;
+    if (side < 2 && D.bc_fuse[side]) continue;    // x1 ghosts are virtual in the fused x1+x2 kernel
     BcArgs b;
     b.k0 = k0; b.k1 = k1;
     b.V = V;
@@ -390,6 +406,7 @@ extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
   if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
   CK(cudaMemcpyAsync(c->V[c->stage_in[stage]], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->ghosts_ok[c->stage_in[stage]] = false;
   return PB200_OK;
 }
 
@@ -427,6 +444,8 @@ extern "C" int pb200_stage_boundary(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
+  // 3-D fast path: the x3 sweep that produced this array already wrote its physical ghost layers
+  if (c->fuse_bc && c->ghosts_ok[c->stage_in[stage]]) return PB200_OK;
   c->cur_stage = stage;
   rc = boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
   c->cur_stage = 0;
@@ -455,6 +474,7 @@ extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
   if (D.ndim == 1) launch_sweep(c, 0, a);
   else if (D.ndim == 2) launch_sweep(c, 1, a);    // x1 + x2 (reads the x2 ghosts)
   else launch_sweep(c, 2, a);                     // x3
+  c->ghosts_ok[c->stage_out[stage]] = c->fuse_bc != 0;
   CK(cudaGetLastError());
   return PB200_OK;
 }
@@ -543,6 +563,7 @@ static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200
   }
   int rc = pb200_step_begin(c, dt);
   if (rc) return rc;
+  for (int k = 0; k < 3; k++) c->ghosts_ok[k] = false;     // this path fills its ghosts slab by slab
   double *A = c->V[c->stage_in[1]], *B = c->V[c->stage_out[1]];
   const size_t plane = (size_t)D.sk;
   auto kbeg = [&](int s) { return s == 0 ? 0 : D.beg[2] + rel0(s); };                // absolute planes of slab s,
@@ -613,6 +634,7 @@ extern "C" int pb200_advance_step_host(pb200_ctx *c, double *vc_host, double dt,
       return advance_step_host_pipelined(c, vc_host, dt, info);
   }
   CK(cudaMemcpyAsync(c->V[c->cur], vc_host, c->vbytes, cudaMemcpyHostToDevice, c->stream));
+  c->ghosts_ok[c->cur] = false;
   int rc = pb200_advance_step(c, dt, info);
   if (rc) return rc;
   CK(cudaMemcpyAsync(vc_host, c->V[c->cur], c->vbytes, cudaMemcpyDeviceToHost, c->stream));

@@ -33,6 +33,8 @@ struct pb200_ctx {
   cudaEvent_t ev0, ev1;
   int launches;
   int cur;           // index of the array holding d->Vc
+  bool ghosts_ok[3]; // V[k]: the physical ghost layers were written by the sweep that produced it
+  int fuse_bc;       // 3-D fast path: fuse Boundary() into the x3 sweep's store (PB200_FUSE_BC=0 switches off)
   int nstages;
   int stage_in[4], stage_out[4];  // array indices per stage (1-based)
   bool in_step;

@@ -44,6 +44,9 @@ struct Dev {
   // (indices incl. ghosts; stride 0 = independent of that coordinate).
   //   bf_kind & 1 (VECTOR):    tab[0..2] = g[IDIR], g[JDIR], g[KDIR] at zone centres
   //   bf_kind & 2 (POTENTIAL): tab[3] = Phi at zone centres, tab[4+d] = Phi at the x_d upper face
+  // x1 boundary types (0 = none / neighbour / userdef) for the VIRTUAL x1 ghost zones of the fused
+  // x1+x2 kernel; entries 2..5 are unused
+  int bc_fuse[6], nghost;
   int bf_kind;
   const double *bf_tab[7];
   long bf_st[7][3];
@@ -325,6 +328,9 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
          sizeof(double);
 }
 
+enum BcType { BC_NONE = 0, BC_OUTFLOW = 1, BC_REFLECTIVE = 2, BC_AXISYMMETRIC = 3,
+              BC_EQTSYMMETRIC = 4, BC_PERIODIC = 5, BC_USERDEF = 8, BC_NEIGHBOUR = 100 };
+
 // BXT: threads per block.  The fused x1+x2 kernel loses 2*XH threads per block to the x1 halo, so
 // on a 512-wide grid 128-thread blocks need 5 blocks (20 warps) per row where 192-thread blocks
 // need 3 (18 warps): the launcher picks the width that runs the fewest warps.
@@ -345,7 +351,20 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   const int ic = min(max(i, 0), d.tot[0] - 1);
   const int tr = blockIdx.y + ((DIR == 1 && d.ndim == 3) ? a.k0 : 0);  // transverse index (k for x2 sweeps, j for x3 sweeps)
   const long st = (DIR == 1) ? d.sj : d.sk;
-  const long base = (DIR == 1) ? ((long)(d.beg[2] + tr) * d.sk + ic) : ((long)(d.beg[1] + tr) * d.sj + ic);
+  // x1 ghost zones are VIRTUAL in the fused kernel: a halo thread loads the zone Boundary() would have
+  // copied into its ghost (outflow: the edge zone, reflective-type: the mirror zone with v_x1 flipped
+  // after landing, periodic: the wrapped zone), so the x1 sides need no fill kernel at all
+  int isrc = ic;
+  bool xflip = false;
+  if (FUSEX && (i < d.beg[0] || i > d.end[0])) {
+    const int hi = i > d.end[0], type = d.bc_fuse[hi];
+    const int nb = d.beg[0], ne = d.end[0], nx1 = ne - nb + 1;
+    if (type == BC_OUTFLOW) isrc = hi ? ne : nb;
+    else if (type == BC_PERIODIC) isrc = hi ? i - nx1 : i + nx1;
+    else if (type != 0) { isrc = hi ? 2 * ne + 1 - i : 2 * nb - 1 - i; xflip = true; }
+    isrc = min(max(isrc, 0), d.tot[0] - 1);
+  }
+  const long base = (DIR == 1) ? ((long)(d.beg[2] + tr) * d.sk + isrc) : ((long)(d.beg[1] + tr) * d.sj + isrc);
   const int cb = d.beg[DIR] + (DIR == 2 ? a.k0 : 0) + blockIdx.z * chunk;
   const int ce = min(cb + chunk - 1, DIR == 2 ? d.beg[2] + a.k1 - 1 : d.end[DIR]);
   const double dt = *a.dt;
@@ -433,6 +452,10 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   for (int n = n0; n <= ce + 1; n++) {
     // ---- data of this iteration has landed in the ring; refill the slot DEPTH ahead ----
     cp_async_wait<DEPTH - 1>();
+    if (FUSEX && xflip) {    // mirror ghost: flip v_x1 of the row that just landed (once per row)
+      double *w = ring + sc * slot_sz + lvar<DIR>(1) * BXT;
+      *w = -*w;
+    }
     const double *slot = ring + sc * slot_sz;
     double vin[NV];
 #pragma unroll
@@ -637,8 +660,6 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
 // ------------------------------------------------------------------------------------
 //  physical boundaries  (Src/boundary.c:228-459 dispatch, :617-767 fills, :503 FlipSign)
 // ------------------------------------------------------------------------------------
-enum BcType { BC_NONE = 0, BC_OUTFLOW = 1, BC_REFLECTIVE = 2, BC_AXISYMMETRIC = 3,
-              BC_EQTSYMMETRIC = 4, BC_PERIODIC = 5, BC_USERDEF = 8, BC_NEIGHBOUR = 100 };
 
 struct BcArgs {
   double *V;

@@ -265,6 +265,32 @@ def test_pipelined_host_call_equals_resident_call_3d(Hydro, monkeypatch, recon, 
     h1.close(); h2.close()
 
 
+@pytest.mark.parametrize("recon,rk", [("LINEAR", "RK2"), ("PARABOLIC", "RK3")])
+@pytest.mark.parametrize("bcs", [("reflective", "outflow", "outflow", "reflective", "periodic", "periodic"),
+                                 ("periodic", "periodic", "reflective", "reflective", "outflow", "reflective"),
+                                 ("outflow",) * 6])
+def test_fused_boundaries_equal_boundary_kernels(Hydro, monkeypatch, recon, rk, bcs):
+    """The fused x1+x2 kernel maps the x1 ghost zones at load time (outflow / mirror / periodic source
+    zone, v_x1 flipped for mirrors) instead of reading ghosts materialised by bc_fill: same interior
+    states, two launches fewer per stage."""
+    nx = (37, 21, 26)
+    kw = dict(dimensions=3, nx=nx, gamma=1.4, reconstruction=recon, time_stepping=rk, bcs=bcs, ntracer=1)
+    v = _state_with_tracers((nx[2], nx[1], nx[0]), 1, seed=21)
+    out, launches = [], []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("PB200_FUSE_BC", fuse)
+        h = Hydro(**kw)
+        h.set_interior(v)
+        n = 0
+        for _ in range(4):
+            info = h.advance_step(3e-4)
+            n += info.launches
+        out.append(h.get_interior()); launches.append(n)
+        h.close()
+    assert launches[0] < launches[1]                 # the fused run skipped bc_fill launches
+    assert np.array_equal(out[0], out[1])
+
+
 def test_errors(Hydro):
     from pluto_sirocco_b200._lib import ENAN, PB200Error
     with pytest.raises(ValueError):
