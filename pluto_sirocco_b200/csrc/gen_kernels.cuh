@@ -52,7 +52,6 @@ struct GenDev {
   const double *A[3];                  // grid->A[d], one extra layer at index -1 along d
   long Aoff[3], Asj[3], Ask[3];
   const double *dx_dl[3];              // grid->dx_dl[d][j][i]
-  const double *gline;                 // unused (kept for layout stability)
   LdwDev ldw;
 };
 

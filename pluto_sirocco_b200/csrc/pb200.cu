@@ -95,8 +95,6 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->gen = gen;
   c->gen_ready = false;
   c->gdev = nullptr;
-  c->gline = nullptr;
-  c->ldw_hook = nullptr;
   c->ldw_on = false;
   c->cur_stage = 0;
   for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
@@ -174,12 +172,10 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   // launches but slows the HBM-bound x3 kernel by 5 %, a net loss.)
   bool fuse_env = true;
   if (const char *p = getenv("PB200_FUSE_BC")) fuse_env = atoi(p) != 0;
-  c->fuse_bc = 0;
-  for (int k = 0; k < 3; k++) c->ghosts_ok[k] = false;
   D.nghost = cfg->nghost;
   for (int s = 0; s < 6; s++) {
     int t = cfg->bc[s];
-    const bool on = s < 2 ? (!gen && D.ndim >= 2 && fuse_env) : (c->fuse_bc != 0);   // x1: virtual ghosts in 2-D and 3-D
+    const bool on = s < 2 && !gen && D.ndim >= 2 && fuse_env;   // x1: virtual ghosts in 2-D and 3-D
     D.bc_fuse[s] = (on && s < 2 * D.ndim && (t == PB200_BC_OUTFLOW || t == PB200_BC_REFLECTIVE || t == PB200_BC_AXISYMMETRIC ||
                                    t == PB200_BC_EQTSYMMETRIC || t == PB200_BC_PERIODIC)) ? t : 0;
   }
@@ -274,7 +270,6 @@ extern "C" int pb200_upload_vc(pb200_ctx *c, const double *h) {
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpyAsync(c->V[c->cur], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->ghosts_ok[c->cur] = false;
   return PB200_OK;
 }
 extern "C" int pb200_download_vc(pb200_ctx *c, double *h) {
@@ -406,7 +401,6 @@ extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
   if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
   CK(cudaMemcpyAsync(c->V[c->stage_in[stage]], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->ghosts_ok[c->stage_in[stage]] = false;
   return PB200_OK;
 }
 
@@ -444,8 +438,6 @@ extern "C" int pb200_stage_boundary(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
-  // 3-D fast path: the x3 sweep that produced this array already wrote its physical ghost layers
-  if (c->fuse_bc && c->ghosts_ok[c->stage_in[stage]]) return PB200_OK;
   c->cur_stage = stage;
   rc = boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
   c->cur_stage = 0;
@@ -474,7 +466,6 @@ extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
   if (D.ndim == 1) launch_sweep(c, 0, a);
   else if (D.ndim == 2) launch_sweep(c, 1, a);    // x1 + x2 (reads the x2 ghosts)
   else launch_sweep(c, 2, a);                     // x3
-  c->ghosts_ok[c->stage_out[stage]] = c->fuse_bc != 0;
   CK(cudaGetLastError());
   return PB200_OK;
 }
@@ -563,7 +554,6 @@ static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200
   }
   int rc = pb200_step_begin(c, dt);
   if (rc) return rc;
-  for (int k = 0; k < 3; k++) c->ghosts_ok[k] = false;     // this path fills its ghosts slab by slab
   double *A = c->V[c->stage_in[1]], *B = c->V[c->stage_out[1]];
   const size_t plane = (size_t)D.sk;
   auto kbeg = [&](int s) { return s == 0 ? 0 : D.beg[2] + rel0(s); };                // absolute planes of slab s,
@@ -634,7 +624,6 @@ extern "C" int pb200_advance_step_host(pb200_ctx *c, double *vc_host, double dt,
       return advance_step_host_pipelined(c, vc_host, dt, info);
   }
   CK(cudaMemcpyAsync(c->V[c->cur], vc_host, c->vbytes, cudaMemcpyHostToDevice, c->stream));
-  c->ghosts_ok[c->cur] = false;
   int rc = pb200_advance_step(c, dt, info);
   if (rc) return rc;
   CK(cudaMemcpyAsync(vc_host, c->V[c->cur], c->vbytes, cudaMemcpyDeviceToHost, c->stream));

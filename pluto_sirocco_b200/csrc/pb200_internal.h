@@ -33,8 +33,6 @@ struct pb200_ctx {
   cudaEvent_t ev0, ev1;
   int launches;
   int cur;           // index of the array holding d->Vc
-  bool ghosts_ok[3]; // V[k]: the physical ghost layers were written by the sweep that produced it
-  int fuse_bc;       // 3-D fast path: fuse Boundary() into the x3 sweep's store (PB200_FUSE_BC=0 switches off)
   int nstages;
   int stage_in[4], stage_out[4];  // array indices per stage (1-based)
   bool in_step;
@@ -51,8 +49,6 @@ struct pb200_ctx {
   unsigned short *gflag;
   unsigned char *gshock;
   std::vector<void *> gen_allocs;
-  double *gline;
-  void (*ldw_hook)(pb200_ctx *, int stage);
   // line-driven wind
   bool ldw_on;
   pb200_ldw_config ldw;
