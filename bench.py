@@ -175,7 +175,9 @@ def reference_rate(cfg, n, nproc, warm, steps, solver="hllc"):
 
     ta = launch(warm)
     tb = launch(warm + steps)
-    dt = max(tb - ta, 1e-9)
+    dt = tb - ta
+    if dt < 0.05 * tb:      # too short to difference reliably: charge the whole second run to its steps
+        dt = tb * steps / float(warm + steps)
     return nproc * n ** 3 * steps / dt / 1e6, dt
 
 
