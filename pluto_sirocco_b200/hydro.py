@@ -467,12 +467,17 @@ class Hydro:
 #  Simulation: the reference's main() time loop around Hydro
 # --------------------------------------------------------------------------------------
 class Simulation:
-    """main() loop of Src/main.c:215-337 for COOLING NO: clip dt at tstop, AdvanceStep,
-    g_time += g_dt, g_dt = NextTimeStep, g_stepNumber++."""
+    """main() loop of Src/main.c:215-337: clip dt at tstop, Integrate, g_time += g_dt,
+    g_dt = NextTimeStep, g_stepNumber++.  With cooling=True (COOLING BLONDIN) Integrate alternates
+    AdvanceStep / SplitSource (even steps: hydro then source, odd steps: source then hydro,
+    Src/main.c:479-485), the time-step accumulators are reset only every second step
+    (Src/main.c:406-415) and NextTimeStep runs every second step (Src/main.c:326-330)."""
 
-    def __init__(self, hydro: Hydro, runtime: Runtime):
+    def __init__(self, hydro: Hydro, runtime: Runtime, cooling: bool = False):
         self.h = hydro
         self.rt = runtime
+        self.cooling = cooling
+        self._invDt = 0.0
         self.g_time = 0.0
         self.g_dt = runtime.first_dt
         self.g_stepNumber = 0
@@ -487,11 +492,31 @@ class Simulation:
             self.g_dt = rt.tstop - self.g_time
             last = True
         self.history.append((self.g_stepNumber, self.g_time, self.g_dt))
-        info = self.h.advance_step(self.g_dt)
+        if not self.cooling:
+            info = self.h.advance_step(self.g_dt)
+            self.g_maxMach = info.maxMach
+            self.g_time += self.g_dt
+            self.g_dt = self.h.next_time_step(info.invDt_hyp, rt.cfl, rt.cfl_max_var, self.g_dt,
+                                              rt.first_dt)
+            self.g_stepNumber += 1
+            return last
+        n = self.g_stepNumber
+        if (n - 1) % 2 == 1:               # Dts->invDt_hyp = 0 only every second step
+            self._invDt = 0.0
+        if n % 2 == 0:
+            info = self.h.advance_step(self.g_dt)
+            self.h.split_source(self.g_dt, self.g_time)
+        else:
+            self.h.split_source(self.g_dt, self.g_time)
+            info = self.h.advance_step(self.g_dt)
         self.g_maxMach = info.maxMach
+        # UpdateStage divides the running maximum by DIMENSIONS on EVERY call (update_stage.c:391-392),
+        # so the first step's contribution of a pair is divided twice
+        nd = float(self.h.dimensions) if self.h.dimensions > 1 else 1.0
+        self._invDt = max(self._invDt / nd, info.invDt_hyp) if self._invDt > 0.0 else info.invDt_hyp
         self.g_time += self.g_dt
-        self.g_dt = self.h.next_time_step(info.invDt_hyp, rt.cfl, rt.cfl_max_var, self.g_dt,
-                                          rt.first_dt)
+        if n % 2 == 1:
+            self.g_dt = self.h.next_time_step(self._invDt, rt.cfl, rt.cfl_max_var, self.g_dt, rt.first_dt)
         self.g_stepNumber += 1
         return last
 

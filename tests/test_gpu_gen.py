@@ -239,3 +239,26 @@ def test_blondin_cooling_vs_oracle_with_tables(Hydro):
         assert relp.max() <= 2e-4, relp.max()
         assert (relp > 1e-11).mean() <= 0.005, (relp > 1e-11).mean()
     h.close(); o.close()
+
+
+def test_ldw_cooling_main_loop_reproduces_reference_dt_sequence(Hydro):
+    """Simulation(cooling=True) mirrors Integrate / NextTimeStep with COOLING != NO (Strang order, dt
+    renewed every second step, the double division of invDt_hyp by DIMENSIONS across a pair of steps,
+    Src/main.c:326-330,406-415,479-485, update_stage.c:391-392): free-running from the first dump it
+    must reproduce the reference's (t, dt) records."""
+    from pluto_sirocco_b200 import Runtime, Simulation
+    g = load_golden("ldw_cool_hll")
+    kw = gen_kwargs_from_golden(g)
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    ldw_setup(h, h.x(0), h.x(1))
+    h.set_interior(_with_entr(g["data"][0], h.nvar))
+    sim = Simulation(h, Runtime(cfl=g["cfl"], cfl_max_var=g["cfl_max_var"], tstop=g["tstop"], first_dt=g["first_dt"]),
+                     cooling=True)
+    nsteps = len(g["data"]) - 1
+    sim.run(maxsteps=nsteps)
+    for (n, t, dt), ref in zip(sim.history, g["steps"]):
+        assert n == int(ref[0]) and abs(t - ref[1]) <= 1e-9 * max(ref[1], 1e-30) and abs(dt - ref[2]) <= 1e-7 * ref[2], (n, t, dt, ref)
+    got, ref = h.get_interior()[:6], g["data"][nsteps]
+    relp = np.abs(got[4] - ref[4]) / ref[4]
+    assert relp.max() <= 5e-4 and np.abs(got[0] - ref[0]).max() <= 1e-6 * np.abs(ref[0]).max()
+    h.close()
