@@ -12,5 +12,3 @@ try:
 except Exception as e: print("$name failed", e)
 PY
 done
-timeout 300 python bench.py --workload ldw --steps 50 --warmup 5 > $OUT/bench_ldw.json 2> $OUT/bench_ldw.err; cut -c1-200 $OUT/bench_ldw.json
-timeout 600 python -m pytest tests -m gpu -x -q -k "ldw" > $OUT/pytest.log 2>&1; tail -n 3 $OUT/pytest.log
