@@ -353,14 +353,15 @@ PB_D void gen_bilinear(const double (&x11)[2], const double (&x22)[2], const dou
   ans[1] = (1.0 - f2) * a + f2 * b;
 }
 
-// VGradCalc(), line_connect.c:504-744: one thread per (zone, angular bin); the offsets that the
-// reference tabulates once (dvds_r/t/mod_offset) are recomputed, they only depend on the grid
+// VGradCalc(), line_connect.c:504-744: one thread per zone, looping over the angular bins so that
+// everything that does not depend on the bin (vertex velocities, interpolation box, the velocity at
+// the cell centre) is computed once; the offsets that the reference tabulates once
+// (dvds_r/t/mod_offset) are recomputed, they only depend on the grid
 static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
   int i, j, k;
   if (!gen_zone(b.lo, b.hi, i, j, k)) return;
   const Dev &d = g.d;
   const LdwDev &w = g.ldw;
-  const int ia = blockIdx.y;
   const long o = (long)k * d.sk + (long)j * d.sj + i;
   const long sj = d.sj;
   const double *x1 = g.x[0], *x2 = g.x[1];
@@ -375,45 +376,47 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
   const double arc = x1i * w.UL * fabs(x22[1] - x11[1]);
   if (maxds > arc) maxds = arc;
   maxds /= 2.0;
-  const double fr = __ldg(w.flux_r + ia * d.sv + o), ft = __ldg(w.flux_t + ia * d.sv + o);
-  const double fp = w.flux_p ? __ldg(w.flux_p + ia * d.sv + o) : 0.0;
-  const double mod_flux = sqrt(fr * fr + ft * ft + fp * fp);
-  double out = -999.0;
-  if (mod_flux != 0.0) {
-    const double st = __ldg(w.sin_t + j), ct = __ldg(w.cos_t + j);
-    const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
-    v11[0] = (V1[o - sj - 1] + V1[o - sj] + V1[o - 1] + V1[o]) / 4.0;
-    v11[1] = (V2[o - sj - 1] + V2[o - sj] + V2[o - 1] + V2[o]) / 4.0;
-    v12[0] = (V1[o + sj - 1] + V1[o - 1] + V1[o + sj] + V1[o]) / 4.0;
-    v12[1] = (V2[o + sj - 1] + V2[o - 1] + V2[o + sj] + V2[o]) / 4.0;
-    v22[0] = (V1[o + sj] + V1[o + sj + 1] + V1[o + 1] + V1[o]) / 4.0;
-    v22[1] = (V2[o + sj] + V2[o + sj + 1] + V2[o + 1] + V2[o]) / 4.0;
-    v21[0] = (V1[o + 1] + V1[o - sj + 1] + V1[o - sj] + V1[o]) / 4.0;
-    v21[1] = (V2[o + 1] + V2[o - sj + 1] + V2[o - sj] + V2[o]) / 4.0;
-    gen_bilinear(x11, x22, v11, v12, v21, v22, x1i * w.UL, x2j, ans1);
-    const double vx1 = (ans1[0] * w.UV * st + ans1[1] * w.UV * ct);
-    const double vz1 = (ans1[0] * w.UV * ct - ans1[1] * w.UV * st);
-    const double x = x1i * st * w.UL, z = x1i * ct * w.UL;
-    const double dx1 = maxds * sa, dx2 = maxds * ca;
-    const double ds = sqrt(dx1 * dx1 + dx2 * dx2);
-    const double r_off = sqrt((x + dx1) * (x + dx1) + (z + dx2) * (z + dx2));
-    const double t_off = atan((x + dx1) / (z + dx2));
-    gen_bilinear(x11, x22, v11, v12, v21, v22, r_off, t_off, ans2);
-    // sin / cos of t_off = atan(q): q / sqrt(1 + q^2), 1 / sqrt(1 + q^2) (principal branch, cos > 0)
-    const double qq = (x + dx1) / (z + dx2);
-    const double co = 1.0 / sqrt(1.0 + qq * qq), so = qq * co;
-    const double vx2 = (ans2[0] * w.UV * so + ans2[1] * w.UV * co);
-    const double vz2 = (ans2[0] * w.UV * co - ans2[1] * w.UV * so);
-    const double v1 = sa * vx1 + ca * vz1;
-    const double v2 = sa * vx2 + ca * vz2;
-    out = fabs((v2 - v1) / ds);
+  const double st = __ldg(w.sin_t + j), ct = __ldg(w.cos_t + j);
+  v11[0] = (V1[o - sj - 1] + V1[o - sj] + V1[o - 1] + V1[o]) / 4.0;
+  v11[1] = (V2[o - sj - 1] + V2[o - sj] + V2[o - 1] + V2[o]) / 4.0;
+  v12[0] = (V1[o + sj - 1] + V1[o - 1] + V1[o + sj] + V1[o]) / 4.0;
+  v12[1] = (V2[o + sj - 1] + V2[o - 1] + V2[o + sj] + V2[o]) / 4.0;
+  v22[0] = (V1[o + sj] + V1[o + sj + 1] + V1[o + 1] + V1[o]) / 4.0;
+  v22[1] = (V2[o + sj] + V2[o + sj + 1] + V2[o + 1] + V2[o]) / 4.0;
+  v21[0] = (V1[o + 1] + V1[o - sj + 1] + V1[o - sj] + V1[o]) / 4.0;
+  v21[1] = (V2[o + 1] + V2[o - sj + 1] + V2[o - sj] + V2[o]) / 4.0;
+  gen_bilinear(x11, x22, v11, v12, v21, v22, x1i * w.UL, x2j, ans1);
+  const double vx1 = (ans1[0] * w.UV * st + ans1[1] * w.UV * ct);
+  const double vz1 = (ans1[0] * w.UV * ct - ans1[1] * w.UV * st);
+  const double x = x1i * st * w.UL, z = x1i * ct * w.UL;
+  for (int ia = 0; ia < w.nangles; ia++) {
+    const double fr = __ldg(w.flux_r + ia * d.sv + o), ft = __ldg(w.flux_t + ia * d.sv + o);
+    const double fp = w.flux_p ? __ldg(w.flux_p + ia * d.sv + o) : 0.0;
+    const double mod_flux = sqrt(fr * fr + ft * ft + fp * fp);
+    double D = 0.0;
+    if (mod_flux != 0.0) {
+      const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
+      const double dx1 = maxds * sa, dx2 = maxds * ca;
+      const double ds = sqrt(dx1 * dx1 + dx2 * dx2);
+      const double r_off = sqrt((x + dx1) * (x + dx1) + (z + dx2) * (z + dx2));
+      const double qq = (x + dx1) / (z + dx2);
+      const double t_off = atan(qq);
+      gen_bilinear(x11, x22, v11, v12, v21, v22, r_off, t_off, ans2);
+      // sin / cos of t_off = atan(q): q / sqrt(1 + q^2), 1 / sqrt(1 + q^2) (principal branch, cos > 0)
+      const double co = 1.0 / sqrt(1.0 + qq * qq), so = qq * co;
+      const double vx2 = (ans2[0] * w.UV * so + ans2[1] * w.UV * co);
+      const double vz2 = (ans2[0] * w.UV * co - ans2[1] * w.UV * so);
+      const double v1 = sa * vx1 + ca * vz1;
+      const double v2 = sa * vx2 + ca * vz2;
+      const double out = fabs((v2 - v1) / ds);
+      // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per angle and SWEEP (the sweeps pass
+      // different centre states); the angle-dependent factor dvds^(-alpha) is taken here, once per
+      // stage, so that the sweeps are left with one pow() per zone instead of 36.
+      // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
+      if (out > 0.0) D = exp(-w.alpharad * log(out));
+    }
+    w.dvds[ia * d.sv + o] = D;
   }
-  // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per angle and SWEEP (the sweeps pass
-  // different centre states); the angle-dependent factor dvds^(-alpha) is taken here, once per
-  // stage, so that the sweeps are left with one pow() per zone instead of 36
-  // exp(-alpha log x): |log x| is O(10) here, so the result is within a few ulp of pow(x, -alpha)
-  // at less than half its cost
-  w.dvds[ia * d.sv + o] = out > 0.0 ? exp(-w.alpharad * log(out)) : 0.0;
 }
 
 // LineForce(), line_connect.c:815-903 (KRAD / ALPHARAD power law, capped at M_max = 4400)

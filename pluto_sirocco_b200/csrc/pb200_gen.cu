@@ -383,6 +383,9 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     return (unsigned)((n + T - 1) / T);
   };
   const unsigned ball = (unsigned)((D.sv + T - 1) / T);
+  auto zones_of = [](const GenBox &b) {
+    return (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
+  };
   GenBox dom;
   for (int d = 0; d < 3; d++) { dom.lo[d] = D.beg[d]; dom.hi[d] = D.end[d]; }
   if (stage == 1) {
@@ -400,8 +403,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     c->launches++;
   }
   if (c->ldw_on) {                              // VGradCalc, update_stage.c:138-140
-    dim3 grid(blocks(dom), c->ldw.nangles);
-    gen_vgrad<<<grid, T, 0, st>>>(G, a, dom);
+    gen_vgrad<<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom);
     c->launches++;
   }
   for (int dir = 0; dir < D.ndim; dir++) {
