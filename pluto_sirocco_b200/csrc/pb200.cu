@@ -29,6 +29,7 @@ static int fail(int code, const std::string &msg) {
       return fail(PB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
   } while (0)
 
+int pb200_fail(int code, const char *msg) { return fail(code, msg); }
 extern "C" const char *pb200_last_error(void) { return g_err.c_str(); }
 extern "C" int pb200_version(void) { return PB200_VERSION; }
 

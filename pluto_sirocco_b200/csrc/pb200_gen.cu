@@ -297,27 +297,29 @@ int pb200_gen_userdef_side(pb200_ctx *c, double *V, int side) {
 }
 
 extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
-  if (!c || !l) return PB200_EINVAL;
-  if (!c->gen || c->cfg.geometry != PB200_SPHERICAL || c->dev.ndim != 2) return PB200_ENOTSUP;
-  if (l->nangles < 1 || l->nangles > 64) return PB200_EINVAL;
-  if (l->krad == 999 && l->alpharad == 999) return PB200_ENOTSUP;   // M_UV fit tables (line_connect.c:185-256)
+  if (!c || !l) return pb200_fail(PB200_EINVAL, "null argument");
+  if (!c->gen || c->cfg.geometry != PB200_SPHERICAL || c->dev.ndim != 2)
+    return pb200_fail(PB200_ENOTSUP, "LINE_DRIVEN_WIND is built for GEOMETRY SPHERICAL, DIMENSIONS 2");
+  if (l->nangles < 1 || l->nangles > 64) return pb200_fail(PB200_EINVAL, "NFLUX_ANGLES must be 1..64");
+  if (l->krad == 999 && l->alpharad == 999)   // M_UV fit tables (line_connect.c:185-256)
+    return pb200_fail(PB200_ENOTSUP, "the M_UV fit-table mode (KRAD = ALPHARAD = 999) is not built");
   cudaSetDevice(c->cfg.device);
   c->ldw = *l;
   c->ldw_on = true;
   size_t n = (size_t)l->nangles * c->dev.sv;
   for (int q = 0; q < 3; q++) {
     if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
-    if (cudaMalloc(&c->ldw_flux[q], n * sizeof(double)) != cudaSuccess) return PB200_ENOMEM;
+    if (cudaMalloc(&c->ldw_flux[q], n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "flux tables: out of device memory");
     cudaMemset(c->ldw_flux[q], 0, n * sizeof(double));
   }
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
-  if (cudaMalloc(&c->ldw_dvds, n * sizeof(double)) != cudaSuccess) return PB200_ENOMEM;
+  if (cudaMalloc(&c->ldw_dvds, n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "dvds array: out of device memory");
   cudaMemset(c->ldw_dvds, 0, n * sizeof(double));
   return PB200_OK;
 }
 
 extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double *ft, const double *fp) {
-  if (!c || !c->ldw_on || !fr || !ft) return PB200_EINVAL;
+  if (!c || !c->ldw_on || !fr || !ft) return pb200_fail(PB200_EINVAL, "pb200_ldw_set_fluxes: call pb200_ldw_enable first; flux_r / flux_t must not be NULL");
   cudaSetDevice(c->cfg.device);
   size_t n = (size_t)c->ldw.nangles * c->dev.sv * sizeof(double);
   if (cudaMemcpy(c->ldw_flux[0], fr, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
@@ -329,7 +331,7 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
 
 // SplitSource() for COOLING BLONDIN (Src/split_source.c:53): BlondinCooling(d->Vc, d, dt, ...)
 extern "C" int pb200_cooling_set_tables(pb200_ctx *c, const double *const tabs[7]) {
-  if (!c || !c->ldw_on) return PB200_EINVAL;
+  if (!c || !c->ldw_on) return pb200_fail(PB200_EINVAL, "pb200_cooling_set_tables: call pb200_ldw_enable first");
   cudaSetDevice(c->cfg.device);
   size_t n = (size_t)c->dev.sv * sizeof(double);
   for (int q = 0; q < 7; q++) {
@@ -342,7 +344,8 @@ extern "C" int pb200_cooling_set_tables(pb200_ctx *c, const double *const tabs[7
 }
 
 extern "C" int pb200_split_source(pb200_ctx *c, double dt, double g_time) {
-  if (!c || !c->gen || !c->ldw_on) return PB200_ENOTSUP;
+  if (!c || !c->gen || !c->ldw_on)
+    return pb200_fail(PB200_ENOTSUP, "pb200_split_source: COOLING BLONDIN needs a line-driven-wind context (pb200_ldw_enable)");
   cudaSetDevice(c->cfg.device);
   int rc = pb200_gen_setup(c);
   if (rc) return rc;

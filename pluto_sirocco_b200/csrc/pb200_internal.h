@@ -57,6 +57,7 @@ struct pb200_ctx {
   int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
 };
 
+int  pb200_fail(int code, const char *msg);   // sets pb200_last_error(), returns code
 int  pb200_gen_setup(pb200_ctx *c);
 void pb200_gen_release(pb200_ctx *c);
 int  pb200_gen_stage(pb200_ctx *c, int stage);
