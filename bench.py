@@ -192,7 +192,7 @@ def run_reference(args):
     res = reference_rate(cfg, n, cores, args.warmup, args.steps, args.solver)
     wl = workload_name(args.size, args.recon, args.rk, args.solver)
     if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/%s/pluto not built on this box" % cfg}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/%s/pluto not built on this box" % cfg})
         return 0
     rate, dt = res
     sample = ("%d concurrent serial processes (no MPI on this image: communication-free upper bound), "
@@ -204,7 +204,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": wl},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -418,7 +418,7 @@ def run_b200(args):
                        "boundaries": "periodic x1/x3, reflective x2" if rt else "reflective-beg/outflow-end", "cfl": cfl},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -538,11 +538,28 @@ def run_ldw(args):
                          "traffic": None, "peak_source": peak_src, "kernel": "whole step (multi-kernel general path)",
                          "algorithmic_bytes_per_zone_update": ALG_BYTES_LDW},
             "cpu_baseline": None}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # libraries (NCCL's version banner, ...) write to fd 1 from C: keep stdout for the JSON line only
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="sedov", choices=["sedov", "rt", "ldw"],
                     help="sedov: BASELINE configs[1] (the metric's config; configs[4] with --recon PARABOLIC --rk RK3 "

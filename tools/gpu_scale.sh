@@ -17,4 +17,4 @@ PY
 run c2 --steps 20 --warmup 3 --no-e2e --no-cpu
 run c3_rt --workload rt --size ${2:-1024} --steps 20 --warmup 3 --no-e2e --no-cpu
 run c5 --size 256 --recon PARABOLIC --rk RK3 --steps 20 --warmup 3 --no-e2e --no-cpu
-timeout 300 python -m pytest tests -m gpu -x -q -k "slab_nccl" > $OUT/pytest.log 2>&1; tail -n 2 $OUT/pytest.log
+
