@@ -107,9 +107,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self, t0=None, t1=None):
+        return sum(1 for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1) and len(r.split(",")) >= 7)
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons of the samples taken under load; the count of samples that
+        fell inside [t0, t1] (the timed region) is reported separately."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -119,7 +124,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for (_, r) in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -131,7 +136,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": self.count(t0, t1) if t0 is not None else None}
 
 
 def measured_peaks():
@@ -287,15 +293,18 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # nvidia-smi needs a few 100 ms to deliver its first sample: start it early
+    for _ in range(args.warmup):
+        one_step()
+    if rank == 0:
+        sampler.rows.clear()     # keep samples taken from here on (all of them under load)
     stream = sh.stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     launches = 0
+    t_reg0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         info = one_step()
@@ -303,11 +312,21 @@ def run_b200(args):
     ev1.record(stream)
     sync_all()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    t_reg1 = time.perf_counter()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+    # a 20-step region lasts 0.3 s and nvidia-smi may deliver no sample inside it: keep the SAME load
+    # running (untimed, same count on every rank) until about 1.5 s of load have been sampled, so that
+    # clocks / throttle reasons under load are on record
+    extra = 0 if ms >= 1500.0 else int((1500.0 - ms) / (ms / args.steps)) + 1
+    for _ in range(extra):
+        one_step()
+    sync_all()
+    clocks = sampler.stop(t_reg0, t_reg1) if rank == 0 else None
+    if clocks is not None:
+        clocks["untimed_steps_added_for_sampling"] = extra
     value = zones_total * args.steps / (ms * 1e-3) / 1e6
 
     # ---- per-kernel times (CUDA events inside the library, on the launching stream) ----
@@ -492,21 +511,37 @@ def run_ldw(args):
         g["dt"] = h.next_time_step(info.invDt_hyp, cfl, cmv, g["dt"], first_dt)
         return info
 
-    for _ in range(args.warmup):
-        one_step()
     sampler = ClockSampler(0)
     sampler.start()
+    for _ in range(args.warmup):
+        one_step()
+    sampler.rows.clear()
     stream = torch.cuda.ExternalStream(h.stream_ptr())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     launches = 0
+    t_reg0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         launches += one_step().launches
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    t_reg1 = time.perf_counter()
+    extra = 0 if ms >= 1500.0 else min(300, int((1500.0 - ms) / (ms / args.steps)) + 1)   # same load, untimed, for the clock samples
+    done = 0
+    saved, saved_dt = h.download(), g["dt"]
+    try:
+        for _ in range(extra):
+            one_step(); done += 1
+    except Exception:        # the synthetic wind is not meant to be integrated far: stop sampling there
+        pass
+    extra = done
+    torch.cuda.synchronize()
+    h.upload(saved)          # the e2e leg continues from the end of the timed region
+    g["dt"] = saved_dt
+    clocks = sampler.stop(t_reg0, t_reg1)
+    clocks["untimed_steps_added_for_sampling"] = extra
     value = zones * args.steps / (ms * 1e-3) / 1e6
     # e2e: host d->Vc in and out every step
     vc = h.download()
