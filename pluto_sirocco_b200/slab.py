@@ -5,8 +5,8 @@ Reference behaviour replaced:
     OUTERMOST active direction (x3 in 3-D, x2 in 2-D), whose ghost planes are contiguous per
     variable in Vc[nv][k][j][i] so no pack kernel is needed;
   * boundary.c:139-158 + al_exchange_dim.c:64-78  per-variable MPI_Sendrecv pairs -> one
-    grouped batch of NCCL send/recv (torch.distributed.batch_isend_irecv) per stage, issued on
-    the stream the sweep kernels run on;
+    grouped batch of NCCL send/recv (torch.distributed.batch_isend_irecv) of packed edge planes per
+    stage, overlapped with the fused x1+x2 kernel;
   * main.c:547 (+ :288) MPI_Allreduce(MAX) of invDt_hyp / g_maxMach -> one 2-double
     all_reduce(MAX).
 One process per GPU (torchrun).  The same code runs on CPU tensors over gloo, which is how
@@ -89,52 +89,72 @@ class Slab:
         return tuple(sl)
 
 
-def post_halo_exchange(vc: torch.Tensor, slab: Slab, nghost: int):
-    """Post the exchange of the ghost planes of direction slab.sdir of vc[nv][k][j][i] (ghosts
-    included) with the neighbouring ranks' edge planes; returns the outstanding requests (wait on
-    them before reading the ghost planes).  With NCCL the transfers run on NCCL's own stream,
-    ordered after the work already enqueued on the current stream, so kernels launched between
-    post and wait overlap with them.  Works for CUDA tensors (nccl) and CPU tensors (gloo).
-    Every plane set is contiguous per variable, so tensors are sent in place (no packing)."""
-    lo, hi = slab.neighbours()
-    if lo is None and hi is None:
-        return []
-    axis = 3 - slab.sdir                 # position of the split direction in [nv][k][j][i]
-    n = vc.shape[axis]
-    ng = nghost
-    ops = []
-    nvar = vc.shape[0]
+class HaloExchange:
+    """One exchange of the ghost planes of direction slab.sdir of vc[nv][k][j][i] (ghosts included)
+    with the neighbouring ranks.  The edge planes of all variables are packed into ONE contiguous
+    buffer per face (a strided device copy), so an exchange is at most 2 sends + 2 receives however
+    many variables there are - at 256^3 zones per GPU the per-message latency, not the bandwidth, is
+    what a stage waits for.  post() packs and posts the transfers (with NCCL they run on NCCL's own
+    stream, ordered after the work already enqueued on the current stream, so kernels launched
+    between post() and finish() overlap with them); finish() waits and unpacks into the ghost planes.
+    Works for CUDA tensors (nccl) and CPU tensors (gloo)."""
 
-    def planes(a, b):
-        return [vc[nv].narrow(axis - 1, a, b - a) for nv in range(nvar)]
+    def __init__(self, slab: Slab, nghost: int):
+        self.slab, self.ng = slab, nghost
+        self._buf = {}
 
-    lo_ghost, lo_edge = planes(0, ng), planes(ng, 2 * ng)
-    hi_edge, hi_ghost = planes(n - 2 * ng, n - ng), planes(n - ng, n)
-    for nv in range(nvar):
-        for t in (lo_ghost[nv], lo_edge[nv], hi_edge[nv], hi_ghost[nv]):
-            assert t.is_contiguous(), "slab planes must be contiguous per variable"
-    # Per peer, NCCL pairs sends and receives in posting order (tags are honoured by gloo
-    # only).  Post "upward" traffic first (hi_edge -> peer's lo_ghost), then "downward", so a
-    # periodic pair of 2 ranks (lo == hi) matches correctly as well.
-    if hi is not None:
-        for nv in range(nvar):
-            ops.append(dist.P2POp(dist.isend, hi_edge[nv], hi, tag=nv))
-    if lo is not None:
-        for nv in range(nvar):
-            ops.append(dist.P2POp(dist.isend, lo_edge[nv], lo, tag=100 + nv))
-    if lo is not None:
-        for nv in range(nvar):
-            ops.append(dist.P2POp(dist.irecv, lo_ghost[nv], lo, tag=nv))
-    if hi is not None:
-        for nv in range(nvar):
-            ops.append(dist.P2POp(dist.irecv, hi_ghost[nv], hi, tag=100 + nv))
-    return dist.batch_isend_irecv(ops)
+    def _buffers(self, vc):
+        key = (vc.data_ptr(), vc.shape)
+        if key not in self._buf:
+            axis = 3 - self.slab.sdir
+            shape = list(vc.shape)
+            shape[axis] = self.ng
+            self._buf[key] = [torch.empty(shape, dtype=vc.dtype, device=vc.device) for _ in range(4)]
+        return self._buf[key]
+
+    def post(self, vc: torch.Tensor):
+        lo, hi = self.slab.neighbours()
+        self._pending = None
+        if lo is None and hi is None:
+            return
+        axis = 3 - self.slab.sdir                 # position of the split direction in [nv][k][j][i]
+        n, ng = vc.shape[axis], self.ng
+        send_lo, send_hi, recv_lo, recv_hi = self._buffers(vc)
+        ops = []
+        # Per peer, NCCL pairs sends and receives in posting order (tags are honoured by gloo only).
+        # Post "upward" traffic first (hi edge -> peer's lo ghosts), then "downward", so a periodic
+        # pair of 2 ranks (lo == hi) matches correctly as well.
+        if hi is not None:
+            send_hi.copy_(vc.narrow(axis, n - 2 * ng, ng))
+            ops.append(dist.P2POp(dist.isend, send_hi, hi, tag=0))
+        if lo is not None:
+            send_lo.copy_(vc.narrow(axis, ng, ng))
+            ops.append(dist.P2POp(dist.isend, send_lo, lo, tag=1))
+        if lo is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_lo, lo, tag=0))
+        if hi is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_hi, hi, tag=1))
+        self._pending = (dist.batch_isend_irecv(ops), vc, axis, n, lo, hi)
+
+    def finish(self):
+        if self._pending is None:
+            return
+        reqs, vc, axis, n, lo, hi = self._pending
+        for r in reqs:
+            r.wait()
+        _, _, recv_lo, recv_hi = self._buffers(vc)
+        if lo is not None:
+            vc.narrow(axis, 0, self.ng).copy_(recv_lo)
+        if hi is not None:
+            vc.narrow(axis, n - self.ng, self.ng).copy_(recv_hi)
+        self._pending = None
 
 
 def exchange_halos(vc: torch.Tensor, slab: Slab, nghost: int):
-    """Blocking form: post + wait."""
-    for r in post_halo_exchange(vc, slab, nghost):
-        r.wait()
+    """Blocking form: pack, post, wait, unpack."""
+    x = HaloExchange(slab, nghost)
+    x.post(vc)
+    x.finish()
 
 
 def allreduce_max(values, device):
@@ -166,6 +186,7 @@ class SlabHydro:
         self.device = torch.device("cuda", hydro.cfg.device)
         self.stream = torch.cuda.ExternalStream(hydro.stream_ptr(), device=self.device)
         self._views = {}
+        self._halo = HaloExchange(slab, hydro.nghost)
 
     def _view(self, ptr):
         if ptr not in self._views:
@@ -180,10 +201,9 @@ class SlabHydro:
                 # the x3 ghost planes are only read by the x3 sweep: fill the physical boundaries,
                 # post the exchange, run the fused x1+x2 kernel while the planes travel, then wait
                 h.stage_boundary(s)
-                reqs = post_halo_exchange(self._view(h.stage_array_ptr(s)), self.slab, h.nghost)
+                self._halo.post(self._view(h.stage_array_ptr(s)))
                 h.stage_begin(s)
-                for r in reqs:
-                    r.wait()
+                self._halo.finish()
                 h.stage_finish(s)
             info = h.step_end()
             if self.slab.world > 1:
