@@ -99,7 +99,8 @@ typedef struct pb200_config {
   int body_force;        /* BODY_FORCE: 0 NO, PB200_BF_VECTOR, PB200_BF_POTENTIAL or both (pluto.h:76-77) */
   int char_limiting;     /* CHAR_LIMITING YES (Src/States/plm_states.c:481) */
   int shock_flattening;  /* SHOCK_FLATTENING MULTID (Src/flag_shock.c:81) */
-  int entropy_switch;    /* ENTROPY_SWITCH ALWAYS: NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219) */
+  int entropy_switch;    /* ENTROPY_SWITCH: 0 NO, 1 SELECTIVE, 2 ALWAYS (same values as Src/pluto.h:60-61);
+                            NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219, flag_shock.c:146,256) */
   int reserved[3];
 } pb200_config;
 

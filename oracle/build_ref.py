@@ -89,6 +89,7 @@ CONFIGS = {
     "sph2d_entr": dict(local="sph", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
                                                "SHOCK_FLATTENING": "MULTID", "ENTROPY_SWITCH": "ALWAYS"},
                        states="plm"),
+    "sph2d_sel": dict(local="sph", overrides={"ENTROPY_SWITCH": "SELECTIVE"}, states="plm"),
     "sph1d": dict(local="sph", overrides={"DIMENSIONS": "1"}, states="plm"),
     "sph3d": dict(local="sph", overrides={"DIMENSIONS": "3"}, states="plm"),
     # C4: the line-driven disc wind of the sirocco coupling, UNMODIFIED user files of the reference

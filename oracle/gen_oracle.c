@@ -49,7 +49,7 @@
 
 typedef struct gen_cfg {
   int ndim, nx[3], ng;
-  int ntracer, entropy;     /* NTRACER; ENTROPY_SWITCH: 0 NO, 1 ALWAYS */
+  int ntracer, entropy;     /* NTRACER; ENTROPY_SWITCH: 0 NO, 1 SELECTIVE, 2 ALWAYS (pluto.h:60-61) */
   int geometry;             /* CARTESIAN 1, SPHERICAL 4 (pluto.h:34-37) */
   int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
   int char_limiting;        /* CHAR_LIMITING */
@@ -609,6 +609,10 @@ static void flag_shock(const gen_cfg *c, const geom_t *g, const double *Vc, uint
           if (c->flattening && gradp > 5.0 * pt_min) {
             flag[o] |= FLAG_HLL | FLAG_MINMOD;
             for (int d = 0; d < c->ndim; d++) { flag[o + st[d]] |= FLAG_MINMOD; flag[o - st[d]] |= FLAG_MINMOD; }
+          }
+          if (c->entropy == 1 && gradp > 0.05 * pt_min) {   /* SELECTIVE: flag_shock.c:256-267, EPS_PSHOCK_ENTROPY */
+            flag[o] &= ~FLAG_ENTROPY;
+            for (int d = 0; d < c->ndim; d++) { flag[o + st[d]] &= ~FLAG_ENTROPY; flag[o - st[d]] &= ~FLAG_ENTROPY; }
           }
         }
       }

@@ -72,7 +72,7 @@ class GenOracle:
             c.xr[d] = xr.ctypes.data
         c.ng = nghost
         c.ntracer = ntracer
-        c.entropy = int(bool(entropy_switch))
+        c.entropy = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
         c.geometry = GEOMETRY[geometry]
         c.limiter = _o.LIMITER[limiter]
         c.char_limiting = int(bool(char_limiting))
@@ -91,7 +91,7 @@ class GenOracle:
         self.nx = tuple(c.nx)
         self.beg = tuple(nghost if d < dimensions else 0 for d in range(3))
         self.tot = tuple(self.nx[d] + 2 * self.beg[d] for d in range(3))
-        self.nvar = 5 + ntracer + c.entropy
+        self.nvar = 5 + ntracer + (1 if c.entropy else 0)
         self.shape = (self.nvar, self.tot[2], self.tot[1], self.tot[0])
         self._h = None
         self._bf = {}

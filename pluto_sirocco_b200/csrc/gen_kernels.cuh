@@ -159,6 +159,7 @@ static __global__ void gen_shock(GenDev g, GenArgs a, GenBox b) {
       gradp = (dir == 0) ? dp : gradp + dp;
     }
     sh = (gradp > 5.0 * pt_min) ? 1 : 0;      // EPS_PSHOCK_FLATTEN, flag_shock.c:69-70
+    if (gradp > 0.05 * pt_min) sh |= 2;       // EPS_PSHOCK_ENTROPY, flag_shock.c:73-74 (ENTROPY_SWITCH SELECTIVE)
   }
   a.shock[o] = sh;
 }
@@ -171,13 +172,16 @@ static __global__ void gen_flags(GenDev g, GenArgs a) {
   const long st[3] = {1, d.sj, d.sk};
   const int idx[3] = {i, j, k};
   unsigned short f = g.entropy ? GF_ENTROPY : 0;
-  if (g.flatten) {
-    if (a.shock[o]) f |= GF_HLL | GF_MINMOD;
-    for (int dir = 0; dir < d.ndim; dir++) {
-      if (idx[dir] > 0 && a.shock[o - st[dir]]) f |= GF_MINMOD;
-      if (idx[dir] < d.tot[dir] - 1 && a.shock[o + st[dir]]) f |= GF_MINMOD;
-    }
+  unsigned char near = a.shock[o];         // own indicator bits and the neighbours' (the reference scatters)
+  for (int dir = 0; dir < d.ndim; dir++) {
+    if (idx[dir] > 0) near |= a.shock[o - st[dir]];
+    if (idx[dir] < d.tot[dir] - 1) near |= a.shock[o + st[dir]];
   }
+  if (g.flatten) {
+    if (a.shock[o] & 1) f |= GF_HLL | GF_MINMOD;
+    if (near & 1) f |= GF_MINMOD;
+  }
+  if (g.entropy == 1 && (near & 2)) f &= ~GF_ENTROPY;    // SELECTIVE: unflag shocked zones and their neighbours
   a.flag[o] = f;
 }
 

@@ -393,7 +393,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   for (int d = 0; d < 3; d++) { dom.lo[d] = D.beg[d]; dom.hi[d] = D.end[d]; }
   if (stage == 1) {
     if (G.flatten || G.entropy) {   // FlagShock, rk_step.c:123-125 (flags were zeroed by main.c:258-261)
-      if (G.flatten) {
+      if (G.flatten || G.entropy == 1) {
         GenBox b;
         for (int d = 0; d < 3; d++) { int inc = d < D.ndim; b.lo[d] = inc; b.hi[d] = D.tot[d] - 1 - inc; }
         gen_shock<<<blocks(b), T, 0, st>>>(G, a, b);

@@ -181,10 +181,10 @@ static void shim_init(Data *d, Grid *grid) {
 #elif SHOCK_FLATTENING != NO
 #error "libplutob200: SHOCK_FLATTENING must be NO or MULTID"
 #endif
-#if ENTROPY_SWITCH == ALWAYS
-  cfg.entropy_switch = 1;
+#if ENTROPY_SWITCH == ALWAYS || ENTROPY_SWITCH == SELECTIVE
+  cfg.entropy_switch = ENTROPY_SWITCH;      /* same codes, Src/pluto.h:60-61 */
 #elif ENTROPY_SWITCH != NO
-#error "libplutob200: ENTROPY_SWITCH must be NO or ALWAYS"
+#error "libplutob200: ENTROPY_SWITCH must be NO, SELECTIVE or ALWAYS"
 #endif
 #if (BODY_FORCE & VECTOR)
   cfg.body_force |= PB200_BF_VECTOR;

@@ -215,7 +215,7 @@ class Hydro:
         cfg.geometry = {"CARTESIAN": L.CARTESIAN, "SPHERICAL": L.SPHERICAL}[geometry]
         cfg.char_limiting = int(bool(char_limiting))
         cfg.shock_flattening = int(bool(shock_flattening))
-        cfg.entropy_switch = int(bool(entropy_switch))
+        cfg.entropy_switch = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
         self.cfg = cfg
         self._lib = lib
         h = C.c_void_p()

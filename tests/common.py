@@ -36,6 +36,12 @@ def load_golden(name):
 BODY_FORCE = dict(none=0, vector=1, potential=2)
 
 
+def _entr_code(g):
+    """fixtures made before SELECTIVE existed stored 0/1 for NO/ALWAYS"""
+    v = int(g["entropy_switch"])
+    return v if "entr_codes" in g or v != 1 else 2
+
+
 def gen_kwargs_from_golden(g):
     """Constructor keywords shared by GenOracle and Hydro for a general-grid fixture."""
     grid = []
@@ -49,7 +55,7 @@ def gen_kwargs_from_golden(g):
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
                 char_limiting=bool(int(g["char_limiting"])), shock_flattening=flat,
-                entropy_switch=bool(int(g["entropy_switch"])),
+                entropy_switch={0: False, 1: "SELECTIVE", 2: "ALWAYS"}[_entr_code(g)],
                 nghost=3 if flat else 2)     # GetNghost(), Src/get_nghost.c:42-51
 
 

@@ -101,6 +101,8 @@ CASES3 = {
                             char_limiting=True, limiter="VANLEER_LIM", shock_flattening=True),
     "sph2d_entr_hll": dict(cfg="sph2d_entr", dims=2, grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, maxsteps=10,
                            char_limiting=True, limiter="VANLEER_LIM", shock_flattening=True, entropy_switch=True),
+    "sph2d_sel_hllc": dict(cfg="sph2d_sel", dims=2, grid=SPH_GRID2, solver="hllc", bcs=SPH_BCS, maxsteps=12,
+                           entropy_switch="SELECTIVE"),
     "sph1d_tvdlf": dict(cfg="sph1d", dims=1, grid=[(1.0, 64, 4.0, "r", 1.02), (1.0, 1, 1.2), (0.0, 1, 1.0)],
                         solver="tvdlf", bcs=("reflective", "outflow") * 3, maxsteps=10),
     "sph3d_hllc": dict(cfg="sph3d", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
@@ -132,7 +134,8 @@ def make_case3(out, name, c):
                         body_force="vector", gm=SPH_PAR["GM"], limiter=c.get("limiter", "DEFAULT"),
                         char_limiting=int(c.get("char_limiting", False)),
                         shock_flattening=int(c.get("shock_flattening", False)),
-                        entropy_switch=int(c.get("entropy_switch", False)))
+                        entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],
+                        entr_codes=1)
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
@@ -175,7 +178,7 @@ def make_case4(out, name, c):
                         gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-4, tstop=1.0,
                         ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=1,
                         body_force="vector", limiter="VANLEER_LIM", char_limiting=1, shock_flattening=1,
-                        entropy_switch=1, cooling=int(c["cooling"]))
+                        entropy_switch=2, entr_codes=1, cooling=int(c["cooling"]))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 

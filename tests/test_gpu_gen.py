@@ -64,7 +64,8 @@ def test_gen_free_run_vs_reference_dumps(Hydro, name):
 @pytest.mark.parametrize("limiter,char,flat,entr", [("DEFAULT", False, False, False), ("DEFAULT", True, True, False),
                                                     ("MC_LIM", True, False, True), ("OSPRE_LIM", False, True, True),
                                                     ("VANALBADA_LIM", True, True, True), ("UMIST_LIM", False, False, False),
-                                                    ("MINMOD_LIM", True, False, False)])
+                                                    ("MINMOD_LIM", True, False, False),
+                                                    ("DEFAULT", False, False, "SELECTIVE"), ("VANLEER_LIM", True, True, "SELECTIVE")])
 @pytest.mark.parametrize("rk,solver", [("RK2", "hllc"), ("RK3", "hll"), ("EULER", "tvdlf")])
 def test_gen_options_vs_oracle(Hydro, geometry, limiter, char, flat, entr, rk, solver):
     """Every limiter / limiting mode / flattening / entropy / solver / RK mix on a stretched 2-D grid
