@@ -161,12 +161,16 @@ typedef struct pb200_ldw_config {
   int    nangles;                 /* NFLUX_ANGLES (<= 64) */
   int    userdef_bc;
   double unit_length, unit_velocity, unit_density;      /* UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY */
-  double mu, krad, alpharad;      /* g_inputParam[MU], [KRAD], [ALPHARAD] (the 999/999 fit-table mode is not built) */
+  double mu, krad, alpharad;      /* g_inputParam[MU], [KRAD], [ALPHARAD]; 999/999 selects the M(t) fit: pb200_ldw_set_mfit() */
   double dfloor, rho_0, rho_alpha, cent_mass, disk_mdot;   /* g_inputParam[DFLOOR], [RHO_0], [RHO_ALPHA], [CENT_MASS], [DISK_MDOT] (cgs) */
   double lx, tx;                  /* g_inputParam[L_star]*[f_x], g_inputParam[T_x] (BLONDIN cooling) */
 } pb200_ldw_config;
 int  pb200_ldw_enable(pb200_ctx *ctx, const pb200_ldw_config *ldw);
 int  pb200_ldw_set_fluxes(pb200_ctx *ctx, const double *flux_r, const double *flux_t, const double *flux_p);
+/* force-multiplier fit for KRAD = ALPHARAD = 999 (M_UV_data.dat, line_connect.c:185-256,849-853):
+ * t_fit = log10(t) [mpoints], m_fit = log10(M) [mpoints][NX3_TOT][NX2_TOT][NX1_TOT] (the globals t_fit and
+ * M_UV_fit, Src/globals.h:194-196) */
+int  pb200_ldw_set_mfit(pb200_ctx *ctx, int mpoints, const double *t_fit, const double *m_fit);
 
 /* COOLING BLONDIN.  pb200_split_source() is SplitSource(d, dt, Dts, grid) (Src/split_source.c:29,
  * called from Integrate, Src/main.c:479-485) for the BLONDIN module: BlondinCooling(d->Vc, d, dt)

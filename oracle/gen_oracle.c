@@ -71,6 +71,9 @@ typedef struct gen_cfg {
   int cooling;              /* COOLING BLONDIN */
   const double *cool_tab[8]; /* comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, xi, T_r? (see ldw section) */
   double lx, tx;            /* L_star*f_x, T_x */
+  int mpoints;              /* MPOINTS of the force-multiplier fit (KRAD = ALPHARAD = 999), line_connect.c:185-256 */
+  const double *t_fit;      /* log10(t), MPOINTS entries */
+  const double *m_fit;      /* log10(M), [MPOINTS][k][j][i] */
 } gen_cfg;
 
 typedef struct {
@@ -1011,7 +1014,23 @@ static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, 
       }
 }
 
-/* LineForce(), line_connect.c:815-903 (KRAD/ALPHARAD power-law multiplier) */
+/* linterp(), line_connect.c:781-811 */
+static double linterp(double x, const double *xarray, const double *yarray, int nelem) {
+  int idx = 0;
+  double result;
+  while (idx < nelem && xarray[idx] < x) idx++;
+  if (idx == 0) result = pow(10.0, yarray[0]);
+  else if (idx >= nelem) result = pow(10.0, yarray[nelem - 1]);
+  else {
+    double x_low = xarray[idx - 1], x_high = xarray[idx], y_low = yarray[idx - 1], y_high = yarray[idx];
+    double slope = (y_high - y_low) / (x_high - x_low);
+    result = pow(10.0, y_low + slope * (x - x_low));
+  }
+  if (isnan(result)) result = 0.0;
+  return result;
+}
+
+/* LineForce(), line_connect.c:815-903 (KRAD/ALPHARAD power law, or the per-zone M(t) fit when both are 999) */
 static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad) {
   double sigma_e = CONST_sigmaT / CONST_amu / 1.18;
   double rho = v[RHO] * c->unit_density;
@@ -1020,12 +1039,16 @@ static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, c
   double M_max = 4400.;
   double UNIT_ACC = c->unit_velocity * c->unit_velocity / c->unit_length;
   grad[0] = grad[1] = grad[2] = 0.0;
+  int fit = (c->krad == 999 && c->alpharad == 999);
+  double M_UV_array[64];
+  if (fit) for (int ii = 0; ii < c->mpoints; ii++) M_UV_array[ii] = c->m_fit[ii * g->sv + o];
   for (int ia = 0; ia < c->nangles; ia++) {
     double flux_r = c->flux_r[ia * g->sv + o], flux_t = c->flux_t[ia * g->sv + o], M_UV;
     double dv = dvds[ia * g->sv + o];
     if (dv > 0.0) {
       double t_UV = sigma_e * rho * v_th / dv;
-      M_UV = c->krad * pow(t_UV, c->alpharad);
+      if (fit) M_UV = linterp(log10(t_UV), c->t_fit, M_UV_array, c->mpoints);
+      else M_UV = c->krad * pow(t_UV, c->alpharad);
       if (M_UV > M_max) M_UV = M_max;
     } else M_UV = 0.0;
     grad[0] += ((1.0 + M_UV) * sigma_e * flux_r / CONST_c) / UNIT_ACC;

@@ -26,7 +26,8 @@ class GenCfg(C.Structure):
                 ("mu", C.c_double), ("krad", C.c_double), ("alpharad", C.c_double), ("t_iso", C.c_double),
                 ("dfloor", C.c_double), ("rho0", C.c_double), ("rho_alpha", C.c_double),
                 ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
-                ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double)]
+                ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
+                ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p)]
 
 
 _bound = False
@@ -106,7 +107,7 @@ class GenOracle:
         self._bf[comp] = a
         self.c.bf_g[comp] = a.ctypes.data
 
-    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p, userdef_bc=True):
+    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p, userdef_bc=True, t_fit=None, m_fit=None):
         """LINE_DRIVEN_WIND SIROCCO_MODE: g_inputParam[] of cv_idl (dict by label), UNIT_* (dict),
         directional fluxes [nangles][k][j][i] incl. ghosts."""
         c = self.c
@@ -121,6 +122,11 @@ class GenOracle:
         c.dfloor, c.rho0, c.rho_alpha = params["DFLOOR"], params["RHO_0"], params["RHO_ALPHA"]
         c.cent_mass, c.disk_mdot = params["CENT_MASS"], params["DISK_MDOT"]
         c.lx, c.tx = params["L_star"] * params["f_x"], params["T_x"]
+        if t_fit is not None:      # force-multiplier fit: t_fit = log10(t) [MPOINTS], m_fit = log10(M) [MPOINTS][k][j][i]
+            self._tfit = np.ascontiguousarray(t_fit, dtype=np.float64)
+            self._mfit = np.ascontiguousarray(m_fit, dtype=np.float64)
+            assert self._mfit.shape == (self._tfit.size,) + self.shape[1:]
+            c.mpoints, c.t_fit, c.m_fit = self._tfit.size, self._tfit.ctypes.data, self._mfit.ctypes.data
 
     def _handle(self):
         if self._h is None:

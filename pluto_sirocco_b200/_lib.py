@@ -65,6 +65,7 @@ SYMBOLS = {
     "pb200_split_source": (C.c_int, [_P, _D, _D]),
     "pb200_ldw_enable": (C.c_int, [_P, C.POINTER(LdwConfig)]),
     "pb200_ldw_set_fluxes": (C.c_int, [_P, _P, _P, _P]),
+    "pb200_ldw_set_mfit": (C.c_int, [_P, C.c_int, _P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),

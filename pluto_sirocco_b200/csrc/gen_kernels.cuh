@@ -37,6 +37,8 @@ struct LdwDev {
   double UL, UV, UD;                        // UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY
   double kelvin_mu;                         // KELVIN * mu
   double krad, alpharad;
+  int mpoints;                              // > 0: force multiplier from the per-zone M(t) fit (KRAD = ALPHARAD = 999)
+  const double *t_fit, *m_fit;              // log10(t) [mpoints]; log10(M) [mpoints][k][j][i]
   double sigma_e, unit_acc;                 // sigma_T/amu/1.18 ; UNIT_ACCELERATION
   double dfloor, pfloor, tfloor, rho_0, rho_alpha, r_WD, gm_code, teff_wd;   // init.c:175-197,296-300
 };
@@ -417,7 +419,7 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
       // different centre states); the angle-dependent factor dvds^(-alpha) is taken here, once per
       // stage, so that the sweeps are left with one pow() per zone instead of 36.
       // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
-      if (out > 0.0) D = exp(-w.alpharad * log(out));
+      if (out > 0.0) D = w.mpoints > 0 ? out : exp(-w.alpharad * log(out));   // fit mode keeps dvds itself
     }
     w.dvds[ia * d.sv + o] = D;
   }
@@ -430,11 +432,31 @@ PB_D void gen_line_force(const GenDev &g, double rho_code, double prs_code, long
   const double T = prs_code / rho_code * w.kelvin_mu;
   const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
   grad[0] = grad[1] = grad[2] = 0.0;
-  const double kS = w.krad * pow(w.sigma_e * rho * v_th, w.alpharad);
+  const bool fit = w.mpoints > 0;
+  const double S = w.sigma_e * rho * v_th;
+  const double kS = fit ? 0.0 : w.krad * pow(S, w.alpharad);
   const double coef = w.sigma_e / (2.99792458e10 * w.unit_acc);
   for (int ia = 0; ia < w.nangles; ia++) {
-    const double D = __ldg(w.dvds + ia * g.d.sv + o);     // dvds^(-alpha), 0 where dvds <= 0
-    const double M = fmin(kS * D, 4400.0);
+    const double D = __ldg(w.dvds + ia * g.d.sv + o);     // dvds^(-alpha) (fit mode: dvds), 0 where dvds <= 0
+    double M;
+    if (!fit) M = fmin(kS * D, 4400.0);
+    else if (!(D > 0.0)) M = 0.0;
+    else {                                                // linterp(log10 t, t_fit, M_UV_fit[.][zone]), line_connect.c:781-811
+      const double x = log10(S / D);
+      int idx = 0;
+      while (idx < w.mpoints && __ldg(w.t_fit + idx) < x) idx++;
+      double y;
+      if (idx == 0) y = __ldg(w.m_fit + o);
+      else if (idx >= w.mpoints) y = __ldg(w.m_fit + (long)(w.mpoints - 1) * g.d.sv + o);
+      else {
+        const double xl = __ldg(w.t_fit + idx - 1), xh = __ldg(w.t_fit + idx);
+        const double yl = __ldg(w.m_fit + (long)(idx - 1) * g.d.sv + o), yh = __ldg(w.m_fit + (long)idx * g.d.sv + o);
+        y = yl + (yh - yl) / (xh - xl) * (x - xl);
+      }
+      M = pow(10.0, y);
+      if (!(M == M)) M = 0.0;
+      M = fmin(M, 4400.0);
+    }
     // ((1 + M) sigma_e F / c) / UNIT_ACCELERATION with the two constant divisions folded into one
     // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)
     const double q = (1.0 + M) * coef;

@@ -100,6 +100,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->cur_stage = 0;
   for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
   c->ldw_dvds = nullptr;
+  c->ldw_mpoints = 0;
+  c->ldw_tfit = c->ldw_mfit = nullptr;
   for (int q = 0; q < 7; q++) c->cool_tab[q] = nullptr;
   Dev &D = c->dev;
   D.ndim = cfg->dimensions;
@@ -196,6 +198,8 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   pb200_gen_release(c);
   for (int q = 0; q < 3; q++) if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
+  if (c->ldw_tfit) cudaFree(c->ldw_tfit);
+  if (c->ldw_mfit) cudaFree(c->ldw_mfit);
   for (int q = 0; q < 7; q++) if (c->cool_tab[q]) cudaFree(c->cool_tab[q]);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
   if (c->acc) cudaFree(c->acc);
@@ -461,7 +465,7 @@ extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
   if (rc) return rc;
   if (c->gen) {
     rc = pb200_gen_stage(c, stage);
-    return rc ? fail(rc, "general-grid stage failed") : PB200_OK;
+    return rc;      // pb200_gen_stage set the error text
   }
   const Dev &D = c->dev;
   if (D.ndim == 1) launch_sweep(c, 0, a);

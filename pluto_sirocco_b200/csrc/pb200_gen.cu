@@ -227,6 +227,7 @@ static void fill_ldw(pb200_ctx *c, GenDev &G) {
   const double KELVIN = L.unit_velocity * L.unit_velocity * amu / kB;      // pluto.h:560
   w.kelvin_mu = KELVIN * L.mu;
   w.krad = L.krad; w.alpharad = L.alpharad;
+  w.mpoints = c->ldw_mpoints; w.t_fit = c->ldw_tfit; w.m_fit = c->ldw_mfit;
   w.sigma_e = sigmaT / amu / 1.18;
   w.unit_acc = L.unit_velocity * L.unit_velocity / L.unit_length;
   w.dfloor = L.dfloor / L.unit_density;
@@ -301,8 +302,6 @@ extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
   if (!c->gen || c->cfg.geometry != PB200_SPHERICAL || c->dev.ndim != 2)
     return pb200_fail(PB200_ENOTSUP, "LINE_DRIVEN_WIND is built for GEOMETRY SPHERICAL, DIMENSIONS 2");
   if (l->nangles < 1 || l->nangles > 64) return pb200_fail(PB200_EINVAL, "NFLUX_ANGLES must be 1..64");
-  if (l->krad == 999 && l->alpharad == 999)   // M_UV fit tables (line_connect.c:185-256)
-    return pb200_fail(PB200_ENOTSUP, "the M_UV fit-table mode (KRAD = ALPHARAD = 999) is not built");
   cudaSetDevice(c->cfg.device);
   c->ldw = *l;
   c->ldw_on = true;
@@ -315,6 +314,24 @@ extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
   if (cudaMalloc(&c->ldw_dvds, n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "dvds array: out of device memory");
   cudaMemset(c->ldw_dvds, 0, n * sizeof(double));
+  return PB200_OK;
+}
+
+// force-multiplier fit of LineForce() (KRAD = ALPHARAD = 999): t_fit = log10(t) [mpoints] and
+// M_UV_fit = log10(M) [mpoints][k][j][i], as read_sirocco_fluxes() leaves them (line_connect.c:185-256)
+extern "C" int pb200_ldw_set_mfit(pb200_ctx *c, int mpoints, const double *t_fit, const double *m_fit) {
+  if (!c || !c->ldw_on || mpoints < 1 || mpoints > 64 || !t_fit || !m_fit)
+    return pb200_fail(PB200_EINVAL, "pb200_ldw_set_mfit: call pb200_ldw_enable first; 1 <= MPOINTS <= 64");
+  cudaSetDevice(c->cfg.device);
+  if (c->ldw_tfit) cudaFree(c->ldw_tfit);
+  if (c->ldw_mfit) cudaFree(c->ldw_mfit);
+  c->ldw_tfit = c->ldw_mfit = nullptr;
+  size_t n = (size_t)mpoints * c->dev.sv * sizeof(double);
+  if (cudaMalloc(&c->ldw_tfit, mpoints * sizeof(double)) != cudaSuccess || cudaMalloc(&c->ldw_mfit, n) != cudaSuccess)
+    return pb200_fail(PB200_ENOMEM, "force-multiplier fit: out of device memory");
+  cudaMemcpy(c->ldw_tfit, t_fit, mpoints * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(c->ldw_mfit, m_fit, n, cudaMemcpyHostToDevice);
+  c->ldw_mpoints = mpoints;
   return PB200_OK;
 }
 
@@ -431,6 +448,8 @@ int pb200_gen_stage(pb200_ctx *c, int stage) {
     comb = 1;
     if (c->nstages == 2) { w0 = 0.5; wc = 0.5; } else { w0 = 0.75; wc = 0.25; }
   } else if (stage == 3) comb = 2;
+  if (c->ldw_on && c->ldw.krad == 999 && c->ldw.alpharad == 999 && c->ldw_mpoints == 0)
+    return pb200_fail(PB200_EINVAL, "KRAD = ALPHARAD = 999 needs the force-multiplier fit (pb200_ldw_set_mfit)");
   switch (c->nvar) {
     case 5: gen_stage_nv<5>(c, stage, w0, wc, comb); break;
     case 6: gen_stage_nv<6>(c, stage, w0, wc, comb); break;
@@ -438,5 +457,5 @@ int pb200_gen_stage(pb200_ctx *c, int stage) {
     case 8: gen_stage_nv<8>(c, stage, w0, wc, comb); break;
     default: return PB200_ENOTSUP;
   }
-  return cudaGetLastError() == cudaSuccess ? PB200_OK : PB200_ECUDA;
+  return cudaGetLastError() == cudaSuccess ? PB200_OK : pb200_fail(PB200_ECUDA, "general-grid stage: kernel launch failed");
 }

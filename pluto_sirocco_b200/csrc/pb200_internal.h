@@ -53,6 +53,8 @@ struct pb200_ctx {
   bool ldw_on;
   pb200_ldw_config ldw;
   double *ldw_flux[3], *ldw_dvds;
+  int ldw_mpoints;                        // force-multiplier fit (0: power law)
+  double *ldw_tfit, *ldw_mfit;
   double *cool_tab[7];                    // BLONDIN tables (null: defaults)
   int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
 };

@@ -140,6 +140,13 @@ static void shim_line_driven_wind(void)
     print ("! AdvanceStep(): line-driven wind set-up failed: %s\n", pb200_last_error());
     QUIT_PLUTO(1);
   }
+  if (l.krad == 999 && l.alpharad == 999) {     /* M(t) fit of M_UV_data.dat (line_connect.c:185-256) */
+    if (M_UV_fit == NULL || t_fit == NULL ||
+        pb200_ldw_set_mfit(s_ctx, MPOINTS, t_fit, M_UV_fit[0][0][0]) != PB200_OK) {
+      print ("! AdvanceStep(): force-multiplier fit missing or not accepted: %s\n", pb200_last_error());
+      QUIT_PLUTO(1);
+    }
+  }
 }
 #endif
 

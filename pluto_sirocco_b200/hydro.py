@@ -327,7 +327,7 @@ class Hydro:
                                                          a.size, si, sj, sk))
 
     # -- line-driven wind ----------------------------------------------------------------------
-    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p=None, userdef_bc=True):
+    def set_ldw(self, *, params, units, flux_r, flux_t, flux_p=None, userdef_bc=True, t_fit=None, m_fit=None):
         """LINE_DRIVEN_WIND SIROCCO_MODE: g_inputParam[] of the cv_idl problem (dict by label), UNIT_*
         (dict), directional fluxes [nangles][k][j][i] incl. ghosts (read_sirocco_fluxes())."""
         lc = L.LdwConfig()
@@ -345,6 +345,12 @@ class Hydro:
         fp = None if flux_p is None else np.ascontiguousarray(flux_p, dtype=np.float64)
         L.check(self._lib.pb200_ldw_set_fluxes(self._h, fr.ctypes.data_as(C.c_void_p), ft.ctypes.data_as(C.c_void_p),
                                                None if fp is None else fp.ctypes.data_as(C.c_void_p)))
+        if t_fit is not None:     # KRAD = ALPHARAD = 999: log10(t) [MPOINTS], log10(M) [MPOINTS][k][j][i]
+            tf = np.ascontiguousarray(t_fit, dtype=np.float64)
+            mf = np.ascontiguousarray(m_fit, dtype=np.float64)
+            assert mf.shape == (tf.size,) + self.shape[1:]
+            L.check(self._lib.pb200_ldw_set_mfit(self._h, tf.size, tf.ctypes.data_as(C.c_void_p),
+                                                 mf.ctypes.data_as(C.c_void_p)))
 
     def set_cooling_tables(self, tabs):
         """Data->comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r

@@ -225,7 +225,7 @@ def write_ldw_flux_files(wd, x1, x2, ng, fr, ft, fp):
                     f.write("%d %d 0 %.17e %.17e %s\n" % (i - ng, j - ng, x1[i] * LDW_UNITS["length"], x2[j], vals))
 
 
-def ldw_setup(obj, x1, x2):
+def ldw_setup(obj, x1, x2, fit=False):
     """Hand the cv_idl problem to a GenOracle or a Hydro: gravity of the central mass
     (BodyForceVector, init.c:372-386), units, parameters and the synthetic flux tables."""
     gm_code = 6.6726e-8 * LDW_PARAMS["CENT_MASS"] / (LDW_UNITS["length"] * LDW_UNITS["velocity"] ** 2)
@@ -233,4 +233,37 @@ def ldw_setup(obj, x1, x2):
     obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
     obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
     fr, ft, fp = ldw_flux_tables(x1, x2)
-    obj.set_ldw(params=LDW_PARAMS, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)
+    if fit:
+        t, M, lt, lM = ldw_mfit_tables(x1, x2)
+        obj.set_ldw(params=dict(LDW_PARAMS, KRAD=999.0, ALPHARAD=999.0), units=LDW_UNITS, flux_r=fr, flux_t=ft,
+                    flux_p=fp, t_fit=lt, m_fit=lM)
+    else:
+        obj.set_ldw(params=LDW_PARAMS, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)
+
+
+LDW_MPOINTS = 12
+
+
+def ldw_mfit_tables(x1, x2, mpoints=LDW_MPOINTS):
+    """Synthetic force-multiplier fit M(t) per zone for the KRAD = ALPHARAD = 999 mode of LineForce()
+    (M_UV_data.dat, line_connect.c:185-256): t on a decade grid, M = k(zone) t^-0.6 capped at 2000.
+    Returns (t, M[mpoints][1][ny][nx]) as written to the file (text round trip) and their log10 taken
+    with libm (math.log10), which is what the reference stores in t_fit / M_UV_fit."""
+    import math
+    t = np.array([float("%.17e" % (10.0 ** e)) for e in np.linspace(-9.0, 2.0, mpoints)])
+    kz = 0.3 + 0.5 * (np.sin(3.0 * np.asarray(x1))[None, None, :] ** 2) * (0.5 + 0.5 * np.cos(2.0 * np.asarray(x2))[None, :, None])
+    M = np.minimum(kz[None] * t[:, None, None, None] ** -0.6, 2000.0)
+    M = np.vectorize(lambda q: float("%.17e" % q))(M)
+    lt = np.array([math.log10(v) for v in t])
+    lM = np.vectorize(math.log10)(M)
+    return t, M, lt, lM
+
+
+def write_ldw_mfit_file(wd, x1, x2, ng, t, M):
+    with open(Path(wd) / "M_UV_data.dat", "w") as f:
+        f.write("# %d\n" % len(t))
+        f.write("t " + " ".join("%.17e" % v for v in t) + "\n")
+        for j in range(ng, len(x2) - ng):
+            for i in range(ng, len(x1) - ng):
+                vals = " ".join("%.17e" % M[m, 0, j, i] for m in range(len(t)))
+                f.write("%d %d %.17e %.17e %s\n" % (i - ng, j - ng, x1[i] * LDW_UNITS["length"], x2[j], vals))

@@ -151,6 +151,8 @@ CASES4 = {
     # with the BLONDIN source step (Strang alternation of Src/main.c:479-485); the prefactor tables
     # of a first (non-restart) run are never assigned by the reference (Src/initialize.c:505-520)
     "ldw_cool_hll": dict(cfg="ldw", grid=LDW_GRID, solver="hll", maxsteps=9, cooling=True),
+    # force multiplier from the per-zone M(t) fit file instead of k t^alpha (KRAD = ALPHARAD = 999)
+    "ldw_nocool_fit_hll": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hll", maxsteps=8, cooling=False, fit=True),
 }
 
 
@@ -165,9 +167,14 @@ def make_case4(out, name, c):
     fr, ft, fp = common.ldw_flux_tables(x1, x2)
     with tempfile.TemporaryDirectory() as wd:
         common.write_ldw_flux_files(wd, x1, x2, ng, fr, ft, fp)
+        params = common.LDW_PARAMS
+        if c.get("fit"):
+            t, M, lt, lM = common.ldw_mfit_tables(x1, x2)
+            common.write_ldw_mfit_file(wd, x1, x2, ng, t, M)
+            params = dict(params, KRAD=999.0, ALPHARAD=999.0)
         r = refrun.run(c["cfg"], wd, shape=(1, nx[1], nx[0]), nvar=6, maxsteps=c["maxsteps"],
                        grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
-                       solver=c["solver"], bcs=common.LDW_BCS, dbl=(-1.0, 1), params=common.LDW_PARAMS, timeout=250)
+                       solver=c["solver"], bcs=common.LDW_BCS, dbl=(-1.0, 1), params=params, timeout=250)
     nd_ = len(r["data"]) - 1
     steps = np.array(r["steps"][:nd_], dtype=np.float64)
     data = np.stack(r["data"][:nd_])
@@ -178,7 +185,7 @@ def make_case4(out, name, c):
                         gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-4, tstop=1.0,
                         ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=1,
                         body_force="vector", limiter="VANLEER_LIM", char_limiting=1, shock_flattening=1,
-                        entropy_switch=2, entr_codes=1, cooling=int(c["cooling"]))
+                        entropy_switch=2, entr_codes=1, cooling=int(c["cooling"]), fit=int(bool(c.get("fit"))))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 

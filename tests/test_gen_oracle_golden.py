@@ -38,7 +38,7 @@ def test_gen_oracle_ldw_per_step_matches_reference_dumps(name):
     flattening, characteristic limiting, tracer, spherical stretched grid."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
-    ldw_setup(o, o.x(0), o.x(1))
+    ldw_setup(o, o.x(0), o.x(1), fit="fit" in name)
     data, steps = g["data"], g["steps"]
     nfile = data.shape[1]
     for n in range(len(data) - 1):

@@ -112,7 +112,7 @@ def test_ldw_per_step_vs_reference_dumps(Hydro, name):
     g = load_golden(name)
     kw = gen_kwargs_from_golden(g)
     h = Hydro(**hydro_kwargs_from_gen(kw))
-    ldw_setup(h, h.x(0), h.x(1))
+    ldw_setup(h, h.x(0), h.x(1), fit="fit" in name)      # ..._fit_...: M(t) fit tables instead of k t^alpha
     data, steps = g["data"], g["steps"]
     nfile = data.shape[1]
     for n in range(len(data) - 1):
