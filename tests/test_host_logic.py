@@ -82,3 +82,34 @@ def test_runtime_parse(tmp_path):
     assert rt.left_bound == ["reflective", "periodic", "reflective"]
     assert rt.right_bound == ["outflow", "periodic", "outflow"]
     assert rt.params["GAMMA"] == 1.4
+
+
+def test_make_grid_matches_the_grid_restated_for_the_oracle_and_grid_out(tmp_path):
+    """pluto_sirocco_b200.make_grid (what a Python caller hands to pb200_set_grid) and
+    oracle/pluto_grid.make_grid (the restatement the oracle was pinned with) are independent
+    transcriptions of Src/set_grid.c:395-450,100-127 and must agree bit for bit; both agree with
+    the 12 digits the reference prints into grid.out when its executable is available."""
+    import numpy as np
+    import pluto_grid
+    from pluto_sirocco_b200 import make_grid
+    specs = [(0.0, 37, 1.0), (-0.5, 16, 0.5, "u"), (0.87, 48, 8.7, "r", 1.05), (0.0, 36, 1.5707963267948966, "r", 0.95)]
+    for spec in specs:
+        for ng in (0, 2, 3):
+            a = make_grid(spec, ng)
+            b = pluto_grid.make_grid(spec, ng)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+            xl, xr, dx = a
+            assert np.all(xr > xl) and np.allclose(xr - xl, dx, rtol=1e-13)
+            assert abs(xl[ng] - spec[0]) < 1e-15 and abs(xr[len(xl) - ng - 1] - spec[2]) < 1e-12 * max(1.0, abs(spec[2]))
+    import refrun
+    if refrun.have_ref("sph2d"):
+        grid = [specs[2], specs[3], (0.0, 1, 1.0)]
+        refrun.run("sph2d", tmp_path, shape=(1, 36, 48), nvar=6, maxsteps=0, timeout=60,
+                   grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-5, solver="hll",
+                   bcs=("outflow",) * 6, dbl=(-1.0, 1), params=dict(GM=1.0, RBLOB=2.0, TBLOB=1.0, PBLOB=5.0))
+        rows = [l.split() for l in (tmp_path / "grid.out").read_text().splitlines() if l and not l.startswith("#")]
+        n1 = int(rows[0][0])
+        ref1 = np.array([[float(r[1]), float(r[2])] for r in rows[1:1 + n1]])
+        xl, xr, _ = make_grid(specs[2], 0)
+        assert np.allclose(ref1[:, 0], xl, rtol=1e-11, atol=1e-12) and np.allclose(ref1[:, 1], xr, rtol=1e-11, atol=1e-12)
