@@ -4,7 +4,7 @@ from pathlib import Path
 import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-_GEN_PREFIXES = ("sph", "ldw")     # general-grid fixtures (GenOracle / the gen path of the library)
+_GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(_GEN_PREFIXES))
 GEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_GEN_PREFIXES))
 
@@ -61,6 +61,8 @@ def gen_kwargs_from_golden(g):
 
 def set_point_mass_gravity(obj, gm):
     """BodyForceVector of oracle/problems/sph/init.c: g = (-GM/x1^2, 0, 0) at the zone centres."""
+    if not getattr(obj, "cfg", getattr(obj, "c", None)).body_force:
+        return
     x1 = obj.x(0)
     obj.set_body_force_vector(0, (-gm / (x1 * x1)).reshape(1, 1, -1))
     obj.set_body_force_vector(1, np.zeros((1, 1, 1)))

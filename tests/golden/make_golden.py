@@ -103,6 +103,11 @@ CASES3 = {
                            char_limiting=True, limiter="VANLEER_LIM", shock_flattening=True, entropy_switch=True),
     "sph2d_sel_hllc": dict(cfg="sph2d_sel", dims=2, grid=SPH_GRID2, solver="hllc", bcs=SPH_BCS, maxsteps=12,
                            entropy_switch="SELECTIVE"),
+    # Cartesian, stretched grids: the FAST path with a non-uniform grid->dx (UNIFORM_CARTESIAN_GRID limiters)
+    "cart3d_stretched_hllc": dict(cfg="sedov3d", dims=3, geometry="CARTESIAN", ntracer=0, body_force="none",
+                                  grid=[(0.0, 20, 1.0, "r", 1.06), (0.0, 16, 1.0, "r", 0.95), (0.0, 12, 1.0)],
+                                  solver="hllc", bcs=("reflective", "outflow") * 3, maxsteps=10,
+                                  params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4), gamma=1.4, cfl=0.3, first_dt=1e-9, tstop=0.5),
     "sph1d_tvdlf": dict(cfg="sph1d", dims=1, grid=[(1.0, 64, 4.0, "r", 1.02), (1.0, 1, 1.2), (0.0, 1, 1.0)],
                         solver="tvdlf", bcs=("reflective", "outflow") * 3, maxsteps=10),
     "sph3d_hllc": dict(cfg="sph3d", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
@@ -116,12 +121,13 @@ def make_case3(out, name, c):
     nd = c["dims"]
     grid = c["grid"]
     nx = [int(grid[d][1]) if d < nd else 1 for d in range(3)]
-    ntr = 1
+    ntr = c.get("ntracer", 1)
     nvar = 5 + ntr      # ENTR is not written: Boundary() recomputes it (ComputeEntropy)
     with tempfile.TemporaryDirectory() as wd:
         r = refrun.run(c["cfg"], wd, shape=(nx[2], nx[1], nx[0]), nvar=nvar, maxsteps=c["maxsteps"],
-                       grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=10.0, first_dt=1e-5,
-                       solver=c["solver"], bcs=c["bcs"], dbl=(-1.0, 1), params=SPH_PAR, timeout=120)
+                       grid=[pluto_grid.ini_string(g) for g in grid], cfl=c.get("cfl", 0.4), tstop=c.get("tstop", 10.0),
+                       first_dt=c.get("first_dt", 1e-5), solver=c["solver"], bcs=c["bcs"], dbl=(-1.0, 1),
+                       params=c.get("params", SPH_PAR), timeout=120)
     nd_ = len(r["data"]) - 1
     steps = np.array(r["steps"][:nd_], dtype=np.float64)
     data = np.stack(r["data"][:nd_])
@@ -129,9 +135,10 @@ def make_case3(out, name, c):
                          g[4] if len(g) > 4 else 1.0] for g in grid], dtype=np.float64)
     np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx), dims=nd,
                         recon="LINEAR", rk="RK2", solver=c["solver"], bcs=np.array(c["bcs"]),
-                        gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-5, tstop=10.0,
-                        ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=ntr,
-                        body_force="vector", gm=SPH_PAR["GM"], limiter=c.get("limiter", "DEFAULT"),
+                        gamma=c.get("gamma", 5. / 3.), cfl=c.get("cfl", 0.4), cfl_max_var=1.1, first_dt=c.get("first_dt", 1e-5),
+                        tstop=c.get("tstop", 10.0),
+                        ref_config=c["cfg"], gridspec=gridarr, geometry=c.get("geometry", "SPHERICAL"), ntracer=ntr,
+                        body_force=c.get("body_force", "vector"), gm=SPH_PAR["GM"], limiter=c.get("limiter", "DEFAULT"),
                         char_limiting=int(c.get("char_limiting", False)),
                         shock_flattening=int(c.get("shock_flattening", False)),
                         entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],

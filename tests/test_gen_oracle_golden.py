@@ -7,7 +7,7 @@ import pytest
 from common import GEN_CASES, gen_kwargs_from_golden, ldw_setup, load_golden, rel_err, set_point_mass_gravity
 from gen_oracle import GenOracle
 
-SPH_CASES = [c for c in GEN_CASES if c.startswith("sph")]
+SPH_CASES = [c for c in GEN_CASES if c.startswith(("sph", "cart"))]
 
 
 @pytest.mark.parametrize("name", SPH_CASES)

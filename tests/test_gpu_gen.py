@@ -9,7 +9,7 @@ from common import (GEN_CASES, TOL_STEP, gen_kwargs_from_golden, hydro_kwargs_fr
 from gen_oracle import GenOracle
 
 pytestmark = pytest.mark.gpu
-SPH_CASES = [c for c in GEN_CASES if c.startswith("sph")]
+SPH_CASES = [c for c in GEN_CASES if c.startswith(("sph", "cart"))]      # cart*: stretched Cartesian grids on the FAST path
 
 
 @pytest.fixture(scope="module")
