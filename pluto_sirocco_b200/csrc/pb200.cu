@@ -373,6 +373,16 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   CK(cudaSetDevice(c->cfg.device));
   c->launches = 0;
   c->nprof = 0;
+  if (c->cfg.reconstruction == PB200_PARABOLIC) {
+    // PPM_CoefficientsSet() derives grid-dependent weights on non-uniform grids (ppm_coeffs.c:124-136);
+    // the kernels carry the uniform-grid weights of PPM_CartCoeff() (ppm_coeffs.c:468-509) only
+    for (int d = 0; d < c->dev.ndim; d++) {
+      const std::vector<double> &dx = c->dx[d];
+      for (size_t i = 1; i < dx.size(); i++)
+        if (fabs(dx[i] - dx[0]) > 1e-12 * fabs(dx[0]))
+          return fail(PB200_ENOTSUP, "RECONSTRUCTION PARABOLIC on a non-uniform grid is not built");
+    }
+  }
   if (c->gen) {
     int rc = pb200_gen_setup(c);
     if (rc) return fail(rc, "general-grid set-up failed (out of device memory?)");

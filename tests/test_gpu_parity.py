@@ -308,6 +308,21 @@ def test_errors(Hydro):
     h.close()
 
 
+def test_ppm_on_stretched_grid_is_refused(Hydro):
+    """The reference derives grid-dependent PPM weights on non-uniform grids (ppm_coeffs.c:124-136);
+    the kernels only carry the uniform ones, so the library must say so instead of computing."""
+    from pluto_sirocco_b200 import make_grid
+    from pluto_sirocco_b200._lib import ENOTSUP, PB200Error
+    arrays = [make_grid((0.0, 32, 1.0, "r", 1.05), 3), make_grid((0.0, 1, 1.0), 0), make_grid((0.0, 1, 1.0), 0)]
+    h = Hydro(dimensions=1, nx=(32, 1, 1), reconstruction="PARABOLIC", time_stepping="RK3", grid_arrays=arrays)
+    v = np.ones((5, 1, 1, 32)); v[1:4] = 0
+    h.set_interior(v)
+    with pytest.raises(PB200Error) as ei:
+        h.advance_step(1e-3)
+    assert ei.value.code == ENOTSUP
+    h.close()
+
+
 def test_uniform_state_is_a_fixed_point(Hydro):
     h = Hydro(dimensions=3, nx=(32, 16, 8), gamma=1.4, bcs=("periodic",) * 6)
     v = np.zeros((5, 8, 16, 32)); v[0] = 2.0; v[1] = 0.3; v[2] = -0.2; v[3] = 0.1; v[4] = 1.5
