@@ -101,3 +101,23 @@ def test_dropin_executable_matches_reference_executable(cuda_lib, tmp_path, cfg,
     assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
     # end of the run: 1e-9 relative L1
     assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    ("sod", dict(shape=(1, 1, 400), grid=[(0, 400, 1), (0, 1, 1), (0, 1, 1)], cfl=0.8, tstop=0.2, first_dt=1e-4,
+                 bcs=SOD_BCS, params={"SCRH": 0})),
+    ("sedov3d", dict(shape=(24, 24, 24), grid=[(0, 24, 1)] * 3, bcs=("reflective", "outflow") * 3,
+                     params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4), cfl=0.3, tstop=0.05, first_dt=1e-9)),
+])
+def test_dropin_full_test_problem_run(cuda_lib, tmp_path, cfg, kw):
+    """The whole test problem to its tstop (C1: Sod to t = 0.2; Sedov 24^3 to t = 0.05), free running:
+    same number of steps and <= 1e-9 relative L1 at the end (north-star tolerance for a full run)."""
+    exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
+    if not exe.exists() or not refrun.have_ref(cfg):
+        pytest.skip("drop-in / reference executables were not built in the container (needs /root/reference)")
+    ref = refrun.run(cfg, tmp_path / "ref", solver="hllc", dbl=(10.0, -1), **kw)       # dumps: t = 0 and the end
+    got = refrun.run(cfg, tmp_path / "b200", solver="hllc", dbl=(10.0, -1), exe=exe, env={"PB200_RESIDENT": "1"}, **kw)
+    assert len(ref["data"]) == len(got["data"]) == 2
+    assert ref["steps"][-1][0] == got["steps"][-1][0] > 100                 # same step count, a real run
+    assert abs(ref["steps"][-1][1] - got["steps"][-1][1]) <= 1e-12 * ref["steps"][-1][1]
+    assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
