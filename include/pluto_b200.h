@@ -200,9 +200,9 @@ int  pb200_boundary(pb200_ctx *ctx);
 int  pb200_advance_step(pb200_ctx *ctx, double dt, pb200_step_info *info);
 
 /* Same call on HOST buffers (the strict drop-in: d->Vc is authoritative on the host):
- * H2D of vc_host, AdvanceStep, D2H back into vc_host.  For 3-D RK2 runs on the Cartesian path with
+ * H2D of vc_host, AdvanceStep, D2H back into vc_host.  For 3-D runs (any RK order) on the Cartesian path with
  * non-periodic x3 sides the three phases are pipelined over slabs of x3 planes (upload of slab
- * s+1, both stages on the slabs that are ready, download of finished slabs all overlap), so the
+ * s+1, the RK stages on the slabs that are ready, download of finished slabs all overlap), so the
  * call costs about one PCIe direction; results are identical to pb200_advance_step().  Ghost zones
  * of vc_host are not written back.  PB200_HOST_PIPELINE=<planes per slab> (0: off). */
 int  pb200_advance_step_host(pb200_ctx *ctx, double *vc_host, double dt, pb200_step_info *info);

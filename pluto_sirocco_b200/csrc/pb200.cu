@@ -546,9 +546,9 @@ extern "C" int pb200_advance_step(pb200_ctx *c, double dt, pb200_step_info *info
   return pb200_step_end(c, info);
 }
 
-// AdvanceStep on a HOST d->Vc as a slab-wise pipeline (3-D, RK2, fast path): the x3 planes travel
-// up in slabs, stage 1 runs on slab s as soon as slab s+1 has arrived, stage 2 on slab s-1 as soon
-// as stage 1 of slab s is done, and every finished slab travels back while the next ones are still
+// AdvanceStep on a HOST d->Vc as a slab-wise pipeline (3-D, fast path, any RK order): the x3 planes
+// travel up in slabs, stage 1 runs on slab s as soon as slab s+1 has arrived, stage 2 on slab s-1 as
+// soon as stage 1 of slab s is done (stage 3 on slab s-2), and every finished slab travels back while the next ones are still
 // being computed - upload, compute and download overlap, so the call costs about one PCIe
 // direction instead of two plus the compute.  Same kernels, same arithmetic as pb200_advance_step.
 static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200_step_info *info) {
@@ -569,7 +569,7 @@ static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200
   }
   int rc = pb200_step_begin(c, dt);
   if (rc) return rc;
-  double *A = c->V[c->stage_in[1]], *B = c->V[c->stage_out[1]];
+  double *A = c->V[c->stage_in[1]];
   const size_t plane = (size_t)D.sk;
   auto kbeg = [&](int s) { return s == 0 ? 0 : D.beg[2] + rel0(s); };                // absolute planes of slab s,
   auto kend = [&](int s) { return s == S - 1 ? D.tot[2] : D.beg[2] + rel1(s); };     // ghosts ride with the end slabs
@@ -580,12 +580,16 @@ static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200
     }
     CK(cudaEventRecord(c->ev_up[s], c->h2d));
   }
-  SweepArgs a1, a2;
-  rc = stage_args(c, 1, a1);
-  if (rc) return rc;
-  rc = stage_args(c, 2, a2);
-  if (rc) return rc;
-  auto run_slab = [&](int stage, SweepArgs a, double *Vin, int q) -> int {
+  const int NS = c->nstages;
+  SweepArgs sa[4];
+  for (int st = 1; st <= NS; st++) {
+    rc = stage_args(c, st, sa[st]);
+    if (rc) { c->in_step = false; return rc; }
+  }
+  double *R = c->V[c->stage_out[NS]];                                           // the step's result array
+  auto run_slab = [&](int stage, int q) -> int {
+    SweepArgs a = sa[stage];
+    double *Vin = c->V[c->stage_in[stage]];
     const int k0 = rel0(q), k1 = rel1(q);                                       // relative to KBEG
     unsigned sides = 0x0f;                                                      // x1, x2 sides of these planes
     int r = boundary_on(c, Vin, sides, D.beg[2] + k0, D.beg[2] + k1);
@@ -595,29 +599,27 @@ static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200
     a.k0 = k0; a.k1 = k1;
     launch_sweep(c, 1, a);
     launch_sweep(c, 2, a);
-    (void)stage;
-    return PB200_OK;
-  };
-  auto finish_slab = [&](int q) -> int {
-    int r = run_slab(2, a2, B, q);
-    if (r) return r;
-    CK(cudaEventRecord(c->ev_done[q], c->stream));
+    if (stage < NS) return PB200_OK;
+    CK(cudaEventRecord(c->ev_done[q], c->stream));                              // last stage: slab q is final
     CK(cudaStreamWaitEvent(c->d2h, c->ev_done[q], 0));
-    const int k0 = D.beg[2] + rel0(q), k1 = D.beg[2] + rel1(q);
     for (int nv = 0; nv < c->nvar; nv++) {
-      size_t o = (size_t)nv * D.sv + (size_t)k0 * plane;
-      CK(cudaMemcpyAsync(h + o, A + o, (size_t)(k1 - k0) * plane * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+      size_t o = (size_t)nv * D.sv + (size_t)(D.beg[2] + k0) * plane;
+      CK(cudaMemcpyAsync(h + o, R + o, (size_t)(k1 - k0) * plane * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
     }
     return PB200_OK;
   };
-  for (int s = 0; s < S; s++) {
-    CK(cudaStreamWaitEvent(c->stream, c->ev_up[s + 1 < S ? s + 1 : S - 1], 0));
-    rc = run_slab(1, a1, A, s);
-    if (rc) { c->in_step = false; return rc; }
-    if (s >= 1) { rc = finish_slab(s - 1); if (rc) { c->in_step = false; return rc; } }
+  // stage st works on slab s-(st-1): its x3 sweep reads the planes next to the slab, which the
+  // stage before it produced one slab ahead earlier in the same iteration; a stage's output slab
+  // is never one that a running earlier stage still reads (slabs are >= 2*nghost planes thick).
+  for (int s = 0; s < S + NS - 1; s++) {
+    if (s < S) CK(cudaStreamWaitEvent(c->stream, c->ev_up[s + 1 < S ? s + 1 : S - 1], 0));
+    for (int st = 1; st <= NS; st++) {
+      const int q = s - (st - 1);
+      if (q < 0 || q >= S) continue;
+      rc = run_slab(st, q);
+      if (rc) { c->in_step = false; return rc; }
+    }
   }
-  rc = finish_slab(S - 1);
-  if (rc) { c->in_step = false; return rc; }
   CK(cudaGetLastError());
   rc = pb200_step_end(c, info);
   CK(cudaStreamSynchronize(c->d2h));
@@ -634,7 +636,7 @@ extern "C" int pb200_advance_step_host(pb200_ctx *c, double *vc_host, double dt,
     const bool x3_ok = c->cfg.bc[4] != PB200_BC_PERIODIC && c->cfg.bc[5] != PB200_BC_PERIODIC &&
                        c->cfg.bc[4] != PB200_BC_NEIGHBOUR && c->cfg.bc[5] != PB200_BC_NEIGHBOUR &&
                        c->cfg.bc[4] != PB200_BC_USERDEF && c->cfg.bc[5] != PB200_BC_USERDEF;
-    if (!c->gen && D.ndim == 3 && c->nstages == 2 && c->host_pipeline >= 2 * c->cfg.nghost &&
+    if (!c->gen && D.ndim == 3 && c->host_pipeline >= 2 * c->cfg.nghost &&
         nk >= 3 * c->host_pipeline && x3_ok && !c->profiling)
       return advance_step_host_pipelined(c, vc_host, dt, info);
   }

@@ -232,17 +232,20 @@ def test_host_call_equals_resident_call(Hydro):
     h1.close(); h2.close()
 
 
-@pytest.mark.parametrize("recon,bcs,ntr,bf", [
-    ("LINEAR", ("reflective", "outflow") * 3, 0, 0),
-    ("PARABOLIC", ("periodic", "periodic", "outflow", "reflective", "outflow", "reflective"), 1, 1),
+@pytest.mark.parametrize("recon,rk,bcs,ntr,bf", [
+    ("LINEAR", "RK2", ("reflective", "outflow") * 3, 0, 0),
+    ("PARABOLIC", "RK2", ("periodic", "periodic", "outflow", "reflective", "outflow", "reflective"), 1, 1),
+    ("PARABOLIC", "RK3", ("outflow", "reflective", "periodic", "periodic", "reflective", "outflow"), 1, 0),
+    ("LINEAR", "EULER", ("outflow",) * 6, 0, 0),
 ])
-def test_pipelined_host_call_equals_resident_call_3d(Hydro, monkeypatch, recon, bcs, ntr, bf):
-    """pb200_advance_step_host() pipelines upload / both stages / download over slabs of x3 planes
-    (3-D, RK2): identical results to the resident call, ragged last slab included."""
+def test_pipelined_host_call_equals_resident_call_3d(Hydro, monkeypatch, recon, rk, bcs, ntr, bf):
+    """pb200_advance_step_host() pipelines upload / all RK stages / download over slabs of x3 planes
+    (3-D, stage q running q-1 slabs behind stage 1): identical results to the resident call, ragged
+    last slab included."""
     import torch
     monkeypatch.setenv("PB200_HOST_PIPELINE", "8")
     nx = (40, 24, 45)                      # 45 planes: 5 slabs of 8, the last one 13 planes thick
-    kw = dict(dimensions=3, nx=nx, gamma=1.4, reconstruction=recon, time_stepping="RK2", bcs=bcs, ntracer=ntr,
+    kw = dict(dimensions=3, nx=nx, gamma=1.4, reconstruction=recon, time_stepping=rk, bcs=bcs, ntracer=ntr,
               body_force=bf)
     h1, h2 = Hydro(**kw), Hydro(**kw)
     if bf:
