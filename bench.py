@@ -377,7 +377,7 @@ def run_b200(args):
         nbytes = int(np.prod(h.shape)) * 8
         e2e = {"value": zones_total * ne / (ems * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": ne,
-               "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, both RK stages and "
+               "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, the RK stages and "
                       "download pipelined over slabs of x3 planes)"}
 
     if rank != 0:
