@@ -30,7 +30,8 @@ enum { GEO_CARTESIAN = 1, GEO_SPHERICAL = 4 };
 struct LdwDev {
   int on, userdef_bc, nangles;
   const double *flux_r, *flux_t, *flux_p;   // [nangles][k][j][i]
-  double *dvds;                             // dvds_array^(-alpha) [nangles][k][j][i] (0 where dvds <= 0)
+  const unsigned long long *mask;           // bit a of zone o: |flux| != 0 in angular bin a (gen_ldw_mask)
+  double *gline;                            // line force [2][k][j][i]: g_r for the r sweep, g_theta for the theta sweep
   const double *sin_a, *cos_a;              // sin/cos((a + 1/2) 2 pi / 36), libm values from the host
   const double *sin_t, *cos_t;              // sin/cos(x2[j])
   const double *xgc1, *xgc2;                // grid->xgc (mid-plane reset uses the centroids)
@@ -359,10 +360,66 @@ PB_D void gen_bilinear(const double (&x11)[2], const double (&x22)[2], const dou
   ans[1] = (1.0 - f2) * a + f2 * b;
 }
 
+// The only use VGradCalc() makes of the flux tables is the test |F| != 0 per zone and bin
+// (line_connect.c:560-575): the tables change when new SIROCCO fluxes arrive, not per step, so
+// the test is taken once per hand-over and kept as one bit per bin - 8 B per zone in place of
+// 3 x 36 x 8 B read by every gen_vgrad launch.
+static __global__ void gen_ldw_mask(LdwDev w, long nz, unsigned long long *mask) {
+  const long o = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nz) return;
+  unsigned long long m = 0ull;
+  for (int ia = 0; ia < w.nangles; ia++) {
+    const double fr = w.flux_r[ia * nz + o], ft = w.flux_t[ia * nz + o], fp = w.flux_p ? w.flux_p[ia * nz + o] : 0.0;
+    if (sqrt(fr * fr + ft * ft + fp * fp) != 0.0) m |= 1ull << ia;
+  }
+  mask[o] = m;
+}
+
+// LineForce(), line_connect.c:815-903, split into its per-zone and per-bin parts.
+// Per zone and sweep: S = sigma_e rho v_th of the sweep's centre state (the r sweep passes
+// (vp + vm)/2, the theta sweep the zone value: rhs_source.c:229-232) and, for the KRAD / ALPHARAD
+// power law, kS = k S^alpha.
+struct LdwZone { double S, kS; };
+PB_D LdwZone gen_ldw_zone(const LdwDev &w, double rho_code, double prs_code) {
+  const double rho = rho_code * w.UD;
+  const double T = prs_code / rho_code * w.kelvin_mu;
+  const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
+  LdwZone z;
+  z.S = w.sigma_e * rho * v_th;
+  z.kS = w.mpoints > 0 ? 0.0 : w.krad * pow(z.S, w.alpharad);
+  return z;
+}
+// Per bin: the force multiplier M(t), capped at M_max = 4400.  D = dvds^(-alpha) for the power law
+// (M = k (S / dvds)^alpha = kS D), D = dvds itself for the per-zone fit; 0 where dvds <= 0.
+PB_D double gen_ldw_M(const LdwDev &w, const LdwZone &z, double D, long o, long nz) {
+  if (w.mpoints <= 0) return fmin(z.kS * D, 4400.0);
+  if (!(D > 0.0)) return 0.0;
+  // linterp(log10 t, t_fit, M_UV_fit[.][zone]), line_connect.c:781-811
+  const double x = log10(z.S / D);
+  int idx = 0;
+  while (idx < w.mpoints && __ldg(w.t_fit + idx) < x) idx++;
+  double y;
+  if (idx == 0) y = __ldg(w.m_fit + o);
+  else if (idx >= w.mpoints) y = __ldg(w.m_fit + (long)(w.mpoints - 1) * nz + o);
+  else {
+    const double xl = __ldg(w.t_fit + idx - 1), xh = __ldg(w.t_fit + idx);
+    const double yl = __ldg(w.m_fit + (long)(idx - 1) * nz + o), yh = __ldg(w.m_fit + (long)idx * nz + o);
+    y = yl + (yh - yl) / (xh - xl) * (x - xl);
+  }
+  double M = pow(10.0, y);
+  if (!(M == M)) M = 0.0;
+  return fmin(M, 4400.0);
+}
+
 // VGradCalc(), line_connect.c:504-744: one thread per zone, looping over the angular bins so that
 // everything that does not depend on the bin (vertex velocities, interpolation box, the velocity at
 // the cell centre) is computed once; the offsets that the reference tabulates once
-// (dvds_r/t/mod_offset) are recomputed, they only depend on the grid
+// (dvds_r/t/mod_offset) are recomputed, they only depend on the grid.
+// The kernel also takes the sums of LineForce() while the gradient of a bin is still in a register:
+// the reference stores dvds_array[36][zones] and every sweep walks it again together with the flux
+// tables (3 x 155 MB per sweep on the 1024 x 512 grid, more than L2 holds); here the 36-bin tables
+// are read ONCE per stage and the sweeps pick up one number per zone.  It runs after States() of
+// the r sweep because that sweep's force uses (vp + vm)/2 as its centre state.
 static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
   int i, j, k;
   if (!gen_zone(b.lo, b.hi, i, j, k)) return;
@@ -395,12 +452,18 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
   const double vx1 = (ans1[0] * w.UV * st + ans1[1] * w.UV * ct);
   const double vz1 = (ans1[0] * w.UV * ct - ans1[1] * w.UV * st);
   const double x = x1i * st * w.UL, z = x1i * ct * w.UL;
+  const unsigned long long mk = __ldg(w.mask + o);
+  const long nz = d.sv;
+  // centre states of the two sweeps (rhs_source.c:229-232)
+  const LdwZone zr = gen_ldw_zone(w, 0.5 * (a.VP[iRHO * nz + o] + a.VM[iRHO * nz + o]),
+                                  0.5 * (a.VP[iPRS * nz + o] + a.VM[iPRS * nz + o]));
+  const LdwZone zt = gen_ldw_zone(w, a.V[iRHO * nz + o], a.V[iPRS * nz + o]);
+  const double coef = w.sigma_e / (2.99792458e10 * w.unit_acc);
+  double g_r = 0.0, g_t = 0.0;
   for (int ia = 0; ia < w.nangles; ia++) {
-    const double fr = __ldg(w.flux_r + ia * d.sv + o), ft = __ldg(w.flux_t + ia * d.sv + o);
-    const double fp = w.flux_p ? __ldg(w.flux_p + ia * d.sv + o) : 0.0;
-    const double mod_flux = sqrt(fr * fr + ft * ft + fp * fp);
+    const double fr = __ldg(w.flux_r + ia * nz + o), ft = __ldg(w.flux_t + ia * nz + o);
     double D = 0.0;
-    if (mod_flux != 0.0) {
+    if ((mk >> ia) & 1ull) {   // mod_flux != 0
       const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
       const double dx1 = maxds * sa, dx2 = maxds * ca;
       const double ds = sqrt(dx1 * dx1 + dx2 * dx2);
@@ -415,54 +478,19 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
       const double v1 = sa * vx1 + ca * vz1;
       const double v2 = sa * vx2 + ca * vz2;
       const double out = fabs((v2 - v1) / ds);
-      // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per angle and SWEEP (the sweeps pass
-      // different centre states); the angle-dependent factor dvds^(-alpha) is taken here, once per
-      // stage, so that the sweeps are left with one pow() per zone instead of 36.
+      // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per bin and SWEEP (the sweeps pass
+      // different centre states); the bin-dependent factor dvds^(-alpha) is taken once and serves
+      // both, so that a zone costs one pow() per sweep instead of 36.
       // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
       if (out > 0.0) D = w.mpoints > 0 ? out : exp(-w.alpharad * log(out));   // fit mode keeps dvds itself
     }
-    w.dvds[ia * d.sv + o] = D;
-  }
-}
-
-// LineForce(), line_connect.c:815-903 (KRAD / ALPHARAD power law, capped at M_max = 4400)
-PB_D void gen_line_force(const GenDev &g, double rho_code, double prs_code, long o, double (&grad)[3]) {
-  const LdwDev &w = g.ldw;
-  const double rho = rho_code * w.UD;
-  const double T = prs_code / rho_code * w.kelvin_mu;
-  const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
-  grad[0] = grad[1] = grad[2] = 0.0;
-  const bool fit = w.mpoints > 0;
-  const double S = w.sigma_e * rho * v_th;
-  const double kS = fit ? 0.0 : w.krad * pow(S, w.alpharad);
-  const double coef = w.sigma_e / (2.99792458e10 * w.unit_acc);
-  for (int ia = 0; ia < w.nangles; ia++) {
-    const double D = __ldg(w.dvds + ia * g.d.sv + o);     // dvds^(-alpha) (fit mode: dvds), 0 where dvds <= 0
-    double M;
-    if (!fit) M = fmin(kS * D, 4400.0);
-    else if (!(D > 0.0)) M = 0.0;
-    else {                                                // linterp(log10 t, t_fit, M_UV_fit[.][zone]), line_connect.c:781-811
-      const double x = log10(S / D);
-      int idx = 0;
-      while (idx < w.mpoints && __ldg(w.t_fit + idx) < x) idx++;
-      double y;
-      if (idx == 0) y = __ldg(w.m_fit + o);
-      else if (idx >= w.mpoints) y = __ldg(w.m_fit + (long)(w.mpoints - 1) * g.d.sv + o);
-      else {
-        const double xl = __ldg(w.t_fit + idx - 1), xh = __ldg(w.t_fit + idx);
-        const double yl = __ldg(w.m_fit + (long)(idx - 1) * g.d.sv + o), yh = __ldg(w.m_fit + (long)idx * g.d.sv + o);
-        y = yl + (yh - yl) / (xh - xl) * (x - xl);
-      }
-      M = pow(10.0, y);
-      if (!(M == M)) M = 0.0;
-      M = fmin(M, 4400.0);
-    }
     // ((1 + M) sigma_e F / c) / UNIT_ACCELERATION with the two constant divisions folded into one
     // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)
-    const double q = (1.0 + M) * coef;
-    grad[0] += q * __ldg(w.flux_r + ia * g.d.sv + o);
-    grad[1] += q * __ldg(w.flux_t + ia * g.d.sv + o);
+    g_r += ((1.0 + gen_ldw_M(w, zr, D, o, nz)) * coef) * fr;
+    g_t += ((1.0 + gen_ldw_M(w, zt, D, o, nz)) * coef) * ft;
   }
+  w.gline[o] = g_r;
+  w.gline[nz + o] = g_t;
 }
 
 // UserDefBoundary(side == 0) of cv_idl (init.c:199-316): floors over the WHOLE array and the
@@ -729,7 +757,7 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
         gv[0] = bf_at(d, 0, i, j, k); gv[1] = bf_at(d, 1, i, j, k); gv[2] = bf_at(d, 2, i, j, k);
       } else {
         if (!g.ldw.on) continue;
-        gen_line_force(g, vg[iRHO], vg[iPRS], o, gv);
+        gv[0] = g.ldw.gline[o]; gv[1] = g.ldw.gline[nz + o]; gv[2] = 0.0;   // LineForce() sums taken by gen_vgrad
       }
       const double gd = dir == 0 ? gv[0] : (dir == 1 ? gv[1] : gv[2]);
       rn += dt * vg[iRHO] * gd;

@@ -100,6 +100,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->cur_stage = 0;
   for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
   c->ldw_dvds = nullptr;
+  c->ldw_mask = nullptr;
   c->ldw_mpoints = 0;
   c->ldw_tfit = c->ldw_mfit = nullptr;
   for (int q = 0; q < 7; q++) c->cool_tab[q] = nullptr;
@@ -198,6 +199,7 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   pb200_gen_release(c);
   for (int q = 0; q < 3; q++) if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
+  if (c->ldw_mask) cudaFree(c->ldw_mask);
   if (c->ldw_tfit) cudaFree(c->ldw_tfit);
   if (c->ldw_mfit) cudaFree(c->ldw_mfit);
   for (int q = 0; q < 7; q++) if (c->cool_tab[q]) cudaFree(c->cool_tab[q]);

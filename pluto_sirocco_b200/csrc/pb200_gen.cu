@@ -222,7 +222,8 @@ static void fill_ldw(pb200_ctx *c, GenDev &G) {
   w.userdef_bc = L.userdef_bc;
   w.nangles = L.nangles;
   w.flux_r = c->ldw_flux[0]; w.flux_t = c->ldw_flux[1]; w.flux_p = c->ldw_flux[2];
-  w.dvds = c->ldw_dvds;
+  w.gline = c->ldw_dvds;
+  w.mask = c->ldw_mask;
   w.UL = L.unit_length; w.UV = L.unit_velocity; w.UD = L.unit_density;
   const double KELVIN = L.unit_velocity * L.unit_velocity * amu / kB;      // pluto.h:560
   w.kelvin_mu = KELVIN * L.mu;
@@ -312,8 +313,11 @@ extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
     cudaMemset(c->ldw_flux[q], 0, n * sizeof(double));
   }
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
-  if (cudaMalloc(&c->ldw_dvds, n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "dvds array: out of device memory");
-  cudaMemset(c->ldw_dvds, 0, n * sizeof(double));
+  if (cudaMalloc(&c->ldw_dvds, 2 * c->dev.sv * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "line force: out of device memory");
+  cudaMemset(c->ldw_dvds, 0, 2 * c->dev.sv * sizeof(double));
+  if (c->ldw_mask) cudaFree(c->ldw_mask);
+  if (cudaMalloc(&c->ldw_mask, c->dev.sv * sizeof(unsigned long long)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "flux mask: out of device memory");
+  cudaMemset(c->ldw_mask, 0, c->dev.sv * sizeof(unsigned long long));
   return PB200_OK;
 }
 
@@ -343,6 +347,12 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
   if (cudaMemcpy(c->ldw_flux[1], ft, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
   if (fp) { if (cudaMemcpy(c->ldw_flux[2], fp, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA; }
   else cudaMemset(c->ldw_flux[2], 0, n);
+  LdwDev w;
+  memset(&w, 0, sizeof(w));
+  w.nangles = c->ldw.nangles;
+  w.flux_r = c->ldw_flux[0]; w.flux_t = c->ldw_flux[1]; w.flux_p = fp ? c->ldw_flux[2] : nullptr;
+  gen_ldw_mask<<<(unsigned)((c->dev.sv + 127) / 128), 128, 0, c->stream>>>(w, c->dev.sv, c->ldw_mask);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return pb200_fail(PB200_ECUDA, "flux mask kernel failed");
   return PB200_OK;
 }
 
@@ -422,16 +432,16 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
     c->launches++;
   }
-  if (c->ldw_on) {                              // VGradCalc, update_stage.c:138-140
-    gen_vgrad<<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom);
-    c->launches++;
-  }
   for (int dir = 0; dir < D.ndim; dir++) {
     a.dir = dir;
     GenBox bs = dom, bf = dom;
     bs.lo[dir] = D.beg[dir] - 1; bs.hi[dir] = D.end[dir] + 1;     // States(nbeg-1, nend+1)
     bf.lo[dir] = D.beg[dir] - 1; bf.hi[dir] = D.end[dir];         // Riemann(nbeg-1, nend)
     gen_states<NV><<<blocks(bs), T, 0, st>>>(G, a, bs);
+    if (dir == 0 && c->ldw_on) {                // VGradCalc (update_stage.c:138-140) + the sums of LineForce()
+      gen_vgrad<<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom);
+      c->launches++;
+    }
     gen_riemann<NV><<<blocks(bf), T, 0, st>>>(G, a, bf);
     gen_rhs<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
     c->launches += 3;

@@ -52,7 +52,8 @@ struct pb200_ctx {
   // line-driven wind
   bool ldw_on;
   pb200_ldw_config ldw;
-  double *ldw_flux[3], *ldw_dvds;
+  double *ldw_flux[3], *ldw_dvds;         // ldw_dvds: the two line-force arrays (g_r, g_theta) gen_vgrad leaves for the sweeps
+  unsigned long long *ldw_mask;           // per zone: bins with a non-zero flux (gen_ldw_mask)
   int ldw_mpoints;                        // force-multiplier fit (0: power law)
   double *ldw_tfit, *ldw_mfit;
   double *cool_tab[7];                    // BLONDIN tables (null: defaults)
