@@ -92,6 +92,13 @@ CONFIGS = {
     "sph2d_sel": dict(local="sph", overrides={"ENTROPY_SWITCH": "SELECTIVE"}, states="plm"),
     "sph1d": dict(local="sph", overrides={"DIMENSIONS": "1"}, states="plm"),
     "sph3d": dict(local="sph", overrides={"DIMENSIONS": "3"}, states="plm"),
+    # cylindrical (r, z) and polar (r, phi[, z]) geometry (oracle/problems/cyl)
+    "cyl2d": dict(local="cyl", overrides={}, states="plm"),
+    "cyl2d_nobf": dict(local="cyl", overrides={"BODY_FORCE": "NO"}, states="plm"),
+    "cyl2d_flat": dict(local="cyl", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
+                                               "SHOCK_FLATTENING": "MULTID"}, states="plm"),
+    "pol2d": dict(local="cyl", overrides={"GEOMETRY": "POLAR"}, states="plm"),
+    "pol3d": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "DIMENSIONS": "3"}, states="plm"),
     # C4: the line-driven disc wind of the sirocco coupling, UNMODIFIED user files of the reference
     # (Test_Problems/LineDrivenWind/cv_idl: init.c, definitions.h, userdef_output.c)
     "ldw": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={}, states="plm",

@@ -8,7 +8,7 @@
  * by oracle/build_ref.py with the user files of oracle/problems/) through the golden dumps of
  * tests/golden/ (tests/test_gen_oracle_golden.py).
  *
- * Scope: PHYSICS HD, EOS IDEAL, GEOMETRY CARTESIAN or SPHERICAL, DIMENSIONS 1-3, uniform or
+ * Scope: PHYSICS HD, EOS IDEAL, GEOMETRY CARTESIAN, CYLINDRICAL, POLAR or SPHERICAL, DIMENSIONS 1-3, uniform or
  * non-uniform grids (grid->xl/xr are inputs: the reference's own set_grid.c output),
  * RECONSTRUCTION LINEAR with every LIMITER, CHAR_LIMITING NO/YES, SHOCK_FLATTENING NO/MULTID,
  * ENTROPY_SWITCH NO/ALWAYS, NTRACER >= 0, BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3,
@@ -40,6 +40,8 @@
 #define FLAG_CONS2PRIM_FAIL 64
 
 #define CARTESIAN 1
+#define CYLINDRICAL 2
+#define POLAR 3
 #define SPHERICAL 4
 
 #define MAXV(a, b) ((a) >= (b) ? (a) : (b))
@@ -50,7 +52,7 @@
 typedef struct gen_cfg {
   int ndim, nx[3], ng;
   int ntracer, entropy;     /* NTRACER; ENTROPY_SWITCH: 0 NO, 1 SELECTIVE, 2 ALWAYS (pluto.h:60-61) */
-  int geometry;             /* CARTESIAN 1, SPHERICAL 4 (pluto.h:34-37) */
+  int geometry;             /* CARTESIAN 1, CYLINDRICAL 2, POLAR 3, SPHERICAL 4 (pluto.h:34-37) */
   int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
   int char_limiting;        /* CHAR_LIMITING */
   int flattening;           /* SHOCK_FLATTENING MULTID */
@@ -137,7 +139,10 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
   for (int i = 0; i < n1; i++) {   /* set_geometry.c:83-97 */
     double xL = x1m[i], xR = x1p[i];
     if (c->geometry == CARTESIAN) { g->xgc[0][i] = x1[i]; g->rt[i] = x1[i]; }
-    else {
+    else if (c->geometry == CYLINDRICAL || c->geometry == POLAR) {
+      g->xgc[0][i] = x1[i] + dx1[i] * dx1[i] / (12.0 * x1[i]);
+      g->rt[i] = x1[i];
+    } else {
       g->xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
       g->rt[i] = (xR * xR * xR - xL * xL * xL) / (xR * xR - xL * xL) / 1.5;
     }
@@ -161,6 +166,9 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
     double v;
     if (c->geometry == CARTESIAN) {
       v = dx1[i]; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * dx3[k];
+    } else if (c->geometry == CYLINDRICAL || c->geometry == POLAR) {   /* set_geometry.c:124-129 */
+      double dVr = fabs(x1[i]) * dx1[i];
+      v = dVr; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * (c->geometry == POLAR ? dx3[k] : 1.0);
     } else {
       double dVr = fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
       double dmu = fabs(cos(x2m[j]) - cos(x2p[j]));
@@ -177,7 +185,10 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
   for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = -1; i < n1; i++) {
     double a;
     if (c->geometry == CARTESIAN) { a = 1.0; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * dx3[k]; }
-    else {
+    else if (c->geometry == CYLINDRICAL || c->geometry == POLAR) {   /* set_geometry.c:150-161 */
+      a = (i == -1) ? fabs(x1m[0]) : fabs(x1p[i]);
+      if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * (c->geometry == POLAR ? dx3[k] : 1.0);
+    } else {
       double dmu = fabs(cos(x2m[j]) - cos(x2p[j]));
       a = (i == -1) ? x1m[0] * x1m[0] : x1p[i] * x1p[i];
       if (nd > 1) a = a * dmu; if (nd > 2) a = a * dx3[k];
@@ -186,7 +197,8 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
   }
   for (int k = 0; k < n3; k++) for (int j = -1; j < n2; j++) for (int i = 0; i < n1; i++) {
     double a;
-    if (c->geometry == CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    if (c->geometry == CARTESIAN || c->geometry == POLAR) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    else if (c->geometry == CYLINDRICAL) { a = fabs(x1[i]); if (nd > 1) a = a * dx1[i]; if (nd > 2) a = a * 1.0; }   /* set_geometry.c:181-182 */
     else {
       a = fabs(x1[i]) * dx1[i];
       if (nd > 1) a = a * ((j == -1) ? fabs(sin(x2m[0])) : fabs(sin(x2p[j])));
@@ -197,6 +209,7 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
   for (int k = -1; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
     double a;
     if (c->geometry == CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * 1.0; }
+    else if (c->geometry == CYLINDRICAL) a = 1.0;   /* set_geometry.c:203-204 */
     else { a = fabs(x1[i]) * dx1[i]; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * 1.0; }
     g->A[2][g->Aoff[2] + k * g->Ask[2] + j * g->Asj[2] + i] = a;
   }
@@ -205,6 +218,8 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
     long o = (long)j * n1 + i;
     g->dx_dl[0][o] = 1.0;
     if (c->geometry == CARTESIAN) { g->dx_dl[1][o] = 1.0; g->dx_dl[2][o] = 1.0; }
+    else if (c->geometry == CYLINDRICAL) g->dx_dl[1][o] = 1.0;
+    else if (c->geometry == POLAR) { g->dx_dl[1][o] = 1.0 / x1[i]; g->dx_dl[2][o] = 1.0; }
     else { g->dx_dl[1][o] = 1.0 / g->rt[i]; g->dx_dl[2][o] = dx2[j] / (g->rt[i] * g->dmu[j]); }
   }
   for (int d = 0; d < 3; d++) {
@@ -550,7 +565,7 @@ static void boundary(const gen_cfg *c, const geom_t *g, double *Vc) {
     for (int nv = 0; nv < nvar; nv++) {
       double sgn = 1.0;
       if ((type == 2 || type == 3 || type == 4) && nv == 1 + dir) sgn = -1.0;
-      if (type == 3 && nv == VX3 && c->geometry == SPHERICAL) sgn = -1.0;   /* boundary.c:560-575: iVPHI */
+      if (type == 3 && c->geometry != CARTESIAN && nv == (c->geometry == POLAR ? VX2 : VX3)) sgn = -1.0;   /* boundary.c:560-575: iVPHI */
       int mirror = (type == 2 || type == 3 || type == 4);
       double *q = Vc + nv * g->sv;
       for (int k = lo[2]; k <= up[2]; k++)
@@ -639,6 +654,7 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
   double *inv_dl = calloc(nmax, 8);
   for (int dir = 0; dir < c->ndim; dir++) {
     int VXn = 1 + dir;
+    const int iMPHI = (c->geometry == POLAR) ? VX2 : VX3;   /* pluto.h: iVPHI per geometry */
     int ntot = g->tot[dir], nbeg = g->beg[dir], nend = g->end[dir];
     long st = dir == 0 ? 1 : (dir == 1 ? g->sj : g->sk);
     int t1 = (dir + 1) % 3, t2 = (dir + 2) % 3;
@@ -669,8 +685,8 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
             q[dir] = n;
             double A = A_at(g, dir, q[2], q[1], q[0]);
             for (int nv = 0; nv < nvar; nv++) s.fA[n][nv] = s.flux[n][nv] * A;
-            if (dir == 0) s.fA[n][VX3] *= fabs(g->xr[0][n]);
-            else if (dir == 1) s.fA[n][VX3] *= fabs(g->sp[n]);
+            if (dir == 0) s.fA[n][iMPHI] *= fabs(g->xr[0][n]);
+            else if (dir == 1 && c->geometry == SPHERICAL) s.fA[n][iMPHI] *= fabs(g->sp[n]);
           }
           for (int n = nbeg; n <= nend; n++) {
             int q[3] = {i, j, k};
@@ -681,8 +697,8 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
             else dtdl = dt / g->dx[dir][n] * g->dx_dl[dir][(long)q[1] * g->tot[0] + q[0]];
             for (int nv = 0; nv < nvar; nv++) s.rhs[n][nv] = -dtdV * (s.fA[n][nv] - s.fA[n - 1][nv]);
             s.rhs[n][VXn] -= dtdl * (s.press[n] - s.press[n - 1]);
-            if (dir == 0) s.rhs[n][VX3] /= fabs(g->x[0][n]);
-            else if (dir == 1) s.rhs[n][VX3] /= fabs(g->s[n]);
+            if (dir == 0) s.rhs[n][iMPHI] /= fabs(g->x[0][n]);
+            else if (dir == 1 && c->geometry == SPHERICAL) s.rhs[n][iMPHI] /= fabs(g->s[n]);
           }
         }
         /* ---- RightHandSideSource ---- */
@@ -699,6 +715,12 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
             double vphi = vc[VX3];
             double Sm = vc[RHO] * (vc[VX2] * vc[VX2] + vphi * vphi);
             s.rhs[n][VX1] += dt * Sm * r_1;
+          } else if ((c->geometry == CYLINDRICAL || c->geometry == POLAR) && dir == 0) {   /* rhs_source.c:201-227 */
+            double r_1 = 1.0 / g->x[0][n];
+            for (int nv = 0; nv < nvar; nv++) vc[nv] = 0.5 * (s.vp[n][nv] + s.vm[n][nv]);
+            vg = vc;
+            double vphi = vc[iMPHI];
+            s.rhs[n][VX1] += dt * (vc[RHO] * vphi * vphi - 0.0) * r_1;
           } else if (c->geometry == SPHERICAL && dir == 1) {   /* rhs_source.c:311-357 */
             double r_1 = 1.0 / g->rt[i];
             double ct = 1.0 / tan(g->x[1][n]);
@@ -740,7 +762,7 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
         /* GetInverse_dl, set_geometry.c:303-375 */
         for (int n = 0; n < ntot; n++) {
           inv_dl[n] = g->inv_dx[dir][n];
-          if (c->geometry == SPHERICAL && dir == 1) inv_dl[n] = g->inv_dx[1][n] * (1.0 / g->x[0][i]);
+          if ((c->geometry == SPHERICAL || c->geometry == POLAR) && dir == 1) inv_dl[n] = g->inv_dx[1][n] * (1.0 / g->x[0][i]);
           if (c->geometry == SPHERICAL && dir == 2) inv_dl[n] = g->inv_dx[2][n] * (1.0 / g->x[0][i]) / sin(g->x[1][j]);
         }
         if (c->ndim > 1) {

@@ -9,7 +9,7 @@ import numpy as np
 import oracle as _o
 from pluto_grid import make_grid
 
-GEOMETRY = dict(CARTESIAN=1, SPHERICAL=4)
+GEOMETRY = dict(CARTESIAN=1, CYLINDRICAL=2, POLAR=3, SPHERICAL=4)
 BCS = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8, neighbour=100)
 
 
