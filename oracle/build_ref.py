@@ -51,9 +51,9 @@ EOS_IDEAL = ["eos"]
 RK = ["rk_step", "update_stage"]
 
 # search path for sources, in make-VPATH order (problem directory first)
-def vpath(problem_dir: Path, extra: list[str]) -> list[Path]:
+def vpath(problem_dir: Path, extra: list[str], eos: str = "Ideal") -> list[Path]:
     s = REF / "Src"
-    return [problem_dir, s, s / "Math_Tools", s / "HD", s / "MHD", s / "EOS" / "Ideal",
+    return [problem_dir, s, s / "Math_Tools", s / "HD", s / "MHD", s / "EOS" / eos,
             s / "States", s / "Time_Stepping"] + [s / e for e in extra]
 
 
@@ -99,6 +99,14 @@ CONFIGS = {
                                                "SHOCK_FLATTENING": "MULTID"}, states="plm"),
     "pol2d": dict(local="cyl", overrides={"GEOMETRY": "POLAR"}, states="plm"),
     "pol3d": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "DIMENSIONS": "3"}, states="plm"),
+    # EOS ISOTHERMAL (oracle/problems/iso): Cartesian 2-D / 3-D, spherical 2-D with gravity
+    "iso2d": dict(local="iso", overrides={}, states="plm"),
+    "iso2d_flat": dict(local="iso", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
+                                               "SHOCK_FLATTENING": "MULTID"}, states="plm"),
+    "iso3d": dict(local="iso", overrides={"DIMENSIONS": "3"}, states="plm"),
+    "iso_sph2d": dict(local="iso", overrides={"GEOMETRY": "SPHERICAL", "BODY_FORCE": "VECTOR",
+                                              "CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",
+                                              "SHOCK_FLATTENING": "MULTID"}, states="plm"),
     # C4: the line-driven disc wind of the sirocco coupling, UNMODIFIED user files of the reference
     # (Test_Problems/LineDrivenWind/cv_idl: init.c, definitions.h, userdef_output.c)
     "ldw": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={}, states="plm",
@@ -150,7 +158,8 @@ def build(cfg_name: str, force: bool = False, verbose: bool = False) -> Path:
     (wd / "definitions.h").write_text(defs)
 
     extra = cfg.get("extra_vpath", [])
-    paths = vpath(problem_dir, extra)
+    eos = "Isothermal" if re.search(r"^#define\s+EOS\s+ISOTHERMAL", defs, re.M) else "Ideal"   # makefile: EOS directory
+    paths = vpath(problem_dir, extra, eos)
     names = CORE + MATH + HD + EOS_IDEAL + RK + ["init"]
     names += ["plm_states"] if cfg["states"] == "plm" else ["ppm_states", "ppm_coeffs"]
     names += cfg.get("extra_objs", [])
@@ -159,7 +168,7 @@ def build(cfg_name: str, force: bool = False, verbose: bool = False) -> Path:
     else:
         names.append("userdef_output")
     s = REF / "Src"
-    incs = ["-I%s" % wd, "-I%s" % s, "-I%s" % (s / "HD"), "-I%s" % (s / "EOS" / "Ideal"),
+    incs = ["-I%s" % wd, "-I%s" % s, "-I%s" % (s / "HD"), "-I%s" % (s / "EOS" / eos),
             "-I%s" % (s / "States"), "-I%s" % (s / "Math_Tools")]
     incs += ["-I%s" % (s / e) for e in extra]
 

@@ -8,7 +8,7 @@
  * by oracle/build_ref.py with the user files of oracle/problems/) through the golden dumps of
  * tests/golden/ (tests/test_gen_oracle_golden.py).
  *
- * Scope: PHYSICS HD, EOS IDEAL, GEOMETRY CARTESIAN, CYLINDRICAL, POLAR or SPHERICAL, DIMENSIONS 1-3, uniform or
+ * Scope: PHYSICS HD, EOS IDEAL or ISOTHERMAL, GEOMETRY CARTESIAN, CYLINDRICAL, POLAR or SPHERICAL, DIMENSIONS 1-3, uniform or
  * non-uniform grids (grid->xl/xr are inputs: the reference's own set_grid.c output),
  * RECONSTRUCTION LINEAR with every LIMITER, CHAR_LIMITING NO/YES, SHOCK_FLATTENING NO/MULTID,
  * ENTROPY_SWITCH NO/ALWAYS, NTRACER >= 0, BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3,
@@ -76,7 +76,13 @@ typedef struct gen_cfg {
   int mpoints;              /* MPOINTS of the force-multiplier fit (KRAD = ALPHARAD = 999), line_connect.c:185-256 */
   const double *t_fit;      /* log10(t), MPOINTS entries */
   const double *m_fit;      /* log10(M), [MPOINTS][k][j][i] */
+  /* --- EOS ISOTHERMAL (Src/EOS/Isothermal/eos.c): no energy equation, NFLX = 4, tracers from index 4 --- */
+  int iso;                  /* 0: EOS IDEAL, 1: EOS ISOTHERMAL */
+  double iso_cs;            /* g_isoSoundSpeed */
 } gen_cfg;
+
+#define NF(c) ((c)->iso ? 4 : NFLX)                     /* NFLX of the configuration (mod_defs.h) */
+#define A2(c, v) ((c)->iso ? (c)->iso_cs * (c)->iso_cs : (c)->gamma * (v)[PRS] / (v)[RHO])   /* SoundSpeed2 */
 
 typedef struct {
   int tot[3], beg[3], end[3], nvar;
@@ -100,7 +106,7 @@ static double A_at(const geom_t *g, int d, int k, int j, int i) {
 
 static geom_t *geom_new(const gen_cfg *c) {
   geom_t *g = calloc(1, sizeof(geom_t));
-  g->nvar = NFLX + c->ntracer + (c->entropy ? 1 : 0);
+  g->nvar = NF(c) + c->ntracer + (c->entropy ? 1 : 0);
   for (int d = 0; d < 3; d++) {
     int act = d < c->ndim;
     int ng = act ? c->ng : 0, nx = act ? c->nx[d] : 1;
@@ -305,9 +311,11 @@ static void prim_to_cons(const gen_cfg *c, int nvar, const double *v, double *u)
   u[VX1] = rho * v[VX1];
   u[VX2] = rho * v[VX2];
   u[VX3] = rho * v[VX3];
-  u[PRS] = v[VX1] * v[VX1] + v[VX2] * v[VX2] + v[VX3] * v[VX3];
-  u[PRS] = 0.5 * rho * u[PRS] + v[PRS] / gmm1;
-  for (int nv = NFLX; nv < nvar; nv++) u[nv] = rho * v[nv];
+  if (!c->iso) {
+    u[PRS] = v[VX1] * v[VX1] + v[VX2] * v[VX2] + v[VX3] * v[VX3];
+    u[PRS] = 0.5 * rho * u[PRS] + v[PRS] / gmm1;
+  }
+  for (int nv = NF(c); nv < nvar; nv++) u[nv] = rho * v[nv];
 }
 
 /* HD/mappers.c:98-290 with ENTROPY_SWITCH */
@@ -323,6 +331,10 @@ static int cons_to_prim(const gen_cfg *c, int nvar, double *u, double *v, uint16
   v[VX2] = u[VX2] * tau;
   v[VX3] = u[VX3] * tau;
   double kin = 0.5 * m2 / u[RHO];
+  if (c->iso) {   /* mappers.c: no energy, no pressure */
+    for (int nv = NF(c); nv < nvar; nv++) v[nv] = u[nv] * tau;
+    return fail;
+  }
   if (u[PRS] < 0.0) { u[PRS] = c->small_pr / gmm1 + kin; *flag |= FLAG_CONS2PRIM_FAIL; fail = 1; }
   int use_entropy = c->entropy && (*flag & FLAG_ENTROPY);
   if (use_entropy) {
@@ -340,7 +352,7 @@ static int cons_to_prim(const gen_cfg *c, int nvar, double *u, double *v, uint16
     }
     if (c->entropy) u[ENTR] = v[PRS] / pow(rho, gmm1);
   }
-  for (int nv = NFLX; nv < nvar; nv++) v[nv] = u[nv] * tau;
+  for (int nv = NF(c); nv < nvar; nv++) v[nv] = u[nv] * tau;
   return fail;
 }
 
@@ -400,7 +412,7 @@ static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int b
       for (int nv = 0; nv < nvar; nv++) {
         int kind;
         if (c->limiter == 0) {
-          if (nv == RHO) kind = 4; else if (nv == PRS) kind = 2; else if (nv >= NFLX) kind = 4; else kind = 3;
+          if (nv == RHO) kind = 4; else if (!c->iso && nv == PRS) kind = 2; else if (nv >= NF(c)) kind = 4; else kind = 3;
         } else kind = c->limiter;
         dv_lim[nv] = lim_apply(kind, uniform, dvp[nv], dvm[nv], cp, cm);
       }
@@ -410,13 +422,15 @@ static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int b
       }
     } else {
       /* SoundSpeed2 (eos.c:33), PrimEigenvectors (eigenv.c:92-200), PrimToChar (eigenv.c:575-616) */
-      double a2 = c->gamma * v[PRS] / v[RHO];
+      const int nf = NF(c);
+      double a2 = A2(c, v);
       double cs = sqrt(a2), rhocs = v[RHO] * cs, rho_cs = v[RHO] / cs;
       double R[NFLX][NFLX], kstp[NFLX], cpk[NFLX], cmk[NFLX], dwp[NFLX], dwm[NFLX], dw_lim[NFLX];
       memset(R, 0, sizeof(R));
-      R[RHO][0] = 0.5 * rho_cs; R[VXn][0] = -0.5; R[PRS][0] = 0.5 * rhocs;
-      R[RHO][1] = 0.5 * rho_cs; R[VXn][1] = 0.5;  R[PRS][1] = 0.5 * rhocs;
-      R[RHO][2] = 1.0; R[VXt][3] = 1.0; R[VXb][4] = 1.0;
+      R[RHO][0] = 0.5 * rho_cs; R[VXn][0] = -0.5;
+      R[RHO][1] = 0.5 * rho_cs; R[VXn][1] = 0.5;
+      if (!c->iso) { R[PRS][0] = 0.5 * rhocs; R[PRS][1] = 0.5 * rhocs; R[RHO][2] = 1.0; R[VXt][3] = 1.0; R[VXb][4] = 1.0; }
+      else { R[VXt][2] = 1.0; R[VXb][3] = 1.0; }   /* eigenv.c:175-178 */
       double L0n = -1.0, L0p = 1.0 / rhocs, L1n = 1.0, L1p = 1.0 / rhocs, L2p = -1.0 / a2;
       for (int k = 0; k < NFLX; k++) kstp[k] = 2.0;
       kstp[0] = kstp[1] = 1.0;
@@ -424,29 +438,37 @@ static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int b
         if (uniform) cpk[k] = cmk[k] = kstp[k];
         else { cpk[k] = (2.0 - cp) + (cp - 1.0) * kstp[k]; cmk[k] = (2.0 - cm) + (cm - 1.0) * kstp[k]; }
       }
-      dwm[0] = L0n * dvm[VXn] + L0p * dvm[PRS]; dwm[1] = L1n * dvm[VXn] + L1p * dvm[PRS];
-      dwm[2] = dvm[RHO] + L2p * dvm[PRS]; dwm[3] = dvm[VXt]; dwm[4] = dvm[VXb];
-      dwp[0] = L0n * dvp[VXn] + L0p * dvp[PRS]; dwp[1] = L1n * dvp[VXn] + L1p * dvp[PRS];
-      dwp[2] = dvp[RHO] + L2p * dvp[PRS]; dwp[3] = dvp[VXt]; dwp[4] = dvp[VXb];
+      if (!c->iso) {
+        dwm[0] = L0n * dvm[VXn] + L0p * dvm[PRS]; dwm[1] = L1n * dvm[VXn] + L1p * dvm[PRS];
+        dwm[2] = dvm[RHO] + L2p * dvm[PRS]; dwm[3] = dvm[VXt]; dwm[4] = dvm[VXb];
+        dwp[0] = L0n * dvp[VXn] + L0p * dvp[PRS]; dwp[1] = L1n * dvp[VXn] + L1p * dvp[PRS];
+        dwp[2] = dvp[RHO] + L2p * dvp[PRS]; dwp[3] = dvp[VXt]; dwp[4] = dvp[VXb];
+      } else {   /* eigenv.c:182-196 (LL[0][RHO] = LL[1][RHO] = 1/rho_cs), PrimToChar eigenv.c:600-605 */
+        double Lr = 1.0 / rho_cs;
+        dwm[0] = Lr * dvm[RHO] + L0n * dvm[VXn]; dwm[1] = Lr * dvm[RHO] + L1n * dvm[VXn];
+        dwm[2] = dvm[VXt]; dwm[3] = dvm[VXb];
+        dwp[0] = Lr * dvp[RHO] + L0n * dvp[VXn]; dwp[1] = Lr * dvp[RHO] + L1n * dvp[VXn];
+        dwp[2] = dvp[VXt]; dwp[3] = dvp[VXb];
+      }
       if (c->flattening && (s->flag[i] & FLAG_FLAT)) {
-        for (int k = NFLX; k--;) dw_lim[k] = 0.0;
+        for (int k = nf; k--;) dw_lim[k] = 0.0;
       } else if (c->flattening && (s->flag[i] & FLAG_MINMOD)) {
-        for (int k = NFLX; k--;) dw_lim[k] = lim_apply(2, uniform, dwp[k], dwm[k], cp, cm);
+        for (int k = nf; k--;) dw_lim[k] = lim_apply(2, uniform, dwp[k], dwm[k], cp, cm);
       } else {
-        for (int k = NFLX; k--;) {
+        for (int k = nf; k--;) {
           if (c->limiter == 0) dw_lim[k] = lim_apply(8, uniform, dwp[k], dwm[k], cpk[k], cmk[k]);
           else dw_lim[k] = lim_apply(c->limiter, uniform, dwp[k], dwm[k], cp, cm);
         }
       }
-      for (int nv = NFLX; nv--;) {
+      for (int nv = nf; nv--;) {
         double dc = 0.0;
-        for (int k = 0; k < NFLX; k++) dc += dw_lim[k] * R[nv][k];
+        for (int k = 0; k < nf; k++) dc += dw_lim[k] * R[nv][k];
         if (dvp[nv] * dvm[nv] > 0.0) {
           double d2v = ABS_MIN(cp * dvp[nv], cm * dvm[nv]);
           dv_lim[nv] = MINMOD_LIMITER(d2v, dc);
         } else dv_lim[nv] = 0.0;
       }
-      for (int nv = NFLX; nv < nvar; nv++)
+      for (int nv = nf; nv < nvar; nv++)
         dv_lim[nv] = lim_apply(c->limiter == 0 ? 4 : c->limiter, uniform, dvp[nv], dvm[nv], cp, cm);
       for (int nv = nvar; nv--;) {
         s->vp[i][nv] = v[nv] + dv_lim[nv] * dp;
@@ -466,24 +488,29 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
     double uL[NVMAX], uR[NVMAX], fL[NFLX], fR[NFLX];
     prim_to_cons(c, nvar, vL, uL);
     prim_to_cons(c, nvar, vR, uR);
-    double a2L = c->gamma * vL[PRS] / vL[RHO];
-    double a2R = c->gamma * vR[PRS] / vR[RHO];
+    const int nf = NF(c);
+    double a2L = A2(c, vL);
+    double a2R = A2(c, vR);
     fL[RHO] = uL[VXn]; fL[VX1] = uL[VX1] * vL[VXn]; fL[VX2] = uL[VX2] * vL[VXn];
-    fL[VX3] = uL[VX3] * vL[VXn]; fL[PRS] = (uL[PRS] + vL[PRS]) * vL[VXn];
+    fL[VX3] = uL[VX3] * vL[VXn];
     fR[RHO] = uR[VXn]; fR[VX1] = uR[VX1] * vR[VXn]; fR[VX2] = uR[VX2] * vR[VXn];
-    fR[VX3] = uR[VX3] * vR[VXn]; fR[PRS] = (uR[PRS] + vR[PRS]) * vR[VXn];
-    double pL = vL[PRS], pR = vR[PRS];
+    fR[VX3] = uR[VX3] * vR[VXn];
+    double pL, pR;
+    if (!c->iso) {
+      fL[PRS] = (uL[PRS] + vL[PRS]) * vL[VXn]; fR[PRS] = (uR[PRS] + vR[PRS]) * vR[VXn];
+      pL = vL[PRS]; pR = vR[PRS];
+    } else { pL = a2L * vL[RHO]; pR = a2R * vR[RHO]; }   /* fluxes.c:47-48 */
     double *flux = s->flux[i];
     if (c->solver == 1) {
       double vRL[NVMAX];
       for (int nv = 0; nv < nvar; nv++) vRL[nv] = 0.5 * (vL[nv] + vR[nv]);
       vRL[VXn] = 0.5 * (fabs(vL[VXn]) + fabs(vR[VXn]));
-      double a2 = c->gamma * vRL[PRS] / vRL[RHO];
+      double a2 = A2(c, vRL);
       double a = sqrt(a2);
       double cmin = vRL[VXn] - a, cmaxv = vRL[VXn] + a;
       s->cmax[i] = MAXV(fabs(cmaxv), fabs(cmin));
       *maxMach = MAXV(*maxMach, fabs(vRL[VXn]) / sqrt(a2));
-      for (int nv = NFLX; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
+      for (int nv = nf; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
       s->press[i] = 0.5 * (pL + pR);
     } else {
       double aL = sqrt(a2L), aR = sqrt(a2R);
@@ -494,15 +521,15 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
       *maxMach = MAXV(scrh, *maxMach);
       s->cmax[i] = MAXV(fabs(SL), fabs(SR));
       if (SL > 0.0) {
-        for (int nv = NFLX; nv--;) flux[nv] = fL[nv];
+        for (int nv = nf; nv--;) flux[nv] = fL[nv];
         s->press[i] = pL;
       } else if (SR < 0.0) {
-        for (int nv = NFLX; nv--;) flux[nv] = fR[nv];
+        for (int nv = nf; nv--;) flux[nv] = fR[nv];
         s->press[i] = pR;
       } else if (c->solver == 2 ||
                  (c->flattening && ((s->flag[i] & FLAG_HLL) || (s->flag[i + 1] & FLAG_HLL)))) {
         scrh = 1.0 / (SR - SL);
-        for (int nv = NFLX; nv--;) {
+        for (int nv = nf; nv--;) {
           flux[nv] = SL * SR * (uR[nv] - uL[nv]) + SR * fL[nv] - SL * fR[nv];
           flux[nv] *= scrh;
         }
@@ -510,11 +537,24 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
       } else {
         double usL[NFLX], usR[NFLX];
         double vxr = vR[VXn], vxl = vL[VXn];
+        double vs;
+        if (c->iso) {   /* hllc.c:137-150 */
+          scrh = 1.0 / (SR - SL);
+          double rho = (SR * uR[RHO] - SL * uL[RHO] - fR[RHO] + fL[RHO]) * scrh;
+          double mx = (SR * uR[VXn] - SL * uL[VXn] - fR[VXn] + fL[VXn]) * scrh;
+          usL[RHO] = usR[RHO] = rho;
+          usL[VXn] = usR[VXn] = mx;
+          vs = (SR * fL[RHO] - SL * fR[RHO] + SR * SL * (uR[RHO] - uL[RHO]));
+          vs *= scrh;
+          vs /= rho;
+          usL[VXt] = rho * vL[VXt]; usR[VXt] = rho * vR[VXt];
+          usL[VXb] = rho * vL[VXb]; usR[VXb] = rho * vR[VXb];
+        } else {
         double qL = vL[PRS] + uL[VXn] * (vL[VXn] - SL);     /* hllc.c:112-116 */
         double qR = vR[PRS] + uR[VXn] * (vR[VXn] - SR);
         double wL = vL[RHO] * (vL[VXn] - SL);
         double wR = vR[RHO] * (vR[VXn] - SR);
-        double vs = (qR - qL) / (wR - wL);
+        vs = (qR - qL) / (wR - wL);
         usL[RHO] = uL[RHO] * (SL - vxl) / (SL - vs);
         usR[RHO] = uR[RHO] * (SR - vxr) / (SR - vs);
         usL[VXn] = usL[RHO] * vs;       usR[VXn] = usR[RHO] * vs;
@@ -524,17 +564,18 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
         usR[PRS] = uR[PRS] / vR[RHO] + (vs - vxr) * (vs + vR[PRS] / (vR[RHO] * (SR - vxr)));
         usL[PRS] *= usL[RHO];
         usR[PRS] *= usR[RHO];
+        }
         if (vs >= 0.0) {
-          for (int nv = NFLX; nv--;) flux[nv] = fL[nv] + SL * (usL[nv] - uL[nv]);
+          for (int nv = nf; nv--;) flux[nv] = fL[nv] + SL * (usL[nv] - uL[nv]);
           s->press[i] = pL;
         } else {
-          for (int nv = NFLX; nv--;) flux[nv] = fR[nv] + SR * (usR[nv] - uR[nv]);
+          for (int nv = nf; nv--;) flux[nv] = fR[nv] + SR * (usR[nv] - uR[nv]);
           s->press[i] = pR;
         }
       }
     }
     const double *ts = flux[RHO] > 0.0 ? vL : vR;
-    for (int nv = NFLX; nv < nvar; nv++) flux[nv] = flux[RHO] * ts[nv];
+    for (int nv = nf; nv < nvar; nv++) flux[nv] = flux[RHO] * ts[nv];
     if (c->entropy) {
       int ENTR = nvar - 1;
       if (flux[RHO] >= 0.0) flux[ENTR] = vL[ENTR] * flux[RHO];
@@ -591,6 +632,12 @@ static void boundary(const gen_cfg *c, const geom_t *g, double *Vc) {
 /* flag_shock.c:81-260 */
 static void flag_shock(const gen_cfg *c, const geom_t *g, const double *Vc, uint16_t *flag) {
   const double *pt = Vc + PRS * g->sv;
+  double *pt_iso = NULL;
+  if (c->iso) {   /* flag_shock.c:138-139 */
+    pt_iso = malloc(g->sv * 8);
+    for (long o = 0; o < g->sv; o++) pt_iso[o] = Vc[RHO * g->sv + o] * c->iso_cs * c->iso_cs;
+    pt = pt_iso;
+  }
   const double *vx[3] = {Vc + VX1 * g->sv, Vc + VX2 * g->sv, Vc + VX3 * g->sv};
   long st[3] = {1, g->sj, g->sk};
   if (c->entropy) for (long o = 0; o < g->sv; o++) flag[o] |= FLAG_ENTROPY;
@@ -634,6 +681,7 @@ static void flag_shock(const gen_cfg *c, const geom_t *g, const double *Vc, uint
           }
         }
       }
+  free(pt_iso);
 }
 
 /* ---------------------------------------------------------------------------------------
@@ -741,17 +789,18 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
               if (!c->ldw) continue;
               ldw_line_force(c, g, vg, dvds, o, gv);
             }
+            const int en = !c->iso;   /* IF_ENERGY */
             s.rhs[n][VXn] += dt * vg[RHO] * gv[dir];
-            s.rhs[n][PRS] += dt * 0.5 * (s.flux[n][RHO] + s.flux[n - 1][RHO]) * gv[dir];
+            if (en) s.rhs[n][PRS] += dt * 0.5 * (s.flux[n][RHO] + s.flux[n - 1][RHO]) * gv[dir];
             if (dir == 0 && c->ndim == 1) {
               s.rhs[n][VX2] += dt * vg[RHO] * gv[1];
-              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX2] * gv[1];
+              if (en) s.rhs[n][PRS] += dt * vg[RHO] * vg[VX2] * gv[1];
               s.rhs[n][VX3] += dt * vg[RHO] * gv[2];
-              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
+              if (en) s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
             }
             if (dir == 1 && c->ndim == 2) {
               s.rhs[n][VX3] += dt * vg[RHO] * gv[2];
-              s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
+              if (en) s.rhs[n][PRS] += dt * vg[RHO] * vg[VX3] * gv[2];
             }
           }
         }

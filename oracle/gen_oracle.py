@@ -27,7 +27,8 @@ class GenCfg(C.Structure):
                 ("dfloor", C.c_double), ("rho0", C.c_double), ("rho_alpha", C.c_double),
                 ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
                 ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
-                ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p)]
+                ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p),
+                ("iso", C.c_int), ("iso_cs", C.c_double)]
 
 
 _bound = False
@@ -58,7 +59,8 @@ class GenOracle:
     def __init__(self, *, dimensions, grid, geometry="CARTESIAN", gamma=5. / 3., reconstruction="LINEAR",
                  time_stepping="RK2", solver="hllc", limiter="DEFAULT", bcs=("outflow",) * 6, ntracer=0,
                  nghost=2, small_density=1e-12, small_pressure=1e-12, body_force=0, char_limiting=False,
-                 shock_flattening=False, entropy_switch=False, ldw=None, **_):
+                 shock_flattening=False, entropy_switch=False, ldw=None, eos="IDEAL",
+                 iso_sound_speed=1.0, **_):
         assert reconstruction == "LINEAR"
         c = GenCfg()
         c.ndim = dimensions
@@ -86,13 +88,16 @@ class GenOracle:
         c.small_dn = small_density
         c.small_pr = small_pressure
         c.body_force = body_force
+        c.iso = int(eos == "ISOTHERMAL")     # NFLX = 4: (rho, v1, v2, v3), tracers from index 4
+        c.iso_cs = float(iso_sound_speed)
+        assert not (c.iso and (c.entropy or ldw is not None)), "EOS ISOTHERMAL: hydro only"
         self.c = c
         self.dimensions = dimensions
         self.nghost = nghost
         self.nx = tuple(c.nx)
         self.beg = tuple(nghost if d < dimensions else 0 for d in range(3))
         self.tot = tuple(self.nx[d] + 2 * self.beg[d] for d in range(3))
-        self.nvar = 5 + ntracer + (1 if c.entropy else 0)
+        self.nvar = (4 if c.iso else 5) + ntracer + (1 if c.entropy else 0)
         self.shape = (self.nvar, self.tot[2], self.tot[1], self.tot[0])
         self._h = None
         self._bf = {}

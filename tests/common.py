@@ -5,8 +5,8 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
-# cylindrical / polar fixtures pin the ORACLE only (the CUDA path refuses these geometries so far)
-_CURV_PREFIXES = ("cyl", "pol")
+# cylindrical / polar / isothermal fixtures pin the ORACLE only (the CUDA path refuses these options so far)
+_CURV_PREFIXES = ("cyl", "pol", "iso")
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -55,7 +55,10 @@ def gen_kwargs_from_golden(g):
         else:
             grid.append((float(row[0]), int(row[1]), float(row[2])))
     flat = bool(int(g["shock_flattening"]))
-    return dict(dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
+    extra = {}
+    if "eos" in g and str(g["eos"]) == "ISOTHERMAL":     # only the oracle-only fixtures carry these keys
+        extra = dict(eos="ISOTHERMAL", iso_sound_speed=float(g["iso_cs"]))
+    return dict(**extra, dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
                 char_limiting=bool(int(g["char_limiting"])), shock_flattening=flat,

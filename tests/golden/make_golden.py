@@ -122,7 +122,8 @@ def make_case3(out, name, c):
     grid = c["grid"]
     nx = [int(grid[d][1]) if d < nd else 1 for d in range(3)]
     ntr = c.get("ntracer", 1)
-    nvar = 5 + ntr      # ENTR is not written: Boundary() recomputes it (ComputeEntropy)
+    iso = c.get("eos", "IDEAL") == "ISOTHERMAL"
+    nvar = (4 if iso else 5) + ntr      # ENTR is not written: Boundary() recomputes it (ComputeEntropy)
     with tempfile.TemporaryDirectory() as wd:
         r = refrun.run(c["cfg"], wd, shape=(nx[2], nx[1], nx[0]), nvar=nvar, maxsteps=c["maxsteps"],
                        grid=[pluto_grid.ini_string(g) for g in grid], cfl=c.get("cfl", 0.4), tstop=c.get("tstop", 10.0),
@@ -142,7 +143,7 @@ def make_case3(out, name, c):
                         char_limiting=int(c.get("char_limiting", False)),
                         shock_flattening=int(c.get("shock_flattening", False)),
                         entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],
-                        entr_codes=1)
+                        entr_codes=1, **(dict(eos="ISOTHERMAL", iso_cs=c["params"]["CS_ISO"]) if iso else {}))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
@@ -173,6 +174,32 @@ CASES5 = {
                       grid=[(0.8, 18, 2.6), (0.0, 20, TWO_PI), (0.0, 10, 1.2, "r", 1.05)], solver="hll",
                       bcs=("outflow", "outflow", "periodic", "periodic", "reflective", "outflow"),
                       params=CYL_PAR, maxsteps=6),
+}
+
+
+# EOS ISOTHERMAL (user files oracle/problems/iso): ORACLE fixtures like the cyl / pol ones
+ISO_PAR = dict(CS_ISO=0.7, GM=1.0)
+CASES6 = {
+    "iso2d_hllc": dict(cfg="iso2d", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                       grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="hllc",
+                       bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
+                       params=ISO_PAR, maxsteps=10, first_dt=1e-4),
+    "iso2d_hll": dict(cfg="iso2d", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                      grid=[(0.0, 40, 1.0), (0.0, 32, 1.0), (0.0, 1, 1.0)], solver="hll",
+                      bcs=("reflective", "outflow", "outflow", "reflective", "periodic", "periodic"),
+                      params=ISO_PAR, maxsteps=8, first_dt=1e-4),
+    "iso2d_flat_hllc": dict(cfg="iso2d_flat", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                            char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
+                            grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="hllc",
+                            bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
+                            params=ISO_PAR, maxsteps=10, first_dt=1e-4),
+    "iso3d_tvdlf": dict(cfg="iso3d", dims=3, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                        grid=[(0.0, 20, 1.0), (0.0, 16, 1.0), (0.0, 12, 1.0)], solver="tvdlf",
+                        bcs=("outflow", "outflow", "periodic", "periodic", "reflective", "outflow"),
+                        params=ISO_PAR, maxsteps=6, first_dt=1e-4),
+    "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
+                               char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
+                               grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),
 }
 
 
@@ -236,6 +263,9 @@ def main():
         if not only or name in only:
             make_case3(out, name, c)
     for name, c in CASES5.items():
+        if not only or name in only:
+            make_case3(out, name, c)
+    for name, c in CASES6.items():
         if not only or name in only:
             make_case3(out, name, c)
     for name, c in CASES4.items():

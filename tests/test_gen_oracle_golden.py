@@ -30,13 +30,16 @@ def test_gen_oracle_per_step_matches_reference_dumps(name):
 
 
 @pytest.mark.parametrize("name", CURV_CASES)
-def test_gen_oracle_cylindrical_and_polar_match_reference_dumps(name):
+def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     """GEOMETRY CYLINDRICAL (r, z) and POLAR (r, phi[, z]) of the oracle against the compiled reference
     (user files oracle/problems/cyl): volumes / areas / centroids of set_geometry.c, the |r| weighting of
     the angular-momentum flux (rhs.c:535-538, :268), the centrifugal source on (vp + vm)/2
     (rhs_source.c:201-227), r dphi in the polar C_dt, the AXISYMMETRIC flip of iVPHI on the axis with
-    r < 0 ghost zones, with and without characteristic limiting + MULTID flattening.  These fixtures pin
-    the oracle ahead of the CUDA path, which still refuses both geometries (PB200_ENOTSUP)."""
+    r < 0 ghost zones, with and without characteristic limiting + MULTID flattening; and EOS ISOTHERMAL
+    (user files oracle/problems/iso; the equation of state of the fork's LineDrivenWind/cv_iso problem):
+    NFLX = 4 state vector, p = cs^2 rho in the fluxes and in FlagShock, the isothermal HLLC star state
+    (hllc.c:137-150) and eigenvectors (eigenv.c:175-196), Cartesian 2-D / 3-D and spherical with gravity.
+    These fixtures pin the oracle ahead of the CUDA path, which still refuses these options (PB200_ENOTSUP)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
     set_point_mass_gravity(o, float(g["gm"]))
