@@ -114,6 +114,10 @@ CONFIGS = {
     # the same without the BLONDIN source step: isolates the hydro + line-force update
     "ldw_nocool": dict(problem="LineDrivenWind/cv_idl", defs="definitions.h", overrides={"COOLING": "NO"},
                        states="plm", extra_vpath=["LineDriven"], extra_objs=["line_connect"]),
+    # the isothermal twin of the line-driven wind problem, UNMODIFIED user files of the reference
+    # (Test_Problems/LineDrivenWind/cv_iso: EOS ISOTHERMAL, COOLING NO)
+    "ldw_iso": dict(problem="LineDrivenWind/cv_iso", defs="definitions.h", overrides={}, states="plm",
+                    extra_vpath=["LineDriven"], extra_objs=["line_connect"]),
     # an arbitrary, time-dependent UserDefBoundary() (oracle/problems/jet): the shim's host-boundary mode
     "jet2d": dict(local="jet", overrides={}, states="plm"),
     "jet2d_ppm": dict(local="jet", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),

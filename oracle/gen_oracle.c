@@ -934,7 +934,8 @@ static double kelvin(const gen_cfg *c) { return c->unit_velocity * c->unit_veloc
 /* UserDefBoundary(side == 0): density / pressure floors over TOT_LOOP and the mid-plane reset
  * (init.c:199-316).  Uc of a floored zone is re-derived like PrimToCons3D(d->Vc, d->Uc, 1-zone box). */
 static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) {
-  int nvar = g->nvar, TRC = NFLX;
+  int nvar = g->nvar, TRC = NF(c);
+  const int en = !c->iso;      /* the #if EOS != ISOTHERMAL blocks of init.c */
   double KELVIN = kelvin(c), mu = c->mu;
   double dfloor = c->dfloor / c->unit_density;
   double rho_0 = c->rho0 / c->unit_density;
@@ -951,17 +952,19 @@ static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) {
     int convert = 0;
     if (*rho < dfloor) {
       if (*rho < 0.0) *rho = dfloor;
-      double cs = sqrt(c->gamma * *prs / *rho);
+      double cs = en ? sqrt(c->gamma * *prs / *rho) : 0.0;
       double dfact = *rho / dfloor;
       *rho = dfloor;
       *v1 = dfact * *v1; *v2 = dfact * *v2; *v3 = dfact * *v3;
-      *prs = pow(cs, 2) * *rho / c->gamma;
-      double temp = *prs / *rho * KELVIN * mu;
-      if (temp < tfloor) { temp = tfloor; *prs = *rho * temp / (KELVIN * mu); }
+      if (en) {
+        *prs = pow(cs, 2) * *rho / c->gamma;
+        double temp = *prs / *rho * KELVIN * mu;
+        if (temp < tfloor) { temp = tfloor; *prs = *rho * temp / (KELVIN * mu); }
+      }
       Vc[TRC * g->sv + o] = 0.0;
       convert = 1;
     }
-    if (*prs < pfloor) { *prs = pfloor; convert = 1; }
+    if (en && *prs < pfloor) { *prs = pfloor; convert = 1; }
     if (convert && g_Uc_for_floor) {
       double v[NVMAX];
       for (int nv = 0; nv < nvar; nv++) v[nv] = Vc[nv * g->sv + o];
@@ -974,10 +977,12 @@ static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) {
       *rho = rho_mid;
       *v1 = 0.0;
       *v3 = sqrt(gm_code / r) * sin(theta);
-      double teff = pow(3.0 * gm_cgs * c->disk_mdot / (8.0 * CONST_PI * CONST_sigma), 0.25);
-      teff *= pow(r_WD * c->unit_length, -0.75);
-      double temp = teff * pow(r_WD / rcyl, 0.75) * pow(1.0 - sqrt(r_WD / rcyl), 0.25);
-      *prs = rho_mid * temp / (KELVIN * mu);
+      if (en) {
+        double teff = pow(3.0 * gm_cgs * c->disk_mdot / (8.0 * CONST_PI * CONST_sigma), 0.25);
+        teff *= pow(r_WD * c->unit_length, -0.75);
+        double temp = teff * pow(r_WD / rcyl, 0.75) * pow(1.0 - sqrt(r_WD / rcyl), 0.25);
+        *prs = rho_mid * temp / (KELVIN * mu);
+      }
       Vc[TRC * g->sv + o] = 1.0;
     }
   }
@@ -985,7 +990,6 @@ static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc) {
 
 /* UserDefBoundary(X1_BEG / X1_END / X2_BEG), init.c:319-363 */
 static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side) {
-  (void)c;
   int nvar = g->nvar;
   int IBEG = g->beg[0], IEND = g->end[0], JBEG = g->beg[1];
   for (int k = 0; k < g->tot[2]; k++) {
@@ -1008,7 +1012,7 @@ static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int 
         for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = Vc[nv * g->sv + os];
         Vc[VX2 * g->sv + o] *= -1.0;
         Vc[RHO * g->sv + o] = Vc[RHO * g->sv + ob];
-        Vc[PRS * g->sv + o] = Vc[PRS * g->sv + ob];
+        if (!c->iso) Vc[PRS * g->sv + o] = Vc[PRS * g->sv + ob];
       }
     }
   }
@@ -1105,7 +1109,7 @@ static double linterp(double x, const double *xarray, const double *yarray, int 
 static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad) {
   double sigma_e = CONST_sigmaT / CONST_amu / 1.18;
   double rho = v[RHO] * c->unit_density;
-  double T = v[PRS] / v[RHO] * kelvin(c) * c->mu;
+  double T = c->iso ? c->t_iso : v[PRS] / v[RHO] * kelvin(c) * c->mu;   /* line_connect.c:851-855 */
   double v_th = sqrt((2.0 * CONST_kB * T) / CONST_mp);
   double M_max = 4400.;
   double UNIT_ACC = c->unit_velocity * c->unit_velocity / c->unit_length;

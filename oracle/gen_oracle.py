@@ -90,7 +90,7 @@ class GenOracle:
         c.body_force = body_force
         c.iso = int(eos == "ISOTHERMAL")     # NFLX = 4: (rho, v1, v2, v3), tracers from index 4
         c.iso_cs = float(iso_sound_speed)
-        assert not (c.iso and (c.entropy or ldw is not None)), "EOS ISOTHERMAL: hydro only"
+        assert not (c.iso and c.entropy), "ENTROPY_SWITCH needs an energy equation"
         self.c = c
         self.dimensions = dimensions
         self.nghost = nghost

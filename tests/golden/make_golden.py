@@ -217,6 +217,8 @@ CASES4 = {
     "ldw_cool_hll": dict(cfg="ldw", grid=LDW_GRID, solver="hll", maxsteps=9, cooling=True),
     # force multiplier from the per-zone M(t) fit file instead of k t^alpha (KRAD = ALPHARAD = 999)
     "ldw_nocool_fit_hll": dict(cfg="ldw_nocool", grid=LDW_GRID, solver="hll", maxsteps=8, cooling=False, fit=True),
+    # EOS ISOTHERMAL twin (cv_iso user files, unmodified): ORACLE fixture ("iso" prefix, tests/common.py)
+    "iso_ldw_hll": dict(cfg="ldw_iso", grid=LDW_GRID, solver="hll", maxsteps=8, cooling=False, iso=True),
 }
 
 
@@ -236,7 +238,8 @@ def make_case4(out, name, c):
             t, M, lt, lM = common.ldw_mfit_tables(x1, x2)
             common.write_ldw_mfit_file(wd, x1, x2, ng, t, M)
             params = dict(params, KRAD=999.0, ALPHARAD=999.0)
-        r = refrun.run(c["cfg"], wd, shape=(1, nx[1], nx[0]), nvar=6, maxsteps=c["maxsteps"],
+        iso = bool(c.get("iso"))
+        r = refrun.run(c["cfg"], wd, shape=(1, nx[1], nx[0]), nvar=5 if iso else 6, maxsteps=c["maxsteps"],
                        grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
                        solver=c["solver"], bcs=common.LDW_BCS, dbl=(-1.0, 1), params=params, timeout=250)
     nd_ = len(r["data"]) - 1
@@ -249,7 +252,11 @@ def make_case4(out, name, c):
                         gamma=5. / 3., cfl=0.4, cfl_max_var=1.1, first_dt=1e-4, tstop=1.0,
                         ref_config=c["cfg"], gridspec=gridarr, geometry="SPHERICAL", ntracer=1,
                         body_force="vector", limiter="VANLEER_LIM", char_limiting=1, shock_flattening=1,
-                        entropy_switch=2, entr_codes=1, cooling=int(c["cooling"]), fit=int(bool(c.get("fit"))))
+                        entropy_switch=0 if iso else 2, entr_codes=1, cooling=int(c["cooling"]),
+                        fit=int(bool(c.get("fit"))),
+                        **(dict(eos="ISOTHERMAL",      # init.c:61-63 of cv_iso: g_isoSoundSpeed
+                                iso_cs=np.sqrt(8.3144598e7 * common.LDW_PARAMS["T_ISO"] / 0.6) / common.LDW_UNITS["velocity"])
+                           if iso else {}))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
