@@ -56,7 +56,7 @@ typedef struct gen_cfg {
   int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
   int char_limiting;        /* CHAR_LIMITING */
   int flattening;           /* SHOCK_FLATTENING MULTID */
-  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc */
+  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc 4 roe */
   int bc[6];                /* pluto.h:163-170; 8 userdef -> ldw_bc != 0 selects the built-in LDW fills */
   double gamma, small_dn, small_pr;
   const double *xl[3], *xr[3];   /* grid->xl, grid->xr incl. ghosts (np_tot each) */
@@ -512,6 +512,115 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
       *maxMach = MAXV(*maxMach, fabs(vRL[VXn]) / sqrt(a2));
       for (int nv = nf; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
       s->press[i] = 0.5 * (pL + pR);
+    } else if (c->solver == 4) {
+      /* HD/roe.c:48-346 (ROE_AVERAGE YES, the file's default) */
+      const double delta = 1.e-7;
+      double gmm1 = c->gamma - 1.0, gmm1_inv = 1.0 / gmm1;
+      double Rc[NFLX][NFLX], lambda[NFLX], alambda[NFLX], eta[NFLX], dv[NFLX], um[NFLX];
+      memset(Rc, 0, sizeof(Rc));
+      int done = 0;
+      if (c->flattening && ((s->flag[i] & FLAG_HLL) || (s->flag[i + 1] & FLAG_HLL))) {   /* roe.c:101-116 */
+        double aL = sqrt(a2L), aR = sqrt(a2R);          /* HLL_Speed, hll_speed.c:76-90 */
+        double bmin = MINV(vL[VXn] - aL, vR[VXn] - aR);
+        double bmax = MAXV(vL[VXn] + aL, vR[VXn] + aR);
+        double scrh = fabs(vL[VXn]) + fabs(vR[VXn]);
+        scrh /= aL + aR;
+        *maxMach = MAXV(scrh, *maxMach);
+        double a = MAXV(fabs(bmin), fabs(bmax));
+        s->cmax[i] = a;
+        bmin = MINV(0.0, bmin);
+        bmax = MAXV(0.0, bmax);
+        scrh = 1.0 / (bmax - bmin);
+        for (int nv = nf; nv--;) {
+          flux[nv] = bmin * bmax * (uR[nv] - uL[nv]) + bmax * fL[nv] - bmin * fR[nv];
+          flux[nv] *= scrh;
+        }
+        s->press[i] = (bmax * pL - bmin * pR) * scrh;
+        done = 1;
+      }
+      if (!done) {
+        const double *ql = vL, *qr = vR;
+        double a2, a, h = 0.0, vel2 = 0.0;
+        for (int nv = nf; nv--;) dv[nv] = qr[nv] - ql[nv];
+        double sq = sqrt(qr[RHO] / ql[RHO]);
+        um[RHO] = ql[RHO] * sq;
+        sq = 1.0 / (1.0 + sq);
+        double cq = 1.0 - sq;
+        um[VX1] = sq * ql[VX1] + cq * qr[VX1];
+        um[VX2] = sq * ql[VX2] + cq * qr[VX2];
+        um[VX3] = sq * ql[VX3] + cq * qr[VX3];
+        if (!c->iso) {
+          vel2 = um[VX1] * um[VX1] + um[VX2] * um[VX2] + um[VX3] * um[VX3];
+          double hl = 0.5 * (ql[VX1] * ql[VX1] + ql[VX2] * ql[VX2] + ql[VX3] * ql[VX3]);
+          hl += a2L * gmm1_inv;
+          double hr = 0.5 * (qr[VX1] * qr[VX1] + qr[VX2] * qr[VX2] + qr[VX3] * qr[VX3]);
+          hr += a2R * gmm1_inv;
+          h = sq * hl + cq * hr;
+          a2 = gmm1 * (h - 0.5 * vel2);
+          a = sqrt(a2);
+        } else {
+          a2 = 0.5 * (a2L + a2R);
+          a = sqrt(a2);
+        }
+        int nn = 0;                         /* u - c_s */
+        lambda[nn] = um[VXn] - a;
+        if (!c->iso) eta[nn] = 0.5 / a2 * (dv[PRS] - dv[VXn] * um[RHO] * a);
+        else eta[nn] = 0.5 * (dv[RHO] - um[RHO] * dv[VXn] / a);
+        Rc[RHO][nn] = 1.0; Rc[VXn][nn] = um[VXn] - a; Rc[VXt][nn] = um[VXt]; Rc[VXb][nn] = um[VXb];
+        if (!c->iso) Rc[PRS][nn] = h - um[VXn] * a;
+        nn = 1;                             /* u + c_s */
+        lambda[nn] = um[VXn] + a;
+        if (!c->iso) eta[nn] = 0.5 / a2 * (dv[PRS] + dv[VXn] * um[RHO] * a);
+        else eta[nn] = 0.5 * (dv[RHO] + um[RHO] * dv[VXn] / a);
+        Rc[RHO][nn] = 1.0; Rc[VXn][nn] = um[VXn] + a; Rc[VXt][nn] = um[VXt]; Rc[VXb][nn] = um[VXb];
+        if (!c->iso) Rc[PRS][nn] = h + um[VXn] * a;
+        if (!c->iso) {                      /* u (entropy wave) */
+          nn = 2;
+          lambda[nn] = um[VXn];
+          eta[nn] = dv[RHO] - dv[PRS] / a2;
+          Rc[RHO][nn] = 1.0; Rc[VX1][nn] = um[VX1]; Rc[VX2][nn] = um[VX2]; Rc[VX3][nn] = um[VX3];
+          Rc[PRS][nn] = 0.5 * vel2;
+        }
+        nn++;                               /* u (shear waves) */
+        lambda[nn] = um[VXn];
+        eta[nn] = um[RHO] * dv[VXt];
+        Rc[VXt][nn] = 1.0;
+        if (!c->iso) Rc[PRS][nn] = um[VXt];
+        nn++;
+        lambda[nn] = um[VXn];
+        eta[nn] = um[RHO] * dv[VXb];
+        Rc[VXb][nn] = 1.0;
+        if (!c->iso) Rc[PRS][nn] = um[VXb];
+        s->cmax[i] = fabs(um[VXn]) + a;
+        *maxMach = MAXV(fabs(um[VXn] / a), *maxMach);
+        if (c->ndim > 1) {                  /* roe.c:262-287: HLL inside strong shocks */
+          double scrh;
+          if (!c->iso) { scrh = fabs(ql[PRS] - qr[PRS]); scrh /= MINV(ql[PRS], qr[PRS]); }
+          else { scrh = fabs(ql[RHO] - qr[RHO]); scrh /= MINV(ql[RHO], qr[RHO]); scrh *= a * a; }
+          if (scrh > 0.5 && (qr[VXn] < ql[VXn])) {
+            double bmin = MINV(0.0, lambda[0]);
+            double bmax = MAXV(0.0, lambda[1]);
+            double scrh1 = 1.0 / (bmax - bmin);
+            for (int nv = nf; nv--;) {
+              flux[nv] = bmin * bmax * (uR[nv] - uL[nv]) + bmax * fL[nv] - bmin * fR[nv];
+              flux[nv] *= scrh1;
+            }
+            s->press[i] = (bmax * pL - bmin * pR) * scrh1;
+            done = 1;
+          }
+        }
+        if (!done) {
+          for (int nv = nf; nv--;) alambda[nv] = fabs(lambda[nv]);
+          if (alambda[0] <= delta) alambda[0] = 0.5 * lambda[0] * lambda[0] / delta + 0.5 * delta;   /* entropy fix */
+          if (alambda[1] <= delta) alambda[1] = 0.5 * lambda[1] * lambda[1] / delta + 0.5 * delta;
+          for (int nv = nf; nv--;) {
+            flux[nv] = fL[nv] + fR[nv];
+            for (int k = nf; k--;) flux[nv] -= alambda[k] * eta[k] * Rc[nv][k];
+            flux[nv] *= 0.5;
+          }
+          s->press[i] = 0.5 * (pL + pR);
+        }
+      }
     } else {
       double aL = sqrt(a2L), aR = sqrt(a2R);
       double SL = MINV(vL[VXn] - aL, vR[VXn] - aR);

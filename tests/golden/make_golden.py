@@ -139,7 +139,7 @@ def make_case3(out, name, c):
                         gamma=c.get("gamma", 5. / 3.), cfl=c.get("cfl", 0.4), cfl_max_var=1.1, first_dt=c.get("first_dt", 1e-5),
                         tstop=c.get("tstop", 10.0),
                         ref_config=c["cfg"], gridspec=gridarr, geometry=c.get("geometry", "SPHERICAL"), ntracer=ntr,
-                        body_force=c.get("body_force", "vector"), gm=c.get("params", SPH_PAR)["GM"], limiter=c.get("limiter", "DEFAULT"),
+                        body_force=c.get("body_force", "vector"), gm=c.get("params", SPH_PAR).get("GM", 0.0), limiter=c.get("limiter", "DEFAULT"),
                         char_limiting=int(c.get("char_limiting", False)),
                         shock_flattening=int(c.get("shock_flattening", False)),
                         entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],
@@ -197,6 +197,17 @@ CASES6 = {
                         grid=[(0.0, 20, 1.0), (0.0, 16, 1.0), (0.0, 12, 1.0)], solver="tvdlf",
                         bcs=("outflow", "outflow", "periodic", "periodic", "reflective", "outflow"),
                         params=ISO_PAR, maxsteps=6, first_dt=1e-4),
+    # Roe solver (HD/roe.c), ideal and isothermal; "roe" prefix: ORACLE fixtures
+    "roe_cart2d": dict(cfg="sedov2d", dims=2, geometry="CARTESIAN", body_force="none", ntracer=0, gamma=1.4,
+                       grid=[(0.0, 32, 1.0), (0.0, 32, 1.0), (0.0, 1, 1.0)], solver="roe",
+                       bcs=("reflective", "outflow", "reflective", "outflow", "outflow", "outflow"),
+                       params=SEDOV_PAR, maxsteps=14, first_dt=1e-9, cfl=0.3),
+    "roe_sph2d_flat": dict(cfg="sph2d_flat", dims=2, grid=SPH_GRID2, solver="roe", bcs=SPH_BCS, maxsteps=10,
+                           char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM"),
+    "roe_iso2d": dict(cfg="iso2d", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                      grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="roe",
+                      bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
+                      params=ISO_PAR, maxsteps=10, first_dt=1e-4),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),

@@ -39,6 +39,8 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     (user files oracle/problems/iso; the equation of state of the fork's LineDrivenWind/cv_iso problem):
     NFLX = 4 state vector, p = cs^2 rho in the fluxes and in FlagShock, the isothermal HLLC star state
     (hllc.c:137-150) and eigenvectors (eigenv.c:175-196), Cartesian 2-D / 3-D and spherical with gravity.
+    The roe_* fixtures add Roe_Solver (HD/roe.c: Roe average, entropy fix, HLL inside strong shocks and
+    flagged zones) for both equations of state.
     These fixtures pin the oracle ahead of the CUDA path, which still refuses these options (PB200_ENOTSUP)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
