@@ -56,7 +56,7 @@ typedef struct gen_cfg {
   int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
   int char_limiting;        /* CHAR_LIMITING */
   int flattening;           /* SHOCK_FLATTENING MULTID */
-  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc 4 roe */
+  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc 4 roe 5 two_shock */
   int bc[6];                /* pluto.h:163-170; 8 userdef -> ldw_bc != 0 selects the built-in LDW fills */
   double gamma, small_dn, small_pr;
   const double *xl[3], *xr[3];   /* grid->xl, grid->xr incl. ghosts (np_tot each) */
@@ -512,6 +512,90 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
       *maxMach = MAXV(*maxMach, fabs(vRL[VXn]) / sqrt(a2));
       for (int nv = nf; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
       s->press[i] = 0.5 * (pL + pR);
+    } else if (c->solver == 5) {
+      /* HD/two_shock.c:28-243 (EOS IDEAL only; MAX_ITER 5, small_p = small_rho = 1e-9) */
+      const double small_p = 1.e-9, small_rho = 1.e-9;
+      double g1_g = 0.5 * (c->gamma + 1.0) / c->gamma;
+      if (c->flattening && ((s->flag[i] & FLAG_HLL) || (s->flag[i + 1] & FLAG_HLL))) {   /* two_shock.c:66-88 */
+        double aL = sqrt(a2L), aR = sqrt(a2R);          /* HLL_Speed, hll_speed.c:76-90 */
+        double cl = MINV(vL[VXn] - aL, vR[VXn] - aR);
+        double cr = MAXV(vL[VXn] + aL, vR[VXn] + aR);
+        double scrh = fabs(vL[VXn]) + fabs(vR[VXn]);
+        scrh /= aL + aR;
+        *maxMach = MAXV(scrh, *maxMach);
+        double cs = MAXV(fabs(cl), fabs(cr));
+        s->cmax[i] = cs;
+        cl = MINV(0.0, cl);
+        cr = MAXV(0.0, cr);
+        double scrh1 = 1.0 / (cr - cl);
+        for (int nv = nf; nv--;) {
+          flux[nv] = cl * cr * (uR[nv] - uL[nv]) + cr * fL[nv] - cl * fR[nv];
+          flux[nv] *= scrh1;
+        }
+        s->press[i] = (cr * pL - cl * pR) * scrh1;
+      } else {
+        const double *ql = vL, *qr = vR, *qs;
+        double cl = sqrt(c->gamma * ql[PRS] * ql[RHO]);
+        double cr = sqrt(c->gamma * qr[PRS] * qr[RHO]);
+        double taul = 1.0 / ql[RHO], taur = 1.0 / qr[RHO];
+        double vxl = 0.0, vxr = 0.0, scrh1, scrh2, scrh3, scrh4, dp;
+        double pstar = qr[PRS] - ql[PRS] - cr * (qr[VXn] - ql[VXn]);
+        pstar = ql[PRS] + pstar * cl / (cl + cr);
+        pstar = MAXV(small_p, pstar);
+        for (int iter = 1; iter <= 5; iter++) {
+          vxl = cl * sqrt(1.0 + g1_g * (pstar - ql[PRS]) / ql[PRS]);
+          vxr = cr * sqrt(1.0 + g1_g * (pstar - qr[PRS]) / qr[PRS]);
+          scrh1 = vxl * vxl;
+          scrh1 = 2.0 * scrh1 * vxl / (scrh1 + cl * cl);
+          scrh2 = vxr * vxr;
+          scrh2 = 2.0 * scrh2 * vxr / (scrh2 + cr * cr);
+          scrh3 = ql[VXn] - (pstar - ql[PRS]) / vxl;
+          scrh4 = qr[VXn] + (pstar - qr[PRS]) / vxr;
+          dp = scrh1 * scrh2 / (scrh1 + scrh2) * (scrh4 - scrh3);
+          pstar -= dp;
+          pstar = MAXV(small_p, pstar);
+          if (fabs(dp / pstar) < 1.e-6) break;
+        }
+        scrh3 = ql[VXn] - (pstar - ql[PRS]) / vxl;
+        scrh4 = qr[VXn] + (pstar - qr[PRS]) / vxr;
+        double ustar = 0.5 * (scrh3 + scrh4);
+        double sigma, taus, cs, zs;
+        if (ustar > 0.0) { sigma = 1.0; taus = taul; cs = cl * taul; zs = vxl; qs = ql; }
+        else { sigma = -1.0; taus = taur; cs = cr * taur; zs = vxr; qs = qr; }
+        double rho_star = taus - (pstar - qs[PRS]) / (zs * zs);
+        rho_star = MAXV(small_rho, 1.0 / rho_star);
+        double cstar = sqrt(c->gamma * pstar / rho_star);
+        double lambda_s, lambda_star;
+        if (pstar < qs[PRS]) {
+          lambda_s = cs - sigma * qs[VXn];
+          lambda_star = cstar - sigma * ustar;
+        } else {
+          lambda_s = lambda_star = zs * taus - sigma * qs[VXn];
+        }
+        double vS[NVMAX], uS[NVMAX];
+        for (int nv = 0; nv < nvar; nv++) vS[nv] = 0.0;
+        if (lambda_star > 0.0) { vS[RHO] = rho_star; vS[VXn] = ustar; vS[PRS] = pstar; }
+        else if (lambda_s < 0.0) { vS[RHO] = qs[RHO]; vS[VXn] = qs[VXn]; vS[PRS] = qs[PRS]; }
+        else {
+          scrh1 = MAXV(lambda_s - lambda_star, lambda_s + lambda_star);
+          scrh1 = MAXV(1.e-12, scrh1);
+          double zeta = 0.5 * (1.0 + (lambda_s + lambda_star) / scrh1);
+          vS[RHO] = zeta * rho_star + (1.0 - zeta) * qs[RHO];
+          vS[VXn] = zeta * ustar + (1.0 - zeta) * qs[VXn];
+          vS[PRS] = zeta * pstar + (1.0 - zeta) * qs[PRS];
+        }
+        vS[VXt] = qs[VXt];
+        vS[VXb] = qs[VXb];
+        prim_to_cons(c, NFLX, vS, uS);
+        double a2S = c->gamma * vS[PRS] / vS[RHO];
+        flux[RHO] = uS[VXn]; flux[VX1] = uS[VX1] * vS[VXn]; flux[VX2] = uS[VX2] * vS[VXn];
+        flux[VX3] = uS[VX3] * vS[VXn]; flux[PRS] = (uS[PRS] + vS[PRS]) * vS[VXn];
+        s->press[i] = vS[PRS];
+        cstar = sqrt(a2S);
+        scrh1 = fabs(vS[VXn]) / cstar;
+        *maxMach = MAXV(scrh1, *maxMach);
+        s->cmax[i] = fabs(vS[VXn]) + cstar;
+      }
     } else if (c->solver == 4) {
       /* HD/roe.c:48-346 (ROE_AVERAGE YES, the file's default) */
       const double delta = 1.e-7;

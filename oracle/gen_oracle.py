@@ -81,7 +81,7 @@ class GenOracle:
         c.char_limiting = int(bool(char_limiting))
         c.flattening = int(bool(shock_flattening))
         c.rk = _o.RK[time_stepping]
-        c.solver = dict(_o.SOLVER, roe=4)[solver]     # Roe_Solver: general-grid oracle only
+        c.solver = dict(_o.SOLVER, roe=4, two_shock=5)[solver]     # Roe_Solver, TwoShock_Solver: general-grid oracle only
         for s in range(6):
             c.bc[s] = BCS[bcs[s]] if isinstance(bcs[s], str) else int(bcs[s])
         c.gamma = gamma

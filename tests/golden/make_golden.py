@@ -208,6 +208,12 @@ CASES6 = {
                       grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="roe",
                       bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
                       params=ISO_PAR, maxsteps=10, first_dt=1e-4),
+    # TwoShock_Solver (HD/two_shock.c); "twoshock" prefix: ORACLE fixtures
+    "twoshock_sph2d_flat": dict(cfg="sph2d_flat", dims=2, grid=SPH_GRID2, solver="two_shock", bcs=SPH_BCS, maxsteps=10,
+                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM"),
+    "twoshock_sph3d": dict(cfg="sph3d", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
+                           solver="two_shock", bcs=("outflow", "outflow", "reflective", "reflective", "periodic", "periodic"),
+                           maxsteps=6),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),
