@@ -90,6 +90,10 @@ CONFIGS = {
                                                "SHOCK_FLATTENING": "MULTID", "ENTROPY_SWITCH": "ALWAYS"},
                        states="plm"),
     "sph2d_sel": dict(local="sph", overrides={"ENTROPY_SWITCH": "SELECTIVE"}, states="plm"),
+    "sph2d_oned": dict(local="sph", overrides={"SHOCK_FLATTENING": "ONED"}, states="plm"),
+    "sph2d_char_oned": dict(local="sph", overrides={"CHAR_LIMITING": "YES", "LIMITER": "MC_LIM",
+                                                    "SHOCK_FLATTENING": "ONED"}, states="plm"),
+    "iso2d_oned": dict(local="iso", overrides={"SHOCK_FLATTENING": "ONED"}, states="plm"),
     "sph1d": dict(local="sph", overrides={"DIMENSIONS": "1"}, states="plm"),
     "sph3d": dict(local="sph", overrides={"DIMENSIONS": "3"}, states="plm"),
     # cylindrical (r, z) and polar (r, phi[, z]) geometry (oracle/problems/cyl)

@@ -79,6 +79,7 @@ typedef struct gen_cfg {
   /* --- EOS ISOTHERMAL (Src/EOS/Isothermal/eos.c): no energy equation, NFLX = 4, tracers from index 4 --- */
   int iso;                  /* 0: EOS IDEAL, 1: EOS ISOTHERMAL */
   double iso_cs;            /* g_isoSoundSpeed */
+  int flatten_oned;         /* SHOCK_FLATTENING ONED (States/flatten.c); `flattening` above is MULTID */
 } gen_cfg;
 
 #define NF(c) ((c)->iso ? 4 : NFLX)                     /* NFLX of the configuration (mod_defs.h) */
@@ -475,6 +476,33 @@ static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int b
         s->vm[i][nv] = v[nv] - dv_lim[nv] * dm;
       }
     }
+  }
+  if (c->flatten_oned) {   /* Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10) */
+    const int P = c->iso ? RHO : PRS;
+    int fb = MAXV(beg, 3), fe = MINV(end, g->tot[dir] - 4);
+    double *f_t = calloc(g->tot[dir] + 4, 8);
+    for (int i = fb - 1; i <= fe + 1; i++) {
+      double dp = s->v[i + 1][P] - s->v[i - 1][P];
+      double min_p = MINV(s->v[i + 1][P], s->v[i - 1][P]);
+      double d2p = s->v[i + 2][P] - s->v[i - 2][P];
+      double scrh = fabs(dp) / min_p;
+      if (scrh < 0.33 || (s->v[i + 1][VXn] > s->v[i - 1][VXn])) f_t[i] = 0.0;
+      else {
+        scrh = 10.0 * (fabs(dp / d2p) - 0.75);
+        scrh = MINV(1.0, scrh);
+        f_t[i] = MAXV(0.0, scrh);
+      }
+    }
+    for (int i = fb; i <= fe; i++) {
+      int sj = (s->v[i + 1][P] < s->v[i - 1][P] ? 1 : -1);
+      double fj = MAXV(f_t[i], f_t[i + sj]);
+      for (int nv = 0; nv < nvar; nv++) {
+        double vf = s->v[i][nv] * fj, scrh = 1.0 - fj;
+        s->vm[i][nv] = vf + s->vm[i][nv] * scrh;
+        s->vp[i][nv] = vf + s->vp[i][nv] * scrh;
+      }
+    }
+    free(f_t);
   }
 }
 

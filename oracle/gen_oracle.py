@@ -28,7 +28,7 @@ class GenCfg(C.Structure):
                 ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
                 ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
                 ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p),
-                ("iso", C.c_int), ("iso_cs", C.c_double)]
+                ("iso", C.c_int), ("iso_cs", C.c_double), ("flatten_oned", C.c_int)]
 
 
 _bound = False
@@ -79,7 +79,8 @@ class GenOracle:
         c.geometry = GEOMETRY[geometry]
         c.limiter = _o.LIMITER[limiter]
         c.char_limiting = int(bool(char_limiting))
-        c.flattening = int(bool(shock_flattening))
+        c.flattening = int(bool(shock_flattening) and shock_flattening != "ONED")     # MULTID
+        c.flatten_oned = int(shock_flattening == "ONED")
         c.rk = _o.RK[time_stepping]
         c.solver = dict(_o.SOLVER, roe=4, two_shock=5)[solver]     # Roe_Solver, TwoShock_Solver: general-grid oracle only
         for s in range(6):

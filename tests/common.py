@@ -6,7 +6,7 @@ import numpy as np
 GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
 # cylindrical / polar / isothermal fixtures pin the ORACLE only (the CUDA path refuses these options so far)
-_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock")
+_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned")
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -54,16 +54,16 @@ def gen_kwargs_from_golden(g):
             grid.append((float(row[0]), int(row[1]), float(row[2]), "r", float(row[4])))
         else:
             grid.append((float(row[0]), int(row[1]), float(row[2])))
-    flat = bool(int(g["shock_flattening"]))
+    flat = int(g["shock_flattening"])      # 0 NO, 1 MULTID, 2 ONED (oracle-only fixtures)
     extra = {}
     if "eos" in g and str(g["eos"]) == "ISOTHERMAL":     # only the oracle-only fixtures carry these keys
         extra = dict(eos="ISOTHERMAL", iso_sound_speed=float(g["iso_cs"]))
     return dict(**extra, dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
-                char_limiting=bool(int(g["char_limiting"])), shock_flattening=flat,
+                char_limiting=bool(int(g["char_limiting"])), shock_flattening={0: False, 1: True, 2: "ONED"}[flat],
                 entropy_switch={0: False, 1: "SELECTIVE", 2: "ALWAYS"}[_entr_code(g)],
-                nghost=3 if flat else 2)     # GetNghost(), Src/get_nghost.c:42-51
+                nghost={0: 2, 1: 3, 2: 4}[flat])     # GetNghost(), Src/get_nghost.c:42-57
 
 
 def set_point_mass_gravity(obj, gm):

@@ -141,7 +141,7 @@ def make_case3(out, name, c):
                         ref_config=c["cfg"], gridspec=gridarr, geometry=c.get("geometry", "SPHERICAL"), ntracer=ntr,
                         body_force=c.get("body_force", "vector"), gm=c.get("params", SPH_PAR).get("GM", 0.0), limiter=c.get("limiter", "DEFAULT"),
                         char_limiting=int(c.get("char_limiting", False)),
-                        shock_flattening=int(c.get("shock_flattening", False)),
+                        shock_flattening=2 if c.get("shock_flattening") == "ONED" else int(bool(c.get("shock_flattening", False))),
                         entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],
                         entr_codes=1, **(dict(eos="ISOTHERMAL", iso_cs=c["params"]["CS_ISO"]) if iso else {}))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
@@ -214,6 +214,15 @@ CASES6 = {
     "twoshock_sph3d": dict(cfg="sph3d", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
                            solver="two_shock", bcs=("outflow", "outflow", "reflective", "reflective", "periodic", "periodic"),
                            maxsteps=6),
+    # SHOCK_FLATTENING ONED (States/flatten.c, NGHOST 4); "oned" prefix: ORACLE fixtures
+    "oned_sph2d_hllc": dict(cfg="sph2d_oned", dims=2, grid=SPH_GRID2, solver="hllc", bcs=SPH_BCS, maxsteps=10,
+                            shock_flattening="ONED"),
+    "oned_sph2d_char_roe": dict(cfg="sph2d_char_oned", dims=2, grid=SPH_GRID2, solver="roe", bcs=SPH_BCS, maxsteps=10,
+                                shock_flattening="ONED", char_limiting=True, limiter="MC_LIM"),
+    "oned_iso2d_hll": dict(cfg="iso2d_oned", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                           grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="hll",
+                           bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
+                           params=ISO_PAR, maxsteps=10, first_dt=1e-4, shock_flattening="ONED"),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),

@@ -40,7 +40,8 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     NFLX = 4 state vector, p = cs^2 rho in the fluxes and in FlagShock, the isothermal HLLC star state
     (hllc.c:137-150) and eigenvectors (eigenv.c:175-196), Cartesian 2-D / 3-D and spherical with gravity.
     The roe_* fixtures add Roe_Solver (HD/roe.c: Roe average, entropy fix, HLL inside strong shocks and
-    flagged zones) for both equations of state, the twoshock_* ones TwoShock_Solver (HD/two_shock.c).
+    flagged zones) for both equations of state, the twoshock_* ones TwoShock_Solver (HD/two_shock.c),
+    the oned_* ones SHOCK_FLATTENING ONED (States/flatten.c, 4 ghost zones).
     These fixtures pin the oracle ahead of the CUDA path, which still refuses these options (PB200_ENOTSUP)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
