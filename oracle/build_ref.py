@@ -103,6 +103,13 @@ CONFIGS = {
                                                "SHOCK_FLATTENING": "MULTID"}, states="plm"),
     "pol2d": dict(local="cyl", overrides={"GEOMETRY": "POLAR"}, states="plm"),
     "pol3d": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "DIMENSIONS": "3"}, states="plm"),
+    # PPM + RK3 on general grids (stretched Cartesian, cylindrical, polar)
+    "kh3d_ppm": dict(local="kh", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
+    "cyl2d_ppm": dict(local="cyl", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
+    "cyl2d_ppm_flat": dict(local="cyl", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3",
+                                                   "SHOCK_FLATTENING": "MULTID"}, states="ppm"),
+    "pol2d_ppm": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "RECONSTRUCTION": "PARABOLIC",
+                                              "TIME_STEPPING": "RK3"}, states="ppm"),
     # EOS ISOTHERMAL (oracle/problems/iso): Cartesian 2-D / 3-D, spherical 2-D with gravity
     "iso2d": dict(local="iso", overrides={}, states="plm"),
     "iso2d_flat": dict(local="iso", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",

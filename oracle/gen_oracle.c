@@ -80,6 +80,8 @@ typedef struct gen_cfg {
   int iso;                  /* 0: EOS IDEAL, 1: EOS ISOTHERMAL */
   double iso_cs;            /* g_isoSoundSpeed */
   int flatten_oned;         /* SHOCK_FLATTENING ONED (States/flatten.c); `flattening` above is MULTID */
+  int ppm;                  /* RECONSTRUCTION PARABOLIC (PPM_ORDER 4), CHAR_LIMITING NO */
+  int uniform[3];           /* grid->uniform[d] (set_grid.c:67-72): one uniform patch along d */
 } gen_cfg;
 
 #define NF(c) ((c)->iso ? 4 : NFLX)                     /* NFLX of the configuration (mod_defs.h) */
@@ -95,6 +97,8 @@ typedef struct {
   double *A[3];        /* A[d] with one extra layer at index -1 along d */
   long Aoff[3], Asj[3], Ask[3];
   double *dx_dl[3];    /* [j][i] */
+  double (*pwp[3])[4];  /* PPM interface weights wp[i][-1..2] (PPM_CoefficientsSet, order 4) */
+  double *php[3], *phm[3];   /* PPM_Q6_Coeffs */
 } geom_t;
 
 /* ---------------------------------------------------------------------------------------
@@ -136,6 +140,7 @@ static geom_t *geom_new(const gen_cfg *c) {
 
 /* grid->dx is an INPUT of the reference's geometry (set_grid.c fills it together with xl/xr and
  * xr - xl is not always bit-identical to it), so the caller may override it. */
+static void ppm_coeffs_set(const gen_cfg *c, geom_t *g);
 static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]) {
   int n1 = g->tot[0], n2 = g->tot[1], n3 = g->tot[2];
   for (int d = 0; d < 3; d++)
@@ -242,13 +247,136 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
       g->dm[d][i] = (xgc[i] - xr[i - 1]) / dx[i];
     }
   }
+  if (c->ppm) ppm_coeffs_set(c, g);
+}
+
+/* ---------------------------------------------------------------------------------------
+ *  PPM (order 4) coefficients on general grids: States/ppm_coeffs.c:60-290 (PPM_CoefficientsSet),
+ *  :300-420 (PPM_FindWeights: B.w = xi^k by LU decomposition), :520-570 (PPM_Q6_Coeffs),
+ *  Math_Tools/math_lu_decomp.c (LUDecompose / LUBackSubst).  Cartesian, cylindrical and polar grids.
+ * --------------------------------------------------------------------------------------- */
+#define POLY_2(a0, a1, a2, x) (a0 + x * (a1 + x * a2))
+#define POLY_4(a0, a1, a2, a3, a4, x) (a0 + x * (a1 + x * (a2 + x * (a3 + x * a4))))
+static int lu_decompose(double a[8][8], int n, int *indx, double *d) {
+  int imax = 0;
+  double big, dum, sum, temp, vv[8];
+  *d = 1.0;
+  for (int i = 0; i < n; i++) {
+    big = 0.0;
+    for (int j = 0; j < n; j++) if ((temp = fabs(a[i][j])) > big) big = temp;
+    if (big == 0.0) return 0;
+    vv[i] = 1.0 / big;
+  }
+  for (int j = 0; j < n; j++) {
+    for (int i = 0; i < j; i++) {
+      sum = a[i][j];
+      for (int k = 0; k < i; k++) sum -= a[i][k] * a[k][j];
+      a[i][j] = sum;
+    }
+    big = 0.0;
+    for (int i = j; i < n; i++) {
+      sum = a[i][j];
+      for (int k = 0; k < j; k++) sum -= a[i][k] * a[k][j];
+      a[i][j] = sum;
+      if ((dum = vv[i] * fabs(sum)) >= big) { big = dum; imax = i; }
+    }
+    if (j != imax) {
+      for (int k = 0; k < n; k++) { dum = a[imax][k]; a[imax][k] = a[j][k]; a[j][k] = dum; }
+      *d = -(*d);
+      vv[imax] = vv[j];
+    }
+    indx[j] = imax;
+    if (a[j][j] == 0.0) a[j][j] = 1.0e-20;
+    if (j != n - 1) {
+      dum = 1.0 / (a[j][j]);
+      for (int i = j + 1; i < n; i++) a[i][j] *= dum;
+    }
+  }
+  return 1;
+}
+static void lu_backsubst(double a[8][8], int n, const int *indx, double *b) {
+  int ii = 0;
+  double sum;
+  for (int i = 0; i < n; i++) {
+    int ip = indx[i];
+    sum = b[ip];
+    b[ip] = b[i];
+    if (ii) for (int j = ii - 1; j <= i - 1; j++) sum -= a[i][j] * b[j];
+    else if (sum) ii = i + 1;
+    b[i] = sum;
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    sum = b[i];
+    for (int j = i + 1; j < n; j++) sum -= a[i][j] * b[j];
+    b[i] = sum / a[i][i];
+  }
+}
+static void ppm_coeffs_set(const gen_cfg *c, geom_t *g) {
+  const int iL = 1, iR = 2, n = 4;
+  for (int d = 0; d < c->ndim; d++) {
+    int nt = g->tot[d];
+    g->pwp[d] = calloc(nt, sizeof(*g->pwp[d]));
+    g->php[d] = calloc(nt, 8); g->phm[d] = calloc(nt, 8);
+    const int radial = (d == 0 && (c->geometry == CYLINDRICAL || c->geometry == POLAR));
+    for (int i = 0; i < nt; i++) {   /* PPM_Q6_Coeffs */
+      g->php[d][i] = 3.0; g->phm[d][i] = 3.0;
+      if (radial) {
+        g->php[d][i] = 3.0 + 0.5 * g->dx[0][i] / g->x[0][i];
+        g->phm[d][i] = 3.0 - 0.5 * g->dx[0][i] / g->x[0][i];
+      }
+    }
+    int beg = iL, end = nt - 1 - iR;
+    if (!c->uniform[d]) {            /* PPM_FindWeights */
+      for (int i = beg; i <= end; i++) {
+        double beta[8][8], a[16], dd;
+        int indx[16];
+        double rc = g->x[d][i];
+        int jb = i - iL, je = i + iR;
+        for (int j = jb; j <= je; j++) {
+          double rp = g->xr[d][j], rm = g->xl[d][j], vol;
+          if (!radial) {
+            vol = (rp - rm);
+            for (int k = 0; k < n; k++) beta[k][j - jb] = (pow(rp - rc, k + 1) - pow(rm - rc, k + 1)) / (k + 1.0) / vol;
+          } else {
+            vol = (rp * rp - rm * rm) / 2.0;
+            for (int k = 0; k < n; k++) {
+              beta[k][j - jb] = pow(rp - rc, k + 1) * ((k + 1.0) * rp + rc) - pow(rm - rc, k + 1) * ((k + 1.0) * rm + rc);
+              beta[k][j - jb] /= (k + 2.0) * (k + 1.0) * vol;
+            }
+          }
+        }
+        lu_decompose(beta, n, indx, &dd);
+        double rp = g->xr[d][i];
+        a[0] = 1.0;
+        for (int k = 1; k < n; k++) a[k] = a[k - 1] * (rp - rc);
+        lu_backsubst(beta, n, indx, a);
+        for (int j = 0; j < n; j++) g->pwp[d][i][j] = a[j];
+      }
+      continue;
+    }
+    for (int i = beg; i <= end; i++) {   /* PPM_CartCoeff */
+      g->pwp[d][i][0] = -1.0 / 12.0; g->pwp[d][i][1] = 7.0 / 12.0;
+      g->pwp[d][i][2] = 7.0 / 12.0;  g->pwp[d][i][3] = -1.0 / 12.0;
+    }
+    if (radial) {                        /* ppm_coeffs.c:150-165 */
+      for (int i = beg; i <= end; i++) {
+        double rp = g->xr[0][i], dr = g->dx[0][i];
+        double i1 = rp / dr, i2 = i1 * i1;
+        double den = 24.0 * POLY_2(4.0, -15.0, 5.0, i2);
+        g->pwp[d][i][0] = POLY_4(-12.0, -1.0, 30.0, -1.0, -10.0, i1) / den;
+        g->pwp[d][i][1] = POLY_4(60.0, -27.0, -210.0, 13.0, 70.0, i1) / den;
+        g->pwp[d][i][2] = POLY_4(60.0, 27.0, -210.0, -13.0, 70.0, i1) / den;
+        g->pwp[d][i][3] = POLY_4(-12.0, 1.0, 30.0, 1.0, -10.0, i1) / den;
+      }
+    }
+  }
 }
 
 static void geom_free(geom_t *g) {
   for (int d = 0; d < 3; d++) {
     free(g->x[d]); free(g->xl[d]); free(g->xr[d]); free(g->dx[d]); free(g->xgc[d]); free(g->inv_dx[d]);
     free(g->cp[d]); free(g->cm[d]); free(g->wp[d]); free(g->wm[d]); free(g->dp[d]); free(g->dm[d]);
-    free(g->A[d]); free(g->dx_dl[d]);
+    free(g->A[d]); free(g->dx_dl[d]); free(g->pwp[d]); free(g->php[d]); free(g->phm[d]);
   }
   free(g->rt); free(g->s); free(g->sp); free(g->dmu); free(g->dV);
   free(g);
@@ -376,6 +504,38 @@ static void sweep_free(sweep_t *s) {
   free(s->press - 1); free(s->cmax - 1); free(s->flag);
 }
 
+/* Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10) */
+static void flatten_oned(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end) {
+  int nvar = g->nvar, VXn = 1 + dir;
+  {
+    const int P = c->iso ? RHO : PRS;
+    int fb = MAXV(beg, 3), fe = MINV(end, g->tot[dir] - 4);
+    double *f_t = calloc(g->tot[dir] + 4, 8);
+    for (int i = fb - 1; i <= fe + 1; i++) {
+      double dp = s->v[i + 1][P] - s->v[i - 1][P];
+      double min_p = MINV(s->v[i + 1][P], s->v[i - 1][P]);
+      double d2p = s->v[i + 2][P] - s->v[i - 2][P];
+      double scrh = fabs(dp) / min_p;
+      if (scrh < 0.33 || (s->v[i + 1][VXn] > s->v[i - 1][VXn])) f_t[i] = 0.0;
+      else {
+        scrh = 10.0 * (fabs(dp / d2p) - 0.75);
+        scrh = MINV(1.0, scrh);
+        f_t[i] = MAXV(0.0, scrh);
+      }
+    }
+    for (int i = fb; i <= fe; i++) {
+      int sj = (s->v[i + 1][P] < s->v[i - 1][P] ? 1 : -1);
+      double fj = MAXV(f_t[i], f_t[i + sj]);
+      for (int nv = 0; nv < nvar; nv++) {
+        double vf = s->v[i][nv] * fj, scrh = 1.0 - fj;
+        s->vm[i][nv] = vf + s->vm[i][nv] * scrh;
+        s->vp[i][nv] = vf + s->vp[i][nv] * scrh;
+      }
+    }
+    free(f_t);
+  }
+}
+
 /* States/plm_states.c:83-337 (CHAR_LIMITING NO) and :481-690 (CHAR_LIMITING YES) */
 static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end) {
   int nvar = g->nvar;
@@ -477,33 +637,55 @@ static void states(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int b
       }
     }
   }
-  if (c->flatten_oned) {   /* Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10) */
-    const int P = c->iso ? RHO : PRS;
-    int fb = MAXV(beg, 3), fe = MINV(end, g->tot[dir] - 4);
-    double *f_t = calloc(g->tot[dir] + 4, 8);
-    for (int i = fb - 1; i <= fe + 1; i++) {
-      double dp = s->v[i + 1][P] - s->v[i - 1][P];
-      double min_p = MINV(s->v[i + 1][P], s->v[i - 1][P]);
-      double d2p = s->v[i + 2][P] - s->v[i - 2][P];
-      double scrh = fabs(dp) / min_p;
-      if (scrh < 0.33 || (s->v[i + 1][VXn] > s->v[i - 1][VXn])) f_t[i] = 0.0;
-      else {
-        scrh = 10.0 * (fabs(dp / d2p) - 0.75);
-        scrh = MINV(1.0, scrh);
-        f_t[i] = MAXV(0.0, scrh);
-      }
+  if (c->flatten_oned) flatten_oned(c, g, s, dir, beg, end);
+}
+
+/* States/ppm_states.c:66-232 (CHAR_LIMITING NO, PPM_ORDER 4) */
+static void states_ppm(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end) {
+  int nvar = g->nvar;
+  for (int i = beg - 1; i <= end; i++) {   /* unique interface value, clipped between the cell averages */
+    const double *wp = g->pwp[dir][i];
+    for (int nv = 0; nv < nvar; nv++) {
+      s->vp[i][nv] = wp[0] * s->v[i - 1][nv] + wp[1] * s->v[i][nv] + wp[2] * s->v[i + 1][nv] + wp[3] * s->v[i + 2][nv];
+      double dv = s->v[i + 1][nv] - s->v[i][nv];
+      double dvp = s->vp[i][nv] - s->v[i][nv];
+      s->vp[i][nv] = s->v[i][nv] + MINMOD_LIMITER(dvp, dv);
     }
-    for (int i = fb; i <= fe; i++) {
-      int sj = (s->v[i + 1][P] < s->v[i - 1][P] ? 1 : -1);
-      double fj = MAXV(f_t[i], f_t[i + sj]);
-      for (int nv = 0; nv < nvar; nv++) {
-        double vf = s->v[i][nv] * fj, scrh = 1.0 - fj;
-        s->vm[i][nv] = vf + s->vm[i][nv] * scrh;
-        s->vp[i][nv] = vf + s->vp[i][nv] * scrh;
-      }
-    }
-    free(f_t);
   }
+  for (int i = beg; i <= end; i++) for (int nv = 0; nv < nvar; nv++) s->vm[i][nv] = s->vp[i - 1][nv];
+  for (int i = beg; i <= end; i++) {
+    const double *v = s->v[i];
+    if (c->flattening) {
+      if (s->flag[i] & FLAG_FLAT) {
+        for (int nv = 0; nv < nvar; nv++) s->vp[i][nv] = s->vm[i][nv] = v[nv];
+        continue;
+      } else if (s->flag[i] & FLAG_MINMOD) {
+        for (int nv = 0; nv < nvar; nv++) {
+          double dvp = (s->v[i + 1][nv] - v[nv]) * g->wp[dir][i];
+          double dvm = (v[nv] - s->v[i - 1][nv]) * g->wm[dir][i];
+          double dv = MINMOD_LIMITER(dvp, dvm);
+          s->vp[i][nv] = v[nv] + dv * g->dp[dir][i];
+          s->vm[i][nv] = v[nv] - dv * g->dm[dir][i];
+        }
+        continue;
+      }
+    }
+    double hp = g->php[dir][i], hm = g->phm[dir][i];
+    double cm = (hm + 1.0) / (hp - 1.0);
+    double cp = (hp + 1.0) / (hm - 1.0);
+    for (int nv = 0; nv < nvar; nv++) {
+      double dvp = s->vp[i][nv] - v[nv];
+      double dvm = s->vm[i][nv] - v[nv];
+      if (dvp * dvm >= 0.0) dvp = dvm = 0.0;
+      else {
+        if (fabs(dvp) >= cm * fabs(dvm)) dvp = -cm * dvm;
+        else if (fabs(dvm) >= cp * fabs(dvp)) dvm = -cp * dvp;
+      }
+      s->vp[i][nv] = v[nv] + dvp;
+      s->vm[i][nv] = v[nv] + dvm;
+    }
+  }
+  if (c->flatten_oned) flatten_oned(c, g, s, dir, beg, end);   /* ppm_states.c:229-231 */
 }
 
 /* HD/hllc.c:28-178, HD/hll.c:30-96, HD/tvdlf.c:38-130, HD/hll_speed.c:76-90, HD/fluxes.c:36-47,
@@ -937,7 +1119,8 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
           for (int nv = 0; nv < nvar; nv++) s.v[n][nv] = Vc[nv * g->sv + base + n * st];
           s.flag[n] = flag[base + n * st];
         }
-        states(c, g, &s, dir, nbeg - 1, nend + 1);
+        if (c->ppm) states_ppm(c, g, &s, dir, nbeg - 1, nend + 1);
+        else states(c, g, &s, dir, nbeg - 1, nend + 1);
         riemann(c, g, &s, dir, nbeg - 1, nend, maxMach);
         /* ---- RightHandSide ---- */
         int i = idx[0], j = idx[1], k = idx[2];

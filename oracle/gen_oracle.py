@@ -28,7 +28,8 @@ class GenCfg(C.Structure):
                 ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
                 ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
                 ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p),
-                ("iso", C.c_int), ("iso_cs", C.c_double), ("flatten_oned", C.c_int)]
+                ("iso", C.c_int), ("iso_cs", C.c_double), ("flatten_oned", C.c_int),
+                ("ppm", C.c_int), ("uniform", C.c_int * 3)]
 
 
 _bound = False
@@ -61,7 +62,9 @@ class GenOracle:
                  nghost=2, small_density=1e-12, small_pressure=1e-12, body_force=0, char_limiting=False,
                  shock_flattening=False, entropy_switch=False, ldw=None, eos="IDEAL",
                  iso_sound_speed=1.0, **_):
-        assert reconstruction == "LINEAR"
+        assert reconstruction in ("LINEAR", "PARABOLIC")
+        assert not (reconstruction == "PARABOLIC" and (char_limiting or geometry == "SPHERICAL")), \
+            "PPM of the general-grid oracle: CHAR_LIMITING NO; Cartesian, cylindrical or polar grids"
         c = GenCfg()
         c.ndim = dimensions
         self._keep = []
@@ -74,6 +77,9 @@ class GenOracle:
             c.xl[d] = xl.ctypes.data
             c.xr[d] = xr.ctypes.data
         c.ng = nghost
+        c.ppm = int(reconstruction == "PARABOLIC")
+        for d in range(3):      # grid->uniform[d]: a single uniform patch (set_grid.c:67-72)
+            c.uniform[d] = int(len(grid[d]) <= 3 or grid[d][3] == "u")
         c.ntracer = ntracer
         c.entropy = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
         c.geometry = GEOMETRY[geometry]

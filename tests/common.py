@@ -6,7 +6,7 @@ import numpy as np
 GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
 # cylindrical / polar / isothermal fixtures pin the ORACLE only (the CUDA path refuses these options so far)
-_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned")
+_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg")
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -63,7 +63,7 @@ def gen_kwargs_from_golden(g):
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
                 char_limiting=bool(int(g["char_limiting"])), shock_flattening={0: False, 1: True, 2: "ONED"}[flat],
                 entropy_switch={0: False, 1: "SELECTIVE", 2: "ALWAYS"}[_entr_code(g)],
-                nghost={0: 2, 1: 3, 2: 4}[flat])     # GetNghost(), Src/get_nghost.c:42-57
+                nghost=max({0: 2, 1: 3, 2: 4}[flat], 3 if g["recon"] == "PARABOLIC" else 2))     # GetNghost(), Src/get_nghost.c:42-57
 
 
 def set_point_mass_gravity(obj, gm):

@@ -135,7 +135,7 @@ def make_case3(out, name, c):
     gridarr = np.array([[g[0], g[1], g[2], 1.0 if (len(g) > 3 and g[3] == "r") else 0.0,
                          g[4] if len(g) > 4 else 1.0] for g in grid], dtype=np.float64)
     np.savez_compressed(out / (name + ".npz"), data=data, steps=steps, nx=np.array(nx), dims=nd,
-                        recon="LINEAR", rk="RK2", solver=c["solver"], bcs=np.array(c["bcs"]),
+                        recon=c.get("recon", "LINEAR"), rk=c.get("rk", "RK2"), solver=c["solver"], bcs=np.array(c["bcs"]),
                         gamma=c.get("gamma", 5. / 3.), cfl=c.get("cfl", 0.4), cfl_max_var=1.1, first_dt=c.get("first_dt", 1e-5),
                         tstop=c.get("tstop", 10.0),
                         ref_config=c["cfg"], gridspec=gridarr, geometry=c.get("geometry", "SPHERICAL"), ntracer=ntr,
@@ -223,6 +223,24 @@ CASES6 = {
                            grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="hll",
                            bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
                            params=ISO_PAR, maxsteps=10, first_dt=1e-4, shock_flattening="ONED"),
+    # RECONSTRUCTION PARABOLIC + RK3 on general grids (ppm_coeffs.c weights); "ppmg" prefix: ORACLE fixtures
+    "ppmg_kh3d_stretched": dict(cfg="kh3d_ppm", dims=3, geometry="CARTESIAN", body_force="none", recon="PARABOLIC", rk="RK3",
+                                grid=[(0.0, 16, 1.0, "r", 1.04), (-0.5, 20, 0.5, "r", 0.97), (0.0, 8, 0.5)],
+                                solver="hllc", bcs=KH_BCS, params=dict(A_KH=0.05, DRHO=1.0, MACH=0.8), gamma=1.4,
+                                maxsteps=6, first_dt=1e-4),
+    "ppmg_cyl2d_uniform": dict(cfg="cyl2d_ppm", dims=2, geometry="CYLINDRICAL", recon="PARABOLIC", rk="RK3",
+                               grid=[(0.8, 36, 3.0), (0.0, 28, 1.5), (0.0, 1, 1.0)], solver="hllc",
+                               bcs=("outflow", "outflow", "eqtsymmetric", "outflow", "periodic", "periodic"),
+                               params=CYL_PAR, maxsteps=8),
+    "ppmg_cyl2d_flat_stretched": dict(cfg="cyl2d_ppm_flat", dims=2, geometry="CYLINDRICAL", recon="PARABOLIC", rk="RK3",
+                                      shock_flattening=True,
+                                      grid=[(0.8, 36, 3.0, "r", 1.03), (0.0, 28, 1.5, "r", 1.02), (0.0, 1, 1.0)], solver="hll",
+                                      bcs=("reflective", "outflow", "eqtsymmetric", "outflow", "periodic", "periodic"),
+                                      params=CYL_PAR, maxsteps=8),
+    "ppmg_pol2d": dict(cfg="pol2d_ppm", dims=2, geometry="POLAR", recon="PARABOLIC", rk="RK3",
+                       grid=[(0.8, 32, 3.0, "r", 1.03), (0.0, 40, TWO_PI), (0.0, 1, 1.0)], solver="roe",
+                       bcs=("reflective", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                       params=CYL_PAR, maxsteps=8),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),

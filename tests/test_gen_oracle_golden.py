@@ -41,7 +41,9 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     (hllc.c:137-150) and eigenvectors (eigenv.c:175-196), Cartesian 2-D / 3-D and spherical with gravity.
     The roe_* fixtures add Roe_Solver (HD/roe.c: Roe average, entropy fix, HLL inside strong shocks and
     flagged zones) for both equations of state, the twoshock_* ones TwoShock_Solver (HD/two_shock.c),
-    the oned_* ones SHOCK_FLATTENING ONED (States/flatten.c, 4 ghost zones).
+    the oned_* ones SHOCK_FLATTENING ONED (States/flatten.c, 4 ghost zones), the ppmg_* ones RECONSTRUCTION
+    PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c (PPM_FindWeights through the LU
+    solve on stretched grids, the closed forms on uniform cylindrical grids, PPM_Q6_Coeffs).
     These fixtures pin the oracle ahead of the CUDA path, which still refuses these options (PB200_ENOTSUP)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
