@@ -110,6 +110,9 @@ CONFIGS = {
                                                    "SHOCK_FLATTENING": "MULTID"}, states="ppm"),
     "pol2d_ppm": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "RECONSTRUCTION": "PARABOLIC",
                                               "TIME_STEPPING": "RK3"}, states="ppm"),
+    "sph2d_ppm": dict(local="sph", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
+    "sph3d_ppm": dict(local="sph", overrides={"DIMENSIONS": "3", "RECONSTRUCTION": "PARABOLIC",
+                                              "TIME_STEPPING": "RK3"}, states="ppm"),
     # EOS ISOTHERMAL (oracle/problems/iso): Cartesian 2-D / 3-D, spherical 2-D with gravity
     "iso2d": dict(local="iso", overrides={}, states="plm"),
     "iso2d_flat": dict(local="iso", overrides={"CHAR_LIMITING": "YES", "LIMITER": "VANLEER_LIM",

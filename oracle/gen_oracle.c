@@ -253,10 +253,35 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
 /* ---------------------------------------------------------------------------------------
  *  PPM (order 4) coefficients on general grids: States/ppm_coeffs.c:60-290 (PPM_CoefficientsSet),
  *  :300-420 (PPM_FindWeights: B.w = xi^k by LU decomposition), :520-570 (PPM_Q6_Coeffs),
- *  Math_Tools/math_lu_decomp.c (LUDecompose / LUBackSubst).  Cartesian, cylindrical and polar grids.
+ *  Math_Tools/math_lu_decomp.c (LUDecompose / LUBackSubst), Math_Tools/math_quadrature.c:30-78,356-409
+ *  (5-point Gauss rule for the sin(theta) moments).  All four geometries.
  * --------------------------------------------------------------------------------------- */
 #define POLY_2(a0, a1, a2, x) (a0 + x * (a1 + x * a2))
 #define POLY_4(a0, a1, a2, a3, a4, x) (a0 + x * (a1 + x * (a2 + x * (a3 + x * a4))))
+#define POLY_6(a0, a1, a2, a3, a4, a5, a6, x) (a0 + x * (a1 + x * (a2 + x * (a3 + x * (a4 + x * (a5 + x * a6))))))
+/* GaussQuadrature(&BetaTheta, NULL, xb, xe, 1, 5): int_xb^xe (x - x0)^k sin(x) dx */
+static double gauss5_beta_theta(double xb0, double xe0, double x0, int k) {
+  double one_third = 1.0 / 3.0, ten_seventh = 10.0 / 7.0, z[5], w[5];
+  z[0] = 0.0;
+  z[1] = sqrt(5.0 - 2.0 * sqrt(ten_seventh)) * one_third;
+  z[2] = -sqrt(5.0 - 2.0 * sqrt(ten_seventh)) * one_third;
+  z[3] = sqrt(5.0 + 2.0 * sqrt(ten_seventh)) * one_third;
+  z[4] = -sqrt(5.0 + 2.0 * sqrt(ten_seventh)) * one_third;
+  w[0] = 128.0 / 225.0;
+  w[1] = (322.0 + 13.0 * sqrt(70.0)) / 900.0;
+  w[2] = (322.0 + 13.0 * sqrt(70.0)) / 900.0;
+  w[3] = (322.0 - 13.0 * sqrt(70.0)) / 900.0;
+  w[4] = (322.0 - 13.0 * sqrt(70.0)) / 900.0;
+  double dx = (xe0 - xb0) / (double)1, I = 0.0;
+  double xb = xb0 + 0 * dx, xe = xb + dx, Isub = 0.0;
+  for (int n = 0; n < 5; n++) {
+    double x = 0.5 * (xe - xb) * z[n] + (xe + xb) * 0.5;
+    Isub += w[n] * (pow(x - x0, k) * sin(x));
+  }
+  Isub *= 0.5 * (xe - xb);
+  I += Isub;
+  return I;
+}
 static int lu_decompose(double a[8][8], int n, int *indx, double *d) {
   int imax = 0;
   double big, dum, sum, temp, vv[8];
@@ -318,15 +343,29 @@ static void ppm_coeffs_set(const gen_cfg *c, geom_t *g) {
     g->pwp[d] = calloc(nt, sizeof(*g->pwp[d]));
     g->php[d] = calloc(nt, 8); g->phm[d] = calloc(nt, 8);
     const int radial = (d == 0 && (c->geometry == CYLINDRICAL || c->geometry == POLAR));
+    const int sph_r = (d == 0 && c->geometry == SPHERICAL), sph_t = (d == 1 && c->geometry == SPHERICAL);
     for (int i = 0; i < nt; i++) {   /* PPM_Q6_Coeffs */
       g->php[d][i] = 3.0; g->phm[d][i] = 3.0;
       if (radial) {
         g->php[d][i] = 3.0 + 0.5 * g->dx[0][i] / g->x[0][i];
         g->phm[d][i] = 3.0 - 0.5 * g->dx[0][i] / g->x[0][i];
+      } else if (sph_r) {
+        double r = g->x[0][i], dr = g->dx[0][i];
+        double den = 20.0 * r * r + dr * dr;
+        g->php[d][i] = 3.0 + 2.0 * dr * (10.0 * r + dr) / den;
+        g->phm[d][i] = 3.0 - 2.0 * dr * (10.0 * r - dr) / den;
+      } else if (sph_t && i > 0) {   /* the reference reads thp[-1] for i = 0; that entry is never used */
+        const double *thp = g->xr[1], *dth = g->dx[1];
+        double cp = cos(thp[i]), sp = sin(thp[i]);
+        double cm = cos(thp[i - 1]), sm = sin(thp[i - 1]);
+        double dmu = cm - cp;
+        double dmu_t = sm - sp;
+        g->php[d][i] = dth[i] * (dmu_t + dth[i] * cp) / (dth[i] * (sp + sm) - 2.0 * dmu);
+        g->phm[d][i] = -dth[i] * (dmu_t + dth[i] * cm) / (dth[i] * (sp + sm) - 2.0 * dmu);
       }
     }
     int beg = iL, end = nt - 1 - iR;
-    if (!c->uniform[d]) {            /* PPM_FindWeights */
+    if (!c->uniform[d] || sph_t) {   /* PPM_FindWeights (the meridional direction always, ppm_coeffs.c:268-269) */
       for (int i = beg; i <= end; i++) {
         double beta[8][8], a[16], dd;
         int indx[16];
@@ -334,7 +373,18 @@ static void ppm_coeffs_set(const gen_cfg *c, geom_t *g) {
         int jb = i - iL, je = i + iR;
         for (int j = jb; j <= je; j++) {
           double rp = g->xr[d][j], rm = g->xl[d][j], vol;
-          if (!radial) {
+          if (sph_t) {
+            vol = cos(rm) - cos(rp);
+            for (int k = 0; k < n; k++) beta[k][j - jb] = gauss5_beta_theta(rm, rp, rc, k);
+            beta[0][j - jb] /= vol; beta[1][j - jb] /= vol; beta[2][j - jb] /= vol; beta[3][j - jb] /= vol;
+          } else if (sph_r) {
+            vol = (rp * rp * rp - rm * rm * rm) / 3.0;
+            for (int k = 0; k < n; k++) {
+              beta[k][j - jb] = pow(rp - rc, k + 1) * ((k * k + 3.0 * k + 2.0) * rp * rp + 2.0 * rc * (k + 1.0) * rp + 2.0 * rc * rc)
+                              - pow(rm - rc, k + 1) * ((k * k + 3.0 * k + 2.0) * rm * rm + 2.0 * rc * (k + 1.0) * rm + 2.0 * rc * rc);
+              beta[k][j - jb] /= (k + 3.0) * (k + 2.0) * (k + 1.0) * vol;
+            }
+          } else if (!radial) {
             vol = (rp - rm);
             for (int k = 0; k < n; k++) beta[k][j - jb] = (pow(rp - rc, k + 1) - pow(rm - rc, k + 1)) / (k + 1.0) / vol;
           } else {
@@ -367,6 +417,17 @@ static void ppm_coeffs_set(const gen_cfg *c, geom_t *g) {
         g->pwp[d][i][1] = POLY_4(60.0, -27.0, -210.0, 13.0, 70.0, i1) / den;
         g->pwp[d][i][2] = POLY_4(60.0, 27.0, -210.0, -13.0, 70.0, i1) / den;
         g->pwp[d][i][3] = POLY_4(-12.0, 1.0, 30.0, 1.0, -10.0, i1) / den;
+      }
+    }
+    if (sph_r) {                         /* ppm_coeffs.c:216-229 */
+      for (int i = beg; i <= end; i++) {
+        double rp = g->xr[0][i], dr = g->dx[0][i];
+        double i1 = fabs(rp / dr), i2 = i1 * i1;
+        double den = 36.0 * POLY_4(16.0, -60.0, 150.0, -85.0, 15.0, i2);
+        g->pwp[d][i][0] = -POLY_2(7, -9, 3, i1) / den * POLY_6(12, 16, -30, -48.0, 23, 48, 15, i1);
+        g->pwp[d][i][1] = POLY_2(1, -3, 3, i1) / den * POLY_6(372, 1008.0, 510, -720, -487, 144, 105, i1);
+        g->pwp[d][i][2] = POLY_2(1, 3, 3.0, i1) / den * POLY_6(372, -1008, 510, 720, -487, -144, 105, i1);
+        g->pwp[d][i][3] = -POLY_2(7, 9, 3, i1) / den * POLY_6(12, -16, -30, 48, 23, -48, 15, i1);
       }
     }
   }
