@@ -8,13 +8,16 @@
  * by oracle/build_ref.py with the user files of oracle/problems/) through the golden dumps of
  * tests/golden/ (tests/test_gen_oracle_golden.py).
  *
- * Scope: PHYSICS HD, EOS IDEAL or ISOTHERMAL, GEOMETRY CARTESIAN, CYLINDRICAL, POLAR or SPHERICAL, DIMENSIONS 1-3, uniform or
- * non-uniform grids (grid->xl/xr are inputs: the reference's own set_grid.c output),
- * RECONSTRUCTION LINEAR with every LIMITER, CHAR_LIMITING NO/YES, SHOCK_FLATTENING NO/MULTID,
- * ENTROPY_SWITCH NO/ALWAYS, NTRACER >= 0, BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3,
- * Solver tvdlf/hll/hllc, outflow/reflective/axisymmetric/eqtsymmetric/periodic boundaries plus
- * the user-defined boundaries of the line-driven-wind problem, LINE_DRIVEN_WIND (VGradCalc +
- * LineForce) and COOLING BLONDIN.
+ * Scope: PHYSICS HD, EOS IDEAL or ISOTHERMAL, GEOMETRY CARTESIAN / CYLINDRICAL / POLAR / SPHERICAL,
+ * DIMENSIONS 1-3, uniform or non-uniform grids (grid->xl/xr are inputs: the reference's own
+ * set_grid.c output), RECONSTRUCTION LINEAR with every LIMITER and CHAR_LIMITING NO/YES, or
+ * PARABOLIC (order 4, CHAR_LIMITING NO) with the general-grid weights of ppm_coeffs.c,
+ * SHOCK_FLATTENING NO / MULTID / ONED, ENTROPY_SWITCH NO / SELECTIVE / ALWAYS, NTRACER >= 0,
+ * BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock,
+ * outflow / reflective / axisymmetric / eqtsymmetric / periodic boundaries plus the user-defined
+ * boundaries of the line-driven-wind problems (cv_idl, cv_iso), LINE_DRIVEN_WIND (VGradCalc +
+ * LineForce, power law or M(t) fit) and COOLING BLONDIN.
+ * The CUDA path covers the subset DESIGN.md lists; the rest is pinned here ahead of it.
  *
  * Plain C17, scalar, pencil by pencil like the reference so that the operation order is the
  * reference's; build with -ffp-contract=off.  Each function cites the reference file:line.
