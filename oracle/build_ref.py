@@ -110,6 +110,9 @@ CONFIGS = {
                                                    "SHOCK_FLATTENING": "MULTID"}, states="ppm"),
     "pol2d_ppm": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "RECONSTRUCTION": "PARABOLIC",
                                               "TIME_STEPPING": "RK3"}, states="ppm"),
+    "sph2d_pot": dict(local="sph", overrides={"BODY_FORCE": "POTENTIAL"}, states="plm"),
+    "sph3d_pot": dict(local="sph", overrides={"DIMENSIONS": "3", "BODY_FORCE": "(VECTOR+POTENTIAL)"}, states="plm"),
+    "pol2d_pot": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "BODY_FORCE": "POTENTIAL"}, states="plm"),
     "sph2d_ppm": dict(local="sph", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
     "sph3d_ppm": dict(local="sph", overrides={"DIMENSIONS": "3", "RECONSTRUCTION": "PARABOLIC",
                                               "TIME_STEPPING": "RK3"}, states="ppm"),

@@ -13,7 +13,7 @@
  * set_grid.c output), RECONSTRUCTION LINEAR with every LIMITER and CHAR_LIMITING NO/YES, or
  * PARABOLIC (order 4, CHAR_LIMITING NO) with the general-grid weights of ppm_coeffs.c,
  * SHOCK_FLATTENING NO / MULTID / ONED, ENTROPY_SWITCH NO / SELECTIVE / ALWAYS, NTRACER >= 0,
- * BODY_FORCE VECTOR, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock,
+ * BODY_FORCE VECTOR / POTENTIAL, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock,
  * outflow / reflective / axisymmetric / eqtsymmetric / periodic boundaries plus the user-defined
  * boundaries of the line-driven-wind problems (cv_idl, cv_iso), LINE_DRIVEN_WIND (VGradCalc +
  * LineForce, power law or M(t) fit) and COOLING BLONDIN.
@@ -63,7 +63,7 @@ typedef struct gen_cfg {
   int bc[6];                /* pluto.h:163-170; 8 userdef -> ldw_bc != 0 selects the built-in LDW fills */
   double gamma, small_dn, small_pr;
   const double *xl[3], *xr[3];   /* grid->xl, grid->xr incl. ghosts (np_tot each) */
-  int body_force;           /* bit 0: VECTOR */
+  int body_force;           /* bit 0: VECTOR, bit 1: POTENTIAL (tables bf_phi below) */
   const double *bf_g[3];    /* BodyForceVector at zone centres, [k][j][i] incl. ghosts */
   /* --- line-driven wind (Src/LineDriven/line_connect.c), COOLING BLONDIN: see ldw section --- */
   int ldw;                  /* LINE_DRIVEN_WIND != NO */
@@ -85,6 +85,8 @@ typedef struct gen_cfg {
   int flatten_oned;         /* SHOCK_FLATTENING ONED (States/flatten.c); `flattening` above is MULTID */
   int ppm;                  /* RECONSTRUCTION PARABOLIC (PPM_ORDER 4), CHAR_LIMITING NO */
   int uniform[3];           /* grid->uniform[d] (set_grid.c:67-72): one uniform patch along d */
+  const double *bf_phi[4];  /* body_force bit 1 (POTENTIAL): BodyForcePotential at zone centres [0] and at the
+                               x1 / x2 / x3 upper faces [1..3], [k][j][i] incl. ghosts */
 } gen_cfg;
 
 #define NF(c) ((c)->iso ? 4 : NFLX)                     /* NFLX of the configuration (mod_defs.h) */
@@ -1167,6 +1169,7 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
   if (c->ndim > 1 && stage == 1) memset(C_dt, 0, sizeof(double) * g->sv);
   if (c->ldw) ldw_vgrad_calc(c, g, Vc, dvds);         /* update_stage.c:116-118 */
   double *inv_dl = calloc(nmax, 8);
+  double *phi_p = calloc(nmax, 8);
   for (int dir = 0; dir < c->ndim; dir++) {
     int VXn = 1 + dir;
     const int iMPHI = (c->geometry == POLAR) ? VX2 : VX3;   /* pluto.h: iVPHI per geometry */
@@ -1186,6 +1189,12 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
         if (c->ppm) states_ppm(c, g, &s, dir, nbeg - 1, nend + 1);
         else states(c, g, &s, dir, nbeg - 1, nend + 1);
         riemann(c, g, &s, dir, nbeg - 1, nend, maxMach);
+        if (c->body_force & 2) {   /* TotalFlux(): flux[ENG] += flux[RHO] phi_p at the faces (rhs.c:171-179,525,581,621) */
+          for (int n = nbeg - 1; n <= nend; n++) {
+            phi_p[n] = c->bf_phi[1 + dir][base + n * st];
+            if (!c->iso) s.flux[n][PRS] += s.flux[n][RHO] * phi_p[n];
+          }
+        }
         /* ---- RightHandSide ---- */
         int i = idx[0], j = idx[1], k = idx[2];
         if (c->geometry == CARTESIAN) {
@@ -1247,9 +1256,28 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
             s.rhs[n][VX2] += dt * Sm * r_1;
           }
           double gv[3];
-          for (int pass = 0; pass < 2; pass++) {
+          for (int pass = 0; pass < 3; pass++) {
             /* pass 0: BodyForceVector (rhs_source.c:253-272,360-376,428-440);
-             * pass 1: LineForce, same pattern (rhs_source.c:284-297,386-396,448-458) */
+             * pass 1: BodyForcePotential (rhs_source.c:274-279,378-383,442-447);
+             * pass 2: LineForce, same pattern as pass 0 (rhs_source.c:284-297,386-396,448-458) */
+            if (pass == 1) {
+              if (!(c->body_force & 2)) continue;
+              double dtdx;
+              if (dir == 0) dtdx = dt / g->dx[0][n];
+              else if (dir == 1) {
+                double scrh = dt;
+                if (c->geometry == POLAR) scrh /= g->x[0][i];
+                else if (c->geometry == SPHERICAL) scrh /= g->rt[i];
+                dtdx = scrh / g->dx[1][n];
+              } else {
+                double scrh = dt;
+                if (c->geometry == SPHERICAL) scrh *= g->dx[1][j] / (g->rt[i] * g->dmu[j]);
+                dtdx = scrh / g->dx[2][n];
+              }
+              s.rhs[n][VXn] -= dtdx * vg[RHO] * (phi_p[n] - phi_p[n - 1]);
+              if (!c->iso) s.rhs[n][PRS] -= c->bf_phi[0][o] * s.rhs[n][RHO];
+              continue;
+            }
             if (pass == 0) {
               if (!(c->body_force & 1)) continue;
               gv[0] = c->bf_g[0][o]; gv[1] = c->bf_g[1][o]; gv[2] = c->bf_g[2][o];
@@ -1299,6 +1327,7 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
     *invDt_hyp /= (double)c->ndim;
   }
   free(inv_dl);
+  free(phi_p);
   sweep_free(&s);
 }
 

@@ -29,7 +29,7 @@ class GenCfg(C.Structure):
                 ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
                 ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p),
                 ("iso", C.c_int), ("iso_cs", C.c_double), ("flatten_oned", C.c_int),
-                ("ppm", C.c_int), ("uniform", C.c_int * 3)]
+                ("ppm", C.c_int), ("uniform", C.c_int * 3), ("bf_phi", C.c_void_p * 4)]
 
 
 _bound = False
@@ -117,6 +117,12 @@ class GenOracle:
         a = np.ascontiguousarray(np.broadcast_to(tab, self.shape[1:]), dtype=np.float64)
         self._bf[comp] = a
         self.c.bf_g[comp] = a.ctypes.data
+
+    def set_body_force_potential(self, where, tab):
+        """where: 0 zone centres, 1..3 the x1 / x2 / x3 upper faces (same convention as Hydro)."""
+        a = np.ascontiguousarray(np.broadcast_to(tab, self.shape[1:]), dtype=np.float64)
+        self._bf[10 + where] = a
+        self.c.bf_phi[where] = a.ctypes.data
 
     def set_ldw(self, *, params, units, flux_r, flux_t, flux_p, userdef_bc=True, t_fit=None, m_fit=None):
         """LINE_DRIVEN_WIND SIROCCO_MODE: g_inputParam[] of cv_idl (dict by label), UNIT_* (dict),

@@ -6,7 +6,7 @@ import numpy as np
 GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
 # cylindrical / polar / isothermal fixtures pin the ORACLE only (the CUDA path refuses these options so far)
-_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg")
+_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot")
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -37,7 +37,7 @@ def load_golden(name):
     return g
 
 
-BODY_FORCE = dict(none=0, vector=1, potential=2)
+BODY_FORCE = dict(none=0, vector=1, potential=2, both=3)
 
 
 def _entr_code(g):
@@ -68,12 +68,19 @@ def gen_kwargs_from_golden(g):
 
 def set_point_mass_gravity(obj, gm):
     """BodyForceVector of oracle/problems/sph/init.c: g = (-GM/x1^2, 0, 0) at the zone centres."""
-    if not getattr(obj, "cfg", getattr(obj, "c", None)).body_force:
+    bf = getattr(obj, "cfg", getattr(obj, "c", None)).body_force
+    if not bf:
         return
     x1 = obj.x(0)
-    obj.set_body_force_vector(0, (-gm / (x1 * x1)).reshape(1, 1, -1))
-    obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
-    obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
+    if bf & 1:
+        obj.set_body_force_vector(0, (-gm / (x1 * x1)).reshape(1, 1, -1))
+        obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
+        obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
+    if bf & 2:     # BodyForcePotential = -GM/x1 at the centres, the x1 upper faces, and (x1 centre) the x2 / x3 faces
+        obj.set_body_force_potential(0, (-gm / x1).reshape(1, 1, -1))
+        obj.set_body_force_potential(1, (-gm / obj.xr[0]).reshape(1, 1, -1))
+        obj.set_body_force_potential(2, (-gm / x1).reshape(1, 1, -1))
+        obj.set_body_force_potential(3, (-gm / x1).reshape(1, 1, -1))
 
 
 def kwargs_from_golden(g):

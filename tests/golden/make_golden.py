@@ -248,6 +248,16 @@ CASES6 = {
     "ppmg_sph3d": dict(cfg="sph3d_ppm", dims=3, recon="PARABOLIC", rk="RK3",
                        grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)], solver="hllc",
                        bcs=("outflow", "outflow", "reflective", "reflective", "periodic", "periodic"), maxsteps=5),
+    # BODY_FORCE POTENTIAL on curvilinear grids; "pot" prefix: ORACLE fixtures
+    "pot_sph2d_hllc": dict(cfg="sph2d_pot", dims=2, grid=SPH_GRID2, solver="hllc", bcs=SPH_BCS, maxsteps=8,
+                           body_force="potential"),
+    "pot_sph3d_both_hll": dict(cfg="sph3d_pot", dims=3, grid=[(1.0, 20, 3.0, "r", 1.04), (0.3, 14, HALF_PI), (0.0, 10, 1.0)],
+                               solver="hll", bcs=("outflow", "outflow", "reflective", "reflective", "periodic", "periodic"),
+                               maxsteps=5, body_force="both"),
+    "pot_pol2d_roe": dict(cfg="pol2d_pot", dims=2, geometry="POLAR", body_force="potential",
+                          grid=[(0.8, 32, 3.0, "r", 1.03), (0.0, 40, TWO_PI), (0.0, 1, 1.0)], solver="roe",
+                          bcs=("reflective", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                          params=CYL_PAR, maxsteps=8),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),

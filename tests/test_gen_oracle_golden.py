@@ -44,7 +44,8 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     the oned_* ones SHOCK_FLATTENING ONED (States/flatten.c, 4 ghost zones), the ppmg_* ones RECONSTRUCTION
     PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c (PPM_FindWeights through the LU
     solve on stretched grids, the closed forms on uniform cylindrical / spherical radial grids, the 5-point
-    Gauss moments of sin(theta) for the meridional direction, PPM_Q6_Coeffs).
+    Gauss moments of sin(theta) for the meridional direction, PPM_Q6_Coeffs), the pot_* ones BODY_FORCE
+    POTENTIAL (and VECTOR + POTENTIAL) on spherical and polar grids.
     These fixtures pin the oracle ahead of the CUDA path, which still refuses these options (PB200_ENOTSUP)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
