@@ -55,6 +55,7 @@ static int upload_grid(pb200_ctx *c, int dir) {
   std::vector<double> inv(n);
   for (int i = 0; i < n; i++) inv[i] = 1.0 / c->dx[dir][i];  // grid->inv_dx
   CK(cudaMemcpy(c->d_invdx[dir], inv.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());   // pageable copy on the legacy stream; the sweeps run on a non-blocking stream
   return PB200_OK;
 }
 
@@ -255,6 +256,7 @@ static int set_bf_table(pb200_ctx *c, int q, const double *tab, long n, long si,
   if (c->d_bf[q]) { cudaFree(c->d_bf[q]); c->d_bf[q] = nullptr; }
   CK(cudaMalloc(&c->d_bf[q], n * sizeof(double)));
   CK(cudaMemcpy(c->d_bf[q], tab, n * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());   // pageable copy on the legacy stream; the sweeps run on a non-blocking stream
   c->dev.bf_tab[q] = c->d_bf[q];
   c->dev.bf_st[q][0] = si; c->dev.bf_st[q][1] = sj; c->dev.bf_st[q][2] = sk;
   return PB200_OK;

@@ -22,16 +22,16 @@ template <typename T>
 T *upload(pb200_ctx *c, const std::vector<T> &h) {
   T *p = nullptr;
   if (cudaMalloc(&p, h.size() * sizeof(T)) != cudaSuccess) return nullptr;
-  cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
-  c->gen_allocs.push_back(p);
+  c->gen_allocs.push_back(p);      // released by pb200_gen_release() whatever happens next
+  if (cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   return p;
 }
 template <typename T>
 T *dalloc(pb200_ctx *c, size_t n) {
   T *p = nullptr;
   if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
-  cudaMemset(p, 0, n * sizeof(T));
   c->gen_allocs.push_back(p);
+  if (cudaMemset(p, 0, n * sizeof(T)) != cudaSuccess) return nullptr;
   return p;
 }
 
@@ -206,7 +206,8 @@ int pb200_gen_setup(pb200_ctx *c) {
     ok &= (G.ldw.xgc1 = upload(c, xgc[0])) != nullptr;
     ok &= (G.ldw.xgc2 = upload(c, xgc[1])) != nullptr;
   }
-  if (!ok) { pb200_gen_release(c); return PB200_ENOMEM; }
+  // the uploads are pageable copies on the legacy stream and the first stage kernels follow on c->stream
+  if (!ok || cudaDeviceSynchronize() != cudaSuccess) { pb200_gen_release(c); return PB200_ENOMEM; }
   c->gen_ready = true;
   return PB200_OK;
 }
@@ -310,14 +311,14 @@ extern "C" int pb200_ldw_enable(pb200_ctx *c, const pb200_ldw_config *l) {
   for (int q = 0; q < 3; q++) {
     if (c->ldw_flux[q]) cudaFree(c->ldw_flux[q]);
     if (cudaMalloc(&c->ldw_flux[q], n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "flux tables: out of device memory");
-    cudaMemset(c->ldw_flux[q], 0, n * sizeof(double));
+    if (cudaMemset(c->ldw_flux[q], 0, n * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ECUDA, "flux tables: cudaMemset failed");
   }
   if (c->ldw_dvds) cudaFree(c->ldw_dvds);
   if (cudaMalloc(&c->ldw_dvds, 2 * c->dev.sv * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "line force: out of device memory");
-  cudaMemset(c->ldw_dvds, 0, 2 * c->dev.sv * sizeof(double));
+  if (cudaMemset(c->ldw_dvds, 0, 2 * c->dev.sv * sizeof(double)) != cudaSuccess) return pb200_fail(PB200_ECUDA, "line force: cudaMemset failed");
   if (c->ldw_mask) cudaFree(c->ldw_mask);
   if (cudaMalloc(&c->ldw_mask, c->dev.sv * sizeof(unsigned long long)) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "flux mask: out of device memory");
-  cudaMemset(c->ldw_mask, 0, c->dev.sv * sizeof(unsigned long long));
+  if (cudaMemset(c->ldw_mask, 0, c->dev.sv * sizeof(unsigned long long)) != cudaSuccess) return pb200_fail(PB200_ECUDA, "flux mask: cudaMemset failed");
   return PB200_OK;
 }
 
@@ -333,8 +334,11 @@ extern "C" int pb200_ldw_set_mfit(pb200_ctx *c, int mpoints, const double *t_fit
   size_t n = (size_t)mpoints * c->dev.sv * sizeof(double);
   if (cudaMalloc(&c->ldw_tfit, mpoints * sizeof(double)) != cudaSuccess || cudaMalloc(&c->ldw_mfit, n) != cudaSuccess)
     return pb200_fail(PB200_ENOMEM, "force-multiplier fit: out of device memory");
-  cudaMemcpy(c->ldw_tfit, t_fit, mpoints * sizeof(double), cudaMemcpyHostToDevice);
-  cudaMemcpy(c->ldw_mfit, m_fit, n, cudaMemcpyHostToDevice);
+  // the tables are read by kernels on c->stream (a non-blocking stream): a pageable cudaMemcpy may
+  // return before its last DMA has landed, so wait for the device before handing them over
+  if (cudaMemcpy(c->ldw_tfit, t_fit, mpoints * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->ldw_mfit, m_fit, n, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+    return pb200_fail(PB200_ECUDA, "force-multiplier fit: upload failed");
   c->ldw_mpoints = mpoints;
   return PB200_OK;
 }
@@ -343,10 +347,12 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
   if (!c || !c->ldw_on || !fr || !ft) return pb200_fail(PB200_EINVAL, "pb200_ldw_set_fluxes: call pb200_ldw_enable first; flux_r / flux_t must not be NULL");
   cudaSetDevice(c->cfg.device);
   size_t n = (size_t)c->ldw.nangles * c->dev.sv * sizeof(double);
-  if (cudaMemcpy(c->ldw_flux[0], fr, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
-  if (cudaMemcpy(c->ldw_flux[1], ft, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
-  if (fp) { if (cudaMemcpy(c->ldw_flux[2], fp, n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA; }
-  else cudaMemset(c->ldw_flux[2], 0, n);
+  if (cudaMemcpy(c->ldw_flux[0], fr, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->ldw_flux[1], ft, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      (fp ? cudaMemcpy(c->ldw_flux[2], fp, n, cudaMemcpyHostToDevice) : cudaMemset(c->ldw_flux[2], 0, n)) != cudaSuccess)
+    return pb200_fail(PB200_ECUDA, "flux tables: upload failed");
+  // pageable copies may still be in flight on the legacy stream; the mask kernel runs on c->stream
+  if (cudaDeviceSynchronize() != cudaSuccess) return pb200_fail(PB200_ECUDA, "flux tables: upload failed");
   LdwDev w;
   memset(&w, 0, sizeof(w));
   w.nangles = c->ldw.nangles;
@@ -364,9 +370,10 @@ extern "C" int pb200_cooling_set_tables(pb200_ctx *c, const double *const tabs[7
   for (int q = 0; q < 7; q++) {
     if (c->cool_tab[q]) { cudaFree(c->cool_tab[q]); c->cool_tab[q] = nullptr; }
     if (!tabs || !tabs[q]) continue;
-    if (cudaMalloc(&c->cool_tab[q], n) != cudaSuccess) return PB200_ENOMEM;
-    if (cudaMemcpy(c->cool_tab[q], tabs[q], n, cudaMemcpyHostToDevice) != cudaSuccess) return PB200_ECUDA;
+    if (cudaMalloc(&c->cool_tab[q], n) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "cooling tables: out of device memory");
+    if (cudaMemcpy(c->cool_tab[q], tabs[q], n, cudaMemcpyHostToDevice) != cudaSuccess) return pb200_fail(PB200_ECUDA, "cooling tables: upload failed");
   }
+  if (cudaDeviceSynchronize() != cudaSuccess) return pb200_fail(PB200_ECUDA, "cooling tables: upload failed");
   return PB200_OK;
 }
 
