@@ -13,7 +13,7 @@
  * set_grid.c output), RECONSTRUCTION LINEAR with every LIMITER and CHAR_LIMITING NO/YES, or
  * PARABOLIC (order 4, CHAR_LIMITING NO) with the general-grid weights of ppm_coeffs.c,
  * SHOCK_FLATTENING NO / MULTID / ONED, ENTROPY_SWITCH NO / SELECTIVE / ALWAYS, NTRACER >= 0,
- * BODY_FORCE VECTOR / POTENTIAL, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock,
+ * BODY_FORCE VECTOR / POTENTIAL, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock / ausm+,
  * outflow / reflective / axisymmetric / eqtsymmetric / periodic boundaries plus the user-defined
  * boundaries of the line-driven-wind problems (cv_idl, cv_iso), LINE_DRIVEN_WIND (VGradCalc +
  * LineForce, power law or M(t) fit) and COOLING BLONDIN.
@@ -59,7 +59,7 @@ typedef struct gen_cfg {
   int limiter;              /* 0 DEFAULT, 1 FLAT, 2 MINMOD, 3 VANLEER, 4 MC, 5 VANALBADA, 6 OSPRE, 7 UMIST */
   int char_limiting;        /* CHAR_LIMITING */
   int flattening;           /* SHOCK_FLATTENING MULTID */
-  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc 4 roe 5 two_shock */
+  int rk, solver;           /* 1 EULER 2 RK2 3 RK3 ; 1 tvdlf 2 hll 3 hllc 4 roe 5 two_shock 6 ausm+ */
   int bc[6];                /* pluto.h:163-170; 8 userdef -> ldw_bc != 0 selects the built-in LDW fills */
   double gamma, small_dn, small_pr;
   const double *xl[3], *xr[3];   /* grid->xl, grid->xr incl. ghosts (np_tot each) */
@@ -788,6 +788,45 @@ static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int 
       *maxMach = MAXV(*maxMach, fabs(vRL[VXn]) / sqrt(a2));
       for (int nv = nf; nv--;) flux[nv] = 0.5 * (fL[nv] + fR[nv] - s->cmax[i] * (uR[nv] - uL[nv]));
       s->press[i] = 0.5 * (pL + pR);
+    } else if (c->solver == 6) {
+      /* HD/ausm.c:20-110 (AUSM+, EOS IDEAL only) */
+      const double alpha = 3.0 / 16.0, beta = 0.125, gm = c->gamma;
+      double aL = sqrt(gm * vL[PRS] / vL[RHO]);
+      double aR = sqrt(gm * vR[PRS] / vR[RHO]);
+      double asL2 = vL[VX1] * vL[VX1] + vL[VX2] * vL[VX2] + vL[VX3] * vL[VX3];
+      asL2 = aL * aL / (gm - 1.0) + 0.5 * asL2;
+      asL2 *= 2.0 * (gm - 1.0) / (gm + 1.0);
+      double asR2 = vR[VX1] * vR[VX1] + vR[VX2] * vR[VX2] + vR[VX3] * vR[VX3];
+      asR2 = aR * aR / (gm - 1.0) + 0.5 * asR2;
+      asR2 *= 2.0 * (gm - 1.0) / (gm + 1.0);
+      double asL = sqrt(asL2), asR = sqrt(asR2);
+      double atL = asL2 / MAXV(asL, fabs(vL[VXn]));
+      double atR = asR2 / MAXV(asR, fabs(vR[VXn]));
+      double a = MINV(atL, atR);
+      double ML = vL[VXn] / a, MpL, PpL, MR, MmR, PmR;
+      if (fabs(ML) >= 1.0) { MpL = 0.5 * (ML + fabs(ML)); PpL = ML > 0.0 ? 1.0 : 0.0; }
+      else {
+        MpL = 0.25 * (ML + 1.0) * (ML + 1.0) + beta * (ML * ML - 1.0) * (ML * ML - 1.0);
+        PpL = 0.25 * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) + alpha * ML * (ML * ML - 1.0) * (ML * ML - 1.0);
+      }
+      MR = vR[VXn] / a;
+      if (fabs(MR) >= 1.0) { MmR = 0.5 * (MR - fabs(MR)); PmR = MR > 0.0 ? 0.0 : 1.0; }
+      else {
+        MmR = -0.25 * (MR - 1.0) * (MR - 1.0) - beta * (MR * MR - 1.0) * (MR * MR - 1.0);
+        PmR = 0.25 * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) - alpha * MR * (MR * MR - 1.0) * (MR * MR - 1.0);
+      }
+      double m = MpL + MmR;
+      double mp = 0.5 * (m + fabs(m));
+      double mm = 0.5 * (m - fabs(m));
+      s->press[i] = PpL * vL[PRS] + PmR * vR[PRS];
+      flux[RHO] = a * (mp * uL[RHO] + mm * uR[RHO]);
+      flux[VX1] = a * (mp * uL[VX1] + mm * uR[VX1]);
+      flux[VX2] = a * (mp * uL[VX2] + mm * uR[VX2]);
+      flux[VX3] = a * (mp * uL[VX3] + mm * uR[VX3]);
+      flux[PRS] = a * (mp * (uL[PRS] + vL[PRS]) + mm * (uR[PRS] + vR[PRS]));
+      s->cmax[i] = MAXV(fabs(vL[VXn]) + aL, fabs(vR[VXn]) + aR);
+      *maxMach = MAXV(fabs(ML), *maxMach);
+      *maxMach = MAXV(fabs(MR), *maxMach);
     } else if (c->solver == 5) {
       /* HD/two_shock.c:28-243 (EOS IDEAL only; MAX_ITER 5, small_p = small_rho = 1e-9) */
       const double small_p = 1.e-9, small_rho = 1.e-9;

@@ -87,7 +87,7 @@ class GenOracle:
         c.flattening = int(bool(shock_flattening) and shock_flattening != "ONED")     # MULTID
         c.flatten_oned = int(shock_flattening == "ONED")
         c.rk = _o.RK[time_stepping]
-        c.solver = dict(_o.SOLVER, roe=4, two_shock=5)[solver]     # Roe_Solver, TwoShock_Solver: general-grid oracle only
+        c.solver = dict(_o.SOLVER, roe=4, two_shock=5, **{"ausm+": 6})[solver]     # Roe, TwoShock, AUSM+: general-grid oracle only
         for s in range(6):
             c.bc[s] = BCS[bcs[s]] if isinstance(bcs[s], str) else int(bcs[s])
         c.gamma = gamma

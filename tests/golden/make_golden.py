@@ -258,6 +258,7 @@ CASES6 = {
                           grid=[(0.8, 32, 3.0, "r", 1.03), (0.0, 40, TWO_PI), (0.0, 1, 1.0)], solver="roe",
                           bcs=("reflective", "outflow", "periodic", "periodic", "periodic", "periodic"),
                           params=CYL_PAR, maxsteps=8),
+    "ausm_sph2d": dict(cfg="sph2d", dims=2, grid=SPH_GRID2, solver="ausm+", bcs=SPH_BCS, maxsteps=8),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),
