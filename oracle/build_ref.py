@@ -113,6 +113,10 @@ CONFIGS = {
     "sph2d_pot": dict(local="sph", overrides={"BODY_FORCE": "POTENTIAL"}, states="plm"),
     "sph3d_pot": dict(local="sph", overrides={"DIMENSIONS": "3", "BODY_FORCE": "(VECTOR+POTENTIAL)"}, states="plm"),
     "pol2d_pot": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "BODY_FORCE": "POTENTIAL"}, states="plm"),
+    "sph2d_ppm_char": dict(local="sph", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3",
+                                                   "CHAR_LIMITING": "YES", "SHOCK_FLATTENING": "MULTID"}, states="ppm"),
+    "iso2d_ppm_char": dict(local="iso", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3",
+                                                   "CHAR_LIMITING": "YES"}, states="ppm"),
     "sph2d_ppm": dict(local="sph", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
     "sph3d_ppm": dict(local="sph", overrides={"DIMENSIONS": "3", "RECONSTRUCTION": "PARABOLIC",
                                               "TIME_STEPPING": "RK3"}, states="ppm"),

@@ -11,7 +11,7 @@
  * Scope: PHYSICS HD, EOS IDEAL or ISOTHERMAL, GEOMETRY CARTESIAN / CYLINDRICAL / POLAR / SPHERICAL,
  * DIMENSIONS 1-3, uniform or non-uniform grids (grid->xl/xr are inputs: the reference's own
  * set_grid.c output), RECONSTRUCTION LINEAR with every LIMITER and CHAR_LIMITING NO/YES, or
- * PARABOLIC (order 4, CHAR_LIMITING NO) with the general-grid weights of ppm_coeffs.c,
+ * PARABOLIC (order 4, CHAR_LIMITING NO/YES) with the general-grid weights of ppm_coeffs.c,
  * SHOCK_FLATTENING NO / MULTID / ONED, ENTROPY_SWITCH NO / SELECTIVE / ALWAYS, NTRACER >= 0,
  * BODY_FORCE VECTOR / POTENTIAL, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock / ausm+,
  * outflow / reflective / axisymmetric / eqtsymmetric / periodic boundaries plus the user-defined
@@ -83,7 +83,7 @@ typedef struct gen_cfg {
   int iso;                  /* 0: EOS IDEAL, 1: EOS ISOTHERMAL */
   double iso_cs;            /* g_isoSoundSpeed */
   int flatten_oned;         /* SHOCK_FLATTENING ONED (States/flatten.c); `flattening` above is MULTID */
-  int ppm;                  /* RECONSTRUCTION PARABOLIC (PPM_ORDER 4), CHAR_LIMITING NO */
+  int ppm;                  /* RECONSTRUCTION PARABOLIC (PPM_ORDER 4) */
   int uniform[3];           /* grid->uniform[d] (set_grid.c:67-72): one uniform patch along d */
   const double *bf_phi[4];  /* body_force bit 1 (POTENTIAL): BodyForcePotential at zone centres [0] and at the
                                x1 / x2 / x3 upper faces [1..3], [k][j][i] incl. ghosts */
@@ -754,6 +754,110 @@ static void states_ppm(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, i
   if (c->flatten_oned) flatten_oned(c, g, s, dir, beg, end);   /* ppm_states.c:229-231 */
 }
 
+/* PrimToChar (eigenv.c:575-616) with the left eigenvectors of PrimEigenvectors (eigenv.c:92-200) of zone v */
+static void prim_to_char(const gen_cfg *c, int nvar, int dir, const double *v, const double *dv, double *w) {
+  int VXn = 1 + dir, VXt = 1 + (dir + 1) % 3, VXb = 1 + (dir + 2) % 3;
+  double a2 = A2(c, v), cs = sqrt(a2), rhocs = v[RHO] * cs, rho_cs = v[RHO] / cs;
+  if (!c->iso) {
+    double L0p = 1.0 / rhocs, L2p = -1.0 / a2;
+    w[0] = -1.0 * dv[VXn] + L0p * dv[PRS];
+    w[1] = 1.0 * dv[VXn] + L0p * dv[PRS];
+    w[2] = dv[RHO] + L2p * dv[PRS];
+    w[3] = dv[VXt];
+    w[4] = dv[VXb];
+  } else {
+    double Lr = 1.0 / rho_cs;
+    w[0] = Lr * dv[RHO] + -1.0 * dv[VXn];
+    w[1] = Lr * dv[RHO] + 1.0 * dv[VXn];
+    w[2] = dv[VXt];
+    w[3] = dv[VXb];
+  }
+  for (int nv = NF(c); nv < nvar; nv++) w[nv] = dv[nv];
+}
+
+/* States/ppm_states.c:280-590 (CHAR_LIMITING YES, PPM_ORDER 4, PARABOLIC_LIM 1) */
+static void states_ppm_char(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end) {
+  int nvar = g->nvar, nf = NF(c);
+  int VXn = 1 + dir, VXt = 1 + (dir + 1) % 3, VXb = 1 + (dir + 2) % 3;
+  int ntot = g->tot[dir];
+  double (*dvF)[NVMAX] = calloc(ntot + 4, sizeof(*dvF));
+  double (*vppm4)[NVMAX] = calloc(ntot + 4, sizeof(*vppm4));
+  for (int i = beg - 2; i <= end + 1; i++) for (int nv = 0; nv < nvar; nv++) dvF[i][nv] = s->v[i + 1][nv] - s->v[i][nv];
+  for (int i = beg - 1; i <= end; i++) {
+    const double *wp = g->pwp[dir][i];
+    for (int nv = 0; nv < nvar; nv++)
+      vppm4[i][nv] = wp[0] * s->v[i - 1][nv] + wp[1] * s->v[i][nv] + wp[2] * s->v[i + 1][nv] + wp[3] * s->v[i + 2][nv];
+  }
+  for (int i = beg; i <= end; i++) {
+    const double *v = s->v[i];
+    if (c->flattening) {
+      if (s->flag[i] & FLAG_FLAT) {
+        for (int nv = 0; nv < nvar; nv++) s->vp[i][nv] = s->vm[i][nv] = v[nv];
+        continue;
+      } else if (s->flag[i] & FLAG_MINMOD) {
+        for (int nv = 0; nv < nvar; nv++) {
+          double dp = dvF[i][nv] * g->wp[dir][i];
+          double dm = dvF[i - 1][nv] * g->wm[dir][i];
+          double dv = MINMOD_LIMITER(dp, dm);
+          s->vp[i][nv] = v[nv] + dv * g->dp[dir][i];
+          s->vm[i][nv] = v[nv] - dv * g->dm[dir][i];
+        }
+        continue;
+      }
+    }
+    double dvp[NVMAX], dvm[NVMAX], dwp[NVMAX], dwm[NVMAX], dwp1[NVMAX], dwm1[NVMAX];
+    for (int nv = 0; nv < nvar; nv++) { dvp[nv] = vppm4[i][nv] - v[nv]; dvm[nv] = vppm4[i - 1][nv] - v[nv]; }
+    prim_to_char(c, nvar, dir, v, dvp, dwp);
+    prim_to_char(c, nvar, dir, v, dvm, dwm);
+    prim_to_char(c, nvar, dir, v, dvF[i - 1], dwm1);
+    prim_to_char(c, nvar, dir, v, dvF[i], dwp1);
+    for (int k = 0; k < nvar; k++) {
+      dwp[k] = MINMOD_LIMITER(dwp[k], dwp1[k]);
+      dwm[k] = MINMOD_LIMITER(dwm[k], -dwm1[k]);
+    }
+    double hp = g->php[dir][i], hm = g->phm[dir][i];
+    double cm = (hm + 1.0) / (hp - 1.0);
+    double cp = (hp + 1.0) / (hm - 1.0);
+    /* right eigenvectors (eigenv.c:140-178) */
+    double a2 = A2(c, v), cs = sqrt(a2), rhocs = v[RHO] * cs, rho_cs = v[RHO] / cs;
+    double R[NFLX][NFLX];
+    memset(R, 0, sizeof(R));
+    R[RHO][0] = 0.5 * rho_cs; R[VXn][0] = -0.5;
+    R[RHO][1] = 0.5 * rho_cs; R[VXn][1] = 0.5;
+    if (!c->iso) { R[PRS][0] = 0.5 * rhocs; R[PRS][1] = 0.5 * rhocs; R[RHO][2] = 1.0; R[VXt][3] = 1.0; R[VXb][4] = 1.0; }
+    else { R[VXt][2] = 1.0; R[VXb][3] = 1.0; }
+    for (int nv = 0; nv < nf; nv++) {
+      double dp = 0.0, dm = 0.0;
+      for (int k = 0; k < nf; k++) { dp += dwp[k] * R[nv][k]; dm += dwm[k] * R[nv][k]; }
+      dvp[nv] = dp;
+      dvm[nv] = dm;
+    }
+    for (int nv = nf; nv < nvar; nv++) { dvp[nv] = dwp[nv]; dvm[nv] = dwm[nv]; }
+    for (int nv = 0; nv < nvar; nv++) {
+      if (dvp[nv] * dvm[nv] >= 0.0) dvp[nv] = dvm[nv] = 0.0;
+      else {
+        if (fabs(dvp[nv]) >= cm * fabs(dvm[nv])) dvp[nv] = -cm * dvm[nv];
+        else if (fabs(dvm[nv]) >= cp * fabs(dvp[nv])) dvm[nv] = -cp * dvp[nv];
+      }
+      s->vp[i][nv] = v[nv] + dvp[nv];
+      s->vm[i][nv] = v[nv] + dvm[nv];
+    }
+    if (s->vp[i][RHO] < 0.0 || s->vm[i][RHO] < 0.0) {
+      dvp[RHO] = 0.5 * (MINMOD_LIMITER(dvF[i][RHO], dvF[i - 1][RHO]));
+      dvm[RHO] = -dvp[RHO];
+      s->vp[i][RHO] = v[RHO] + dvp[RHO];
+      s->vm[i][RHO] = v[RHO] + dvm[RHO];
+    }
+    if (!c->iso && (s->vp[i][PRS] < 0.0 || s->vm[i][PRS] < 0.0)) {
+      dvp[PRS] = 0.5 * (MINMOD_LIMITER(dvF[i][PRS], dvF[i - 1][PRS]));
+      dvm[PRS] = -dvp[PRS];
+      s->vp[i][PRS] = v[PRS] + dvp[PRS];
+      s->vm[i][PRS] = v[PRS] + dvm[PRS];
+    }
+  }
+  free(dvF); free(vppm4);
+}
+
 /* HD/hllc.c:28-178, HD/hll.c:30-96, HD/tvdlf.c:38-130, HD/hll_speed.c:76-90, HD/fluxes.c:36-47,
  * adv_flux.c:47-134 (scalars + entropy) */
 static void riemann(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int beg, int end, double *maxMach) {
@@ -1225,7 +1329,8 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
           for (int nv = 0; nv < nvar; nv++) s.v[n][nv] = Vc[nv * g->sv + base + n * st];
           s.flag[n] = flag[base + n * st];
         }
-        if (c->ppm) states_ppm(c, g, &s, dir, nbeg - 1, nend + 1);
+        if (c->ppm && c->char_limiting) states_ppm_char(c, g, &s, dir, nbeg - 1, nend + 1);
+        else if (c->ppm) states_ppm(c, g, &s, dir, nbeg - 1, nend + 1);
         else states(c, g, &s, dir, nbeg - 1, nend + 1);
         riemann(c, g, &s, dir, nbeg - 1, nend, maxMach);
         if (c->body_force & 2) {   /* TotalFlux(): flux[ENG] += flux[RHO] phi_p at the faces (rhs.c:171-179,525,581,621) */

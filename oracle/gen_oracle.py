@@ -63,7 +63,6 @@ class GenOracle:
                  shock_flattening=False, entropy_switch=False, ldw=None, eos="IDEAL",
                  iso_sound_speed=1.0, **_):
         assert reconstruction in ("LINEAR", "PARABOLIC")
-        assert not (reconstruction == "PARABOLIC" and char_limiting), "PPM of the general-grid oracle: CHAR_LIMITING NO"
         c = GenCfg()
         c.ndim = dimensions
         self._keep = []

@@ -259,6 +259,13 @@ CASES6 = {
                           bcs=("reflective", "outflow", "periodic", "periodic", "periodic", "periodic"),
                           params=CYL_PAR, maxsteps=8),
     "ausm_sph2d": dict(cfg="sph2d", dims=2, grid=SPH_GRID2, solver="ausm+", bcs=SPH_BCS, maxsteps=8),
+    "ppmg_sph2d_char_flat": dict(cfg="sph2d_ppm_char", dims=2, recon="PARABOLIC", rk="RK3", grid=SPH_GRID2, solver="hllc",
+                                 bcs=SPH_BCS, maxsteps=8, char_limiting=True, shock_flattening=True),
+    "ppmg_iso2d_char": dict(cfg="iso2d_ppm_char", dims=2, geometry="CARTESIAN", eos="ISOTHERMAL", body_force="none",
+                            recon="PARABOLIC", rk="RK3", char_limiting=True,
+                            grid=[(0.0, 40, 1.0), (0.0, 32, 1.0, "r", 1.02), (0.0, 1, 1.0)], solver="hll",
+                            bcs=("outflow", "reflective", "periodic", "periodic", "periodic", "periodic"),
+                            params=ISO_PAR, maxsteps=8, first_dt=1e-4),
     "iso_sph2d_flat_hll": dict(cfg="iso_sph2d", dims=2, geometry="SPHERICAL", eos="ISOTHERMAL",
                                char_limiting=True, shock_flattening=True, limiter="VANLEER_LIM",
                                grid=SPH_GRID2, solver="hll", bcs=SPH_BCS, params=ISO_PAR, maxsteps=10),
