@@ -29,7 +29,7 @@ class Cfg(C.Structure):
 
 def build(force=False):
     if LIB.exists() and not force and LIB.stat().st_mtime >= max((HERE / f).stat().st_mtime
-                                                                 for f in ("hd_oracle.c", "gen_oracle.c")):
+                                                                 for f in ("hd_oracle.c", "gen_oracle.c", "tables_oracle.c")):
         return LIB
     r = subprocess.run(["make", "-C", str(HERE), "-B"], capture_output=True, text=True)
     if r.returncode != 0:

@@ -1,4 +1,4 @@
-"""CPU: libplutob200.so loads and exports every symbol include/pluto_b200.h declares;
+"""CPU: libplutob200.so loads and exports every symbol include/*.h declares;
 host-only entry points behave like the reference's host logic.  No GPU compute here."""
 import ctypes as C
 import re
@@ -20,7 +20,7 @@ def lib():
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "pluto_b200.h").read_text()
+    text = "".join(p.read_text() for p in sorted((ROOT / "include").glob("*.h")))    # every header of the boundary
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(pb200_\w+)\s*\(", text)))
 
