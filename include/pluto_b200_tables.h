@@ -1,7 +1,8 @@
 /* pluto_b200_tables.h -- host-side ingestion of the SIROCCO tables of the line-driven-wind coupling.
  *
  * Replaces the readers of Src/LineDriven/line_connect.c:43-262 (read_sirocco_fluxes: the three
- * directional_flux_{r,theta,phi}.dat files and the force-multiplier fit M_UV_data.dat).  The
+ * directional_flux_{r,theta,phi}.dat files and the force-multiplier fit M_UV_data.dat) and :267-497
+ * (read_sirocco_heatcool: py_heatcool.dat, prefactors.dat).  The
  * reference walks ALL interior zones for every row of a file to find the zone whose centre matches
  * the row's coordinates (line_connect.c:132-150, :223-243): O(rows x zones), 2.7e11 coordinate tests
  * per file on the 1024 x 512 grid.  These functions keep the file formats, the parsing (the same
@@ -46,6 +47,15 @@ long pb200_read_flux_file(const char *path, const pb200_table_grid *g, int nangl
  * Returns the number of zones filled, < 0 on error as above. */
 long pb200_read_mfit_file(const char *path, const pb200_table_grid *g, int *mpoints, double *t_fit,
                           double *m_fit);
+
+/* read_sirocco_heatcool() (line_connect.c:267-497), the two files of a restarted run; one row per
+ * line, tolerance 1e-5, predicate fabs((x_row - x_zone)/x_row) < tol:
+ *   py_heatcool.dat -> xi[nx2_tot][nx1_tot] (floored at 1) and t_r[...] (floored at 1e3), line_connect.c:334-361;
+ *   prefactors.dat  -> pre[6][nx2_tot][nx1_tot] = comp_h, comp_c, xray_h, line_c, brem_c, xi_ion, :433-466.
+ * Zones no row matches keep what the arrays held (the reference presets the prefactors to 1).
+ * Return the number of zone assignments (the reference's icount), < 0 on error as above. */
+long pb200_read_heatcool_file(const char *path, const pb200_table_grid *g, double *xi, double *t_r);
+long pb200_read_prefactors_file(const char *path, const pb200_table_grid *g, double *pre);
 
 #ifdef __cplusplus
 }

@@ -91,3 +91,62 @@ long ref_read_mfit_file(const char *path, const tgrid *g, int *mpoints, double *
   fclose(fptr);
   return icount;
 }
+
+/* line_connect.c:318-361: py_heatcool.dat; xi, t_r [nx2_tot][nx1_tot] */
+long ref_read_heatcool_file(const char *path, const tgrid *g, double *xi_out, double *tr_out) {
+  FILE *fptr_hc = fopen(path, "r");
+  char aline[LINELENGTH];
+  int ii, jj, nwords, icount = 0;
+  double rcen, thetacen, vol, t_e, t_r, xi, ne, heat_xray, heat_comp, heat_lines, heat_ff, cool_comp, cool_lines, cool_ff, dens, n_h;
+  double tol = 1e-5;
+  if (fptr_hc == NULL) return -1;
+  if (fgets(aline, LINELENGTH, fptr_hc) == NULL) { fclose(fptr_hc); return -2; }
+  while (fgets(aline, LINELENGTH, fptr_hc) != NULL) {
+    nwords = sscanf(aline, "%d %d %le %le %le %le %le %le %le %le %le %le %le %le %le %le %le %le",
+                    &ii, &jj, &rcen, &thetacen, &vol, &t_e, &t_r, &xi, &ne, &heat_xray, &heat_comp, &heat_lines, &heat_ff,
+                    &cool_comp, &cool_lines, &cool_ff, &dens, &n_h);
+    if (nwords == 18) {
+      for (int j = g->jbeg; j <= g->jend; j++) for (int i = g->ibeg; i <= g->iend; i++) {
+        if (fabs(((rcen / g->unit_length) - g->x1[i]) / (rcen / g->unit_length)) < tol &&
+            fabs((thetacen - g->x2[j]) / thetacen) < tol) {
+          long o = (long)j * g->nx1_tot + i;
+          icount++;
+          xi_out[o] = xi;
+          tr_out[o] = t_r;
+          if (xi_out[o] < 1.0) xi_out[o] = 1.0;
+          if (tr_out[o] < 1.e3) tr_out[o] = 1.e3;
+        }
+      }
+    } else { fclose(fptr_hc); return -3; }
+  }
+  fclose(fptr_hc);
+  return icount;
+}
+
+/* line_connect.c:420-466: prefactors.dat; pre[6][nx2_tot][nx1_tot] = comp_h, comp_c, xray_h, line_c, brem_c, xi_ion */
+long ref_read_prefactors_file(const char *path, const tgrid *g, double *pre) {
+  FILE *fptr = fopen(path, "r");
+  char aline[LINELENGTH];
+  int ii, jj, nwords, icount = 0;
+  double rcen, thetacen, dens, comp_h_pre, comp_c_pre, xray_h_pre, brem_c_pre, line_c_pre, xi_ion_pre, tol = 1e-5;
+  long plane = (long)g->nx1_tot * g->nx2_tot;
+  if (fptr == NULL) return -1;
+  if (fgets(aline, LINELENGTH, fptr) == NULL) { fclose(fptr); return -2; }
+  while (fgets(aline, LINELENGTH, fptr) != NULL) {
+    nwords = sscanf(aline, "%d %le %d %le %le %le %le %le %le %le %le", &ii, &rcen, &jj, &thetacen, &dens, &comp_h_pre,
+                    &comp_c_pre, &xray_h_pre, &brem_c_pre, &line_c_pre, &xi_ion_pre);
+    if (nwords == 11) {
+      for (int j = g->jbeg; j <= g->jend; j++) for (int i = g->ibeg; i <= g->iend; i++) {
+        if (fabs(((rcen / g->unit_length) - g->x1[i]) / (rcen / g->unit_length)) < tol &&
+            fabs((thetacen - g->x2[j]) / thetacen) < tol) {
+          long o = (long)j * g->nx1_tot + i;
+          icount++;
+          pre[0 * plane + o] = comp_h_pre; pre[1 * plane + o] = comp_c_pre; pre[2 * plane + o] = xray_h_pre;
+          pre[3 * plane + o] = line_c_pre; pre[4 * plane + o] = brem_c_pre; pre[5 * plane + o] = xi_ion_pre;
+        }
+      }
+    } else { fclose(fptr); return -3; }
+  }
+  fclose(fptr);
+  return icount;
+}

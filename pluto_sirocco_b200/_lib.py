@@ -70,6 +70,8 @@ SYMBOLS = {
     "pb200_flux_file_nangles": (C.c_int, [C.c_char_p]),
     "pb200_read_flux_file": (C.c_long, [C.c_char_p, _P, C.c_int, _P]),
     "pb200_read_mfit_file": (C.c_long, [C.c_char_p, _P, C.POINTER(C.c_int), _P, _P]),
+    "pb200_read_heatcool_file": (C.c_long, [C.c_char_p, _P, _P, _P]),
+    "pb200_read_prefactors_file": (C.c_long, [C.c_char_p, _P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),

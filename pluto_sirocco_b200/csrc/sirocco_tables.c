@@ -8,17 +8,21 @@
 
 #define LINELENGTH 400      /* line_connect.c:24 */
 
-/* the reference's predicate (line_connect.c:133-134): fabs(1.0 - (xin / x[n])) < tol */
-static int matches(double xin, double xn, double tol) { return fabs(1.0 - (xin / xn)) < tol; }
+/* the reference's predicates: read_sirocco_fluxes (line_connect.c:133-134) fabs(1.0 - (xin / x[n])) < tol,
+ * read_sirocco_heatcool (line_connect.c:344-345,449-450) fabs((xin - x[n]) / xin) < tol */
+static int matches_mode(int mode, double xin, double xn, double tol) {
+  return mode == 0 ? fabs(1.0 - (xin / xn)) < tol : fabs((xin - xn) / xin) < tol;
+}
+#define matches(xin, xn, tol) matches_mode(a.mode, xin, xn, tol)
 
 /* All n in [beg, end] with matches(xin, x[n]), ascending, as [*lo, *hi] (empty: *lo > *hi).
  * x ascending and positive over [beg, end] (the zone centres of a radial / polar grid): the matching
  * zones are contiguous around the bisection point.  Anything else falls back to a linear scan,
  * which is still O(n1 + n2) per row instead of O(n1 n2). */
-typedef struct { int sorted; } axis_info;
+typedef struct { int sorted, mode; } axis_info;   /* mode: which predicate (0 fluxes, 1 heatcool) */
 
-static axis_info axis_check(const double *x, int beg, int end) {
-  axis_info a = {1};
+static axis_info axis_check(const double *x, int beg, int end, int mode) {
+  axis_info a = {1, mode};
   if (!(x[beg] > 0.0)) a.sorted = 0;
   for (int n = beg; n < end && a.sorted; n++) if (!(x[n + 1] > x[n])) a.sorted = 0;
   return a;
@@ -60,7 +64,7 @@ int pb200_flux_file_nangles(const char *path) {
 static long read_rows(FILE *f, const pb200_table_grid *g, int skip_third, int nval, int take_log10, double *out) {
   const double tol = 1e-6;
   const long plane = (long)g->nx1_tot * g->nx2_tot;
-  axis_info a1 = axis_check(g->x1, g->ibeg, g->iend), a2 = axis_check(g->x2, g->jbeg, g->jend);
+  axis_info a1 = axis_check(g->x1, g->ibeg, g->iend, 0), a2 = axis_check(g->x2, g->jbeg, g->jend, 0);
   long ii, jj, icount = 0;
   double x1in, x2in, temp;
   int I[MAXM], J[MAXM];
@@ -115,6 +119,67 @@ long pb200_read_mfit_file(const char *path, const pb200_table_grid *g, int *mpoi
     t_fit[m] = log10(temp);
   }
   long n = read_rows(f, g, 0, *mpoints, 1, m_fit);
+  fclose(f);
+  return n;
+}
+
+/* ---- read_sirocco_heatcool(): py_heatcool.dat and prefactors.dat (line_connect.c:318-497) ----
+ * one row per LINE (fgets + sscanf), tolerance 1e-5, every matching zone takes the row's values */
+static long read_lines(FILE *f, const pb200_table_grid *g, int which, double *a0, double *a1) {
+  const double tol = 1e-5;
+  const long plane = (long)g->nx1_tot * g->nx2_tot;
+  char aline[LINELENGTH];
+  axis_info a1i = axis_check(g->x1, g->ibeg, g->iend, 1), a2i = axis_check(g->x2, g->jbeg, g->jend, 1);
+  long icount = 0;
+  int I[MAXM], J[MAXM];
+  while (fgets(aline, LINELENGTH, f) != NULL) {
+    int ii, jj, nwords;
+    double rcen, thetacen, v[16];
+    if (which == 0) {   /* py_heatcool.dat: i j rcen thetacen vol t_e t_r xi ne heat*4 cool*3 dens n_h */
+      nwords = sscanf(aline, "%d %d %le %le %le %le %le %le %le %le %le %le %le %le %le %le %le %le", &ii, &jj, &rcen, &thetacen,
+                      &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8], &v[9], &v[10], &v[11], &v[12], &v[13]);
+      if (nwords != 18) return -3;
+    } else {            /* prefactors.dat: i rcen j thetacen dens comp_h comp_c xray_h brem_c line_c xi_ion */
+      nwords = sscanf(aline, "%d %le %d %le %le %le %le %le %le %le %le", &ii, &rcen, &jj, &thetacen,
+                      &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+      if (nwords != 11) return -3;
+    }
+    int nI = find_matches(g->x1, g->ibeg, g->iend, a1i, rcen / g->unit_length, tol, I, MAXM);
+    int nJ = find_matches(g->x2, g->jbeg, g->jend, a2i, thetacen, tol, J, MAXM);
+    if (nI > MAXM || nJ > MAXM) return -3;
+    for (int q = 0; q < nJ; q++) for (int p = 0; p < nI; p++) {
+      long o = (long)J[q] * g->nx1_tot + I[p];
+      icount++;
+      if (which == 0) {
+        double xi = v[3], t_r = v[2];                       /* line_connect.c:353-356 */
+        a0[o] = xi; a1[o] = t_r;
+        if (a0[o] < 1.0) a0[o] = 1.0;
+        if (a1[o] < 1.e3) a1[o] = 1.e3;
+      } else {                                              /* line_connect.c:458-463: comp_h, comp_c, xray_h, line_c, brem_c, xi_ion */
+        a0[0 * plane + o] = v[1]; a0[1 * plane + o] = v[2]; a0[2 * plane + o] = v[3];
+        a0[3 * plane + o] = v[5]; a0[4 * plane + o] = v[4]; a0[5 * plane + o] = v[6];
+      }
+    }
+  }
+  return icount;
+}
+
+long pb200_read_heatcool_file(const char *path, const pb200_table_grid *g, double *xi, double *t_r) {
+  FILE *f = fopen(path, "r");
+  char aline[LINELENGTH];
+  if (!f) return -1;
+  if (fgets(aline, LINELENGTH, f) == NULL) { fclose(f); return -2; }
+  long n = read_lines(f, g, 0, xi, t_r);
+  fclose(f);
+  return n;
+}
+
+long pb200_read_prefactors_file(const char *path, const pb200_table_grid *g, double *pre) {
+  FILE *f = fopen(path, "r");
+  char aline[LINELENGTH];
+  if (!f) return -1;
+  if (fgets(aline, LINELENGTH, f) == NULL) { fclose(f); return -2; }
+  long n = read_lines(f, g, 1, pre, NULL);
   fclose(f);
   return n;
 }

@@ -42,6 +42,11 @@ def readers(tmp_path_factory):
     O.ref_read_flux_file.argtypes = [C.c_char_p, C.POINTER(TGrid), C.POINTER(C.c_int), C.c_void_p]
     O.ref_read_mfit_file.restype = C.c_long
     O.ref_read_mfit_file.argtypes = [C.c_char_p, C.POINTER(TGrid), C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    for L_, pre in ((P, "pb200_"), (O, "ref_")):
+        f = getattr(L_, pre + "read_heatcool_file")
+        f.restype, f.argtypes = C.c_long, [C.c_char_p, C.POINTER(TGrid), C.c_void_p, C.c_void_p]
+        f = getattr(L_, pre + "read_prefactors_file")
+        f.restype, f.argtypes = C.c_long, [C.c_char_p, C.POINTER(TGrid), C.c_void_p]
     return P, O
 
 
@@ -208,3 +213,58 @@ def test_dropin_reads_the_tables_through_the_wrapped_reader(tmp_path):
     assert "libplutob200 table readers" in logs["1"] and "libplutob200 table readers" not in logs["0"]
     for fast in ("0", "1"):
         assert logs[fast].count("Read 36 fluxes for 1728 cells") == 3, logs[fast][-2000:]
+
+
+def _write_heatcool(path, x1, x2, ng, rng, extra=()):
+    """py_heatcool.dat as read by read_sirocco_heatcool() (line_connect.c:334-341): a header line, then
+    i j rcen thetacen vol t_e t_r xi ne heat_xray heat_comp heat_lines heat_ff cool_comp cool_lines cool_ff rho n_h"""
+    UL = LDW_UNITS["length"]
+    rows = []
+    for j in range(ng, len(x2) - ng):
+        for i in range(ng, len(x1) - ng):
+            v = rng.uniform(0.1, 10.0, 14)
+            v[2] = 10.0 ** rng.uniform(2.0, 6.0)       # t_r: some below the 1e3 floor
+            v[3] = 10.0 ** rng.uniform(-1.0, 4.0)      # xi: some below the floor of 1
+            rows.append("%d %d %.17e %.17e %s" % (i - ng, j - ng, x1[i] * UL, x2[j], " ".join("%.17e" % q for q in v)))
+    rng.shuffle(rows)
+    Path(path).write_text("# header\n" + "\n".join(list(rows) + list(extra)) + "\n")
+
+
+def test_heatcool_and_prefactor_files(readers, tmp_path):
+    g, x1, x2, ng = make_grid(22, 16)
+    P, O = readers
+    rng = np.random.default_rng(11)
+    UL = LDW_UNITS["length"]
+    junk = " ".join("%.17e" % q for q in rng.uniform(1.0, 2.0, 14))
+    extra = ["0 0 %.17e %.17e %s" % (x1[0] * UL, x2[0], junk),                                   # ghost zone
+             "5 5 %.17e %.17e %s" % (x1[ng + 5] * UL * (1 + 6e-6), x2[ng + 5] * (1 - 6e-6), junk),   # inside 1e-5
+             "6 5 %.17e %.17e %s" % (x1[ng + 6] * UL * (1 + 3e-5), x2[ng + 5], junk)]            # outside
+    _write_heatcool(tmp_path / "py_heatcool.dat", x1, x2, ng, rng, extra)
+    shape = (g.nx2_tot, g.nx1_tot)
+    xa, ta, xb, tb = (np.full(shape, -7.0) for _ in range(4))
+    path = str(tmp_path / "py_heatcool.dat").encode()
+    na = P.pb200_read_heatcool_file(path, C.byref(g), xa.ctypes.data, ta.ctypes.data)
+    nb = O.ref_read_heatcool_file(path, C.byref(g), xb.ctypes.data, tb.ctypes.data)
+    assert na == nb == 22 * 16 + 1
+    assert np.array_equal(xa, xb) and np.array_equal(ta, tb)
+    inner = (slice(g.jbeg, g.jend + 1), slice(g.ibeg, g.iend + 1))
+    assert xa[inner].min() >= 1.0 and ta[inner].min() >= 1.0e3 and (xa[inner] == 1.0).any() and (ta[inner] == 1.0e3).any()
+    # prefactors.dat (line_connect.c:433-437): header, then i rcen j thetacen dens comp_h comp_c xray_h brem_c line_c xi_ion
+    rows = []
+    for j in range(ng, len(x2) - ng):
+        for i in range(ng, len(x1) - ng):
+            rows.append("%d %.17e %d %.17e %s" % (i - ng, x1[i] * UL, j - ng, x2[j],
+                                                  " ".join("%.17e" % q for q in rng.uniform(0.5, 2.0, 7))))
+    rng.shuffle(rows)
+    rows = rows[:-5]                                   # five zones without a row keep their preset value
+    (tmp_path / "prefactors.dat").write_text("# header\n" + "\n".join(rows) + "\n")
+    pa, pb = np.ones((6,) + shape), np.ones((6,) + shape)
+    path = str(tmp_path / "prefactors.dat").encode()
+    na = P.pb200_read_prefactors_file(path, C.byref(g), pa.ctypes.data)
+    nb = O.ref_read_prefactors_file(path, C.byref(g), pb.ctypes.data)
+    assert na == nb == 22 * 16 - 5 and np.array_equal(pa, pb)
+    # malformed line -> the reference exits; both report -3
+    (tmp_path / "bad.dat").write_text("# header\n1 2 3.0\n")
+    assert P.pb200_read_prefactors_file(str(tmp_path / "bad.dat").encode(), C.byref(g), pa.ctypes.data) == -3
+    assert O.ref_read_prefactors_file(str(tmp_path / "bad.dat").encode(), C.byref(g), pb.ctypes.data) == -3
+    assert P.pb200_read_heatcool_file(str(tmp_path / "none.dat").encode(), C.byref(g), xa.ctypes.data, ta.ctypes.data) == -1
