@@ -24,3 +24,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:gen_
 ncu -i $OUT/full_ldw.ncu-rep --page raw --csv > $OUT/full_ldw_raw.csv 2>/dev/null
 rm -f $OUT/full_ldw.ncu-rep $OUT/full.ncu-rep
 ls -la $OUT
+# the line-driven-wind drop-in once more with the library's table readers behind read_sirocco_fluxes
+PB200_FAST_TABLES=1 timeout 600 python -m pytest tests/test_dropin_gpu.py -q -k line_driven > $OUT/pytest_fast_tables.log 2>&1
+tail -2 $OUT/pytest_fast_tables.log
