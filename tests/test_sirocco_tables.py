@@ -268,3 +268,25 @@ def test_heatcool_and_prefactor_files(readers, tmp_path):
     assert P.pb200_read_prefactors_file(str(tmp_path / "bad.dat").encode(), C.byref(g), pa.ctypes.data) == -3
     assert O.ref_read_prefactors_file(str(tmp_path / "bad.dat").encode(), C.byref(g), pb.ctypes.data) == -3
     assert P.pb200_read_heatcool_file(str(tmp_path / "none.dat").encode(), C.byref(g), xa.ctypes.data, ta.ctypes.data) == -1
+
+
+def test_python_front_end_round_trip(tmp_path):
+    """pluto_sirocco_b200.tables: the files written from the synthetic tables come back as the arrays
+    Hydro.set_ldw() is handed in the parity tests (interior zones; ghost zones zero)."""
+    from pluto_sirocco_b200 import tables
+    g, x1, x2, ng = make_grid(20, 14)
+    fr, ft, fp = ldw_flux_tables(x1, x2)
+    write_ldw_flux_files(tmp_path, x1, x2, ng, fr, ft, fp)
+    got = tables.read_flux_files(tmp_path, x1, x2, ng, LDW_UNITS["length"])
+    inner = (slice(None), slice(None), slice(ng, -ng), slice(ng, -ng))
+    for a, b in zip(got, (fr, ft, fp)):
+        assert a.shape == b.shape and np.array_equal(a[inner], b[inner])
+        assert not a[:, :, :ng].any() and not a[:, :, :, :ng].any()
+    (tmp_path / "directional_flux_phi.dat").unlink()
+    assert tables.read_flux_files(tmp_path, x1, x2, ng, LDW_UNITS["length"])[2] is None
+    t, M, lt, lM = ldw_mfit_tables(x1, x2)
+    write_ldw_mfit_file(tmp_path, x1, x2, ng, t, M)
+    tf, mf = tables.read_mfit_file(tmp_path, x1, x2, ng, LDW_UNITS["length"])
+    assert np.array_equal(tf, lt) and np.array_equal(mf[inner], lM[inner])
+    with pytest.raises(tables.TableError):
+        tables.read_mfit_file(tmp_path / "nowhere", x1, x2, ng, LDW_UNITS["length"])
