@@ -56,6 +56,11 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     def cc(unit):
         name, src, defs = unit
         obj = objdir / (name + ".o")
+        # per-unit stamp: an unchanged unit (same sources, headers and flags) is not recompiled
+        ustamp = objdir / (name + ".sha256")
+        udig = hashlib.sha256((dig + " ".join(defs) + src).encode()).hexdigest()
+        if obj.exists() and not force and ustamp.exists() and ustamp.read_text() == udig:
+            return obj
         if src.endswith(".c"):
             cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=c99", "-fPIC", "-I", str(PKG.parent / "include"),
                    "-c", str(CSRC / src), "-o", str(obj)]
@@ -69,6 +74,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if verbose:
             print(" ".join(cmd))
             print(r.stderr)
+        ustamp.write_text(udig)
         return obj
 
     import concurrent.futures as cf

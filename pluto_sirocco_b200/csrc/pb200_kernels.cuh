@@ -322,10 +322,13 @@ __host__ __device__ constexpr int ring_slots() {
 __host__ __device__ inline int ring_nq(int nv, bool first, int comb, bool cdt_in) {
   return nv + (first ? 0 : nv) + ((first && comb) ? nv : 0) + (cdt_in ? 1 : 0);
 }
+// The V rows stay in the ring while the x1 sweep of the fused kernel still needs them (ring_slots);
+// the zone-aligned quantities (acc, V^n, cdt of the zone an iteration finishes) are consumed by the
+// iteration they land for and live in a second, short ring of DEPTH + 1 slots.
 template <bool FUSEX, int NV, int RECON, int BXT = BX>
 __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
-  return ((size_t)ring_slots<FUSEX, RECON>() * nq * BXT + (FUSEX ? (size_t)(2 * NV + 2) * BXT : 0)) *
-         sizeof(double);
+  return ((size_t)ring_slots<FUSEX, RECON>() * NV * BXT + (size_t)(DEPTH + 1) * (nq - NV) * BXT +
+          (FUSEX ? (size_t)(2 * NV + 2) * BXT : 0)) * sizeof(double);
 }
 
 enum BcType { BC_NONE = 0, BC_OUTFLOW = 1, BC_REFLECTIVE = 2, BC_AXISYMMETRIC = 3,
@@ -334,8 +337,16 @@ enum BcType { BC_NONE = 0, BC_OUTFLOW = 1, BC_REFLECTIVE = 2, BC_AXISYMMETRIC = 
 // BXT: threads per block.  The fused x1+x2 kernel loses 2*XH threads per block to the x1 halo, so
 // on a 512-wide grid 128-thread blocks need 5 blocks (20 warps) per row where 192-thread blocks
 // need 3 (18 warps): the launcher picks the width that runs the fewest warps.
+// PB_REG128: run the fused x1+x2 kernel at 16 warps per SM (128 registers per thread, block widths
+// 256 / 128 / 64) instead of 12 (168 registers, widths 192 / 160 / 128)
+#ifndef PB_REG128
+#define PB_REG128 0
+#endif
+__host__ __device__ constexpr int fused_minblk(bool fusex, int bxt) {
+  return (PB_REG128 && fusex) ? 512 / bxt : (bxt == 128 ? PB_MINBLK : 2);
+}
 template <int DIR, bool FUSEX, bool LAST, int NV, int RECON, int SOLVER, int LIM, int BF, int BXT = BX>
-__global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(Dev d, SweepArgs a, int chunk) {
+__global__ void __launch_bounds__(BXT, fused_minblk(FUSEX, BXT)) sweep_fused(Dev d, SweepArgs a, int chunk) {
   static_assert(DIR == 1 || DIR == 2, "marching sweeps are x2/x3");
   constexpr int LEAD = recon_lead<RECON>();
   constexpr int XH = recon_xhalo<RECON>();
@@ -381,16 +392,20 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   const bool cdt_in = cdt_on && !FIRST;
   const int qA = NV, q0 = qA + (FIRST ? 0 : NV), qC = q0 + (use_v0 ? NV : 0);
   const int nq = qC + (cdt_in ? 1 : 0);
-  const int slot_sz = nq * BXT;
-  double *ring = smem + t;                              // [RING][nq][BXT]
-  double *exm = smem + RING * slot_sz;                  // FUSEX: [NV][BXT] right states (vm)
+  constexpr int RING2 = DEPTH + 1;
+  constexpr int slot_sz = NV * BXT;
+  const int z_sz = (nq - NV) * BXT;
+  double *ring = smem + t;                              // [RING][NV][BXT]   V rows
+  double *ring2 = ring + RING * slot_sz - qA * BXT;     // [RING2][nq-NV][BXT] zone-aligned quantities, indexed from qA
+  double *exm = smem + RING * slot_sz + RING2 * z_sz;   // FUSEX: [NV][BXT] right states (vm)
   double *exf = exm + NV * BXT;                          //        [NV+2][BXT] fluxes, prs, cmax
 
   const int n0 = cb - LEAD;  // first iteration: consumes V row cb, so the ring holds rows >= cb
   // iteration m consumes V row m+LEAD and the stored quantities of zone m-1
-  auto issue = [&](int m, int s) {
+  auto issue = [&](int m, int s, int s2) {
     if (m <= ce + 1) {
       double *slot = ring + s * slot_sz;
+      double *zslot = ring2 + s2 * z_sz;
       const long oV = base + (long)(m + LEAD) * st;
 #pragma unroll
       for (int c = 0; c < NV; c++) cp_async8(slot + c * BXT, a.V + gvar<DIR>(c) * d.sv + oV);
@@ -399,18 +414,19 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
         const long oz = base + (long)z * st;
         if (!FIRST) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) cp_async8(slot + (qA + v) * BXT, a.acc + v * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(zslot + (qA + v) * BXT, a.acc + v * d.sv + oz);
         }
         if (use_v0) {
 #pragma unroll
-          for (int v = 0; v < NV; v++) cp_async8(slot + (q0 + v) * BXT, a.V0 + v * d.sv + oz);
+          for (int v = 0; v < NV; v++) cp_async8(zslot + (q0 + v) * BXT, a.V0 + v * d.sv + oz);
         }
-        if (cdt_in) cp_async8(slot + qC * BXT, a.cdt + oz);
+        if (cdt_in) cp_async8(zslot + qC * BXT, a.cdt + oz);
       }
     }
     cp_async_commit();
   };
   auto wrap = [](int s) { return s >= RING ? s - RING : s; };
+  auto wrap2 = [](int s) { return s >= RING2 ? s - RING2 : s; };
 
   Ratio mach;
   mach.init();
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   Face<NV> Fm;                     // face n-3/2
 
 #pragma unroll
-  for (int g = 0; g < DEPTH; g++) issue(n0 + g, g);
+  for (int g = 0; g < DEPTH; g++) issue(n0 + g, g, g);
   {
     double b0[NV];
     load_zone<DIR, NV>(a.V, base + (long)(n0 - 1) * st, d.sv, b0);
@@ -447,7 +463,7 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
   double rho_c = v0[iRHO], phi_m = 0.0;
   const int jt = (DIR == 1) ? 0 : d.beg[1] + tr, kt = (DIR == 1) ? d.beg[2] + tr : 0;
 
-  int sc = 0;  // ring slot consumed by this iteration
+  int sc = 0, sc2 = 0;  // ring slots consumed by this iteration
 #pragma unroll MARCH_UNROLL
   for (int n = n0; n <= ce + 1; n++) {
     // ---- data of this iteration has landed in the ring; refill the slot DEPTH ahead ----
@@ -457,6 +473,7 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
       *w = -*w;
     }
     const double *slot = ring + sc * slot_sz;
+    const double *zslot = ring2 + sc2 * z_sz;
     double vin[NV];
 #pragma unroll
     for (int c = 0; c < NV; c++) vin[c] = slot[c * BXT];
@@ -466,16 +483,16 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
     if (fin) {
       if (!FIRST) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) U[v] = slot[(qA + v) * BXT];
+        for (int v = 0; v < NV; v++) U[v] = zslot[(qA + v) * BXT];
       }
       if (use_v0) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) v0z[v] = slot[(q0 + v) * BXT];
+        for (int v = 0; v < NV; v++) v0z[v] = zslot[(q0 + v) * BXT];
       }
-      if (cdt_in) cin = slot[qC * BXT];
+      if (cdt_in) cin = zslot[qC * BXT];
     }
     const double inv_dl = __ldg(inv_dx + max(z, 0));
-    issue(n + DEPTH, wrap(sc + DEPTH));
+    issue(n + DEPTH, wrap(sc + DEPTH), wrap2(sc2 + DEPTH));
 
     // ---- reconstruct zone n along DIR ----
     double vp[NV], vm[NV];
@@ -652,6 +669,7 @@ __global__ void __launch_bounds__(BXT, BXT == 128 ? PB_MINBLK : 2) sweep_fused(D
       else v0[nv] = vin[nv];
     }
     sc = wrap(sc + 1);
+    sc2 = wrap2(sc2 + 1);
   }
   cp_async_wait<0>();
   block_reduce_t<BXT>(cdt_max, mach.value(), nfail, nan, a.stage == 1 && LAST, a.red);

@@ -2,6 +2,7 @@
 // pair: compile with -DPB_NV=<5|6|7> -DPB_BF=<0|1>.  Solver / reconstruction / limiter are
 // run-time options of the reference ([Solver] in pluto.ini) or cheap to carry as template
 // parameters, so every combination is instantiated here.
+#include <cstdlib>
 #include <unordered_map>
 
 #include "pb200_internal.h"
@@ -64,35 +65,42 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
       // 128, 160 and 192 threads so that the FEWEST WARPS run (512 zones, PLM: 2x192 + 1x160 = 17
       // warps instead of 5x128 = 20); one launch per block width, at its x1 offset.
       const int h2 = 2 * recon_xhalo<RECON>();
-      const int W[3] = {192, 160, 128};
-      int best[3] = {0, 0, (nx + 128 - h2 - 1) / (128 - h2)}, bestw = best[2] * 4;
-      for (int n0 = 0; n0 * (192 - h2) < nx + (192 - h2); n0++)
-        for (int n1 = 0; n0 * (192 - h2) + n1 * (160 - h2) < nx + (160 - h2); n1++) {
-          int rest = nx - n0 * (192 - h2) - n1 * (160 - h2);
-          int n2 = rest > 0 ? (rest + 128 - h2 - 1) / (128 - h2) : 0;
-          int w = n0 * 6 + n1 * 5 + n2 * 4;
+#if PB_REG128
+      constexpr int W0 = 256, W1 = 128, W2 = 64;
+#else
+      constexpr int W0 = 192, W1 = 160, W2 = 128;
+#endif
+      const int W[3] = {W0, W1, W2};
+      int best[3] = {0, 0, (nx + W2 - h2 - 1) / (W2 - h2)}, bestw = best[2] * (W2 / 32);
+      for (int n0 = 0; n0 * (W0 - h2) < nx + (W0 - h2); n0++)
+        for (int n1 = 0; n0 * (W0 - h2) + n1 * (W1 - h2) < nx + (W1 - h2); n1++) {
+          int rest = nx - n0 * (W0 - h2) - n1 * (W1 - h2);
+          int n2 = rest > 0 ? (rest + W2 - h2 - 1) / (W2 - h2) : 0;
+          int w = n0 * (W0 / 32) + n1 * (W1 / 32) + n2 * (W2 / 32);
           if (w < bestw || (w == bestw && n0 + n1 + n2 < best[0] + best[1] + best[2])) {
             bestw = w; best[0] = n0; best[1] = n1; best[2] = n2;
           }
         }
+      // experiment hook: PB200_SMEM_PAD=<bytes> inflates the dynamic shared memory (lowers occupancy)
+      static const size_t smem_pad = getenv("PB200_SMEM_PAD") ? (size_t)atol(getenv("PB200_SMEM_PAD")) : 0;
       SweepArgs b = a;
       b.i0 = 0;
       for (int g = 0; g < 3; g++) {
         if (!best[g]) continue;
         int chunk;
-        const int nchunk = chunks(best[g], W[g] == 128 ? 3 : 2, chunk);
+        const int nchunk = chunks(best[g], fused_minblk(true, W[g]), chunk);
         dim3 grid(best[g], ntr, nchunk);
 #define PB_LAUNCH_FUSED(LASTF, WIDTH)                                                        \
   {                                                                                          \
     auto k = sweep_fused<1, true, LASTF, NV, RECON, SOLVER, LIM, BF, WIDTH>;                 \
-    size_t shm = sweep_smem_bytes<true, NV, RECON, WIDTH>(nq);                               \
+    size_t shm = sweep_smem_bytes<true, NV, RECON, WIDTH>(nq) + smem_pad;                    \
     set_smem(k, shm);                                                                        \
     k<<<grid, WIDTH, shm, c->stream>>>(D, b, chunk);                                         \
   }
         if (last) {
-          if (W[g] == 192) PB_LAUNCH_FUSED(true, 192) else if (W[g] == 160) PB_LAUNCH_FUSED(true, 160) else PB_LAUNCH_FUSED(true, 128)
+          if (g == 0) PB_LAUNCH_FUSED(true, W0) else if (g == 1) PB_LAUNCH_FUSED(true, W1) else PB_LAUNCH_FUSED(true, W2)
         } else {
-          if (W[g] == 192) PB_LAUNCH_FUSED(false, 192) else if (W[g] == 160) PB_LAUNCH_FUSED(false, 160) else PB_LAUNCH_FUSED(false, 128)
+          if (g == 0) PB_LAUNCH_FUSED(false, W0) else if (g == 1) PB_LAUNCH_FUSED(false, W1) else PB_LAUNCH_FUSED(false, W2)
         }
 #undef PB_LAUNCH_FUSED
         b.i0 += best[g] * (W[g] - h2);
@@ -113,28 +121,56 @@ static void launch_dir(pb200_ctx *c, int dir, const SweepArgs &a) {
   c->launches++;
 }
 
+// PB_HOT_ONLY (kernel experiments, never the shipped library): only NVAR 5 without body force,
+// LINEAR + HLLC + LIMITER DEFAULT is instantiated, so that a variant library builds in seconds
+#ifdef PB_HOT_ONLY
+#include <cstdio>
+#include <cstdlib>
+#define PB_HOT_REFUSE() do { fprintf(stderr, "PB_HOT_ONLY build: configuration not instantiated\n"); abort(); } while (0)
+#endif
+
 template <int NV, int RECON, int SOLVER, int BF>
 static void launch_lim(pb200_ctx *c, int dir, const SweepArgs &a) {
+#ifdef PB_HOT_ONLY
+  if (c->cfg.limiter != PB200_LIM_DEFAULT) PB_HOT_REFUSE();
+  launch_dir<NV, RECON, SOLVER, LIM_DEFAULT, BF>(c, dir, a);
+#else
   // LIMITER DEFAULT is compiled in; any other choice takes the run-time limiter switch
   if (RECON != RECON_LINEAR || c->cfg.limiter == PB200_LIM_DEFAULT) launch_dir<NV, RECON, SOLVER, LIM_DEFAULT, BF>(c, dir, a);
   else launch_dir<NV, RECON, SOLVER, LIM_RT, BF>(c, dir, a);
+#endif
 }
 
 template <int NV, int RECON, int BF>
 static void launch_solver(pb200_ctx *c, int dir, const SweepArgs &a) {
+#ifdef PB_HOT_ONLY
+  if (c->cfg.solver != PB200_HLLC) PB_HOT_REFUSE();
+  launch_lim<NV, RECON, SOLVER_HLLC, BF>(c, dir, a);
+#else
   switch (c->cfg.solver) {
     case PB200_TVDLF: launch_lim<NV, RECON, SOLVER_TVDLF, BF>(c, dir, a); break;
     case PB200_HLL: launch_lim<NV, RECON, SOLVER_HLL, BF>(c, dir, a); break;
     default: launch_lim<NV, RECON, SOLVER_HLLC, BF>(c, dir, a); break;
   }
+#endif
 }
 
 #define PB_CAT2(a, b, c, d) a##b##c##d
 #define PB_CAT(a, b, c, d) PB_CAT2(a, b, c, d)
 void PB_CAT(pb200_launch_sweep_nv, PB_NV, _bf, PB_BF)(pb200_ctx *c, int dir, const SweepArgs &a) {
+#ifdef PB_HOT_ONLY
+#if PB_NV == 5 && PB_BF == 0
+  if (c->cfg.reconstruction != PB200_LINEAR && c->cfg.reconstruction != PB200_PARABOLIC) PB_HOT_REFUSE();
+  if (c->cfg.reconstruction == PB200_PARABOLIC) launch_solver<PB_NV, RECON_PARABOLIC, PB_BF>(c, dir, a);
+  else launch_solver<PB_NV, RECON_LINEAR, PB_BF>(c, dir, a);
+#else
+  PB_HOT_REFUSE();
+#endif
+#else
   switch (c->cfg.reconstruction) {
     case PB200_FLAT: launch_solver<PB_NV, RECON_FLAT, PB_BF>(c, dir, a); break;
     case PB200_PARABOLIC: launch_solver<PB_NV, RECON_PARABOLIC, PB_BF>(c, dir, a); break;
     default: launch_solver<PB_NV, RECON_LINEAR, PB_BF>(c, dir, a); break;
   }
+#endif
 }
