@@ -265,6 +265,37 @@ int  pb200_kernel_times(const pb200_ctx *ctx, int max, float *ms, int *dir, int 
 /* CUDA stream (cudaStream_t as void*) all kernels of ctx are launched on */
 void *pb200_stream(pb200_ctx *ctx);
 
+/* ---- several GPUs of one box from ONE host thread -------------------------------------------
+ * Replaces the reference's parallel layer for this path when the host stays the reference's own C
+ * driver: the domain decomposition of Src/Parallel/al_decompose.c:40,125-158 becomes a 1-D slab split
+ * along the outermost active direction, the ghost-zone exchange inside Boundary()
+ * (Src/boundary.c:139-158 -> Src/Parallel/al_exchange_dim.c:64-90) one grouped ncclSend/ncclRecv batch
+ * of packed edge planes per RK stage on a communication stream per device (overlapped with the fused
+ * x1+x2 kernel), and the MPI_Allreduce(MAX) of Src/main.c:288,547 one ncclAllReduce(ncclMax) per step.
+ * cfg describes the GLOBAL grid; devices = NULL means devices 0..ngpus-1.  All host arrays handed to
+ * the pb200_multi_* calls are GLOBAL arrays in the reference's layout; results are bit-identical to
+ * the single-GPU path.  NCCL (libnccl.so.2) is loaded at run time when ngpus > 1.  Cartesian
+ * fast path only (the 2-D general-path problems are single-GPU: replicas only). */
+typedef struct pb200_multi pb200_multi;
+int  pb200_multi_create(const pb200_config *cfg, int ngpus, const int *devices, pb200_multi **out);
+void pb200_multi_destroy(pb200_multi *m);
+int  pb200_multi_ngpus(const pb200_multi *m);
+/* the per-device context of a rank (for per-rank calls such as pb200_set_profiling) and the planes
+ * [offset, offset + count) of the split direction it owns (interior index) */
+pb200_ctx *pb200_multi_ctx(pb200_multi *m, int rank);
+int  pb200_multi_slab(const pb200_multi *m, int rank, int *offset, int *count);
+int  pb200_multi_set_grid(pb200_multi *m, int dir, const double *xl, const double *xr, const double *dx);
+int  pb200_multi_set_body_force_vector(pb200_multi *m, int comp, const double *tab, long n,
+                                       long si, long sj, long sk);
+int  pb200_multi_set_body_force_potential(pb200_multi *m, int where, const double *tab, long n,
+                                          long si, long sj, long sk);
+int  pb200_multi_upload_vc(pb200_multi *m, const double *vc_host);
+int  pb200_multi_download_vc(pb200_multi *m, double *vc_host);
+int  pb200_multi_advance_step(pb200_multi *m, double dt, pb200_step_info *info);
+int  pb200_multi_advance_step_host(pb200_multi *m, double *vc_host, double dt, pb200_step_info *info);
+int  pb200_multi_integrate(pb200_multi *m, int nsteps, double tstop, double cfl, double cfl_max_var,
+                           double first_dt, double *t, double *dt, pb200_step_info *last);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,20 @@ SYMBOLS = {
     "pb200_set_profiling": (C.c_int, [_P, C.c_int]),
     "pb200_kernel_times": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int)]),
+    # several GPUs from one host thread (csrc/pb200_multi.cu)
+    "pb200_multi_create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(C.c_int), C.POINTER(_P)]),
+    "pb200_multi_destroy": (None, [_P]),
+    "pb200_multi_ngpus": (C.c_int, [_P]),
+    "pb200_multi_ctx": (_P, [_P, C.c_int]),
+    "pb200_multi_slab": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pb200_multi_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pb200_multi_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
+    "pb200_multi_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
+    "pb200_multi_upload_vc": (C.c_int, [_P, _P]),
+    "pb200_multi_download_vc": (C.c_int, [_P, _P]),
+    "pb200_multi_advance_step": (C.c_int, [_P, _D, C.POINTER(StepInfo)]),
+    "pb200_multi_advance_step_host": (C.c_int, [_P, _P, _D, C.POINTER(StepInfo)]),
+    "pb200_multi_integrate": (C.c_int, [_P, C.c_int, _D, _D, _D, _D, _PD, _PD, C.POINTER(StepInfo)]),
 }
 
 _lib = None

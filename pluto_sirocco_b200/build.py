@@ -15,14 +15,14 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libplutob200.so"
-SOURCES = ["pb200.cu", "pb200_sweeps.cu", "pb200_gen.cu", "sirocco_tables.c"]
+SOURCES = ["pb200.cu", "pb200_sweeps.cu", "pb200_gen.cu", "pb200_multi.cu", "sirocco_tables.c"]
 HEADERS = ["hd_physics.cuh", "pb200_kernels.cuh", "gen_kernels.cuh", "pb200_internal.h", "../../include/pluto_b200.h",
            "../../include/pluto_b200_tables.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 # translation units: (object name, source, extra defines).  pb200_sweeps.cu is compiled once per
 # (NVAR, BODY_FORCE) pair so that the kernel instantiations build in parallel.
-UNITS = [("pb200", "pb200.cu", []), ("pb200_gen", "pb200_gen.cu", []),
+UNITS = [("pb200", "pb200.cu", []), ("pb200_gen", "pb200_gen.cu", []), ("pb200_multi", "pb200_multi.cu", []),
          ("sirocco_tables", "sirocco_tables.c", [])] + [   # host-only C (table readers): compiled with gcc
     ("sweeps_nv%d_bf%d" % (nv, bf), "pb200_sweeps.cu", ["-DPB_NV=%d" % nv, "-DPB_BF=%d" % bf])
     for nv in (5, 6, 7) for bf in (0, 1)]
@@ -81,7 +81,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     with cf.ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(cc, UNITS))
     r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)]
-                       + [str(o) for o in objs], capture_output=True, text=True)
+                       + [str(o) for o in objs] + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     stamp.write_text(dig)

@@ -412,12 +412,14 @@ extern "C" double *pb200_stage_array(pb200_ctx *c, int stage) {
 
 extern "C" int pb200_stage_download(pb200_ctx *c, int stage, double *h) {
   if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
+  CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpyAsync(h, c->V[c->stage_in[stage]], c->vbytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PB200_OK;
 }
 extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
   if (!c || !h || !c->in_step || stage < 1 || stage > c->nstages) return fail(PB200_EINVAL, "bad argument");
+  CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpyAsync(c->V[c->stage_in[stage]], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PB200_OK;
@@ -555,7 +557,21 @@ extern "C" int pb200_advance_step(pb200_ctx *c, double dt, pb200_step_info *info
 // soon as stage 1 of slab s is done (stage 3 on slab s-2), and every finished slab travels back while the next ones are still
 // being computed - upload, compute and download overlap, so the call costs about one PCIe
 // direction instead of two plus the compute.  Same kernels, same arithmetic as pb200_advance_step.
+static int advance_step_host_pipelined_body(pb200_ctx *c, double *h, double dt, pb200_step_info *info);
 static int advance_step_host_pipelined(pb200_ctx *c, double *h, double dt, pb200_step_info *info) {
+  int rc = advance_step_host_pipelined_body(c, h, dt, info);
+  if (rc) {
+    // asynchronous copies may still touch the caller's buffer: drain all three streams first
+    const std::string msg = g_err;
+    if (c->h2d) cudaStreamSynchronize(c->h2d);
+    if (c->d2h) cudaStreamSynchronize(c->d2h);
+    cudaStreamSynchronize(c->stream);
+    c->in_step = false;
+    g_err = msg;
+  }
+  return rc;
+}
+static int advance_step_host_pipelined_body(pb200_ctx *c, double *h, double dt, pb200_step_info *info) {
   const Dev &D = c->dev;
   const int nk = D.end[2] - D.beg[2] + 1, ng = c->cfg.nghost;
   int per = c->host_pipeline;

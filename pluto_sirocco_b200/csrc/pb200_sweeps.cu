@@ -19,9 +19,12 @@ using namespace pb;
 // ---- sweeps ------------------------------------------------------------------------------
 template <typename K>
 static void set_smem(K k, size_t shm) {
-  // high-water mark of the opt-in dynamic shared memory per kernel
-  static std::unordered_map<const void *, size_t> cur;
-  size_t &c = cur[(const void *)k];
+  // high-water mark of the opt-in dynamic shared memory per (device, kernel): the attribute is
+  // per device, and a process may drive several (pb200_multi)
+  static std::unordered_map<const void *, size_t> cur[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t &c = cur[dev & 63][(const void *)k];
   if (shm > c) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); c = shm; }
 }
 

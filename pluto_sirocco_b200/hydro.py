@@ -178,6 +178,105 @@ def make_grid(spec, nghost):
 # --------------------------------------------------------------------------------------
 #  Hydro: one block of the grid resident on one B200
 # --------------------------------------------------------------------------------------
+class MultiHydro:
+    """Front end of pb200_multi_* (csrc/pb200_multi.cu): one host thread, N GPUs, slab split along the
+    outermost active direction, NCCL exchange inside the library.  Arrays are GLOBAL d->Vc arrays.
+    devices may repeat an ordinal (ranks sharing a GPU: the slab logic on a single-GPU box)."""
+
+    def __init__(self, ngpus, *, dimensions, nx, devices=None, xbeg=(0., 0., 0.), xend=(1., 1., 1.), gamma=5. / 3.,
+                 reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
+                 bcs=("outflow",) * 6, ntracer=0, nghost=None, small_density=1e-12, small_pressure=1e-12,
+                 body_force=0):
+        lib = L.load()
+        cfg = L.Config()
+        lib.pb200_config_default(C.byref(cfg))
+        cfg.dimensions = dimensions
+        for d in range(3):
+            cfg.nx[d] = int(nx[d]) if d < dimensions else 1
+            cfg.xbeg[d] = float(xbeg[d])
+            cfg.xend[d] = float(xend[d])
+        cfg.reconstruction = _RECON[reconstruction]
+        cfg.nghost = nghost if nghost is not None else (3 if reconstruction == "PARABOLIC" else 2)
+        cfg.ntracer = ntracer
+        cfg.limiter = L.LIMITERS[limiter]
+        cfg.time_stepping = _TSTEP[time_stepping]
+        cfg.solver = _SOLVERS[solver]
+        for s in range(6):
+            cfg.bc[s] = L.BC[bcs[s]] if isinstance(bcs[s], str) else int(bcs[s])
+        cfg.gamma, cfg.small_density, cfg.small_pressure = gamma, small_density, small_pressure
+        cfg.body_force = int(body_force)
+        self.cfg, self._lib, self.ngpus = cfg, lib, int(ngpus)
+        devs = None if devices is None else (C.c_int * self.ngpus)(*devices)
+        h = C.c_void_p()
+        L.check(lib.pb200_multi_create(C.byref(cfg), self.ngpus, devs, C.byref(h)))
+        self._h = h
+        ng = cfg.nghost
+        self.nghost, self.dimensions = ng, dimensions
+        self.tot = tuple(cfg.nx[d] + 2 * ng if d < dimensions else 1 for d in range(3))
+        self.nvar = 5 + ntracer
+        self.shape = (self.nvar, self.tot[2], self.tot[1], self.tot[0])
+        self.beg = tuple(ng if d < dimensions else 0 for d in range(3))
+        self.nx = tuple(cfg.nx[d] for d in range(3))
+        self.last = L.StepInfo()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    interior = lambda self: Hydro.interior(self)
+    _bf_table = lambda self, tab: Hydro._bf_table(self, tab)
+
+    def set_body_force_vector(self, comp, tab):
+        a, si, sj, sk = self._bf_table(tab)
+        L.check(self._lib.pb200_multi_set_body_force_vector(self._h, int(comp), a.ctypes.data_as(C.c_void_p), a.size, si, sj, sk))
+
+    def set_body_force_potential(self, where, tab):
+        a, si, sj, sk = self._bf_table(tab)
+        L.check(self._lib.pb200_multi_set_body_force_potential(self._h, int(where), a.ctypes.data_as(C.c_void_p), a.size, si, sj, sk))
+
+    def upload(self, vc):
+        vc = np.ascontiguousarray(vc, dtype=np.float64)
+        assert vc.shape == self.shape
+        L.check(self._lib.pb200_multi_upload_vc(self._h, vc.ctypes.data_as(C.c_void_p)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros(self.shape, dtype=np.float64)
+        L.check(self._lib.pb200_multi_download_vc(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_interior(self, v_int):
+        vc = np.ones(self.shape)
+        vc[1:4] = 0.0
+        vc[self.interior()] = v_int
+        self.upload(vc)
+
+    def get_interior(self):
+        return self.download()[self.interior()].copy()
+
+    def advance_step(self, dt):
+        L.check(self._lib.pb200_multi_advance_step(self._h, float(dt), C.byref(self.last)))
+        return self.last
+
+    def advance_step_host(self, vc, dt):
+        assert vc.flags["C_CONTIGUOUS"] and vc.shape == self.shape and vc.dtype == np.float64
+        L.check(self._lib.pb200_multi_advance_step_host(self._h, vc.ctypes.data_as(C.c_void_p), float(dt), C.byref(self.last)))
+        return self.last
+
+    def integrate(self, nsteps, *, t, dt, tstop, cfl, cfl_max_var, first_dt):
+        tt, dd = C.c_double(t), C.c_double(dt)
+        n = L.check(self._lib.pb200_multi_integrate(self._h, int(nsteps), float(tstop), float(cfl), float(cfl_max_var),
+                                                    float(first_dt), C.byref(tt), C.byref(dd), C.byref(self.last)))
+        return n, tt.value, dd.value
+
+
 class Hydro:
     """Device-resident d->Vc plus the AdvanceStep family of calls."""
 
