@@ -184,6 +184,13 @@ int  pb200_ldw_set_mfit(pb200_ctx *ctx, int mpoints, const double *t_fit, const 
 int  pb200_cooling_set_tables(pb200_ctx *ctx, const double *const tabs[7]);
 int  pb200_split_source(pb200_ctx *ctx, double dt, double g_time);
 
+/* INTERNAL_BOUNDARY YES: zones flagged FLAG_INTERNAL_BOUNDARY in d->flag keep a zero right-hand side in
+ * every sweep (InternalBoundaryReset(), Src/int_bound_reset.c:17-40, called from Src/MHD/rhs.c:416-417; the
+ * default INTERNAL_BOUNDARY_CFL YES leaves the signal speeds alone).  mask[NX3_TOT][NX2_TOT][NX1_TOT]: non-zero
+ * = flagged; NULL = none.  The reference clears the flags every step (Src/main.c:258-261) and user code sets
+ * them again inside Boundary(); call this whenever they change. */
+int  pb200_set_internal_boundary_mask(pb200_ctx *ctx, const unsigned char *mask);
+
 /* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
 int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);
 int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);
@@ -255,6 +262,12 @@ int  pb200_step_end(pb200_ctx *ctx, pb200_step_info *info);
  * the correctness path for user plug-ins, not a CPU implementation of the update. */
 int  pb200_stage_download(pb200_ctx *ctx, int stage, double *vc_host);
 int  pb200_stage_upload(pb200_ctx *ctx, int stage, const double *vc_host);
+/* Same mode, stages > 1: conservative states the caller's Boundary() wrote into d->Uc (user code that changes
+ * interior zones converts them itself with PrimToCons3D on 1-zone boxes, e.g. cv_idl/init.c:272-275; zones it
+ * changes WITHOUT converting keep the previous stage's d->Uc, and so they do here).  zone[n] = offsets
+ * k*NX2_TOT*NX1_TOT + j*NX1_TOT + i, u[n][NVAR] in the reference's variable order.  The general path keeps
+ * d->Uc on the device between stages; the Cartesian path keeps none (cons(V) is recomputed) and ignores this. */
+int  pb200_stage_patch_u(pb200_ctx *ctx, long n, const long *zone, const double *u);
 int  pb200_nstages(const pb200_ctx *ctx);
 /* Measurement aid (the reference's FUNCTION_CLOCK_PROFILE, Src/pluto.h:414-419, rk_step.c:
  * 51-55): record CUDA events around every sweep kernel of the following steps;

@@ -43,8 +43,9 @@ def build(cfg: str, force: bool = False) -> Path:
     # read_sirocco_fluxes is wrapped too: the shim can hand the table files to the library's readers
     # (include/pluto_b200_tables.h, exported by libplutob200.so)
     objs = [str(o) for o in sorted((wd / "obj").glob("*.o")) if o.name != "rk_step.o"]
+    ldw = (wd / "obj" / "line_connect.o").exists()      # read_sirocco_heatcool exists in line-driven-wind builds only
     cmd = ["gcc"] + objs + [str(obj),
-           "-Wl,--wrap=WriteData,--wrap=Analysis,--wrap=SplitSource,--wrap=read_sirocco_fluxes", "-L%s" % lib.parent, "-lplutob200",
+           "-Wl,--wrap=WriteData,--wrap=Analysis,--wrap=SplitSource,--wrap=read_sirocco_fluxes" + (",--wrap=read_sirocco_heatcool" if ldw else ""), "-L%s" % lib.parent, "-lplutob200",
            "-Wl,-rpath,$ORIGIN/../../../pluto_sirocco_b200/lib", "-lm", "-o", str(exe)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:

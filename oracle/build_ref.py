@@ -142,8 +142,17 @@ CONFIGS = {
     # an arbitrary, time-dependent UserDefBoundary() (oracle/problems/jet): the shim's host-boundary mode
     "jet2d": dict(local="jet", overrides={}, states="plm"),
     "jet2d_ppm": dict(local="jet", overrides={"RECONSTRUCTION": "PARABOLIC", "TIME_STEPPING": "RK3"}, states="ppm"),
+    # INTERNAL_BOUNDARY YES with FLAG_INTERNAL_BOUNDARY zones (oracle/problems/tunnel): InternalBoundaryReset()
+    "tunnel2d": dict(local="tunnel", overrides={}, states="plm"),
+    "tunnel3d_ppm": dict(local="tunnel", overrides={"DIMENSIONS": "3", "RECONSTRUCTION": "PARABOLIC",
+                                                    "TIME_STEPPING": "RK3"}, states="ppm"),
     # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
     "kh3d": dict(local="kh", overrides={}, states="plm"),
+    # the SAME reference sources compiled with FMA contraction (-mfma -ffp-contract=fast): a second, equally
+    # valid rounding of the reference.  Long free-running comparisons use |ref_fma - ref| as the yardstick of
+    # how far round-off differences are amplified by the flow itself (tests/test_dropin_gpu.py).
+    "rt3d_vec_fma": dict(local="rt", overrides={}, states="plm", cflags=["-mfma", "-ffp-contract=fast"]),
+    "kh3d_fma": dict(local="kh", overrides={}, states="plm", cflags=["-mfma", "-ffp-contract=fast"]),
 }
 
 
@@ -200,7 +209,7 @@ def build(cfg_name: str, force: bool = False, verbose: bool = False) -> Path:
     def cc(name: str):
         src = find_source(name, paths)
         obj = wd / "obj" / (name + ".o")
-        cmd = ["gcc"] + CFLAGS + incs + [str(src), "-o", str(obj)]
+        cmd = ["gcc"] + CFLAGS + cfg.get("cflags", []) + incs + [str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("gcc failed for %s:\n%s" % (src, r.stderr[-4000:]))

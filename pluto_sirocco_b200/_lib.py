@@ -72,6 +72,7 @@ SYMBOLS = {
     "pb200_read_mfit_file": (C.c_long, [C.c_char_p, _P, C.POINTER(C.c_int), _P, _P]),
     "pb200_read_heatcool_file": (C.c_long, [C.c_char_p, _P, _P, _P]),
     "pb200_read_prefactors_file": (C.c_long, [C.c_char_p, _P, _P]),
+    "pb200_set_internal_boundary_mask": (C.c_int, [_P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),
@@ -91,6 +92,7 @@ SYMBOLS = {
     "pb200_stage_finish": (C.c_int, [_P, C.c_int]),
     "pb200_stage_download": (C.c_int, [_P, C.c_int, _P]),
     "pb200_stage_upload": (C.c_int, [_P, C.c_int, _P]),
+    "pb200_stage_patch_u": (C.c_int, [_P, C.c_long, _P, _P]),
     "pb200_step_end": (C.c_int, [_P, C.POINTER(StepInfo)]),
     "pb200_nstages": (C.c_int, [_P]),
     "pb200_stream": (_P, [_P]),

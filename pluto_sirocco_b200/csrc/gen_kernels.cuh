@@ -70,6 +70,7 @@ struct GenArgs {
   unsigned long long *red;
   double w0, wc;
   int comb, stage, dir;
+  const unsigned char *ibmask;   // FLAG_INTERNAL_BOUNDARY zones: rhs = 0 (int_bound_reset.c:34-35), null: none
 };
 
 PB_D double gen_A(const GenDev &g, int dir, int k, int j, int i) {
@@ -775,6 +776,10 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
     }
     if (dir == 0) rhs[1] = rn; else if (dir == 1) rhs[2] = rn; else rhs[3] = rn;
     (void)gn;
+    if (a.ibmask && a.ibmask[o]) {   // InternalBoundaryReset(), rhs.c:416-417
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) rhs[nv] = 0.0;
+    }
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] += rhs[nv];
     // GetInverse_dl (set_geometry.c:303-375) and C_dt (update_stage.c:303-322)

@@ -99,6 +99,10 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->gdev = nullptr;
   c->ldw_on = false;
   c->cur_stage = 0;
+  c->d_ibmask = nullptr;
+  c->stage_uploaded = false;
+  c->d_iblist = nullptr;
+  c->ib_n = 0;
   for (int q = 0; q < 3; q++) c->ldw_flux[q] = nullptr;
   c->ldw_dvds = nullptr;
   c->ldw_mask = nullptr;
@@ -204,6 +208,8 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   if (c->ldw_tfit) cudaFree(c->ldw_tfit);
   if (c->ldw_mfit) cudaFree(c->ldw_mfit);
   for (int q = 0; q < 7; q++) if (c->cool_tab[q]) cudaFree(c->cool_tab[q]);
+  if (c->d_ibmask) cudaFree(c->d_ibmask);
+  if (c->d_iblist) cudaFree(c->d_iblist);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
   if (c->acc) cudaFree(c->acc);
   if (c->cdt) cudaFree(c->cdt);
@@ -366,6 +372,78 @@ __global__ void reset_red(unsigned long long *red, double *dt, double dtval) {
   *dt = dtval;
 }
 
+// ---- FLAG_INTERNAL_BOUNDARY --------------------------------------------------------------
+// InternalBoundaryReset() (Src/int_bound_reset.c:17-40, called at the end of RightHandSide(),
+// Src/MHD/rhs.c:416-417) zeroes the right-hand side of flagged zones in every sweep (fluxes AND
+// sources; with the default INTERNAL_BOUNDARY_CFL YES the signal speeds stay), i.e. a flagged zone
+// leaves a stage as  prim(w0 U0 + wc cons(V_in))  while its neighbours still see its face fluxes.
+// Fast path: the sweeps run unchanged and ib_fix rewrites the flagged zones afterwards (they are
+// few; no cost for the hot kernels when there are none).  General path: gen_rhs zeroes its rhs.
+// The frozen states are computed BEFORE the last sweep of the stage (which may overwrite V^n in place:
+// stage 2 of RK2 writes into the array that holds V^n) and scattered after it.
+template <int NV>
+__global__ void ib_gather(Dev d, const long *list, long n, const double *Vin, const double *V0, double *buf,
+                          int comb, double w0, double wc) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long o = list[t];
+  double v[NV], v0[NV], U[NV], vn[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) { v[nv] = Vin[nv * d.sv + o]; v0[nv] = V0[nv * d.sv + o]; }
+  prim2cons<NV>(v, U, d.gas);
+  int nfail = 0, nan = 0;
+  combine_c2p<NV>(U, v0, d.gas, comb, w0, wc, vn, nfail, nan, true);
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) buf[nv * n + t] = vn[nv];
+}
+__global__ void ib_scatter(Dev d, const long *list, long n, const double *buf, double *Vout, int nvar) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long o = list[t];
+  for (int nv = 0; nv < nvar; nv++) Vout[nv * d.sv + o] = buf[nv * n + t];
+}
+
+extern "C" int pb200_set_internal_boundary_mask(pb200_ctx *c, const unsigned char *mask) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->d_iblist) { cudaFree(c->d_iblist); c->d_iblist = nullptr; }
+  c->ib_n = 0;
+  if (!mask) {
+    if (c->d_ibmask) { cudaFree(c->d_ibmask); c->d_ibmask = nullptr; }
+    return PB200_OK;
+  }
+  const Dev &D = c->dev;
+  std::vector<long> list;
+  for (int k = D.beg[2]; k <= D.end[2]; k++)
+    for (int j = D.beg[1]; j <= D.end[1]; j++)
+      for (int i = D.beg[0]; i <= D.end[0]; i++) {
+        const long o = (long)k * D.sk + (long)j * D.sj + i;
+        if (mask[o]) list.push_back(o);
+      }
+  if (!c->d_ibmask) CK(cudaMalloc(&c->d_ibmask, c->nzone));
+  CK(cudaMemcpyAsync(c->d_ibmask, mask, c->nzone, cudaMemcpyHostToDevice, c->stream));
+  if (!list.empty()) {
+    CK(cudaMalloc(&c->d_iblist, list.size() * (sizeof(long) + c->nvar * sizeof(double))));   // list + the gather buffer
+    CK(cudaMemcpyAsync(c->d_iblist, list.data(), list.size() * sizeof(long), cudaMemcpyHostToDevice, c->stream));
+    c->ib_n = (long)list.size();
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return PB200_OK;
+}
+
+static void internal_boundary_fix(pb200_ctx *c, const SweepArgs &a, bool after) {
+  if (!c->ib_n || c->gen) return;
+  const int nb = (int)((c->ib_n + 127) / 128);
+  double *buf = (double *)(c->d_iblist + c->ib_n);
+  if (after) ib_scatter<<<nb, 128, 0, c->stream>>>(c->dev, c->d_iblist, c->ib_n, buf, a.Vout, c->nvar);
+  else switch (c->nvar) {
+    case 5: ib_gather<5><<<nb, 128, 0, c->stream>>>(c->dev, c->d_iblist, c->ib_n, a.V, a.V0, buf, a.comb, a.w0, a.wc); break;
+    case 6: ib_gather<6><<<nb, 128, 0, c->stream>>>(c->dev, c->d_iblist, c->ib_n, a.V, a.V0, buf, a.comb, a.w0, a.wc); break;
+    default: ib_gather<7><<<nb, 128, 0, c->stream>>>(c->dev, c->d_iblist, c->ib_n, a.V, a.V0, buf, a.comb, a.w0, a.wc); break;
+  }
+  c->launches++;
+}
+
 extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   if (!c) return fail(PB200_EINVAL, "null ctx");
   if (!(dt > 0.0)) return fail(PB200_EINVAL, "dt must be > 0");
@@ -422,7 +500,14 @@ extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaMemcpyAsync(c->V[c->stage_in[stage]], h, c->vbytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->stage_uploaded = true;
   return PB200_OK;
+}
+
+extern "C" int pb200_stage_patch_u(pb200_ctx *c, long n, const long *zone, const double *u) {
+  if (!c || !c->in_step || n < 0 || (n > 0 && (!zone || !u))) return fail(PB200_EINVAL, "bad argument");
+  CK(cudaSetDevice(c->cfg.device));
+  return pb200_gen_patch_u(c, n, zone, u);     // the Cartesian path keeps no d->Uc: cons(V) is recomputed
 }
 
 // A stage in three parts so that a slab-decomposed caller can overlap the halo exchange of the
@@ -484,9 +569,11 @@ extern "C" int pb200_stage_finish(pb200_ctx *c, int stage) {
     return rc;      // pb200_gen_stage set the error text
   }
   const Dev &D = c->dev;
+  internal_boundary_fix(c, a, false);             // InternalBoundaryReset(): flagged zones keep w0 U0 + wc U ...
   if (D.ndim == 1) launch_sweep(c, 0, a);
   else if (D.ndim == 2) launch_sweep(c, 1, a);    // x1 + x2 (reads the x2 ghosts)
   else launch_sweep(c, 2, a);                     // x3
+  internal_boundary_fix(c, a, true);              // ... written over what the sweeps left in those zones
   CK(cudaGetLastError());
   return PB200_OK;
 }
@@ -657,7 +744,7 @@ extern "C" int pb200_advance_step_host(pb200_ctx *c, double *vc_host, double dt,
                        c->cfg.bc[4] != PB200_BC_NEIGHBOUR && c->cfg.bc[5] != PB200_BC_NEIGHBOUR &&
                        c->cfg.bc[4] != PB200_BC_USERDEF && c->cfg.bc[5] != PB200_BC_USERDEF;
     if (!c->gen && D.ndim == 3 && c->host_pipeline >= 2 * c->cfg.nghost &&
-        nk >= 3 * c->host_pipeline && x3_ok && !c->profiling)
+        nk >= 3 * c->host_pipeline && x3_ok && !c->profiling && !c->ib_n)
       return advance_step_host_pipelined(c, vc_host, dt, info);
   }
   CK(cudaMemcpyAsync(c->V[c->cur], vc_host, c->vbytes, cudaMemcpyHostToDevice, c->stream));

@@ -414,6 +414,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   a.cdt = c->gcdt; a.flag = c->gflag; a.shock = c->gshock;
   a.dt = c->d_dt; a.red = c->d_red;
   a.w0 = w0; a.wc = wc; a.comb = comb; a.stage = stage; a.dir = 0;
+  a.ibmask = c->ib_n ? c->d_ibmask : nullptr;
   const int T = 128;
   auto blocks = [&](const GenBox &b) {
     long n = (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
@@ -439,6 +440,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
     c->launches++;
   }
+  c->stage_uploaded = false;
   for (int dir = 0; dir < D.ndim; dir++) {
     a.dir = dir;
     GenBox bs = dom, bf = dom;
@@ -455,6 +457,31 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   }
   gen_finish<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
   c->launches++;
+}
+
+// Host-boundary mode, stages > 1: user code that changes interior zones inside Boundary() converts them
+// itself (PrimToCons3D on 1-zone boxes, e.g. cv_idl/init.c:272-275) - d->Uc of every other zone, converted
+// or not, stays what the previous stage left.  The caller hands over exactly the zones its Boundary() wrote.
+__global__ void gen_patch_u(double *U, long sv, int nvar, long n, const long *zone, const double *u) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  for (int nv = 0; nv < nvar; nv++) U[nv * sv + zone[t]] = u[t * nvar + nv];
+}
+int pb200_gen_patch_u(pb200_ctx *c, long n, const long *zone, const double *u) {
+  if (!c->gen || !c->gen_ready || n <= 0) return PB200_OK;
+  long *dz = nullptr;
+  double *du = nullptr;
+  if (cudaMalloc(&dz, n * sizeof(long)) != cudaSuccess || cudaMalloc(&du, n * c->nvar * sizeof(double)) != cudaSuccess) {
+    if (dz) cudaFree(dz);
+    return pb200_fail(PB200_ENOMEM, "pb200_stage_patch_u: out of device memory");
+  }
+  cudaMemcpyAsync(dz, zone, n * sizeof(long), cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(du, u, n * c->nvar * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  gen_patch_u<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->gU, c->dev.sv, c->nvar, n, dz, du);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(dz);
+  cudaFree(du);
+  return cudaGetLastError() == cudaSuccess ? PB200_OK : pb200_fail(PB200_ECUDA, "pb200_stage_patch_u failed");
 }
 
 // one stage of AdvanceStep() on the general path; Boundary() fills were enqueued by the caller

@@ -58,12 +58,19 @@ struct pb200_ctx {
   double *ldw_tfit, *ldw_mfit;
   double *cool_tab[7];                    // BLONDIN tables (null: defaults)
   int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
+  // FLAG_INTERNAL_BOUNDARY zones (Src/int_bound_reset.c): byte mask over all zones (general path) and
+  // the list of flagged interior zones (fast path: ib_fix after the last sweep of a stage)
+  bool stage_uploaded;                    // pb200_stage_upload() replaced the array the next stage sweeps
+  unsigned char *d_ibmask;
+  long *d_iblist;
+  long ib_n;
 };
 
 int  pb200_fail(int code, const char *msg);   // sets pb200_last_error(), returns code
 int  pb200_gen_setup(pb200_ctx *c);
 void pb200_gen_release(pb200_ctx *c);
 int  pb200_gen_stage(pb200_ctx *c, int stage);
+int  pb200_gen_patch_u(pb200_ctx *c, long n, const long *zone, const double *u);
 int  pb200_gen_internal_boundary(pb200_ctx *c, double *V);   // UserDefBoundary(side == 0)
 int  pb200_gen_userdef_side(pb200_ctx *c, double *V, int side);
 int  pb200_gen_entropy(pb200_ctx *c, double *V);               // ComputeEntropy at the end of Boundary()

@@ -13,13 +13,29 @@
  *                      H2D(d->Vc) -> AdvanceStep on the GPU -> D2H(d->Vc).
  *   PB200_RESIDENT=1   the state stays in HBM between steps; d->Vc is refreshed only before
  *                      WriteData()/Analysis() (link with -Wl,--wrap=WriteData,--wrap=Analysis).
+ *   PB200_NGPUS=N      slab-decompose the grid over N GPUs of the box from this one host thread
+ *                      (pb200_multi_*: NCCL halo exchange and dt reduction inside the library);
+ *                      the replacement of the reference's MPI layer (Src/Parallel, boundary.c:139-158,
+ *                      main.c:288,547) for the unmodified serial C driver.  Cartesian 2-D/3-D path.
+ *   PB200_DEVICES=a,b,..   device ordinal of every rank (may repeat: ranks sharing a GPU)
+ *   PB200_HOST_BOUNDARY=1  force the reference's own Boundary() on the host per stage.
+ *   PB200_LDW_CVIDL_BC=0|1 line-driven wind: never / always use the device copies of cv_idl's
+ *                      UserDefBoundary(); default: use them only if they REPRODUCE the linked
+ *                      UserDefBoundary() on the initial state and on a perturbed copy of it.
+ *
+ * No silent wrong answers: user callbacks the device path cannot honour are detected at start-up
+ * (state-dependent BodyForceVector, FLAG_INTERNAL_BOUNDARY zones, a UserDefBoundary() that is not
+ * cv_idl's) and either routed through the host (slow, correct) or refused with QUIT_PLUTO.
  */
 #include "pluto.h"
 #include "pluto_b200.h"
 
 static pb200_ctx *s_ctx = NULL;
+static pb200_multi *s_multi = NULL;   /* PB200_NGPUS > 1 */
 static int s_resident = 0, s_dirty = 0;
 static int s_host_bc = 0;   /* boundaries are filled by the reference's own Boundary() on the host */
+static int s_bf_time_dependent = 0;   /* BodyForce*() reads g_time: tables are re-evaluated every step */
+static int s_ldw_device_bc = 0;       /* the device copies of cv_idl's UserDefBoundary() are in use */
 
 static int translate_limiter(void) {
 #ifdef LIMITER
@@ -51,8 +67,7 @@ static int translate_limiter(void) {
 /* Evaluate a user body-force callback once on the reference's own grid arrays and hand the
  * result over as the smallest strided table: axes the values do not depend on get stride 0
  * (a constant g is one double, a Phi(x2) potential NX2_TOT doubles).                        */
-typedef int (*bf_setter)(pb200_ctx *, int, const double *, long, long, long, long);
-static void shim_set_table(bf_setter set, int sel, const double *full)
+static void shim_set_table(int vector, int sel, const double *full)
 {
   long n[3] = {NX1_TOT, NX2_TOT, NX3_TOT}, st_full[3] = {1, NX1_TOT, (long)NX1_TOT*NX2_TOT};
   long dep[3] = {0, 0, 0}, st[3], m[3], i, j, k, cnt = 1;
@@ -67,7 +82,12 @@ static void shim_set_table(bf_setter set, int sel, const double *full)
   tab = (double *) malloc(cnt*sizeof(double));
   for (k = 0; k < m[2]; k++) for (j = 0; j < m[1]; j++) for (i = 0; i < m[0]; i++)
     tab[i*st[0] + j*st[1] + k*st[2]] = full[k*st_full[2] + j*st_full[1] + i];
-  if (set(s_ctx, sel, tab, cnt, st[0], st[1], st[2]) != PB200_OK) {
+  int rc;
+  if (s_multi != NULL) rc = vector ? pb200_multi_set_body_force_vector(s_multi, sel, tab, cnt, st[0], st[1], st[2])
+                                   : pb200_multi_set_body_force_potential(s_multi, sel, tab, cnt, st[0], st[1], st[2]);
+  else                 rc = vector ? pb200_set_body_force_vector(s_ctx, sel, tab, cnt, st[0], st[1], st[2])
+                                   : pb200_set_body_force_potential(s_ctx, sel, tab, cnt, st[0], st[1], st[2]);
+  if (rc != PB200_OK) {
     print ("! AdvanceStep(): body-force table: %s\n", pb200_last_error());
     QUIT_PLUTO(1);
   }
@@ -89,7 +109,7 @@ static void shim_body_force(Data *d, Grid *grid)
     o = ((long)k*NX2_TOT + j)*NX1_TOT + i;
     for (c = 0; c < 3; c++) full[c*ntot + o] = g[c];
   }
-  for (c = 0; c < 3; c++) shim_set_table(pb200_set_body_force_vector, c, full + c*ntot);
+  for (c = 0; c < 3; c++) shim_set_table(1, c, full + c*ntot);
 #endif
 #if (BODY_FORCE & POTENTIAL)
   for (c = 0; c < 4; c++) {              /* rhs.c:168-182, rhs_source.c:279,382,441 */
@@ -100,10 +120,47 @@ static void shim_body_force(Data *d, Grid *grid)
                                    c == 2 ? grid->xr[JDIR][j] : x2[j],
                                    c == 3 ? grid->xr[KDIR][k] : x3[k]);
     }
-    shim_set_table(pb200_set_body_force_potential, c, full);
+    shim_set_table(0, c, full);
   }
 #endif
   free(full);
+}
+
+/* The device path tabulates the body force by POSITION.  Probe the user's callbacks once: a force
+ * that changes with the state v[] cannot be tabulated (refused), one that changes with g_time is
+ * re-tabulated before every step.                                                               */
+static void shim_probe_body_force(Data *d, Grid *grid)
+{
+  int i, j, k, nv, c, n = 0, dep_v = 0, dep_t = 0;
+  double t_save = g_time;
+  TOT_LOOP(k,j,i) {
+    if ((n++) % 97 != 0) continue;                  /* a sample of zones is enough */
+    double x1 = grid->x[IDIR][i], x2 = grid->x[JDIR][j], x3 = grid->x[KDIR][k];
+#if (BODY_FORCE & VECTOR)
+    double v[NVAR], w[NVAR], g0[3] = {0,0,0}, g1[3] = {0,0,0}, g2[3] = {0,0,0};
+    NVAR_LOOP(nv) { v[nv] = d->Vc[nv][k][j][i]; w[nv] = 1.37*v[nv] + 0.11; }
+    BodyForceVector(v, g0, x1, x2, x3);
+    BodyForceVector(w, g1, x1, x2, x3);
+    g_time = t_save + 1.2345;
+    BodyForceVector(v, g2, x1, x2, x3);
+    g_time = t_save;
+    for (c = 0; c < 3; c++) { if (g1[c] != g0[c]) dep_v = 1; if (g2[c] != g0[c]) dep_t = 1; }
+#endif
+#if (BODY_FORCE & POTENTIAL)
+    double p0 = BodyForcePotential(x1, x2, x3), p1;
+    g_time = t_save + 1.2345;
+    p1 = BodyForcePotential(x1, x2, x3);
+    g_time = t_save;
+    if (p1 != p0) dep_t = 1;
+#endif
+  }
+  if (dep_v) {
+    print ("! AdvanceStep(): BodyForceVector() depends on the state v[]; libplutob200 tabulates the body\n");
+    print ("!                force by position and cannot honour that.  Not supported on the GPU path.\n");
+    QUIT_PLUTO(1);
+  }
+  s_bf_time_dependent = dep_t;
+  if (dep_t) print ("> AdvanceStep(): the body force depends on g_time: tables are re-evaluated every step\n");
 }
 #endif
 
@@ -156,15 +213,71 @@ void __wrap_read_sirocco_fluxes (Data *d, Grid *grid)
   }
 }
 
+/* read_sirocco_heatcool() (Src/LineDriven/line_connect.c:267-497, called from Src/main.c:176,197): the
+ * restart branch (flag != 0) reads py_heatcool.dat and prefactors.dat with the same O(rows x zones)
+ * search; with PB200_FAST_TABLES=1 the library's bisection readers fill the same Data arrays
+ * (sirocco_xi, sirocco_t_r and the six *_pre tables, Src/structs.h:621-643).  Link with
+ * --wrap=read_sirocco_heatcool.  flag == 0 (analytic initialisation) stays the reference's code. */
+void __real_read_sirocco_heatcool (Data *d, Grid *grid, int flag);
+void __wrap_read_sirocco_heatcool (Data *d, Grid *grid, int flag)
+{
+  const char *env = getenv("PB200_FAST_TABLES");
+#if COOLING == NO
+  __real_read_sirocco_heatcool (d, grid, flag); (void)env; return;
+#else
+  if (env == NULL || atoi(env) == 0 || flag == 0) { __real_read_sirocco_heatcool (d, grid, flag); return; }
+  int i, j, k;
+  long n;
+  pb200_table_grid tg;
+  tg.nx1_tot = NX1_TOT; tg.nx2_tot = NX2_TOT;
+  tg.ibeg = IBEG; tg.iend = IEND; tg.jbeg = JBEG; tg.jend = JEND;
+  tg.x1 = grid->x[IDIR]; tg.x2 = grid->x[JDIR];
+  tg.unit_length = UNIT_LENGTH;
+  if (NX3_TOT != 1) { print ("! read_sirocco_heatcool (libplutob200): the tables are 2-D (NX3_TOT = 1)\n"); QUIT_PLUTO(1); }
+  print ("> read_sirocco_heatcool: libplutob200 table readers\n");
+  n = pb200_read_heatcool_file ("py_heatcool.dat", &tg, d->sirocco_xi[0][0], d->sirocco_t_r[0][0]);
+  if (n == -1) {                                       /* line_connect.c:309-323: no file -> analytic values */
+    print ("NO py_heatcool file\n");
+    DOM_LOOP(k,j,i) {
+      double rho = d->Vc[RHO][k][j][i]*UNIT_DENSITY, r = grid->x[IDIR][i]*UNIT_LENGTH;
+      double nH = rho/(1.43*CONST_mp), lx = g_inputParam[L_star]*g_inputParam[f_x];
+      d->sirocco_xi[k][j][i]  = lx/nH/(r*r);
+      d->sirocco_t_r[k][j][i] = g_inputParam[T_x];
+    }
+  } else if (n < 0) { print ("! py_heatcool file incorrectly formatted (error %ld)\n", n); QUIT_PLUTO(1); }
+  else print ("Read in %ld py_heatcool entries\n", n);
+  DOM_LOOP(k,j,i) {                                    /* line_connect.c:400-410 */
+    d->comp_h_pre[k][j][i] = d->comp_c_pre[k][j][i] = d->xray_h_pre[k][j][i] = 1.0;
+    d->line_c_pre[k][j][i] = d->brem_c_pre[k][j][i] = d->xi_ion_pre[k][j][i] = 1.0;
+  }
+  {
+    size_t nz = (size_t)NX2_TOT*NX1_TOT;
+    double *pre = (double *) malloc (6*nz*sizeof(double));
+    double *dst[6] = {d->comp_h_pre[0][0], d->comp_c_pre[0][0], d->xray_h_pre[0][0], d->line_c_pre[0][0],
+                      d->brem_c_pre[0][0], d->xi_ion_pre[0][0]};
+    int q;
+    for (q = 0; q < 6; q++) memcpy (pre + q*nz, dst[q], nz*sizeof(double));
+    n = pb200_read_prefactors_file ("prefactors.dat", &tg, pre);
+    if (n == -1) print ("NO prefactor file\n");
+    else if (n < 0) { print ("! Prefactor file incorrectly formatted (error %ld)\n", n); QUIT_PLUTO(1); }
+    else {
+      for (q = 0; q < 6; q++) memcpy (dst[q], pre + q*nz, nz*sizeof(double));
+      print ("Read in %ld prefactors\n", n);
+    }
+    free (pre);
+  }
+#endif
+}
+
 /* LINE_DRIVEN_WIND SIROCCO_MODE: parameters of the cv_idl problem and the flux tables that
  * read_sirocco_fluxes() left in the globals flux_{r,t,p}_UV[NFLUX_ANGLES][k][j][i]
  * (Src/globals.h:193-200, Src/main.c:157-200).  ARRAY_4D payloads are contiguous.           */
-static void shim_line_driven_wind(void)
+static void shim_line_driven_wind(int device_bc)
 {
   pb200_ldw_config l;
   memset(&l, 0, sizeof(l));
   l.nangles       = NFLUX_ANGLES;
-  l.userdef_bc    = 1;       /* the UserDefBoundary() of Test_Problems/LineDrivenWind/cv_idl */
+  l.userdef_bc    = device_bc;   /* device copies of the UserDefBoundary() of Test_Problems/LineDrivenWind/cv_idl */
   l.unit_length   = UNIT_LENGTH;
   l.unit_velocity = UNIT_VELOCITY;
   l.unit_density  = UNIT_DENSITY;
@@ -198,7 +311,7 @@ static void shim_line_driven_wind(void)
 }
 #endif
 
-static void shim_init(Data *d, Grid *grid) {
+static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
   pb200_config cfg;
   int dir;
   pb200_config_default(&cfg);
@@ -255,16 +368,6 @@ static void shim_init(Data *d, Grid *grid) {
     print ("! AdvanceStep(): this Riemann solver is not available in libplutob200\n");
     QUIT_PLUTO(1);
   }
-  /* USERDEF sides (other than the line-driven-wind problem's, which has device versions) and
-     INTERNAL_BOUNDARY are arbitrary host code: fall back to the reference's Boundary() per stage */
-#if LINE_DRIVEN_WIND == NO
-  for (dir = 0; dir < DIMENSIONS; dir++)
-    if (grid->lbound[dir] == USERDEF || grid->rbound[dir] == USERDEF) s_host_bc = 1;
-#if INTERNAL_BOUNDARY == YES
-  s_host_bc = 1;
-#endif
-#endif
-  if (getenv("PB200_HOST_BOUNDARY")) s_host_bc = atoi(getenv("PB200_HOST_BOUNDARY"));
   for (dir = 0; dir < 3; dir++) {
     cfg.nx[dir]   = grid->np_int[dir];
     cfg.xbeg[dir] = grid->xbeg[dir];
@@ -276,22 +379,36 @@ static void shim_init(Data *d, Grid *grid) {
   cfg.small_density  = g_smallDensity;
   cfg.small_pressure = g_smallPressure;
   if (getenv("PB200_DEVICE")) cfg.device = atoi(getenv("PB200_DEVICE"));
-  s_resident = getenv("PB200_RESIDENT") && atoi(getenv("PB200_RESIDENT"));
-  if (pb200_create(&cfg, &s_ctx) != PB200_OK) {
+  *pcfg = cfg;
+}
+
+/* create the device context(s) for the current s_host_bc / device-boundary choice and hand over the
+ * grid, the body-force tables and the line-driven-wind tables                                     */
+static void shim_create(Data *d, Grid *grid, int ngpus, int ldw_device_bc) {
+  pb200_config cfg;
+  int dir, rc;
+  shim_fill_config(&cfg, d, grid);
+  if (ngpus > 1) {
+    int devs[64], nd = 0;                      /* PB200_DEVICES=0,1,...: device ordinal of every rank */
+    const char *dl = getenv("PB200_DEVICES");
+    while (dl != NULL && *dl != '\0' && nd < 64) { devs[nd++] = atoi(dl); dl = strchr(dl, ','); if (dl) dl++; }
+    rc = pb200_multi_create(&cfg, ngpus, nd == ngpus ? devs : NULL, &s_multi);
+    if (rc != PB200_OK) { print ("! AdvanceStep(): pb200_multi_create (PB200_NGPUS=%d): %s\n", ngpus, pb200_last_error()); QUIT_PLUTO(1); }
+    s_ctx = pb200_multi_ctx(s_multi, 0);
+  } else if (pb200_create(&cfg, &s_ctx) != PB200_OK) {
     print ("! AdvanceStep(): pb200_create: %s\n", pb200_last_error());
     QUIT_PLUTO(1);
   }
   for (dir = 0; dir < DIMENSIONS; dir++) {   /* the reference's own grid arrays */
-    if (pb200_set_grid(s_ctx, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir]) != PB200_OK) {
-      print ("! AdvanceStep(): pb200_set_grid: %s\n", pb200_last_error());
-      QUIT_PLUTO(1);
-    }
+    rc = s_multi ? pb200_multi_set_grid(s_multi, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir])
+                 : pb200_set_grid(s_ctx, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir]);
+    if (rc != PB200_OK) { print ("! AdvanceStep(): pb200_set_grid: %s\n", pb200_last_error()); QUIT_PLUTO(1); }
   }
 #if BODY_FORCE != NO
   shim_body_force(d, grid);
 #endif
 #if LINE_DRIVEN_WIND != NO
-  shim_line_driven_wind();
+  shim_line_driven_wind(ldw_device_bc);
 #if COOLING == BLONDIN
   {   /* Data tables of the BLONDIN module (Src/structs.h:621-643, contiguous ARRAY_3D payloads) */
     const double *tabs[7] = {d->comp_h_pre[0][0], d->comp_c_pre[0][0], d->xray_h_pre[0][0], d->line_c_pre[0][0],
@@ -302,10 +419,134 @@ static void shim_init(Data *d, Grid *grid) {
     }
   }
 #endif
+#else
+  (void)ldw_device_bc;
 #endif
-  print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode%s)\n", pb200_version(),
+}
+
+#if LINE_DRIVEN_WIND != NO
+/* Do the device copies of cv_idl's UserDefBoundary() reproduce the UserDefBoundary() this executable
+ * was linked with?  Boundary(d, 0, grid) on the host against pb200_boundary() on the device, on the
+ * initial state and on a perturbed copy (rarefied / cold / counter-streaming zones, so that the
+ * floors, the mid-plane reset and the inflow switches of the user's code act).  Returns 1 if equal. */
+static int shim_probe_ldw_boundary(Data *d, Grid *grid) {
+  size_t n = (size_t)NVAR*NX3_TOT*NX2_TOT*NX1_TOT, q;
+  double *vc = d->Vc[0][0][0];
+  double *save = (double *) malloc (n*sizeof(double)), *dev = (double *) malloc (n*sizeof(double));
+  int pass, ok = 1, i, j, k;
+  memcpy (save, vc, n*sizeof(double));
+  for (pass = 0; pass < 2 && ok; pass++) {
+    if (pass == 1) DOM_LOOP(k,j,i) {
+      if ((i + 2*j) % 3 == 0) d->Vc[RHO][k][j][i] *= 1.e-9;
+      if ((2*i + j) % 5 == 0) d->Vc[PRS][k][j][i] *= 1.e-9;
+      if ((i + j) % 7 == 0)   d->Vc[VX1][k][j][i] = -d->Vc[VX1][k][j][i] - 0.3;
+      if ((i + 3*j) % 4 == 0) d->Vc[VX2][k][j][i] = 0.7 - d->Vc[VX2][k][j][i];
+    }
+    if (pb200_upload_vc (s_ctx, vc) != PB200_OK || pb200_boundary (s_ctx) != PB200_OK ||
+        pb200_download_vc (s_ctx, dev) != PB200_OK) { ok = 0; break; }
+    Boundary (d, 0, grid);
+    for (q = 0; q < n; q++) {
+      double a = dev[q], b = vc[q], sc = fabs(b) > 1.e-300 ? fabs(b) : 1.e-300;
+      if (!(fabs(a - b) <= 1.e-11*sc)) { ok = 0; break; }
+    }
+    memcpy (vc, save, n*sizeof(double));
+  }
+  free (save); free (dev);
+  return ok;
+}
+#endif
+
+static void shim_init(Data *d, Grid *grid) {
+  int dir, ngpus = 1, ldw_device_bc = 0;
+  s_resident = getenv("PB200_RESIDENT") && atoi(getenv("PB200_RESIDENT"));
+  if (getenv("PB200_NGPUS")) ngpus = atoi(getenv("PB200_NGPUS"));
+  if (ngpus < 1) ngpus = 1;
+  /* USERDEF sides and INTERNAL_BOUNDARY are arbitrary host code: the reference's Boundary() per stage
+     (the line-driven-wind problem has device versions, used only when they are verified below)   */
+#if LINE_DRIVEN_WIND == NO
+  for (dir = 0; dir < DIMENSIONS; dir++)
+    if (grid->lbound[dir] == USERDEF || grid->rbound[dir] == USERDEF) s_host_bc = 1;
+#if INTERNAL_BOUNDARY == YES
+  s_host_bc = 1;
+#endif
+#else
+  ldw_device_bc = 1;
+  if (getenv("PB200_LDW_CVIDL_BC")) ldw_device_bc = atoi(getenv("PB200_LDW_CVIDL_BC")) != 0;
+  if (!ldw_device_bc) s_host_bc = 1;
+#endif
+  if (getenv("PB200_HOST_BOUNDARY")) { s_host_bc = atoi(getenv("PB200_HOST_BOUNDARY")); if (s_host_bc) ldw_device_bc = 0; }
+  if (ngpus > 1 && s_host_bc) {
+    print ("! AdvanceStep(): PB200_NGPUS > 1 needs boundaries the device can fill (no USERDEF / INTERNAL_BOUNDARY)\n");
+    QUIT_PLUTO(1);
+  }
+#if BODY_FORCE != NO
+  shim_probe_body_force(d, grid);
+#endif
+  shim_create(d, grid, ngpus, ldw_device_bc);
+#if LINE_DRIVEN_WIND != NO
+  if (ldw_device_bc && getenv("PB200_LDW_CVIDL_BC") == NULL) {
+    if (shim_probe_ldw_boundary(d, grid)) {
+      print ("> AdvanceStep(): UserDefBoundary() verified against the device version (cv_idl)\n");
+    } else {
+      print ("> AdvanceStep(): UserDefBoundary() differs from the device version of cv_idl's:\n");
+      print (">                boundaries are filled by the host's Boundary() every stage\n");
+      pb200_destroy(s_ctx); s_ctx = NULL;
+      s_host_bc = 1; ldw_device_bc = 0;
+      shim_create(d, grid, 1, 0);
+    }
+  }
+#endif
+  s_ldw_device_bc = ldw_device_bc;
+  print ("> AdvanceStep() runs on the GPU (libplutob200 v%d, %s mode%s", pb200_version(),
          s_resident ? "resident" : "strict host-buffer",
          s_host_bc ? ", boundaries by the host's Boundary()/UserDefBoundary()" : "");
+  if (s_multi) print (", %d GPUs", pb200_multi_ngpus(s_multi));
+  print (")\n");
+}
+
+/* FLAG_INTERNAL_BOUNDARY (Src/int_bound_reset.c:17-40, called from rhs.c:416-417): zones whose update is
+ * frozen.  The reference re-reads d->flag every sweep; the host zeroes the flags at the top of every
+ * step (main.c:258-261) and user code sets them in UserDefBoundary(side 0), i.e. inside Boundary().
+ * In host-boundary mode the mask therefore travels to the device after every Boundary() call.    */
+#if INTERNAL_BOUNDARY == YES
+static unsigned char *s_ibmask = NULL;
+static int shim_internal_boundary_mask(const Data *d)
+{
+  long ntot = (long)NX1_TOT*NX2_TOT*NX3_TOT, o = 0, any = 0;
+  int i, j, k;
+  if (s_ibmask == NULL) s_ibmask = (unsigned char *) malloc (ntot);
+  TOT_LOOP(k,j,i) { s_ibmask[o] = (d->flag[k][j][i] & FLAG_INTERNAL_BOUNDARY) ? 1 : 0; any |= s_ibmask[o]; o++; }
+  return pb200_set_internal_boundary_mask(s_ctx, any ? s_ibmask : NULL);
+}
+#endif
+
+/* Host-boundary mode, stages > 1: user code that changes INTERIOR zones inside Boundary() converts them
+ * itself (PrimToCons3D on 1-zone boxes, cv_idl/init.c:272-275); zones it changes without converting keep the
+ * d->Uc of the previous stage in the reference.  Mark d->Uc with a NaN payload before Boundary(), collect the
+ * zones whose mark is gone afterwards and hand exactly those to the device copy of d->Uc.            */
+static void shim_mark_uc(Data *d)
+{
+  int i, j, k;
+  union { double f; unsigned long long u; } mark;
+  mark.u = 0x7ff8dead00b20000ull;
+  DOM_LOOP(k,j,i) d->Uc[k][j][i][RHO] = mark.f;
+}
+static int shim_patch_uc(Data *d)
+{
+  static long *zone = NULL;
+  static double *u = NULL;
+  long n = 0, ntot = (long)NX1_TOT*NX2_TOT*NX3_TOT;
+  int i, j, k, nv;
+  union { double f; unsigned long long u; } q;
+  if (zone == NULL) { zone = (long *) malloc (ntot*sizeof(long)); u = (double *) malloc (ntot*NVAR*sizeof(double)); }
+  DOM_LOOP(k,j,i) {
+    q.f = d->Uc[k][j][i][RHO];
+    if (q.u == 0x7ff8dead00b20000ull) continue;
+    zone[n] = ((long)k*NX2_TOT + j)*NX1_TOT + i;
+    NVAR_LOOP(nv) u[n*NVAR + nv] = d->Uc[k][j][i][nv];
+    n++;
+  }
+  return pb200_stage_patch_u(s_ctx, n, zone, u);
 }
 
 int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
@@ -318,8 +559,11 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
     shim_init(d, grid);
     /* page-lock the contiguous payload of d->Vc (ARRAY_4D, Src/arrays.c:251-330) for the copies */
     pb200_host_register(vc, (size_t)NVAR*NX3_TOT*NX2_TOT*NX1_TOT*sizeof(double));
-    if (s_resident) pb200_upload_vc(s_ctx, vc);
+    if (s_resident) { if (s_multi) pb200_multi_upload_vc(s_multi, vc); else pb200_upload_vc(s_ctx, vc); }
   }
+#if BODY_FORCE != NO
+  if (s_bf_time_dependent) shim_body_force(d, grid);     /* g(t), Phi(t): tables for this step's g_time */
+#endif
   if (s_host_bc) {
     /* per stage: D2H, the reference's Boundary() (-> UserDefBoundary) on d->Vc, H2D, stage */
     int s, ns = pb200_nstages(s_ctx);
@@ -328,12 +572,21 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
       g_intStage = s;
       if (s > 1 || s_resident) rc = pb200_stage_download(s_ctx, s, vc);
       if (rc != PB200_OK) break;
+      if (s > 1) shim_mark_uc(d);                 /* which zones of d->Uc does the user's Boundary() write? */
       Boundary (d, 0, grid);
+      if (s > 1) { rc = shim_patch_uc(d); if (rc != PB200_OK) break; }
+#if INTERNAL_BOUNDARY == YES
+      rc = shim_internal_boundary_mask(d);
+      if (rc != PB200_OK) break;
+#endif
       rc = pb200_stage_upload(s_ctx, s, vc);
       if (rc == PB200_OK) rc = pb200_stage(s_ctx, s);
     }
     if (rc == PB200_OK) rc = pb200_step_end(s_ctx, &info);
     if (rc == PB200_OK) rc = pb200_download_vc(s_ctx, vc);
+  } else if (s_multi) {
+    if (s_resident) { rc = pb200_multi_advance_step(s_multi, g_dt, &info); s_dirty = 1; }
+    else rc = pb200_multi_advance_step_host(s_multi, vc, g_dt, &info);
   } else if (s_resident) {
     rc = pb200_advance_step(s_ctx, g_dt, &info);
     s_dirty = 1;
@@ -344,7 +597,14 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
     print ("! AdvanceStep(): %s\n", pb200_last_error());
     QUIT_PLUTO(1);
   }
-  Dts->invDt_hyp = MAX(Dts->invDt_hyp, info.invDt_hyp);   /* update_stage.c:320,391 */
+  /* update_stage.c:320 (1-D) / :389-392: invDt_hyp = MAX(invDt_hyp, max C_dt) / DIMENSIONS, where the
+     old value survives from the previous step when COOLING != NO (main.c:406-415 resets Dts only every
+     second step); info.invDt_hyp is max C_dt / DIMENSIONS already                               */
+#if DIMENSIONS > 1
+  Dts->invDt_hyp = MAX(Dts->invDt_hyp/(double)DIMENSIONS, info.invDt_hyp);
+#else
+  Dts->invDt_hyp = MAX(Dts->invDt_hyp, info.invDt_hyp);
+#endif
   g_maxMach      = MAX(g_maxMach, info.maxMach);          /* hll_speed.c:89 */
   return 0;
 }
@@ -353,22 +613,34 @@ int AdvanceStep (Data *d, timeStep *Dts, Grid *grid)
 void pb200_shim_sync_to_host(const Data *d)
 {
   if (s_ctx != NULL && s_resident && s_dirty) {
-    pb200_download_vc(s_ctx, d->Vc[0][0][0]);
+    if (s_multi) pb200_multi_download_vc(s_multi, d->Vc[0][0][0]);
+    else pb200_download_vc(s_ctx, d->Vc[0][0][0]);
     s_dirty = 0;
   }
 }
-/* resident mode with COOLING BLONDIN: the source step runs on the device copy as well
- * (link with -Wl,--wrap=SplitSource); host-buffer mode keeps the reference's own SplitSource() */
+/* The source step (link with -Wl,--wrap=SplitSource).  Resident mode with COOLING BLONDIN and the
+ * line-driven wind: BlondinCooling on the device copy.  Every other module (POWER_LAW, TABULATED, ...,
+ * STS / RKL parabolic terms) is the reference's own host code: in resident mode the state is brought
+ * down, the reference's SplitSource() runs on d->Vc, and the result goes back up, so the host copy is
+ * never stale.  Host-buffer mode keeps the reference's SplitSource() on d->Vc as it is.           */
 void __real_SplitSource (Data *, double, timeStep *, Grid *);
 void __wrap_SplitSource (Data *d, double dt, timeStep *Dts, Grid *grid)
 {
 #if COOLING == BLONDIN && LINE_DRIVEN_WIND != NO
-  if (s_ctx != NULL && s_resident) {
+  if (s_ctx != NULL && s_resident && !s_host_bc) {
     if (pb200_split_source(s_ctx, dt, g_time) != PB200_OK) {
       print ("! SplitSource(): pb200_split_source failed\n");
       QUIT_PLUTO(1);
     }
     s_dirty = 1;
+    return;
+  }
+#endif
+#if COOLING != NO || (defined(PARABOLIC_FLUX) && PARABOLIC_FLUX != NO)
+  if (s_ctx != NULL && s_resident) {
+    pb200_shim_sync_to_host(d);
+    __real_SplitSource(d, dt, Dts, grid);
+    if (s_multi) pb200_multi_upload_vc(s_multi, d->Vc[0][0][0]); else pb200_upload_vc(s_ctx, d->Vc[0][0][0]);
     return;
   }
 #endif

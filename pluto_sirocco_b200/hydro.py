@@ -459,6 +459,16 @@ class Hydro:
         ptrs = (C.c_void_p * 7)(*[None if a is None else a.ctypes.data for a in keep])
         L.check(self._lib.pb200_cooling_set_tables(self._h, C.byref(ptrs)))
 
+    def set_internal_boundary_mask(self, mask):
+        """FLAG_INTERNAL_BOUNDARY zones (bool/uint8 [NX3_TOT][NX2_TOT][NX1_TOT], None: none): rhs = 0 in every
+        sweep, InternalBoundaryReset() (Src/int_bound_reset.c:17)."""
+        if mask is None:
+            L.check(self._lib.pb200_set_internal_boundary_mask(self._h, None))
+            return
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert m.shape == self.shape[1:]
+        L.check(self._lib.pb200_set_internal_boundary_mask(self._h, m.ctypes.data_as(C.c_void_p)))
+
     def split_source(self, dt, g_time):
         """SplitSource(d, dt, Dts, grid) for COOLING BLONDIN (Src/split_source.c:53)."""
         L.check(self._lib.pb200_split_source(self._h, float(dt), float(g_time)))
