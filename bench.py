@@ -84,6 +84,20 @@ def rt_block(nx, zoff, nglob, gamma=5. / 3., eta=2.0, grav=-0.1):
     return v
 
 
+def busy_block(nx, seed):
+    """"busy" state: the seeded waves + jumps of tests/common.py random_state (shocks, contacts, every limiter and
+    solver branch active in every zone neighbourhood), generated on a block of <= 128 zones per direction and
+    tiled periodically over the grid."""
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    from common import random_state
+    n1, n2, n3 = nx
+    b = [min(m, 128) for m in (n3, n2, n1)]
+    v = random_state(tuple(b), seed=seed, smooth=False)
+    reps = [1] + [-(-m // q) for m, q in zip((n3, n2, n1), b)]
+    return np.tile(v, reps)[:, :n3, :n2, :n1]
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -151,23 +165,25 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------
 #  reference arm: the unmodified reference C build on the host cores
 # --------------------------------------------------------------------------------------
-def reference_rate(cfg, n, nproc, warm, steps, solver="hllc"):
+def reference_rate(cfg, shape, nproc, warm, steps, solver="hllc"):
     """Mzones/s of `nproc` concurrent serial reference processes (no MPI on this image, so this
-    is the communication-free upper bound of an MPI run) on n^3 zones each.  Timed by
-    differencing a (warm) and a (warm+steps) run so initialisation is excluded."""
+    is the communication-free upper bound of an MPI run), each on a block of shape = (nx1, nx2, nx3)
+    zones of the Sedov problem.  Timed by differencing a (warm) and a (warm+steps) run so
+    initialisation is excluded."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import refrun
     exe = refrun.REFDIR / cfg / "pluto"
     if not exe.exists():
         return None
+    n1, n2, n3 = shape
 
     def launch(maxsteps):
         procs, dirs = [], []
         for p in range(nproc):
             d = tempfile.mkdtemp(prefix="plref_")
             dirs.append(d)
-            refrun.write_ini(Path(d) / "pluto.ini", grid=[(0, n, 1)] * 3, cfl=0.3, tstop=0.5, first_dt=1e-9,
-                             solver=solver, bcs=SEDOV_BCS, params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4))
+            refrun.write_ini(Path(d) / "pluto.ini", grid=[(0, n1, 1), (0, n2, 1), (0, n3, n3 / float(n1))], cfl=0.3, tstop=0.5,
+                             first_dt=1e-9, solver=solver, bcs=SEDOV_BCS, params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4))
             procs.append(subprocess.Popen([str(exe), "-no-write", "-maxsteps", str(maxsteps)], cwd=d,
                                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
         t0 = time.perf_counter()
@@ -184,34 +200,167 @@ def reference_rate(cfg, n, nproc, warm, steps, solver="hllc"):
     dt = tb - ta
     if dt < 0.05 * tb:      # too short to difference reliably: charge the whole second run to its steps
         dt = tb * steps / float(warm + steps)
-    return nproc * n ** 3 * steps / dt / 1e6, dt
+    return nproc * n1 * n2 * n3 * steps / dt / 1e6, dt
+
+
+def cart_config(args, world, zones_local, nvar=5):
+    """`config` of the Cartesian workloads: the SAME dict in both arms (the reference arm times a bounded
+    sample of this workload and says which in cpu_baseline.sample)."""
+    n, rt = args.size, args.workload == "rt"
+    tot = (n + 4) ** 3 if args.recon == "LINEAR" else (n + 6) ** 3
+    return {"workload": workload_name(n, args.recon, args.rk, args.solver, rt), "state": "rt" if rt else args.state,
+            "zones_per_gpu": zones_local, "decomposition": "x3 slabs" if world > 1 else "none",
+            "l2": "inputs (%.1f GB per state array) larger than L2, no flush needed" % (nvar * tot * 8 / 1e9),
+            "boundaries": "periodic x1/x3, reflective x2" if rt else "reflective-beg/outflow-end", "cfl": 0.4 if rt else 0.3}
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the unmodified executable, oracle/_ref) on all host
+    cores, on THIS arm's workload: the n^3-per-GPU Sedov grid is cut into x3 slabs, one serial process per core
+    (what its MPI build would do minus the communication); a step of the sample covers min(n^3, budget) zones."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = len(os.sched_getaffinity(0))
     cfg = "sedov3d" if args.recon == "LINEAR" else "sedov3d_ppm"
-    n = args.ref_size
-    # keep the run bounded: about steps*n^3/1e6 seconds per process
-    res = reference_rate(cfg, n, cores, args.warmup, args.steps, args.solver)
-    wl = workload_name(args.size, args.recon, args.rk, args.solver)
+    n = args.size
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    # bound the run to ~2.5 minutes: K+W steps at ~2.5 Mzones/s per core
+    nsteps = args.steps + max(args.warmup, 1)
+    budget = int(150.0 * 2.5e6 / nsteps)                       # zones per process and step
+    nproc = min(cores, max(1, n // 8))
+    planes = max(4, min(n // nproc, budget // (n * n)))
+    if args.ref_size:                                           # explicit cubic sample (tests)
+        shape = (args.ref_size,) * 3
+    else:
+        shape = (n, n, planes)
+    res = reference_rate(cfg, shape, nproc, max(args.warmup, 1), args.steps, args.solver)
     if res is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref/%s/pluto not built on this box" % cfg})
         return 0
     rate, dt = res
-    sample = ("%d concurrent serial processes (no MPI on this image: communication-free upper bound), "
-              "%d^3 zones each, same problem/solver, %d timed steps (init excluded by differencing two runs); "
-              "gcc -O3 -std=c17 (Config/Linux.gcc.defs)" % (cores, n, args.steps))
+    frac = nproc * shape[0] * shape[1] * shape[2] / float(n ** 3 * world)
+    sample = ("%d concurrent serial processes of the unmodified reference executable (no MPI on this image: the "
+              "communication-free upper bound of its MPI build), each on a %d x %d x %d slab of the workload's grid "
+              "(%.0f %% of the %d^3 x %d-GPU zones per step), same problem / solver / reconstruction, %d timed steps "
+              "(initialisation excluded by differencing two runs); gcc -O3 -std=c17 (Config/Linux.gcc.defs)"
+              % (nproc, shape[0], shape[1], shape[2], 100.0 * frac, n, world, args.steps))
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": wl},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "data": "synthetic", "config": cart_config(args, world, n ** 3),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nproc, "kind": "reference", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
+
+
+# --------------------------------------------------------------------------------------
+#  short measurements of the other BASELINE configs (reported under "secondary")
+# --------------------------------------------------------------------------------------
+def quick_cart(*, workload, size, recon, rk, state, steps, warmup=3, solver="hllc"):
+    """Device-resident zone-updates/s of a Cartesian workload on the ranks of this job (all ranks call this).
+    Same slab machinery and timing rules as the headline: W warm-up steps, K steps between CUDA events on the
+    launching stream, barrier + synchronize on both sides, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pluto_sirocco_b200 import Hydro
+    from pluto_sirocco_b200.slab import Slab, SlabHydro
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n, rt = size, workload == "rt"
+    if rt:
+        gnx, bcs = (n, n, n), ("periodic", "periodic", "reflective", "reflective", "periodic", "periodic")
+        gxb, gxe, gamma, ntr, bf = (-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), 5. / 3., 1, 1
+        zones_local = n * n * (n // world)
+    else:
+        gnx, bcs = (n, n, n * world), SEDOV_BCS
+        gxb, gxe, gamma, ntr, bf = (0., 0., 0.), (1., 1., float(world)), 1.4, 0, 0
+        zones_local = n ** 3
+    slab = Slab(rank, world, 3, gnx, gxb, gxe, bcs)
+    xb, xe = slab.local_extent()
+    h = Hydro(dimensions=3, nx=slab.local_nx(), xbeg=xb, xend=xe, gamma=gamma, reconstruction=recon, time_stepping=rk,
+              solver=solver, bcs=slab.local_bcs(), device=local_rank, dx=slab.global_dx(), ntracer=ntr, body_force=bf)
+    if rt:
+        for comp, val in enumerate((0.0, -0.1, 0.0)):
+            h.set_body_force_vector(comp, np.full((1, 1, 1), val))
+    sh = SlabHydro(h, slab)
+    vc = np.ones(h.shape)
+    vc[1:4] = 0.0
+    if rt:
+        vc[h.interior()] = rt_block(slab.local_nx(), slab.offset, n)
+    elif state == "sedov":
+        vc[h.interior()] = sedov_block(slab.local_nx(), slab.offset, n)
+    else:
+        vc[h.interior()] = busy_block(slab.local_nx(), rank)
+    h.upload(vc)
+    del vc
+    cfl, cmv, first_dt = (0.4, 1.1, 1e-3) if rt else (0.3, 1.1, 1e-9)
+    g = {"dt": first_dt if (state == "sedov" or rt) else 1e-5}
+
+    def one_step():
+        inv, mach, info = sh.advance_step(g["dt"])
+        g["dt"] = h.next_time_step(inv, cfl, cmv, g["dt"], first_dt)
+        return info
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, warmup)):
+        one_step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    launches = 0
+    ev0.record(sh.stream)
+    for _ in range(steps):
+        launches += one_step().launches
+    ev1.record(sh.stream)
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    nvar = h.nvar
+    h.close()
+    torch.cuda.empty_cache()
+    peak, _ = measured_peaks()
+    alg = (ALG_BYTES_RK2 if rk == "RK2" else ALG_BYTES_RK3) * nvar / 5.0
+    step_ms = ms / steps
+    return {"workload": workload_name(n, recon, rk, solver, rt), "state": "rt" if rt else state, "n_gpus": world,
+            "value": zones_local * world * steps / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+            "zones_per_gpu": zones_local, "scaling": "strong" if rt else "weak",
+            "roofline_step_frac": alg * zones_local / (step_ms * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_zone_update": alg, "gpu_launches": launches * world}
+
+
+def quick_sod(steps=400):
+    """C1: Test_Problems/HD/Sod (400 zones, PLM + HLLC + RK2), the main loop run by pb200_integrate()."""
+    import numpy as np
+    import torch
+    from pluto_sirocco_b200 import Hydro
+    h = Hydro(dimensions=1, nx=(400, 1, 1), gamma=1.4, bcs=("outflow",) * 6, device=int(os.environ.get("LOCAL_RANK", "0")))
+    x = (np.arange(400) + 0.5) / 400
+    v = np.zeros((5, 1, 1, 400))
+    v[0, 0, 0] = np.where(x < 0.5, 1.0, 0.125)
+    v[4, 0, 0] = np.where(x < 0.5, 1.0, 0.1)
+    h.set_interior(v)
+    h.integrate(20, t=0.0, dt=1e-4, tstop=1e9, cfl=0.8, cfl_max_var=1.1, first_dt=1e-4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n, t, dt = h.integrate(steps, t=0.0, dt=1e-4, tstop=1e9, cfl=0.8, cfl_max_var=1.1, first_dt=1e-4)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = h.last.launches
+    h.close()
+    return {"workload": "sod1d-400 PLM+HLLC+RK2 (Test_Problems/HD/Sod conf 01)", "n_gpus": 1, "value": 400 * n / wall / 1e6,
+            "unit": UNIT, "ms_per_step": 1e3 * wall / n, "steps": n, "gpu_launches_per_step": launches,
+            "note": "launch/latency bound: 400 zones; wall clock of pb200_integrate() incl. the per-step dt read-back"}
 
 
 # --------------------------------------------------------------------------------------
@@ -274,9 +423,7 @@ def run_b200(args):
     elif args.state == "sedov":
         vc[h.interior()] = sedov_block(slab.local_nx(), slab.offset, n)
     else:   # "busy": seeded waves + jumps everywhere: every limiter/solver branch is exercised
-        sys.path.insert(0, str(ROOT / "tests"))
-        from common import random_state
-        vc[h.interior()] = random_state((n, n, n), seed=rank, smooth=False)
+        vc[h.interior()] = busy_block(slab.local_nx(), rank)
     h.upload(vc)
 
     cfl, cmv, first_dt = (0.4, 1.1, 1e-3) if rt else (0.3, 1.1, 1e-9)
@@ -380,13 +527,39 @@ def run_b200(args):
                "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, the RK stages and "
                       "download pipelined over slabs of x3 planes)"}
 
+    # ---- the other BASELINE configs, a few steps each (device-resident), reported under "secondary" ----
+    nvar_head, shape_head = h.nvar, tuple(h.shape)
+    secondary = None
+    headline_cfg = (not rt and args.size == 512 and args.recon == "LINEAR" and args.rk == "RK2" and args.state == "sedov")
+    if headline_cfg and not args.no_secondary:
+        h.close()
+        torch.cuda.empty_cache()
+        secondary = {}
+        ks = max(5, min(args.steps, 10))
+        # configs[1] again on a state with structure in every zone (the Sedov state is uniform outside the blast)
+        secondary["c2_sedov_grid_busy_state"] = quick_cart(workload="sedov", size=512, recon="LINEAR", rk="RK2", state="busy", steps=ks)
+        # configs[4]: PPM + HLLC + RK3, 256^3 per GPU, weak scaling
+        secondary["c5_ppm_rk3_256"] = quick_cart(workload="sedov", size=256, recon="PARABOLIC", rk="RK3", state="sedov", steps=2 * ks)
+        # configs[2]: Rayleigh-Taylor 1024^3 over 8 GPUs (strong-scaling form: n^3 GLOBAL zones over the ranks of this job;
+        # the named size needs all 8 GPUs, smaller jobs run 512^3)
+        secondary["c3_rayleigh_taylor"] = quick_cart(workload="rt", size=1024 if world == 8 else 512, recon="LINEAR", rk="RK2",
+                                                     state="rt", steps=ks)
+        if rank == 0:
+            secondary["c1_sod_400"] = quick_sod()
+        if world == 1:
+            # configs[3]: the line-driven wind on the general path (single GPU: replicas only)
+            try:
+                secondary["c4_line_driven_wind"] = run_ldw(args, as_dict=True)
+            except Exception as e:      # never lose the headline line to a secondary
+                secondary["c4_line_driven_wind"] = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_peaks()
-    alg = (ALG_BYTES_RK2 if args.rk == "RK2" else ALG_BYTES_RK3) * h.nvar / 5.0   # 40 B per 5-vector -> 8 B x NVAR
+    alg = (ALG_BYTES_RK2 if args.rk == "RK2" else ALG_BYTES_RK3) * nvar_head / 5.0   # 40 B per 5-vector -> 8 B x NVAR
     nlaunch_sweeps = len(kern)
     step_ms = ms / args.steps
     achieved_step = alg * zones_local / (step_ms * 1e-3) / 1e9          # GB/s per GPU, whole step
@@ -409,7 +582,7 @@ def run_b200(args):
     cpu_baseline = None
     if not args.no_cpu and not rt:
         cfg = "sedov3d" if args.recon == "LINEAR" else "sedov3d_ppm"
-        r = reference_rate(cfg, args.cpu_size, 1, 1, args.cpu_steps, args.solver)
+        r = reference_rate(cfg, (args.cpu_size,) * 3, 1, 1, args.cpu_steps, args.solver)
         if r is not None:
             cpu_baseline = {"value": r[0], "unit": UNIT, "cores": 1, "kind": "reference",
                             "sample": "unmodified reference executable (oracle/_ref/%s), %d^3 zones, %d steps, 1 core, "
@@ -431,12 +604,9 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if rt else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n, args.recon, args.rk, args.solver, rt), "state": "rt" if rt else args.state,
-                       "zones_per_gpu": zones_local, "decomposition": "x3 slabs" if world > 1 else "none",
-                       "l2": "inputs (%.1f GB per state array) larger than L2, no flush needed" % (int(np.prod(h.shape)) * 8 / 1e9),
-                       "boundaries": "periodic x1/x3, reflective x2" if rt else "reflective-beg/outflow-end", "cfl": cfl},
+            "config": cart_config(args, world, zones_local, nvar_head),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline,
-            "cpu_baseline": cpu_baseline}
+            "cpu_baseline": cpu_baseline, "secondary": secondary}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -475,7 +645,7 @@ def ldw_state(x1, x2, P, U):
     return v
 
 
-def run_ldw(args):
+def run_ldw(args, as_dict=False):
     """C4: 1024 x 512 spherical r-theta grid, NVAR 7 (tracer + entropy), char-limited PLM (van Leer),
     MULTID flattening, entropy switch, BODY_FORCE VECTOR, VGradCalc + LineForce with 36-angle
     synthetic sirocco tables, cv_idl user boundaries; HLL, RK2 (pluto_sirocco_sub.py:46-118)."""
@@ -528,7 +698,7 @@ def run_ldw(args):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     t_reg1 = time.perf_counter()
-    extra = 0 if ms >= 1500.0 else min(300, int((1500.0 - ms) / (ms / args.steps)) + 1)   # same load, untimed, for the clock samples
+    extra = 0 if (ms >= 1500.0 or as_dict) else min(300, int((1500.0 - ms) / (ms / args.steps)) + 1)   # same load, untimed, for the clock samples
     done = 0
     saved, saved_dt = h.download(), g["dt"]
     try:
@@ -573,6 +743,11 @@ def run_ldw(args):
                          "traffic": None, "peak_source": peak_src, "kernel": "whole step (multi-kernel general path)",
                          "algorithmic_bytes_per_zone_update": ALG_BYTES_LDW},
             "cpu_baseline": None}
+    h.close()
+    if as_dict:
+        return {k: line[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "config", "e2e")} | {
+            "n_gpus": 1, "roofline_step_frac": line["roofline"]["frac"],
+            "algorithmic_bytes_per_zone_update": ALG_BYTES_LDW}
     emit(line)
     return 0
 
@@ -613,9 +788,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=8)
-    ap.add_argument("--ref-size", type=int, default=96)
+    ap.add_argument("--ref-size", type=int, default=0, help="reference arm: cubic sample of this size instead of x3 slabs of the workload grid")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -330,7 +330,7 @@ def make_case4(out, name, c):
 
 
 def make_long_sedov(out):
-    """long_sedov3d_64.npz: the Sedov problem (Test_Problems/HD/Sedov conf 05) at 64^3, free running to t = 0.5 with
+    """runs/long_sedov3d_64.npz: the Sedov problem (Test_Problems/HD/Sedov conf 05) at 64^3, free running to t = 0.5 with
     the unmodified reference (1273 steps, ~5 core-minutes), reduced to what a GPU-box test compares against."""
     build_ref.build("sedov3d")
     with tempfile.TemporaryDirectory() as wd:
@@ -338,7 +338,8 @@ def make_long_sedov(out):
                        params=dict(ENRG0=1.0, DNST0=1.0, GAMMA=1.4), cfl=0.3, tstop=0.5, first_dt=1e-9,
                        solver="hllc", dbl=(1000.0, -1), timeout=3600)
     a, st = r["data"][-1], r["steps"][-1]
-    np.savez_compressed(out / "long_sedov3d_64.npz", nstep=st[0], t=st[1], dt=st[2], sub=a[:, ::4, ::4, ::4].copy(),
+    (out / "runs").mkdir(exist_ok=True)
+    np.savez_compressed(out / "runs" / "long_sedov3d_64.npz", nstep=st[0], t=st[1], dt=st[2], sub=a[:, ::4, ::4, ::4].copy(),
                         plane=a[:, 0].copy(), sums=a.reshape(5, -1).sum(axis=1), sumsq=(a.reshape(5, -1) ** 2).sum(axis=1),
                         mass=a[0].sum(), energy=(0.5 * a[0] * (a[1] ** 2 + a[2] ** 2 + a[3] ** 2) + a[4] / 0.4).sum())
 

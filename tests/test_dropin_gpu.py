@@ -215,14 +215,14 @@ SEDOV64 = dict(shape=(64, 64, 64), grid=[(0, 64, 1)] * 3, bcs=("reflective", "ou
 def test_dropin_sedov_64_to_tstop_vs_reference_fixture(cuda_lib, tmp_path):
     """SURVEY 8d / north star: the Sedov test problem at 64^3 to t = 0.5 (1273 steps, the blast fills the box),
     free running through the drop-in executable.  The unmodified reference needs ~5 core-minutes for this run, so
-    its end state was reduced to a fixture in the container (tests/golden/long_sedov3d_64.npz: every 4th zone
+    its end state was reduced to a fixture in the container (tests/golden/runs/long_sedov3d_64.npz: every 4th zone
     per direction, the k = 0 plane, per-variable sums; written from oracle/_ref/sedov3d by the recipe in
     tests/golden/make_golden.py::make_long_sedov) instead of re-running it on the GPU box."""
     cfg = "sedov3d"
     exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
     if not exe.exists():
         pytest.skip("drop-in executable was not built in the container (needs /root/reference)")
-    g = np.load(ROOT / "tests" / "golden" / "long_sedov3d_64.npz")
+    g = np.load(ROOT / "tests" / "golden" / "runs" / "long_sedov3d_64.npz")
     got = refrun.run(cfg, tmp_path / "b200", solver="hllc", dbl=(1000.0, -1), exe=exe, env={"PB200_RESIDENT": "1"},
                      timeout=900, **SEDOV64)
     n, t, dt = got["steps"][-1]
