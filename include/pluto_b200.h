@@ -191,6 +191,11 @@ int  pb200_split_source(pb200_ctx *ctx, double dt, double g_time);
  * them again inside Boundary(); call this whenever they change. */
 int  pb200_set_internal_boundary_mask(pb200_ctx *ctx, const unsigned char *mask);
 
+/* Test aid for the cooling module's arithmetic: the library's device versions of the C library's exp / log / log10 /
+ * pow (GNU libc 2.39, x86-64 FMA variants - what BlondinCooling() of the reference build calls through libm) on host
+ * arrays: which = 0 exp(x), 1 log(x), 2 log10(x), 3 pow(x, y).  Results equal the C library's bit for bit. */
+int  pb200_libm_probe(int which, long n, const double *x, const double *y, double *out);
+
 /* d->Vc  host -> device / device -> host (whole array incl. ghosts) */
 int  pb200_upload_vc(pb200_ctx *ctx, const double *vc_host);
 int  pb200_download_vc(pb200_ctx *ctx, double *vc_host);

@@ -73,6 +73,7 @@ SYMBOLS = {
     "pb200_read_heatcool_file": (C.c_long, [C.c_char_p, _P, _P, _P]),
     "pb200_read_prefactors_file": (C.c_long, [C.c_char_p, _P, _P]),
     "pb200_set_internal_boundary_mask": (C.c_int, [_P, _P]),
+    "pb200_libm_probe": (C.c_int, [C.c_int, C.c_long, _P, _P, _P]),
     "pb200_upload_vc": (C.c_int, [_P, _P]),
     "pb200_download_vc": (C.c_int, [_P, _P]),
     "pb200_device_vc": (_P, [_P]),

@@ -15,14 +15,15 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libplutob200.so"
-SOURCES = ["pb200.cu", "pb200_sweeps.cu", "pb200_gen.cu", "pb200_multi.cu", "sirocco_tables.c"]
-HEADERS = ["hd_physics.cuh", "pb200_kernels.cuh", "gen_kernels.cuh", "pb200_internal.h", "../../include/pluto_b200.h",
+SOURCES = ["pb200.cu", "pb200_sweeps.cu", "pb200_gen.cu", "pb200_cool.cu", "pb200_multi.cu", "sirocco_tables.c"]
+HEADERS = ["hd_physics.cuh", "pb200_kernels.cuh", "gen_kernels.cuh", "glibc_math.cuh", "glibc_libm_tables.h", "pb200_internal.h", "../../include/pluto_b200.h",
            "../../include/pluto_b200_tables.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 # translation units: (object name, source, extra defines).  pb200_sweeps.cu is compiled once per
 # (NVAR, BODY_FORCE) pair so that the kernel instantiations build in parallel.
 UNITS = [("pb200", "pb200.cu", []), ("pb200_gen", "pb200_gen.cu", []), ("pb200_multi", "pb200_multi.cu", []),
+         ("pb200_cool", "pb200_cool.cu", ["-fmad=false"]),      # BLONDIN: no FMA contraction, like the reference build
          ("sirocco_tables", "sirocco_tables.c", [])] + [   # host-only C (table readers): compiled with gcc
     ("sweeps_nv%d_bf%d" % (nv, bf), "pb200_sweeps.cu", ["-DPB_NV=%d" % nv, "-DPB_BF=%d" % bf])
     for nv in (5, 6, 7) for bf in (0, 1)]

@@ -33,6 +33,7 @@ struct LdwDev {
   const unsigned long long *mask;           // bit a of zone o: |flux| != 0 in angular bin a (gen_ldw_mask)
   double *gline;                            // line force [2][k][j][i]: g_r for the r sweep, g_theta for the theta sweep
   const double *sin_a, *cos_a;              // sin/cos((a + 1/2) 2 pi / 36), libm values from the host
+  const double *inv_ca;                     // 1 / sqrt(sin_a^2 + cos_a^2) (the bin's part of 1/ds, line_connect.c:566)
   const double *sin_t, *cos_t;              // sin/cos(x2[j])
   const double *xgc1, *xgc2;                // grid->xgc (mid-plane reset uses the centroids)
   double UL, UV, UD;                        // UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY
@@ -51,6 +52,7 @@ struct GenDev {
   const double *x[3], *xr[3], *dx[3], *inv_dx[3];
   const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
   const double *rt, *s, *sp;           // grid->rt[i], s[j], sp[j]
+  const double *cot, *sin2;            // 1/tan(x2[j]) and sin(x2[j]) with the host's libm (rhs_source.c:350, set_geometry.c:344)
   const double *dV;                    // grid->dV[k][j][i]
   const double *A[3];                  // grid->A[d], one extra layer at index -1 along d
   long Aoff[3], Asj[3], Ask[3];
@@ -71,6 +73,11 @@ struct GenArgs {
   double w0, wc;
   int comb, stage, dir;
   const unsigned char *ibmask;   // FLAG_INTERNAL_BOUNDARY zones: rhs = 0 (int_bound_reset.c:34-35), null: none
+  // fused sweeps with the line-driven wind: the r sweep leaves its centre state (rho, p) and mean mass flux per zone
+  // in cen[3][zones]; gen_vgrad takes the line force from them and the theta sweep adds the r sweep's force terms
+  // (the force of a sweep needs the states of that sweep, and the r sweep's states are not stored any more)
+  double *cen;
+  int defer;
 };
 
 PB_D double gen_A(const GenDev &g, int dir, int k, int j, int i) {
@@ -211,17 +218,14 @@ static __global__ void gen_p2c(GenDev g, GenArgs a, GenBox b) {
 }
 
 // ---- States: PLM on general grids, primitive or characteristic limiting -------------------
+// vp / vm of ONE zone (States(), plm_states.c): shared by gen_states (one kernel per reference stage) and by
+// the fused sweep kernel gen_sweep / gen_vgrad.  n = the zone's index along dir, st = its stride, o = its offset.
 template <int NV>
-static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
-  int i, j, k;
-  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const unsigned short *__restrict__ flag, int dir,
+                          int n, long st, long o, double (&v)[NV], double (&vpo)[NV], double (&vmo)[NV]) {
   const Dev &d = g.d;
-  const int dir = a.dir;
-  const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
-  const long o = (long)k * d.sk + (long)j * d.sj + i;
-  const int n = dir == 0 ? i : (dir == 1 ? j : k);
   const bool uniform = g.geometry == GEO_CARTESIAN;     // UNIFORM_CARTESIAN_GRID, plm_coeffs.h:23-29
-  double v[NV], dvp[NV], dvm[NV], dvl[NV];
+  double dvp[NV], dvm[NV], dvl[NV];
   double cp = 2.0, cm = 2.0, dp = 0.5, dm = 0.5, wp = 1.0, wm = 1.0;
   if (!uniform) {
     cp = __ldg(g.cp[dir] + n); cm = __ldg(g.cm[dir] + n); wp = __ldg(g.wp[dir] + n); wm = __ldg(g.wm[dir] + n);
@@ -229,12 +233,12 @@ static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   }
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
-    v[nv] = a.V[nv * d.sv + o];
-    double fp = a.V[nv * d.sv + o + st] - v[nv], fm = v[nv] - a.V[nv * d.sv + o - st];
+    v[nv] = V[nv * d.sv + o];
+    double fp = V[nv * d.sv + o + st] - v[nv], fm = v[nv] - V[nv * d.sv + o - st];
     dvp[nv] = uniform ? fp : fp * wp;
     dvm[nv] = uniform ? fm : fm * wm;
   }
-  const unsigned short fl = g.flatten ? a.flag[o] : 0;
+  const unsigned short fl = g.flatten ? flag[o] : 0;
   if (!g.char_lim) {
     if (fl & GF_FLAT) {
 #pragma unroll
@@ -299,12 +303,63 @@ static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   }
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
-    a.VP[nv * d.sv + o] = v[nv] + dvl[nv] * dp;
-    a.VM[nv * d.sv + o] = v[nv] - dvl[nv] * dm;
+    vpo[nv] = v[nv] + dvl[nv] * dp;
+    vmo[nv] = v[nv] - dvl[nv] * dm;
+  }
+}
+
+template <int NV>
+static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
+  const Dev &d = g.d;
+  const int dir = a.dir;
+  const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  const int n = dir == 0 ? i : (dir == 1 ? j : k);
+  double v[NV], vp[NV], vm[NV];
+  gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    a.VP[nv * d.sv + o] = vp[nv];
+    a.VM[nv * d.sv + o] = vm[nv];
   }
 }
 
 // ---- Riemann solver + AdvectFlux at the face between zone n and n+1 -------------------------
+// vLg / vRg: left / right state in GLOBAL variable order; F: flux in global order, F[NV] = pressure, F[NV+1] = cmax
+template <int NV>
+PB_D double gen_face(const GenDev &g, int dir, const double (&vLg)[NV], const double (&vRg)[NV], bool hll, double (&F)[NV + 2]) {
+  const int gn = 1 + dir, gt = 1 + (dir + 1) % 3, gb = 1 + (dir + 2) % 3;
+  double vL[NV], vR[NV];     // sweep-local order (n, t, b)
+  vL[0] = vLg[0]; vR[0] = vRg[0];
+  vL[1] = dir == 0 ? vLg[1] : (dir == 1 ? vLg[2] : vLg[3]); vR[1] = dir == 0 ? vRg[1] : (dir == 1 ? vRg[2] : vRg[3]);
+  vL[2] = dir == 0 ? vLg[2] : (dir == 1 ? vLg[3] : vLg[1]); vR[2] = dir == 0 ? vRg[2] : (dir == 1 ? vRg[3] : vRg[1]);
+  vL[3] = dir == 0 ? vLg[3] : (dir == 1 ? vLg[1] : vLg[2]); vR[3] = dir == 0 ? vRg[3] : (dir == 1 ? vRg[1] : vRg[2]);
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) { vL[nv] = vLg[nv]; vR[nv] = vRg[nv]; }
+  Face<NV> Ff;
+  Ratio mach;
+  mach.init();
+  if (g.solver == SOLVER_TVDLF) riemann<NV, SOLVER_TVDLF>(vL, vR, g.d.gas, Ff, mach);
+  else if (g.solver == SOLVER_HLL) riemann<NV, SOLVER_HLL>(vL, vR, g.d.gas, Ff, mach);
+  else riemann<NV, SOLVER_HLLC>(vL, vR, g.d.gas, Ff, mach, true, hll);
+  if (g.entropy) {    // adv_flux.c:131-134: ">=" for the entropy, ">" for the other scalars
+    Ff.f[NV - 1] = Ff.f[iRHO] * sel(Ff.f[iRHO] >= 0.0, vL[NV - 1], vR[NV - 1]);
+  }
+  F[0] = Ff.f[0];
+  // local -> global: F[gn] = f[1], F[gt] = f[2], F[gb] = f[3]
+  F[1] = dir == 0 ? Ff.f[1] : (dir == 1 ? Ff.f[3] : Ff.f[2]);
+  F[2] = dir == 0 ? Ff.f[2] : (dir == 1 ? Ff.f[1] : Ff.f[3]);
+  F[3] = dir == 0 ? Ff.f[3] : (dir == 1 ? Ff.f[2] : Ff.f[1]);
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) F[nv] = Ff.f[nv];
+  F[NV] = Ff.prs;
+  F[NV + 1] = Ff.cmax;
+  (void)gn; (void)gt; (void)gb;
+  return mach.value();
+}
+
 template <int NV>
 static __global__ void gen_riemann(GenDev g, GenArgs a, GenBox b) {
   int i, j, k;
@@ -314,34 +369,14 @@ static __global__ void gen_riemann(GenDev g, GenArgs a, GenBox b) {
     const int dir = a.dir;
     const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
     const long o = (long)k * d.sk + (long)j * d.sj + i;
-    const int gn = 1 + dir, gt = 1 + (dir + 1) % 3, gb = 1 + (dir + 2) % 3;
-    double vL[NV], vR[NV];     // sweep-local order (n, t, b)
-    vL[0] = a.VP[o]; vR[0] = a.VM[o + st];
-    vL[1] = a.VP[gn * d.sv + o]; vR[1] = a.VM[gn * d.sv + o + st];
-    vL[2] = a.VP[gt * d.sv + o]; vR[2] = a.VM[gt * d.sv + o + st];
-    vL[3] = a.VP[gb * d.sv + o]; vR[3] = a.VM[gb * d.sv + o + st];
+    double vL[NV], vR[NV], F[NV + 2];
 #pragma unroll
-    for (int nv = 4; nv < NV; nv++) { vL[nv] = a.VP[nv * d.sv + o]; vR[nv] = a.VM[nv * d.sv + o + st]; }
+    for (int nv = 0; nv < NV; nv++) { vL[nv] = a.VP[nv * d.sv + o]; vR[nv] = a.VM[nv * d.sv + o + st]; }
     const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
-    Face<NV> F;
-    Ratio mach;
-    mach.init();
-    if (g.solver == SOLVER_TVDLF) riemann<NV, SOLVER_TVDLF>(vL, vR, d.gas, F, mach);
-    else if (g.solver == SOLVER_HLL) riemann<NV, SOLVER_HLL>(vL, vR, d.gas, F, mach);
-    else riemann<NV, SOLVER_HLLC>(vL, vR, d.gas, F, mach, true, hll);
-    if (g.entropy) {    // adv_flux.c:131-134: ">=" for the entropy, ">" for the other scalars
-      F.f[NV - 1] = F.f[iRHO] * sel(F.f[iRHO] >= 0.0, vL[NV - 1], vR[NV - 1]);
-    }
-    machv = mach.value();
+    machv = gen_face<NV>(g, dir, vL, vR, hll, F);
     const long nz = d.sv;
-    a.F[o] = F.f[0];
-    a.F[gn * nz + o] = F.f[1];
-    a.F[gt * nz + o] = F.f[2];
-    a.F[gb * nz + o] = F.f[3];
 #pragma unroll
-    for (int nv = 4; nv < NV; nv++) a.F[nv * nz + o] = F.f[nv];
-    a.F[NV * nz + o] = F.prs;
-    a.F[(NV + 1) * nz + o] = F.cmax;
+    for (int nv = 0; nv < NV + 2; nv++) a.F[nv * nz + o] = F[nv];
   }
   machv = warp_max(machv);
   if ((threadIdx.x & 31) == 0 && machv > 0.0) atomic_max_pos(a.red + 1, machv);
@@ -421,7 +456,8 @@ PB_D double gen_ldw_M(const LdwDev &w, const LdwZone &z, double D, long o, long 
 // tables (3 x 155 MB per sweep on the 1024 x 512 grid, more than L2 holds); here the 36-bin tables
 // are read ONCE per stage and the sweeps pick up one number per zone.  It runs after States() of
 // the r sweep because that sweep's force uses (vp + vm)/2 as its centre state.
-static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
+template <int NV>
+static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenBox b, int fused) {
   int i, j, k;
   if (!gen_zone(b.lo, b.hi, i, j, k)) return;
   const Dev &d = g.d;
@@ -456,29 +492,56 @@ static __global__ void gen_vgrad(GenDev g, GenArgs a, GenBox b) {
   const unsigned long long mk = __ldg(w.mask + o);
   const long nz = d.sv;
   // centre states of the two sweeps (rhs_source.c:229-232)
-  const LdwZone zr = gen_ldw_zone(w, 0.5 * (a.VP[iRHO * nz + o] + a.VM[iRHO * nz + o]),
-                                  0.5 * (a.VP[iPRS * nz + o] + a.VM[iPRS * nz + o]));
+  double rho_c, prs_c;
+  if (fused) {     // left by the fused r sweep (gen_sweep, dir 0)
+    rho_c = a.cen[o];
+    prs_c = a.cen[nz + o];
+  } else {
+    rho_c = 0.5 * (a.VP[iRHO * nz + o] + a.VM[iRHO * nz + o]);
+    prs_c = 0.5 * (a.VP[iPRS * nz + o] + a.VM[iPRS * nz + o]);
+  }
+  const LdwZone zr = gen_ldw_zone(w, rho_c, prs_c);
   const LdwZone zt = gen_ldw_zone(w, a.V[iRHO * nz + o], a.V[iPRS * nz + o]);
   const double coef = w.sigma_e / (2.99792458e10 * w.unit_acc);
   double g_r = 0.0, g_t = 0.0;
+  // per zone: the reciprocals the 36 bins share (<= 1 ulp each against the reference's divisions)
+  const double inv_b0 = 1.0 / (x22[0] - x11[0]), inv_b1 = 1.0 / (x22[1] - x11[1]);
+  const double inv_maxds = 1.0 / maxds;
+  const double vUV[2][4] = {{v11[0] * w.UV, v12[0] * w.UV, v21[0] * w.UV, v22[0] * w.UV},
+                            {v11[1] * w.UV, v12[1] * w.UV, v21[1] * w.UV, v22[1] * w.UV}};
   for (int ia = 0; ia < w.nangles; ia++) {
     const double fr = __ldg(w.flux_r + ia * nz + o), ft = __ldg(w.flux_t + ia * nz + o);
     double D = 0.0;
     if ((mk >> ia) & 1ull) {   // mod_flux != 0
       const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
       const double dx1 = maxds * sa, dx2 = maxds * ca;
-      const double ds = sqrt(dx1 * dx1 + dx2 * dx2);
-      const double r_off = sqrt((x + dx1) * (x + dx1) + (z + dx2) * (z + dx2));
-      const double qq = (x + dx1) / (z + dx2);
-      const double t_off = atan(qq);
-      gen_bilinear(x11, x22, v11, v12, v21, v22, r_off, t_off, ans2);
-      // sin / cos of t_off = atan(q): q / sqrt(1 + q^2), 1 / sqrt(1 + q^2) (principal branch, cos > 0)
-      const double co = 1.0 / sqrt(1.0 + qq * qq), so = qq * co;
-      const double vx2 = (ans2[0] * w.UV * so + ans2[1] * w.UV * co);
-      const double vz2 = (ans2[0] * w.UV * co - ans2[1] * w.UV * so);
+      const double X = x + dx1, Z = z + dx2;
+      // r_off = sqrt(X^2 + Z^2); sin / cos of t_off = atan(X / Z) (principal branch: cos > 0) are X / r, Z / r
+      const double s2 = X * X + Z * Z;
+      const double rs = rsqrt_fast(s2);
+      const double r_off = s2 * rs;
+      const double co = fabs(Z) * rs, so = (Z < 0.0 ? -X : X) * rs;
+      // t_off = atan(X / Z) = theta_j + atan(y), y = tan(t_off - theta_j) = (z dx1 - x dx2) / (z Z + x X): the offset
+      // point is at most half a zone away, so |y| << 1 and the odd series converges in a few terms (|y| < 0.06:
+      // next term y^14/15 < 6e-19); anything else takes atan() itself
+      double t_off;
+      const double yy = (z * dx1 - x * dx2) * rcp_fast(z * Z + x * X);
+      if (Z > 0.0 && fabs(yy) < 0.06) {
+        const double y2 = yy * yy;
+        const double p = 1.0 + y2 * (-1.0 / 3.0 + y2 * (1.0 / 5.0 + y2 * (-1.0 / 7.0 + y2 * (1.0 / 9.0 + y2 * (-1.0 / 11.0 + y2 * (1.0 / 13.0))))));
+        t_off = x2j + yy * p;
+      } else t_off = atan(X / Z);
+      // bilinear() of the two velocity components at (r_off, t_off), line_connect.c:746-767
+      const double f1 = (r_off - x11[0]) * inv_b0, f2 = (t_off - x11[1]) * inv_b1;
+      const double a0 = (1.0 - f1) * vUV[0][0] + f1 * vUV[0][2], b0 = (1.0 - f1) * vUV[0][1] + f1 * vUV[0][3];
+      const double a1 = (1.0 - f1) * vUV[1][0] + f1 * vUV[1][2], b1 = (1.0 - f1) * vUV[1][1] + f1 * vUV[1][3];
+      const double q0 = (1.0 - f2) * a0 + f2 * b0, q1 = (1.0 - f2) * a1 + f2 * b1;     // ans2[] * UNIT_VELOCITY
+      const double vx2 = (q0 * so + q1 * co);
+      const double vz2 = (q0 * co - q1 * so);
       const double v1 = sa * vx1 + ca * vz1;
       const double v2 = sa * vx2 + ca * vz2;
-      const double out = fabs((v2 - v1) / ds);
+      // ds = sqrt(dx1^2 + dx2^2) = maxds sqrt(sa^2 + ca^2): the bin's constant comes from the host table
+      const double out = fabs(v2 - v1) * (inv_maxds * __ldg(w.inv_ca + ia));
       // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per bin and SWEEP (the sweeps pass
       // different centre states); the bin-dependent factor dvds^(-alpha) is taken once and serves
       // both, so that a zone costs one pow() per sweep instead of 36.
@@ -577,132 +640,21 @@ static __global__ void gen_ldw_side(GenDev g, double *V, int side) {
   }
 }
 
-// ---- COOLING BLONDIN: BlondinCooling(), Src/Cooling/BLONDIN/cooling.c:50-330 ---------------
-struct CoolDev {
-  const double *tab[7];   // comp_h_pre, comp_c_pre, xray_h_pre, line_c_pre, brem_c_pre, sirocco_xi, sirocco_t_r (null: 1 / unused)
-  double dt_share;        // dt * UNIT_TIME
-  double unit_pressure, lx, tx, mu;
-  int analytic_xi;        // g_time <= 3.0 (cooling.c:99-106)
-};
-struct CoolZone {
-  double comp_c_pre, comp_h_pre, line_c_pre, brem_c_pre, xray_h_pre;
-  double nH, xi, tx, sqxi, sqsqxi, n, E, hc_init, dt_share;
-};
-PB_D double cool_ne_rat(double T) {
-  if (T < 1.5e4) return 1e-2 + pow(10.0, (-51.59417133 + 12.27740153 * log10(T)));
-  else if (T < 3.3e4) return pow(10.0, (-3.80749689 + 0.86092628 * log10(T)));
-  return 1.21;
-}
-PB_D double cool_heatcool(const CoolZone &q, double T) {
-  const double sqT = sqrt(T);
-  const double ne = q.nH * cool_ne_rat(T);
-  const double comp_heat = q.comp_h_pre * (8.9e-36 * q.xi * q.tx);
-  const double comp_cool = q.comp_c_pre * (8.9e-36 * q.xi * (4.0 * T));
-  const double xray_heat = q.xray_h_pre * (1.5e-21 * (q.sqsqxi / sqT));
-  const double line_cool = q.line_c_pre * ((1e-16 * exp(-1.3e5 / T) / q.sqxi / T) + fmin(fmin(1e-24, 5e-27 * sqT), 1.5e-17 / T));
-  const double brem_cool = q.brem_c_pre * (3.3e-27 * sqT);
-  return q.nH * (ne * comp_heat + q.nH * xray_heat - ne * comp_cool - ne * line_cool - ne * brem_cool);
-}
-PB_D double cool_zfunc(const CoolZone &q, double temp) {
-  return (temp * q.n * 1.3806505e-16 / (2.0 / 3.0)) - q.E - q.dt_share * (q.hc_init + cool_heatcool(q, temp)) / 2.0;
-}
-template <bool ZF>
-__device__ double cool_zbrent(const CoolZone &z, double x1, double x2, double tol) {
-  auto F = [&](double x) { return ZF ? cool_zfunc(z, x) : cool_heatcool(z, x); };
-  const double EPS = 3.0e-8;
-  double a = x1, b = x2, c = x2, d = 0.0, e = 0.0;
-  double fa = F(a), fb = F(b), fc = fb, p, q, r, s, tol1, xm;
-  if (fb * fa > 0.0) return b;
-  for (int iter = 1; iter <= 100; iter++) {
-    if (fb * fc > 0.0) { c = a; fc = fa; e = d = b - a; }
-    if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
-    tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol;
-    xm = 0.5 * (c - b);
-    if (fabs(xm) <= tol1 || fb == 0.0) return b;
-    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
-      s = fb / fa;
-      if (a == c) { p = 2.0 * xm * s; q = 1.0 - s; }
-      else {
-        q = fa / fc; r = fb / fc;
-        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
-        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
-      }
-      if (p > 0.0) q = -q;
-      p = fabs(p);
-      const double min1 = 3.0 * xm * q - fabs(tol1 * q), min2 = fabs(e * q);
-      if (2.0 * p < (min1 < min2 ? min1 : min2)) { e = d; d = p / q; }
-      else { d = xm; e = d; }
-    } else { d = xm; e = d; }
-    a = b; fa = fb;
-    if (fabs(d) > tol1) b += d;
-    else b += (xm > 0.0 ? fabs(tol1) : -fabs(tol1));
-    fb = F(b);
-  }
-  return b;
-}
-
-static __global__ void gen_blondin(GenDev g, double *V, CoolDev cd, GenBox b) {
-  int i, j, k;
-  if (!gen_zone(b.lo, b.hi, i, j, k)) return;
-  const Dev &d = g.d;
-  const long o = (long)k * d.sk + (long)j * d.sj + i;
-  CoolZone q;
-  q.dt_share = cd.dt_share;
-  q.comp_h_pre = cd.tab[0] ? cd.tab[0][o] : 1.0;     // defaults of read_sirocco_heatcool(), line_connect.c:383-393
-  q.comp_c_pre = cd.tab[1] ? cd.tab[1][o] : 1.0;
-  q.xray_h_pre = cd.tab[2] ? cd.tab[2][o] : 1.0;
-  q.line_c_pre = cd.tab[3] ? cd.tab[3][o] : 1.0;
-  q.brem_c_pre = cd.tab[4] ? cd.tab[4][o] : 1.0;
-  const double r = __ldg(g.x[0] + i) * g.ldw.UL;
-  const double rho_code = V[o], pr = V[iPRS * d.sv + o];
-  const double rho = rho_code * g.ldw.UD;
-  q.E = (pr * cd.unit_pressure) / (d.gas.gamma - 1);
-  q.nH = rho / (1.43 * 1.67262171e-24);
-  if (cd.analytic_xi || !cd.tab[5] || !cd.tab[6]) { q.xi = cd.lx / q.nH / r / r; q.tx = cd.tx; }
-  else { q.xi = cd.tab[5][o]; q.tx = cd.tab[6][o]; }
-  q.n = rho / (cd.mu * 1.67262171e-24);
-  const double T = q.E * (2.0 / 3.0) / (q.n * 1.3806505e-16);
-  if (T < 1.e4) return;                               // g_minCoolingTemp
-  q.sqxi = sqrt(q.xi);
-  q.sqsqxi = pow(q.xi, 0.25);
-  q.hc_init = cool_heatcool(q, T);
-  double t_l = T * 0.9, t_u = T * 1.1, T_f;
-  double test = cool_zfunc(q, t_l) * cool_zfunc(q, t_u);
-  int guard = 0;
-  while (test > 0 && test == test && guard++ < 4000) {
-    t_l *= 0.9; t_u *= 1.1;
-    test = cool_zfunc(q, t_l) * cool_zfunc(q, t_u);
-  }
-  if (test != test) T_f = T;
-  else {
-    T_f = cool_zbrent<true>(q, t_l, t_u, 1.0);
-    const double hc_final = cool_heatcool(q, T_f);
-    if (hc_final * q.hc_init < 0.0) T_f = cool_zbrent<false>(q, fmin(T_f, T), fmax(T_f, T), 1.0);
-  }
-  T_f = fmax(T_f, 1.e4);
-  const double E_f = T_f / (2.0 / 3.0) * (q.n * 1.3806505e-16);
-  V[iPRS * d.sv + o] = E_f * (d.gas.gamma - 1) / cd.unit_pressure;
-}
-
 // ---- RightHandSide + RightHandSideSource + U += rhs + C_dt -------------------------------
+// rhs of ONE zone from the fluxes of its two faces along dir (fp: upper face n+1/2, fm: lower face, global variable
+// order, pressure and cmax passed separately) and the centre state vg (stateC->v, or (vp + vm)/2 for the spherical
+// r sweep, rhs_source.c:229-232).  cdt_c: the zone's C_dt term of this direction (DIMENSIONS > 1);
+// inv_max: the 1-D invDt_hyp candidates.  Shared by gen_rhs and the fused gen_sweep.
 template <int NV>
-static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
-  int i, j, k;
+PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j, int k, long o, double (&fp)[NV],
+                       double (&fm)[NV], double pp, double pm, double cp_, double cm_, const double (&vg)[NV],
+                       double (&rhs)[NV], double &cdt_c, double &inv_max, int ldw_mode = 0, double *mf_out = nullptr) {
+  // ldw_mode 1: leave the line force of this (r) sweep to the theta sweep; 2: add it here (theta sweep)
   const Dev &d = g.d;
-  double inv_max = 0.0;
-  if (gen_zone(b.lo, b.hi, i, j, k)) {
-    const int dir = a.dir;
-    const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
-    const long o = (long)k * d.sk + (long)j * d.sj + i;
-    const long nz = d.sv;
-    const int n = dir == 0 ? i : (dir == 1 ? j : k);
-    const double dt = *a.dt;
-    const int gn = 1 + dir;
-    double rhs[NV], fp[NV], fm[NV];
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) { fp[nv] = a.F[nv * nz + o]; fm[nv] = a.F[nv * nz + o - st]; }
-    const double pp = a.F[NV * nz + o], pm = a.F[NV * nz + o - st];
-    const double cp_ = a.F[(NV + 1) * nz + o], cm_ = a.F[(NV + 1) * nz + o - st];
+  const long nz = d.sv;
+  const int n = dir == 0 ? i : (dir == 1 ? j : k);
+  const double dt = *a.dt;
+  {
     const double frp = fp[iRHO], frm = fm[iRHO];      // mass fluxes (not area weighted)
     double dpn;   // pressure-gradient term of the normal momentum
     if (g.geometry == GEO_CARTESIAN) {
@@ -728,15 +680,6 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
       if (dir == 0) rhs[3] /= fabs(__ldg(g.x[0] + n));
       else if (dir == 1) rhs[3] /= fabs(__ldg(g.s + n));
     }
-    // centre state (stateC->v) and, for the spherical r sweep, vc = (vp + vm)/2  (rhs_source.c:229-232)
-    double vg[NV];
-    if (g.geometry == GEO_SPHERICAL && dir == 0) {
-#pragma unroll
-      for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (a.VP[nv * nz + o] + a.VM[nv * nz + o]);
-    } else {
-#pragma unroll
-      for (int nv = 0; nv < NV; nv++) vg[nv] = a.V[nv * nz + o];
-    }
     double sn = 0.0;   // source of the normal momentum
     if (g.geometry == GEO_SPHERICAL && dir == 0) {
       const double r_1 = 1.0 / __ldg(g.x[0] + n);
@@ -744,7 +687,7 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
       sn = dt * Sm * r_1;
     } else if (g.geometry == GEO_SPHERICAL && dir == 1) {
       const double r_1 = 1.0 / __ldg(g.rt + i);
-      const double ct = 1.0 / tan(__ldg(g.x[1] + n));
+      const double ct = __ldg(g.cot + n);          // 1/tan(x2[j]) with the host's libm tan(), like the reference
       const double Sm = vg[iRHO] * (-vg[2] * vg[1] + ct * vg[3] * vg[3]);
       sn = dt * Sm * r_1;
     }
@@ -757,7 +700,7 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
         if (!(d.bf_kind & 1)) continue;
         gv[0] = bf_at(d, 0, i, j, k); gv[1] = bf_at(d, 1, i, j, k); gv[2] = bf_at(d, 2, i, j, k);
       } else {
-        if (!g.ldw.on) continue;
+        if (!g.ldw.on || ldw_mode == 1) continue;
         gv[0] = g.ldw.gline[o]; gv[1] = g.ldw.gline[nz + o]; gv[2] = 0.0;   // LineForce() sums taken by gen_vgrad
       }
       const double gd = dir == 0 ? gv[0] : (dir == 1 ? gv[1] : gv[2]);
@@ -775,31 +718,156 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
       }
     }
     if (dir == 0) rhs[1] = rn; else if (dir == 1) rhs[2] = rn; else rhs[3] = rn;
-    (void)gn;
+    if (mf_out) *mf_out = 0.5 * (frp + frm);
+    if (ldw_mode == 2) {   // the r sweep's line force (rhs_source.c:284-297) with that sweep's centre density and mass flux
+      const double g_r = g.ldw.gline[o];
+      rhs[1] += dt * a.cen[o] * g_r;
+      rhs[iPRS] += dt * a.cen[2 * nz + o] * g_r;
+    }
     if (a.ibmask && a.ibmask[o]) {   // InternalBoundaryReset(), rhs.c:416-417
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) rhs[nv] = 0.0;
     }
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] += rhs[nv];
     // GetInverse_dl (set_geometry.c:303-375) and C_dt (update_stage.c:303-322)
     double inv_dl = __ldg(g.inv_dx[dir] + n);
     if (g.geometry == GEO_SPHERICAL && dir == 1) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i));
-    if (g.geometry == GEO_SPHERICAL && dir == 2) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i)) / sin(__ldg(g.x[1] + j));
+    if (g.geometry == GEO_SPHERICAL && dir == 2) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i)) / __ldg(g.sin2 + j);
     if (d.ndim > 1) {
-      if (a.stage == 1) {
-        const double c = 0.5 * (cm_ + cp_) * inv_dl;
-        a.cdt[o] = (dir == 0) ? c : a.cdt[o] + c;
-      }
+      cdt_c = 0.5 * (cm_ + cp_) * inv_dl;
     } else {
       // 1-D: every stage, faces IBEG-1..IEND with inv_dl of the face's left zone
       inv_max = cp_ * inv_dl;
       if (n == d.beg[0]) inv_max = fmax(inv_max, cm_ * __ldg(g.inv_dx[0] + n - 1));
     }
   }
+}
+
+template <int NV>
+static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
+  int i, j, k;
+  const Dev &d = g.d;
+  double inv_max = 0.0;
+  if (gen_zone(b.lo, b.hi, i, j, k)) {
+    const int dir = a.dir;
+    const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+    const long o = (long)k * d.sk + (long)j * d.sj + i;
+    const long nz = d.sv;
+    double rhs[NV], fp[NV], fm[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { fp[nv] = a.F[nv * nz + o]; fm[nv] = a.F[nv * nz + o - st]; }
+    const double pp = a.F[NV * nz + o], pm = a.F[NV * nz + o - st];
+    const double cp_ = a.F[(NV + 1) * nz + o], cm_ = a.F[(NV + 1) * nz + o - st];
+    // centre state (stateC->v) and, for the spherical r sweep, vc = (vp + vm)/2  (rhs_source.c:229-232)
+    double vg[NV];
+    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (a.VP[nv * nz + o] + a.VM[nv * nz + o]);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = a.V[nv * nz + o];
+    }
+    double cdt_c = 0.0;
+    gen_zone_rhs<NV>(g, a, dir, i, j, k, o, fp, fm, pp, pm, cp_, cm_, vg, rhs, cdt_c, inv_max);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] += rhs[nv];
+    if (d.ndim > 1 && a.stage == 1) a.cdt[o] = (dir == 0) ? cdt_c : a.cdt[o] + cdt_c;
+  }
   if (g.d.ndim == 1) {
     inv_max = warp_max(inv_max);
     if ((threadIdx.x & 31) == 0 && inv_max > 0.0) atomic_max_pos(a.red + 0, inv_max);
+  }
+}
+
+// ---- the fused sweep: States -> Riemann -> RightHandSide of one direction in ONE kernel -------------------
+// (north star: "each directional sweep is a single fused kernel": the L/R states, the fluxes and the right-hand
+// side never leave the SM; the VP / VM / F arrays of the multi-kernel form are not touched.)
+// Thread <-> zone.  A block covers S consecutive zones along the sweep direction for L lanes across it
+// (dir 0: S = 128, L = 1, one row of i;  dir 1, 2: S = 16 rows/planes of L = 32 zones of i, so that global accesses
+// stay coalesced along i).  The first and last zone of a tile only supply their states: S - 2 zones per tile are
+// updated.  vm of zone n+1 and the flux of face n-1/2 reach zone n through shared memory (two barriers).
+// FIRST (stage 1, first direction) also does PrimToCons3D + the U0 copy (rk_step.c:129-130) of its zones.
+template <int NV, int S, int L>
+static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, int first) {
+  __shared__ double sh[NV + 2][S * L];
+  const Dev &d = g.d;
+  const int dir = a.dir;
+  const int tid = threadIdx.x, s = tid / L, l = tid % L;
+  // tile origin: blockIdx.x tiles the lanes (i for dir != 0), blockIdx.y the sweep direction, blockIdx.z the rest
+  int idx[3];
+  const int n = d.beg[dir] - 1 + (int)blockIdx.y * (S - 2) + s;
+  if (dir == 0) { idx[0] = n; idx[1] = d.beg[1] + (int)blockIdx.x; idx[2] = d.beg[2] + (int)blockIdx.z; }
+  else if (dir == 1) { idx[0] = d.beg[0] + (int)blockIdx.x * L + l; idx[1] = n; idx[2] = d.beg[2] + (int)blockIdx.z; }
+  else { idx[0] = d.beg[0] + (int)blockIdx.x * L + l; idx[1] = d.beg[1] + (int)blockIdx.z; idx[2] = n; }
+  const int i = idx[0], j = idx[1], k = idx[2];
+  const bool lane_ok = (dir == 0 || i <= d.end[0]) && (dir == 1 || j <= d.end[1]) && (dir == 2 || k <= d.end[2]);
+  const bool st_ok = lane_ok && n <= d.end[dir] + 1;            // States(nbeg-1, nend+1)
+  const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
+  const long o = (long)k * d.sk + (long)j * d.sj + i;
+  const long nz = d.sv;
+  double v[NV], vp[NV], vm[NV];
+  if (st_ok) gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
+  else {
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) v[nv] = vp[nv] = vm[nv] = 1.0;
+  }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) sh[nv][tid] = vm[nv];
+  __syncthreads();
+  const bool face_ok = st_ok && s < S - 1 && n <= d.end[dir];   // Riemann(nbeg-1, nend)
+  double F[NV + 2], machv = 0.0;
+  if (face_ok) {
+    double vR[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) vR[nv] = sh[nv][tid + L];
+    const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
+    machv = gen_face<NV>(g, dir, vp, vR, hll, F);
+  } else {
+#pragma unroll
+    for (int nv = 0; nv < NV + 2; nv++) F[nv] = 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int nv = 0; nv < NV + 2; nv++) sh[nv][tid] = F[nv];
+  __syncthreads();
+  double inv_max = 0.0;
+  if (face_ok && s >= 1 && n >= d.beg[dir]) {
+    double fp[NV], fm[NV], rhs[NV], vg[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { fp[nv] = F[nv]; fm[nv] = sh[nv][tid - L]; }
+    const double pp = F[NV], pm = sh[NV][tid - L], cp_ = F[NV + 1], cm_ = sh[NV + 1][tid - L];
+    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (vp[nv] + vm[nv]);
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) vg[nv] = v[nv];
+    }
+    double cdt_c = 0.0, mf = 0.0;
+    const int ldw_mode = (a.defer && g.ldw.on) ? (dir == 0 ? 1 : (dir == 1 ? 2 : 0)) : 0;
+    gen_zone_rhs<NV>(g, a, dir, i, j, k, o, fp, fm, pp, pm, cp_, cm_, vg, rhs, cdt_c, inv_max, ldw_mode, &mf);
+    if (ldw_mode == 1) { a.cen[o] = vg[iRHO]; a.cen[nz + o] = vg[iPRS]; a.cen[2 * nz + o] = mf; }
+    if (first) {
+      // PrimToCons3D + RBoxCopy(U0): exact restatement (no reciprocal sharing), these values seed U0
+      double u[NV];
+      const double rho = v[iRHO];
+      u[0] = rho; u[1] = rho * v[1]; u[2] = rho * v[2]; u[3] = rho * v[3];
+      double k2 = v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+      u[4] = 0.5 * rho * k2 + v[4] / d.gas.gmm1;
+#pragma unroll
+      for (int nv = NFLX; nv < NV; nv++) u[nv] = rho * v[nv];
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) { a.U0[nv * nz + o] = u[nv]; a.U[nv * nz + o] = u[nv] + rhs[nv]; }
+    } else {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] += rhs[nv];
+    }
+    if (d.ndim > 1 && a.stage == 1) a.cdt[o] = (dir == 0) ? cdt_c : a.cdt[o] + cdt_c;
+  }
+  machv = warp_max(machv);
+  if ((tid & 31) == 0 && machv > 0.0) atomic_max_pos(a.red + 1, machv);
+  if (d.ndim == 1) {
+    inv_max = warp_max(inv_max);
+    if ((tid & 31) == 0 && inv_max > 0.0) atomic_max_pos(a.red + 0, inv_max);
   }
 }
 

@@ -100,6 +100,14 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->ldw_on = false;
   c->cur_stage = 0;
   c->d_ibmask = nullptr;
+  c->graph_exec = nullptr;
+  c->graph_sig = 0;
+  c->graph_launches = 0;
+  c->gen_epoch = 0;
+  c->capturing = false;
+  // PB200_GRAPH=0|1 overrides; default: grids below 4 M zones (above that a step is milliseconds of kernels)
+  c->use_graph = -1;
+  if (const char *p = getenv("PB200_GRAPH")) c->use_graph = atoi(p) != 0;
   c->stage_uploaded = false;
   c->d_iblist = nullptr;
   c->ib_n = 0;
@@ -208,6 +216,7 @@ extern "C" void pb200_destroy(pb200_ctx *c) {
   if (c->ldw_tfit) cudaFree(c->ldw_tfit);
   if (c->ldw_mfit) cudaFree(c->ldw_mfit);
   for (int q = 0; q < 7; q++) if (c->cool_tab[q]) cudaFree(c->cool_tab[q]);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->d_ibmask) cudaFree(c->d_ibmask);
   if (c->d_iblist) cudaFree(c->d_iblist);
   for (int k = 0; k < 3; k++) if (c->V[k]) cudaFree(c->V[k]);
@@ -364,12 +373,14 @@ static void launch_sweep(pb200_ctx *c, int dir, const SweepArgs &a) {
 // NaN screen of the array about to be swept is folded into the reduction cell by a tiny
 // kernel over the dt-reduction result instead of a full pass: a NaN anywhere propagates to
 // cmax of its faces, and fmax() drops NaNs, so test invDt/maxMach via the c2p counter.
-__global__ void reset_red(unsigned long long *red, double *dt, double dtval) {
+// g_dt comes from a pinned host cell (device-visible under UVA), not from a kernel argument, so that a
+// captured graph of the step can be replayed with a new dt
+__global__ void reset_red(unsigned long long *red, double *dt, const double *dt_host) {
   red[0] = 0ull;
   red[1] = 0ull;
   red[2] = 0ull;
   red[3] = 0ull;
-  *dt = dtval;
+  *dt = *dt_host;
 }
 
 // ---- FLAG_INTERNAL_BOUNDARY --------------------------------------------------------------
@@ -469,8 +480,12 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
     int rc = pb200_gen_setup(c);
     if (rc) return fail(rc, "general-grid set-up failed (out of device memory?)");
   }
-  CK(cudaEventRecord(c->ev0, c->stream));
-  reset_red<<<1, 1, 0, c->stream>>>(c->d_red, c->d_dt, dt);
+  if (!c->capturing) {
+    CK(cudaStreamSynchronize(c->stream));    // h_dt of the previous step has been consumed
+    CK(cudaEventRecord(c->ev0, c->stream));
+  }
+  *c->h_dt = dt;
+  reset_red<<<1, 1, 0, c->stream>>>(c->d_red, c->d_dt, c->h_dt);
   c->launches++;
   // array rotation: stage s sweeps stage_in[s] and writes stage_out[s]
   int A = c->cur, B = (c->cur + 1) % (c->nstages == 3 ? 3 : 2), C = (c->cur + 2) % 3;
@@ -586,11 +601,43 @@ extern "C" int pb200_stage(pb200_ctx *c, int stage) {
   return pb200_stage_finish(c, stage);
 }
 
+static int finish_info(pb200_ctx *c, pb200_step_info *info);
 extern "C" int pb200_step_end(pb200_ctx *c, pb200_step_info *info) {
   if (!c || !c->in_step) return fail(PB200_EINVAL, "pb200_step_end outside a step");
   c->in_step = false;
   if (c->nstages == 1) c->cur = c->stage_out[1];  // EULER: result lives in the other array
   CK(cudaMemcpyAsync(c->h_red, c->d_red, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  return finish_info(c, info);
+}
+
+static unsigned long long graph_signature(const pb200_ctx *c) {
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&h](const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t k = 0; k < n; k++) { h ^= b[k]; h *= 1099511628211ull; }
+  };
+  mix(&c->dev, sizeof(c->dev));
+  mix(&c->cfg, sizeof(c->cfg));
+  mix(&c->cur, sizeof(c->cur));
+  mix(&c->ldw_on, sizeof(c->ldw_on));
+  mix(&c->ldw, sizeof(c->ldw));
+  mix(c->ldw_flux, sizeof(c->ldw_flux));
+  mix(&c->ldw_dvds, sizeof(void *));
+  mix(&c->ldw_mask, sizeof(void *));
+  mix(&c->ldw_mpoints, sizeof(int));
+  mix(&c->ldw_tfit, sizeof(void *));
+  mix(&c->ldw_mfit, sizeof(void *));
+  mix(&c->d_ibmask, sizeof(void *));
+  mix(&c->d_iblist, sizeof(void *));
+  mix(&c->ib_n, sizeof(long));
+  mix(&c->gdev, sizeof(void *));
+  mix(&c->gen_epoch, sizeof(int));
+  mix(&c->gen_ready, sizeof(bool));
+  mix(c->V, sizeof(c->V));
+  return h;
+}
+
+static int finish_info(pb200_ctx *c, pb200_step_info *info) {
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   double invdt, mach;
@@ -629,7 +676,64 @@ extern "C" int pb200_kernel_times(const pb200_ctx *c, int max, float *ms, int *d
   return n;
 }
 
+// everything that ends up in a kernel argument of a step: if it changes, the captured graph is stale
+static unsigned long long graph_signature(const pb200_ctx *c);
+
+static int finish_info(pb200_ctx *c, pb200_step_info *info);
+
+static int advance_step_graph(pb200_ctx *c, double dt, pb200_step_info *info) {
+  if (!(dt > 0.0)) return fail(PB200_EINVAL, "dt must be > 0");
+  CK(cudaSetDevice(c->cfg.device));
+  if (c->gen) {
+    int rc = pb200_gen_setup(c);      // allocations and uploads happen here, outside the capture
+    if (rc) return fail(rc, "general-grid set-up failed (out of device memory?)");
+  }
+  const unsigned long long sig = graph_signature(c);
+  if (!c->graph_exec || sig != c->graph_sig) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    int rc = pb200_step_begin(c, dt);
+    for (int s = 1; s <= c->nstages && !rc; s++) rc = pb200_stage(c, s);
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemcpyAsync(c->h_red, c->d_red, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+    c->capturing = false;
+    c->in_step = false;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || e2 != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return fail(PB200_ECUDA, "CUDA graph capture of the step failed");
+    }
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->graph_exec = nullptr; return fail(PB200_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    c->graph_sig = sig;
+    c->graph_launches = c->launches;
+  }
+  *c->h_dt = dt;     // read by the first node of the graph
+  CK(cudaEventRecord(c->ev0, c->stream));
+  CK(cudaGraphLaunch(c->graph_exec, c->stream));
+  c->launches = c->graph_launches;
+  c->nprof = 0;
+  if (c->nstages == 1) c->cur = c->stage_out[1];
+  return finish_info(c, info);
+}
+
 extern "C" int pb200_advance_step(pb200_ctx *c, double dt, pb200_step_info *info) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  const bool small = c->nzone < 4L * 1000 * 1000;
+  if ((c->use_graph == 1 || (c->use_graph < 0 && small)) && !c->profiling && c->nstages > 1 && !c->in_step) {
+    for (int q = 0; q < 7; q++) {   // the table check of pb200_step_begin
+      bool need = (q < 3) ? (c->cfg.body_force & PB200_BF_VECTOR) != 0
+                          : ((c->cfg.body_force & PB200_BF_POTENTIAL) != 0 && (q == 3 || q - 4 < c->dev.ndim));
+      if (need && !c->dev.bf_tab[q]) return fail(PB200_EINVAL, "BODY_FORCE table not set (pb200_set_body_force_*)");
+    }
+    return advance_step_graph(c, dt, info);
+  }
   int rc = pb200_step_begin(c, dt);
   if (rc) return rc;
   for (int s = 1; s <= c->nstages; s++) {

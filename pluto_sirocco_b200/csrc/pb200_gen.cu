@@ -37,7 +37,8 @@ T *dalloc(pb200_ctx *c, size_t n) {
 
 }  // namespace
 
-static void fill_ldw(pb200_ctx *c, GenDev &G);
+void pb200_fill_ldw(pb200_ctx *c, pb::GenDev &G);
+static void fill_ldw(pb200_ctx *c, GenDev &G) { pb200_fill_ldw(c, G); }
 
 void pb200_gen_release(pb200_ctx *c) {
   for (void *p : c->gen_allocs) cudaFree(p);
@@ -51,6 +52,7 @@ int pb200_gen_setup(pb200_ctx *c) {
   if (c->gen_ready) return PB200_OK;
   pb200_gen_release(c);
   c->gdev = new GenDev;
+  c->gen_epoch++;
   GenDev &G = *c->gdev;
   memset(&G, 0, sizeof(G));
   G.d = c->dev;
@@ -178,6 +180,13 @@ int pb200_gen_setup(pb200_ctx *c) {
     ok &= (G.A[d] = upload(c, A[d])) != nullptr;
     ok &= (G.dx_dl[d] = upload(c, dxdl[d])) != nullptr;
   }
+  {
+    std::vector<double> cot(n2, 0.0), sn2(n2, 1.0);
+    if (geo == PB200_SPHERICAL && nd > 1)
+      for (int j = 0; j < n2; j++) { cot[j] = 1.0 / tan(x2[j]); sn2[j] = sin(x2[j]); }
+    ok &= (G.cot = upload(c, cot)) != nullptr;
+    ok &= (G.sin2 = upload(c, sn2)) != nullptr;
+  }
   ok &= (G.rt = upload(c, rt)) != nullptr;
   ok &= (G.s = upload(c, s)) != nullptr;
   ok &= (G.sp = upload(c, sp)) != nullptr;
@@ -193,11 +202,13 @@ int pb200_gen_setup(pb200_ctx *c) {
   ok &= (c->gcdt = dalloc<double>(c, nz)) != nullptr;
   // line-driven wind: libm sin/cos tables of the angular bins and of theta, centroids
   {
-    std::vector<double> sa(64), ca(64), st(n2), ct(n2);
+    std::vector<double> sa(64), ca(64), ica(64), st(n2), ct(n2);
     for (int a = 0; a < 64; a++) {
       double theta_angle = (a + 0.5) * (2.0 * 3.14159265358979) / 36.0;     // line_connect.c:563
       sa[a] = sin(theta_angle); ca[a] = cos(theta_angle);
+      ica[a] = 1.0 / sqrt(sa[a] * sa[a] + ca[a] * ca[a]);
     }
+    ok &= (G.ldw.inv_ca = upload(c, ica)) != nullptr;
     for (int j = 0; j < n2; j++) { st[j] = sin(x2[j]); ct[j] = cos(x2[j]); }
     ok &= (G.ldw.sin_a = upload(c, sa)) != nullptr;
     ok &= (G.ldw.cos_a = upload(c, ca)) != nullptr;
@@ -213,7 +224,7 @@ int pb200_gen_setup(pb200_ctx *c) {
 }
 
 // constants of the line-driven-wind problem (cv_idl/init.c:175-197, line_connect.c:831-846)
-static void fill_ldw(pb200_ctx *c, GenDev &G) {
+void pb200_fill_ldw(pb200_ctx *c, pb::GenDev &G) {
   LdwDev &w = G.ldw;
   w.on = c->ldw_on;
   if (!c->ldw_on) return;
@@ -363,44 +374,6 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
 }
 
 // SplitSource() for COOLING BLONDIN (Src/split_source.c:53): BlondinCooling(d->Vc, d, dt, ...)
-extern "C" int pb200_cooling_set_tables(pb200_ctx *c, const double *const tabs[7]) {
-  if (!c || !c->ldw_on) return pb200_fail(PB200_EINVAL, "pb200_cooling_set_tables: call pb200_ldw_enable first");
-  cudaSetDevice(c->cfg.device);
-  size_t n = (size_t)c->dev.sv * sizeof(double);
-  for (int q = 0; q < 7; q++) {
-    if (c->cool_tab[q]) { cudaFree(c->cool_tab[q]); c->cool_tab[q] = nullptr; }
-    if (!tabs || !tabs[q]) continue;
-    if (cudaMalloc(&c->cool_tab[q], n) != cudaSuccess) return pb200_fail(PB200_ENOMEM, "cooling tables: out of device memory");
-    if (cudaMemcpy(c->cool_tab[q], tabs[q], n, cudaMemcpyHostToDevice) != cudaSuccess) return pb200_fail(PB200_ECUDA, "cooling tables: upload failed");
-  }
-  if (cudaDeviceSynchronize() != cudaSuccess) return pb200_fail(PB200_ECUDA, "cooling tables: upload failed");
-  return PB200_OK;
-}
-
-extern "C" int pb200_split_source(pb200_ctx *c, double dt, double g_time) {
-  if (!c || !c->gen || !c->ldw_on)
-    return pb200_fail(PB200_ENOTSUP, "pb200_split_source: COOLING BLONDIN needs a line-driven-wind context (pb200_ldw_enable)");
-  cudaSetDevice(c->cfg.device);
-  int rc = pb200_gen_setup(c);
-  if (rc) return rc;
-  GenDev G = *c->gdev;
-  G.d = c->dev;
-  fill_ldw(c, G);
-  const pb200_ldw_config &L = c->ldw;
-  CoolDev cd;
-  for (int q = 0; q < 7; q++) cd.tab[q] = c->cool_tab[q];
-  cd.dt_share = dt * (L.unit_length / L.unit_velocity);                     // dt * UNIT_TIME
-  cd.unit_pressure = L.unit_density * L.unit_velocity * L.unit_velocity;    // UNIT_PRESSURE
-  cd.lx = L.lx; cd.tx = L.tx; cd.mu = L.mu;
-  cd.analytic_xi = g_time <= 3.0;
-  GenBox dom;
-  for (int d = 0; d < 3; d++) { dom.lo[d] = c->dev.beg[d]; dom.hi[d] = c->dev.end[d]; }
-  long n = (long)(dom.hi[0] - dom.lo[0] + 1) * (dom.hi[1] - dom.lo[1] + 1) * (dom.hi[2] - dom.lo[2] + 1);
-  gen_blondin<<<(unsigned)((n + 63) / 64), 64, 0, c->stream>>>(G, c->V[c->cur], cd, dom);
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return PB200_ECUDA;
-  return PB200_OK;
-}
-
 template <int NV>
 static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
   GenDev G = *c->gdev;
@@ -415,6 +388,10 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   a.dt = c->d_dt; a.red = c->d_red;
   a.w0 = w0; a.wc = wc; a.comb = comb; a.stage = stage; a.dir = 0;
   a.ibmask = c->ib_n ? c->d_ibmask : nullptr;
+  // PB200_GEN_FUSED=0: the one-kernel-per-reference-stage form (gen_states -> gen_riemann -> gen_rhs through
+  // the VP / VM / F arrays); default: one fused kernel per direction (gen_sweep)
+  static const bool fused_env = !(getenv("PB200_GEN_FUSED") && atoi(getenv("PB200_GEN_FUSED")) == 0);
+  const bool fused = fused_env;
   const int T = 128;
   auto blocks = [&](const GenBox &b) {
     long n = (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
@@ -437,18 +414,37 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
       gen_flags<<<ball, T, 0, st>>>(G, a);
       c->launches++;
     }
-    gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
-    c->launches++;
+    if (!fused) {
+      gen_p2c<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
+      c->launches++;
+    }
   }
   c->stage_uploaded = false;
-  for (int dir = 0; dir < D.ndim; dir++) {
+  a.cen = c->gVP;                 // the fused form does not store VP: 3 of its arrays carry the r sweep's centre data
+  a.defer = (fused && c->ldw_on && D.ndim >= 2) ? 1 : 0;
+  for (int dir = 0; dir < D.ndim && fused; dir++) {
+    // one kernel per direction: States -> Riemann -> RightHandSide (+ PrimToCons3D / U0 in the first one)
+    a.dir = dir;
+    const int nx = D.end[0] - D.beg[0] + 1, ny = D.end[1] - D.beg[1] + 1, nzz = D.end[2] - D.beg[2] + 1;
+    if (c->ldw_on && ((dir == 0 && !a.defer) || (dir == 1 && a.defer))) {
+      // VGradCalc (update_stage.c:138-140) + the sums of LineForce(): after the r sweep, whose centre state it needs
+      gen_vgrad<NV><<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom, a.defer);
+      c->launches++;
+    }
+    const int first = (stage == 1 && dir == 0) ? 1 : 0;
+    if (dir == 0) gen_sweep<NV, 128, 1><<<dim3(ny, (nx + 125) / 126, nzz), 128, 0, st>>>(G, a, first);
+    else if (dir == 1) gen_sweep<NV, 16, 32><<<dim3((nx + 31) / 32, (ny + 13) / 14, nzz), 512, 0, st>>>(G, a, first);
+    else gen_sweep<NV, 16, 32><<<dim3((nx + 31) / 32, (nzz + 13) / 14, ny), 512, 0, st>>>(G, a, first);
+    c->launches++;
+  }
+  for (int dir = 0; dir < D.ndim && !fused; dir++) {
     a.dir = dir;
     GenBox bs = dom, bf = dom;
     bs.lo[dir] = D.beg[dir] - 1; bs.hi[dir] = D.end[dir] + 1;     // States(nbeg-1, nend+1)
     bf.lo[dir] = D.beg[dir] - 1; bf.hi[dir] = D.end[dir];         // Riemann(nbeg-1, nend)
     gen_states<NV><<<blocks(bs), T, 0, st>>>(G, a, bs);
     if (dir == 0 && c->ldw_on) {                // VGradCalc (update_stage.c:138-140) + the sums of LineForce()
-      gen_vgrad<<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom);
+      gen_vgrad<NV><<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom, 0);
       c->launches++;
     }
     gen_riemann<NV><<<blocks(bf), T, 0, st>>>(G, a, bf);

@@ -60,6 +60,13 @@ struct pb200_ctx {
   int cur_stage;                          // stage whose Boundary() is being filled (0: outside a step)
   // FLAG_INTERNAL_BOUNDARY zones (Src/int_bound_reset.c): byte mask over all zones (general path) and
   // the list of flagged interior zones (fast path: ib_fix after the last sweep of a stage)
+  // CUDA graph of one whole AdvanceStep (small grids are launch bound: Sod-400 has 7 launches of a few
+  // microseconds per step, the line-driven wind 30): captured on the first pb200_advance_step() and
+  // replayed while nothing that feeds a kernel argument has changed (graph_sig)
+  cudaGraphExec_t graph_exec;
+  unsigned long long graph_sig;
+  int graph_launches, use_graph, gen_epoch;
+  bool capturing;
   bool stage_uploaded;                    // pb200_stage_upload() replaced the array the next stage sweeps
   unsigned char *d_ibmask;
   long *d_iblist;

@@ -194,14 +194,14 @@ def test_ldw_with_blondin_cooling_vs_reference_dumps(Hydro):
         else:
             h.split_source(dt, t); h.advance_step(dt)
         got, ref = h.get_interior()[:nfile], data[n + 1]
-        for nv in (0, 1, 2, 3, 5):
+        # every step within the per-step contract, pressure included: the cooling solve runs the reference's
+        # arithmetic (csrc/pb200_cool.cu: no FMA contraction, IEEE sqrt / division, glibc's exp / pow / log10 bit for
+        # bit), so the Brent iterates are the reference's and the solve is well conditioned (test_glibc_math.py)
+        for nv in (0, 1, 2, 3, 4, 5):
             scale = np.abs(ref[1:4]).max() if 1 <= nv <= 3 else np.abs(ref[nv]).max()
-            lim = TOL_STEP if n % 2 == 0 else 1e-9      # odd steps: the hydro step starts from the cooled pressure
-            assert np.abs(got[nv] - ref[nv]).max() <= lim * scale, (n, nv)
+            assert np.abs(got[nv] - ref[nv]).max() <= TOL_STEP * scale, (n, nv, np.abs(got[nv] - ref[nv]).max() / scale)
         relp = np.abs(got[4] - ref[4]) / ref[4]
-        assert relp.max() <= 2e-4, (n, relp.max())
-        bad += int((relp > 1e-11).sum()); tot += relp.size
-    assert bad <= 0.002 * tot, (bad, tot)
+        assert relp.max() <= 1e-11, (n, relp.max())       # zone by zone (pressure spans 8 decades)
     h.close()
 
 
@@ -237,8 +237,9 @@ def test_blondin_cooling_vs_oracle_with_tables(Hydro):
         relp = np.abs(got[4] - ref[4]) / ref[4]
         changed = np.abs(ref[4] - v[4]) / v[4]
         assert (changed > 1e-3).mean() > 0.2, "test state did not exercise the cooling"
-        assert relp.max() <= 2e-4, relp.max()
-        assert (relp > 1e-11).mean() <= 0.005, (relp > 1e-11).mean()
+        # same input bits, same arithmetic (csrc/pb200_cool.cu: -fmad=false, IEEE sqrt and division, glibc's exp /
+        # pow / log10 restated bit for bit in csrc/glibc_math.cuh): the same sequence of Brent iterates
+        assert np.array_equal(got[4], ref[4]), (relp.max(), int((relp > 0).sum()))
     h.close(); o.close()
 
 
