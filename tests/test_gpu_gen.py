@@ -126,6 +126,56 @@ def test_ldw_per_step_vs_reference_dumps(Hydro, name):
     h.close()
 
 
+def test_ldw_bench_grid_1024x512_vs_oracle(Hydro):
+    """C4 at the size BASELINE.json names: the line-driven wind on the 1024 x 512 r-theta grid of bench.py (same grid
+    ratios, same synthetic 36-angle tables handed over directly, same initial state), 4 free-running RK2 steps of the
+    library against the general oracle: per-step tolerance on every variable and on the dt the step returns (each step
+    starts from the oracle's state, like the per-step tests on the reference dumps)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    from common import LDW_BCS, LDW_PARAMS, LDW_UNITS, ldw_flux_tables
+    n1, n2 = 1024, 512
+    grid = [(0.87, n1, 8.7, "r", 1.005), (0.0, n2, float(np.radians(90.0)), "r", 0.995), (0.0, 1, 1.0)]
+    kw = dict(dimensions=2, grid=grid, geometry="SPHERICAL", gamma=5. / 3., time_stepping="RK2", solver="hll",
+              limiter="VANLEER_LIM", bcs=LDW_BCS, ntracer=1, body_force=1, char_limiting=True,
+              shock_flattening=True, entropy_switch=True, nghost=3)
+    o = GenOracle(**kw)
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    x1, x2 = o.x(0), o.x(1)
+    gm_code = 6.6726e-8 * LDW_PARAMS["CENT_MASS"] / (LDW_UNITS["length"] * LDW_UNITS["velocity"] ** 2)
+    fr, ft, fp = ldw_flux_tables(x1, x2, roundtrip=False)
+    for obj in (o, h):
+        obj.set_body_force_vector(0, (-gm_code / (x1 * x1)).reshape(1, 1, -1))
+        obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
+        obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
+        obj.set_ldw(params=LDW_PARAMS, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)
+    v = bench.ldw_state(x1[3:-3], x2[3:-3], LDW_PARAMS, LDW_UNITS)
+    assert v.shape == (7, 1, n2, n1)
+    vc = o.embed(v)
+    h.set_interior(v)
+    dt = dto = 1e-4
+    for n in range(4):
+        inv, mach, nf = o.advance_step(vc, dto)
+        info = h.advance_step(dt)
+        got, ref = h.get_interior(), vc[o.interior()]
+        # 3.1 M values per step: all of them within 1e-11 and all but a handful within the 1e-12 contract.  The
+        # stragglers (measured: one zone per step, 3e-12 of the velocity scale) sit on the disc / wind interface, where
+        # the density jumps by ten decades and the round-off of the dense neighbour's momentum flux lands on a zone
+        # of 1e-10 the density (same effect, same remark: test_ldw_floors_and_boundaries_vs_oracle)
+        assert rel_err(got[:6], ref[:6]) <= 1e-11, (n, rel_err(got[:6], ref[:6]))
+        nbad = 0
+        for nv in range(6):
+            scale = np.abs(ref[1:4]).max() if 1 <= nv <= 3 else np.abs(ref[nv]).max()
+            nbad += int((np.abs(got[nv] - ref[nv]) > TOL_STEP * scale).sum())
+        assert nbad <= 4, (n, nbad)
+        assert abs(info.invDt_hyp - inv) <= TOL_STEP * inv
+        dt = dto = min(0.4 / inv, 1.1 * dto)
+        h.set_interior(ref)
+    h.close(); o.close()
+
+
 def test_ldw_floors_and_boundaries_vs_oracle(Hydro):
     """User boundaries of cv_idl on a state that triggers the density / pressure floors (also
     inside stage 2, where Uc is re-derived), the mid-plane reset and the hybrid X2_BEG fill."""
