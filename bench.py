@@ -84,6 +84,31 @@ def rt_block(nx, zoff, nglob, gamma=5. / 3., eta=2.0, grav=-0.1):
     return v
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first touch) to the CPUs of the NUMA
+    node the GPU hangs off.  With the buffers of all ranks on one socket every H2D / D2H copy of the other socket's
+    GPUs crosses the inter-socket link, which caps the host-buffer (e2e) rate of an 8-GPU job far below 8 PCIe links.
+    Returns a short description for the JSON line (None when the topology cannot be read)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "numa_node unknown for %s" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "node %d has no CPU this process may use" % node
+        os.sched_setaffinity(0, allowed)
+        return "GPU %d (%s) -> NUMA node %d, %d CPUs" % (index, bdf, node, len(allowed))
+    except Exception as e:      # containers without sysfs, old torch: run unbound
+        return "unbound (%s)" % type(e).__name__
+
+
 def busy_block(nx, seed):
     """"busy" state: the seeded waves + jumps of tests/common.py random_state (shocks, contacts, every limiter and
     solver branch active in every zone neighbourhood), generated on a block of <= 128 zones per direction and
@@ -379,6 +404,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa else "off"
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")     # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -525,7 +551,9 @@ def run_b200(args):
         e2e = {"value": zones_total * ne / (ems * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": ne,
                "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, the RK stages and "
-                      "download pipelined over slabs of x3 planes)"}
+                      "download pipelined over slabs of x3 planes)" if world == 1 else
+                      "per rank: upload of the pinned host d->Vc slab, AdvanceStep with NCCL halo exchange, download, every step",
+               "host_numa": numa}
 
     # ---- the other BASELINE configs, a few steps each (device-resident), reported under "secondary" ----
     nvar_head, shape_head = h.nvar, tuple(h.shape)
@@ -788,6 +816,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=8)

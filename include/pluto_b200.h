@@ -65,6 +65,9 @@ extern "C" {
 
 /* BODY_FORCE bits: same values as Src/pluto.h (VECTOR 4, POTENTIAL 8) are NOT assumed; the
  * shim translates. */
+#define PB200_EOS_IDEAL      0
+#define PB200_EOS_ISOTHERMAL 1
+
 #define PB200_BF_VECTOR    1
 #define PB200_BF_POTENTIAL 2
 
@@ -101,7 +104,10 @@ typedef struct pb200_config {
   int shock_flattening;  /* SHOCK_FLATTENING MULTID (Src/flag_shock.c:81) */
   int entropy_switch;    /* ENTROPY_SWITCH: 0 NO, 1 SELECTIVE, 2 ALWAYS (same values as Src/pluto.h:60-61);
                             NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219, flag_shock.c:146,256) */
-  int reserved[3];
+  int eos;               /* EOS: 0 IDEAL, PB200_EOS_ISOTHERMAL (Src/EOS/Isothermal: no energy equation, NVAR = 4 + NTRACER;
+                            general path; e.g. Test_Problems/LineDrivenWind/cv_iso) */
+  int reserved[2];
+  double iso_sound_speed;/* g_isoSoundSpeed (EOS ISOTHERMAL) */
 } pb200_config;
 
 /* What one AdvanceStep leaves in timeStep / globals (Src/structs.h:372, globals.h). */
@@ -130,6 +136,22 @@ int  pb200_shape(const pb200_ctx *ctx, int tot[3], int *nvar);
  * xr-xl); default = uniform from xbeg/xend (Src/set_grid.c:405-412).  Needed before the
  * first step only for non-uniform grids. */
 int  pb200_set_grid(pb200_ctx *ctx, int dir, const double *xl, const double *xr, const double *dx);
+
+/* Geometry of the general (curvilinear / non-uniform) path.  By default the library evaluates the formulas of
+ * Src/set_geometry.c:83-254 from xl / xr / dx itself (with the host's libm, bit-identical to the reference); a caller
+ * that owns a Grid hands over the reference's own arrays instead, so that whatever the host set up is what the kernels
+ * use.  All arrays in the reference's layout, ghost zones included:
+ *   dV[NX3_TOT][NX2_TOT][NX1_TOT]                         grid->dV
+ *   A[0] [NX3_TOT][NX2_TOT][NX1_TOT+1]  (first entry = index -1 along x1)   &grid->A[IDIR][0][0][-1]
+ *   A[1] [NX3_TOT][NX2_TOT+1][NX1_TOT]  (first row   = index -1 along x2)   &grid->A[JDIR][0][-1][0]
+ *   A[2] [NX3_TOT+1][NX2_TOT][NX1_TOT]  (first plane = index -1 along x3)   &grid->A[KDIR][-1][0][0]
+ *   dx_dl[d][NX2_TOT][NX1_TOT]                            grid->dx_dl[d]
+ *   rt[NX1_TOT], s[NX2_TOT], sp[NX2_TOT]                  grid->rt, grid->s, grid->sp
+ * (Src/set_geometry.c:49-61).  Call before the first step. */
+typedef struct pb200_geometry {
+  const double *dV, *A[3], *dx_dl[3], *rt, *s, *sp;
+} pb200_geometry;
+int  pb200_set_geometry(pb200_ctx *ctx, const pb200_geometry *geo);
 
 /* BODY_FORCE tables.  The reference calls the user's BodyForceVector(v, g, x1, x2, x3) per zone
  * and sweep (Src/MHD/rhs_source.c:256,367) and BodyForcePotential(x1, x2, x3) at zone centres
@@ -164,6 +186,7 @@ typedef struct pb200_ldw_config {
   double mu, krad, alpharad;      /* g_inputParam[MU], [KRAD], [ALPHARAD]; 999/999 selects the M(t) fit: pb200_ldw_set_mfit() */
   double dfloor, rho_0, rho_alpha, cent_mass, disk_mdot;   /* g_inputParam[DFLOOR], [RHO_0], [RHO_ALPHA], [CENT_MASS], [DISK_MDOT] (cgs) */
   double lx, tx;                  /* g_inputParam[L_star]*[f_x], g_inputParam[T_x] (BLONDIN cooling) */
+  double t_iso;                   /* EOS ISOTHERMAL: g_inputParam[T_ISO], the temperature LineForce() uses (line_connect.c:851-855) */
 } pb200_ldw_config;
 int  pb200_ldw_enable(pb200_ctx *ctx, const pb200_ldw_config *ldw);
 int  pb200_ldw_set_fluxes(pb200_ctx *ctx, const double *flux_r, const double *flux_t, const double *flux_p);

@@ -33,7 +33,9 @@ def build(cfg: str, force: bool = False) -> Path:
         return exe
     out.mkdir(parents=True, exist_ok=True)
     s = build_ref.REF / "Src"
-    incs = ["-I%s" % wd, "-I%s" % s, "-I%s" % (s / "HD"), "-I%s" % (s / "EOS" / "Ideal"),
+    import re
+    eos = "Isothermal" if re.search(r"^#define\s+EOS\s+ISOTHERMAL", (wd / "definitions.h").read_text(), re.M) else "Ideal"
+    incs = ["-I%s" % wd, "-I%s" % s, "-I%s" % (s / "HD"), "-I%s" % (s / "EOS" / eos),
             "-I%s" % (s / "States"), "-I%s" % (s / "Math_Tools"), "-I%s" % (ROOT / "include")]
     obj = out / "pluto_shim.o"
     r = subprocess.run(["gcc", "-c", "-O2", "-std=gnu17"] + incs + [str(shim), "-o", str(obj)],

@@ -30,7 +30,7 @@ class Config(C.Structure):
                 ("small_pressure", C.c_double), ("xbeg", C.c_double * 3),
                 ("xend", C.c_double * 3), ("device", C.c_int), ("body_force", C.c_int),
                 ("char_limiting", C.c_int), ("shock_flattening", C.c_int), ("entropy_switch", C.c_int),
-                ("reserved", C.c_int * 3)]
+                ("eos", C.c_int), ("reserved", C.c_int * 2), ("iso_sound_speed", C.c_double)]
 
 
 class LdwConfig(C.Structure):
@@ -38,7 +38,7 @@ class LdwConfig(C.Structure):
                 ("unit_velocity", C.c_double), ("unit_density", C.c_double), ("mu", C.c_double),
                 ("krad", C.c_double), ("alpharad", C.c_double), ("dfloor", C.c_double), ("rho_0", C.c_double),
                 ("rho_alpha", C.c_double), ("cent_mass", C.c_double), ("disk_mdot", C.c_double),
-                ("lx", C.c_double), ("tx", C.c_double)]
+                ("lx", C.c_double), ("tx", C.c_double), ("t_iso", C.c_double)]
 
 
 class StepInfo(C.Structure):
@@ -59,6 +59,7 @@ SYMBOLS = {
     "pb200_destroy": (None, [_P]),
     "pb200_shape": (C.c_int, [_P, C.POINTER(C.c_int * 3), C.POINTER(C.c_int)]),
     "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pb200_set_geometry": (C.c_int, [_P, _P]),
     "pb200_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_cooling_set_tables": (C.c_int, [_P, C.POINTER(C.c_void_p * 7)]),

@@ -39,6 +39,7 @@ struct LdwDev {
   double UL, UV, UD;                        // UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY
   double kelvin_mu;                         // KELVIN * mu
   double krad, alpharad;
+  double t_iso;                             // > 0: EOS ISOTHERMAL, the temperature of LineForce() is g_inputParam[T_ISO]
   int mpoints;                              // > 0: force multiplier from the per-zone M(t) fit (KRAD = ALPHARAD = 999)
   const double *t_fit, *m_fit;              // log10(t) [mpoints]; log10(M) [mpoints][k][j][i]
   double sigma_e, unit_acc;                 // sigma_T/amu/1.18 ; UNIT_ACCELERATION
@@ -48,6 +49,9 @@ struct LdwDev {
 struct GenDev {
   Dev d;
   int nvar, geometry, limiter, char_lim, flatten, entropy, solver;
+  // EOS ISOTHERMAL (Src/EOS/Isothermal/eos.c): no energy equation, NFLX = 4, scalars start at index 4, p = cs2 rho
+  int iso;
+  double cs2;                          // g_isoSoundSpeed^2
   // 1-D grid arrays per direction (np_tot entries): grid->x, xr, dx, inv_dx and PLM_Coeffs
   const double *x[3], *xr[3], *dx[3], *inv_dx[3];
   const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
@@ -79,6 +83,11 @@ struct GenArgs {
   double *cen;
   int defer;
 };
+
+// index of the pressure in a per-zone vector of NV variables; with EOS ISOTHERMAL there is none (the expressions that
+// use it are never evaluated then; the clamp only keeps the constant index inside the array for NV = 4)
+template <int NV> __host__ __device__ constexpr int pidx() { return NV > 4 ? 4 : 0; }
+PB_D int gen_nflx(const GenDev &g) { return g.iso ? 4 : 5; }
 
 PB_D double gen_A(const GenDev &g, int dir, int k, int j, int i) {
   return __ldg(g.A[dir] + g.Aoff[dir] + (long)k * g.Ask[dir] + (long)j * g.Asj[dir] + i);
@@ -147,7 +156,8 @@ static __global__ void gen_shock(GenDev g, GenArgs a, GenBox b) {
   const long o = (long)k * d.sk + (long)j * d.sj + i;
   const long st[3] = {1, d.sj, d.sk};
   const int idx[3] = {i, j, k};
-  const double *pt = a.V + iPRS * d.sv;
+  // EOS ISOTHERMAL: pt = cs2 rho (flag_shock.c:138-139); the same factor on every zone of the stencil
+  auto pt = [&](long q) { return g.iso ? a.V[q] * g.cs2 : a.V[iPRS * d.sv + q]; };
   double divv = 0.0;
   for (int dir = 0; dir < d.ndim; dir++) {
     const double *vx = a.V + (1 + dir) * d.sv;
@@ -163,10 +173,10 @@ static __global__ void gen_shock(GenDev g, GenArgs a, GenBox b) {
   if (g.geometry != GEO_CARTESIAN) divv = divv / __ldg(g.dV + o);
   unsigned char sh = 0;
   if (divv < 0.0) {
-    double pt_min = pt[o], gradp = 0.0;
+    double pt_min = pt(o), gradp = 0.0;
     for (int dir = 0; dir < d.ndim; dir++) {
-      pt_min = fmin(pt_min, fmin(pt[o + st[dir]], pt[o - st[dir]]));
-      double dp = fabs(pt[o + st[dir]] - pt[o - st[dir]]);
+      pt_min = fmin(pt_min, fmin(pt(o + st[dir]), pt(o - st[dir])));
+      double dp = fabs(pt(o + st[dir]) - pt(o - st[dir]));
       gradp = (dir == 0) ? dp : gradp + dp;
     }
     sh = (gradp > 5.0 * pt_min) ? 1 : 0;      // EPS_PSHOCK_FLATTEN, flag_shock.c:69-70
@@ -210,9 +220,9 @@ static __global__ void gen_p2c(GenDev g, GenArgs a, GenBox b) {
   const double rho = v[iRHO];
   u[0] = rho; u[1] = rho * v[1]; u[2] = rho * v[2]; u[3] = rho * v[3];
   double k2 = v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-  u[4] = 0.5 * rho * k2 + v[4] / d.gas.gmm1;
+  if (!g.iso) u[pidx<NV>()] = 0.5 * rho * k2 + v[pidx<NV>()] / d.gas.gmm1;
 #pragma unroll
-  for (int nv = NFLX; nv < NV; nv++) u[nv] = rho * v[nv];
+  for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) u[nv] = rho * v[nv];
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) { a.U[nv * d.sv + o] = u[nv]; a.U0[nv * d.sv + o] = u[nv]; }
 }
@@ -250,13 +260,14 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) {
         int kind = g.limiter;
-        if (kind == LIM_DEFAULT) kind = (nv == iRHO || nv >= NFLX) ? LIM_MC : (nv == iPRS ? LIM_MINMOD : LIM_VANLEER);
+        if (kind == LIM_DEFAULT) kind = (nv == iRHO || nv >= gen_nflx(g)) ? LIM_MC : ((!g.iso && nv == iPRS) ? LIM_MINMOD : LIM_VANLEER);
         dvl[nv] = gen_lim(kind, uniform, dvp[nv], dvm[nv], cp, cm);
       }
     }
   } else {
     // SoundSpeed2, PrimEigenvectors (HD/eigenv.c:92-200), PrimToChar (:575-616)
-    const double a2 = d.gas.gamma * v[iPRS] / v[iRHO];
+    constexpr int P = pidx<NV>();
+    const double a2 = g.iso ? g.cs2 : d.gas.gamma * v[P] / v[iRHO];
     const double cs = sqrt(a2), rhocs = v[iRHO] * cs, rho_cs = v[iRHO] / cs;
     const double L0p = 1.0 / rhocs, L2p = -1.0 / a2;
     // dvp/dvm of the normal, tangent, bitangent velocity: select without dynamic register indexing
@@ -267,12 +278,20 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
     const double mt_ = dir == 0 ? dvm[2] : (dir == 1 ? dvm[3] : dvm[1]);
     const double mb_ = dir == 0 ? dvm[3] : (dir == 1 ? dvm[1] : dvm[2]);
     double dwp[NFLX], dwm[NFLX], dwl[NFLX];
-    dwm[0] = -1.0 * mn + L0p * dvm[iPRS]; dwm[1] = 1.0 * mn + L0p * dvm[iPRS];
-    dwm[2] = dvm[iRHO] + L2p * dvm[iPRS]; dwm[3] = mt_; dwm[4] = mb_;
-    dwp[0] = -1.0 * pn + L0p * dvp[iPRS]; dwp[1] = 1.0 * pn + L0p * dvp[iPRS];
-    dwp[2] = dvp[iRHO] + L2p * dvp[iPRS]; dwp[3] = pt_; dwp[4] = pb_;
+    const int nf = gen_nflx(g);
+    if (!g.iso) {
+      dwm[0] = -1.0 * mn + L0p * dvm[P]; dwm[1] = 1.0 * mn + L0p * dvm[P];
+      dwm[2] = dvm[iRHO] + L2p * dvm[P]; dwm[3] = mt_; dwm[4] = mb_;
+      dwp[0] = -1.0 * pn + L0p * dvp[P]; dwp[1] = 1.0 * pn + L0p * dvp[P];
+      dwp[2] = dvp[iRHO] + L2p * dvp[P]; dwp[3] = pt_; dwp[4] = pb_;
+    } else {   // eigenv.c:182-196 (LL[0][RHO] = LL[1][RHO] = 1/rho_cs), PrimToChar eigenv.c:600-605
+      const double Lr = 1.0 / rho_cs;
+      dwm[0] = Lr * dvm[iRHO] + -1.0 * mn; dwm[1] = Lr * dvm[iRHO] + 1.0 * mn; dwm[2] = mt_; dwm[3] = mb_; dwm[4] = 0.0;
+      dwp[0] = Lr * dvp[iRHO] + -1.0 * pn; dwp[1] = Lr * dvp[iRHO] + 1.0 * pn; dwp[2] = pt_; dwp[3] = pb_; dwp[4] = 0.0;
+    }
 #pragma unroll
     for (int q = 0; q < NFLX; q++) {
+      if (q >= nf) { dwl[q] = 0.0; continue; }
       if (fl & GF_FLAT) dwl[q] = 0.0;
       else if (fl & GF_MINMOD) dwl[q] = gen_lim(LIM_MINMOD, uniform, dwp[q], dwm[q], cp, cm);
       else if (g.limiter == LIM_DEFAULT) {
@@ -284,22 +303,30 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
     }
     // dv = sum_k dw_lim[k] R[nv][k]: the reference adds all five products, zeros included
     double dc[NFLX];
-    dc[iRHO] = (((dwl[0] * (0.5 * rho_cs) + dwl[1] * (0.5 * rho_cs)) + dwl[2] * 1.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
-    dc[iPRS] = (((dwl[0] * (0.5 * rhocs) + dwl[1] * (0.5 * rhocs)) + dwl[2] * 0.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
-    const double dcn = dwl[0] * -0.5 + dwl[1] * 0.5, dct = dwl[3], dcb = dwl[4];
+    double dcn, dct, dcb;
+    if (!g.iso) {
+      dc[iRHO] = (((dwl[0] * (0.5 * rho_cs) + dwl[1] * (0.5 * rho_cs)) + dwl[2] * 1.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
+      dc[iPRS] = (((dwl[0] * (0.5 * rhocs) + dwl[1] * (0.5 * rhocs)) + dwl[2] * 0.0) + dwl[3] * 0.0) + dwl[4] * 0.0;
+      dcn = dwl[0] * -0.5 + dwl[1] * 0.5; dct = dwl[3]; dcb = dwl[4];
+    } else {   // R[RHO][0,1] = rho_cs/2, R[VXn][0,1] = -+1/2, R[VXt][2] = R[VXb][3] = 1 (eigenv.c:175-178); 4 products each
+      dc[iRHO] = ((dwl[0] * (0.5 * rho_cs) + dwl[1] * (0.5 * rho_cs)) + dwl[2] * 0.0) + dwl[3] * 0.0;
+      dc[iPRS] = 0.0;
+      dcn = ((dwl[0] * -0.5 + dwl[1] * 0.5) + dwl[2] * 0.0) + dwl[3] * 0.0; dct = dwl[2]; dcb = dwl[3];
+    }
     dc[1] = dir == 0 ? dcn : (dir == 1 ? dcb : dct);
     dc[2] = dir == 0 ? dct : (dir == 1 ? dcn : dcb);
     dc[3] = dir == 0 ? dcb : (dir == 1 ? dct : dcn);
 #pragma unroll
-    for (int nv = 0; nv < NFLX; nv++) {
+    for (int nv = 0; nv < (NV < NFLX ? NV : NFLX); nv++) {
+      if (nv >= nf) continue;
       if (dvp[nv] * dvm[nv] > 0.0) {
         double d2v = absmin(cp * dvp[nv], cm * dvm[nv]);
         dvl[nv] = (d2v * dc[nv] > 0.0) ? absmin(d2v, dc[nv]) : 0.0;
       } else dvl[nv] = 0.0;
     }
 #pragma unroll
-    for (int nv = NFLX; nv < NV; nv++)
-      dvl[nv] = gen_lim(g.limiter == LIM_DEFAULT ? LIM_MC : g.limiter, uniform, dvp[nv], dvm[nv], cp, cm);
+    for (int nv = 4; nv < NV; nv++)
+      if (nv >= nf) dvl[nv] = gen_lim(g.limiter == LIM_DEFAULT ? LIM_MC : g.limiter, uniform, dvp[nv], dvm[nv], cp, cm);
   }
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
@@ -326,6 +353,77 @@ static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   }
 }
 
+// ---- EOS ISOTHERMAL Riemann solvers: HD/tvdlf.c:100-130, HD/hll.c:72-96, HD/hllc.c:119-178 with the
+// "#if EOS == ISOTHERMAL" star state (hllc.c:137-150), fluxes.c:36-48 (p = cs2 rho), hll_speed.c:76-90.
+// q: (rho, v_n, v_t, v_b, scalars...) in sweep-local order; f[0..3] mass and momentum fluxes (no pressure in f[1]).
+// Written with the reference's own operations (plain divisions): the isothermal problems are small grids.
+template <int NV>
+PB_D double riemann_iso(const double (&vL)[NV], const double (&vR)[NV], double cs2, int solver, bool force_hll,
+                        double (&f)[NV], double &prs, double &cmax) {
+  double uL[4], uR[4], fL[4], fR[4];
+  uL[0] = vL[0]; uL[1] = vL[0] * vL[1]; uL[2] = vL[0] * vL[2]; uL[3] = vL[0] * vL[3];
+  uR[0] = vR[0]; uR[1] = vR[0] * vR[1]; uR[2] = vR[0] * vR[2]; uR[3] = vR[0] * vR[3];
+  fL[0] = uL[1]; fL[1] = uL[1] * vL[1]; fL[2] = uL[2] * vL[1]; fL[3] = uL[3] * vL[1];
+  fR[0] = uR[1]; fR[1] = uR[1] * vR[1]; fR[2] = uR[2] * vR[1]; fR[3] = uR[3] * vR[1];
+  const double pL = cs2 * vL[0], pR = cs2 * vR[0];
+  double machv;
+  if (solver == SOLVER_TVDLF) {
+    const double vn = 0.5 * (fabs(vL[1]) + fabs(vR[1]));
+    const double a = sqrt(cs2);
+    const double cmin = vn - a, cmaxv = vn + a;
+    cmax = fmax(fabs(cmaxv), fabs(cmin));
+    machv = fabs(vn) / sqrt(cs2);
+#pragma unroll
+    for (int nv = 0; nv < 4; nv++) f[nv] = 0.5 * (fL[nv] + fR[nv] - cmax * (uR[nv] - uL[nv]));
+    prs = 0.5 * (pL + pR);
+  } else {
+    const double aL = sqrt(cs2), aR = sqrt(cs2);
+    const double SL = fmin(vL[1] - aL, vR[1] - aR), SR = fmax(vL[1] + aL, vR[1] + aR);
+    double scrh = fabs(vL[1]) + fabs(vR[1]);
+    scrh /= aL + aR;
+    machv = scrh;
+    cmax = fmax(fabs(SL), fabs(SR));
+    if (SL > 0.0) {
+#pragma unroll
+      for (int nv = 0; nv < 4; nv++) f[nv] = fL[nv];
+      prs = pL;
+    } else if (SR < 0.0) {
+#pragma unroll
+      for (int nv = 0; nv < 4; nv++) f[nv] = fR[nv];
+      prs = pR;
+    } else if (solver == SOLVER_HLL || force_hll) {
+      scrh = 1.0 / (SR - SL);
+#pragma unroll
+      for (int nv = 0; nv < 4; nv++) {
+        f[nv] = SL * SR * (uR[nv] - uL[nv]) + SR * fL[nv] - SL * fR[nv];
+        f[nv] *= scrh;
+      }
+      prs = (SR * pL - SL * pR) * scrh;
+    } else {
+      scrh = 1.0 / (SR - SL);
+      const double rho = (SR * uR[0] - SL * uL[0] - fR[0] + fL[0]) * scrh;
+      const double mx = (SR * uR[1] - SL * uL[1] - fR[1] + fL[1]) * scrh;
+      double vs = (SR * fL[0] - SL * fR[0] + SR * SL * (uR[0] - uL[0]));
+      vs *= scrh;
+      vs /= rho;
+      if (vs >= 0.0) {
+        const double us[4] = {rho, mx, rho * vL[2], rho * vL[3]};
+#pragma unroll
+        for (int nv = 0; nv < 4; nv++) f[nv] = fL[nv] + SL * (us[nv] - uL[nv]);
+        prs = pL;
+      } else {
+        const double us[4] = {rho, mx, rho * vR[2], rho * vR[3]};
+#pragma unroll
+        for (int nv = 0; nv < 4; nv++) f[nv] = fR[nv] + SR * (us[nv] - uR[nv]);
+        prs = pR;
+      }
+    }
+  }
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) f[nv] = f[0] * (f[0] > 0.0 ? vL[nv] : vR[nv]);    // adv_flux.c:61-72
+  return machv;
+}
+
 // ---- Riemann solver + AdvectFlux at the face between zone n and n+1 -------------------------
 // vLg / vRg: left / right state in GLOBAL variable order; F: flux in global order, F[NV] = pressure, F[NV+1] = cmax
 template <int NV>
@@ -338,6 +436,19 @@ PB_D double gen_face(const GenDev &g, int dir, const double (&vLg)[NV], const do
   vL[3] = dir == 0 ? vLg[3] : (dir == 1 ? vLg[1] : vLg[2]); vR[3] = dir == 0 ? vRg[3] : (dir == 1 ? vRg[1] : vRg[2]);
 #pragma unroll
   for (int nv = 4; nv < NV; nv++) { vL[nv] = vLg[nv]; vR[nv] = vRg[nv]; }
+  if (g.iso) {
+    double fl[NV], prs, cmx;
+    const double mv = riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
+    F[0] = fl[0];
+    F[1] = dir == 0 ? fl[1] : (dir == 1 ? fl[3] : fl[2]);
+    F[2] = dir == 0 ? fl[2] : (dir == 1 ? fl[1] : fl[3]);
+    F[3] = dir == 0 ? fl[3] : (dir == 1 ? fl[2] : fl[1]);
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) F[nv] = fl[nv];
+    F[NV] = prs;
+    F[NV + 1] = cmx;
+    return mv;
+  }
   Face<NV> Ff;
   Ratio mach;
   mach.init();
@@ -418,7 +529,7 @@ static __global__ void gen_ldw_mask(LdwDev w, long nz, unsigned long long *mask)
 struct LdwZone { double S, kS; };
 PB_D LdwZone gen_ldw_zone(const LdwDev &w, double rho_code, double prs_code) {
   const double rho = rho_code * w.UD;
-  const double T = prs_code / rho_code * w.kelvin_mu;
+  const double T = w.t_iso > 0.0 ? w.t_iso : prs_code / rho_code * w.kelvin_mu;    // EOS ISOTHERMAL: T_ISO (line_connect.c:851-855)
   const double v_th = sqrt((2.0 * 1.3806505e-16 * T) / 1.67262171e-24);
   LdwZone z;
   z.S = w.sigma_e * rho * v_th;
@@ -498,10 +609,10 @@ static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenB
     prs_c = a.cen[nz + o];
   } else {
     rho_c = 0.5 * (a.VP[iRHO * nz + o] + a.VM[iRHO * nz + o]);
-    prs_c = 0.5 * (a.VP[iPRS * nz + o] + a.VM[iPRS * nz + o]);
+    prs_c = g.iso ? 0.0 : 0.5 * (a.VP[iPRS * nz + o] + a.VM[iPRS * nz + o]);
   }
   const LdwZone zr = gen_ldw_zone(w, rho_c, prs_c);
-  const LdwZone zt = gen_ldw_zone(w, a.V[iRHO * nz + o], a.V[iPRS * nz + o]);
+  const LdwZone zt = gen_ldw_zone(w, a.V[iRHO * nz + o], g.iso ? 0.0 : a.V[iPRS * nz + o]);
   const double coef = w.sigma_e / (2.99792458e10 * w.unit_acc);
   double g_r = 0.0, g_t = 0.0;
   // per zone: the reciprocals the 36 bins share (<= 1 ulp each against the reference's divisions)
@@ -571,28 +682,34 @@ static __global__ void gen_ldw_floor(GenDev g, GenArgs a, int update_U) {
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) v[nv] = a.V[nv * d.sv + o];
   bool convert = false;
+  constexpr int P = pidx<NV>();
+  const bool en = !g.iso;                   // the "#if EOS != ISOTHERMAL" blocks of init.c
+  const int TRC = gen_nflx(g);
   if (v[iRHO] < w.dfloor) {
     if (v[iRHO] < 0.0) v[iRHO] = w.dfloor;
-    const double cs = sqrt(d.gas.gamma * v[iPRS] / v[iRHO]);
+    const double cs = en ? sqrt(d.gas.gamma * v[P] / v[iRHO]) : 0.0;
     const double dfact = v[iRHO] / w.dfloor;
     v[iRHO] = w.dfloor;
     v[1] = dfact * v[1]; v[2] = dfact * v[2]; v[3] = dfact * v[3];
-    v[iPRS] = (cs * cs) * v[iRHO] / d.gas.gamma;
-    double temp = v[iPRS] / v[iRHO] * w.kelvin_mu;
-    if (temp < w.tfloor) { temp = w.tfloor; v[iPRS] = v[iRHO] * temp / w.kelvin_mu; }
-    v[NFLX] = 0.0;
+    if (en) {
+      v[P] = (cs * cs) * v[iRHO] / d.gas.gamma;
+      double temp = v[P] / v[iRHO] * w.kelvin_mu;
+      if (temp < w.tfloor) { temp = w.tfloor; v[P] = v[iRHO] * temp / w.kelvin_mu; }
+    }
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) if (nv == TRC) v[nv] = 0.0;
     convert = true;
   }
-  if (v[iPRS] < w.pfloor) { v[iPRS] = w.pfloor; convert = true; }
+  if (en && v[P] < w.pfloor) { v[P] = w.pfloor; convert = true; }
   if (convert && update_U) {
     const double rho = v[iRHO];
     a.U[o] = rho;
     a.U[1 * d.sv + o] = rho * v[1];
     a.U[2 * d.sv + o] = rho * v[2];
     a.U[3 * d.sv + o] = rho * v[3];
-    a.U[4 * d.sv + o] = 0.5 * rho * (v[1] * v[1] + v[2] * v[2] + v[3] * v[3]) + v[iPRS] / d.gas.gmm1;
+    if (en) a.U[4 * d.sv + o] = 0.5 * rho * (v[1] * v[1] + v[2] * v[2] + v[3] * v[3]) + v[P] / d.gas.gmm1;
 #pragma unroll
-    for (int nv = NFLX; nv < NV; nv++) a.U[nv * d.sv + o] = rho * v[nv];
+    for (int nv = 4; nv < NV; nv++) if (nv >= TRC) a.U[nv * d.sv + o] = rho * v[nv];
   }
   if (j == d.end[1]) {
     const double r = __ldg(w.xgc1 + i), theta = __ldg(w.xgc2 + j);
@@ -602,9 +719,12 @@ static __global__ void gen_ldw_floor(GenDev g, GenArgs a, int update_U) {
     v[iRHO] = rho_mid;
     v[1] = 0.0;
     v[3] = sqrt(w.gm_code / r) * sth;
-    const double temp = w.teff_wd * pow(w.r_WD / rcyl, 0.75) * pow(1.0 - sqrt(w.r_WD / rcyl), 0.25);
-    v[iPRS] = rho_mid * temp / w.kelvin_mu;
-    v[NFLX] = 1.0;
+    if (en) {
+      const double temp = w.teff_wd * pow(w.r_WD / rcyl, 0.75) * pow(1.0 - sqrt(w.r_WD / rcyl), 0.25);
+      v[P] = rho_mid * temp / w.kelvin_mu;
+    }
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) if (nv == TRC) v[nv] = 1.0;
     convert = true;
   }
   if (convert) {
@@ -636,7 +756,7 @@ static __global__ void gen_ldw_side(GenDev g, double *V, int side) {
   else {
     V[2 * d.sv + o] *= -1.0;
     V[o] = V[ob];
-    V[iPRS * d.sv + o] = V[iPRS * d.sv + ob];
+    if (!g.iso) V[iPRS * d.sv + o] = V[iPRS * d.sv + ob];
   }
 }
 
@@ -704,17 +824,19 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
         gv[0] = g.ldw.gline[o]; gv[1] = g.ldw.gline[nz + o]; gv[2] = 0.0;   // LineForce() sums taken by gen_vgrad
       }
       const double gd = dir == 0 ? gv[0] : (dir == 1 ? gv[1] : gv[2]);
+      constexpr int P = pidx<NV>();
+      const bool en = !g.iso;                // IF_ENERGY (rhs_source.c)
       rn += dt * vg[iRHO] * gd;
-      rhs[iPRS] += dt * 0.5 * (frp + frm) * gd;
+      if (en) rhs[P] += dt * 0.5 * (frp + frm) * gd;
       if (dir == 0 && d.ndim == 1) {
         rhs[2] += dt * vg[iRHO] * gv[1];
-        rhs[iPRS] += dt * vg[iRHO] * vg[2] * gv[1];
+        if (en) rhs[P] += dt * vg[iRHO] * vg[2] * gv[1];
         rhs[3] += dt * vg[iRHO] * gv[2];
-        rhs[iPRS] += dt * vg[iRHO] * vg[3] * gv[2];
+        if (en) rhs[P] += dt * vg[iRHO] * vg[3] * gv[2];
       }
       if (dir == 1 && d.ndim == 2) {
         rhs[3] += dt * vg[iRHO] * gv[2];
-        rhs[iPRS] += dt * vg[iRHO] * vg[3] * gv[2];
+        if (en) rhs[P] += dt * vg[iRHO] * vg[3] * gv[2];
       }
     }
     if (dir == 0) rhs[1] = rn; else if (dir == 1) rhs[2] = rn; else rhs[3] = rn;
@@ -722,7 +844,7 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
     if (ldw_mode == 2) {   // the r sweep's line force (rhs_source.c:284-297) with that sweep's centre density and mass flux
       const double g_r = g.ldw.gline[o];
       rhs[1] += dt * a.cen[o] * g_r;
-      rhs[iPRS] += dt * a.cen[2 * nz + o] * g_r;
+      if (!g.iso) rhs[pidx<NV>()] += dt * a.cen[2 * nz + o] * g_r;
     }
     if (a.ibmask && a.ibmask[o]) {   // InternalBoundaryReset(), rhs.c:416-417
 #pragma unroll
@@ -845,16 +967,16 @@ static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, i
     double cdt_c = 0.0, mf = 0.0;
     const int ldw_mode = (a.defer && g.ldw.on) ? (dir == 0 ? 1 : (dir == 1 ? 2 : 0)) : 0;
     gen_zone_rhs<NV>(g, a, dir, i, j, k, o, fp, fm, pp, pm, cp_, cm_, vg, rhs, cdt_c, inv_max, ldw_mode, &mf);
-    if (ldw_mode == 1) { a.cen[o] = vg[iRHO]; a.cen[nz + o] = vg[iPRS]; a.cen[2 * nz + o] = mf; }
+    if (ldw_mode == 1) { a.cen[o] = vg[iRHO]; a.cen[nz + o] = vg[pidx<NV>()]; a.cen[2 * nz + o] = mf; }
     if (first) {
       // PrimToCons3D + RBoxCopy(U0): exact restatement (no reciprocal sharing), these values seed U0
       double u[NV];
       const double rho = v[iRHO];
       u[0] = rho; u[1] = rho * v[1]; u[2] = rho * v[2]; u[3] = rho * v[3];
       double k2 = v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-      u[4] = 0.5 * rho * k2 + v[4] / d.gas.gmm1;
+      if (!g.iso) u[pidx<NV>()] = 0.5 * rho * k2 + v[pidx<NV>()] / d.gas.gmm1;
 #pragma unroll
-      for (int nv = NFLX; nv < NV; nv++) u[nv] = rho * v[nv];
+      for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) u[nv] = rho * v[nv];
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) { a.U0[nv * nz + o] = u[nv]; a.U[nv * nz + o] = u[nv] + rhs[nv]; }
     } else {
@@ -900,21 +1022,26 @@ static __global__ void gen_finish(GenDev g, GenArgs a, GenBox b) {
     const double rho = u[0], tau = 1.0 / u[0];
     v[0] = rho; v[1] = u[1] * tau; v[2] = u[2] * tau; v[3] = u[3] * tau;
     const double kin = 0.5 * m2 / u[0];
-    if (u[4] < 0.0) { u[4] = gs.small_pr / gs.gmm1 + kin; bad = true; }
+    constexpr int P = pidx<NV>();
+    if (g.iso) {
+      // mappers.c with EOS ISOTHERMAL: no energy, no pressure
+    } else {
+    if (u[P] < 0.0) { u[P] = gs.small_pr / gs.gmm1 + kin; bad = true; }
     if (g.entropy && (fl & GF_ENTROPY)) {
       const double rhog1 = pow(rho, gs.gmm1);
-      v[4] = u[NV - 1] * rhog1;
-      if (v[4] < 0.0) { v[4] = gs.small_pr; bad = true; }
-      u[4] = v[4] / gs.gmm1 + kin;
+      v[P] = u[NV - 1] * rhog1;
+      if (v[P] < 0.0) { v[P] = gs.small_pr; bad = true; }
+      u[P] = v[P] / gs.gmm1 + kin;
     } else {
-      v[4] = gs.gmm1 * (u[4] - kin);
-      if (v[4] < 0.0) { v[4] = gs.small_pr; u[4] = v[4] / gs.gmm1 + kin; bad = true; }
-      if (g.entropy) u[NV - 1] = v[4] / pow(rho, gs.gmm1);
+      v[P] = gs.gmm1 * (u[P] - kin);
+      if (v[P] < 0.0) { v[P] = gs.small_pr; u[P] = v[P] / gs.gmm1 + kin; bad = true; }
+      if (g.entropy) u[NV - 1] = v[P] / pow(rho, gs.gmm1);
+    }
     }
 #pragma unroll
-    for (int nv = NFLX; nv < NV; nv++) v[nv] = u[nv] * tau;
+    for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) v[nv] = u[nv] * tau;
     if (bad) { fl |= GF_C2P_FAIL; nfail = 1; a.flag[o] = fl; }
-    nan = !(v[4] == v[4]) || !(v[0] == v[0]);
+    nan = !(v[1] == v[1]) || !(v[0] == v[0]) || (!g.iso && !(v[P] == v[P]));
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) { a.U[nv * nz + o] = u[nv]; a.V[nv * nz + o] = v[nv]; }
     if (a.stage == 1 && d.ndim > 1) cmaxv = a.cdt[o];

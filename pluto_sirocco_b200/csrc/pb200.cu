@@ -67,8 +67,12 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
     return fail(PB200_ENOTSUP, "geometry: CARTESIAN and SPHERICAL are built");
   // curvilinear geometry, characteristic limiting, MULTID flattening and the entropy switch run
   // on the general-grid path (pb200_gen.cu)
+  const bool iso = cfg->eos == PB200_EOS_ISOTHERMAL;
+  if (cfg->eos != PB200_EOS_IDEAL && !iso) return fail(PB200_EINVAL, "eos must be IDEAL or ISOTHERMAL");
+  if (iso && !(cfg->iso_sound_speed > 0.0)) return fail(PB200_EINVAL, "EOS ISOTHERMAL needs iso_sound_speed > 0 (g_isoSoundSpeed)");
+  if (iso && cfg->entropy_switch) return fail(PB200_EINVAL, "ENTROPY_SWITCH needs an energy equation (EOS IDEAL)");
   const bool gen = cfg->geometry != PB200_CARTESIAN || cfg->char_limiting || cfg->shock_flattening ||
-                   cfg->entropy_switch;
+                   cfg->entropy_switch || iso;
   if (gen && cfg->reconstruction != PB200_LINEAR)
     return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR");
   if (cfg->body_force & PB200_BF_POTENTIAL && gen)
@@ -93,13 +97,14 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
 
   pb200_ctx *c = new pb200_ctx();
   c->cfg = *cfg;
-  c->nvar = 5 + cfg->ntracer + (cfg->entropy_switch ? 1 : 0);
+  c->nvar = (iso ? 4 : 5) + cfg->ntracer + (cfg->entropy_switch ? 1 : 0);
   c->gen = gen;
   c->gen_ready = false;
   c->gdev = nullptr;
   c->ldw_on = false;
   c->cur_stage = 0;
   c->d_ibmask = nullptr;
+  c->geo_set = false;
   c->graph_exec = nullptr;
   c->graph_sig = 0;
   c->graph_launches = 0;
@@ -260,6 +265,25 @@ extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const dou
   CK(cudaSetDevice(c->cfg.device));
   c->gen_ready = false;
   return upload_grid(c, dir);
+}
+
+extern "C" int pb200_set_geometry(pb200_ctx *c, const pb200_geometry *g) {
+  if (!c || !g || !g->dV || !g->rt || !g->s || !g->sp) return fail(PB200_EINVAL, "null argument");
+  const Dev &D = c->dev;
+  const size_t n1 = D.tot[0], n2 = D.tot[1], n3 = D.tot[2];
+  c->geo_dV.assign(g->dV, g->dV + n1 * n2 * n3);
+  const size_t na[3] = {(n1 + 1) * n2 * n3, n1 * (n2 + 1) * n3, n1 * n2 * (n3 + 1)};
+  for (int d = 0; d < 3; d++) {
+    if (!g->A[d] || !g->dx_dl[d]) return fail(PB200_EINVAL, "null argument");
+    c->geo_A[d].assign(g->A[d], g->A[d] + na[d]);
+    c->geo_dxdl[d].assign(g->dx_dl[d], g->dx_dl[d] + n1 * n2);
+  }
+  c->geo_rt.assign(g->rt, g->rt + n1);
+  c->geo_s.assign(g->s, g->s + n2);
+  c->geo_sp.assign(g->sp, g->sp + n2);
+  c->geo_set = true;
+  c->gen_ready = false;
+  return PB200_OK;
 }
 
 static int set_bf_table(pb200_ctx *c, int q, const double *tab, long n, long si, long sj, long sk) {

@@ -66,6 +66,8 @@ int pb200_gen_setup(pb200_ctx *c) {
   G.flatten = c->cfg.shock_flattening;
   G.entropy = c->cfg.entropy_switch;
   G.solver = c->cfg.solver;
+  G.iso = c->cfg.eos == PB200_EOS_ISOTHERMAL;
+  G.cs2 = c->cfg.iso_sound_speed * c->cfg.iso_sound_speed;
 
   std::vector<double> x[3], xgc[3], inv[3], cp[3], cm[3], wp[3], wm[3], dp[3], dm[3];
   for (int d = 0; d < 3; d++) {
@@ -165,6 +167,13 @@ int pb200_gen_setup(pb200_ctx *c) {
       dm[d][i] = (xgc[d][i] - xr[i - 1]) / dx[i];
     }
   }
+  if (c->geo_set) {
+    // the caller's Grid arrays (grid->dV, A[], dx_dl[], rt, s, sp of Src/set_geometry.c) take the place of this
+    // function's own evaluation of the same formulas: a user-modified geometry is honoured as it is
+    dV = c->geo_dV;
+    for (int d = 0; d < 3; d++) { A[d] = c->geo_A[d]; dxdl[d] = c->geo_dxdl[d]; }
+    rt = c->geo_rt; s = c->geo_s; sp = c->geo_sp;
+  }
   bool ok = true;
   for (int d = 0; d < 3; d++) {
     ok &= (G.x[d] = upload(c, x[d])) != nullptr;
@@ -240,6 +249,7 @@ void pb200_fill_ldw(pb200_ctx *c, pb::GenDev &G) {
   const double KELVIN = L.unit_velocity * L.unit_velocity * amu / kB;      // pluto.h:560
   w.kelvin_mu = KELVIN * L.mu;
   w.krad = L.krad; w.alpharad = L.alpharad;
+  w.t_iso = c->cfg.eos == PB200_EOS_ISOTHERMAL ? L.t_iso : 0.0;
   w.mpoints = c->ldw_mpoints; w.t_fit = c->ldw_tfit; w.m_fit = c->ldw_mfit;
   w.sigma_e = sigmaT / amu / 1.18;
   w.unit_acc = L.unit_velocity * L.unit_velocity / L.unit_length;
@@ -273,11 +283,13 @@ int pb200_gen_internal_boundary(pb200_ctx *c, double *V) {
   if (!c->gen || !c->ldw_on || !c->ldw.userdef_bc) return PB200_OK;
   int rc = pb200_gen_setup(c);
   if (rc) return rc;
+  if (c->nvar - (c->cfg.eos == PB200_EOS_ISOTHERMAL ? 4 : 5) < 1) return PB200_ENOTSUP;    // the problem carries a tracer
   switch (c->nvar) {
+    case 5: gen_floor_nv<5>(c, V); break;
     case 6: gen_floor_nv<6>(c, V); break;
     case 7: gen_floor_nv<7>(c, V); break;
     case 8: gen_floor_nv<8>(c, V); break;
-    default: return PB200_ENOTSUP;    // the problem carries a tracer: NVAR >= 6
+    default: return PB200_ENOTSUP;
   }
   return PB200_OK;
 }
@@ -491,6 +503,7 @@ int pb200_gen_stage(pb200_ctx *c, int stage) {
   if (c->ldw_on && c->ldw.krad == 999 && c->ldw.alpharad == 999 && c->ldw_mpoints == 0)
     return pb200_fail(PB200_EINVAL, "KRAD = ALPHARAD = 999 needs the force-multiplier fit (pb200_ldw_set_mfit)");
   switch (c->nvar) {
+    case 4: gen_stage_nv<4>(c, stage, w0, wc, comb); break;
     case 5: gen_stage_nv<5>(c, stage, w0, wc, comb); break;
     case 6: gen_stage_nv<6>(c, stage, w0, wc, comb); break;
     case 7: gen_stage_nv<7>(c, stage, w0, wc, comb); break;

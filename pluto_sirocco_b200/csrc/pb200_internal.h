@@ -26,6 +26,9 @@ struct pb200_ctx {
   double *d_invdx[3];
   double *d_bf[7];   // body-force tables (Dev::bf_tab)
   std::vector<double> xl[3], xr[3], dx[3];
+  // the caller's own Grid arrays (pb200_set_geometry): used by the general path instead of its own evaluation
+  std::vector<double> geo_dV, geo_A[3], geo_dxdl[3], geo_rt, geo_s, geo_sp;
+  bool geo_set;
   cudaStream_t stream;
   cudaStream_t h2d, d2h;        // copy streams of the slab-wise host pipeline (pb200_advance_step_host)
   cudaEvent_t ev_up[64], ev_done[64];

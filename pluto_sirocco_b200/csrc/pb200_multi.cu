@@ -127,7 +127,7 @@ extern "C" int pb200_multi_create(const pb200_config *gcfg, int ngpus, const int
   *out = nullptr;
   if (gcfg->dimensions < 2 && ngpus > 1)
     return pb200_fail(PB200_ENOTSUP, "1-D grids are not decomposed (replicas only)");
-  const bool gen = gcfg->geometry != PB200_CARTESIAN || gcfg->char_limiting || gcfg->shock_flattening || gcfg->entropy_switch;
+  const bool gen = gcfg->geometry != PB200_CARTESIAN || gcfg->char_limiting || gcfg->shock_flattening || gcfg->entropy_switch || gcfg->eos != PB200_EOS_IDEAL;
   if (gen && ngpus > 1) return pb200_fail(PB200_ENOTSUP, "the general-grid path runs on one GPU (replicas only)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

@@ -291,6 +291,9 @@ static void shim_line_driven_wind(int device_bc)
   l.disk_mdot = g_inputParam[DISK_MDOT];
   l.lx        = g_inputParam[L_star]*g_inputParam[f_x];
   l.tx        = g_inputParam[T_x];
+#if EOS == ISOTHERMAL
+  l.t_iso     = g_inputParam[T_ISO];          /* line_connect.c:851-855 */
+#endif
   if (flux_r_UV == NULL || flux_t_UV == NULL) {
     print ("! AdvanceStep(): no sirocco flux tables (directional_flux_*.dat) were read\n");
     QUIT_PLUTO(1);
@@ -315,8 +318,12 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
   pb200_config cfg;
   int dir;
   pb200_config_default(&cfg);
-#if PHYSICS != HD || EOS != IDEAL
-#error "libplutob200: only PHYSICS HD with EOS IDEAL is on the B200 path"
+#if PHYSICS != HD || (EOS != IDEAL && EOS != ISOTHERMAL)
+#error "libplutob200: PHYSICS HD with EOS IDEAL or ISOTHERMAL is on the B200 path"
+#endif
+#if EOS == ISOTHERMAL
+  cfg.eos = PB200_EOS_ISOTHERMAL;
+  cfg.iso_sound_speed = g_isoSoundSpeed;      /* set by the user's Init() (e.g. cv_iso/init.c:61-63) */
 #endif
   cfg.dimensions = DIMENSIONS;
   cfg.geometry   = GEOMETRY;          /* same codes, Src/pluto.h:34-37 */
@@ -375,7 +382,9 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
     cfg.bc[2*dir]     = s_host_bc ? PB200_BC_NEIGHBOUR : grid->lbound[dir];   /* same codes, Src/pluto.h:163-170 */
     cfg.bc[2*dir + 1] = s_host_bc ? PB200_BC_NEIGHBOUR : grid->rbound[dir];
   }
+#if EOS == IDEAL
   cfg.gamma          = g_gamma;
+#endif
   cfg.small_density  = g_smallDensity;
   cfg.small_pressure = g_smallPressure;
   if (getenv("PB200_DEVICE")) cfg.device = atoi(getenv("PB200_DEVICE"));
@@ -404,6 +413,16 @@ static void shim_create(Data *d, Grid *grid, int ngpus, int ldw_device_bc) {
                  : pb200_set_grid(s_ctx, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir]);
     if (rc != PB200_OK) { print ("! AdvanceStep(): pb200_set_grid: %s\n", pb200_last_error()); QUIT_PLUTO(1); }
   }
+#if GEOMETRY != CARTESIAN
+  if (s_multi == NULL) {     /* the reference's own geometry arrays (Src/set_geometry.c:49-61), not a re-evaluation */
+    pb200_geometry geo;
+    geo.dV = grid->dV[0][0];
+    geo.A[0] = &grid->A[IDIR][0][0][-1]; geo.A[1] = &grid->A[JDIR][0][-1][0]; geo.A[2] = &grid->A[KDIR][-1][0][0];
+    geo.dx_dl[0] = grid->dx_dl[IDIR][0]; geo.dx_dl[1] = grid->dx_dl[JDIR][0]; geo.dx_dl[2] = grid->dx_dl[KDIR][0];
+    geo.rt = grid->rt; geo.s = grid->s; geo.sp = grid->sp;
+    if (pb200_set_geometry(s_ctx, &geo) != PB200_OK) { print ("! AdvanceStep(): pb200_set_geometry: %s\n", pb200_last_error()); QUIT_PLUTO(1); }
+  }
+#endif
 #if BODY_FORCE != NO
   shim_body_force(d, grid);
 #endif
@@ -438,7 +457,9 @@ static int shim_probe_ldw_boundary(Data *d, Grid *grid) {
   for (pass = 0; pass < 2 && ok; pass++) {
     if (pass == 1) DOM_LOOP(k,j,i) {
       if ((i + 2*j) % 3 == 0) d->Vc[RHO][k][j][i] *= 1.e-9;
+#if HAVE_ENERGY
       if ((2*i + j) % 5 == 0) d->Vc[PRS][k][j][i] *= 1.e-9;
+#endif
       if ((i + j) % 7 == 0)   d->Vc[VX1][k][j][i] = -d->Vc[VX1][k][j][i] - 0.3;
       if ((i + 3*j) % 4 == 0) d->Vc[VX2][k][j][i] = 0.7 - d->Vc[VX2][k][j][i];
     }

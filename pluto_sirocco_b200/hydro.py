@@ -285,7 +285,7 @@ class Hydro:
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
                  small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0,
                  geometry="CARTESIAN", grid_arrays=None, char_limiting=False, shock_flattening=False,
-                 entropy_switch=False):
+                 entropy_switch=False, eos="IDEAL", iso_sound_speed=0.0):
         lib = L.load()
         cfg = L.Config()
         lib.pb200_config_default(C.byref(cfg))
@@ -315,6 +315,8 @@ class Hydro:
         cfg.char_limiting = int(bool(char_limiting))
         cfg.shock_flattening = int(bool(shock_flattening))
         cfg.entropy_switch = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
+        cfg.eos = {"IDEAL": 0, "ISOTHERMAL": 1}[eos]
+        cfg.iso_sound_speed = float(iso_sound_speed)
         self.cfg = cfg
         self._lib = lib
         h = C.c_void_p()
@@ -440,6 +442,7 @@ class Hydro:
         lc.dfloor, lc.rho_0, lc.rho_alpha = params["DFLOOR"], params["RHO_0"], params["RHO_ALPHA"]
         lc.cent_mass, lc.disk_mdot = params["CENT_MASS"], params["DISK_MDOT"]
         lc.lx, lc.tx = params["L_star"] * params["f_x"], params["T_x"]
+        lc.t_iso = params.get("T_ISO", 0.0)
         L.check(self._lib.pb200_ldw_enable(self._h, C.byref(lc)))
         fp = None if flux_p is None else np.ascontiguousarray(flux_p, dtype=np.float64)
         L.check(self._lib.pb200_ldw_set_fluxes(self._h, fr.ctypes.data_as(C.c_void_p), ft.ctypes.data_as(C.c_void_p),

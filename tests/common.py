@@ -5,8 +5,10 @@ import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
-# cylindrical / polar / isothermal fixtures pin the ORACLE only (the CUDA path refuses these options so far)
+# cylindrical / polar / Roe / two-shock / ONED / general-grid PPM fixtures pin the ORACLE only (the CUDA path refuses
+# these options); the iso* fixtures (EOS ISOTHERMAL) run on the CUDA path too: ISO_CASES
 _CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot", "ausm")
+ISO_CASES = ["iso2d_hll", "iso2d_hllc", "iso2d_flat_hllc", "iso3d_tvdlf", "iso_sph2d_flat_hll"]
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))

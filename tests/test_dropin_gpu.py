@@ -275,3 +275,34 @@ def test_dropin_long_runs_to_tstop(cuda_lib, tmp_path, cfg, kw, tstop, strict):
         qa = a[0].sum() if tot == "mass" else (0.5 * a[0] * (a[1] ** 2 + a[2] ** 2 + a[3] ** 2) + g1 * a[4]).sum()
         qb = b[0].sum() if tot == "mass" else (0.5 * b[0] * (b[1] ** 2 + b[2] ** 2 + b[3] ** 2) + g1 * b[4]).sum()
         assert abs(qa - qb) <= 1e-11 * abs(qa)
+
+
+def test_dropin_isothermal_line_driven_wind_matches_reference_executable(cuda_lib, tmp_path):
+    """The fork's second wind problem, Test_Problems/LineDrivenWind/cv_iso (EOS ISOTHERMAL, COOLING NO, unmodified user
+    files): the reference's driver with AdvanceStep on the GPU against the stock executable."""
+    import pluto_grid
+    from common import LDW_BCS, LDW_PARAMS, ldw_flux_tables, write_ldw_flux_files
+    cfg = "ldw_iso"
+    exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
+    if not exe.exists() or not refrun.have_ref(cfg):
+        pytest.skip("drop-in / reference executables were not built in the container (needs /root/reference)")
+    grid = [(0.87, 48, 8.7, "r", 1.05), (0.0, 36, 1.5707963267948966, "r", 0.95), (0.0, 1, 1.0)]
+    xl1, xr1, _ = pluto_grid.make_grid(grid[0], 3)
+    xl2, xr2, _ = pluto_grid.make_grid(grid[1], 3)
+    x1, x2 = 0.5 * (xl1 + xr1), 0.5 * (xl2 + xr2)
+    fr, ft, fp = ldw_flux_tables(x1, x2)
+    out = {}
+    for tag, ex in (("ref", None), ("b200", exe)):
+        wd = tmp_path / tag
+        wd.mkdir()
+        write_ldw_flux_files(wd, x1, x2, 3, fr, ft, fp)
+        out[tag] = refrun.run(cfg, wd, shape=(1, 36, 48), nvar=5, maxsteps=10, timeout=250, exe=ex,
+                              grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
+                              solver="hll", bcs=LDW_BCS, dbl=(-1.0, 1), params=LDW_PARAMS)
+    ref, got = out["ref"], out["b200"]
+    assert "runs on the GPU" in got["log"]
+    assert len(got["data"]) == len(ref["data"]) >= 8
+    for (n1, t1, d1), (n2, t2, d2) in zip(ref["steps"], got["steps"]):
+        assert n1 == n2 and abs(t1 - t2) <= 1e-11 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-10 * d1
+    assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
+    assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN

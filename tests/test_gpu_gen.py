@@ -98,6 +98,51 @@ def test_gen_options_vs_oracle(Hydro, geometry, limiter, char, flat, entr, rk, s
     h.close(); o.close()
 
 
+@pytest.mark.parametrize("name", __import__("common").ISO_CASES)
+def test_isothermal_per_step_vs_reference_dumps(Hydro, name):
+    """EOS ISOTHERMAL on the CUDA path (Src/EOS/Isothermal, NFLX = 4: p = cs^2 rho in the fluxes and in FlagShock,
+    the isothermal HLLC star state hllc.c:137-150, the isothermal eigenvectors eigenv.c:175-196) against the dumps
+    of the compiled reference (user files oracle/problems/iso): Cartesian 2-D / 3-D, spherical 2-D with gravity,
+    characteristic limiting and MULTID flattening, HLL / HLLC / TVDLF."""
+    g = load_golden(name)
+    kw = gen_kwargs_from_golden(g)
+    assert kw["eos"] == "ISOTHERMAL"
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    set_point_mass_gravity(h, float(g["gm"]))
+    data, steps = g["data"], g["steps"]
+    assert h.nvar == data.shape[1] == 4 + g["ntracer"]
+    for n in range(len(data) - 1):
+        h.set_interior(data[n])
+        dt = steps[n, 2]
+        info = h.advance_step(dt)
+        e = rel_err(h.get_interior(), data[n + 1])
+        assert e <= TOL_STEP, (name, n, e)
+        dtn = h.next_time_step(info.invDt_hyp, g["cfl"], g["cfl_max_var"], dt, g["first_dt"])
+        assert abs(dtn - steps[n + 1, 2]) <= TOL_STEP * steps[n + 1, 2], (name, n)
+    h.close()
+
+
+def test_isothermal_line_driven_wind_vs_reference_dumps(Hydro):
+    """Test_Problems/LineDrivenWind/cv_iso, the fork's isothermal wind problem (unmodified user files in the
+    reference run that made the fixture): line force with T = T_ISO (line_connect.c:851-855), floors and user
+    boundaries without their pressure parts (init.c "#if EOS != ISOTHERMAL"), NVAR = 5 (tracer at index 4)."""
+    g = load_golden("iso_ldw_hll")
+    kw = gen_kwargs_from_golden(g)
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    ldw_setup(h, h.x(0), h.x(1))
+    data, steps = g["data"], g["steps"]
+    assert h.nvar == data.shape[1] == 5
+    for n in range(len(data) - 1):
+        h.set_interior(data[n])
+        dt = steps[n, 2]
+        info = h.advance_step(dt)
+        e = rel_err(h.get_interior(), data[n + 1])
+        assert e <= TOL_STEP, (n, e)
+        dtn = h.next_time_step(info.invDt_hyp, g["cfl"], g["cfl_max_var"], dt, g["first_dt"])
+        assert abs(dtn - steps[n + 1, 2]) <= TOL_STEP * steps[n + 1, 2], n
+    h.close()
+
+
 LDW_CASES = [c for c in GEN_CASES if c.startswith("ldw_nocool")]
 
 
