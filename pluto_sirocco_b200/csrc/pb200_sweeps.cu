@@ -3,6 +3,7 @@
 // run-time options of the reference ([Solver] in pluto.ini) or cheap to carry as template
 // parameters, so every combination is instantiated here.
 #include <cstdlib>
+#include <mutex>
 #include <unordered_map>
 
 #include "pb200_internal.h"
@@ -22,6 +23,8 @@ static void set_smem(K k, size_t shm) {
   // high-water mark of the opt-in dynamic shared memory per (device, kernel): the attribute is
   // per device, and a process may drive several (pb200_multi)
   static std::unordered_map<const void *, size_t> cur[64];
+  static std::mutex mtx;          // the worker threads of pb200_multi launch concurrently
+  std::lock_guard<std::mutex> lock(mtx);
   int dev = 0;
   cudaGetDevice(&dev);
   size_t &c = cur[dev & 63][(const void *)k];
