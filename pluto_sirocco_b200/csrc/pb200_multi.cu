@@ -152,8 +152,9 @@ extern "C" int pb200_multi_create(const pb200_config *gcfg, int ngpus, const int
   // PB200_MULTI_EXCHANGE=copy: cudaMemcpyPeerAsync between the packed buffers instead of ncclSend/ncclRecv
   m->use_nccl = !dup && !(getenv("PB200_MULTI_EXCHANGE") && !strcmp(getenv("PB200_MULTI_EXCHANGE"), "copy"));
   // The caller stays single threaded (the reference's driver is); inside a step the library fans the launch work of
-  // the N devices out to N short-lived worker threads - with one thread, 8 devices x ~100 launches and stream / event
-  // calls per step cost 6 ms of host time against 15 ms of GPU time (measured).  PB200_MULTI_THREADS=0: one thread.
+  // the N devices out to N short-lived worker threads, so that short steps (PPM + RK3 at 256^3: 4.8 ms of GPU time,
+  // ~40 launches and as many stream / event calls per device) are not limited by one thread's enqueue rate
+  // (measured at N = 2: 4.78 ms per step against 5.67 ms).  PB200_MULTI_THREADS=0: one thread.
   m->threads = m->use_nccl && !(getenv("PB200_MULTI_THREADS") && atoi(getenv("PB200_MULTI_THREADS")) == 0);
   m->ctx.assign(ngpus, nullptr);
   m->comm.assign(ngpus, nullptr);

@@ -26,6 +26,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Mzones/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the reference arm runs a bounded sample of THIS arm's workload and carries this arm's config dict
+    import argparse
+    sys.path.insert(0, str(ROOT))
+    import bench
+    mine = bench.cart_config(argparse.Namespace(size=512, workload="sedov", recon="LINEAR", rk="RK2", solver="hllc",
+                                                state="sedov"), 1, 512 ** 3)
+    assert d["config"] == mine
+    assert "slab" in d["cpu_baseline"]["sample"] or "16 x 16 x 16" in d["cpu_baseline"]["sample"]
 
 
 def test_cuda_arm_has_no_cpu_fallback():

@@ -21,6 +21,8 @@ ap.add_argument("--rk", default="RK2")
 a = ap.parse_args()
 out = {"ngpus": a.ngpus}
 for tag, n, host in (("resident", a.size, False), ("host", a.host_size, True)):
+    if n <= 0:
+        continue
     N = a.ngpus
     m = MultiHydro(N, dimensions=3, nx=(n, n, n * N), xend=(1.0, 1.0, float(N)), gamma=1.4, reconstruction=a.recon,
                    time_stepping=a.rk, bcs=bench.SEDOV_BCS)
@@ -35,12 +37,16 @@ for tag, n, host in (("resident", a.size, False), ("host", a.host_size, True)):
         info = step(); dt = min(0.3 / info.invDt_hyp, 1.1 * dt)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    per = []
     for _ in range(a.steps):
+        t1 = time.perf_counter()
         info = step(); dt = min(0.3 / info.invDt_hyp, 1.1 * dt)
-    for d in range(N):
-        torch.cuda.synchronize(d)
-    wall = time.perf_counter() - t0
+        per.append(round(1e3 * (time.perf_counter() - t1), 2))
+    # every call returns after its own stream synchronisation (pb200_step_end): the sum of the per-call times is the
+    # wall time of the loop.  (torch.cuda.synchronize(d) on a device torch has not touched yet initialises a context
+    # there - 7 ms each - which an earlier version of this script charged to the steps.)
+    wall = sum(per) * 1e-3
     out[tag] = {"zones_per_gpu": n ** 3, "ms_per_step": 1e3 * wall / a.steps, "Mzones_per_s": n ** 3 * N * a.steps / wall / 1e6,
-                "gpu_ms_max": info.gpu_ms, "launches_per_step": info.launches}
+                "gpu_ms_max": info.gpu_ms, "launches_per_step": info.launches, "per_step_ms": per}
     m.close(); del pin
 print(json.dumps(out))
