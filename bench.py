@@ -520,12 +520,67 @@ def run_b200(args):
     if not args.no_e2e:
         h.download(vc)
         dt_e = g["dt"]
+        deep = None
+        if world > 1 and not rt:
+            # Host-buffer steps of a slab-decomposed grid WITHOUT an exchange inside the step: every rank's host array
+            # carries a deep halo of E = nghost x nstages planes of its neighbours on each cut face, the rank's block
+            # (own + halo planes, any fill on the cut faces) goes through the same slab-pipelined call as at N = 1, only
+            # the own planes come back (pb200_set_owned_planes), and afterwards the neighbours' fresh edge planes are
+            # fetched into the host halo (NCCL device to device, then D2H of those few planes).
+            from pluto_sirocco_b200.slab import device_view
+            E = h.nghost * h.nstages()
+            lo_ext, hi_ext = (E if rank > 0 else 0), (E if rank < world - 1 else 0)
+            nloc = n + lo_ext + hi_ext
+            he = Hydro(dimensions=3, nx=(n, n, nloc), xbeg=(0., 0., (rank * n - lo_ext) / float(n)),
+                       xend=(1., 1., (rank * n + n + hi_ext) / float(n)), gamma=gamma, reconstruction=args.recon,
+                       time_stepping=args.rk, solver=args.solver, bcs=SEDOV_BCS, device=local_rank, dx=slab.global_dx())
+            he.set_owned_planes(lo_ext, lo_ext + n)
+            pin_e = torch.empty(he.shape, dtype=torch.float64, pin_memory=True)
+            vce = pin_e.numpy()
+            vce[:] = 1.0
+            vce[1:4] = 0.0
+            vce[he.interior()] = sedov_block((n, n, nloc), rank * n - lo_ext, n)
+            ng = he.nghost
+            dev = torch.device("cuda", local_rank)
+            bufs = [torch.empty((he.nvar, E) + he.shape[2:], dtype=torch.float64, device=dev) for _ in range(4)]
+            deep = dict(he=he, vce=vce, pin=pin_e, E=E, lo=lo_ext, hi=hi_ext, ng=ng, bufs=bufs, dev=dev)
+            dt_e = first_dt
+
+        def deep_refresh_halo():
+            """the neighbours' fresh edge planes -> this rank's host halo planes"""
+            he, E, ng, lo_ext, hi_ext = deep["he"], deep["E"], deep["ng"], deep["lo"], deep["hi"]
+            view = device_view(he.device_vc_ptr(), he.shape, deep["dev"])
+            send_lo, send_hi, recv_lo, recv_hi = deep["bufs"]
+            k_own0 = ng + lo_ext
+            ops = []
+            if hi_ext:
+                send_hi.copy_(view[:, k_own0 + n - E:k_own0 + n])
+                ops.append(dist.P2POp(dist.isend, send_hi, rank + 1))
+            if lo_ext:
+                send_lo.copy_(view[:, k_own0:k_own0 + E])
+                ops.append(dist.P2POp(dist.isend, send_lo, rank - 1))
+            if lo_ext:
+                ops.append(dist.P2POp(dist.irecv, recv_lo, rank - 1))
+            if hi_ext:
+                ops.append(dist.P2POp(dist.irecv, recv_hi, rank + 1))
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            if lo_ext:
+                deep["pin"][:, ng:ng + E].copy_(recv_lo, non_blocking=True)
+            if hi_ext:
+                deep["pin"][:, k_own0 + n:k_own0 + n + E].copy_(recv_hi, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
         def e2e_step():
             nonlocal dt_e
             if world == 1:
                 info = h.advance_step_host(vc, dt_e)
                 inv = info.invDt_hyp
+            elif deep is not None:
+                info = deep["he"].advance_step_host(deep["vce"], dt_e)
+                inv, mach = __import__("pluto_sirocco_b200.slab", fromlist=["allreduce_max"]).allreduce_max(
+                    [info.invDt_hyp, info.maxMach], deep["dev"])
+                deep_refresh_halo()
             else:
                 h.upload(vc)
                 inv, mach, info = sh.advance_step(dt_e)
@@ -548,12 +603,24 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = t.item()
         nbytes = int(np.prod(h.shape)) * 8
+        up_b, down_b = nbytes * world, nbytes * world
+        api = ("pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, the RK stages and "
+               "download pipelined over slabs of x3 planes)")
+        if world > 1 and deep is None:
+            api = "per rank: upload of the pinned host d->Vc slab, AdvanceStep with NCCL halo exchange, download, every step"
+        if deep is not None:
+            he = deep["he"]
+            plane_b = he.nvar * he.shape[2] * he.shape[3] * 8
+            mine = torch.tensor([float(np.prod(he.shape)) * 8, float(plane_b * (n + deep["lo"] + deep["hi"]))],
+                                dtype=torch.float64, device="cuda")
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+            up_b, down_b = int(mine[0].item()), int(mine[1].item())
+            api = ("per rank: pb200_advance_step_host on the rank's slab + a deep halo of nghost x nstages = %d planes per cut "
+                   "face (no exchange inside the step, slab-pipelined like N = 1, own planes come back: "
+                   "pb200_set_owned_planes), then the neighbours' edge planes refresh the host halo" % deep["E"])
+            he.close()
         e2e = {"value": zones_total * ne / (ems * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world, "steps": ne,
-               "api": "pb200_advance_step_host (pinned host d->Vc in, d->Vc out, every step; upload, the RK stages and "
-                      "download pipelined over slabs of x3 planes)" if world == 1 else
-                      "per rank: upload of the pinned host d->Vc slab, AdvanceStep with NCCL halo exchange, download, every step",
-               "host_numa": numa}
+               "h2d_bytes_per_step": up_b, "d2h_bytes_per_step": down_b, "steps": ne, "api": api, "host_numa": numa}
 
     # ---- the other BASELINE configs, a few steps each (device-resident), reported under "secondary" ----
     nvar_head, shape_head = h.nvar, tuple(h.shape)

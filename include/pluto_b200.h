@@ -241,6 +241,12 @@ int  pb200_advance_step(pb200_ctx *ctx, double dt, pb200_step_info *info);
  * call costs about one PCIe direction; results are identical to pb200_advance_step().  Ghost zones
  * of vc_host are not written back.  PB200_HOST_PIPELINE=<planes per slab> (0: off). */
 int  pb200_advance_step_host(pb200_ctx *ctx, double *vc_host, double dt, pb200_step_info *info);
+/* Deep halo for host-buffer steps of a slab-decomposed grid (replaces the per-stage exchange of Src/boundary.c:139-158
+ * when every step starts from host data anyway): a block is given nghost x nstages extra planes of its neighbours on
+ * each cut face, steps WITHOUT any exchange (the cut faces get any fill type; what they contaminate never reaches the
+ * owned planes within one step), and only its own planes [k0, k1) (interior x3 indices of this block) are downloaded
+ * by pb200_advance_step_host() and counted in invDt_hyp / maxMach.  3-D Cartesian path. */
+int  pb200_set_owned_planes(pb200_ctx *ctx, int k0, int k1);
 /* cudaHostRegister / cudaHostUnregister of a caller-owned buffer (the reference's d->Vc payload):
  * page-locked memory makes the copies above asynchronous and full speed. */
 int  pb200_host_register(void *ptr, size_t bytes);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "pb200_boundary": (C.c_int, [_P]),
     "pb200_advance_step": (C.c_int, [_P, _D, C.POINTER(StepInfo)]),
     "pb200_advance_step_host": (C.c_int, [_P, _P, _D, C.POINTER(StepInfo)]),
+    "pb200_set_owned_planes": (C.c_int, [_P, C.c_int, C.c_int]),
     "pb200_host_register": (C.c_int, [_P, C.c_size_t]),
     "pb200_host_unregister": (C.c_int, [_P]),
     "pb200_next_time_step": (_D, [_D, _D, _D, _D, _D]),

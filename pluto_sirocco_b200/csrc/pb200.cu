@@ -132,6 +132,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
     D.beg[d] = ng;
     D.end[d] = ng + nx - 1;
   }
+  c->own_k0 = 0;
+  c->own_k1 = D.end[2] - D.beg[2] + 1;
   D.sj = D.tot[0];
   D.sk = (long)D.tot[0] * D.tot[1];
   D.sv = D.sk * D.tot[2];
@@ -543,6 +545,16 @@ extern "C" int pb200_stage_upload(pb200_ctx *c, int stage, const double *h) {
   return PB200_OK;
 }
 
+extern "C" int pb200_set_owned_planes(pb200_ctx *c, int k0, int k1) {
+  if (!c) return fail(PB200_EINVAL, "null ctx");
+  const int nk = c->dev.end[2] - c->dev.beg[2] + 1;
+  if (c->gen || c->dev.ndim != 3) return fail(PB200_ENOTSUP, "owned planes: 3-D Cartesian path");
+  if (k0 < 0 || k1 > nk || k0 >= k1) return fail(PB200_EINVAL, "owned planes: need 0 <= k0 < k1 <= NX3");
+  c->own_k0 = k0;
+  c->own_k1 = k1;
+  return PB200_OK;
+}
+
 extern "C" int pb200_stage_patch_u(pb200_ctx *c, long n, const long *zone, const double *u) {
   if (!c || !c->in_step || n < 0 || (n > 0 && (!zone || !u))) return fail(PB200_EINVAL, "bad argument");
   CK(cudaSetDevice(c->cfg.device));
@@ -569,6 +581,8 @@ static int stage_args(pb200_ctx *c, int stage, SweepArgs &a) {
   a.i0 = 0;
   a.k0 = 0;
   a.k1 = c->dev.end[2] - c->dev.beg[2] + 1;
+  a.ko0 = c->own_k0;
+  a.ko1 = c->own_k1;
   a.comb = 0; a.w0 = 0.0; a.wc = 1.0;
   if (stage == 2) {  // rk_step.c:18-24
     a.comb = 1;
@@ -643,6 +657,8 @@ static unsigned long long graph_signature(const pb200_ctx *c) {
   mix(&c->dev, sizeof(c->dev));
   mix(&c->cfg, sizeof(c->cfg));
   mix(&c->cur, sizeof(c->cur));
+  mix(&c->own_k0, sizeof(int));
+  mix(&c->own_k1, sizeof(int));
   mix(&c->ldw_on, sizeof(c->ldw_on));
   mix(&c->ldw, sizeof(c->ldw));
   mix(c->ldw_flux, sizeof(c->ldw_flux));
@@ -837,9 +853,10 @@ static int advance_step_host_pipelined_body(pb200_ctx *c, double *h, double dt, 
     if (stage < NS) return PB200_OK;
     CK(cudaEventRecord(c->ev_done[q], c->stream));                              // last stage: slab q is final
     CK(cudaStreamWaitEvent(c->d2h, c->ev_done[q], 0));
-    for (int nv = 0; nv < c->nvar; nv++) {
-      size_t o = (size_t)nv * D.sv + (size_t)(D.beg[2] + k0) * plane;
-      CK(cudaMemcpyAsync(h + o, R + o, (size_t)(k1 - k0) * plane * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
+    const int d0 = k0 > c->own_k0 ? k0 : c->own_k0, d1 = k1 < c->own_k1 ? k1 : c->own_k1;   // owned planes only
+    for (int nv = 0; nv < c->nvar && d1 > d0; nv++) {
+      size_t o = (size_t)nv * D.sv + (size_t)(D.beg[2] + d0) * plane;
+      CK(cudaMemcpyAsync(h + o, R + o, (size_t)(d1 - d0) * plane * sizeof(double), cudaMemcpyDeviceToHost, c->d2h));
     }
     return PB200_OK;
   };

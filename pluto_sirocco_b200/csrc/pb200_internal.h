@@ -70,6 +70,7 @@ struct pb200_ctx {
   unsigned long long graph_sig;
   int graph_launches, use_graph, gen_epoch;
   bool capturing;
+  int own_k0, own_k1;                     // pb200_set_owned_planes (relative to KBEG); default: the whole interior
   bool stage_uploaded;                    // pb200_stage_upload() replaced the array the next stage sweeps
   unsigned char *d_ibmask;
   long *d_iblist;

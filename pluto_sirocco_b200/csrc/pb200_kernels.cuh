@@ -70,6 +70,11 @@ struct SweepArgs {
   int limiter;
   int i0;      // first interior zone (relative to IBEG) of this launch of the fused kernel
   int k0, k1;  // x3 planes [k0, k1) relative to KBEG covered by this launch (slab-wise host pipeline); 3-D
+  // x3 planes [ko0, ko1) relative to KBEG whose zones count in the reductions (C_dt max, max Mach number).  The
+  // whole interior by default; a block that carries a deep halo of planes it does not own (host-buffer steps of a
+  // slab-decomposed grid without exchange, pb200_set_owned_planes) restricts them to its own planes, so that
+  // invDt_hyp and g_maxMach equal those of the undecomposed grid.
+  int ko0, ko1;
 };
 
 // local (sweep) component c=1,2,3 -> global velocity variable, Src/set_indexes.c:18-110
@@ -361,6 +366,8 @@ __global__ void __launch_bounds__(BXT, fused_minblk(FUSEX, BXT)) sweep_fused(Dev
   const bool own = (t >= LO) && (t < BXT - HI) && (i <= d.end[0]);
   const int ic = min(max(i, 0), d.tot[0] - 1);
   const int tr = blockIdx.y + ((DIR == 1 && d.ndim == 3) ? a.k0 : 0);  // transverse index (k for x2 sweeps, j for x3 sweeps)
+  // x2 march of a 3-D grid: the whole block sits on one x3 plane (block uniform)
+  const bool plane_own = !(DIR == 1 && d.ndim == 3) || (tr >= a.ko0 && tr < a.ko1);
   const long st = (DIR == 1) ? d.sj : d.sk;
   // x1 ghost zones are VIRTUAL in the fused kernel: a halo thread loads the zone Boundary() would have
   // copied into its ghost (outflow: the edge zone, reflective-type: the mirror zone with v_x1 flipped
@@ -522,7 +529,9 @@ __global__ void __launch_bounds__(BXT, fused_minblk(FUSEX, BXT)) sweep_fused(Dev
     // With FUSEX the call is placed between the two barriers of the x1 sweep, next to the x1
     // Riemann problem: two independent dependency chains for the scheduler to interleave.
     Face<NV> Fp;
-    if (!FUSEX || !fin) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own && n >= cb);
+    // x3 march: face n-1/2 counts if one of its two zones (n-1, n) is owned
+    const bool face_own = (DIR == 2) ? (n - d.beg[2] >= a.ko0 && n - d.beg[2] <= a.ko1) : plane_own;
+    if (!FUSEX || !fin) riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own && n >= cb && face_own);
     // zone z = n-1 sits at (ic, z, kt) for the x2 march and (ic, jt, z) for the x3 march
     const int zj = (DIR == 1) ? max(z, 0) : jt, zk = (DIR == 1) ? kt : max(z, 0);
     double phi_p = 0.0;
@@ -576,8 +585,8 @@ __global__ void __launch_bounds__(BXT, fused_minblk(FUSEX, BXT)) sweep_fused(Dev
         for (int v = 0; v < NV; v++) xr[v] = exm[v * BXT + tp];
         Face<NV> Gp;
         const bool xface = t >= LO - 1 && t < BXT - HI && i >= d.beg[0] - 1 && i <= d.end[0];
-        riemann<NV, SOLVER>(xp, xr, d.gas, Gp, mach, xface);
-        riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own);
+        riemann<NV, SOLVER>(xp, xr, d.gas, Gp, mach, xface && plane_own);
+        riemann<NV, SOLVER>(vpL, vm, d.gas, Fp, mach, own && plane_own);
         double phx = 0.0;
         if (BF && (d.bf_kind & 2)) {   // TotalFlux(): F_E += F_rho Phi(x1p) (rhs.c:524-526)
           phx = bf_at(d, 4, ic, zj, zk);
@@ -653,7 +662,8 @@ __global__ void __launch_bounds__(BXT, fused_minblk(FUSEX, BXT)) sweep_fused(Dev
         double c = 0.5 * (Fm.cmax + Fp.cmax) * inv_dl;
         if (FUSEX) c = cx + c;
         else if (!FIRST) c = cin + c;
-        if (LAST) cdt_max = fmax(cdt_max, own ? c : 0.0);
+        const bool zone_own = (DIR == 2) ? (z - d.beg[2] >= a.ko0 && z - d.beg[2] < a.ko1) : plane_own;
+        if (LAST) cdt_max = fmax(cdt_max, (own && zone_own) ? c : 0.0);
         else if (own) a.cdt[oz] = c;
       }
     } else {

@@ -518,6 +518,11 @@ class Hydro:
                                                   float(dt), C.byref(self.last)))
         return self.last
 
+    def set_owned_planes(self, k0, k1):
+        """Deep-halo block of a slab decomposition: only the x3 planes [k0, k1) are downloaded by
+        advance_step_host() and counted in invDt_hyp / maxMach (pb200_set_owned_planes)."""
+        L.check(self._lib.pb200_set_owned_planes(self._h, int(k0), int(k1)))
+
     def next_time_step(self, invDt_hyp, cfl, cfl_max_var, g_dt, first_dt) -> float:
         """NextTimeStep(), Src/main.c:521."""
         r = self._lib.pb200_next_time_step(invDt_hyp, cfl, cfl_max_var, g_dt, first_dt)

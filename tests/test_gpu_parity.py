@@ -269,6 +269,55 @@ def test_pipelined_host_call_equals_resident_call_3d(Hydro, monkeypatch, recon, 
 
 
 @pytest.mark.parametrize("recon,rk", [("LINEAR", "RK2"), ("PARABOLIC", "RK3")])
+def test_deep_halo_host_steps_equal_undecomposed(Hydro, monkeypatch, recon, rk):
+    """Host-buffer steps of a slab-decomposed grid without any exchange inside the step (bench.py e2e at N > 1): two
+    blocks, each with its own planes plus nghost x nstages planes of the neighbour on the cut face, go through the
+    slab-pipelined pb200_advance_step_host(); only the own planes come back and count in invDt_hyp / maxMach
+    (pb200_set_owned_planes); the host halos are refreshed from the neighbour's own planes between steps.  Same
+    states, invDt_hyp and maxMach as the undecomposed grid."""
+    import torch
+    monkeypatch.setenv("PB200_HOST_PIPELINE", "6")
+    nx, nz = (32, 24), 40
+    bcs = ("reflective", "outflow") * 3
+    kw = dict(dimensions=3, gamma=1.4, reconstruction=recon, time_stepping=rk, bcs=bcs)
+    full = Hydro(nx=nx + (nz,), **kw)
+    ng, E = full.nghost, full.nghost * full.nstages()
+    v = random_state((nz, nx[1], nx[0]), seed=21, smooth=False)
+    full.set_interior(v)
+    half = nz // 2
+    dz = 1.0 / nz
+    blocks = []
+    for r, (k0, k1, lo, hi) in enumerate([(0, half, 0, E), (half, nz, E, 0)]):
+        nloc = (k1 - k0) + lo + hi
+        h = Hydro(nx=nx + (nloc,), xbeg=(0., 0., (k0 - lo) * dz), xend=(1., 1., (k1 + hi) * dz), dx=(1. / nx[0], 1. / nx[1], dz), **kw)
+        h.set_owned_planes(lo, lo + (k1 - k0))
+        pin = torch.empty(h.shape, dtype=torch.float64, pin_memory=True)
+        vc = pin.numpy()
+        vc[:] = 1.0; vc[1:4] = 0.0
+        vc[h.interior()] = v[:, k0 - lo:k1 + hi]
+        blocks.append(dict(h=h, vc=vc, pin=pin, k0=k0, k1=k1, lo=lo, hi=hi))
+    dt = 2e-4
+    for n in range(3):
+        i0 = full.advance_step(dt)
+        infos = [b["h"].advance_step_host(b["vc"], dt) for b in blocks]
+        assert abs(max(i.invDt_hyp for i in infos) - i0.invDt_hyp) <= 1e-14 * i0.invDt_hyp
+        assert abs(max(i.maxMach for i in infos) - i0.maxMach) <= 1e-14 * i0.maxMach
+        a, b = blocks
+        own_a = a["vc"][:, ng:ng + half]                       # block 0 owns planes [0, half)
+        own_b = b["vc"][:, ng + E:ng + E + (nz - half)]        # block 1 owns [half, nz)
+        a["vc"][:, ng + half:ng + half + E] = own_b[:, :E]      # refresh the host halos from the neighbour's own planes
+        b["vc"][:, ng:ng + E] = own_a[:, half - E:half]
+        dt = min(0.3 / i0.invDt_hyp, 1.1 * dt)
+    ref = full.get_interior()
+    got = np.concatenate([blocks[0]["vc"][blocks[0]["h"].interior()][:, :half],
+                          blocks[1]["vc"][blocks[1]["h"].interior()][:, E:]], axis=1)
+    assert rel_err(got, ref) <= 1e-14
+    full.close()
+    for b in blocks:
+        b["h"].close()
+
+
+@pytest.mark.parametrize("recon,rk", [("LINEAR", "RK2"), ("PARABOLIC", "RK3")])
 @pytest.mark.parametrize("bcs", [("reflective", "outflow", "outflow", "reflective", "periodic", "periodic"),
                                  ("periodic", "periodic", "reflective", "reflective", "outflow", "reflective"),
                                  ("outflow",) * 6])
