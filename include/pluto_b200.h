@@ -29,8 +29,10 @@ extern "C" {
 
 /* GEOMETRY: same values as Src/pluto.h:34-37.  The other option codes below are this
  * library's own; the shim translates the reference macros (pluto.h:66-70,254-287). */
-#define PB200_CARTESIAN 1   /* pluto.h: CARTESIAN   */
-#define PB200_SPHERICAL 4   /* pluto.h: SPHERICAL   */
+#define PB200_CARTESIAN   1 /* pluto.h: CARTESIAN   */
+#define PB200_CYLINDRICAL 2 /* pluto.h: CYLINDRICAL (r, z), 1-D / 2-D */
+#define PB200_POLAR       3 /* pluto.h: POLAR (r, phi, z) */
+#define PB200_SPHERICAL   4 /* pluto.h: SPHERICAL (r, theta, phi) */
 
 #define PB200_FLAT      1   /* RECONSTRUCTION FLAT      */
 #define PB200_LINEAR    2   /* RECONSTRUCTION LINEAR    (Src/States/plm_states.c)  */

@@ -23,7 +23,7 @@
 namespace pb {
 
 enum { GF_MINMOD = 1, GF_FLAT = 2, GF_HLL = 4, GF_ENTROPY = 8, GF_C2P_FAIL = 64 };   // pluto.h:212-221
-enum { GEO_CARTESIAN = 1, GEO_SPHERICAL = 4 };
+enum { GEO_CARTESIAN = 1, GEO_CYLINDRICAL = 2, GEO_POLAR = 3, GEO_SPHERICAL = 4 };    // Src/pluto.h:34-37
 
 // LINE_DRIVEN_WIND SIROCCO_MODE (Src/LineDriven/line_connect.c) + the user boundaries of
 // Test_Problems/LineDrivenWind/cv_idl/init.c
@@ -485,6 +485,7 @@ static __global__ void gen_riemann(GenDev g, GenArgs a, GenBox b) {
     for (int nv = 0; nv < NV; nv++) { vL[nv] = a.VP[nv * d.sv + o]; vR[nv] = a.VM[nv * d.sv + o + st]; }
     const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
     machv = gen_face<NV>(g, dir, vL, vR, hll, F);
+    if ((d.bf_kind & 2) && !g.iso) F[pidx<NV>()] += F[iRHO] * bf_at(d, 4 + dir, i, j, k);   // TotalFlux(), rhs.c:171-179,525
     const long nz = d.sv;
 #pragma unroll
     for (int nv = 0; nv < NV + 2; nv++) a.F[nv * nz + o] = F[nv];
@@ -789,22 +790,30 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
       const double Ap = gen_A(g, dir, k, j, i), Am = gen_A(g, dir, m[2], m[1], m[0]);
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) { fp[nv] = fp[nv] * Ap; fm[nv] = fm[nv] * Am; }
-      if (dir == 0) { fp[3] *= fabs(__ldg(g.xr[0] + n)); fm[3] *= fabs(__ldg(g.xr[0] + n - 1)); }
-      else if (dir == 1) { fp[3] *= fabs(__ldg(g.sp + n)); fm[3] *= fabs(__ldg(g.sp + n - 1)); }
+      // angular momentum: iMPHI = VX2 (POLAR: r, phi, z) or VX3 (CYLINDRICAL r, z [, phi]; SPHERICAL r, theta, phi)
+      const bool mphi2 = g.geometry == GEO_POLAR;
+      if (dir == 0) {
+        const double ap = fabs(__ldg(g.xr[0] + n)), am = fabs(__ldg(g.xr[0] + n - 1));
+        if (mphi2) { fp[2] *= ap; fm[2] *= am; } else { fp[3] *= ap; fm[3] *= am; }
+      } else if (dir == 1 && g.geometry == GEO_SPHERICAL) { fp[3] *= fabs(__ldg(g.sp + n)); fm[3] *= fabs(__ldg(g.sp + n - 1)); }
       const double dtdV = dt / __ldg(g.dV + o);
       double dtdl = dt / __ldg(g.dx[dir] + n);
       if (dir != 0) dtdl = dtdl * __ldg(g.dx_dl[dir] + (long)j * d.tot[0] + i);
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (fp[nv] - fm[nv]);
       dpn = dtdl * (pp - pm);
-      if (dir == 0) rhs[3] /= fabs(__ldg(g.x[0] + n));
-      else if (dir == 1) rhs[3] /= fabs(__ldg(g.s + n));
+      if (dir == 0) { if (mphi2) rhs[2] /= fabs(__ldg(g.x[0] + n)); else rhs[3] /= fabs(__ldg(g.x[0] + n)); }
+      else if (dir == 1 && g.geometry == GEO_SPHERICAL) rhs[3] /= fabs(__ldg(g.s + n));
     }
     double sn = 0.0;   // source of the normal momentum
     if (g.geometry == GEO_SPHERICAL && dir == 0) {
       const double r_1 = 1.0 / __ldg(g.x[0] + n);
       const double Sm = vg[iRHO] * (vg[2] * vg[2] + vg[3] * vg[3]);
       sn = dt * Sm * r_1;
+    } else if ((g.geometry == GEO_CYLINDRICAL || g.geometry == GEO_POLAR) && dir == 0) {   // rhs_source.c:201-227
+      const double r_1 = 1.0 / __ldg(g.x[0] + n);
+      const double vphi = g.geometry == GEO_POLAR ? vg[2] : vg[3];
+      sn = dt * (vg[iRHO] * vphi * vphi - 0.0) * r_1;
     } else if (g.geometry == GEO_SPHERICAL && dir == 1) {
       const double r_1 = 1.0 / __ldg(g.rt + i);
       const double ct = __ldg(g.cot + n);          // 1/tan(x2[j]) with the host's libm tan(), like the reference
@@ -813,9 +822,32 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
     }
     // accumulate in the reference's order: flux difference, pressure gradient, geometry, forces
     double rn = (dir == 0 ? rhs[1] : (dir == 1 ? rhs[2] : rhs[3])) - dpn;
-    if (g.geometry == GEO_SPHERICAL && dir <= 1) rn += sn;
-    for (int pass = 0; pass < 2; pass++) {
+    if ((g.geometry == GEO_SPHERICAL && dir <= 1) || ((g.geometry == GEO_CYLINDRICAL || g.geometry == GEO_POLAR) && dir == 0)) rn += sn;
+    for (int pass = 0; pass < 3; pass++) {
+      // pass 0: BodyForceVector (rhs_source.c:253-272,360-376,428-440); pass 1: BodyForcePotential (:274-279,378-383,
+      // 442-447); pass 2: LineForce, same pattern as pass 0 (:284-297,386-396,448-458)
       double gv[3];
+      if (pass == 1) {
+        if (!(d.bf_kind & 2)) continue;
+        double dtdx;
+        if (dir == 0) dtdx = dt / __ldg(g.dx[0] + n);
+        else if (dir == 1) {
+          double scrh = dt;
+          if (g.geometry == GEO_POLAR) scrh /= __ldg(g.x[0] + i);
+          else if (g.geometry == GEO_SPHERICAL) scrh /= __ldg(g.rt + i);
+          dtdx = scrh / __ldg(g.dx[1] + n);
+        } else {
+          double scrh = dt;
+          if (g.geometry == GEO_SPHERICAL) scrh *= __ldg(g.dx_dl[2] + (long)j * d.tot[0] + i);   // dx2[j] / (rt[i] dmu[j])
+          dtdx = scrh / __ldg(g.dx[2] + n);
+        }
+        int m[3] = {i, j, k};
+        m[dir] -= 1;
+        const double php = bf_at(d, 4 + dir, i, j, k), phm = bf_at(d, 4 + dir, m[0], m[1], m[2]);
+        rn -= dtdx * vg[iRHO] * (php - phm);
+        if (!g.iso) rhs[pidx<NV>()] -= bf_at(d, 3, i, j, k) * rhs[iRHO];
+        continue;
+      }
       if (pass == 0) {
         if (!(d.bf_kind & 1)) continue;
         gv[0] = bf_at(d, 0, i, j, k); gv[1] = bf_at(d, 1, i, j, k); gv[2] = bf_at(d, 2, i, j, k);
@@ -852,7 +884,7 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
     }
     // GetInverse_dl (set_geometry.c:303-375) and C_dt (update_stage.c:303-322)
     double inv_dl = __ldg(g.inv_dx[dir] + n);
-    if (g.geometry == GEO_SPHERICAL && dir == 1) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i));
+    if ((g.geometry == GEO_SPHERICAL || g.geometry == GEO_POLAR) && dir == 1) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i));
     if (g.geometry == GEO_SPHERICAL && dir == 2) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i)) / __ldg(g.sin2 + j);
     if (d.ndim > 1) {
       cdt_c = 0.5 * (cm_ + cp_) * inv_dl;
@@ -881,7 +913,7 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
     const double cp_ = a.F[(NV + 1) * nz + o], cm_ = a.F[(NV + 1) * nz + o - st];
     // centre state (stateC->v) and, for the spherical r sweep, vc = (vp + vm)/2  (rhs_source.c:229-232)
     double vg[NV];
-    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+    if (g.geometry != GEO_CARTESIAN && dir == 0) {       // spherical, cylindrical, polar r sweep: (vp + vm)/2
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (a.VP[nv * nz + o] + a.VM[nv * nz + o]);
     } else {
@@ -943,6 +975,7 @@ static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, i
     for (int nv = 0; nv < NV; nv++) vR[nv] = sh[nv][tid + L];
     const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
     machv = gen_face<NV>(g, dir, vp, vR, hll, F);
+    if ((d.bf_kind & 2) && !g.iso) F[pidx<NV>()] += F[iRHO] * bf_at(d, 4 + dir, i, j, k);   // TotalFlux(), rhs.c:171-179,525
   } else {
 #pragma unroll
     for (int nv = 0; nv < NV + 2; nv++) F[nv] = 0.0;
@@ -957,7 +990,7 @@ static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, i
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) { fp[nv] = F[nv]; fm[nv] = sh[nv][tid - L]; }
     const double pp = F[NV], pm = sh[NV][tid - L], cp_ = F[NV + 1], cm_ = sh[NV + 1][tid - L];
-    if (g.geometry == GEO_SPHERICAL && dir == 0) {
+    if (g.geometry != GEO_CARTESIAN && dir == 0) {
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) vg[nv] = 0.5 * (vp[nv] + vm[nv]);
     } else {

@@ -63,8 +63,9 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (!cfg || !out) return fail(PB200_EINVAL, "null argument");
   *out = nullptr;
   if (cfg->dimensions < 1 || cfg->dimensions > 3) return fail(PB200_EINVAL, "dimensions must be 1..3");
-  if (cfg->geometry != PB200_CARTESIAN && cfg->geometry != PB200_SPHERICAL)
-    return fail(PB200_ENOTSUP, "geometry: CARTESIAN and SPHERICAL are built");
+  if (cfg->geometry < PB200_CARTESIAN || cfg->geometry > PB200_SPHERICAL) return fail(PB200_EINVAL, "bad geometry");
+  if (cfg->geometry == PB200_CYLINDRICAL && cfg->dimensions == 3)
+    return fail(PB200_ENOTSUP, "GEOMETRY CYLINDRICAL is 1-D / 2-D (r, z) in the reference; use POLAR for (r, phi, z)");
   // curvilinear geometry, characteristic limiting, MULTID flattening and the entropy switch run
   // on the general-grid path (pb200_gen.cu)
   const bool iso = cfg->eos == PB200_EOS_ISOTHERMAL;
@@ -75,8 +76,6 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
                    cfg->entropy_switch || iso;
   if (gen && cfg->reconstruction != PB200_LINEAR)
     return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR");
-  if (cfg->body_force & PB200_BF_POTENTIAL && gen)
-    return fail(PB200_ENOTSUP, "BODY_FORCE POTENTIAL on the general-grid path");
   if (cfg->ntracer < 0 || cfg->ntracer > 2) return fail(PB200_ENOTSUP, "ntracer must be 0..2");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
@@ -363,7 +362,8 @@ static int boundary_on(pb200_ctx *c, double *V, unsigned sides = 0x3f, int k0 = 
     b.nghost = c->cfg.nghost;
     for (int nv = 0; nv < 16; nv++) b.sign[nv] = 1.0;
     b.sign[1 + side / 2] = -1.0;  // FlipSign(): normal velocity (Src/boundary.c:503)
-    if (type == PB200_BC_AXISYMMETRIC && c->cfg.geometry != PB200_CARTESIAN) b.sign[3] = -1.0;  // iVPHI (boundary.c:548)
+    if (type == PB200_BC_AXISYMMETRIC && c->cfg.geometry != PB200_CARTESIAN)
+      b.sign[c->cfg.geometry == PB200_POLAR ? 2 : 3] = -1.0;  // iVPHI: VX2 (POLAR), VX3 otherwise (boundary.c:548, pluto.h)
     int ext[3] = {D.tot[0], D.tot[1], D.tot[2]};
     ext[side / 2] = b.nghost;
     if (side < 4) ext[2] = k1 - k0;

@@ -81,7 +81,10 @@ int pb200_gen_setup(pb200_ctx *c) {
   for (int i = 0; i < n1; i++) {                 // set_geometry.c:83-97
     double xL = x1m[i], xR = x1p[i];
     if (geo == PB200_CARTESIAN) { xgc[0][i] = x1[i]; rt[i] = x1[i]; }
-    else {
+    else if (geo == PB200_CYLINDRICAL || geo == PB200_POLAR) {
+      xgc[0][i] = x1[i] + dx1[i] * dx1[i] / (12.0 * x1[i]);
+      rt[i] = x1[i];
+    } else {
       xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
       rt[i] = (xR * xR * xR - xL * xL * xL) / (xR * xR - xL * xL) / 1.5;
     }
@@ -103,7 +106,10 @@ int pb200_gen_setup(pb200_ctx *c) {
   for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
     double v;
     if (geo == PB200_CARTESIAN) { v = dx1[i]; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * dx3[k]; }
-    else {
+    else if (geo == PB200_CYLINDRICAL || geo == PB200_POLAR) {     // set_geometry.c:124-129
+      double dVr = fabs(x1[i]) * dx1[i];
+      v = dVr; if (nd > 1) v = v * dx2[j]; if (nd > 2) v = v * (geo == PB200_POLAR ? dx3[k] : 1.0);
+    } else {
       double dVr = fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
       double dm_ = fabs(cos(x2m[j]) - cos(x2p[j]));
       v = dVr; if (nd > 1) v = v * dm_; if (nd > 2) v = v * dx3[k];
@@ -121,7 +127,11 @@ int pb200_gen_setup(pb200_ctx *c) {
   for (int k = 0; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = -1; i < n1; i++) {
     double a;
     if (geo == PB200_CARTESIAN) { a = 1.0; if (nd > 1) a = a * dx2[j]; if (nd > 2) a = a * dx3[k]; }
-    else {
+    else if (geo == PB200_CYLINDRICAL || geo == PB200_POLAR) {     // set_geometry.c:150-161
+      a = (i == -1) ? fabs(x1m[0]) : fabs(x1p[i]);
+      if (nd > 1) a = a * dx2[j];
+      if (nd > 2) a = a * (geo == PB200_POLAR ? dx3[k] : 1.0);
+    } else {
       double dm_ = fabs(cos(x2m[j]) - cos(x2p[j]));
       a = (i == -1) ? x1m[0] * x1m[0] : x1p[i] * x1p[i];
       if (nd > 1) a = a * dm_;
@@ -131,7 +141,8 @@ int pb200_gen_setup(pb200_ctx *c) {
   }
   for (int k = 0; k < n3; k++) for (int j = -1; j < n2; j++) for (int i = 0; i < n1; i++) {
     double a;
-    if (geo == PB200_CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    if (geo == PB200_CARTESIAN || geo == PB200_POLAR) { a = dx1[i]; if (nd > 1) a = a * 1.0; if (nd > 2) a = a * dx3[k]; }
+    else if (geo == PB200_CYLINDRICAL) { a = fabs(x1[i]); if (nd > 1) a = a * dx1[i]; if (nd > 2) a = a * 1.0; }   // set_geometry.c:181-182
     else {
       a = fabs(x1[i]) * dx1[i];
       if (nd > 1) a = a * ((j == -1) ? fabs(sin(x2m[0])) : fabs(sin(x2p[j])));
@@ -142,6 +153,7 @@ int pb200_gen_setup(pb200_ctx *c) {
   for (int k = -1; k < n3; k++) for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) {
     double a;
     if (geo == PB200_CARTESIAN) { a = dx1[i]; if (nd > 1) a = a * dx2[j]; }
+    else if (geo == PB200_CYLINDRICAL) a = 1.0;      // set_geometry.c:203-204
     else { a = fabs(x1[i]) * dx1[i]; if (nd > 1) a = a * dx2[j]; }
     A[2][G.Aoff[2] + (long)k * G.Ask[2] + (long)j * G.Asj[2] + i] = a;
   }
@@ -152,6 +164,8 @@ int pb200_gen_setup(pb200_ctx *c) {
       dxdl[1][(size_t)j * n1 + i] = 1.0 / rt[i];
       dxdl[2][(size_t)j * n1 + i] = dx2[j] / (rt[i] * dmu[j]);
     }
+  if (geo == PB200_POLAR)
+    for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) dxdl[1][(size_t)j * n1 + i] = 1.0 / x1[i];   // set_geometry.c:228
   for (int d = 0; d < 3; d++) {
     int n = D.tot[d];
     cp[d].assign(n, 2.0); cm[d].assign(n, 2.0); wp[d].assign(n, 1.0); wm[d].assign(n, 1.0);

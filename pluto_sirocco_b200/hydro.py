@@ -311,7 +311,7 @@ class Hydro:
         cfg.small_pressure = small_pressure
         cfg.device = device
         cfg.body_force = int(body_force)
-        cfg.geometry = {"CARTESIAN": L.CARTESIAN, "SPHERICAL": L.SPHERICAL}[geometry]
+        cfg.geometry = {"CARTESIAN": 1, "CYLINDRICAL": 2, "POLAR": 3, "SPHERICAL": 4}[geometry]
         cfg.char_limiting = int(bool(char_limiting))
         cfg.shock_flattening = int(bool(shock_flattening))
         cfg.entropy_switch = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
@@ -392,6 +392,17 @@ class Hydro:
         if self._grid is not None:
             return 0.5 * (self._grid[d][0] + self._grid[d][1])
         return self.cell_centers(d)
+
+    @property
+    def xr(self):
+        """grid->xr[d] (upper zone faces incl. ghosts) of the three directions."""
+        if self._grid is not None:
+            return [self._grid[d][1] for d in range(3)]
+        out = []
+        for d in range(3):
+            dx = (self.cfg.xend[d] - self.cfg.xbeg[d]) / self.nx[d]
+            out.append(self.cfg.xbeg[d] + (np.arange(self.tot[d]) - self.beg[d] + 1) * dx)
+        return out
 
     def cell_centers(self, d):
         n = self.tot[d]

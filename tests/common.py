@@ -9,6 +9,9 @@ _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / 
 # these options); the iso* fixtures (EOS ISOTHERMAL) run on the CUDA path too: ISO_CASES
 _CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot", "ausm")
 ISO_CASES = ["iso2d_hll", "iso2d_hllc", "iso2d_flat_hllc", "iso3d_tvdlf", "iso_sph2d_flat_hll"]
+# CYLINDRICAL / POLAR geometry and BODY_FORCE POTENTIAL on curvilinear grids: on the CUDA path as well
+CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2d_hllc", "pol3d_hll", "pot_sph2d_hllc",
+                  "pot_sph3d_both_hll"]
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))

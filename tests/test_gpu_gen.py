@@ -122,6 +122,30 @@ def test_isothermal_per_step_vs_reference_dumps(Hydro, name):
     h.close()
 
 
+@pytest.mark.parametrize("name", __import__("common").CURV_GPU_CASES)
+def test_cylindrical_polar_potential_per_step_vs_reference_dumps(Hydro, name):
+    """GEOMETRY CYLINDRICAL (r, z) and POLAR (r, phi[, z]) and BODY_FORCE POTENTIAL (and VECTOR + POTENTIAL) on
+    spherical grids, on the CUDA path against the dumps of the compiled reference (user files oracle/problems/cyl,
+    sph): volumes / areas / centroids of set_geometry.c, the |r| weighting of the angular-momentum flux
+    (rhs.c:535-538, :268) with iMPHI = VX2 for POLAR, the centrifugal source on (vp + vm)/2 (rhs_source.c:201-227),
+    r dphi in the polar C_dt, the AXISYMMETRIC flip of iVPHI, Phi at the faces in the energy flux (rhs.c:171-179) and
+    the potential gradient / work terms (rhs_source.c:274-279,378-383,442-447)."""
+    g = load_golden(name)
+    kw = gen_kwargs_from_golden(g)
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    set_point_mass_gravity(h, float(g["gm"]))
+    data, steps = g["data"], g["steps"]
+    for n in range(len(data) - 1):
+        h.set_interior(data[n])
+        dt = steps[n, 2]
+        info = h.advance_step(dt)
+        e = rel_err(h.get_interior(), data[n + 1])
+        assert e <= TOL_STEP, (name, n, e)
+        dtn = h.next_time_step(info.invDt_hyp, g["cfl"], g["cfl_max_var"], dt, g["first_dt"])
+        assert abs(dtn - steps[n + 1, 2]) <= TOL_STEP * steps[n + 1, 2], (name, n)
+    h.close()
+
+
 def test_isothermal_line_driven_wind_vs_reference_dumps(Hydro):
     """Test_Problems/LineDrivenWind/cv_iso, the fork's isothermal wind problem (unmodified user files in the
     reference run that made the fixture): line force with T = T_ISO (line_connect.c:851-855), floors and user
