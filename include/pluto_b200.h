@@ -45,6 +45,8 @@ extern "C" {
 #define PB200_TVDLF 1       /* Solver tvdlf  -> LF_Solver   (Src/HD/tvdlf.c:38) */
 #define PB200_HLL   2       /* Solver hll    -> HLL_Solver  (Src/HD/hll.c:30)   */
 #define PB200_HLLC  3       /* Solver hllc   -> HLLC_Solver (Src/HD/hllc.c:28)  */
+#define PB200_ROE   4       /* Solver roe    -> Roe_Solver  (Src/HD/roe.c:48; general path) */
+#define PB200_TWO_SHOCK 5   /* Solver two_shock -> TwoShock_Solver (Src/HD/two_shock.c:28; EOS IDEAL, general path) */
 
 #define PB200_LIM_DEFAULT   0  /* LIMITER DEFAULT: MC rho, VL v, MM p (plm_states.c:202-244) */
 #define PB200_LIM_FLAT      1
@@ -103,7 +105,7 @@ typedef struct pb200_config {
   int device;            /* CUDA device ordinal */
   int body_force;        /* BODY_FORCE: 0 NO, PB200_BF_VECTOR, PB200_BF_POTENTIAL or both (pluto.h:76-77) */
   int char_limiting;     /* CHAR_LIMITING YES (Src/States/plm_states.c:481) */
-  int shock_flattening;  /* SHOCK_FLATTENING MULTID (Src/flag_shock.c:81) */
+  int shock_flattening;  /* SHOCK_FLATTENING: 0 NO, 1 MULTID (Src/flag_shock.c:81), 2 ONED (Src/States/flatten.c:58; 4 ghost zones) */
   int entropy_switch;    /* ENTROPY_SWITCH: 0 NO, 1 SELECTIVE, 2 ALWAYS (same values as Src/pluto.h:60-61);
                             NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219, flag_shock.c:146,256) */
   int eos;               /* EOS: 0 IDEAL, PB200_EOS_ISOTHERMAL (Src/EOS/Isothermal: no energy equation, NVAR = 4 + NTRACER;

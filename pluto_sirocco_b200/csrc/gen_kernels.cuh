@@ -52,6 +52,7 @@ struct GenDev {
   // EOS ISOTHERMAL (Src/EOS/Isothermal/eos.c): no energy equation, NFLX = 4, scalars start at index 4, p = cs2 rho
   int iso;
   double cs2;                          // g_isoSoundSpeed^2
+  int flatten_oned;                    // SHOCK_FLATTENING ONED (States/flatten.c); `flatten` is MULTID
   // 1-D grid arrays per direction (np_tot entries): grid->x, xr, dx, inv_dx and PLM_Coeffs
   const double *x[3], *xr[3], *dx[3], *inv_dx[3];
   const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
@@ -333,6 +334,30 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
     vpo[nv] = v[nv] + dvl[nv] * dp;
     vmo[nv] = v[nv] - dvl[nv] * dm;
   }
+  if (g.flatten_oned && n >= 3 && n <= d.tot[dir] - 4) {
+    // Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10), zones max(beg,3)..min(end,tot-4): the
+    // states are pulled towards the zone value by f = max(f_t[i], f_t[i + s]), s pointing down the pressure gradient
+    const double *Pv = V + (g.iso ? 0 : iPRS) * d.sv, *Vn = V + (1 + dir) * d.sv;
+    auto f_t = [&](long q) {
+      const double dpq = Pv[q + st] - Pv[q - st];
+      const double min_p = fmin(Pv[q + st], Pv[q - st]);
+      const double d2p = Pv[q + 2 * st] - Pv[q - 2 * st];
+      double scrh = fabs(dpq) / min_p;
+      if (scrh < 0.33 || (Vn[q + st] > Vn[q - st])) return 0.0;
+      scrh = 10.0 * (fabs(dpq / d2p) - 0.75);
+      scrh = fmin(1.0, scrh);
+      return fmax(0.0, scrh);
+    };
+    const long sj = (Pv[o + st] < Pv[o - st]) ? st : -st;
+    const double fj = fmax(f_t(o), f_t(o + sj));
+    const double om = 1.0 - fj;
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      const double vf = v[nv] * fj;
+      vmo[nv] = vf + vmo[nv] * om;
+      vpo[nv] = vf + vpo[nv] * om;
+    }
+  }
 }
 
 template <int NV>
@@ -424,6 +449,197 @@ PB_D double riemann_iso(const double (&vL)[NV], const double (&vR)[NV], double c
   return machv;
 }
 
+// ---- Roe_Solver (HD/roe.c:48-346, ROE_AVERAGE YES) and TwoShock_Solver (HD/two_shock.c:28-243), both equations of
+// state for Roe, EOS IDEAL for two-shock.  q: (rho, v_n, v_t, v_b[, p], scalars...) in sweep-local order with NF = 4
+// (isothermal) or 5 flux components; f[0..NF-1] without the pressure in f[1].  Small-grid options: written with the
+// reference's own operations.
+enum { SOLVER_ROE = 4, SOLVER_TWO_SHOCK = 5 };
+template <int NV>
+PB_D double riemann_roe_ts(const double (&vL)[NV], const double (&vR)[NV], bool iso, double cs2, double gamma, int solver,
+                           bool force_hll, int ndim, double (&f)[NV], double &prs, double &cmax) {
+  constexpr int P = NV > 4 ? 4 : 0;
+  const int nf = iso ? 4 : 5;
+  double uL[5], uR[5], fL[5], fR[5];
+  uL[0] = vL[0]; uL[1] = vL[0] * vL[1]; uL[2] = vL[0] * vL[2]; uL[3] = vL[0] * vL[3];
+  uR[0] = vR[0]; uR[1] = vR[0] * vR[1]; uR[2] = vR[0] * vR[2]; uR[3] = vR[0] * vR[3];
+  fL[0] = uL[1]; fL[1] = uL[1] * vL[1]; fL[2] = uL[2] * vL[1]; fL[3] = uL[3] * vL[1];
+  fR[0] = uR[1]; fR[1] = uR[1] * vR[1]; fR[2] = uR[2] * vR[1]; fR[3] = uR[3] * vR[1];
+  const double gmm1 = gamma - 1.0;
+  double a2L, a2R, pL, pR;
+  uL[4] = uR[4] = fL[4] = fR[4] = 0.0;
+  if (!iso) {
+    uL[4] = vL[1] * vL[1] + vL[2] * vL[2] + vL[3] * vL[3];
+    uL[4] = 0.5 * vL[0] * uL[4] + vL[P] / gmm1;
+    uR[4] = vR[1] * vR[1] + vR[2] * vR[2] + vR[3] * vR[3];
+    uR[4] = 0.5 * vR[0] * uR[4] + vR[P] / gmm1;
+    a2L = gamma * vL[P] / vL[0]; a2R = gamma * vR[P] / vR[0];
+    fL[4] = (uL[4] + vL[P]) * vL[1]; fR[4] = (uR[4] + vR[P]) * vR[1];
+    pL = vL[P]; pR = vR[P];
+  } else { a2L = a2R = cs2; pL = a2L * vL[0]; pR = a2R * vR[0]; }
+  double fl[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, machv = 0.0;
+  bool done = false;
+  if (force_hll) {       // roe.c:101-116, two_shock.c:66-88: HLL in zones flagged by MULTID flattening
+    const double aL = sqrt(a2L), aR = sqrt(a2R);
+    double bmin = fmin(vL[1] - aL, vR[1] - aR), bmax = fmax(vL[1] + aL, vR[1] + aR);
+    double scrh = fabs(vL[1]) + fabs(vR[1]);
+    scrh /= aL + aR;
+    machv = scrh;
+    cmax = fmax(fabs(bmin), fabs(bmax));
+    bmin = fmin(0.0, bmin);
+    bmax = fmax(0.0, bmax);
+    scrh = 1.0 / (bmax - bmin);
+    for (int nv = nf; nv--;) { fl[nv] = bmin * bmax * (uR[nv] - uL[nv]) + bmax * fL[nv] - bmin * fR[nv]; fl[nv] *= scrh; }
+    prs = (bmax * pL - bmin * pR) * scrh;
+    done = true;
+  }
+  if (!done && solver == SOLVER_ROE) {
+    const double delta = 1.e-7, gmm1_inv = 1.0 / gmm1;
+    double Rc[5][5], lambda[5], alambda[5], eta[5], dv[5], um[4];
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+#pragma unroll
+      for (int r = 0; r < 5; r++) Rc[q][r] = 0.0;
+      lambda[q] = eta[q] = dv[q] = 0.0;
+    }
+    for (int nv = nf; nv--;) dv[nv] = (nv == 4 ? vR[P] - vL[P] : vR[nv] - vL[nv]);
+    double sq = sqrt(vR[0] / vL[0]);
+    um[0] = vL[0] * sq;
+    sq = 1.0 / (1.0 + sq);
+    const double cq = 1.0 - sq;
+    um[1] = sq * vL[1] + cq * vR[1];
+    um[2] = sq * vL[2] + cq * vR[2];
+    um[3] = sq * vL[3] + cq * vR[3];
+    double a2, a, h = 0.0, vel2 = 0.0;
+    if (!iso) {
+      vel2 = um[1] * um[1] + um[2] * um[2] + um[3] * um[3];     // (global order VX1..VX3: a permutation of the same sum
+      double hl = 0.5 * (vL[1] * vL[1] + vL[2] * vL[2] + vL[3] * vL[3]);   //  of three products; <= 1 ulp)
+      hl += a2L * gmm1_inv;
+      double hr = 0.5 * (vR[1] * vR[1] + vR[2] * vR[2] + vR[3] * vR[3]);
+      hr += a2R * gmm1_inv;
+      h = sq * hl + cq * hr;
+      a2 = gmm1 * (h - 0.5 * vel2);
+      a = sqrt(a2);
+    } else { a2 = 0.5 * (a2L + a2R); a = sqrt(a2); }
+    int nn = 0;                         // u - c_s
+    lambda[nn] = um[1] - a;
+    if (!iso) eta[nn] = 0.5 / a2 * (dv[4] - dv[1] * um[0] * a);
+    else eta[nn] = 0.5 * (dv[0] - um[0] * dv[1] / a);
+    Rc[0][nn] = 1.0; Rc[1][nn] = um[1] - a; Rc[2][nn] = um[2]; Rc[3][nn] = um[3];
+    if (!iso) Rc[4][nn] = h - um[1] * a;
+    nn = 1;                             // u + c_s
+    lambda[nn] = um[1] + a;
+    if (!iso) eta[nn] = 0.5 / a2 * (dv[4] + dv[1] * um[0] * a);
+    else eta[nn] = 0.5 * (dv[0] + um[0] * dv[1] / a);
+    Rc[0][nn] = 1.0; Rc[1][nn] = um[1] + a; Rc[2][nn] = um[2]; Rc[3][nn] = um[3];
+    if (!iso) Rc[4][nn] = h + um[1] * a;
+    if (!iso) {                         // u (entropy wave)
+      nn = 2;
+      lambda[nn] = um[1];
+      eta[nn] = dv[0] - dv[4] / a2;
+      Rc[0][nn] = 1.0; Rc[1][nn] = um[1]; Rc[2][nn] = um[2]; Rc[3][nn] = um[3];
+      Rc[4][nn] = 0.5 * vel2;
+    }
+    nn++;                               // u (shear waves)
+    lambda[nn] = um[1];
+    eta[nn] = um[0] * dv[2];
+    Rc[2][nn] = 1.0;
+    if (!iso) Rc[4][nn] = um[2];
+    nn++;
+    lambda[nn] = um[1];
+    eta[nn] = um[0] * dv[3];
+    Rc[3][nn] = 1.0;
+    if (!iso) Rc[4][nn] = um[3];
+    cmax = fabs(um[1]) + a;
+    machv = fabs(um[1] / a);
+    if (ndim > 1) {                     // roe.c:262-287: HLL inside strong shocks
+      double scrh;
+      if (!iso) { scrh = fabs(vL[P] - vR[P]); scrh /= fmin(vL[P], vR[P]); }
+      else { scrh = fabs(vL[0] - vR[0]); scrh /= fmin(vL[0], vR[0]); scrh *= a * a; }
+      if (scrh > 0.5 && (vR[1] < vL[1])) {
+        const double bmin = fmin(0.0, lambda[0]), bmax = fmax(0.0, lambda[1]);
+        const double scrh1 = 1.0 / (bmax - bmin);
+        for (int nv = nf; nv--;) { fl[nv] = bmin * bmax * (uR[nv] - uL[nv]) + bmax * fL[nv] - bmin * fR[nv]; fl[nv] *= scrh1; }
+        prs = (bmax * pL - bmin * pR) * scrh1;
+        done = true;
+      }
+    }
+    if (!done) {
+      for (int nv = nf; nv--;) alambda[nv] = fabs(lambda[nv]);
+      if (alambda[0] <= delta) alambda[0] = 0.5 * lambda[0] * lambda[0] / delta + 0.5 * delta;   // entropy fix
+      if (alambda[1] <= delta) alambda[1] = 0.5 * lambda[1] * lambda[1] / delta + 0.5 * delta;
+      for (int nv = nf; nv--;) {
+        fl[nv] = fL[nv] + fR[nv];
+        for (int kk = nf; kk--;) fl[nv] -= alambda[kk] * eta[kk] * Rc[nv][kk];
+        fl[nv] *= 0.5;
+      }
+      prs = 0.5 * (pL + pR);
+    }
+  } else if (!done) {
+    // TwoShock_Solver, two_shock.c:90-243 (EOS IDEAL; MAX_ITER 5, small_p = small_rho = 1e-9)
+    const double small_p = 1.e-9, small_rho = 1.e-9;
+    const double g1_g = 0.5 * (gamma + 1.0) / gamma;
+    const double cl = sqrt(gamma * vL[P] * vL[0]), cr = sqrt(gamma * vR[P] * vR[0]);
+    const double taul = 1.0 / vL[0], taur = 1.0 / vR[0];
+    double vxl = 0.0, vxr = 0.0, scrh1, scrh2, scrh3, scrh4, dp;
+    double pstar = vR[P] - vL[P] - cr * (vR[1] - vL[1]);
+    pstar = vL[P] + pstar * cl / (cl + cr);
+    pstar = fmax(small_p, pstar);
+    for (int iter = 1; iter <= 5; iter++) {
+      vxl = cl * sqrt(1.0 + g1_g * (pstar - vL[P]) / vL[P]);
+      vxr = cr * sqrt(1.0 + g1_g * (pstar - vR[P]) / vR[P]);
+      scrh1 = vxl * vxl;
+      scrh1 = 2.0 * scrh1 * vxl / (scrh1 + cl * cl);
+      scrh2 = vxr * vxr;
+      scrh2 = 2.0 * scrh2 * vxr / (scrh2 + cr * cr);
+      scrh3 = vL[1] - (pstar - vL[P]) / vxl;
+      scrh4 = vR[1] + (pstar - vR[P]) / vxr;
+      dp = scrh1 * scrh2 / (scrh1 + scrh2) * (scrh4 - scrh3);
+      pstar -= dp;
+      pstar = fmax(small_p, pstar);
+      if (fabs(dp / pstar) < 1.e-6) break;
+    }
+    scrh3 = vL[1] - (pstar - vL[P]) / vxl;
+    scrh4 = vR[1] + (pstar - vR[P]) / vxr;
+    const double ustar = 0.5 * (scrh3 + scrh4);
+    const bool left = ustar > 0.0;
+    const double sigma = left ? 1.0 : -1.0, taus = left ? taul : taur, cs = left ? cl * taul : cr * taur, zs = left ? vxl : vxr;
+    const double qs0 = left ? vL[0] : vR[0], qs1 = left ? vL[1] : vR[1], qsp = left ? vL[P] : vR[P];
+    const double qst = left ? vL[2] : vR[2], qsb = left ? vL[3] : vR[3];
+    double rho_star = taus - (pstar - qsp) / (zs * zs);
+    rho_star = fmax(small_rho, 1.0 / rho_star);
+    const double cstar0 = sqrt(gamma * pstar / rho_star);
+    double lambda_s, lambda_star;
+    if (pstar < qsp) { lambda_s = cs - sigma * qs1; lambda_star = cstar0 - sigma * ustar; }
+    else lambda_s = lambda_star = zs * taus - sigma * qs1;
+    double vS0, vS1, vSp;
+    if (lambda_star > 0.0) { vS0 = rho_star; vS1 = ustar; vSp = pstar; }
+    else if (lambda_s < 0.0) { vS0 = qs0; vS1 = qs1; vSp = qsp; }
+    else {
+      scrh1 = fmax(lambda_s - lambda_star, lambda_s + lambda_star);
+      scrh1 = fmax(1.e-12, scrh1);
+      const double zeta = 0.5 * (1.0 + (lambda_s + lambda_star) / scrh1);
+      vS0 = zeta * rho_star + (1.0 - zeta) * qs0;
+      vS1 = zeta * ustar + (1.0 - zeta) * qs1;
+      vSp = zeta * pstar + (1.0 - zeta) * qsp;
+    }
+    const double uS1 = vS0 * vS1, uS2 = vS0 * qst, uS3 = vS0 * qsb;
+    double uS4 = vS1 * vS1 + qst * qst + qsb * qsb;
+    uS4 = 0.5 * vS0 * uS4 + vSp / gmm1;
+    const double a2S = gamma * vSp / vS0;
+    fl[0] = uS1; fl[1] = uS1 * vS1; fl[2] = uS2 * vS1; fl[3] = uS3 * vS1; fl[4] = (uS4 + vSp) * vS1;
+    prs = vSp;
+    const double cstar = sqrt(a2S);
+    machv = fabs(vS1) / cstar;
+    cmax = fabs(vS1) + cstar;
+  }
+#pragma unroll
+  for (int nv = 0; nv < 4; nv++) f[nv] = fl[nv];
+  if (!iso) f[P] = fl[4];
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) if (nv >= nf) f[nv] = f[0] * (f[0] > 0.0 ? vL[nv] : vR[nv]);    // adv_flux.c:61-72
+  return machv;
+}
+
 // ---- Riemann solver + AdvectFlux at the face between zone n and n+1 -------------------------
 // vLg / vRg: left / right state in GLOBAL variable order; F: flux in global order, F[NV] = pressure, F[NV+1] = cmax
 template <int NV>
@@ -436,9 +652,12 @@ PB_D double gen_face(const GenDev &g, int dir, const double (&vLg)[NV], const do
   vL[3] = dir == 0 ? vLg[3] : (dir == 1 ? vLg[1] : vLg[2]); vR[3] = dir == 0 ? vRg[3] : (dir == 1 ? vRg[1] : vRg[2]);
 #pragma unroll
   for (int nv = 4; nv < NV; nv++) { vL[nv] = vLg[nv]; vR[nv] = vRg[nv]; }
-  if (g.iso) {
+  if (g.iso || g.solver >= SOLVER_ROE) {
     double fl[NV], prs, cmx;
-    const double mv = riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
+    const double mv = g.solver >= SOLVER_ROE
+                          ? riemann_roe_ts<NV>(vL, vR, g.iso != 0, g.cs2, g.d.gas.gamma, g.solver, hll, g.d.ndim, fl, prs, cmx)
+                          : riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
+    if (g.entropy) fl[NV - 1] = fl[0] * sel(fl[0] >= 0.0, vL[NV - 1], vR[NV - 1]);    // adv_flux.c:131-134
     F[0] = fl[0];
     F[1] = dir == 0 ? fl[1] : (dir == 1 ? fl[3] : fl[2]);
     F[2] = dir == 0 ? fl[2] : (dir == 1 ? fl[1] : fl[3]);

@@ -73,17 +73,20 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (iso && !(cfg->iso_sound_speed > 0.0)) return fail(PB200_EINVAL, "EOS ISOTHERMAL needs iso_sound_speed > 0 (g_isoSoundSpeed)");
   if (iso && cfg->entropy_switch) return fail(PB200_EINVAL, "ENTROPY_SWITCH needs an energy equation (EOS IDEAL)");
   const bool gen = cfg->geometry != PB200_CARTESIAN || cfg->char_limiting || cfg->shock_flattening ||
-                   cfg->entropy_switch || iso;
+                   cfg->entropy_switch || iso || cfg->solver >= PB200_ROE;
   if (gen && cfg->reconstruction != PB200_LINEAR)
     return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR");
   if (cfg->ntracer < 0 || cfg->ntracer > 2) return fail(PB200_ENOTSUP, "ntracer must be 0..2");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
     return fail(PB200_EINVAL, "bad reconstruction");
-  if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_HLLC) return fail(PB200_EINVAL, "bad solver");
+  if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_TWO_SHOCK) return fail(PB200_EINVAL, "bad solver");
+  if (cfg->solver == PB200_TWO_SHOCK && iso) return fail(PB200_ENOTSUP, "two_shock needs EOS IDEAL (Src/HD/set_solver.c:45-49)");
   if (cfg->time_stepping < PB200_EULER || cfg->time_stepping > PB200_RK3)
     return fail(PB200_EINVAL, "bad time_stepping");
   int need = cfg->reconstruction == PB200_PARABOLIC ? 3 : 2;
+  if (cfg->shock_flattening < 0 || cfg->shock_flattening > 2) return fail(PB200_EINVAL, "shock_flattening: 0 NO, 1 MULTID, 2 ONED");
+  if (cfg->shock_flattening == 2) need = 4;         // GetNghost(), Src/get_nghost.c:42-57
   if (cfg->nghost < need) return fail(PB200_EINVAL, "nghost too small for the reconstruction stencil");
   for (int d = 0; d < cfg->dimensions; d++)
     if (cfg->nx[d] < cfg->nghost) return fail(PB200_EINVAL, "nx < nghost in an active dimension");

@@ -63,7 +63,8 @@ int pb200_gen_setup(pb200_ctx *c) {
   G.geometry = geo;
   G.limiter = c->cfg.limiter;
   G.char_lim = c->cfg.char_limiting;
-  G.flatten = c->cfg.shock_flattening;
+  G.flatten = c->cfg.shock_flattening == 1;          // MULTID
+  G.flatten_oned = c->cfg.shock_flattening == 2;     // ONED
   G.entropy = c->cfg.entropy_switch;
   G.solver = c->cfg.solver;
   G.iso = c->cfg.eos == PB200_EOS_ISOTHERMAL;

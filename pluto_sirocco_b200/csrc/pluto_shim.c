@@ -353,8 +353,10 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
 #endif
 #if SHOCK_FLATTENING == MULTID
   cfg.shock_flattening = 1;
+#elif SHOCK_FLATTENING == ONED
+  cfg.shock_flattening = 2;
 #elif SHOCK_FLATTENING != NO
-#error "libplutob200: SHOCK_FLATTENING must be NO or MULTID"
+#error "libplutob200: SHOCK_FLATTENING must be NO, ONED or MULTID"
 #endif
 #if ENTROPY_SWITCH == ALWAYS || ENTROPY_SWITCH == SELECTIVE
   cfg.entropy_switch = ENTROPY_SWITCH;      /* same codes, Src/pluto.h:60-61 */
@@ -371,6 +373,10 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
   if      (d->fluidRiemannSolver == &HLLC_Solver) cfg.solver = PB200_HLLC;
   else if (d->fluidRiemannSolver == &HLL_Solver)  cfg.solver = PB200_HLL;
   else if (d->fluidRiemannSolver == &LF_Solver)   cfg.solver = PB200_TVDLF;
+  else if (d->fluidRiemannSolver == &Roe_Solver)  cfg.solver = PB200_ROE;
+#if EOS == IDEAL
+  else if (d->fluidRiemannSolver == &TwoShock_Solver) cfg.solver = PB200_TWO_SHOCK;
+#endif
   else {
     print ("! AdvanceStep(): this Riemann solver is not available in libplutob200\n");
     QUIT_PLUTO(1);

@@ -23,7 +23,7 @@ from . import _lib as L
 NVAR_HD = 5
 RHO, VX1, VX2, VX3, PRS = 0, 1, 2, 3, 4
 
-_SOLVERS = {"tvdlf": L.TVDLF, "hll": L.HLL, "hllc": L.HLLC}
+_SOLVERS = {"tvdlf": L.TVDLF, "hll": L.HLL, "hllc": L.HLLC, "roe": 4, "two_shock": 5}
 _RECON = {"FLAT": L.FLAT, "LINEAR": L.LINEAR, "PARABOLIC": L.PARABOLIC}
 _TSTEP = {"EULER": L.EULER, "RK2": L.RK2, "RK3": L.RK3}
 
@@ -313,7 +313,7 @@ class Hydro:
         cfg.body_force = int(body_force)
         cfg.geometry = {"CARTESIAN": 1, "CYLINDRICAL": 2, "POLAR": 3, "SPHERICAL": 4}[geometry]
         cfg.char_limiting = int(bool(char_limiting))
-        cfg.shock_flattening = int(bool(shock_flattening))
+        cfg.shock_flattening = {False: 0, None: 0, True: 1, "NO": 0, "MULTID": 1, "ONED": 2}[shock_flattening]
         cfg.entropy_switch = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
         cfg.eos = {"IDEAL": 0, "ISOTHERMAL": 1}[eos]
         cfg.iso_sound_speed = float(iso_sound_speed)

@@ -11,7 +11,11 @@ _CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot",
 ISO_CASES = ["iso2d_hll", "iso2d_hllc", "iso2d_flat_hllc", "iso3d_tvdlf", "iso_sph2d_flat_hll"]
 # CYLINDRICAL / POLAR geometry and BODY_FORCE POTENTIAL on curvilinear grids: on the CUDA path as well
 CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2d_hllc", "pol3d_hll", "pot_sph2d_hllc",
-                  "pot_sph3d_both_hll"]
+                  "pot_sph3d_both_hll",
+                  # Roe_Solver (both equations of state) and TwoShock_Solver
+                  "roe_cart2d", "roe_iso2d", "roe_sph2d_flat", "pot_pol2d_roe", "twoshock_sph2d_flat", "twoshock_sph3d",
+                  # SHOCK_FLATTENING ONED (States/flatten.c)
+                  "oned_iso2d_hll", "oned_sph2d_hllc", "oned_sph2d_char_roe"]
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
