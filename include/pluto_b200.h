@@ -156,6 +156,17 @@ typedef struct pb200_geometry {
   const double *dV, *A[3], *dx_dl[3], *rt, *s, *sp;
 } pb200_geometry;
 int  pb200_set_geometry(pb200_ctx *ctx, const pb200_geometry *geo);
+/* grid->uniform[d] (Src/set_grid.c:67-72, Src/runtime_setup.c:83-89): 1 when direction d is one uniform patch of
+ * pluto.ini.  RECONSTRUCTION PARABOLIC picks its interface weights by it (PPM_CoefficientsSet, Src/States/
+ * ppm_coeffs.c:88-136): closed forms on uniform directions, PPM_FindWeights otherwise.  Not called: a direction
+ * counts as uniform when its dx is constant to round-off. */
+int  pb200_set_grid_uniform(pb200_ctx *ctx, const int uniform[3]);
+/* PPM_CoefficientsSet() of one direction (Src/States/ppm_coeffs.c:60-290), host only: interface weights w[ntot][4]
+ * (v_{i+1/2} = sum_j w[i][j] v_{i-1+j}, entries 1 .. ntot-3) and the extremum coefficients h+ / h- [ntot]
+ * (PPM_Q6_Coeffs) from the zone edges (and grid->dx; null: xr - xl) of the direction, the way the general path
+ * evaluates them. */
+int  pb200_ppm_coefficients(int geometry, int dir, int ntot, const double *xl, const double *xr, const double *dx,
+                            int uniform, double *w, double *hp, double *hm);
 
 /* BODY_FORCE tables.  The reference calls the user's BodyForceVector(v, g, x1, x2, x3) per zone
  * and sweep (Src/MHD/rhs_source.c:256,367) and BodyForcePotential(x1, x2, x3) at zone centres

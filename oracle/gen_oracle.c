@@ -1515,6 +1515,18 @@ void gen_get_geometry(void *p, int which, double *out) {
   }
 }
 
+/* PPM coefficients of direction d for the tests: w[tot][4], hp[tot], hm[tot] */
+void gen_get_ppm(void *p, int d, double *w, double *hp, double *hm) {
+  gen_ctx *x = p;
+  const geom_t *g = x->g;
+  if (!g->pwp[d]) return;
+  for (int i = 0; i < g->tot[d]; i++) {
+    for (int j = 0; j < 4; j++) w[4 * i + j] = g->pwp[d][i][j];
+    hp[i] = g->php[d][i];
+    hm[i] = g->phm[d][i];
+  }
+}
+
 int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *maxMach) {
   gen_ctx *x = p;
   const gen_cfg *c = &x->c;

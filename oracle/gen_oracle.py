@@ -45,6 +45,7 @@ def lib():
         L.gen_nvar.argtypes = [C.c_void_p]
         L.gen_boundary.argtypes = [C.c_void_p, C.c_void_p]
         L.gen_get_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.gen_get_ppm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gen_blondin_cooling.restype = None
         L.gen_blondin_cooling.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
         L.gen_advance_step.restype = C.c_int
@@ -180,6 +181,13 @@ class GenOracle:
         out = np.zeros(self.shape[1:])
         lib().gen_get_geometry(self._handle(), which, out.ctypes.data)
         return out
+
+    def ppm_coefficients(self, d):
+        """(w[tot][4], h+[tot], h-[tot]) of PPM_CoefficientsSet for direction d."""
+        n = self.shape[3 - d]
+        w, hp, hm = np.zeros((n, 4)), np.zeros(n), np.zeros(n)
+        lib().gen_get_ppm(self._handle(), d, w.ctypes.data, hp.ctypes.data, hm.ctypes.data)
+        return w, hp, hm
 
     def advance_step(self, vc, dt):
         assert vc.flags["C_CONTIGUOUS"] and vc.shape == self.shape and vc.dtype == np.float64

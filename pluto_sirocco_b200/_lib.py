@@ -60,6 +60,8 @@ SYMBOLS = {
     "pb200_shape": (C.c_int, [_P, C.POINTER(C.c_int * 3), C.POINTER(C.c_int)]),
     "pb200_set_grid": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pb200_set_geometry": (C.c_int, [_P, _P]),
+    "pb200_set_grid_uniform": (C.c_int, [_P, _P]),
+    "pb200_ppm_coefficients": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
     "pb200_set_body_force_vector": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_set_body_force_potential": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_long, C.c_long, C.c_long]),
     "pb200_cooling_set_tables": (C.c_int, [_P, C.POINTER(C.c_void_p * 7)]),

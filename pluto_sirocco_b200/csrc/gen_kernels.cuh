@@ -53,6 +53,9 @@ struct GenDev {
   int iso;
   double cs2;                          // g_isoSoundSpeed^2
   int flatten_oned;                    // SHOCK_FLATTENING ONED (States/flatten.c); `flatten` is MULTID
+  // RECONSTRUCTION PARABOLIC (PPM_ORDER 4): interface weights [tot][4] and h+ / h- per direction (States/ppm_coeffs.c)
+  int ppm;
+  const double *pw[3], *php[3], *phm[3];
   // 1-D grid arrays per direction (np_tot entries): grid->x, xr, dx, inv_dx and PLM_Coeffs
   const double *x[3], *xr[3], *dx[3], *inv_dx[3];
   const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
@@ -231,6 +234,176 @@ static __global__ void gen_p2c(GenDev g, GenArgs a, GenBox b) {
 // ---- States: PLM on general grids, primitive or characteristic limiting -------------------
 // vp / vm of ONE zone (States(), plm_states.c): shared by gen_states (one kernel per reference stage) and by
 // the fused sweep kernel gen_sweep / gen_vgrad.  n = the zone's index along dir, st = its stride, o = its offset.
+// Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10), zones max(beg,3)..min(end,tot-4): the
+// states are pulled towards the zone value by f = max(f_t[i], f_t[i + s]), s pointing down the pressure gradient
+template <int NV>
+PB_D void gen_flatten_oned(const GenDev &g, const double *__restrict__ V, int dir, int n, long st, long o,
+                           const double (&v)[NV], double (&vpo)[NV], double (&vmo)[NV]) {
+  const Dev &d = g.d;
+  if (!(g.flatten_oned && n >= 3 && n <= d.tot[dir] - 4)) return;
+  const double *Pv = V + (g.iso ? 0 : iPRS) * d.sv, *Vn = V + (1 + dir) * d.sv;
+  auto f_t = [&](long q) {
+    const double dpq = Pv[q + st] - Pv[q - st];
+    const double min_p = fmin(Pv[q + st], Pv[q - st]);
+    const double d2p = Pv[q + 2 * st] - Pv[q - 2 * st];
+    double scrh = fabs(dpq) / min_p;
+    if (scrh < 0.33 || (Vn[q + st] > Vn[q - st])) return 0.0;
+    scrh = 10.0 * (fabs(dpq / d2p) - 0.75);
+    scrh = fmin(1.0, scrh);
+    return fmax(0.0, scrh);
+  };
+  const long sj = (Pv[o + st] < Pv[o - st]) ? st : -st;
+  const double fj = fmax(f_t(o), f_t(o + sj));
+  const double om = 1.0 - fj;
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    const double vf = v[nv] * fj;
+    vmo[nv] = vf + vmo[nv] * om;
+    vpo[nv] = vf + vpo[nv] * om;
+  }
+}
+
+// PPM states of zone n (PPM_ORDER 4, PARABOLIC_LIM 1): States/ppm_states.c:66-232 (CHAR_LIMITING NO) and :280-590
+// (CHAR_LIMITING YES).  v+ of a zone needs the interface values at n+1/2 (zones n-1..n+2) and n-1/2 (n-2..n+1).
+PB_D double gen_minmod(double a, double b) { return a * b > 0.0 ? (fabs(a) < fabs(b) ? a : b) : 0.0; }
+
+template <int NV>
+PB_D void gen_prim_to_char(const GenDev &g, int dir, const double (&v)[NV], double cs, const double (&dv)[NV], double (&w)[NV]) {
+  // PrimToChar (HD/eigenv.c:575-616) with the left eigenvectors of the zone (eigenv.c:92-200)
+  constexpr int P = pidx<NV>();
+  const double n_ = dir == 0 ? dv[1] : (dir == 1 ? dv[2] : dv[3]);
+  const double t_ = dir == 0 ? dv[2] : (dir == 1 ? dv[3] : dv[1]);
+  const double b_ = dir == 0 ? dv[3] : (dir == 1 ? dv[1] : dv[2]);
+  if (!g.iso) {
+    const double L0p = 1.0 / (v[iRHO] * cs), L2p = -1.0 / (cs * cs);
+    w[0] = -1.0 * n_ + L0p * dv[P];
+    w[1] = 1.0 * n_ + L0p * dv[P];
+    w[2] = dv[iRHO] + L2p * dv[P];
+    w[3] = t_;
+    if (NV > 4) w[pidx<NV>()] = b_;
+  } else {
+    const double Lr = 1.0 / (v[iRHO] / cs);
+    w[0] = Lr * dv[iRHO] + -1.0 * n_;
+    w[1] = Lr * dv[iRHO] + 1.0 * n_;
+    w[2] = t_;
+    w[3] = b_;
+  }
+  const int nf = gen_nflx(g);
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) if (nv >= nf) w[nv] = dv[nv];
+}
+
+template <int NV>
+PB_D void gen_zone_states_ppm(const GenDev &g, const double *__restrict__ V, const unsigned short *__restrict__ flag, int dir,
+                              int n, long st, long o, double (&v)[NV], double (&vpo)[NV], double (&vmo)[NV]) {
+  const Dev &d = g.d;
+  constexpr int P = pidx<NV>();
+  const double *wq = g.pw[dir] + 4 * (long)n;
+  const double a0 = __ldg(wq - 4), a1 = __ldg(wq - 3), a2 = __ldg(wq - 2), a3 = __ldg(wq - 1);   // interface n-1/2
+  const double b0 = __ldg(wq), b1 = __ldg(wq + 1), b2 = __ldg(wq + 2), b3 = __ldg(wq + 3);       // interface n+1/2
+  const double hp = __ldg(g.php[dir] + n), hm = __ldg(g.phm[dir] + n);
+  const double cm = (hm + 1.0) / (hp - 1.0), cp = (hp + 1.0) / (hm - 1.0);
+  const unsigned short fl = g.flatten ? flag[o] : 0;
+  double dfp[NV], dfm[NV], ip[NV], im[NV], vl1[NV];   // v(n+1) - v(n), v(n) - v(n-1), 4th-order interface values, v(n-1)
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    const double *q = V + nv * d.sv + o;
+    const double m2 = q[-2 * st], m1 = q[-st], c0 = q[0], p1 = q[st], p2 = q[2 * st];
+    v[nv] = c0;
+    vl1[nv] = m1;
+    dfp[nv] = p1 - c0;
+    dfm[nv] = c0 - m1;
+    ip[nv] = b0 * m1 + b1 * c0 + b2 * p1 + b3 * p2;
+    im[nv] = a0 * m2 + a1 * m1 + a2 * c0 + a3 * p1;
+  }
+  if (fl & GF_FLAT) {
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) vpo[nv] = vmo[nv] = v[nv];
+  } else if (fl & GF_MINMOD) {                  // PLM weights of plm_coeffs.c on the flagged zones
+    const bool uniform = g.geometry == GEO_CARTESIAN;
+    const double wp = uniform ? 1.0 : __ldg(g.wp[dir] + n), wm = uniform ? 1.0 : __ldg(g.wm[dir] + n);
+    const double dp = uniform ? 0.5 : __ldg(g.dp[dir] + n), dm = uniform ? 0.5 : __ldg(g.dm[dir] + n);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      const double dv = gen_minmod(dfp[nv] * wp, dfm[nv] * wm);
+      vpo[nv] = v[nv] + dv * dp;
+      vmo[nv] = v[nv] - dv * dm;
+    }
+  } else if (!g.char_lim) {
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      // interface values clipped between the two cell averages (ppm_states.c:118-126), then the parabola limiter
+      const double m1 = vl1[nv];
+      const double vr = v[nv] + gen_minmod(ip[nv] - v[nv], dfp[nv]);
+      const double vl = m1 + gen_minmod(im[nv] - m1, dfm[nv]);
+      double dvp = vr - v[nv], dvm = vl - v[nv];
+      if (dvp * dvm >= 0.0) dvp = dvm = 0.0;
+      else if (fabs(dvp) >= cm * fabs(dvm)) dvp = -cm * dvm;
+      else if (fabs(dvm) >= cp * fabs(dvp)) dvm = -cp * dvp;
+      vpo[nv] = v[nv] + dvp;
+      vmo[nv] = v[nv] + dvm;
+    }
+  } else {
+    const double a2s = g.iso ? g.cs2 : d.gas.gamma * v[P] / v[iRHO];
+    const double cs = sqrt(a2s), rhocs = v[iRHO] * cs, rho_cs = v[iRHO] / cs;
+    double dvp[NV], dvm[NV], dwp[NV], dwm[NV], dwp1[NV], dwm1[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) { dvp[nv] = ip[nv] - v[nv]; dvm[nv] = im[nv] - v[nv]; }
+    gen_prim_to_char<NV>(g, dir, v, cs, dvp, dwp);
+    gen_prim_to_char<NV>(g, dir, v, cs, dvm, dwm);
+    gen_prim_to_char<NV>(g, dir, v, cs, dfm, dwm1);
+    gen_prim_to_char<NV>(g, dir, v, cs, dfp, dwp1);
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      dwp[q] = gen_minmod(dwp[q], dwp1[q]);
+      dwm[q] = gen_minmod(dwm[q], -dwm1[q]);
+    }
+    // dv = R dw with the right eigenvectors of eigenv.c:140-178
+    double pn, pt_, pb_, mn, mt_, mb_;
+    if (!g.iso) {
+      dvp[iRHO] = (dwp[0] * (0.5 * rho_cs) + dwp[1] * (0.5 * rho_cs)) + dwp[2];
+      dvm[iRHO] = (dwm[0] * (0.5 * rho_cs) + dwm[1] * (0.5 * rho_cs)) + dwm[2];
+      dvp[P] = dwp[0] * (0.5 * rhocs) + dwp[1] * (0.5 * rhocs);
+      dvm[P] = dwm[0] * (0.5 * rhocs) + dwm[1] * (0.5 * rhocs);
+      pn = dwp[0] * -0.5 + dwp[1] * 0.5; pt_ = dwp[3]; pb_ = dwp[P];
+      mn = dwm[0] * -0.5 + dwm[1] * 0.5; mt_ = dwm[3]; mb_ = dwm[P];
+    } else {
+      dvp[iRHO] = dwp[0] * (0.5 * rho_cs) + dwp[1] * (0.5 * rho_cs);
+      dvm[iRHO] = dwm[0] * (0.5 * rho_cs) + dwm[1] * (0.5 * rho_cs);
+      pn = dwp[0] * -0.5 + dwp[1] * 0.5; pt_ = dwp[2]; pb_ = dwp[3];
+      mn = dwm[0] * -0.5 + dwm[1] * 0.5; mt_ = dwm[2]; mb_ = dwm[3];
+    }
+    dvp[1] = dir == 0 ? pn : (dir == 1 ? pb_ : pt_);
+    dvp[2] = dir == 0 ? pt_ : (dir == 1 ? pn : pb_);
+    dvp[3] = dir == 0 ? pb_ : (dir == 1 ? pt_ : pn);
+    dvm[1] = dir == 0 ? mn : (dir == 1 ? mb_ : mt_);
+    dvm[2] = dir == 0 ? mt_ : (dir == 1 ? mn : mb_);
+    dvm[3] = dir == 0 ? mb_ : (dir == 1 ? mt_ : mn);
+    const int nf = gen_nflx(g);
+#pragma unroll
+    for (int nv = 4; nv < NV; nv++) if (nv >= nf) { dvp[nv] = dwp[nv]; dvm[nv] = dwm[nv]; }
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      if (dvp[nv] * dvm[nv] >= 0.0) dvp[nv] = dvm[nv] = 0.0;
+      else if (fabs(dvp[nv]) >= cm * fabs(dvm[nv])) dvp[nv] = -cm * dvm[nv];
+      else if (fabs(dvm[nv]) >= cp * fabs(dvp[nv])) dvm[nv] = -cp * dvp[nv];
+      vpo[nv] = v[nv] + dvp[nv];
+      vmo[nv] = v[nv] + dvm[nv];
+    }
+    if (vpo[iRHO] < 0.0 || vmo[iRHO] < 0.0) {       // ppm_states.c:560-575: back to a minmod slope
+      const double h = 0.5 * gen_minmod(dfp[iRHO], dfm[iRHO]);
+      vpo[iRHO] = v[iRHO] + h;
+      vmo[iRHO] = v[iRHO] + -h;
+    }
+    if (!g.iso && (vpo[P] < 0.0 || vmo[P] < 0.0)) {
+      const double h = 0.5 * gen_minmod(dfp[P], dfm[P]);
+      vpo[P] = v[P] + h;
+      vmo[P] = v[P] + -h;
+    }
+  }
+  gen_flatten_oned<NV>(g, V, dir, n, st, o, v, vpo, vmo);
+}
+
 template <int NV>
 PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const unsigned short *__restrict__ flag, int dir,
                           int n, long st, long o, double (&v)[NV], double (&vpo)[NV], double (&vmo)[NV]) {
@@ -334,30 +507,7 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
     vpo[nv] = v[nv] + dvl[nv] * dp;
     vmo[nv] = v[nv] - dvl[nv] * dm;
   }
-  if (g.flatten_oned && n >= 3 && n <= d.tot[dir] - 4) {
-    // Flatten(), States/flatten.c:58-130 (HD: EPS2 0.33, OME1 0.75, OME2 10), zones max(beg,3)..min(end,tot-4): the
-    // states are pulled towards the zone value by f = max(f_t[i], f_t[i + s]), s pointing down the pressure gradient
-    const double *Pv = V + (g.iso ? 0 : iPRS) * d.sv, *Vn = V + (1 + dir) * d.sv;
-    auto f_t = [&](long q) {
-      const double dpq = Pv[q + st] - Pv[q - st];
-      const double min_p = fmin(Pv[q + st], Pv[q - st]);
-      const double d2p = Pv[q + 2 * st] - Pv[q - 2 * st];
-      double scrh = fabs(dpq) / min_p;
-      if (scrh < 0.33 || (Vn[q + st] > Vn[q - st])) return 0.0;
-      scrh = 10.0 * (fabs(dpq / d2p) - 0.75);
-      scrh = fmin(1.0, scrh);
-      return fmax(0.0, scrh);
-    };
-    const long sj = (Pv[o + st] < Pv[o - st]) ? st : -st;
-    const double fj = fmax(f_t(o), f_t(o + sj));
-    const double om = 1.0 - fj;
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) {
-      const double vf = v[nv] * fj;
-      vmo[nv] = vf + vmo[nv] * om;
-      vpo[nv] = vf + vpo[nv] * om;
-    }
-  }
+  gen_flatten_oned<NV>(g, V, dir, n, st, o, v, vpo, vmo);
 }
 
 template <int NV>
@@ -370,7 +520,8 @@ static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   const long o = (long)k * d.sk + (long)j * d.sj + i;
   const int n = dir == 0 ? i : (dir == 1 ? j : k);
   double v[NV], vp[NV], vm[NV];
-  gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
+  if (g.ppm) gen_zone_states_ppm<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
+  else gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
     a.VP[nv * d.sv + o] = vp[nv];

@@ -74,8 +74,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (iso && cfg->entropy_switch) return fail(PB200_EINVAL, "ENTROPY_SWITCH needs an energy equation (EOS IDEAL)");
   const bool gen = cfg->geometry != PB200_CARTESIAN || cfg->char_limiting || cfg->shock_flattening ||
                    cfg->entropy_switch || iso || cfg->solver >= PB200_ROE;
-  if (gen && cfg->reconstruction != PB200_LINEAR)
-    return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR");
+  if (gen && cfg->reconstruction == PB200_FLAT)
+    return fail(PB200_ENOTSUP, "the general-grid path is built for RECONSTRUCTION LINEAR and PARABOLIC");
   if (cfg->ntracer < 0 || cfg->ntracer > 2) return fail(PB200_ENOTSUP, "ntracer must be 0..2");
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
@@ -107,6 +107,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   c->cur_stage = 0;
   c->d_ibmask = nullptr;
   c->geo_set = false;
+  for (int d = 0; d < 3; d++) c->grid_uniform[d] = -1;
   c->graph_exec = nullptr;
   c->graph_sig = 0;
   c->graph_launches = 0;
@@ -257,6 +258,26 @@ extern "C" int pb200_shape(const pb200_ctx *c, int tot[3], int *nvar) {
   return PB200_OK;
 }
 
+// grid->uniform[d] of the reference is an input-file property (one uniform patch); when the caller has not passed it,
+// a direction counts as uniform if its dx is constant to round-off
+bool pb200_grid_is_uniform(const pb200_ctx *c, int dir) {
+  if (c->grid_uniform[dir] >= 0) return c->grid_uniform[dir] != 0;
+  const std::vector<double> &dx = c->dx[dir];
+  for (size_t i = 1; i < dx.size(); i++)
+    if (fabs(dx[i] - dx[0]) > 1e-12 * fabs(dx[0])) return false;
+  return true;
+}
+
+// RECONSTRUCTION PARABOLIC: the marching kernels carry the uniform-grid weights of PPM_CartCoeff() (ppm_coeffs.c:468-509);
+// a non-uniform direction needs the grid-dependent weights (ppm_coeffs.c:124-136), which the general path holds
+static void ppm_route(pb200_ctx *c) {
+  if (c->cfg.reconstruction != PB200_PARABOLIC || c->gen) return;
+  for (int d = 0; d < c->dev.ndim; d++)
+    if (!pb200_grid_is_uniform(c, d)) c->gen = true;
+  if (c->gen)                                    // the general path reads real x1 ghost zones (no virtual ghosts)
+    for (int s = 0; s < 6; s++) c->dev.bc_fuse[s] = 0;
+}
+
 extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const double *xr, const double *dx) {
   if (!c || dir < 0 || dir > 2 || !xl || !xr) return fail(PB200_EINVAL, "bad argument");
   int n = c->dev.tot[dir];
@@ -268,7 +289,16 @@ extern "C" int pb200_set_grid(pb200_ctx *c, int dir, const double *xl, const dou
   }
   CK(cudaSetDevice(c->cfg.device));
   c->gen_ready = false;
+  ppm_route(c);
   return upload_grid(c, dir);
+}
+
+extern "C" int pb200_set_grid_uniform(pb200_ctx *c, const int uniform[3]) {
+  if (!c || !uniform) return fail(PB200_EINVAL, "null argument");
+  for (int d = 0; d < 3; d++) c->grid_uniform[d] = uniform[d] ? 1 : 0;
+  c->gen_ready = false;
+  ppm_route(c);
+  return PB200_OK;
 }
 
 extern "C" int pb200_set_geometry(pb200_ctx *c, const pb200_geometry *g) {
@@ -495,16 +525,6 @@ extern "C" int pb200_step_begin(pb200_ctx *c, double dt) {
   CK(cudaSetDevice(c->cfg.device));
   c->launches = 0;
   c->nprof = 0;
-  if (c->cfg.reconstruction == PB200_PARABOLIC) {
-    // PPM_CoefficientsSet() derives grid-dependent weights on non-uniform grids (ppm_coeffs.c:124-136);
-    // the kernels carry the uniform-grid weights of PPM_CartCoeff() (ppm_coeffs.c:468-509) only
-    for (int d = 0; d < c->dev.ndim; d++) {
-      const std::vector<double> &dx = c->dx[d];
-      for (size_t i = 1; i < dx.size(); i++)
-        if (fabs(dx[i] - dx[0]) > 1e-12 * fabs(dx[0]))
-          return fail(PB200_ENOTSUP, "RECONSTRUCTION PARABOLIC on a non-uniform grid is not built");
-    }
-  }
   if (c->gen) {
     int rc = pb200_gen_setup(c);
     if (rc) return fail(rc, "general-grid set-up failed (out of device memory?)");

@@ -48,6 +48,9 @@ void pb200_gen_release(pb200_ctx *c) {
   c->gdev = nullptr;
 }
 
+static void ppm_coefficients(int geo, int d, int nt, const double *xl, const double *xr, const double *dx, const double *xc,
+                             bool uniform, std::vector<double> &w, std::vector<double> &hp, std::vector<double> &hm);
+
 int pb200_gen_setup(pb200_ctx *c) {
   if (c->gen_ready) return PB200_OK;
   pb200_gen_release(c);
@@ -203,6 +206,15 @@ int pb200_gen_setup(pb200_ctx *c) {
     ok &= (G.dm[d] = upload(c, dm[d])) != nullptr;
     ok &= (G.A[d] = upload(c, A[d])) != nullptr;
     ok &= (G.dx_dl[d] = upload(c, dxdl[d])) != nullptr;
+  }
+  G.ppm = c->cfg.reconstruction == PB200_PARABOLIC;
+  for (int d = 0; d < 3 && G.ppm; d++) {
+    std::vector<double> w, hp, hm;
+    ppm_coefficients(geo, d, D.tot[d], c->xl[d].data(), c->xr[d].data(), c->dx[d].data(), x[d].data(),
+                     pb200_grid_is_uniform(c, d), w, hp, hm);
+    ok &= (G.pw[d] = upload(c, w)) != nullptr;
+    ok &= (G.php[d] = upload(c, hp)) != nullptr;
+    ok &= (G.phm[d] = upload(c, hm)) != nullptr;
   }
   {
     std::vector<double> cot(n2, 0.0), sn2(n2, 1.0);
@@ -400,6 +412,187 @@ extern "C" int pb200_ldw_set_fluxes(pb200_ctx *c, const double *fr, const double
   return PB200_OK;
 }
 
+// ---- RECONSTRUCTION PARABOLIC on general grids: PPM_CoefficientsSet(), States/ppm_coeffs.c:60-290 --------------------
+// The interface weights w (v_{i+1/2} = sum_j w[j] v_{i-1+j}) and the extremum coefficients h+ / h- (PPM_Q6_Coeffs,
+// :520-570) are grid constants, evaluated once on the host in the reference's own operation order - same libm,
+// no FMA contraction in host code - so they are the doubles the reference holds.
+
+// B w = b by Crout LU with implicit row scaling and partial pivoting, the algorithm (and operation order) of
+// Math_Tools/math_lu_decomp.c LUDecompose() + LUBackSubst(); 4 unknowns
+static void ppm_solve4(double (&m)[4][4], double (&b)[4]) {
+  const int n = 4;
+  int piv[4];
+  double scale[4];
+  for (int r = 0; r < n; r++) {
+    double big = 0.0;
+    for (int q = 0; q < n; q++) { const double t = fabs(m[r][q]); if (t > big) big = t; }
+    scale[r] = 1.0 / big;
+  }
+  for (int col = 0; col < n; col++) {
+    for (int r = 0; r < col; r++) {
+      double acc = m[r][col];
+      for (int q = 0; q < r; q++) acc -= m[r][q] * m[q][col];
+      m[r][col] = acc;
+    }
+    double best = 0.0;
+    int rbest = col;
+    for (int r = col; r < n; r++) {
+      double acc = m[r][col];
+      for (int q = 0; q < col; q++) acc -= m[r][q] * m[q][col];
+      m[r][col] = acc;
+      const double merit = scale[r] * fabs(acc);
+      if (merit >= best) { best = merit; rbest = r; }
+    }
+    if (rbest != col) {
+      for (int q = 0; q < n; q++) std::swap(m[rbest][q], m[col][q]);
+      scale[rbest] = scale[col];
+    }
+    piv[col] = rbest;
+    if (m[col][col] == 0.0) m[col][col] = 1.0e-20;
+    if (col != n - 1) {
+      const double inv = 1.0 / m[col][col];
+      for (int r = col + 1; r < n; r++) m[r][col] *= inv;
+    }
+  }
+  int first = 0;                                   // forward substitution skipping leading zeros of b
+  for (int r = 0; r < n; r++) {
+    const int pr = piv[r];
+    double acc = b[pr];
+    b[pr] = b[r];
+    if (first) for (int q = first - 1; q <= r - 1; q++) acc -= m[r][q] * b[q];
+    else if (acc) first = r + 1;
+    b[r] = acc;
+  }
+  for (int r = n - 1; r >= 0; r--) {
+    double acc = b[r];
+    for (int q = r + 1; q < n; q++) acc -= m[r][q] * b[q];
+    b[r] = acc / m[r][r];
+  }
+}
+
+// int_a^b (x - x0)^k sin(x) dx by one panel of the 5-point Gauss-Legendre rule: GaussQuadrature(&BetaTheta, ., a, b, 1, 5),
+// Math_Tools/math_quadrature.c:30-78,356-409
+static double ppm_theta_moment(double a, double b, double x0, int k) {
+  const double third = 1.0 / 3.0, c107 = 10.0 / 7.0;
+  const double node[5] = {0.0, sqrt(5.0 - 2.0 * sqrt(c107)) * third, -sqrt(5.0 - 2.0 * sqrt(c107)) * third,
+                          sqrt(5.0 + 2.0 * sqrt(c107)) * third, -sqrt(5.0 + 2.0 * sqrt(c107)) * third};
+  const double wgt[5] = {128.0 / 225.0, (322.0 + 13.0 * sqrt(70.0)) / 900.0, (322.0 + 13.0 * sqrt(70.0)) / 900.0,
+                         (322.0 - 13.0 * sqrt(70.0)) / 900.0, (322.0 - 13.0 * sqrt(70.0)) / 900.0};
+  const double h = (b - a) / (double)1;
+  const double lo = a + 0 * h, hi = lo + h;
+  double panel = 0.0;
+  for (int q = 0; q < 5; q++) {
+    const double x = 0.5 * (hi - lo) * node[q] + (hi + lo) * 0.5;
+    panel += wgt[q] * (pow(x - x0, k) * sin(x));
+  }
+  panel *= 0.5 * (hi - lo);
+  double total = 0.0;
+  total += panel;
+  return total;
+}
+
+static inline double poly2(double a0, double a1, double a2, double x) { return a0 + x * (a1 + x * a2); }
+static inline double poly4(double a0, double a1, double a2, double a3, double a4, double x) {
+  return a0 + x * (a1 + x * (a2 + x * (a3 + x * a4)));
+}
+static inline double poly6(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double x) {
+  return a0 + x * (a1 + x * (a2 + x * (a3 + x * (a4 + x * (a5 + x * a6)))));
+}
+
+// weights [tot][4], h+ [tot], h- [tot] of direction d; `uniform`: grid->uniform[d] (one uniform patch, set_grid.c:67-72)
+static void ppm_coefficients(int geo, int d, int nt, const double *xl, const double *xr, const double *dx, const double *xc,
+                             bool uniform, std::vector<double> &w, std::vector<double> &hp, std::vector<double> &hm) {
+  const bool radial = d == 0 && (geo == PB200_CYLINDRICAL || geo == PB200_POLAR);
+  const bool sph_r = d == 0 && geo == PB200_SPHERICAL, sph_t = d == 1 && geo == PB200_SPHERICAL;
+  w.assign((size_t)nt * 4, 0.0); hp.assign(nt, 3.0); hm.assign(nt, 3.0);
+  for (int i = 0; i < nt; i++) {                   // PPM_Q6_Coeffs, ppm_coeffs.c:520-570
+    if (radial) {
+      hp[i] = 3.0 + 0.5 * dx[i] / xc[i];
+      hm[i] = 3.0 - 0.5 * dx[i] / xc[i];
+    } else if (sph_r) {
+      const double r = xc[i], dr = dx[i], den = 20.0 * r * r + dr * dr;
+      hp[i] = 3.0 + 2.0 * dr * (10.0 * r + dr) / den;
+      hm[i] = 3.0 - 2.0 * dr * (10.0 * r - dr) / den;
+    } else if (sph_t && i > 0) {
+      const double cp = cos(xr[i]), sp = sin(xr[i]), cm = cos(xr[i - 1]), sm = sin(xr[i - 1]);
+      const double dmu = cm - cp, dmu_t = sm - sp;
+      hp[i] = dx[i] * (dmu_t + dx[i] * cp) / (dx[i] * (sp + sm) - 2.0 * dmu);
+      hm[i] = -dx[i] * (dmu_t + dx[i] * cm) / (dx[i] * (sp + sm) - 2.0 * dmu);
+    }
+  }
+  const int first = 1, last = nt - 1 - 2;          // stencil i-1 .. i+2
+  if (!uniform || sph_t) {                         // PPM_FindWeights, ppm_coeffs.c:300-420 (theta: always, :268-269)
+    for (int i = first; i <= last; i++) {
+      double beta[4][4], rhs[4];
+      const double x0 = xc[i];
+      for (int j = i - 1; j <= i + 2; j++) {
+        const double rp = xr[j], rm = xl[j];
+        const int col = j - (i - 1);
+        if (sph_t) {
+          const double vol = cos(rm) - cos(rp);
+          for (int k = 0; k < 4; k++) beta[k][col] = ppm_theta_moment(rm, rp, x0, k);
+          for (int k = 0; k < 4; k++) beta[k][col] /= vol;
+        } else if (sph_r) {
+          const double vol = (rp * rp * rp - rm * rm * rm) / 3.0;
+          for (int k = 0; k < 4; k++) {
+            beta[k][col] = pow(rp - x0, k + 1) * ((k * k + 3.0 * k + 2.0) * rp * rp + 2.0 * x0 * (k + 1.0) * rp + 2.0 * x0 * x0)
+                         - pow(rm - x0, k + 1) * ((k * k + 3.0 * k + 2.0) * rm * rm + 2.0 * x0 * (k + 1.0) * rm + 2.0 * x0 * x0);
+            beta[k][col] /= (k + 3.0) * (k + 2.0) * (k + 1.0) * vol;
+          }
+        } else if (!radial) {
+          const double vol = rp - rm;
+          for (int k = 0; k < 4; k++) beta[k][col] = (pow(rp - x0, k + 1) - pow(rm - x0, k + 1)) / (k + 1.0) / vol;
+        } else {
+          const double vol = (rp * rp - rm * rm) / 2.0;
+          for (int k = 0; k < 4; k++) {
+            beta[k][col] = pow(rp - x0, k + 1) * ((k + 1.0) * rp + x0) - pow(rm - x0, k + 1) * ((k + 1.0) * rm + x0);
+            beta[k][col] /= (k + 2.0) * (k + 1.0) * vol;
+          }
+        }
+      }
+      rhs[0] = 1.0;
+      for (int k = 1; k < 4; k++) rhs[k] = rhs[k - 1] * (xr[i] - x0);
+      ppm_solve4(beta, rhs);
+      for (int j = 0; j < 4; j++) w[(size_t)i * 4 + j] = rhs[j];
+    }
+    return;
+  }
+  for (int i = first; i <= last; i++) {            // PPM_CartCoeff, ppm_coeffs.c:468-509
+    double *q = &w[(size_t)i * 4];
+    q[0] = -1.0 / 12.0; q[1] = 7.0 / 12.0; q[2] = 7.0 / 12.0; q[3] = -1.0 / 12.0;
+    if (radial) {                                  // ppm_coeffs.c:150-165
+      const double i1 = xr[i] / dx[i], i2 = i1 * i1;
+      const double den = 24.0 * poly2(4.0, -15.0, 5.0, i2);
+      q[0] = poly4(-12.0, -1.0, 30.0, -1.0, -10.0, i1) / den;
+      q[1] = poly4(60.0, -27.0, -210.0, 13.0, 70.0, i1) / den;
+      q[2] = poly4(60.0, 27.0, -210.0, -13.0, 70.0, i1) / den;
+      q[3] = poly4(-12.0, 1.0, 30.0, 1.0, -10.0, i1) / den;
+    }
+    if (sph_r) {                                   // ppm_coeffs.c:216-229
+      const double i1 = fabs(xr[i] / dx[i]), i2 = i1 * i1;
+      const double den = 36.0 * poly4(16.0, -60.0, 150.0, -85.0, 15.0, i2);
+      q[0] = -poly2(7, -9, 3, i1) / den * poly6(12, 16, -30, -48.0, 23, 48, 15, i1);
+      q[1] = poly2(1, -3, 3, i1) / den * poly6(372, 1008.0, 510, -720, -487, 144, 105, i1);
+      q[2] = poly2(1, 3, 3.0, i1) / den * poly6(372, -1008, 510, 720, -487, -144, 105, i1);
+      q[3] = -poly2(7, 9, 3, i1) / den * poly6(12, -16, -30, 48, 23, -48, 15, i1);
+    }
+  }
+}
+
+// host-only entry (no device needed): the coefficients of one direction, for callers and tests that want to look at them
+extern "C" int pb200_ppm_coefficients(int geometry, int dir, int ntot, const double *xl, const double *xr, const double *dxin,
+                                      int uniform, double *w, double *hp, double *hm) {
+  if (geometry < PB200_CARTESIAN || geometry > PB200_SPHERICAL || dir < 0 || dir > 2 || ntot < 4 || !xl || !xr || !w || !hp || !hm)
+    return pb200_fail(PB200_EINVAL, "pb200_ppm_coefficients: bad argument");
+  std::vector<double> dx(ntot), xc(ntot), vw, vp, vm;
+  for (int i = 0; i < ntot; i++) { dx[i] = dxin ? dxin[i] : xr[i] - xl[i]; xc[i] = 0.5 * (xl[i] + xr[i]); }   // set_grid.c:135-137
+  ppm_coefficients(geometry, dir, ntot, xl, xr, dx.data(), xc.data(), uniform != 0, vw, vp, vm);
+  std::copy(vw.begin(), vw.end(), w);
+  std::copy(vp.begin(), vp.end(), hp);
+  std::copy(vm.begin(), vm.end(), hm);
+  return PB200_OK;
+}
+
 // SplitSource() for COOLING BLONDIN (Src/split_source.c:53): BlondinCooling(d->Vc, d, dt, ...)
 template <int NV>
 static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
@@ -418,7 +611,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   // PB200_GEN_FUSED=0: the one-kernel-per-reference-stage form (gen_states -> gen_riemann -> gen_rhs through
   // the VP / VM / F arrays); default: one fused kernel per direction (gen_sweep)
   static const bool fused_env = !(getenv("PB200_GEN_FUSED") && atoi(getenv("PB200_GEN_FUSED")) == 0);
-  const bool fused = fused_env;
+  const bool fused = fused_env && !G.ppm;      // PARABOLIC: gen_states carries the PPM states, gen_sweep does not
   const int T = 128;
   auto blocks = [&](const GenBox &b) {
     long n = (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);

@@ -29,6 +29,7 @@ struct pb200_ctx {
   // the caller's own Grid arrays (pb200_set_geometry): used by the general path instead of its own evaluation
   std::vector<double> geo_dV, geo_A[3], geo_dxdl[3], geo_rt, geo_s, geo_sp;
   bool geo_set;
+  int grid_uniform[3];     // grid->uniform[d] (set_grid.c:67-72): 1 / 0 from pb200_set_grid_uniform, -1: inferred from dx
   cudaStream_t stream;
   cudaStream_t h2d, d2h;        // copy streams of the slab-wise host pipeline (pb200_advance_step_host)
   cudaEvent_t ev_up[64], ev_done[64];
@@ -82,6 +83,7 @@ int  pb200_gen_setup(pb200_ctx *c);
 void pb200_gen_release(pb200_ctx *c);
 int  pb200_gen_stage(pb200_ctx *c, int stage);
 int  pb200_gen_patch_u(pb200_ctx *c, long n, const long *zone, const double *u);
+bool pb200_grid_is_uniform(const pb200_ctx *c, int dir);
 int  pb200_gen_internal_boundary(pb200_ctx *c, double *V);   // UserDefBoundary(side == 0)
 int  pb200_gen_userdef_side(pb200_ctx *c, double *V, int side);
 int  pb200_gen_entropy(pb200_ctx *c, double *V);               // ComputeEntropy at the end of Boundary()

@@ -258,6 +258,8 @@ extern "C" int pb200_multi_set_grid(pb200_multi *m, int dir, const double *xl, c
     const int o = dir == m->sdir ? m->offset[r] : 0;
     int rc = pb200_set_grid(m->ctx[r], dir, xl + o, xr + o, dx ? dx + o : nullptr);
     if (rc) return rc;
+    if (m->ctx[r]->gen && m->n > 1)
+      return pb200_fail(PB200_ENOTSUP, "RECONSTRUCTION PARABOLIC on a non-uniform grid runs on the general path: one GPU");
   }
   return PB200_OK;
 }

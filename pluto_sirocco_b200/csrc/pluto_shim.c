@@ -419,6 +419,9 @@ static void shim_create(Data *d, Grid *grid, int ngpus, int ldw_device_bc) {
                  : pb200_set_grid(s_ctx, dir, grid->xl[dir], grid->xr[dir], grid->dx[dir]);
     if (rc != PB200_OK) { print ("! AdvanceStep(): pb200_set_grid: %s\n", pb200_last_error()); QUIT_PLUTO(1); }
   }
+  if (s_multi == NULL && pb200_set_grid_uniform(s_ctx, grid->uniform) != PB200_OK) {
+    print ("! AdvanceStep(): pb200_set_grid_uniform: %s\n", pb200_last_error()); QUIT_PLUTO(1);
+  }
 #if GEOMETRY != CARTESIAN
   if (s_multi == NULL) {     /* the reference's own geometry arrays (Src/set_geometry.c:49-61), not a re-evaluation */
     pb200_geometry geo;

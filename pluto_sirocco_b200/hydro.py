@@ -284,7 +284,7 @@ class Hydro:
                  reconstruction="LINEAR", time_stepping="RK2", solver="hllc", limiter="DEFAULT",
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
                  small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0,
-                 geometry="CARTESIAN", grid_arrays=None, char_limiting=False, shock_flattening=False,
+                 geometry="CARTESIAN", grid_arrays=None, grid_uniform=None, char_limiting=False, shock_flattening=False,
                  entropy_switch=False, eos="IDEAL", iso_sound_speed=0.0):
         lib = L.load()
         cfg = L.Config()
@@ -344,6 +344,9 @@ class Hydro:
                 self._grid.append((xl, xr, dxa))
                 L.check(lib.pb200_set_grid(h, d, xl.ctypes.data_as(C.c_void_p), xr.ctypes.data_as(C.c_void_p),
                                            dxa.ctypes.data_as(C.c_void_p)))
+        if grid_uniform is not None:   # grid->uniform[d]: one uniform patch in pluto.ini (PPM weights, ppm_coeffs.c:88-136)
+            u = (C.c_int * 3)(*[int(bool(grid_uniform[d])) if d < len(grid_uniform) else 1 for d in range(3)])
+            L.check(lib.pb200_set_grid_uniform(h, u))
         if dx is not None:      # block of a larger uniform grid: impose the global grid->dx
             for d in range(dimensions):
                 n = self.tot[d]

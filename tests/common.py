@@ -15,7 +15,10 @@ CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2
                   # Roe_Solver (both equations of state) and TwoShock_Solver
                   "roe_cart2d", "roe_iso2d", "roe_sph2d_flat", "pot_pol2d_roe", "twoshock_sph2d_flat", "twoshock_sph3d",
                   # SHOCK_FLATTENING ONED (States/flatten.c)
-                  "oned_iso2d_hll", "oned_sph2d_hllc", "oned_sph2d_char_roe"]
+                  "oned_iso2d_hll", "oned_sph2d_hllc", "oned_sph2d_char_roe",
+                  # RECONSTRUCTION PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c
+                  "ppmg_cyl2d_flat_stretched", "ppmg_cyl2d_uniform", "ppmg_iso2d_char", "ppmg_kh3d_stretched", "ppmg_pol2d",
+                  "ppmg_sph2d_char_flat", "ppmg_sph2d_stretched", "ppmg_sph2d_uniform", "ppmg_sph3d"]
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -198,6 +201,7 @@ def hydro_kwargs_from_gen(kw):
     kw["xbeg"] = tuple(float(grid[d][0]) for d in range(3))
     kw["xend"] = tuple(float(grid[d][2]) for d in range(3))
     kw["grid_arrays"] = arrays
+    kw["grid_uniform"] = tuple(len(grid[d]) <= 3 or grid[d][3] == "u" for d in range(3))   # grid->uniform[d]
     return kw
 
 

@@ -129,7 +129,11 @@ def test_cylindrical_polar_potential_per_step_vs_reference_dumps(Hydro, name):
     sph): volumes / areas / centroids of set_geometry.c, the |r| weighting of the angular-momentum flux
     (rhs.c:535-538, :268) with iMPHI = VX2 for POLAR, the centrifugal source on (vp + vm)/2 (rhs_source.c:201-227),
     r dphi in the polar C_dt, the AXISYMMETRIC flip of iVPHI, Phi at the faces in the energy flux (rhs.c:171-179) and
-    the potential gradient / work terms (rhs_source.c:274-279,378-383,442-447)."""
+    the potential gradient / work terms (rhs_source.c:274-279,378-383,442-447).  roe_* / twoshock_*: Roe_Solver
+    (HD/roe.c, both equations of state) and TwoShock_Solver (HD/two_shock.c); oned_*: SHOCK_FLATTENING ONED
+    (States/flatten.c, 4 ghost zones); ppmg_*: RECONSTRUCTION PARABOLIC + RK3 with the weights of PPM_CoefficientsSet
+    (States/ppm_coeffs.c: LU solve on stretched grids, closed forms on uniform radial grids, Gauss moments of
+    sin(theta)), with and without CHAR_LIMITING / MULTID flattening (States/ppm_states.c)."""
     g = load_golden(name)
     kw = gen_kwargs_from_golden(g)
     h = Hydro(**hydro_kwargs_from_gen(kw))

@@ -360,19 +360,32 @@ def test_errors(Hydro):
     h.close()
 
 
-def test_ppm_on_stretched_grid_is_refused(Hydro):
-    """The reference derives grid-dependent PPM weights on non-uniform grids (ppm_coeffs.c:124-136);
-    the kernels only carry the uniform ones, so the library must say so instead of computing."""
+def test_ppm_on_stretched_grid_takes_the_general_path(Hydro):
+    """The reference derives grid-dependent PPM weights on non-uniform grids (ppm_coeffs.c:124-136); the marching
+    kernels only carry the uniform ones, so a stretched direction routes the context to the general path (which
+    holds PPM_FindWeights' weights; parity: the ppmg_* fixtures of tests/test_gpu_gen.py).  Here: a constant state
+    stays constant (the weights sum to one) and the same grid flagged uniform agrees with the marching kernels."""
     from pluto_sirocco_b200 import make_grid
-    from pluto_sirocco_b200._lib import ENOTSUP, PB200Error
     arrays = [make_grid((0.0, 32, 1.0, "r", 1.05), 3), make_grid((0.0, 1, 1.0), 0), make_grid((0.0, 1, 1.0), 0)]
     h = Hydro(dimensions=1, nx=(32, 1, 1), reconstruction="PARABOLIC", time_stepping="RK3", grid_arrays=arrays)
     v = np.ones((5, 1, 1, 32)); v[1:4] = 0
     h.set_interior(v)
-    with pytest.raises(PB200Error) as ei:
-        h.advance_step(1e-3)
-    assert ei.value.code == ENOTSUP
+    h.advance_step(1e-3)
+    assert rel_err(h.get_interior(), v) <= 1e-14
     h.close()
+    rng = np.random.default_rng(5)
+    v = 1.0 + 0.1 * rng.random((5, 1, 1, 32)); v[2:4] = 0
+    uni = [make_grid((0.0, 32, 1.0), 3), make_grid((0.0, 1, 1.0), 0), make_grid((0.0, 1, 1.0), 0)]
+    out = []
+    for flag in ((1, 1, 1), (0, 1, 1)):      # (0, ..): PPM_FindWeights on the uniform grid, general path
+        h = Hydro(dimensions=1, nx=(32, 1, 1), reconstruction="PARABOLIC", time_stepping="RK3", grid_arrays=uni,
+                  grid_uniform=flag, bcs=("periodic",) * 6)
+        h.set_interior(v)
+        for _ in range(3):
+            h.advance_step(2e-3)
+        out.append(h.get_interior())
+        h.close()
+    assert rel_err(out[1], out[0]) <= 1e-12
 
 
 def test_uniform_state_is_a_fixed_point(Hydro):
