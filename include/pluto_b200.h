@@ -47,6 +47,7 @@ extern "C" {
 #define PB200_HLLC  3       /* Solver hllc   -> HLLC_Solver (Src/HD/hllc.c:28)  */
 #define PB200_ROE   4       /* Solver roe    -> Roe_Solver  (Src/HD/roe.c:48; general path) */
 #define PB200_TWO_SHOCK 5   /* Solver two_shock -> TwoShock_Solver (Src/HD/two_shock.c:28; EOS IDEAL, general path) */
+#define PB200_AUSM  6       /* Solver ausm+  -> AUSMp_Solver (Src/HD/ausm.c:20; EOS IDEAL, general path) */
 
 #define PB200_LIM_DEFAULT   0  /* LIMITER DEFAULT: MC rho, VL v, MM p (plm_states.c:202-244) */
 #define PB200_LIM_FLAT      1

@@ -604,7 +604,7 @@ PB_D double riemann_iso(const double (&vL)[NV], const double (&vR)[NV], double c
 // state for Roe, EOS IDEAL for two-shock.  q: (rho, v_n, v_t, v_b[, p], scalars...) in sweep-local order with NF = 4
 // (isothermal) or 5 flux components; f[0..NF-1] without the pressure in f[1].  Small-grid options: written with the
 // reference's own operations.
-enum { SOLVER_ROE = 4, SOLVER_TWO_SHOCK = 5 };
+enum { SOLVER_ROE = 4, SOLVER_TWO_SHOCK = 5, SOLVER_AUSM = 6 };
 template <int NV>
 PB_D double riemann_roe_ts(const double (&vL)[NV], const double (&vR)[NV], bool iso, double cs2, double gamma, int solver,
                            bool force_hll, int ndim, double (&f)[NV], double &prs, double &cmax) {
@@ -629,7 +629,40 @@ PB_D double riemann_roe_ts(const double (&vL)[NV], const double (&vR)[NV], bool 
   } else { a2L = a2R = cs2; pL = a2L * vL[0]; pR = a2R * vR[0]; }
   double fl[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, machv = 0.0;
   bool done = false;
-  if (force_hll) {       // roe.c:101-116, two_shock.c:66-88: HLL in zones flagged by MULTID flattening
+  if (solver == SOLVER_AUSM) {      // AUSMp_Solver, HD/ausm.c:20-110 (EOS IDEAL; no HLL switch in flagged zones)
+    const double alpha = 3.0 / 16.0, beta = 0.125;
+    const double aL = sqrt(gamma * vL[P] / vL[0]), aR = sqrt(gamma * vR[P] / vR[0]);
+    double asL2 = vL[1] * vL[1] + vL[2] * vL[2] + vL[3] * vL[3];
+    asL2 = aL * aL / gmm1 + 0.5 * asL2;
+    asL2 *= 2.0 * gmm1 / (gamma + 1.0);
+    double asR2 = vR[1] * vR[1] + vR[2] * vR[2] + vR[3] * vR[3];
+    asR2 = aR * aR / gmm1 + 0.5 * asR2;
+    asR2 *= 2.0 * gmm1 / (gamma + 1.0);
+    const double asL = sqrt(asL2), asR = sqrt(asR2);
+    const double atL = asL2 / fmax(asL, fabs(vL[1])), atR = asR2 / fmax(asR, fabs(vR[1]));
+    const double a = fmin(atL, atR);
+    const double ML = vL[1] / a, MR = vR[1] / a;
+    double MpL, PpL, MmR, PmR;
+    if (fabs(ML) >= 1.0) { MpL = 0.5 * (ML + fabs(ML)); PpL = ML > 0.0 ? 1.0 : 0.0; }
+    else {
+      MpL = 0.25 * (ML + 1.0) * (ML + 1.0) + beta * (ML * ML - 1.0) * (ML * ML - 1.0);
+      PpL = 0.25 * (ML + 1.0) * (ML + 1.0) * (2.0 - ML) + alpha * ML * (ML * ML - 1.0) * (ML * ML - 1.0);
+    }
+    if (fabs(MR) >= 1.0) { MmR = 0.5 * (MR - fabs(MR)); PmR = MR > 0.0 ? 0.0 : 1.0; }
+    else {
+      MmR = -0.25 * (MR - 1.0) * (MR - 1.0) - beta * (MR * MR - 1.0) * (MR * MR - 1.0);
+      PmR = 0.25 * (MR - 1.0) * (MR - 1.0) * (2.0 + MR) - alpha * MR * (MR * MR - 1.0) * (MR * MR - 1.0);
+    }
+    const double m = MpL + MmR;
+    const double mp = 0.5 * (m + fabs(m)), mm = 0.5 * (m - fabs(m));
+    prs = PpL * vL[P] + PmR * vR[P];
+#pragma unroll
+    for (int nv = 0; nv < 4; nv++) fl[nv] = a * (mp * uL[nv] + mm * uR[nv]);
+    fl[4] = a * (mp * (uL[4] + vL[P]) + mm * (uR[4] + vR[P]));
+    cmax = fmax(fabs(vL[1]) + aL, fabs(vR[1]) + aR);
+    machv = fmax(fabs(ML), fabs(MR));
+    done = true;
+  } else if (force_hll) {       // roe.c:101-116, two_shock.c:66-88: HLL in zones flagged by MULTID flattening
     const double aL = sqrt(a2L), aR = sqrt(a2R);
     double bmin = fmin(vL[1] - aL, vR[1] - aR), bmax = fmax(vL[1] + aL, vR[1] + aR);
     double scrh = fabs(vL[1]) + fabs(vR[1]);

@@ -80,8 +80,8 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (cfg->body_force < 0 || cfg->body_force > 3) return fail(PB200_EINVAL, "bad body_force");
   if (cfg->reconstruction < PB200_FLAT || cfg->reconstruction > PB200_PARABOLIC)
     return fail(PB200_EINVAL, "bad reconstruction");
-  if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_TWO_SHOCK) return fail(PB200_EINVAL, "bad solver");
-  if (cfg->solver == PB200_TWO_SHOCK && iso) return fail(PB200_ENOTSUP, "two_shock needs EOS IDEAL (Src/HD/set_solver.c:45-49)");
+  if (cfg->solver < PB200_TVDLF || cfg->solver > PB200_AUSM) return fail(PB200_EINVAL, "bad solver");
+  if (cfg->solver >= PB200_TWO_SHOCK && iso) return fail(PB200_ENOTSUP, "two_shock and ausm+ need EOS IDEAL (Src/HD/set_solver.c:25-49)");
   if (cfg->time_stepping < PB200_EULER || cfg->time_stepping > PB200_RK3)
     return fail(PB200_EINVAL, "bad time_stepping");
   int need = cfg->reconstruction == PB200_PARABOLIC ? 3 : 2;

@@ -376,6 +376,7 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
   else if (d->fluidRiemannSolver == &Roe_Solver)  cfg.solver = PB200_ROE;
 #if EOS == IDEAL
   else if (d->fluidRiemannSolver == &TwoShock_Solver) cfg.solver = PB200_TWO_SHOCK;
+  else if (d->fluidRiemannSolver == &AUSMp_Solver)    cfg.solver = PB200_AUSM;
 #endif
   else {
     print ("! AdvanceStep(): this Riemann solver is not available in libplutob200\n");

@@ -23,7 +23,7 @@ from . import _lib as L
 NVAR_HD = 5
 RHO, VX1, VX2, VX3, PRS = 0, 1, 2, 3, 4
 
-_SOLVERS = {"tvdlf": L.TVDLF, "hll": L.HLL, "hllc": L.HLLC, "roe": 4, "two_shock": 5}
+_SOLVERS = {"tvdlf": L.TVDLF, "hll": L.HLL, "hllc": L.HLLC, "roe": 4, "two_shock": 5, "ausm+": 6}
 _RECON = {"FLAT": L.FLAT, "LINEAR": L.LINEAR, "PARABOLIC": L.PARABOLIC}
 _TSTEP = {"EULER": L.EULER, "RK2": L.RK2, "RK3": L.RK3}
 

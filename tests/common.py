@@ -13,7 +13,7 @@ ISO_CASES = ["iso2d_hll", "iso2d_hllc", "iso2d_flat_hllc", "iso3d_tvdlf", "iso_s
 CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2d_hllc", "pol3d_hll", "pot_sph2d_hllc",
                   "pot_sph3d_both_hll",
                   # Roe_Solver (both equations of state) and TwoShock_Solver
-                  "roe_cart2d", "roe_iso2d", "roe_sph2d_flat", "pot_pol2d_roe", "twoshock_sph2d_flat", "twoshock_sph3d",
+                  "roe_cart2d", "roe_iso2d", "roe_sph2d_flat", "pot_pol2d_roe", "twoshock_sph2d_flat", "twoshock_sph3d", "ausm_sph2d",
                   # SHOCK_FLATTENING ONED (States/flatten.c)
                   "oned_iso2d_hll", "oned_sph2d_hllc", "oned_sph2d_char_roe",
                   # RECONSTRUCTION PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c
