@@ -66,9 +66,9 @@ def gen_kwargs_from_golden(g):
             grid.append((float(row[0]), int(row[1]), float(row[2]), "r", float(row[4])))
         else:
             grid.append((float(row[0]), int(row[1]), float(row[2])))
-    flat = int(g["shock_flattening"])      # 0 NO, 1 MULTID, 2 ONED (oracle-only fixtures)
+    flat = int(g["shock_flattening"])      # 0 NO, 1 MULTID, 2 ONED
     extra = {}
-    if "eos" in g and str(g["eos"]) == "ISOTHERMAL":     # only the oracle-only fixtures carry these keys
+    if "eos" in g and str(g["eos"]) == "ISOTHERMAL":     # only the iso* fixtures carry these keys
         extra = dict(eos="ISOTHERMAL", iso_sound_speed=float(g["iso_cs"]))
     return dict(**extra, dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],

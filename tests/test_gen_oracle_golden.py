@@ -46,8 +46,8 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     solve on stretched grids, the closed forms on uniform cylindrical / spherical radial grids, the 5-point
     Gauss moments of sin(theta) for the meridional direction, PPM_Q6_Coeffs), the pot_* ones BODY_FORCE
     POTENTIAL (and VECTOR + POTENTIAL) on spherical and polar grids.
-    These fixtures pin the oracle; the CUDA path runs the iso* ones too (tests/test_gpu_gen.py: ISO_CASES, EOS
-    ISOTHERMAL) and still refuses the other options (PB200_ENOTSUP)."""
+    These fixtures pin the oracle; the CUDA path runs every one of them too (tests/test_gpu_gen.py: ISO_CASES,
+    CURV_GPU_CASES)."""
     g = load_golden(name)
     o = GenOracle(**gen_kwargs_from_golden(g))
     set_point_mass_gravity(o, float(g["gm"]))
