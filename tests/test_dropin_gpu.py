@@ -306,3 +306,53 @@ def test_dropin_isothermal_line_driven_wind_matches_reference_executable(cuda_li
         assert n1 == n2 and abs(t1 - t2) <= 1e-11 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-10 * d1
     assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
     assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
+
+
+HALF_PI, TWO_PI = 1.5707963267948966, 6.283185307179586
+SPH_PAR = dict(GM=1.0, RBLOB=2.0, TBLOB=1.0, PBLOB=5.0)
+CYL_PAR = dict(GM=1.0, RBLOB=1.6, ZBLOB=0.6, PBLOB=4.0)
+GENERAL_OPTION_CASES = {
+    # RECONSTRUCTION PARABOLIC + RK3 on a stretched Cartesian grid: the shim hands grid->uniform over and the
+    # context leaves the marching kernels for the general path (PPM_FindWeights weights); Roe solver
+    "kh3d_ppm": dict(nvar=6, grid=[(0.0, 16, 1.0, "r", 1.04), (-0.5, 20, 0.5, "r", 0.97), (0.0, 8, 0.5)], solver="roe",
+                     bcs=("periodic", "periodic", "outflow", "outflow", "periodic", "periodic"),
+                     params=dict(A_KH=0.05, DRHO=1.0, MACH=0.8), first_dt=1e-4, maxsteps=8),
+    # POLAR geometry + PPM: the reference's own Grid arrays through pb200_set_geometry, iMPHI = VX2
+    "pol2d_ppm": dict(nvar=6, grid=[(0.8, 32, 3.0, "r", 1.03), (0.0, 40, TWO_PI), (0.0, 1, 1.0)], solver="hllc",
+                      bcs=("reflective", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                      params=CYL_PAR, first_dt=1e-5, maxsteps=10),
+    # CYLINDRICAL + PPM + MULTID flattening with the AUSM+ solver
+    "cyl2d_ppm_flat": dict(nvar=6, grid=[(0.8, 36, 3.0, "r", 1.03), (0.0, 28, 1.5, "r", 1.02), (0.0, 1, 1.0)], solver="ausm+",
+                           bcs=("reflective", "outflow", "eqtsymmetric", "outflow", "periodic", "periodic"),
+                           params=CYL_PAR, first_dt=1e-5, maxsteps=10),
+    # SPHERICAL + CHAR_LIMITING + SHOCK_FLATTENING ONED (4 ghost zones) with the two-shock solver
+    "sph2d_char_oned": dict(nvar=6, grid=[(1.0, 40, 4.0, "r", 1.03), (0.2, 28, HALF_PI, "r", 0.97), (0.0, 1, 1.0)],
+                            solver="two_shock", bcs=("outflow", "outflow", "axisymmetric", "reflective", "periodic", "periodic"),
+                            params=SPH_PAR, first_dt=1e-5, maxsteps=10),
+}
+
+
+@pytest.mark.parametrize("cfg", list(GENERAL_OPTION_CASES))
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_dropin_general_path_options_match_reference_executable(cuda_lib, tmp_path, cfg, resident):
+    """The options the general path gained last (CYLINDRICAL / POLAR, PPM on stretched and curvilinear grids, ONED
+    flattening, Roe / two-shock / AUSM+) through the reference's own driver: pluto.ini parser, SetGrid / SetGeometry,
+    the user's Init / BodyForceVector, Boundary and NextTimeStep are the reference's objects; AdvanceStep is the shim."""
+    import pluto_grid
+    exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
+    if not exe.exists() or not refrun.have_ref(cfg):
+        pytest.skip("drop-in / reference executables were not built in the container (needs /root/reference)")
+    kw = dict(GENERAL_OPTION_CASES[cfg])
+    grid = kw.pop("grid")
+    nx = [int(g[1]) for g in grid]
+    kw.update(shape=(nx[2], nx[1], nx[0]), grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=10.0, dbl=(-1.0, 1),
+              timeout=200)
+    ref = refrun.run(cfg, tmp_path / "ref", **kw)
+    got = refrun.run(cfg, tmp_path / "b200", exe=exe, env={"PB200_RESIDENT": resident}, **kw)
+    assert "runs on the GPU" in got["log"]
+    assert len(got["data"]) == len(ref["data"]) >= 7
+    for (n1, t1, d1), (n2, t2, d2) in zip(ref["steps"], got["steps"]):
+        assert n1 == n2 and abs(t1 - t2) <= 1e-11 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-10 * d1
+    assert np.array_equal(ref["data"][0], got["data"][0])
+    assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
+    assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
