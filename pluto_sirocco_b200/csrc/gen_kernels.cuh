@@ -826,7 +826,9 @@ PB_D double riemann_roe_ts(const double (&vL)[NV], const double (&vR)[NV], bool 
 
 // ---- Riemann solver + AdvectFlux at the face between zone n and n+1 -------------------------
 // vLg / vRg: left / right state in GLOBAL variable order; F: flux in global order, F[NV] = pressure, F[NV+1] = cmax
-template <int NV>
+// X: the Roe / two-shock / AUSM+ code is compiled in (the fused sweeps are instantiated with and without it, so that the
+// HLL-family kernels keep their register budget)
+template <int NV, bool X = true>
 PB_D double gen_face(const GenDev &g, int dir, const double (&vLg)[NV], const double (&vRg)[NV], bool hll, double (&F)[NV + 2]) {
   const int gn = 1 + dir, gt = 1 + (dir + 1) % 3, gb = 1 + (dir + 2) % 3;
   double vL[NV], vR[NV];     // sweep-local order (n, t, b)
@@ -836,11 +838,13 @@ PB_D double gen_face(const GenDev &g, int dir, const double (&vLg)[NV], const do
   vL[3] = dir == 0 ? vLg[3] : (dir == 1 ? vLg[1] : vLg[2]); vR[3] = dir == 0 ? vRg[3] : (dir == 1 ? vRg[1] : vRg[2]);
 #pragma unroll
   for (int nv = 4; nv < NV; nv++) { vL[nv] = vLg[nv]; vR[nv] = vRg[nv]; }
-  if (g.iso || g.solver >= SOLVER_ROE) {
+  if (g.iso || (X && g.solver >= SOLVER_ROE)) {
     double fl[NV], prs, cmx;
-    const double mv = g.solver >= SOLVER_ROE
-                          ? riemann_roe_ts<NV>(vL, vR, g.iso != 0, g.cs2, g.d.gas.gamma, g.solver, hll, g.d.ndim, fl, prs, cmx)
-                          : riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
+    double mv;
+    if constexpr (X) {
+      mv = g.solver >= SOLVER_ROE ? riemann_roe_ts<NV>(vL, vR, g.iso != 0, g.cs2, g.d.gas.gamma, g.solver, hll, g.d.ndim, fl, prs, cmx)
+                                  : riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
+    } else mv = riemann_iso<NV>(vL, vR, g.cs2, g.solver, hll, fl, prs, cmx);
     if (g.entropy) fl[NV - 1] = fl[0] * sel(fl[0] >= 0.0, vL[NV - 1], vR[NV - 1]);    // adv_flux.c:131-134
     F[0] = fl[0];
     F[1] = dir == 0 ? fl[1] : (dir == 1 ? fl[3] : fl[2]);
@@ -1343,7 +1347,7 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
 // stay coalesced along i).  The first and last zone of a tile only supply their states: S - 2 zones per tile are
 // updated.  vm of zone n+1 and the flux of face n-1/2 reach zone n through shared memory (two barriers).
 // FIRST (stage 1, first direction) also does PrimToCons3D + the U0 copy (rk_step.c:129-130) of its zones.
-template <int NV, int S, int L>
+template <int NV, int S, int L, bool X>
 static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, int first) {
   __shared__ double sh[NV + 2][S * L];
   const Dev &d = g.d;
@@ -1377,7 +1381,7 @@ static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, i
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) vR[nv] = sh[nv][tid + L];
     const bool hll = g.flatten && ((a.flag[o] & GF_HLL) || (a.flag[o + st] & GF_HLL));
-    machv = gen_face<NV>(g, dir, vp, vR, hll, F);
+    machv = gen_face<NV, X>(g, dir, vp, vR, hll, F);
     if ((d.bf_kind & 2) && !g.iso) F[pidx<NV>()] += F[iRHO] * bf_at(d, 4 + dir, i, j, k);   // TotalFlux(), rhs.c:171-179,525
   } else {
 #pragma unroll

@@ -51,6 +51,17 @@ void pb200_gen_release(pb200_ctx *c) {
 static void ppm_coefficients(int geo, int d, int nt, const double *xl, const double *xr, const double *dx, const double *xc,
                              bool uniform, std::vector<double> &w, std::vector<double> &hp, std::vector<double> &hm);
 
+// fused-sweep tile shapes (alternatives measured on the 1024 x 512 line-driven wind: profiles/r02_v4_gen_tiles.txt)
+#ifndef PB_GEN_S0
+#define PB_GEN_S0 128
+#endif
+#ifndef PB_GEN_S1
+#define PB_GEN_S1 16
+#endif
+#ifndef PB_GEN_L1
+#define PB_GEN_L1 32
+#endif
+
 int pb200_gen_setup(pb200_ctx *c) {
   if (c->gen_ready) return PB200_OK;
   pb200_gen_release(c);
@@ -652,9 +663,17 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
       c->launches++;
     }
     const int first = (stage == 1 && dir == 0) ? 1 : 0;
-    if (dir == 0) gen_sweep<NV, 128, 1><<<dim3(ny, (nx + 125) / 126, nzz), 128, 0, st>>>(G, a, first);
-    else if (dir == 1) gen_sweep<NV, 16, 32><<<dim3((nx + 31) / 32, (ny + 13) / 14, nzz), 512, 0, st>>>(G, a, first);
-    else gen_sweep<NV, 16, 32><<<dim3((nx + 31) / 32, (nzz + 13) / 14, ny), 512, 0, st>>>(G, a, first);
+    // tile shapes (zones along the sweep x lanes across it); S - 2 zones of a tile are updated
+    constexpr int S0 = PB_GEN_S0, S1 = PB_GEN_S1, L1 = PB_GEN_L1;
+    const dim3 g0(ny, (nx + S0 - 3) / (S0 - 2), nzz), g1((nx + L1 - 1) / L1, (ny + S1 - 3) / (S1 - 2), nzz),
+        g2((nx + L1 - 1) / L1, (nzz + S1 - 3) / (S1 - 2), ny);
+    if (G.solver >= SOLVER_ROE) {       // Roe / two-shock / AUSM+: the instantiation that carries them
+      if (dir == 0) gen_sweep<NV, S0, 1, true><<<g0, S0, 0, st>>>(G, a, first);
+      else gen_sweep<NV, S1, L1, true><<<dir == 1 ? g1 : g2, S1 * L1, 0, st>>>(G, a, first);
+    } else {
+      if (dir == 0) gen_sweep<NV, S0, 1, false><<<g0, S0, 0, st>>>(G, a, first);
+      else gen_sweep<NV, S1, L1, false><<<dir == 1 ? g1 : g2, S1 * L1, 0, st>>>(G, a, first);
+    }
     c->launches++;
   }
   for (int dir = 0; dir < D.ndim && !fused; dir++) {
