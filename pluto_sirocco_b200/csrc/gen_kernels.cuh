@@ -39,6 +39,7 @@ struct LdwDev {
   double UL, UV, UD;                        // UNIT_LENGTH, UNIT_VELOCITY, UNIT_DENSITY
   double kelvin_mu;                         // KELVIN * mu
   double krad, alpharad;
+  int alpha_m06;                            // ALPHARAD == -0.6 (the value cv_idl ships): dvds^0.6 through pow_three_fifths()
   double t_iso;                             // > 0: EOS ISOTHERMAL, the temperature of LineForce() is g_inputParam[T_ISO]
   int mpoints;                              // > 0: force multiplier from the per-zone M(t) fit (KRAD = ALPHARAD = 999)
   const double *t_fit, *m_fit;              // log10(t) [mpoints]; log10(M) [mpoints][k][j][i]
@@ -1065,7 +1066,11 @@ static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenB
       // different centre states); the bin-dependent factor dvds^(-alpha) is taken once and serves
       // both, so that a zone costs one pow() per sweep instead of 36.
       // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
-      if (out > 0.0) D = w.mpoints > 0 ? out : exp(-w.alpharad * log(out));   // fit mode keeps dvds itself
+      if (out > 0.0) {
+        if (w.mpoints > 0) D = out;              // fit mode keeps dvds itself
+        else if (w.alpha_m06 && out >= 1e-12 && out <= 1e12) D = pow_three_fifths(out);
+        else D = exp(-w.alpharad * log(out));
+      }
     }
     // ((1 + M) sigma_e F / c) / UNIT_ACCELERATION with the two constant divisions folded into one
     // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)

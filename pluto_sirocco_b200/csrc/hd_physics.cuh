@@ -76,6 +76,23 @@ PB_D double sqrt_fast(double x) {   // sqrt(0) = 0, sqrt(<0) = NaN like libm
   return x == 0.0 ? 0.0 : s;
 }
 PB_D double div_fast(double a, double b) { return a * rcp_fast(b); }
+// x^(3/5) for 1e-12 <= x <= 1e12: with c = x^3, z -> c^(-1/5) by the division-free Newton step z <- z (6 - c z^5) / 5
+// from a single-precision seed (ex2.approx(-0.6 lg2.approx(x)): relative error < 1e-5; each step maps e to 3 e^2:
+// 3e-10, 3e-19), and c^(1/5) = c z^4.  ~20 FP64 operations where exp(0.6 log(x)) takes ~60; a few ulp like it.
+PB_D double pow_three_fifths(double x) {
+  float lx, sd;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lx) : "f"((float)x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(-0.6f * lx));
+  const double c = x * x * x;
+  double z = (double)sd;
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double z2 = z * z, z4 = z2 * z2;
+    z = (z * 0.2) * fma(-c * z4, z, 6.0);
+  }
+  const double z2 = z * z;
+  return c * (z2 * z2);
+}
 
 PB_D double sel(bool c, double a, double b) { return c ? a : b; }
 PB_D double absmin(double a, double b) { return fabs(a) < fabs(b) ? a : b; }

@@ -287,6 +287,7 @@ void pb200_fill_ldw(pb200_ctx *c, pb::GenDev &G) {
   const double KELVIN = L.unit_velocity * L.unit_velocity * amu / kB;      // pluto.h:560
   w.kelvin_mu = KELVIN * L.mu;
   w.krad = L.krad; w.alpharad = L.alpharad;
+  w.alpha_m06 = L.alpharad == -0.6 && !getenv("PB200_LDW_GENERIC_POW");
   w.t_iso = c->cfg.eos == PB200_EOS_ISOTHERMAL ? L.t_iso : 0.0;
   w.mpoints = c->ldw_mpoints; w.t_fit = c->ldw_tfit; w.m_fit = c->ldw_mfit;
   w.sigma_e = sigmaT / amu / 1.18;

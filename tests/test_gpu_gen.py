@@ -249,6 +249,43 @@ def test_ldw_bench_grid_1024x512_vs_oracle(Hydro):
     h.close(); o.close()
 
 
+@pytest.mark.parametrize("alpha", [-0.6, -0.7, -0.45])
+def test_ldw_force_multiplier_exponents_vs_oracle(Hydro, alpha):
+    """M(t) = k t^alpha of LineForce() (line_connect.c:858-870) for the exponent cv_idl ships (-0.6: the per-bin
+    dvds^0.6 goes through pow_three_fifths(), a Newton fifth root) and for others (exp / log): three steps from a
+    developed wind state against the oracle, which calls libm's pow() like the reference."""
+    from common import LDW_BCS, LDW_PARAMS, LDW_UNITS, ldw_flux_tables
+    grid = [(0.87, 48, 8.7, "r", 1.05), (0.0, 36, 1.5707963267948966, "r", 0.95), (0.0, 1, 1.0)]
+    kw = dict(dimensions=2, grid=grid, geometry="SPHERICAL", gamma=5. / 3., time_stepping="RK2", solver="hll",
+              limiter="VANLEER_LIM", bcs=LDW_BCS, ntracer=1, body_force=1, char_limiting=True,
+              shock_flattening=True, entropy_switch=True, nghost=3)
+    o = GenOracle(**kw)
+    h = Hydro(**hydro_kwargs_from_gen(kw))
+    params = dict(LDW_PARAMS, ALPHARAD=alpha)
+    gm_code = 6.6726e-8 * params["CENT_MASS"] / (LDW_UNITS["length"] * LDW_UNITS["velocity"] ** 2)
+    for obj in (o, h):
+        x1, x2 = obj.x(0), obj.x(1)
+        fr, ft, fp = ldw_flux_tables(x1, x2)
+        obj.set_body_force_vector(0, (-gm_code / (x1 * x1)).reshape(1, 1, -1))
+        obj.set_body_force_vector(1, np.zeros((1, 1, 1)))
+        obj.set_body_force_vector(2, np.zeros((1, 1, 1)))
+        obj.set_ldw(params=params, units=LDW_UNITS, flux_r=fr, flux_t=ft, flux_p=fp)
+    g = load_golden("ldw_nocool_hll")
+    v = np.zeros((7, 1, 36, 48))
+    v[:6] = g["data"][5]
+    v[6] = 1.0
+    vc = o.embed(v); h.set_interior(v)
+    dt = float(g["steps"][5, 2])
+    for n in range(3):
+        inv, mach, nf = o.advance_step(vc, dt)
+        info = h.advance_step(dt)
+        got, ref = h.get_interior(), vc[o.interior()]
+        assert rel_err(got[:6], ref[:6]) <= TOL_STEP, (alpha, n, rel_err(got[:6], ref[:6]))
+        assert abs(info.invDt_hyp - inv) <= TOL_STEP * inv
+        h.set_interior(ref)
+    h.close(); o.close()
+
+
 def test_ldw_floors_and_boundaries_vs_oracle(Hydro):
     """User boundaries of cv_idl on a state that triggers the density / pressure floors (also
     inside stage 2, where Uc is re-derived), the mid-plane reset and the hybrid X2_BEG fill."""
