@@ -1029,8 +1029,7 @@ static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenB
   const double inv_maxds = 1.0 / maxds;
   const double vUV[2][4] = {{v11[0] * w.UV, v12[0] * w.UV, v21[0] * w.UV, v22[0] * w.UV},
                             {v11[1] * w.UV, v12[1] * w.UV, v21[1] * w.UV, v22[1] * w.UV}};
-  for (int ia = 0; ia < w.nangles; ia++) {
-    const double fr = __ldg(w.flux_r + ia * nz + o), ft = __ldg(w.flux_t + ia * nz + o);
+  auto bin = [&](int ia, double fr, double ft) {
     double D = 0.0;
     if ((mk >> ia) & 1ull) {   // mod_flux != 0
       const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
@@ -1076,7 +1075,21 @@ static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenB
     // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)
     g_r += ((1.0 + gen_ldw_M(w, zr, D, o, nz)) * coef) * fr;
     g_t += ((1.0 + gen_ldw_M(w, zt, D, o, nz)) * coef) * ft;
+  };
+  // NB bins per iteration: their (coalesced, streaming) flux loads are issued together and the NB independent
+  // dependency chains interleave - the kernel waits on load and FP64 latencies, not on a pipe
+  // (profiles/r02_v4_gen_tiles.txt: 1, 2, 3, 4 bins per iteration -> 0.998, 0.950, 0.937, 0.937 ms per C4 step).
+  // The sums still take the bins in order.
+  constexpr int NB = 3;
+  int ia = 0;
+  for (; ia + NB - 1 < w.nangles; ia += NB) {
+    double fa[NB], ta[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) { fa[q] = __ldg(w.flux_r + (ia + q) * nz + o); ta[q] = __ldg(w.flux_t + (ia + q) * nz + o); }
+#pragma unroll
+    for (int q = 0; q < NB; q++) bin(ia + q, fa[q], ta[q]);
   }
+  for (; ia < w.nangles; ia++) bin(ia, __ldg(w.flux_r + ia * nz + o), __ldg(w.flux_t + ia * nz + o));
   w.gline[o] = g_r;
   w.gline[nz + o] = g_t;
 }
@@ -1352,8 +1365,8 @@ static __global__ void gen_rhs(GenDev g, GenArgs a, GenBox b) {
 // stay coalesced along i).  The first and last zone of a tile only supply their states: S - 2 zones per tile are
 // updated.  vm of zone n+1 and the flux of face n-1/2 reach zone n through shared memory (two barriers).
 // FIRST (stage 1, first direction) also does PrimToCons3D + the U0 copy (rk_step.c:129-130) of its zones.
-template <int NV, int S, int L, bool X>
-static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, int first) {
+template <int NV, int S, int L, bool X, int MB = 1>
+static __global__ void __launch_bounds__(S * L, MB) gen_sweep(GenDev g, GenArgs a, int first) {
   __shared__ double sh[NV + 2][S * L];
   const Dev &d = g.d;
   const int dir = a.dir;
@@ -1370,6 +1383,17 @@ static __global__ void __launch_bounds__(S * L) gen_sweep(GenDev g, GenArgs a, i
   const long st = dir == 0 ? 1 : (dir == 1 ? d.sj : d.sk);
   const long o = (long)k * d.sk + (long)j * d.sj + i;
   const long nz = d.sv;
+  if (st_ok) {
+    // the lines the Riemann and right-hand-side phases will read are requested (into L2) before the states are built:
+    // a tile's warps wait on global-memory latency most of the time (ncu: long scoreboard), -2.4 % per C4 step
+    auto pf = [&](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) pf(a.U + nv * nz + o);
+    pf(a.cdt + o);
+    pf(g.dV + o);
+    pf(g.A[dir] + g.Aoff[dir] + (long)k * g.Ask[dir] + (long)j * g.Asj[dir] + i);
+    if (g.ldw.on) { pf(g.ldw.gline + o); pf(g.ldw.gline + nz + o); if (a.defer) { pf(a.cen + o); pf(a.cen + nz + o); pf(a.cen + 2 * nz + o); } }
+  }
   double v[NV], vp[NV], vm[NV];
   if (st_ok) gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
   else {

@@ -52,6 +52,9 @@ static void ppm_coefficients(int geo, int d, int nt, const double *xl, const dou
                              bool uniform, std::vector<double> &w, std::vector<double> &hp, std::vector<double> &hm);
 
 // fused-sweep tile shapes (alternatives measured on the 1024 x 512 line-driven wind: profiles/r02_v4_gen_tiles.txt)
+#ifndef PB_GEN_MB0
+#define PB_GEN_MB0 4      // resident r-sweep tiles per SM the register budget is cut for (128 registers: 16 warps instead of 12)
+#endif
 #ifndef PB_GEN_S0
 #define PB_GEN_S0 128
 #endif
@@ -669,10 +672,10 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     const dim3 g0(ny, (nx + S0 - 3) / (S0 - 2), nzz), g1((nx + L1 - 1) / L1, (ny + S1 - 3) / (S1 - 2), nzz),
         g2((nx + L1 - 1) / L1, (nzz + S1 - 3) / (S1 - 2), ny);
     if (G.solver >= SOLVER_ROE) {       // Roe / two-shock / AUSM+: the instantiation that carries them
-      if (dir == 0) gen_sweep<NV, S0, 1, true><<<g0, S0, 0, st>>>(G, a, first);
+      if (dir == 0) gen_sweep<NV, S0, 1, true, PB_GEN_MB0><<<g0, S0, 0, st>>>(G, a, first);
       else gen_sweep<NV, S1, L1, true><<<dir == 1 ? g1 : g2, S1 * L1, 0, st>>>(G, a, first);
     } else {
-      if (dir == 0) gen_sweep<NV, S0, 1, false><<<g0, S0, 0, st>>>(G, a, first);
+      if (dir == 0) gen_sweep<NV, S0, 1, false, PB_GEN_MB0><<<g0, S0, 0, st>>>(G, a, first);
       else gen_sweep<NV, S1, L1, false><<<dir == 1 ? g1 : g2, S1 * L1, 0, st>>>(G, a, first);
     }
     c->launches++;
