@@ -346,7 +346,7 @@ def test_fused_boundaries_equal_boundary_kernels(Hydro, monkeypatch, recon, rk, 
 def test_errors(Hydro):
     from pluto_sirocco_b200._lib import ENAN, PB200Error
     with pytest.raises(ValueError):
-        Hydro(dimensions=1, nx=(32, 1, 1), solver="roe")          # SetSolver: not available
+        Hydro(dimensions=1, nx=(32, 1, 1), solver="hlld")         # SetSolver (HD/set_solver.c): not an HD solver
     h = Hydro(dimensions=1, nx=(32, 1, 1))
     v = np.ones((5, 1, 1, 32)); v[1:4] = 0
     h.set_interior(v)
