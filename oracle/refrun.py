@@ -75,7 +75,7 @@ def read_dbl(path, nvar, shape):
 
 
 def run(cfg, workdir, *, shape, nvar=5, maxsteps=None, no_write=False, extra_args=(),
-        timeout=300, exe=None, env=None, **ini):
+        timeout=300, exe=None, env=None, keep=False, **ini):
     """Run oracle/_ref/<cfg>/pluto in `workdir` with a generated pluto.ini.
 
     shape = (nz, ny, nx) interior zones.  Returns dict(steps=[(nstep,t,dt)], data=[arrays],
@@ -85,11 +85,12 @@ def run(cfg, workdir, *, shape, nvar=5, maxsteps=None, no_write=False, extra_arg
         raise FileNotFoundError("%s missing: run `python oracle/build_ref.py %s`" % (exe, cfg))
     wd = Path(workdir)
     wd.mkdir(parents=True, exist_ok=True)
-    for f in wd.glob("data.*.dbl"):
-        f.unlink()
-    for f in ("restart.out", "dbl.out", "grid.out"):
-        if (wd / f).exists():
-            (wd / f).unlink()
+    if not keep:      # keep=True: a restart cycle (-restart) continues from the files of the previous run
+        for f in wd.glob("data.*.dbl"):
+            f.unlink()
+        for f in ("restart.out", "dbl.out", "grid.out"):
+            if (wd / f).exists():
+                (wd / f).unlink()
     write_ini(wd / "pluto.ini", **ini)
     cmd = [str(exe)]
     if maxsteps is not None:

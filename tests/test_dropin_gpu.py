@@ -356,3 +356,66 @@ def test_dropin_general_path_options_match_reference_executable(cuda_lib, tmp_pa
     assert np.array_equal(ref["data"][0], got["data"][0])
     assert rel_err(got["data"][1], ref["data"][1]) <= TOL_STEP
     assert rel_l1(got["data"][-1], ref["data"][-1]) <= TOL_RUN
+
+
+def _coupling_cycles(cfg, wd, exe, env, ncycles=3, steps_per_cycle=5):
+    """What Test_Problems/LineDrivenWind/cv_idl/pluto_sirocco_dir_iso.py:100-140 does around the hydro code, with
+    synthetic sirocco output: cycle 0 runs ./pluto with the k-alpha force multiplier and the initial flux files; every
+    later cycle gets new directional_flux_*.dat, M_UV_data.dat (KRAD = ALPHARAD = 999), py_heatcool.dat and
+    prefactors.dat and runs ./pluto -restart from the last dbl file (Src/main.c:142-201 re-reads all tables)."""
+    import pluto_grid
+    from common import (LDW_BCS, LDW_PARAMS, LDW_UNITS, ldw_flux_tables, ldw_mfit_tables, write_ldw_flux_files,
+                        write_ldw_mfit_file)
+    from test_sirocco_tables import _write_heatcool
+    grid = [(0.87, 48, 8.7, "r", 1.05), (0.0, 36, 1.5707963267948966, "r", 0.95), (0.0, 1, 1.0)]
+    ng = 3
+    xl1, xr1, _ = pluto_grid.make_grid(grid[0], ng)
+    xl2, xr2, _ = pluto_grid.make_grid(grid[1], ng)
+    x1, x2 = 0.5 * (xl1 + xr1), 0.5 * (xl2 + xr2)
+    fr, ft, fp = ldw_flux_tables(x1, x2)
+    wd.mkdir()
+    out = []
+    for cyc in range(ncycles):
+        scale = 1.0 + 0.15 * cyc                      # the radiation field changes from cycle to cycle
+        write_ldw_flux_files(wd, x1, x2, ng, fr * scale, ft * scale, fp)
+        params = dict(LDW_PARAMS)
+        if cyc > 0:
+            rng = np.random.default_rng(100 + cyc)
+            t, M, lt, lM = ldw_mfit_tables(x1, x2)
+            write_ldw_mfit_file(wd, x1, x2, ng, t, M * scale)
+            _write_heatcool(wd / "py_heatcool.dat", x1, x2, ng, rng)
+            rows = []
+            for j in range(ng, len(x2) - ng):
+                for i in range(ng, len(x1) - ng):
+                    rows.append("%d %.17e %d %.17e %s" % (i - ng, x1[i] * LDW_UNITS["length"], j - ng, x2[j],
+                                                          " ".join("%.17e" % q for q in rng.uniform(0.5, 2.0, 7))))
+            (wd / "prefactors.dat").write_text("# header\n" + "\n".join(rows) + "\n")
+            params.update(KRAD=999.0, ALPHARAD=999.0)
+        r = refrun.run(cfg, wd, shape=(1, 36, 48), nvar=6, maxsteps=steps_per_cycle * (cyc + 1), timeout=250, exe=exe,
+                       env=env, keep=cyc > 0, extra_args=("-restart", str(len(out[-1]["data"]) - 1)) if cyc > 0 else (),
+                       grid=[pluto_grid.ini_string(g) for g in grid], cfl=0.4, tstop=1.0, first_dt=1e-4,
+                       solver="hll", bcs=LDW_BCS, dbl=(-1.0, 1), params=params)
+        out.append(r)
+    return out
+
+
+@pytest.mark.parametrize("resident", ["0", "1"])
+def test_dropin_coupling_cycles_with_restart(cuda_lib, tmp_path, resident):
+    """three cycles of the pluto <-> sirocco loop on the drop-in executable - restart from its own
+    data.NNNN.dbl / restart.out, new flux, force-multiplier, heating / cooling and prefactor files every cycle (read by
+    the library's table readers, PB200_FAST_TABLES=1) - against the stock executable put through the same cycles."""
+    cfg = "ldw"
+    exe = ROOT / "integration" / "_build" / cfg / "pluto_b200"
+    if not exe.exists() or not refrun.have_ref(cfg):
+        pytest.skip("drop-in / reference executables were not built in the container (needs /root/reference)")
+    ref = _coupling_cycles(cfg, tmp_path / "ref", None, {})
+    got = _coupling_cycles(cfg, tmp_path / "b200", exe, {"PB200_RESIDENT": resident, "PB200_FAST_TABLES": "1"})
+    for cyc, (r, g) in enumerate(zip(ref, got)):
+        assert "runs on the GPU" in g["log"]
+        if cyc > 0:
+            assert "libplutob200 table readers" in g["log"] and "Read in 1728 py_heatcool entries" in r["log"]
+        assert len(g["data"]) == len(r["data"]) and len(r["steps"]) == len(g["steps"])
+        for (n1, t1, d1), (n2, t2, d2) in zip(r["steps"], g["steps"]):
+            assert n1 == n2 and abs(t1 - t2) <= 1e-10 * max(t1, 1e-30) and abs(d1 - d2) <= 1e-9 * d1
+        assert rel_l1(g["data"][-1], r["data"][-1]) <= TOL_RUN, (cyc, rel_l1(g["data"][-1], r["data"][-1]))
+    assert ref[-1]["steps"][-1][0] >= 15 and len(ref[-1]["data"]) > len(ref[0]["data"])
