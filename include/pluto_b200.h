@@ -66,6 +66,7 @@ extern "C" {
 #define PB200_BC_EQTSYMMETRIC 4
 #define PB200_BC_PERIODIC     5
 #define PB200_BC_USERDEF      8
+#define PB200_BC_POLARAXIS    9   /* PolarAxisBoundary(), Src/boundary.c:770-840 (general path) */
 #define PB200_BC_NEIGHBOUR    100
 
 /* BODY_FORCE bits: same values as Src/pluto.h (VECTOR 4, POTENTIAL 8) are NOT assumed; the
@@ -111,7 +112,11 @@ typedef struct pb200_config {
                             NVAR grows by ENTR (Src/entropy_switch.c, mappers.c:186-219, flag_shock.c:146,256) */
   int eos;               /* EOS: 0 IDEAL, PB200_EOS_ISOTHERMAL (Src/EOS/Isothermal: no energy equation, NVAR = 4 + NTRACER;
                             general path; e.g. Test_Problems/LineDrivenWind/cv_iso) */
-  int reserved[2];
+  int ring_average;      /* RING_AVERAGE (Src/ring_average.c, pluto.h:479): chunk size at the axis, a power of two > 1; 0 / 1: off.
+                            POLAR (axis at X1-beg) and SPHERICAL (axis at X2-beg / X2-end) with PB200_BC_POLARAXIS there
+                            and a periodic phi direction; general path */
+  int ring_average_rec;  /* RING_AVERAGE_REC 1 (none), 2 (van Leer), 5 (MP5, the reference's default when on; 3 ghost zones);
+                            0: that default */
   double iso_sound_speed;/* g_isoSoundSpeed (EOS ISOTHERMAL) */
 } pb200_config;
 

@@ -148,6 +148,13 @@ CONFIGS = {
                                                     "TIME_STEPPING": "RK3"}, states="ppm"),
     # C3: Kelvin-Helmholtz shear layer with a tracer (oracle/problems/kh)
     "kh3d": dict(local="kh", overrides={}, states="plm"),
+    # RING_AVERAGE (Src/ring_average.c) with the POLARAXIS boundary: polar (r, phi[, z]) from r = 0, spherical from theta = 0
+    "pol2d_ring": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "BODY_FORCE": "NO", "RING_AVERAGE": "8"}, states="plm"),
+    "pol2d_ring_vl": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "BODY_FORCE": "NO", "RING_AVERAGE": "8",
+                                                  "RING_AVERAGE_REC": "2"}, states="plm"),
+    "pol3d_ring": dict(local="cyl", overrides={"GEOMETRY": "POLAR", "DIMENSIONS": "3", "BODY_FORCE": "NO",
+                                               "RING_AVERAGE": "4"}, states="plm"),
+    "sph3d_ring": dict(local="sph", overrides={"DIMENSIONS": "3", "RING_AVERAGE": "4", "PHI_PERTURB": "YES"}, states="plm"),
     # the SAME reference sources compiled with FMA contraction (-mfma -ffp-contract=fast): a second, equally
     # valid rounding of the reference.  Long free-running comparisons use |ref_fma - ref| as the yardstick of
     # how far round-off differences are amplified by the flow itself (tests/test_dropin_gpu.py).

@@ -87,6 +87,9 @@ typedef struct gen_cfg {
   int uniform[3];           /* grid->uniform[d] (set_grid.c:67-72): one uniform patch along d */
   const double *bf_phi[4];  /* body_force bit 1 (POTENTIAL): BodyForcePotential at zone centres [0] and at the
                                x1 / x2 / x3 upper faces [1..3], [k][j][i] incl. ghosts */
+  /* --- RING_AVERAGE (Src/ring_average.c; Zhang et al. 2019): chunk size at the axis (> 1: on) and
+         RING_AVERAGE_REC 1 / 2 / 5 (pluto.h:479-489); needs a POLARAXIS boundary (bc code 9) --- */
+  int ring_average, ring_rec;
 } gen_cfg;
 
 #define NF(c) ((c)->iso ? 4 : NFLX)                     /* NFLX of the configuration (mod_defs.h) */
@@ -104,6 +107,7 @@ typedef struct {
   double *dx_dl[3];    /* [j][i] */
   double (*pwp[3])[4];  /* PPM interface weights wp[i][-1..2] (PPM_CoefficientsSet, order 4) */
   double *php[3], *phm[3];   /* PPM_Q6_Coeffs */
+  int *csize;          /* grid->ring_av_csize[]: per i (POLAR) or j (SPHERICAL), 0 outside the interior */
 } geom_t;
 
 /* ---------------------------------------------------------------------------------------
@@ -146,6 +150,7 @@ static geom_t *geom_new(const gen_cfg *c) {
 /* grid->dx is an INPUT of the reference's geometry (set_grid.c fills it together with xl/xr and
  * xr - xl is not always bit-identical to it), so the caller may override it. */
 static void ppm_coeffs_set(const gen_cfg *c, geom_t *g);
+static void ring_size(const gen_cfg *c, geom_t *g);
 static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]) {
   int n1 = g->tot[0], n2 = g->tot[1], n3 = g->tot[2];
   for (int d = 0; d < 3; d++)
@@ -253,6 +258,7 @@ static void geom_finish(const gen_cfg *c, geom_t *g, const double *const dxin[3]
     }
   }
   if (c->ppm) ppm_coeffs_set(c, g);
+  ring_size(c, g);
 }
 
 /* ---------------------------------------------------------------------------------------
@@ -444,7 +450,7 @@ static void geom_free(geom_t *g) {
     free(g->cp[d]); free(g->cm[d]); free(g->wp[d]); free(g->wm[d]); free(g->dp[d]); free(g->dm[d]);
     free(g->A[d]); free(g->dx_dl[d]); free(g->pwp[d]); free(g->php[d]); free(g->phm[d]);
   }
-  free(g->rt); free(g->s); free(g->sp); free(g->dmu); free(g->dV);
+  free(g->rt); free(g->s); free(g->sp); free(g->dmu); free(g->dV); free(g->csize);
   free(g);
 }
 
@@ -1204,12 +1210,36 @@ static double *g_Uc_for_floor = NULL;   /* Uc, while Boundary() runs inside stag
 static void ldw_userdef_side(const gen_cfg *c, const geom_t *g, double *Vc, int side);
 static void ldw_internal_floor(const gen_cfg *c, const geom_t *g, double *Vc);
 
+/* PolarAxisBoundary(), boundary.c:770-840: ghost zones across the axis take the zone half a turn away, the two
+ * components that change sign through the axis flipped */
+static void polar_axis_boundary(const gen_cfg *c, const geom_t *g, double *Vc, int side) {
+  int nvar = g->nvar, dir = side / 2, hi = side & 1;
+  int pdir = c->geometry == POLAR ? 1 : 2;                 /* phi: x2 (POLAR), x3 (SPHERICAL) */
+  int nphi = g->end[pdir] - g->beg[pdir] + 1;
+  int lo[3] = {0, 0, 0}, up[3] = {g->tot[0] - 1, g->tot[1] - 1, g->tot[2] - 1};
+  if (hi) { lo[dir] = g->end[dir] + 1; up[dir] = g->tot[dir] - 1; }
+  else { lo[dir] = 0; up[dir] = g->beg[dir] - 1; }
+  for (int k = lo[2]; k <= up[2]; k++)
+    for (int j = lo[1]; j <= up[1]; j++)
+      for (int i = lo[0]; i <= up[0]; i++) {
+        int src[3] = {i, j, k};
+        src[pdir] += nphi / 2;
+        if (src[pdir] > g->end[pdir]) src[pdir] -= nphi;
+        src[dir] = hi ? 2 * g->end[dir] - src[dir] + 1 : 2 * g->beg[dir] - src[dir] - 1;
+        long o = k * g->sk + j * g->sj + i, os = src[2] * g->sk + src[1] * g->sj + src[0];
+        for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = Vc[nv * g->sv + os];
+        Vc[(1 + dir) * g->sv + o] *= -1.0;                 /* POLAR: VX1, VX2; SPHERICAL: VX2, VX3 */
+        Vc[(1 + pdir) * g->sv + o] *= -1.0;
+      }
+}
+
 static void boundary(const gen_cfg *c, const geom_t *g, double *Vc) {
   int nvar = g->nvar;
   if (c->ldw_bc) ldw_internal_floor(c, g, Vc);        /* boundary.c:126-128, side == 0 */
   for (int side = 0; side < 2 * c->ndim; side++) {
     int type = c->bc[side], dir = side / 2, hi = side & 1;
     if (type == 8) { if (c->ldw_bc) ldw_userdef_side(c, g, Vc, side); continue; }
+    if (type == 9) { polar_axis_boundary(c, g, Vc, side); continue; }
     if (type != 1 && type != 2 && type != 3 && type != 4 && type != 5) continue;
     int nb = g->beg[dir], ne = g->end[dir], nxd = ne - nb + 1;
     int lo[3] = {0, 0, 0}, up[3] = {g->tot[0] - 1, g->tot[1] - 1, g->tot[2] - 1};
@@ -1302,6 +1332,154 @@ static void flag_shock(const gen_cfg *c, const geom_t *g, const double *Vc, uint
 static void ldw_vgrad_calc(const gen_cfg *c, const geom_t *g, const double *Vc, double *dvds);
 static void ldw_line_force(const gen_cfg *c, const geom_t *g, const double *v, const double *dvds, long o, double *grad);
 
+/* ---------------------------------------------------------------------------------------
+ *  RING_AVERAGE: Src/ring_average.c (RingAverageSize :620-735, RingAverageCons :27-131,
+ *  RingAverageReconstruct :172-400), MP5_Reconstruct / Median of Src/reconstruct.c:38-93,296-304
+ * --------------------------------------------------------------------------------------- */
+static void ring_size(const gen_cfg *c, geom_t *g) {
+  int rd = c->geometry == POLAR ? 0 : 1;                   /* rings are counted along r (POLAR) or theta (SPHERICAL) */
+  g->csize = calloc(g->tot[rd], sizeof(int));
+  if (c->ring_average <= 1) return;
+  int cs;
+  if (c->bc[2 * rd] == 9) {                                /* axis at the lower boundary */
+    cs = c->ring_average;
+    for (int n = g->beg[rd]; n <= g->end[rd]; n++) { g->csize[n] = cs; if (cs > 1) cs >>= 1; }
+  } else for (int n = g->beg[rd]; n <= g->end[rd]; n++) g->csize[n] = 1;
+  if (c->geometry == SPHERICAL) {                          /* south pole */
+    if (c->bc[3] == 9) {
+      cs = c->ring_average;
+      for (int n = g->end[1]; n >= g->beg[1]; n--) { g->csize[n] = MAXV(g->csize[n], cs); if (cs > 1) cs >>= 1; }
+    } else for (int n = g->end[1]; n >= g->beg[1]; n--) g->csize[n] = MAXV(g->csize[n], 1);
+  }
+}
+
+static void ring_average_cons(const gen_cfg *c, const geom_t *g, double *Uc) {
+  int nvar = g->nvar;
+  double uav[NVMAX], dVav;
+  if (c->geometry == POLAR) {
+    if (g->csize[g->beg[0]] == 1) return;
+    int i = g->beg[0];
+    while (i <= g->end[0] && g->csize[i] > 1) {
+      for (int k = g->beg[2]; k <= g->end[2]; k++)
+        for (int j = g->beg[1]; j <= g->end[1]; j += g->csize[i]) {
+          dVav = 0.0;
+          for (int nv = 0; nv < nvar; nv++) uav[nv] = 0.0;
+          for (int j1 = j; j1 < j + g->csize[i]; j1++) {
+            long o = k * g->sk + j1 * g->sj + i;
+            dVav += g->dV[o];
+            for (int nv = 0; nv < nvar; nv++) uav[nv] += Uc[o * nvar + nv] * g->dV[o];
+          }
+          for (int j1 = j; j1 < j + g->csize[i]; j1++) {
+            long o = k * g->sk + j1 * g->sj + i;
+            for (int nv = 0; nv < nvar; nv++) Uc[o * nvar + nv] = uav[nv] / dVav;
+          }
+        }
+      i++;
+    }
+  } else {
+    if (g->csize[g->beg[1]] == 1 && g->csize[g->end[1]] == 1) return;
+    for (int pole = 0; pole < 2; pole++) {
+      int j = pole ? g->end[1] : g->beg[1];
+      while (j >= g->beg[1] && j <= g->end[1] && g->csize[j] > 1) {
+        for (int i = g->beg[0]; i <= g->end[0]; i++)
+          for (int k = g->beg[2]; k <= g->end[2]; k += g->csize[j]) {
+            dVav = 0.0;
+            for (int nv = 0; nv < nvar; nv++) uav[nv] = 0.0;
+            for (int k1 = k; k1 < k + g->csize[j]; k1++) {
+              long o = k1 * g->sk + j * g->sj + i;
+              dVav += g->dV[o];
+              for (int nv = 0; nv < nvar; nv++) uav[nv] += Uc[o * nvar + nv] * g->dV[o];
+            }
+            for (int k1 = k; k1 < k + g->csize[j]; k1++) {
+              long o = k1 * g->sk + j * g->sj + i;
+              for (int nv = 0; nv < nvar; nv++) Uc[o * nvar + nv] = uav[nv] / dVav;
+            }
+          }
+        j += pole ? -1 : 1;
+      }
+    }
+  }
+}
+
+static double mp5_reconstruct(const double *F, int j) {
+  const double alpha = 4.0, epsm = 1.e-12;
+  double f = 2.0 * F[j - 2] - 13.0 * F[j - 1] + 47.0 * F[j] + 27.0 * F[j + 1] - 3.0 * F[j + 2];
+  f /= 60.0;
+  double fMP = F[j] + MINMOD_LIMITER(F[j + 1] - F[j], alpha * (F[j] - F[j - 1]));
+  if ((f - F[j]) * (f - fMP) <= epsm) return f;
+  double d2m = F[j - 2] + F[j] - 2.0 * F[j - 1];
+  double d2 = F[j - 1] + F[j + 1] - 2.0 * F[j];
+  double d2p = F[j] + F[j + 2] - 2.0 * F[j + 1];
+  double scrh1 = MINMOD_LIMITER(4.0 * d2 - d2p, 4.0 * d2p - d2);
+  double scrh2 = MINMOD_LIMITER(d2, d2p);
+  double dMMp = MINMOD_LIMITER(scrh1, scrh2);
+  scrh1 = MINMOD_LIMITER(4.0 * d2m - d2, 4.0 * d2 - d2m);
+  scrh2 = MINMOD_LIMITER(d2, d2m);
+  double dMMm = MINMOD_LIMITER(scrh1, scrh2);
+  double fUL = F[j] + alpha * (F[j] - F[j - 1]);
+  double fAV = 0.5 * (F[j] + F[j + 1]);
+  double fMD = fAV - 0.5 * dMMp;
+  double fLC = 0.5 * (3.0 * F[j] - F[j - 1]) + 4.0 / 3.0 * dMMm;
+  scrh1 = MINV(F[j], F[j + 1]); scrh1 = MINV(scrh1, fMD);
+  scrh2 = MINV(F[j], fUL); scrh2 = MINV(scrh2, fLC);
+  double fmin = MAXV(scrh1, scrh2);
+  scrh1 = MAXV(F[j], F[j + 1]); scrh1 = MAXV(scrh1, fMD);
+  scrh2 = MAXV(F[j], fUL); scrh2 = MAXV(scrh2, fLC);
+  double fmax = MINV(scrh1, scrh2);
+  return f + MINMOD_LIMITER(fmin - f, fmax - f);             /* Median(f, fmin, fmax) */
+}
+
+/* chunk averages -> states on the reduced grid -> parabola through (vam, va, vap) evaluated at the sub-zone edges */
+static void ring_reconstruct(const gen_cfg *c, const geom_t *g, sweep_t *s, int dir, int chunk_size) {
+  if (c->ring_rec == 1 || chunk_size == 1) return;
+  int nvar = g->nvar, ngh = c->ng;
+  int dbeg = g->beg[dir], dend = g->end[dir], nphi = dend - dbeg + 1;
+  int nchunks = nphi / chunk_size, cbeg = dbeg, cend = dbeg + nchunks - 1;
+  int nmax = g->tot[dir] + 8;
+  double (*va)[NVMAX] = calloc(nmax, sizeof(*va)), (*vap)[NVMAX] = calloc(nmax, sizeof(*vap)), (*vam)[NVMAX] = calloc(nmax, sizeof(*vam));
+  for (int j = dbeg; j <= dend; j += chunk_size) {
+    int ja = (j - dbeg) / chunk_size + dbeg;
+    for (int nv = 0; nv < nvar; nv++) va[ja][nv] = s->v[j][nv];
+  }
+  for (int j = 0; j < cbeg; j++) for (int nv = 0; nv < nvar; nv++) va[j][nv] = va[j + nchunks][nv];
+  for (int j = cend + 1; j <= cend + ngh; j++) for (int nv = 0; nv < nvar; nv++) va[j][nv] = va[j - nchunks][nv];
+  if (c->ring_rec == 2) {
+    for (int j = cbeg - 1; j <= cend + 1; j++)
+      for (int nv = 0; nv < nvar; nv++) {
+        double dvap = va[j + 1][nv] - va[j][nv], dvam = va[j][nv] - va[j - 1][nv];
+        double dva = (dvap * dvam > 0.0 ? 2.0 * dvap * dvam / (dvap + dvam) : 0.0);     /* VANLEER_LIMITER */
+        vap[j][nv] = va[j][nv] + 0.5 * dva;
+        vam[j][nv] = va[j][nv] - 0.5 * dva;
+      }
+  } else {      /* RING_AVERAGE_REC 5 */
+    int nphi_tot = nchunks + 2 * ngh;
+    double *qfwd = calloc(nmax, 8), *qbck = calloc(nmax, 8);
+    for (int nv = 0; nv < nvar; nv++) {
+      for (int j = 0; j < nphi_tot; j++) { qfwd[j] = va[j][nv]; qbck[j] = va[nphi_tot - j - 1][nv]; }
+      for (int j = cbeg - 1; j <= cend; j++) {
+        vap[j][nv] = mp5_reconstruct(qfwd, j);
+        vam[j][nv] = mp5_reconstruct(qbck, cend - (j - cbeg));
+      }
+    }
+    free(qfwd); free(qbck);
+  }
+  for (int j = dbeg; j <= dend; j++) {
+    int ja = (j - dbeg) / chunk_size + dbeg;
+    int k = (j - dbeg) % chunk_size + 1;
+    double xp = k / (double)chunk_size, xm = (k - 1.0) / (double)chunk_size;
+    for (int nv = 0; nv < nvar; nv++) {
+      double A = 3.0 * ((vap[ja][nv] + vam[ja][nv]) - 2.0 * va[ja][nv]);
+      double B = -4.0 * vam[ja][nv] - 2.0 * vap[ja][nv] + 6.0 * va[ja][nv];
+      double Cc = vam[ja][nv];
+      s->vp[j][nv] = A * xp * xp + B * xp + Cc;
+      s->vm[j][nv] = A * xm * xm + B * xm + Cc;
+    }
+  }
+  for (int j = 0; j < dbeg; j++) for (int nv = 0; nv < nvar; nv++) { s->vp[j][nv] = s->vp[j + nphi][nv]; s->vm[j][nv] = s->vm[j + nphi][nv]; }
+  for (int j = dend + 1; j <= dend + ngh; j++) for (int nv = 0; nv < nvar; nv++) { s->vp[j][nv] = s->vp[j - nphi][nv]; s->vm[j][nv] = s->vm[j - nphi][nv]; }
+  free(va); free(vap); free(vam);
+}
+
 /* Time_Stepping/update_stage.c:35-394 + MHD/rhs.c:84-420 + MHD/rhs_source.c:101-470 */
 static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, double *Uc, const uint16_t *flag,
                          double *C_dt, double *dvds, double dt, int stage, double *invDt_hyp, double *maxMach) {
@@ -1332,6 +1510,11 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
         if (c->ppm && c->char_limiting) states_ppm_char(c, g, &s, dir, nbeg - 1, nend + 1);
         else if (c->ppm) states_ppm(c, g, &s, dir, nbeg - 1, nend + 1);
         else states(c, g, &s, dir, nbeg - 1, nend + 1);
+        /* RingAverageReconstruct after States() in the phi sweep, update_stage.c:230-234 */
+        int ring_line = 0;
+        if (c->ring_average > 1 && c->geometry == POLAR && dir == 1) ring_line = g->csize[idx[0]];
+        if (c->ring_average > 1 && c->geometry == SPHERICAL && dir == 2) ring_line = g->csize[idx[1]];
+        if (ring_line > 1) ring_reconstruct(c, g, &s, dir, ring_line);
         riemann(c, g, &s, dir, nbeg - 1, nend, maxMach);
         if (c->body_force & 2) {   /* TotalFlux(): flux[ENG] += flux[RHO] phi_p at the faces (rhs.c:171-179,525,581,621) */
           for (int n = nbeg - 1; n <= nend; n++) {
@@ -1448,6 +1631,8 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
           double *U = Uc + (base + n * st) * nvar;
           for (int nv = 0; nv < nvar; nv++) U[nv] += s.rhs[n][nv];
         }
+        double ring_q = 1.0;        /* update_stage.c:305-311 */
+        if (ring_line > 1) ring_q = 1.0 / ring_line;
         /* GetInverse_dl, set_geometry.c:303-375 */
         for (int n = 0; n < ntot; n++) {
           inv_dl[n] = g->inv_dx[dir][n];
@@ -1457,7 +1642,7 @@ static void update_stage(const gen_cfg *c, const geom_t *g, const double *Vc, do
         if (c->ndim > 1) {
           if (stage == 1)
             for (int n = nbeg; n <= nend; n++)
-              C_dt[base + n * st] += 0.5 * (s.cmax[n - 1] + s.cmax[n]) * inv_dl[n];
+              C_dt[base + n * st] += 0.5 * (s.cmax[n - 1] + s.cmax[n]) * inv_dl[n] * ring_q;
         } else {
           for (int n = nbeg - 1; n <= nend; n++) *invDt_hyp = MAXV(*invDt_hyp, s.cmax[n] * inv_dl[n]);
         }
@@ -1535,6 +1720,23 @@ int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *
   long ntot = g->sv * nvar;
   memset(x->flag, 0, g->sv * sizeof(uint16_t));          /* main.c:258-261 */
   double v[NVMAX];
+  if (c->ring_average > 1) {      /* rk_step.c:115-119: PrimToCons3D, RingAverageCons, ConsToPrim3D before Boundary() */
+    for (int k = g->beg[2]; k <= g->end[2]; k++)
+      for (int j = g->beg[1]; j <= g->end[1]; j++)
+        for (int i = g->beg[0]; i <= g->end[0]; i++) {
+          long o = k * g->sk + j * g->sj + i;
+          for (int nv = 0; nv < nvar; nv++) v[nv] = Vc[nv * g->sv + o];
+          prim_to_cons(c, nvar, v, x->Uc + o * nvar);
+        }
+    ring_average_cons(c, g, x->Uc);
+    for (int k = g->beg[2]; k <= g->end[2]; k++)
+      for (int j = g->beg[1]; j <= g->end[1]; j++)
+        for (int i = g->beg[0]; i <= g->end[0]; i++) {
+          long o = k * g->sk + j * g->sj + i;
+          nfail += cons_to_prim(c, nvar, x->Uc + o * nvar, v, &x->flag[o]);
+          for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = v[nv];
+        }
+  }
   for (int stage = 1; stage <= c->rk; stage++) {
     g_Uc_for_floor = (stage > 1) ? x->Uc : NULL;    /* stage 1 re-derives all of Uc right after */
     boundary(c, g, Vc);
@@ -1562,9 +1764,20 @@ int gen_advance_step(void *p, double *Vc, double dt, double *invDt_hyp, double *
           double *U = x->Uc + o * nvar, *U0 = x->U0 + o * nvar;
           if (stage == 2) for (int nv = 0; nv < nvar; nv++) U[nv] = w0 * U0[nv] + wc * U[nv];
           if (stage == 3) for (int nv = 0; nv < nvar; nv++) U[nv] = (1.0 / 3.0) * (U0[nv] + 2.0 * U[nv]);
+          if (c->ring_average > 1) continue;      /* RingAverageCons comes between the combination and ConsToPrim3D */
           nfail += cons_to_prim(c, nvar, U, v, &x->flag[o]);
           for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = v[nv];
         }
+    if (c->ring_average > 1) {                    /* rk_step.c:167-169,238-240,306-308 */
+      ring_average_cons(c, g, x->Uc);
+      for (int k = g->beg[2]; k <= g->end[2]; k++)
+        for (int j = g->beg[1]; j <= g->end[1]; j++)
+          for (int i = g->beg[0]; i <= g->end[0]; i++) {
+            long o = k * g->sk + j * g->sj + i;
+            nfail += cons_to_prim(c, nvar, x->Uc + o * nvar, v, &x->flag[o]);
+            for (int nv = 0; nv < nvar; nv++) Vc[nv * g->sv + o] = v[nv];
+          }
+    }
   }
   return nfail;
 }

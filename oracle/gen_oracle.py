@@ -10,7 +10,7 @@ import oracle as _o
 from pluto_grid import make_grid
 
 GEOMETRY = dict(CARTESIAN=1, CYLINDRICAL=2, POLAR=3, SPHERICAL=4)
-BCS = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8, neighbour=100)
+BCS = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8, polaraxis=9, neighbour=100)
 
 
 class GenCfg(C.Structure):
@@ -29,7 +29,8 @@ class GenCfg(C.Structure):
                 ("cooling", C.c_int), ("cool_tab", C.c_void_p * 8), ("lx", C.c_double), ("tx", C.c_double),
                 ("mpoints", C.c_int), ("t_fit", C.c_void_p), ("m_fit", C.c_void_p),
                 ("iso", C.c_int), ("iso_cs", C.c_double), ("flatten_oned", C.c_int),
-                ("ppm", C.c_int), ("uniform", C.c_int * 3), ("bf_phi", C.c_void_p * 4)]
+                ("ppm", C.c_int), ("uniform", C.c_int * 3), ("bf_phi", C.c_void_p * 4),
+                ("ring_average", C.c_int), ("ring_rec", C.c_int)]
 
 
 _bound = False
@@ -62,7 +63,7 @@ class GenOracle:
                  time_stepping="RK2", solver="hllc", limiter="DEFAULT", bcs=("outflow",) * 6, ntracer=0,
                  nghost=2, small_density=1e-12, small_pressure=1e-12, body_force=0, char_limiting=False,
                  shock_flattening=False, entropy_switch=False, ldw=None, eos="IDEAL",
-                 iso_sound_speed=1.0, **_):
+                 iso_sound_speed=1.0, ring_average=0, ring_average_rec=None, **_):
         assert reconstruction in ("LINEAR", "PARABOLIC")
         c = GenCfg()
         c.ndim = dimensions
@@ -96,6 +97,8 @@ class GenOracle:
         c.body_force = body_force
         c.iso = int(eos == "ISOTHERMAL")     # NFLX = 4: (rho, v1, v2, v3), tracers from index 4
         c.iso_cs = float(iso_sound_speed)
+        c.ring_average = int(ring_average)     # RING_AVERAGE (pluto.h:479-489): REC defaults to 5 when on
+        c.ring_rec = int(ring_average_rec) if ring_average_rec else (5 if c.ring_average > 1 else 1)
         assert not (c.iso and c.entropy), "ENTROPY_SWITCH needs an energy equation"
         self.c = c
         self.dimensions = dimensions

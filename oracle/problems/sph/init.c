@@ -18,6 +18,12 @@ void Init (double *v, double x1, double x2, double x3)
   v[VX2] = 0.10*cos(2.0*r)*sin(2.0*th);
   v[VX3] = 0.7*sqrt(gm/r)*sin(th);
   v[PRS] = 0.05*pow(r, -2.5) + g_inputParam[PBLOB]*blob;
+#ifdef PHI_PERTURB     /* off in the configurations that made the earlier fixtures: a non-axisymmetric state for RING_AVERAGE */
+  v[RHO] *= 1.0 + 0.25*sin(x3)*sin(th) + 0.1*cos(3.0*x3)*sin(th)*sin(th);
+  v[VX1] += 0.05*cos(2.0*x3)*sin(th);
+  v[VX3] *= 1.0 + 0.1*cos(x3);
+  v[PRS] *= 1.0 + 0.2*cos(x3 - 0.7)*sin(th);
+#endif
 #if NTRACER > 0
   v[TRC] = (blob > 0.1 ? 1.0 : 0.0);
 #endif

@@ -17,7 +17,7 @@ EULER, RK2, RK3 = 1, 2, 3
 TVDLF, HLL, HLLC = 1, 2, 3
 LIMITERS = dict(DEFAULT=0, FLAT_LIM=1, MINMOD_LIM=2, VANLEER_LIM=3, MC_LIM=4, VANALBADA_LIM=5,
                 OSPRE_LIM=6, UMIST_LIM=7)
-BC = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8,
+BC = dict(outflow=1, reflective=2, axisymmetric=3, eqtsymmetric=4, periodic=5, userdef=8, polaraxis=9,
           neighbour=100)
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ENAN, ENOTSUP = 0, -1, -2, -3, -4, -5, -6
 
@@ -30,7 +30,7 @@ class Config(C.Structure):
                 ("small_pressure", C.c_double), ("xbeg", C.c_double * 3),
                 ("xend", C.c_double * 3), ("device", C.c_int), ("body_force", C.c_int),
                 ("char_limiting", C.c_int), ("shock_flattening", C.c_int), ("entropy_switch", C.c_int),
-                ("eos", C.c_int), ("reserved", C.c_int * 2), ("iso_sound_speed", C.c_double)]
+                ("eos", C.c_int), ("ring_average", C.c_int), ("ring_average_rec", C.c_int), ("iso_sound_speed", C.c_double)]
 
 
 class LdwConfig(C.Structure):

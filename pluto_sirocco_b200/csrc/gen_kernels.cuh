@@ -57,6 +57,10 @@ struct GenDev {
   // RECONSTRUCTION PARABOLIC (PPM_ORDER 4): interface weights [tot][4] and h+ / h- per direction (States/ppm_coeffs.c)
   int ppm;
   const double *pw[3], *php[3], *phm[3];
+  // RING_AVERAGE (Src/ring_average.c): chunk size at the axis (> 1: on), RING_AVERAGE_REC 1 / 2 / 5 and
+  // grid->ring_av_csize[] per i (POLAR) or j (SPHERICAL)
+  int ring_average, ring_rec;
+  const int *csize;
   // 1-D grid arrays per direction (np_tot entries): grid->x, xr, dx, inv_dx and PLM_Coeffs
   const double *x[3], *xr[3], *dx[3], *inv_dx[3];
   const double *cp[3], *cm[3], *wp[3], *wm[3], *dp[3], *dm[3];
@@ -511,6 +515,80 @@ PB_D void gen_zone_states(const GenDev &g, const double *__restrict__ V, const u
   gen_flatten_oned<NV>(g, V, dir, n, st, o, v, vpo, vmo);
 }
 
+// ---- RING_AVERAGE (Src/ring_average.c): reconstruction on the reduced grid; RingAverageCons is gen_ring below ----
+// chunk size of the ring zone (i, j) belongs to; 1 = not averaged
+PB_D int gen_ring_of(const GenDev &g, int i, int j) {
+  if (g.ring_average <= 1) return 1;
+  const int cs = __ldg(g.csize + (g.geometry == GEO_POLAR ? i : j));
+  return cs > 1 ? cs : 1;
+}
+PB_D int gen_ring_dir(const GenDev &g) { return g.geometry == GEO_POLAR ? 1 : 2; }     // phi: x2 (POLAR), x3 (SPHERICAL)
+
+// Monotonicity-preserving reconstruction of Suresh & Huynh as MP5_Reconstruct() has it (Src/reconstruct.c:38-93,
+// MP5_ALPHA 4, Median :296-304): right-edge value of the middle one of five zone averages
+PB_D double gen_mp5(double fm2, double fm1, double f0, double fp1, double fp2) {
+  const double alpha = 4.0, epsm = 1.e-12;
+  double f = 2.0 * fm2 - 13.0 * fm1 + 47.0 * f0 + 27.0 * fp1 - 3.0 * fp2;
+  f /= 60.0;
+  const double fMP = f0 + gen_minmod(fp1 - f0, alpha * (f0 - fm1));
+  if ((f - f0) * (f - fMP) <= epsm) return f;
+  const double d2m = fm2 + f0 - 2.0 * fm1, d2 = fm1 + fp1 - 2.0 * f0, d2p = f0 + fp2 - 2.0 * fp1;
+  double s1 = gen_minmod(4.0 * d2 - d2p, 4.0 * d2p - d2), s2 = gen_minmod(d2, d2p);
+  const double dMMp = gen_minmod(s1, s2);
+  s1 = gen_minmod(4.0 * d2m - d2, 4.0 * d2 - d2m); s2 = gen_minmod(d2, d2m);
+  const double dMMm = gen_minmod(s1, s2);
+  const double fUL = f0 + alpha * (f0 - fm1), fAV = 0.5 * (f0 + fp1);
+  const double fMD = fAV - 0.5 * dMMp, fLC = 0.5 * (3.0 * f0 - fm1) + 4.0 / 3.0 * dMMm;
+  s1 = fmin(f0, fp1); s1 = fmin(s1, fMD);
+  s2 = fmin(f0, fUL); s2 = fmin(s2, fLC);
+  const double lo = fmax(s1, s2);
+  s1 = fmax(f0, fp1); s1 = fmax(s1, fMD);
+  s2 = fmax(f0, fUL); s2 = fmax(s2, fLC);
+  const double hi = fmin(s1, s2);
+  return f + gen_minmod(lo - f, hi - f);
+}
+
+// RingAverageReconstruct() (ring_average.c:172-400) for zone n of a phi line whose ring has chunk size cs > 1: the chunk
+// averages (periodic in phi) are reconstructed on the reduced grid (RING_AVERAGE_REC 2: van Leer, 5: MP5) and the parabola
+// through (vam, va, vap) is evaluated at the edges of the zone inside its chunk.  Ghost zones take the periodic image.
+template <int NV>
+PB_D void gen_ring_states(const GenDev &g, const double *__restrict__ V, int dir, int n, long st, long o, int cs,
+                          double (&v)[NV], double (&vpo)[NV], double (&vmo)[NV]) {
+  const Dev &d = g.d;
+  const int dbeg = d.beg[dir], dend = d.end[dir], nphi = dend - dbeg + 1, nch = nphi / cs;
+  int jw = n;
+  if (jw < dbeg) jw += nphi; else if (jw > dend) jw -= nphi;
+  const int ja = (jw - dbeg) / cs, kk = (jw - dbeg) % cs + 1;
+  const long base = o - (long)n * st;
+  const double xp = kk / (double)cs, xm = (kk - 1.0) / (double)cs;
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    const double *q = V + nv * d.sv + base;
+    v[nv] = q[(long)n * st];
+    auto VA = [&](int m) {
+      int c = (ja + m) % nch;
+      if (c < 0) c += nch;
+      return q[(long)(dbeg + c * cs) * st];
+    };
+    const double va = VA(0);
+    double vap, vam;
+    if (g.ring_rec == 2) {
+      const double dvap = VA(1) - va, dvam = va - VA(-1);
+      const double dva = dvap * dvam > 0.0 ? 2.0 * dvap * dvam / (dvap + dvam) : 0.0;     // VANLEER_LIMITER
+      vap = va + 0.5 * dva;
+      vam = va - 0.5 * dva;
+    } else {
+      const double m2 = VA(-2), m1 = VA(-1), p1 = VA(1), p2 = VA(2);
+      vap = gen_mp5(m2, m1, va, p1, p2);
+      vam = gen_mp5(p2, p1, va, m1, m2);
+    }
+    const double A = 3.0 * ((vap + vam) - 2.0 * va);
+    const double B = -4.0 * vam - 2.0 * vap + 6.0 * va;
+    vpo[nv] = A * xp * xp + B * xp + vam;
+    vmo[nv] = A * xm * xm + B * xm + vam;
+  }
+}
+
 template <int NV>
 static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   int i, j, k;
@@ -521,7 +599,9 @@ static __global__ void gen_states(GenDev g, GenArgs a, GenBox b) {
   const long o = (long)k * d.sk + (long)j * d.sj + i;
   const int n = dir == 0 ? i : (dir == 1 ? j : k);
   double v[NV], vp[NV], vm[NV];
-  if (g.ppm) gen_zone_states_ppm<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
+  const int ring = (g.ring_average > 1 && g.ring_rec != 1 && dir == gen_ring_dir(g)) ? gen_ring_of(g, i, j) : 1;
+  if (ring > 1) gen_ring_states<NV>(g, a.V, dir, n, st, o, ring, v, vp, vm);      // update_stage.c:230-234
+  else if (g.ppm) gen_zone_states_ppm<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
   else gen_zone_states<NV>(g, a.V, a.flag, dir, n, st, o, v, vp, vm);
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
@@ -1312,7 +1392,9 @@ PB_D void gen_zone_rhs(const GenDev &g, const GenArgs &a, int dir, int i, int j,
     if ((g.geometry == GEO_SPHERICAL || g.geometry == GEO_POLAR) && dir == 1) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i));
     if (g.geometry == GEO_SPHERICAL && dir == 2) inv_dl = inv_dl * (1.0 / __ldg(g.x[0] + i)) / __ldg(g.sin2 + j);
     if (d.ndim > 1) {
-      cdt_c = 0.5 * (cm_ + cp_) * inv_dl;
+      double q = 1.0;                                   // update_stage.c:305-311
+      if (g.ring_average > 1 && dir == gen_ring_dir(g)) q = 1.0 / gen_ring_of(g, i, j);
+      cdt_c = 0.5 * (cm_ + cp_) * inv_dl * q;
     } else {
       // 1-D: every stage, faces IBEG-1..IEND with inv_dl of the face's left zone
       inv_max = cp_ * inv_dl;
@@ -1462,6 +1544,104 @@ static __global__ void __launch_bounds__(S * L, MB) gen_sweep(GenDev g, GenArgs 
   }
 }
 
+// ---- RING_AVERAGE, Src/ring_average.c ---------------------------------------------------------
+// ConsToPrim (HD/mappers.c:98-290, entropy aware) of one zone; returns true when a floor was applied
+template <int NV>
+PB_D bool gen_c2p(const GenDev &g, double (&u)[NV], double (&v)[NV], unsigned short fl) {
+  const Gas &gs = g.d.gas;
+  constexpr int P = pidx<NV>();
+  const double m2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+  bool bad = false;
+  if (u[0] < 0.0) { u[0] = gs.small_dn; bad = true; }
+  const double rho = u[0], tau = 1.0 / u[0];
+  v[0] = rho; v[1] = u[1] * tau; v[2] = u[2] * tau; v[3] = u[3] * tau;
+  const double kin = 0.5 * m2 / u[0];
+  if (!g.iso) {
+    if (u[P] < 0.0) { u[P] = gs.small_pr / gs.gmm1 + kin; bad = true; }
+    if (g.entropy && (fl & GF_ENTROPY)) {
+      const double rhog1 = pow(rho, gs.gmm1);
+      v[P] = u[NV - 1] * rhog1;
+      if (v[P] < 0.0) { v[P] = gs.small_pr; bad = true; }
+      u[P] = v[P] / gs.gmm1 + kin;
+    } else {
+      v[P] = gs.gmm1 * (u[P] - kin);
+      if (v[P] < 0.0) { v[P] = gs.small_pr; u[P] = v[P] / gs.gmm1 + kin; bad = true; }
+      if (g.entropy) u[NV - 1] = v[P] / pow(rho, gs.gmm1);
+    }
+  }
+#pragma unroll
+  for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) v[nv] = u[nv] * tau;
+  return bad;
+}
+
+// RingAverageCons() + ConsToPrim3D.  from_prim = 1: the round trip at the start of a step (rk_step.c:115-119:
+// PrimToCons3D, RingAverageCons, ConsToPrim3D over the whole domain, averaged or not); 0: after a stage, on the
+// rings only (gen_finish has left the combined U of those zones and converted all the others).
+// One thread per zone; the first zone of a chunk sums its chunk in the reference's order and writes all its zones.
+template <int NV>
+static __global__ void gen_ring(GenDev g, GenArgs a, GenBox b, int from_prim) {
+  int i, j, k;
+  const Dev &d = g.d;
+  int nfail = 0, nan = 0;
+  if (gen_zone(b.lo, b.hi, i, j, k)) {
+    const long nz = d.sv;
+    const int cs = gen_ring_of(g, i, j);
+    const int pd = gen_ring_dir(g);
+    const int np = pd == 1 ? j : k;
+    const long stp = pd == 1 ? d.sj : d.sk;
+    const long o = (long)k * d.sk + (long)j * d.sj + i;
+    const bool first = (np - d.beg[pd]) % cs == 0;
+    if ((cs > 1 || from_prim) && first) {
+      double uav[NV], dVav = 0.0;
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) uav[nv] = 0.0;
+      for (int m = 0; m < cs; m++) {
+        const long om = o + m * stp;
+        double u[NV];
+        if (from_prim) {
+          double v[NV];
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) v[nv] = a.V[nv * nz + om];
+          const double rho = v[iRHO];
+          u[0] = rho; u[1] = rho * v[1]; u[2] = rho * v[2]; u[3] = rho * v[3];
+          const double k2 = v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+          if (!g.iso) u[pidx<NV>()] = 0.5 * rho * k2 + v[pidx<NV>()] / d.gas.gmm1;
+#pragma unroll
+          for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) u[nv] = rho * v[nv];
+        } else {
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) u[nv] = a.U[nv * nz + om];
+        }
+        if (cs == 1) {
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) uav[nv] = u[nv];
+        } else {
+          const double dv = __ldg(g.dV + om);
+          dVav += dv;
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) uav[nv] += u[nv] * dv;
+        }
+      }
+      if (cs > 1) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) uav[nv] = uav[nv] / dVav;
+      }
+      for (int m = 0; m < cs; m++) {
+        const long om = o + m * stp;
+        double u[NV], v[NV];
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) u[nv] = uav[nv];
+        unsigned short fl = a.flag[om];
+        if (gen_c2p<NV>(g, u, v, fl)) { fl |= GF_C2P_FAIL; nfail = 1; a.flag[om] = fl; }
+        nan |= !(v[1] == v[1]) || !(v[0] == v[0]) || (!g.iso && !(v[pidx<NV>()] == v[pidx<NV>()]));
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) { a.U[nv * nz + om] = u[nv]; a.V[nv * nz + om] = v[nv]; }
+      }
+    }
+  }
+  block_reduce(0.0, 0.0, nfail, nan, false, a.red);
+}
+
 // ---- RK combination + ConsToPrim3D (entropy aware) + dt reduction ---------------------------
 template <int NV>
 static __global__ void gen_finish(GenDev g, GenArgs a, GenBox b) {
@@ -1482,37 +1662,19 @@ static __global__ void gen_finish(GenDev g, GenArgs a, GenBox b) {
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) u[nv] = (1.0 / 3.0) * (a.U0[nv * nz + o] + 2.0 * u[nv]);
     }
-    // ConsToPrim, mappers.c:98-290
-    unsigned short fl = a.flag[o];
-    const Gas &gs = d.gas;
-    const double m2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
-    bool bad = false;
-    if (u[0] < 0.0) { u[0] = gs.small_dn; bad = true; }
-    const double rho = u[0], tau = 1.0 / u[0];
-    v[0] = rho; v[1] = u[1] * tau; v[2] = u[2] * tau; v[3] = u[3] * tau;
-    const double kin = 0.5 * m2 / u[0];
-    constexpr int P = pidx<NV>();
-    if (g.iso) {
-      // mappers.c with EOS ISOTHERMAL: no energy, no pressure
-    } else {
-    if (u[P] < 0.0) { u[P] = gs.small_pr / gs.gmm1 + kin; bad = true; }
-    if (g.entropy && (fl & GF_ENTROPY)) {
-      const double rhog1 = pow(rho, gs.gmm1);
-      v[P] = u[NV - 1] * rhog1;
-      if (v[P] < 0.0) { v[P] = gs.small_pr; bad = true; }
-      u[P] = v[P] / gs.gmm1 + kin;
-    } else {
-      v[P] = gs.gmm1 * (u[P] - kin);
-      if (v[P] < 0.0) { v[P] = gs.small_pr; u[P] = v[P] / gs.gmm1 + kin; bad = true; }
-      if (g.entropy) u[NV - 1] = v[P] / pow(rho, gs.gmm1);
-    }
-    }
+    if (gen_ring_of(g, i, j) > 1) {
+      // RING_AVERAGE: RingAverageCons comes between the combination and ConsToPrim3D (rk_step.c:167-169,238-240,
+      // 306-308): gen_ring converts these zones
 #pragma unroll
-    for (int nv = 4; nv < NV; nv++) if (nv >= gen_nflx(g)) v[nv] = u[nv] * tau;
-    if (bad) { fl |= GF_C2P_FAIL; nfail = 1; a.flag[o] = fl; }
-    nan = !(v[1] == v[1]) || !(v[0] == v[0]) || (!g.iso && !(v[P] == v[P]));
+      for (int nv = 0; nv < NV; nv++) a.U[nv * nz + o] = u[nv];
+    } else {
+      // ConsToPrim, mappers.c:98-290
+      unsigned short fl = a.flag[o];
+      if (gen_c2p<NV>(g, u, v, fl)) { fl |= GF_C2P_FAIL; nfail = 1; a.flag[o] = fl; }
+      nan = !(v[1] == v[1]) || !(v[0] == v[0]) || (!g.iso && !(v[pidx<NV>()] == v[pidx<NV>()]));
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) { a.U[nv * nz + o] = u[nv]; a.V[nv * nz + o] = v[nv]; }
+      for (int nv = 0; nv < NV; nv++) { a.U[nv * nz + o] = u[nv]; a.V[nv * nz + o] = v[nv]; }
+    }
     if (a.stage == 1 && d.ndim > 1) cmaxv = a.cdt[o];
   }
   block_reduce(cmaxv, 0.0, nfail, nan, a.stage == 1 && g.d.ndim > 1, a.red);

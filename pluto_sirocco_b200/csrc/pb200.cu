@@ -72,6 +72,29 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   if (cfg->eos != PB200_EOS_IDEAL && !iso) return fail(PB200_EINVAL, "eos must be IDEAL or ISOTHERMAL");
   if (iso && !(cfg->iso_sound_speed > 0.0)) return fail(PB200_EINVAL, "EOS ISOTHERMAL needs iso_sound_speed > 0 (g_isoSoundSpeed)");
   if (iso && cfg->entropy_switch) return fail(PB200_EINVAL, "ENTROPY_SWITCH needs an energy equation (EOS IDEAL)");
+  const int ring = cfg->ring_average > 1 ? cfg->ring_average : 0;
+  const int ring_rec = ring ? (cfg->ring_average_rec ? cfg->ring_average_rec : 5) : 1;     // pluto.h:483-489
+  if (ring) {     // RingAverageSize(), ring_average.c:620-735, and what RingAverageReconstruct() relies on
+    const int pd = cfg->geometry == PB200_POLAR ? 1 : 2;
+    if (cfg->geometry != PB200_POLAR && cfg->geometry != PB200_SPHERICAL)
+      return fail(PB200_EINVAL, "RING_AVERAGE cannot be used in this geometry (ring_average.c:50)");
+    if (cfg->dimensions <= pd) return fail(PB200_EINVAL, "RING_AVERAGE needs the phi direction");
+    if ((ring & (ring - 1)) != 0 || cfg->nx[pd] % ring != 0)
+      return fail(PB200_EINVAL, "RING_AVERAGE must be a power of two that divides the number of phi zones");
+    if (cfg->nx[pd] / ring < cfg->nghost)
+      return fail(PB200_ENOTSUP, "RING_AVERAGE: fewer chunks on the innermost ring than ghost zones");
+    if (cfg->bc[2 * pd] != PB200_BC_PERIODIC || cfg->bc[2 * pd + 1] != PB200_BC_PERIODIC)
+      return fail(PB200_EINVAL, "RING_AVERAGE needs a periodic phi direction");
+    if (ring_rec != 1 && ring_rec != 2 && ring_rec != 5) return fail(PB200_EINVAL, "RING_AVERAGE_REC must be 1, 2 or 5");
+    if (cfg->entropy_switch) return fail(PB200_ENOTSUP, "RING_AVERAGE with ENTROPY_SWITCH is not built");
+  }
+  for (int s = 0; s < 2 * cfg->dimensions; s++)
+    if (cfg->bc[s] == PB200_BC_POLARAXIS) {      // Boundary(), boundary.c:344-364
+      const bool ok = (cfg->geometry == PB200_POLAR && s == 0) || (cfg->geometry == PB200_SPHERICAL && (s == 2 || s == 3));
+      if (!ok) return fail(PB200_EINVAL, "polaraxis: X1-beg in POLAR, an X2 boundary in SPHERICAL geometry");
+      const int pd = cfg->geometry == PB200_POLAR ? 1 : 2;
+      if (cfg->dimensions <= pd || cfg->nx[pd] % 2) return fail(PB200_EINVAL, "polaraxis needs an even number of phi zones");
+    }
   const bool gen = cfg->geometry != PB200_CARTESIAN || cfg->char_limiting || cfg->shock_flattening ||
                    cfg->entropy_switch || iso || cfg->solver >= PB200_ROE;
   if (gen && cfg->reconstruction == PB200_FLAT)
@@ -87,6 +110,7 @@ extern "C" int pb200_create(const pb200_config *cfg, pb200_ctx **out) {
   int need = cfg->reconstruction == PB200_PARABOLIC ? 3 : 2;
   if (cfg->shock_flattening < 0 || cfg->shock_flattening > 2) return fail(PB200_EINVAL, "shock_flattening: 0 NO, 1 MULTID, 2 ONED");
   if (cfg->shock_flattening == 2) need = 4;         // GetNghost(), Src/get_nghost.c:42-57
+  if (ring && ring_rec > 2 && need < 3) need = 3;   // get_nghost.c:40
   if (cfg->nghost < need) return fail(PB200_EINVAL, "nghost too small for the reconstruction stencil");
   for (int d = 0; d < cfg->dimensions; d++)
     if (cfg->nx[d] < cfg->nghost) return fail(PB200_EINVAL, "nx < nghost in an active dimension");
@@ -397,6 +421,8 @@ static int boundary_on(pb200_ctx *c, double *V, unsigned sides = 0x3f, int k0 = 
     b.sign[1 + side / 2] = -1.0;  // FlipSign(): normal velocity (Src/boundary.c:503)
     if (type == PB200_BC_AXISYMMETRIC && c->cfg.geometry != PB200_CARTESIAN)
       b.sign[c->cfg.geometry == PB200_POLAR ? 2 : 3] = -1.0;  // iVPHI: VX2 (POLAR), VX3 otherwise (boundary.c:548, pluto.h)
+    b.pdir = c->cfg.geometry == PB200_POLAR ? 1 : 2;
+    if (type == PB200_BC_POLARAXIS) b.sign[1 + b.pdir] = -1.0;  // PolarAxisBoundary(): v_normal and v_phi change sign
     int ext[3] = {D.tot[0], D.tot[1], D.tot[2]};
     ext[side / 2] = b.nghost;
     if (side < 4) ext[2] = k1 - k0;
@@ -620,6 +646,10 @@ extern "C" int pb200_stage_boundary(pb200_ctx *c, int stage) {
   SweepArgs a;
   int rc = stage_args(c, stage, a);
   if (rc) return rc;
+  if (stage == 1) {                               // RING_AVERAGE: rk_step.c:115-119, ahead of the first Boundary()
+    rc = pb200_gen_ring_start(c);
+    if (rc) return rc;
+  }
   c->cur_stage = stage;
   rc = boundary_on(c, c->V[c->stage_in[stage]]);  // Boundary(d, 0, grid), rk_step.c:121,213,285
   c->cur_stage = 0;

@@ -221,6 +221,27 @@ int pb200_gen_setup(pb200_ctx *c) {
     ok &= (G.A[d] = upload(c, A[d])) != nullptr;
     ok &= (G.dx_dl[d] = upload(c, dxdl[d])) != nullptr;
   }
+  G.ring_average = c->cfg.ring_average > 1 ? c->cfg.ring_average : 0;
+  G.ring_rec = G.ring_average ? (c->cfg.ring_average_rec ? c->cfg.ring_average_rec : 5) : 1;
+  {   // RingAverageSize(), ring_average.c:620-735: chunk sizes halve ring by ring away from the axis
+    const int rd = geo == PB200_POLAR ? 0 : 1;
+    std::vector<int> cs(D.tot[rd], 0);
+    if (G.ring_average) {
+      int q = G.ring_average;
+      for (int n = D.beg[rd]; n <= D.end[rd]; n++) {
+        cs[n] = c->cfg.bc[2 * rd] == PB200_BC_POLARAXIS ? q : 1;
+        if (q > 1) q >>= 1;
+      }
+      if (geo == PB200_SPHERICAL) {
+        q = G.ring_average;
+        for (int n = D.end[1]; n >= D.beg[1]; n--) {
+          cs[n] = std::max(cs[n], c->cfg.bc[3] == PB200_BC_POLARAXIS ? q : 1);
+          if (q > 1) q >>= 1;
+        }
+      }
+    }
+    ok &= (G.csize = upload(c, cs)) != nullptr;
+  }
   G.ppm = c->cfg.reconstruction == PB200_PARABOLIC;
   for (int d = 0; d < 3 && G.ppm; d++) {
     std::vector<double> w, hp, hm;
@@ -626,7 +647,8 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   // PB200_GEN_FUSED=0: the one-kernel-per-reference-stage form (gen_states -> gen_riemann -> gen_rhs through
   // the VP / VM / F arrays); default: one fused kernel per direction (gen_sweep)
   static const bool fused_env = !(getenv("PB200_GEN_FUSED") && atoi(getenv("PB200_GEN_FUSED")) == 0);
-  const bool fused = fused_env && !G.ppm;      // PARABOLIC: gen_states carries the PPM states, gen_sweep does not
+  // PARABOLIC and RING_AVERAGE: gen_states carries the PPM / ring states, gen_sweep does not
+  const bool fused = fused_env && !G.ppm && !G.ring_average;
   const int T = 128;
   auto blocks = [&](const GenBox &b) {
     long n = (long)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
@@ -696,6 +718,37 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
   }
   gen_finish<NV><<<blocks(dom), T, 0, st>>>(G, a, dom);
   c->launches++;
+  if (G.ring_average) {        // RingAverageCons + ConsToPrim3D of the averaged rings (rk_step.c:167-169,238-240,306-308)
+    gen_ring<NV><<<blocks(dom), T, 0, st>>>(G, a, dom, 0);
+    c->launches++;
+  }
+}
+
+// rk_step.c:115-119: PrimToCons3D, RingAverageCons, ConsToPrim3D before the first Boundary() of a step
+template <int NV>
+static void gen_ring_start_nv(pb200_ctx *c) {
+  GenDev G = *c->gdev;
+  G.d = c->dev;
+  GenArgs a;
+  memset(&a, 0, sizeof(a));
+  a.V = c->V[c->cur];
+  a.U = c->gU; a.flag = c->gflag; a.red = c->d_red;
+  GenBox dom;
+  for (int d = 0; d < 3; d++) { dom.lo[d] = c->dev.beg[d]; dom.hi[d] = c->dev.end[d]; }
+  const long n = (long)(dom.hi[0] - dom.lo[0] + 1) * (dom.hi[1] - dom.lo[1] + 1) * (dom.hi[2] - dom.lo[2] + 1);
+  gen_ring<NV><<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(G, a, dom, 1);
+  c->launches++;
+}
+int pb200_gen_ring_start(pb200_ctx *c) {
+  if (!c->gen || !c->gen_ready || c->cfg.ring_average <= 1) return PB200_OK;
+  switch (c->nvar) {
+    case 4: gen_ring_start_nv<4>(c); break;
+    case 5: gen_ring_start_nv<5>(c); break;
+    case 6: gen_ring_start_nv<6>(c); break;
+    case 7: gen_ring_start_nv<7>(c); break;
+    default: return PB200_ENOTSUP;
+  }
+  return cudaGetLastError() == cudaSuccess ? PB200_OK : pb200_fail(PB200_ECUDA, "ring average: kernel launch failed");
 }
 
 // Host-boundary mode, stages > 1: user code that changes interior zones inside Boundary() converts them

@@ -84,6 +84,7 @@ void pb200_gen_release(pb200_ctx *c);
 int  pb200_gen_stage(pb200_ctx *c, int stage);
 int  pb200_gen_patch_u(pb200_ctx *c, long n, const long *zone, const double *u);
 bool pb200_grid_is_uniform(const pb200_ctx *c, int dir);
+int  pb200_gen_ring_start(pb200_ctx *c);
 int  pb200_gen_internal_boundary(pb200_ctx *c, double *V);   // UserDefBoundary(side == 0)
 int  pb200_gen_userdef_side(pb200_ctx *c, double *V, int side);
 int  pb200_gen_entropy(pb200_ctx *c, double *V);               // ComputeEntropy at the end of Boundary()

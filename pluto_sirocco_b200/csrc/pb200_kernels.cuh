@@ -337,7 +337,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq) {
 }
 
 enum BcType { BC_NONE = 0, BC_OUTFLOW = 1, BC_REFLECTIVE = 2, BC_AXISYMMETRIC = 3,
-              BC_EQTSYMMETRIC = 4, BC_PERIODIC = 5, BC_USERDEF = 8, BC_NEIGHBOUR = 100 };
+              BC_EQTSYMMETRIC = 4, BC_PERIODIC = 5, BC_USERDEF = 8, BC_POLARAXIS = 9, BC_NEIGHBOUR = 100 };
 
 // BXT: threads per block.  The fused x1+x2 kernel loses 2*XH threads per block to the x1 halo, so
 // on a 512-wide grid 128-thread blocks need 5 blocks (20 warps) per row where 192-thread blocks
@@ -697,6 +697,7 @@ struct BcArgs {
   int nghost;
   double sign[16];
   int k0, k1;     // restrict the fill of an x1 / x2 side to the x3 planes [k0, k1) (absolute indices)
+  int pdir;       // BC_POLARAXIS: the phi direction (x2 POLAR, x3 SPHERICAL), PolarAxisBoundary() boundary.c:770-840
 };
 
 static __global__ void bc_fill(Dev d, BcArgs b) {
@@ -721,10 +722,15 @@ static __global__ void bc_fill(Dev d, BcArgs b) {
   if (b.type == BC_OUTFLOW) src = hi ? ne : nb;
   else if (b.type == BC_PERIODIC) src = hi ? n - nx : n + nx;
   else src = hi ? 2 * ne + 1 - n : 2 * nb - 1 - n;
-  const bool flip = (b.type == BC_REFLECTIVE || b.type == BC_AXISYMMETRIC || b.type == BC_EQTSYMMETRIC);
+  const bool flip = (b.type == BC_REFLECTIVE || b.type == BC_AXISYMMETRIC || b.type == BC_EQTSYMMETRIC || b.type == BC_POLARAXIS);
   c[dir] = n;
   long dst_off = (long)c[2] * d.sk + (long)c[1] * d.sj + c[0];
   c[dir] = src;
+  if (b.type == BC_POLARAXIS) {      // the mirror zone lies half a turn away
+    const int nphi = d.end[b.pdir] - d.beg[b.pdir] + 1;
+    c[b.pdir] += nphi / 2;
+    if (c[b.pdir] > d.end[b.pdir]) c[b.pdir] -= nphi;
+  }
   long src_off = (long)c[2] * d.sk + (long)c[1] * d.sj + c[0];
   for (int nv = 0; nv < b.nvar; nv++) {
     double q = b.V[nv * d.sv + src_off];

@@ -351,6 +351,10 @@ static void shim_fill_config(pb200_config *pcfg, Data *d, Grid *grid) {
 #if CHAR_LIMITING == YES
   cfg.char_limiting = 1;
 #endif
+#if RING_AVERAGE > 1
+  cfg.ring_average = RING_AVERAGE;
+  cfg.ring_average_rec = RING_AVERAGE_REC;
+#endif
 #if SHOCK_FLATTENING == MULTID
   cfg.shock_flattening = 1;
 #elif SHOCK_FLATTENING == ONED

@@ -285,7 +285,7 @@ class Hydro:
                  bcs=("outflow",) * 6, ntracer=0, nghost=None, device=0,
                  small_density=1e-12, small_pressure=1e-12, dx=None, body_force=0,
                  geometry="CARTESIAN", grid_arrays=None, grid_uniform=None, char_limiting=False, shock_flattening=False,
-                 entropy_switch=False, eos="IDEAL", iso_sound_speed=0.0):
+                 entropy_switch=False, eos="IDEAL", iso_sound_speed=0.0, ring_average=0, ring_average_rec=None):
         lib = L.load()
         cfg = L.Config()
         lib.pb200_config_default(C.byref(cfg))
@@ -317,6 +317,8 @@ class Hydro:
         cfg.entropy_switch = {False: 0, None: 0, True: 2, "NO": 0, "SELECTIVE": 1, "ALWAYS": 2}[entropy_switch]
         cfg.eos = {"IDEAL": 0, "ISOTHERMAL": 1}[eos]
         cfg.iso_sound_speed = float(iso_sound_speed)
+        cfg.ring_average = int(ring_average)                    # RING_AVERAGE, RING_AVERAGE_REC (pluto.h:479-489)
+        cfg.ring_average_rec = int(ring_average_rec or 0)
         self.cfg = cfg
         self._lib = lib
         h = C.c_void_p()

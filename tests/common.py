@@ -7,7 +7,7 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 _GEN_PREFIXES = ("sph", "ldw", "cart")     # general-grid fixtures (GenOracle / the gen path of the library)
 # cylindrical / polar / Roe / two-shock / ONED / general-grid PPM fixtures pin the ORACLE only (the CUDA path refuses
 # these options); the iso* fixtures (EOS ISOTHERMAL) run on the CUDA path too: ISO_CASES
-_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot", "ausm")
+_CURV_PREFIXES = ("cyl", "pol", "iso", "roe", "twoshock", "oned", "ppmg", "pot", "ausm", "ring")
 ISO_CASES = ["iso2d_hll", "iso2d_hllc", "iso2d_flat_hllc", "iso3d_tvdlf", "iso_sph2d_flat_hll"]
 # CYLINDRICAL / POLAR geometry and BODY_FORCE POTENTIAL on curvilinear grids: on the CUDA path as well
 CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2d_hllc", "pol3d_hll", "pot_sph2d_hllc",
@@ -18,7 +18,9 @@ CURV_GPU_CASES = ["cyl2d_axis_hllc", "cyl2d_flat_tvdlf", "cyl2d_grav_hll", "pol2
                   "oned_iso2d_hll", "oned_sph2d_hllc", "oned_sph2d_char_roe",
                   # RECONSTRUCTION PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c
                   "ppmg_cyl2d_flat_stretched", "ppmg_cyl2d_uniform", "ppmg_iso2d_char", "ppmg_kh3d_stretched", "ppmg_pol2d",
-                  "ppmg_sph2d_char_flat", "ppmg_sph2d_stretched", "ppmg_sph2d_uniform", "ppmg_sph3d"]
+                  "ppmg_sph2d_char_flat", "ppmg_sph2d_stretched", "ppmg_sph2d_uniform", "ppmg_sph3d",
+                  # RING_AVERAGE (Src/ring_average.c) with POLARAXIS boundaries
+                  "ring_pol2d_mp5", "ring_pol2d_vl", "ring_pol3d_mp5", "ring_sph3d_mp5"]
 CURV_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if p.stem.startswith(_CURV_PREFIXES))
 GOLDEN_CASES = sorted(p.stem for p in GOLDEN.glob("*.npz")
                       if not p.stem.startswith(_GEN_PREFIXES + _CURV_PREFIXES))
@@ -70,12 +72,15 @@ def gen_kwargs_from_golden(g):
     extra = {}
     if "eos" in g and str(g["eos"]) == "ISOTHERMAL":     # only the iso* fixtures carry these keys
         extra = dict(eos="ISOTHERMAL", iso_sound_speed=float(g["iso_cs"]))
+    if "ring_average" in g:     # RING_AVERAGE fixtures
+        extra.update(ring_average=int(g["ring_average"]), ring_average_rec=int(g["ring_rec"]))
     return dict(**extra, dimensions=g["dims"], grid=grid, geometry=str(g["geometry"]), gamma=g["gamma"],
                 reconstruction=g["recon"], time_stepping=g["rk"], solver=g["solver"], bcs=g["bcs"],
                 ntracer=g["ntracer"], limiter=g["limiter"], body_force=BODY_FORCE[g["body_force"]],
                 char_limiting=bool(int(g["char_limiting"])), shock_flattening={0: False, 1: True, 2: "ONED"}[flat],
                 entropy_switch={0: False, 1: "SELECTIVE", 2: "ALWAYS"}[_entr_code(g)],
-                nghost=max({0: 2, 1: 3, 2: 4}[flat], 3 if g["recon"] == "PARABOLIC" else 2))     # GetNghost(), Src/get_nghost.c:42-57
+                nghost=max({0: 2, 1: 3, 2: 4}[flat], 3 if g["recon"] == "PARABOLIC" else 2,
+                           3 if ("ring_rec" in g and int(g["ring_rec"]) > 2) else 2))     # GetNghost(), Src/get_nghost.c:37-57
 
 
 def set_point_mass_gravity(obj, gm):

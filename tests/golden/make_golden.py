@@ -143,7 +143,8 @@ def make_case3(out, name, c):
                         char_limiting=int(c.get("char_limiting", False)),
                         shock_flattening=2 if c.get("shock_flattening") == "ONED" else int(bool(c.get("shock_flattening", False))),
                         entropy_switch={False: 0, True: 2, "SELECTIVE": 1, "ALWAYS": 2}[c.get("entropy_switch", False)],
-                        entr_codes=1, **(dict(eos="ISOTHERMAL", iso_cs=c["params"]["CS_ISO"]) if iso else {}))
+                        entr_codes=1, **(dict(eos="ISOTHERMAL", iso_cs=c["params"]["CS_ISO"]) if iso else {}),
+                        **(dict(ring_average=c["ring_average"], ring_rec=c.get("ring_rec", 5)) if c.get("ring_average") else {}))
     print(name, data.shape, "%.1f kB" % ((out / (name + ".npz")).stat().st_size / 1e3))
 
 
@@ -291,6 +292,26 @@ CASES4 = {
 }
 
 
+# RING_AVERAGE (Src/ring_average.c) with POLARAXIS boundaries; "ring" prefix
+CASES7 = {
+    "ring_pol2d_mp5": dict(cfg="pol2d_ring", dims=2, geometry="POLAR", body_force="none", ring_average=8,
+                           grid=[(0.0, 24, 2.4), (0.0, 32, TWO_PI), (0.0, 1, 1.0)], solver="hllc",
+                           bcs=("polaraxis", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                           params=CYL_PAR, maxsteps=8),
+    "ring_pol2d_vl": dict(cfg="pol2d_ring_vl", dims=2, geometry="POLAR", body_force="none", ring_average=8, ring_rec=2,
+                          grid=[(0.0, 24, 2.4, "r", 1.03), (0.0, 32, TWO_PI), (0.0, 1, 1.0)], solver="hll",
+                          bcs=("polaraxis", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                          params=CYL_PAR, maxsteps=8),
+    "ring_pol3d_mp5": dict(cfg="pol3d_ring", dims=3, geometry="POLAR", body_force="none", ring_average=4,
+                           grid=[(0.0, 14, 2.1), (0.0, 16, TWO_PI), (0.0, 8, 1.2)], solver="hll",
+                           bcs=("polaraxis", "outflow", "periodic", "periodic", "reflective", "outflow"),
+                           params=CYL_PAR, maxsteps=6),
+    "ring_sph3d_mp5": dict(cfg="sph3d_ring", dims=3, ring_average=4,
+                           grid=[(1.0, 14, 3.0, "r", 1.04), (0.0, 12, HALF_PI), (0.0, 16, TWO_PI)], solver="hllc",
+                           bcs=("outflow", "outflow", "polaraxis", "eqtsymmetric", "periodic", "periodic"), maxsteps=6),
+}
+
+
 def make_case4(out, name, c):
     build_ref.build(c["cfg"])
     grid = c["grid"]
@@ -360,6 +381,9 @@ def main():
         if not only or name in only:
             make_case3(out, name, c)
     for name, c in CASES6.items():
+        if not only or name in only:
+            make_case3(out, name, c)
+    for name, c in CASES7.items():
         if not only or name in only:
             make_case3(out, name, c)
     for name, c in CASES4.items():
