@@ -329,6 +329,14 @@ GENERAL_OPTION_CASES = {
     "sph2d_char_oned": dict(nvar=6, grid=[(1.0, 40, 4.0, "r", 1.03), (0.2, 28, HALF_PI, "r", 0.97), (0.0, 1, 1.0)],
                             solver="two_shock", bcs=("outflow", "outflow", "axisymmetric", "reflective", "periodic", "periodic"),
                             params=SPH_PAR, first_dt=1e-5, maxsteps=10),
+    # RING_AVERAGE 8 (MP5 on the reduced grid) in POLAR geometry from r = 0 with the polaraxis boundary
+    "pol2d_ring": dict(nvar=6, grid=[(0.0, 24, 2.4), (0.0, 32, TWO_PI), (0.0, 1, 1.0)], solver="hllc",
+                       bcs=("polaraxis", "outflow", "periodic", "periodic", "periodic", "periodic"),
+                       params=CYL_PAR, first_dt=1e-5, maxsteps=10),
+    # RING_AVERAGE 4 in SPHERICAL geometry from theta = 0 (non-axisymmetric state)
+    "sph3d_ring": dict(nvar=6, grid=[(1.0, 14, 3.0, "r", 1.04), (0.0, 12, HALF_PI), (0.0, 16, TWO_PI)], solver="hll",
+                       bcs=("outflow", "outflow", "polaraxis", "eqtsymmetric", "periodic", "periodic"),
+                       params=SPH_PAR, first_dt=1e-5, maxsteps=8),
 }
 
 

@@ -45,7 +45,9 @@ def test_gen_oracle_cylindrical_polar_isothermal_match_reference_dumps(name):
     PARABOLIC + RK3 with the general-grid weights of States/ppm_coeffs.c (PPM_FindWeights through the LU
     solve on stretched grids, the closed forms on uniform cylindrical / spherical radial grids, the 5-point
     Gauss moments of sin(theta) for the meridional direction, PPM_Q6_Coeffs), the pot_* ones BODY_FORCE
-    POTENTIAL (and VECTOR + POTENTIAL) on spherical and polar grids.
+    POTENTIAL (and VECTOR + POTENTIAL) on spherical and polar grids, the ring_* ones RING_AVERAGE (Src/ring_average.c:
+    RingAverageCons around every stage, RingAverageReconstruct with MP5 / van Leer on the reduced grid, the chunked C_dt)
+    with the polaraxis boundary (boundary.c:770-840) in POLAR 2-D / 3-D and SPHERICAL 3-D.
     These fixtures pin the oracle; the CUDA path runs every one of them too (tests/test_gpu_gen.py: ISO_CASES,
     CURV_GPU_CASES)."""
     g = load_golden(name)

@@ -133,7 +133,8 @@ def test_cylindrical_polar_potential_per_step_vs_reference_dumps(Hydro, name):
     (HD/roe.c, both equations of state) and TwoShock_Solver (HD/two_shock.c); oned_*: SHOCK_FLATTENING ONED
     (States/flatten.c, 4 ghost zones); ppmg_*: RECONSTRUCTION PARABOLIC + RK3 with the weights of PPM_CoefficientsSet
     (States/ppm_coeffs.c: LU solve on stretched grids, closed forms on uniform radial grids, Gauss moments of
-    sin(theta)), with and without CHAR_LIMITING / MULTID flattening (States/ppm_states.c)."""
+    sin(theta)), with and without CHAR_LIMITING / MULTID flattening (States/ppm_states.c); ring_*: RING_AVERAGE
+    (Src/ring_average.c) with the polaraxis boundary in POLAR and SPHERICAL geometry."""
     g = load_golden(name)
     kw = gen_kwargs_from_golden(g)
     h = Hydro(**hydro_kwargs_from_gen(kw))
