@@ -129,7 +129,8 @@ extern "C" int pb200_multi_create(const pb200_config *gcfg, int ngpus, const int
   *out = nullptr;
   if (gcfg->dimensions < 2 && ngpus > 1)
     return pb200_fail(PB200_ENOTSUP, "1-D grids are not decomposed (replicas only)");
-  const bool gen = gcfg->geometry != PB200_CARTESIAN || gcfg->char_limiting || gcfg->shock_flattening || gcfg->entropy_switch || gcfg->eos != PB200_EOS_IDEAL;
+  const bool gen = gcfg->geometry != PB200_CARTESIAN || gcfg->char_limiting || gcfg->shock_flattening || gcfg->entropy_switch ||
+                   gcfg->eos != PB200_EOS_IDEAL || gcfg->solver >= PB200_ROE || gcfg->ring_average > 1;    // as pb200_create routes
   if (gen && ngpus > 1) return pb200_fail(PB200_ENOTSUP, "the general-grid path runs on one GPU (replicas only)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
