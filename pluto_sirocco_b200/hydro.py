@@ -45,6 +45,10 @@ class Definitions:
     EOS: str = "IDEAL"
     ENTROPY_SWITCH: str = "NO"
     LIMITER: str = "DEFAULT"
+    CHAR_LIMITING: str = "NO"
+    SHOCK_FLATTENING: str = "NO"
+    RING_AVERAGE: str = "NO"          # chunk size at the axis (an integer > 1) or NO, Src/pluto.h:479
+    RING_AVERAGE_REC: str = ""        # 1 / 2 / 5; empty: the reference's default (5 when RING_AVERAGE is on)
     user_params: list = field(default_factory=list)   # labels, in index order
     extra: dict = field(default_factory=dict)
 
@@ -73,19 +77,45 @@ class Definitions:
                 d.extra[k] = v
         return d
 
+    def ring_average(self):
+        """(RING_AVERAGE, RING_AVERAGE_REC) as integers; (0, 1) when off (Src/pluto.h:479-489)."""
+        ra = 0 if self.RING_AVERAGE in ("NO", "0", "1") else int(self.RING_AVERAGE)
+        rec = int(self.RING_AVERAGE_REC) if self.RING_AVERAGE_REC else (5 if ra > 1 else 1)
+        return ra, rec
+
     def nghost(self) -> int:
-        """GetNghost(), Src/get_nghost.c:19-42."""
-        return 3 if self.RECONSTRUCTION == "PARABOLIC" else 2
+        """GetNghost(), Src/get_nghost.c:19-60."""
+        n = 2
+        if self.RECONSTRUCTION == "PARABOLIC" or self.ring_average()[1] > 2:
+            n = 3
+        if self.SHOCK_FLATTENING == "ONED":
+            n = max(4, n)
+        elif self.SHOCK_FLATTENING == "MULTID":
+            n = max(3, n)
+        return n
+
+    def body_force_bits(self) -> int:
+        """BODY_FORCE as the bit mask of Src/pluto.h:76-77 (VECTOR 1, POTENTIAL 2)."""
+        b = self.BODY_FORCE.upper()
+        return (1 if "VECTOR" in b else 0) | (2 if "POTENTIAL" in b else 0)
 
     def check_supported(self):
         if self.PHYSICS != "HD":
             raise NotImplementedError("PHYSICS %s: only HD is on the hot path" % self.PHYSICS)
-        if self.EOS != "IDEAL":
+        if self.EOS not in ("IDEAL", "ISOTHERMAL"):
             raise NotImplementedError("EOS %s" % self.EOS)
+        if self.GEOMETRY not in ("CARTESIAN", "CYLINDRICAL", "POLAR", "SPHERICAL"):
+            raise NotImplementedError("GEOMETRY %s" % self.GEOMETRY)
         if self.RECONSTRUCTION not in _RECON:
             raise NotImplementedError("RECONSTRUCTION %s" % self.RECONSTRUCTION)
         if self.TIME_STEPPING not in _TSTEP:
             raise NotImplementedError("TIME_STEPPING %s" % self.TIME_STEPPING)
+        if self.SHOCK_FLATTENING not in ("NO", "MULTID", "ONED"):
+            raise NotImplementedError("SHOCK_FLATTENING %s" % self.SHOCK_FLATTENING)
+        if self.ENTROPY_SWITCH not in ("NO", "SELECTIVE", "ALWAYS"):
+            raise NotImplementedError("ENTROPY_SWITCH %s" % self.ENTROPY_SWITCH)
+        if self.COOLING != "NO":
+            raise NotImplementedError("COOLING %s: the source step goes through the drop-in shim (csrc/pluto_shim.c)" % self.COOLING)
 
 
 @dataclass
@@ -102,6 +132,7 @@ class Runtime:
     left_bound: list = field(default_factory=lambda: ["outflow"] * 3)
     right_bound: list = field(default_factory=lambda: ["outflow"] * 3)
     params: dict = field(default_factory=dict)
+    grid: list = field(default_factory=lambda: [None, None, None])   # make_grid() specs of the [Grid] lines
 
     @classmethod
     def parse(cls, path) -> "Runtime":
@@ -120,11 +151,16 @@ class Runtime:
             if section == "Grid" and re.match(r"X[123]-grid", key):
                 d = int(key[1]) - 1
                 npatch = int(tok[1])
-                if npatch != 1 or tok[4] != "u":
-                    raise NotImplementedError("only single uniform patches ('u') are parsed here")
+                if npatch != 1 or tok[4] not in ("u", "uniform", "r"):
+                    raise NotImplementedError("only single 'u' (uniform) or 'r' (ratio, this fork) patches are parsed here")
                 rt.xbeg[d] = float(tok[2])
                 rt.npoint[d] = int(tok[3])
-                rt.xend[d] = float(tok[5])
+                if tok[4] == "r":       # X1-grid 1 xL n r xR ratio (set_grid.c, the fork's ratio grid)
+                    rt.xend[d] = float(tok[5])
+                    rt.grid[d] = (rt.xbeg[d], rt.npoint[d], rt.xend[d], "r", float(tok[6]))
+                else:
+                    rt.xend[d] = float(tok[5])
+                    rt.grid[d] = (rt.xbeg[d], rt.npoint[d], rt.xend[d])
             elif section == "Time":
                 if key == "CFL": rt.cfl = float(tok[1])
                 elif key == "CFL_max_var": rt.cfl_max_var = float(tok[1])
@@ -358,18 +394,37 @@ class Hydro:
                 L.check(lib.pb200_set_grid(h, d, xl.ctypes.data_as(C.c_void_p),
                                            xr.ctypes.data_as(C.c_void_p), dxa.ctypes.data_as(C.c_void_p)))
 
-    @classmethod
-    def from_files(cls, definitions: Definitions, runtime: Runtime, gamma=5. / 3., device=0):
+    @staticmethod
+    def kwargs_from_files(definitions: Definitions, runtime: Runtime, gamma=5. / 3., iso_sound_speed=0.0, device=0):
+        """Constructor keywords for the problem a definitions.h + pluto.ini pair describes: the compile-time options
+        the shim reads as macros (csrc/pluto_shim.c: shim_fill_config) and the run-time ones it reads from Runtime /
+        Grid.  g_gamma and g_isoSoundSpeed are set by the user's Init() in the reference: pass them in."""
         definitions.check_supported()
         nd = definitions.DIMENSIONS
         bcs = []
         for d in range(3):
             bcs += [runtime.left_bound[d], runtime.right_bound[d]]
-        return cls(dimensions=nd, nx=runtime.npoint, xbeg=runtime.xbeg, xend=runtime.xend,
-                   gamma=gamma, reconstruction=definitions.RECONSTRUCTION,
-                   time_stepping=definitions.TIME_STEPPING, solver=runtime.solver,
-                   limiter=definitions.LIMITER, bcs=bcs, ntracer=definitions.NTRACER,
-                   device=device)
+        ng = definitions.nghost()
+        ra, rec = definitions.ring_average()
+        kw = dict(dimensions=nd, nx=tuple(int(runtime.npoint[d]) if d < nd else 1 for d in range(3)),
+                  xbeg=tuple(runtime.xbeg), xend=tuple(runtime.xend), gamma=gamma,
+                  reconstruction=definitions.RECONSTRUCTION, time_stepping=definitions.TIME_STEPPING,
+                  solver=runtime.solver, limiter=definitions.LIMITER, bcs=tuple(bcs), ntracer=definitions.NTRACER,
+                  nghost=ng, device=device, geometry=definitions.GEOMETRY, body_force=definitions.body_force_bits(),
+                  char_limiting=definitions.CHAR_LIMITING == "YES",
+                  shock_flattening={"NO": False, "MULTID": True, "ONED": "ONED"}[definitions.SHOCK_FLATTENING],
+                  entropy_switch={"NO": False, "SELECTIVE": "SELECTIVE", "ALWAYS": "ALWAYS"}[definitions.ENTROPY_SWITCH],
+                  eos=definitions.EOS, iso_sound_speed=iso_sound_speed, ring_average=ra, ring_average_rec=rec)
+        specs = [runtime.grid[d] if runtime.grid[d] is not None else (runtime.xbeg[d], runtime.npoint[d], runtime.xend[d])
+                 for d in range(3)]
+        kw["grid_arrays"] = [make_grid(specs[d], ng if d < nd else 0) if d < nd else make_grid((specs[d][0], 1, specs[d][2]), 0)
+                             for d in range(3)]
+        kw["grid_uniform"] = tuple(len(specs[d]) <= 3 for d in range(3))      # grid->uniform[d], set_grid.c:67-72
+        return kw
+
+    @classmethod
+    def from_files(cls, definitions: Definitions, runtime: Runtime, gamma=5. / 3., iso_sound_speed=0.0, device=0):
+        return cls(**cls.kwargs_from_files(definitions, runtime, gamma=gamma, iso_sound_speed=iso_sound_speed, device=device))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self):

@@ -425,3 +425,33 @@ def test_ldw_cooling_main_loop_reproduces_reference_dt_sequence(Hydro):
     relp = np.abs(got[4] - ref[4]) / ref[4]
     assert relp.max() <= 5e-4 and np.abs(got[0] - ref[0]).max() <= 1e-6 * np.abs(ref[0]).max()
     h.close()
+
+
+@pytest.mark.parametrize("name,ref_cfg", [("ring_pol2d_vl", "pol2d_ring_vl"), ("oned_sph2d_char_roe", "sph2d_char_oned")])
+def test_hydro_from_definitions_and_pluto_ini_reproduces_the_reference_dumps(Hydro, tmp_path, name, ref_cfg):
+    """The unchanged user surface end to end in Python: Definitions.parse(definitions.h) + Runtime.parse(pluto.ini) ->
+    Hydro.from_files() -> the per-step dumps of the reference executable that was compiled from that definitions.h."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import build_ref
+    import pluto_grid
+    import refrun
+    from pluto_sirocco_b200.hydro import Definitions, Runtime
+    g = load_golden(name)
+    cfg = build_ref.CONFIGS[ref_cfg]
+    d = Definitions.parse(build_ref.patch_definitions((build_ref.HERE / "problems" / cfg["local"] / "definitions.h").read_text(),
+                                                      cfg["overrides"]))
+    grid = [(float(r[0]), int(r[1]), float(r[2]), "r", float(r[4])) if r[3] == 1.0 else (float(r[0]), int(r[1]), float(r[2]))
+            for r in g["gridspec"]]
+    refrun.write_ini(tmp_path / "pluto.ini", grid=[pluto_grid.ini_string(s) for s in grid], cfl=float(g["cfl"]),
+                     tstop=float(g["tstop"]), first_dt=float(g["first_dt"]), solver=str(g["solver"]),
+                     bcs=tuple(str(b) for b in g["bcs"]))
+    h = Hydro.from_files(d, Runtime.parse(tmp_path / "pluto.ini"), gamma=float(g["gamma"]))
+    set_point_mass_gravity(h, float(g["gm"]))
+    data, steps = g["data"], g["steps"]
+    for n in range(3):
+        h.set_interior(data[n])
+        info = h.advance_step(steps[n, 2])
+        assert rel_err(h.get_interior(), data[n + 1]) <= TOL_STEP, (name, n)
+    h.close()

@@ -113,3 +113,54 @@ def test_make_grid_matches_the_grid_restated_for_the_oracle_and_grid_out(tmp_pat
         ref1 = np.array([[float(r[1]), float(r[2])] for r in rows[1:1 + n1]])
         xl, xr, _ = make_grid(specs[2], 0)
         assert np.allclose(ref1[:, 0], xl, rtol=1e-11, atol=1e-12) and np.allclose(ref1[:, 1], xr, rtol=1e-11, atol=1e-12)
+
+
+import numpy as np
+import pytest
+
+# fixture -> reference build configuration of oracle/build_ref.py whose definitions.h it was generated with
+FILES_CASES = {"sph2d_flat_hllc": "sph2d_flat", "pol3d_hll": "pol3d", "iso2d_flat_hllc": "iso2d_flat", "oned_sph2d_char_roe": "sph2d_char_oned",
+               "ppmg_kh3d_stretched": "kh3d_ppm", "ring_pol2d_vl": "pol2d_ring_vl", "ring_sph3d_mp5": "sph3d_ring",
+               "pot_sph3d_both_hll": "sph3d_pot", "sph2d_sel_hllc": "sph2d_sel"}
+
+
+@pytest.mark.parametrize("name", list(FILES_CASES))
+def test_kwargs_from_definitions_and_pluto_ini(name, tmp_path):
+    """Hydro.kwargs_from_files(): the definitions.h the reference executable of a fixture was compiled with and the
+    pluto.ini it ran on give the same library configuration (options, ghost zones, grid arrays, grid->uniform) as the
+    fixture's own record - the host-side mirror of what csrc/pluto_shim.c reads from the macros, Runtime and Grid."""
+    import build_ref
+    import pluto_grid
+    import refrun
+    from common import gen_kwargs_from_golden, hydro_kwargs_from_gen, load_golden
+    from pluto_sirocco_b200.hydro import Hydro
+    g = load_golden(name)
+    cfg = build_ref.CONFIGS[FILES_CASES[name]]
+    defs_text = build_ref.patch_definitions((build_ref.HERE / "problems" / cfg["local"] / "definitions.h").read_text(),
+                                            cfg["overrides"])
+    d = Definitions.parse(defs_text)
+    want = hydro_kwargs_from_gen(gen_kwargs_from_golden(g))
+    grid = []
+    for row in g["gridspec"]:
+        grid.append((float(row[0]), int(row[1]), float(row[2]), "r", float(row[4])) if row[3] == 1.0
+                    else (float(row[0]), int(row[1]), float(row[2])))
+    refrun.write_ini(tmp_path / "pluto.ini", grid=[pluto_grid.ini_string(s) for s in grid], cfl=float(g["cfl"]),
+                     tstop=float(g["tstop"]), first_dt=float(g["first_dt"]), solver=str(g["solver"]), bcs=tuple(str(b) for b in g["bcs"]))
+    rt = Runtime.parse(tmp_path / "pluto.ini")
+    got = Hydro.kwargs_from_files(d, rt, gamma=float(g["gamma"]), iso_sound_speed=float(g["iso_cs"]) if "iso_cs" in g else 0.0)
+    nd = int(g["dims"])
+    assert got["dimensions"] == nd and got["nx"][:nd] == tuple(want["nx"])[:nd] and got["nghost"] == want["nghost"]
+    for key in ("geometry", "reconstruction", "time_stepping", "solver", "limiter", "ntracer", "body_force"):
+        assert got[key] == want[key], (key, got[key], want[key])
+    assert bool(got["char_limiting"]) == bool(want["char_limiting"])
+    assert got["shock_flattening"] == want["shock_flattening"]
+    assert (got["entropy_switch"] or False) == (want["entropy_switch"] or False)
+    assert got["eos"] == want.get("eos", "IDEAL")
+    assert got["ring_average"] == want.get("ring_average", 0)
+    if got["ring_average"]:
+        assert got["ring_average_rec"] == want["ring_average_rec"]
+    assert tuple(got["bcs"])[:2 * nd] == tuple(str(b) for b in g["bcs"])[:2 * nd]
+    for dd in range(nd):
+        for a, b in zip(got["grid_arrays"][dd], want["grid_arrays"][dd]):
+            assert np.array_equal(a, b), (name, dd)
+        assert got["grid_uniform"][dd] == want["grid_uniform"][dd]
