@@ -18,7 +18,19 @@
 // The sweep direction is a RUN-TIME argument (only global-memory indices depend on it); the
 // number of variables is a template parameter so that per-zone vectors live in registers.
 #pragma once
+#include <type_traits>
+
 #include "pb200_kernels.cuh"
+
+// gen_vgrad: active bins per loop iteration and the resident 64-thread blocks per SM its register budget is cut for.
+// Measured on C4, one box, ms per step (profiles/r02_v4_gen_tiles.txt): 1 bin 0.820, 2 bins / 128 registers 0.801,
+// 3 bins / 128 registers 0.806, 3 bins / 188 registers (uncapped: 5 blocks per SM) 0.928; loop before: 0.880
+#ifndef PB_VGRAD_NB
+#define PB_VGRAD_NB 2
+#endif
+#ifndef PB_VGRAD_MINB
+#define PB_VGRAD_MINB 8
+#endif
 
 namespace pb {
 
@@ -1056,8 +1068,8 @@ PB_D double gen_ldw_M(const LdwDev &w, const LdwZone &z, double D, long o, long 
 // tables (3 x 155 MB per sweep on the 1024 x 512 grid, more than L2 holds); here the 36-bin tables
 // are read ONCE per stage and the sweeps pick up one number per zone.  It runs after States() of
 // the r sweep because that sweep's force uses (vp + vm)/2 as its centre state.
-template <int NV>
-static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenBox b, int fused) {
+template <int NV, int NBINS = PB_VGRAD_NB, int MINB = PB_VGRAD_MINB>
+static __global__ void __launch_bounds__(64, MINB) gen_vgrad(GenDev g, GenArgs a, GenBox b, int fused) {
   int i, j, k;
   if (!gen_zone(b.lo, b.hi, i, j, k)) return;
   const Dev &d = g.d;
@@ -1109,67 +1121,100 @@ static __global__ void __launch_bounds__(64) gen_vgrad(GenDev g, GenArgs a, GenB
   const double inv_maxds = 1.0 / maxds;
   const double vUV[2][4] = {{v11[0] * w.UV, v12[0] * w.UV, v21[0] * w.UV, v22[0] * w.UV},
                             {v11[1] * w.UV, v12[1] * w.UV, v21[1] * w.UV, v22[1] * w.UV}};
-  auto bin = [&](int ia, double fr, double ft) {
-    double D = 0.0;
-    if ((mk >> ia) & 1ull) {   // mod_flux != 0
-      const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
-      const double dx1 = maxds * sa, dx2 = maxds * ca;
-      const double X = x + dx1, Z = z + dx2;
-      // r_off = sqrt(X^2 + Z^2); sin / cos of t_off = atan(X / Z) (principal branch: cos > 0) are X / r, Z / r
-      const double s2 = X * X + Z * Z;
-      const double rs = rsqrt_fast(s2);
-      const double r_off = s2 * rs;
-      const double co = fabs(Z) * rs, so = (Z < 0.0 ? -X : X) * rs;
-      // t_off = atan(X / Z) = theta_j + atan(y), y = tan(t_off - theta_j) = (z dx1 - x dx2) / (z Z + x X): the offset
-      // point is at most half a zone away, so |y| << 1 and the odd series converges in a few terms (|y| < 0.06:
-      // next term y^14/15 < 6e-19); anything else takes atan() itself
-      double t_off;
-      const double yy = (z * dx1 - x * dx2) * rcp_fast(z * Z + x * X);
-      if (Z > 0.0 && fabs(yy) < 0.06) {
-        const double y2 = yy * yy;
-        const double p = 1.0 + y2 * (-1.0 / 3.0 + y2 * (1.0 / 5.0 + y2 * (-1.0 / 7.0 + y2 * (1.0 / 9.0 + y2 * (-1.0 / 11.0 + y2 * (1.0 / 13.0))))));
-        t_off = x2j + yy * p;
-      } else t_off = atan(X / Z);
-      // bilinear() of the two velocity components at (r_off, t_off), line_connect.c:746-767
-      const double f1 = (r_off - x11[0]) * inv_b0, f2 = (t_off - x11[1]) * inv_b1;
-      const double a0 = (1.0 - f1) * vUV[0][0] + f1 * vUV[0][2], b0 = (1.0 - f1) * vUV[0][1] + f1 * vUV[0][3];
-      const double a1 = (1.0 - f1) * vUV[1][0] + f1 * vUV[1][2], b1 = (1.0 - f1) * vUV[1][1] + f1 * vUV[1][3];
-      const double q0 = (1.0 - f2) * a0 + f2 * b0, q1 = (1.0 - f2) * a1 + f2 * b1;     // ans2[] * UNIT_VELOCITY
-      const double vx2 = (q0 * so + q1 * co);
-      const double vz2 = (q0 * co - q1 * so);
-      const double v1 = sa * vx1 + ca * vz1;
-      const double v2 = sa * vx2 + ca * vz2;
-      // ds = sqrt(dx1^2 + dx2^2) = maxds sqrt(sa^2 + ca^2): the bin's constant comes from the host table
-      const double out = fabs(v2 - v1) * (inv_maxds * __ldg(w.inv_ca + ia));
-      // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per bin and SWEEP (the sweeps pass
-      // different centre states); the bin-dependent factor dvds^(-alpha) is taken once and serves
-      // both, so that a zone costs one pow() per sweep instead of 36.
-      // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
-      if (out > 0.0) {
-        if (w.mpoints > 0) D = out;              // fit mode keeps dvds itself
-        else if (w.alpha_m06 && out >= 1e-12 && out <= 1e12) D = pow_three_fifths(out);
-        else D = exp(-w.alpharad * log(out));
+  // dvds^(-alpha) (power law) or dvds itself (fit mode) of ONE ACTIVE bin, 0 when the gradient vanishes.
+  // MODE 0: fit mode, 1: ALPHARAD = -0.6 (pow_three_fifths), 2: any exponent (exp / log).
+  // FAST: straight-line code (no branch, so that the bins of a group interleave): the small-angle series for
+  // t_off - theta_j and the 3/5 power; `slow` reports the (rare) bins that need atan() or exp / log, which are then
+  // re-evaluated with FAST = false - same operations as before for every bin, chosen per bin instead of per branch.
+  auto binD = [&](auto mode, auto fast, int ia, bool &slow) -> double {
+    constexpr int MODE = decltype(mode)::value;
+    constexpr bool FAST = decltype(fast)::value;
+    const double sa = __ldg(w.sin_a + ia), ca = __ldg(w.cos_a + ia);
+    const double dx1 = maxds * sa, dx2 = maxds * ca;
+    const double X = x + dx1, Z = z + dx2;
+    // r_off = sqrt(X^2 + Z^2); sin / cos of t_off = atan(X / Z) (principal branch: cos > 0) are X / r, Z / r
+    const double s2 = X * X + Z * Z;
+    const double rs = rsqrt_fast(s2);
+    const double r_off = s2 * rs;
+    const double co = fabs(Z) * rs, so = (Z < 0.0 ? -X : X) * rs;
+    // t_off = atan(X / Z) = theta_j + atan(y), y = tan(t_off - theta_j) = (z dx1 - x dx2) / (z Z + x X): the offset
+    // point is at most half a zone away, so |y| << 1 and the odd series converges in a few terms (|y| < 0.06:
+    // next term y^14/15 < 6e-19); anything else takes atan() itself
+    const double yy = (z * dx1 - x * dx2) * rcp_fast(z * Z + x * X);
+    const bool small = Z > 0.0 && fabs(yy) < 0.06;
+    double t_off;
+    if (FAST || small) {
+      const double y2 = yy * yy;
+      const double p = 1.0 + y2 * (-1.0 / 3.0 + y2 * (1.0 / 5.0 + y2 * (-1.0 / 7.0 + y2 * (1.0 / 9.0 + y2 * (-1.0 / 11.0 + y2 * (1.0 / 13.0))))));
+      t_off = x2j + yy * p;
+    } else t_off = atan(X / Z);
+    // bilinear() of the two velocity components at (r_off, t_off), line_connect.c:746-767
+    const double f1 = (r_off - x11[0]) * inv_b0, f2 = (t_off - x11[1]) * inv_b1;
+    const double a0 = (1.0 - f1) * vUV[0][0] + f1 * vUV[0][2], b0 = (1.0 - f1) * vUV[0][1] + f1 * vUV[0][3];
+    const double a1 = (1.0 - f1) * vUV[1][0] + f1 * vUV[1][2], b1 = (1.0 - f1) * vUV[1][1] + f1 * vUV[1][3];
+    const double q0 = (1.0 - f2) * a0 + f2 * b0, q1 = (1.0 - f2) * a1 + f2 * b1;     // ans2[] * UNIT_VELOCITY
+    const double vx2 = (q0 * so + q1 * co);
+    const double vz2 = (q0 * co - q1 * so);
+    const double v1 = sa * vx1 + ca * vz1;
+    const double v2 = sa * vx2 + ca * vz2;
+    // ds = sqrt(dx1^2 + dx2^2) = maxds sqrt(sa^2 + ca^2): the bin's constant comes from the host table
+    const double out = fabs(v2 - v1) * (inv_maxds * __ldg(w.inv_ca + ia));
+    // LineForce() needs M = k (sigma_e rho v_th / dvds)^alpha per bin and SWEEP (the sweeps pass
+    // different centre states); the bin-dependent factor dvds^(-alpha) is taken once and serves
+    // both, so that a zone costs one pow() per sweep instead of 36.
+    // exp(-alpha log x): |log x| is O(10) here, within a few ulp of pow(x, -alpha) at half its cost
+    const bool in_range = out >= 1e-12 && out <= 1e12;
+    double D;
+    if (MODE == 0) D = out;                                   // fit mode keeps dvds itself
+    else if (MODE == 1 && (FAST || in_range)) D = pow_three_fifths(out);
+    else if (FAST) D = 0.0;                                   // MODE 2: exp / log in the second pass
+    else D = out > 0.0 ? exp(-w.alpharad * log(out)) : 0.0;
+    slow = FAST && out > 0.0 && (!small || (MODE == 1 && !in_range) || MODE == 2);
+    return out > 0.0 ? D : 0.0;
+  };
+  // Only the bins with flux (mask bits) are visited: a bin without flux adds (1 + M(0)) coef * 0 to both sums.  NB active
+  // bins per iteration: their (streaming) flux loads are issued together, the NB gradient evaluations are straight-line
+  // and independent - the kernel waits on load and FP64 latencies, not on a pipe - and the sums take the bins in order.
+  // The last group of a zone is padded with copies of its first bin (discarded).
+  auto sweep_bins = [&](auto mode) {
+    constexpr int NB = NBINS;
+    unsigned long long rem = w.nangles < 64 ? (mk & ((1ull << w.nangles) - 1ull)) : mk;
+    while (rem) {
+      int ib[NB];
+      bool on[NB], slow[NB];
+      double fa[NB], ta[NB], Dq[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        on[q] = rem != 0ull;
+        ib[q] = on[q] ? __ffsll((long long)rem) - 1 : ib[0];
+        rem &= rem - 1ull;                          // clears the lowest set bit; 0 stays 0
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        fa[q] = on[q] ? __ldg(w.flux_r + ib[q] * nz + o) : 0.0;
+        ta[q] = on[q] ? __ldg(w.flux_t + ib[q] * nz + o) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) Dq[q] = binD(mode, std::true_type{}, ib[q], slow[q]);
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        bool dummy;
+        if (slow[q] && on[q]) Dq[q] = binD(mode, std::false_type{}, ib[q], dummy);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        if (on[q]) {
+          // ((1 + M) sigma_e F / c) / UNIT_ACCELERATION with the two constant divisions folded into one
+          // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)
+          g_r += ((1.0 + gen_ldw_M(w, zr, Dq[q], o, nz)) * coef) * fa[q];
+          g_t += ((1.0 + gen_ldw_M(w, zt, Dq[q], o, nz)) * coef) * ta[q];
+        }
       }
     }
-    // ((1 + M) sigma_e F / c) / UNIT_ACCELERATION with the two constant divisions folded into one
-    // factor (<= 1 ulp per term; 144 FP64 divisions per zone and sweep otherwise)
-    g_r += ((1.0 + gen_ldw_M(w, zr, D, o, nz)) * coef) * fr;
-    g_t += ((1.0 + gen_ldw_M(w, zt, D, o, nz)) * coef) * ft;
   };
-  // NB bins per iteration: their (coalesced, streaming) flux loads are issued together and the NB independent
-  // dependency chains interleave - the kernel waits on load and FP64 latencies, not on a pipe
-  // (profiles/r02_v4_gen_tiles.txt: 1, 2, 3, 4 bins per iteration -> 0.998, 0.950, 0.937, 0.937 ms per C4 step).
-  // The sums still take the bins in order.
-  constexpr int NB = 3;
-  int ia = 0;
-  for (; ia + NB - 1 < w.nangles; ia += NB) {
-    double fa[NB], ta[NB];
-#pragma unroll
-    for (int q = 0; q < NB; q++) { fa[q] = __ldg(w.flux_r + (ia + q) * nz + o); ta[q] = __ldg(w.flux_t + (ia + q) * nz + o); }
-#pragma unroll
-    for (int q = 0; q < NB; q++) bin(ia + q, fa[q], ta[q]);
-  }
-  for (; ia < w.nangles; ia++) bin(ia, __ldg(w.flux_r + ia * nz + o), __ldg(w.flux_t + ia * nz + o));
+  if (w.mpoints > 0) sweep_bins(std::integral_constant<int, 0>{});
+  else if (w.alpha_m06) sweep_bins(std::integral_constant<int, 1>{});
+  else sweep_bins(std::integral_constant<int, 2>{});
   w.gline[o] = g_r;
   w.gline[nz + o] = g_t;
 }

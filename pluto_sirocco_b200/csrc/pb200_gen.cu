@@ -629,6 +629,11 @@ extern "C" int pb200_ppm_coefficients(int geometry, int dir, int ntot, const dou
   return PB200_OK;
 }
 
+template <int NV>
+static void launch_vgrad(const GenDev &G, const GenArgs &a, const GenBox &dom, int defer, unsigned nb, cudaStream_t st) {
+  gen_vgrad<NV><<<nb, 64, 0, st>>>(G, a, dom, defer);
+}
+
 // SplitSource() for COOLING BLONDIN (Src/split_source.c:53): BlondinCooling(d->Vc, d, dt, ...)
 template <int NV>
 static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb) {
@@ -685,7 +690,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     const int nx = D.end[0] - D.beg[0] + 1, ny = D.end[1] - D.beg[1] + 1, nzz = D.end[2] - D.beg[2] + 1;
     if (c->ldw_on && ((dir == 0 && !a.defer) || (dir == 1 && a.defer))) {
       // VGradCalc (update_stage.c:138-140) + the sums of LineForce(): after the r sweep, whose centre state it needs
-      gen_vgrad<NV><<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom, a.defer);
+      launch_vgrad<NV>(G, a, dom, a.defer, (unsigned)((zones_of(dom) + 63) / 64), st);
       c->launches++;
     }
     const int first = (stage == 1 && dir == 0) ? 1 : 0;
@@ -709,7 +714,7 @@ static void gen_stage_nv(pb200_ctx *c, int stage, double w0, double wc, int comb
     bf.lo[dir] = D.beg[dir] - 1; bf.hi[dir] = D.end[dir];         // Riemann(nbeg-1, nend)
     gen_states<NV><<<blocks(bs), T, 0, st>>>(G, a, bs);
     if (dir == 0 && c->ldw_on) {                // VGradCalc (update_stage.c:138-140) + the sums of LineForce()
-      gen_vgrad<NV><<<(unsigned)((zones_of(dom) + 63) / 64), 64, 0, st>>>(G, a, dom, 0);
+      launch_vgrad<NV>(G, a, dom, 0, (unsigned)((zones_of(dom) + 63) / 64), st);
       c->launches++;
     }
     gen_riemann<NV><<<blocks(bf), T, 0, st>>>(G, a, bf);
