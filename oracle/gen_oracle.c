@@ -14,10 +14,11 @@
  * PARABOLIC (order 4, CHAR_LIMITING NO/YES) with the general-grid weights of ppm_coeffs.c,
  * SHOCK_FLATTENING NO / MULTID / ONED, ENTROPY_SWITCH NO / SELECTIVE / ALWAYS, NTRACER >= 0,
  * BODY_FORCE VECTOR / POTENTIAL, TIME_STEPPING EULER/RK2/RK3, Solver tvdlf / hll / hllc / roe / two_shock / ausm+,
- * outflow / reflective / axisymmetric / eqtsymmetric / periodic boundaries plus the user-defined
- * boundaries of the line-driven-wind problems (cv_idl, cv_iso), LINE_DRIVEN_WIND (VGradCalc +
- * LineForce, power law or M(t) fit) and COOLING BLONDIN.
- * The CUDA path covers the subset DESIGN.md lists; the rest is pinned here ahead of it.
+ * outflow / reflective / axisymmetric / eqtsymmetric / periodic / polaraxis boundaries plus the
+ * user-defined boundaries of the line-driven-wind problems (cv_idl, cv_iso), RING_AVERAGE
+ * (ring_average.c, RING_AVERAGE_REC 1 / 2 / 5), LINE_DRIVEN_WIND (VGradCalc + LineForce, power law
+ * or M(t) fit) and COOLING BLONDIN.
+ * The CUDA path runs every one of these fixtures too (tests/test_gpu_gen.py).
  *
  * Plain C17, scalar, pencil by pencil like the reference so that the operation order is the
  * reference's; build with -ffp-contract=off.  Each function cites the reference file:line.
